@@ -1,0 +1,347 @@
+/*
+ * ref_harness.cpp -- the UNMODIFIED reference compiled as a checker.  TEST INFRASTRUCTURE ONLY.
+ *
+ * This file contains no reference code: it #includes the reference's own headers from the
+ * read-only checkout (the Makefile passes -I$(REF), default /root/reference, and compiles
+ * $(REF)/dsp_complex.cpp next to it) and wraps the three hot-path classes behind a small
+ * extern "C" surface so that tests and bench.py can drive them through ctypes:
+ *
+ *   dsptl::Mixer<cs16,cs16,int16_t,N>                         mixers.h:130-188
+ *   dsptl::FilterDnsamplingFir<cs16,cs16,cs32,int32_t,M>      dsptl_dnsampling_filters.h:43-220
+ *   (obsolete twin, no taps%M assert)                         dnsampling_filters.h:43-172
+ *   dsptl::FilterUpsamplingFir<cs16,cs16,cs32,int32_t,L>      upsampling_filters.h:35-323
+ *   FilterFir<cs16,cs16,cs32,int32_t>                         filters.h:42-169
+ *
+ * The two decimator headers share an include guard and a class name, so the obsolete one is
+ * included inside namespace ref_obsolete (its std/dsp_complex includes are already satisfied).
+ * Output goes to oracle/_ref/ (git-ignored, but it travels to the GPU box).
+ */
+#include <array>
+#include <cassert>
+#include <chrono>
+#include <cmath>
+#include <complex>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "dsp_complex.h"
+#include "constants.h"
+#include "generators.h"
+
+namespace ref_obsolete {
+#include "dnsampling_filters.h"
+}
+#undef _DNSAMPLING_FILTER_FIR_H
+#include "dsptl_dnsampling_filters.h"
+#include "mixers.h"
+#include "upsampling_filters.h"
+#include "filters.h"
+
+typedef std::complex<int16_t> cs16;
+typedef std::complex<int32_t> cs32;
+
+static_assert(sizeof(cs16) == 4, "interleaved I/Q layout");
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+struct MixerBase {
+    virtual ~MixerBase() {}
+    virtual void setFrequency(float) = 0;
+    virtual void reset(float) = 0;
+    virtual void adjustFrequency(float) = 0;
+    virtual void step(std::vector<cs16> &in, std::vector<cs16> &out) = 0;
+    virtual int phi() = 0;
+    virtual int freq() = 0;
+};
+template <unsigned N>
+struct MixerT : MixerBase, dsptl::Mixer<cs16, cs16, int16_t, N> {
+    typedef dsptl::Mixer<cs16, cs16, int16_t, N> B;
+    void setFrequency(float f) { B::setFrequency(f); }
+    void reset(float f) { B::reset(f); }
+    void adjustFrequency(float f) { B::adjustFrequency(f); }
+    void step(std::vector<cs16> &in, std::vector<cs16> &out) { B::step(in, out); }
+    int phi() { return B::phi; }     // protected members, visible to the derived wrapper
+    int freq() { return B::freq; }
+};
+
+struct DecBase {
+    virtual ~DecBase() {}
+    virtual void step(const std::vector<cs16> &in, std::vector<cs16> &out) = 0;
+    virtual void reset() = 0;
+    virtual void setLeftShiftBy2(int) = 0;
+};
+template <class F>
+struct DecT : DecBase {
+    F f;
+    explicit DecT(const std::vector<int32_t> &taps) : f(taps) {}
+    void step(const std::vector<cs16> &in, std::vector<cs16> &out) { f.step(in, out); }
+    void reset() { f.reset(); }
+    void setLeftShiftBy2(int s) { f.setLeftShiftBy2(s); }
+};
+
+struct UpBase {
+    virtual ~UpBase() {}
+    virtual void setCoefficients(const std::vector<int32_t> &) = 0;
+    virtual void step(const std::vector<cs16> &in, std::vector<cs16> &out, bool flush) = 0;
+    virtual void stepIt(const std::vector<cs16> &in, std::vector<cs16>::iterator out, bool flush) = 0;
+    virtual void reset() = 0;
+    virtual int getLength() = 0;
+    virtual int getImpLength() = 0;
+    virtual int getUpsamplingRatio() = 0;
+};
+template <unsigned L>
+struct UpT : UpBase {
+    dsptl::FilterUpsamplingFir<cs16, cs16, cs32, int32_t, L> f;
+    explicit UpT(const std::vector<int32_t> &taps) : f(taps) {}
+    void setCoefficients(const std::vector<int32_t> &t) { f.setCoefficients(t); }
+    void step(const std::vector<cs16> &in, std::vector<cs16> &out, bool flush) { f.step(in, out, flush); }
+    void stepIt(const std::vector<cs16> &in, std::vector<cs16>::iterator out, bool flush) { f.step(in, out, flush); }
+    void reset() { f.reset(); }
+    int getLength() { return f.getLength(); }
+    int getImpLength() { return f.getImpLength(); }
+    int getUpsamplingRatio() { return f.getUpsamplingRatio(); }
+};
+
+#define RATIOS(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(10) X(12) X(16) X(20) X(24) X(32) X(64)
+
+DecBase *make_dec(int variant, int M, const std::vector<int32_t> &taps)
+{
+    switch (M) {
+#define X(m)                                                                                     \
+    case m:                                                                                      \
+        if (variant == 0)                                                                        \
+            return new DecT<ref_obsolete::dsptl::FilterDnsamplingFir<cs16, cs16, cs32, int32_t, m> >(taps); \
+        return new DecT<dsptl::FilterDnsamplingFir<cs16, cs16, cs32, int32_t, m> >(taps);
+        RATIOS(X)
+#undef X
+    }
+    return nullptr;
+}
+
+UpBase *make_up(int L, const std::vector<int32_t> &taps)
+{
+    switch (L) {
+#define X(l) \
+    case l:  \
+        return new UpT<l>(taps);
+        RATIOS(X)
+#undef X
+    }
+    return nullptr;
+}
+
+MixerBase *make_mixer(unsigned N)
+{
+    switch (N) {
+    case 256: return new MixerT<256>();
+    case 1024: return new MixerT<1024>();
+    case 4096: return new MixerT<4096>();
+    case 8192: return new MixerT<8192>();
+    }
+    return nullptr;
+}
+
+inline std::vector<cs16> to_vec(const int16_t *iq, size_t n)
+{
+    std::vector<cs16> v(n);
+    if (n) std::memcpy(v.data(), iq, n * sizeof(cs16));
+    return v;
+}
+
+}  // namespace
+
+extern "C" {
+
+// --- mixer -----------------------------------------------------------------------------------
+void *ref_mixer_create(unsigned n_table) { return make_mixer(n_table); }
+void ref_mixer_destroy(void *h) { delete static_cast<MixerBase *>(h); }
+int ref_mixer_set_frequency(void *h, float f)
+{
+    if (!(f <= 1 && f >= -1)) return -1;  // mixers.h:54 would assert
+    static_cast<MixerBase *>(h)->setFrequency(f);
+    return 0;
+}
+void ref_mixer_reset(void *h, float f) { static_cast<MixerBase *>(h)->reset(f); }
+void ref_mixer_adjust_frequency(void *h, float f) { static_cast<MixerBase *>(h)->adjustFrequency(f); }
+int ref_mixer_phi(void *h) { return static_cast<MixerBase *>(h)->phi(); }
+int ref_mixer_freq(void *h) { return static_cast<MixerBase *>(h)->freq(); }
+void ref_mixer_step(void *h, const int16_t *in_iq, int16_t *out_iq, size_t n)
+{
+    std::vector<cs16> in = to_vec(in_iq, n), out(n);
+    static_cast<MixerBase *>(h)->step(in, out);
+    if (n) std::memcpy(out_iq, out.data(), n * sizeof(cs16));
+}
+
+// --- decimator (variant 0 = dnsampling_filters.h, 1 = dsptl_dnsampling_filters.h) ---------------
+void *ref_dec_create(int variant, int M, const int32_t *taps, int ntaps)
+{
+    if (ntaps < 1) return nullptr;
+    if (variant != 0 && ntaps % M != 0) return nullptr;  // dsptl_dnsampling_filters.h:122 would assert
+    return make_dec(variant, M, std::vector<int32_t>(taps, taps + ntaps));
+}
+void ref_dec_destroy(void *h) { delete static_cast<DecBase *>(h); }
+void ref_dec_reset(void *h) { static_cast<DecBase *>(h)->reset(); }
+void ref_dec_set_left_shift(void *h, int s) { static_cast<DecBase *>(h)->setLeftShiftBy2(s); }
+void ref_dec_step(void *h, const int16_t *in_iq, size_t n_in, int M, int16_t *out_iq)
+{
+    std::vector<cs16> in = to_vec(in_iq, n_in), out(n_in / M);
+    static_cast<DecBase *>(h)->step(in, out);
+    if (!out.empty()) std::memcpy(out_iq, out.data(), out.size() * sizeof(cs16));
+}
+
+// --- plain FIR (filters.h) ----------------------------------------------------------------------
+void *ref_fir_create(const int32_t *taps, int ntaps)
+{
+    return new FilterFir<cs16, cs16, cs32, int32_t>(std::vector<int32_t>(taps, taps + ntaps));
+}
+void ref_fir_destroy(void *h) { delete static_cast<FilterFir<cs16, cs16, cs32, int32_t> *>(h); }
+void ref_fir_reset(void *h) { static_cast<FilterFir<cs16, cs16, cs32, int32_t> *>(h)->reset(); }
+void ref_fir_step(void *h, const int16_t *in_iq, size_t n, int16_t *out_iq)
+{
+    std::vector<cs16> in = to_vec(in_iq, n), out(n);
+    static_cast<FilterFir<cs16, cs16, cs32, int32_t> *>(h)->step(in, out);
+    if (n) std::memcpy(out_iq, out.data(), n * sizeof(cs16));
+}
+
+// --- upsampler ----------------------------------------------------------------------------------
+void *ref_up_create(int L, const int32_t *taps, int ntaps)
+{
+    if (ntaps < 1 || ntaps % L != 0) return nullptr;  // upsampling_filters.h:110,113 would assert
+    return make_up(L, std::vector<int32_t>(taps, taps + ntaps));
+}
+void ref_up_destroy(void *h) { delete static_cast<UpBase *>(h); }
+void ref_up_reset(void *h) { static_cast<UpBase *>(h)->reset(); }
+int ref_up_set_coefficients(void *h, const int32_t *taps, int ntaps)
+{
+    UpBase *u = static_cast<UpBase *>(h);
+    if (ntaps < 1 || ntaps % u->getUpsamplingRatio() != 0) return -1;
+    u->setCoefficients(std::vector<int32_t>(taps, taps + ntaps));
+    return 0;
+}
+int ref_up_get_length(void *h) { return static_cast<UpBase *>(h)->getLength(); }
+int ref_up_get_imp_length(void *h) { return static_cast<UpBase *>(h)->getImpLength(); }
+int ref_up_get_ratio(void *h) { return static_cast<UpBase *>(h)->getUpsamplingRatio(); }
+// shift_mode 0: vector overload (shift 15 - round(log2 L)); 1: iterator overload (shift 0).
+// out_iq must hold L*(n_in + (flush ? length/L : 0)) samples.
+void ref_up_step(void *h, const int16_t *in_iq, size_t n_in, int16_t *out_iq, int flush, int shift_mode)
+{
+    UpBase *u = static_cast<UpBase *>(h);
+    const size_t L = (size_t)u->getUpsamplingRatio();
+    const size_t n_out = L * (n_in + (flush ? (size_t)u->getLength() / L : 0));
+    std::vector<cs16> in = to_vec(in_iq, n_in), out(n_out);
+    if (shift_mode == 0)
+        u->step(in, out, flush != 0);
+    else
+        u->stepIt(in, out.begin(), flush != 0);
+    if (n_out) std::memcpy(out_iq, out.data(), n_out * sizeof(cs16));
+}
+
+// --- CPU baseline: time the reference's own step() calls on a bank of independent channels -----
+// One Mixer / decimator object set per channel (that is how the reference models a channel),
+// channels dealt round-robin over n_threads std::threads, streaming blocks of block_len samples.
+// kind: 0 = dec only, 1 = mix + dec, 2 = mix + dec + dec2, 3 = upsampler (M1 is L).
+// in_iq: [C][n_per_ch] interleaved I/Q; out_iq may be NULL (timing only) or [C][n_out_per_ch].
+// Returns wall seconds spent inside step() calls (vector marshalling excluded), < 0 on error.
+double ref_bench_bank(int kind, int C, size_t n_per_ch, size_t block_len, int n_threads,
+                      const int16_t *in_iq, int16_t *out_iq,
+                      int M1, const int32_t *taps1, int ntaps1,
+                      int M2, const int32_t *taps2, int ntaps2,
+                      const float *lo_freq /* [C] or NULL */)
+{
+    if (n_threads < 1) n_threads = 1;
+    if (block_len == 0 || n_per_ch % block_len != 0) return -1.0;
+    const size_t ratio_num = (kind == 3) ? (size_t)M1 : 1;
+    const size_t ratio_den = (kind == 3) ? 1 : (size_t)M1 * (kind == 2 ? (size_t)M2 : 1);
+    if (kind != 3 && block_len % ratio_den != 0) return -1.0;
+    const size_t n_out_per_ch = n_per_ch * ratio_num / ratio_den;
+
+    struct Chan {
+        MixerBase *mix = nullptr;
+        DecBase *d1 = nullptr, *d2 = nullptr;
+        UpBase *up = nullptr;
+    };
+    std::vector<Chan> ch((size_t)C);
+    for (int c = 0; c < C; ++c) {
+        if (kind == 1 || kind == 2) {
+            ch[c].mix = make_mixer(4096);
+            ch[c].mix->setFrequency(lo_freq ? lo_freq[c] : 0.f);
+        }
+        if (kind <= 2) {
+            ch[c].d1 = make_dec(0, M1, std::vector<int32_t>(taps1, taps1 + ntaps1));
+            if (!ch[c].d1) return -2.0;
+        }
+        if (kind == 2) {
+            ch[c].d2 = make_dec(0, M2, std::vector<int32_t>(taps2, taps2 + ntaps2));
+            if (!ch[c].d2) return -2.0;
+        }
+        if (kind == 3) {
+            if (ntaps1 % M1) return -2.0;
+            ch[c].up = make_up(M1, std::vector<int32_t>(taps1, taps1 + ntaps1));
+            if (!ch[c].up) return -2.0;
+        }
+    }
+
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t) {
+        th.emplace_back([&, t]() {
+            std::vector<cs16> in(block_len), mixed(block_len), o1, o2;
+            for (int c = t; c < C; c += n_threads) {
+                for (size_t b0 = 0; b0 < n_per_ch; b0 += block_len) {
+                    std::memcpy(in.data(), in_iq + 2 * ((size_t)c * n_per_ch + b0), block_len * sizeof(cs16));
+                    const std::vector<cs16> *res = nullptr;
+                    if (kind == 3) {
+                        o1.resize(block_len * (size_t)M1);
+                        ch[c].up->step(in, o1, false);
+                        res = &o1;
+                    } else {
+                        std::vector<cs16> *src = &in;
+                        if (ch[c].mix) {
+                            ch[c].mix->step(in, mixed);
+                            src = &mixed;
+                        }
+                        o1.resize(block_len / (size_t)M1);
+                        ch[c].d1->step(*src, o1);
+                        res = &o1;
+                        if (ch[c].d2) {
+                            o2.resize(o1.size() / (size_t)M2);
+                            ch[c].d2->step(o1, o2);
+                            res = &o2;
+                        }
+                    }
+                    if (out_iq) {
+                        const size_t o0 = b0 * ratio_num / ratio_den;
+                        std::memcpy(out_iq + 2 * ((size_t)c * n_out_per_ch + o0), res->data(), res->size() * sizeof(cs16));
+                    }
+                }
+            }
+        });
+    }
+    for (auto &x : th) x.join();
+    double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+
+    for (auto &c : ch) {
+        delete c.mix;
+        delete c.d1;
+        delete c.d2;
+        delete c.up;
+    }
+    return secs;
+}
+
+const char *ref_build_info()
+{
+    return "SrcDsp reference headers, unmodified, g++ " __VERSION__
+#ifdef __OPTIMIZE__
+           " optimised"
+#else
+           " -O0 (makefile flags)"
+#endif
+        ;
+}
+
+}  // extern "C"
