@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the SrcDsp DDC hot path on B200 (contract: see README/DESIGN).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2]
+
+Workload (BASELINE.json configs[1], "cfg2"): decimate-by-16, 255-tap polyphase FIR over 256
+independent complex int16 channels x 16 Mi samples each, per GPU (weak scaling: N GPUs run
+N x 256 channels, contiguous channel batches per rank, no data-path collective).
+
+One "step" = one pass of the decimator bank over the whole 16 GiB device-resident batch
+(much larger than the 126 MB L2, so no L2 flush is needed between timed iterations).
+
+  value      whole-job output Msamples/s, input already resident in HBM, CUDA-event timed
+  e2e        same metric through the public API with HOST (pinned) buffers: H2D + kernels + D2H
+  roofline   dominant kernel's algorithmic bytes / its measured duration vs measured HBM peak
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref) timed on this box's host cores
+
+`--impl reference` times the reference's own CPU implementation (oracle/_ref, all host threads)
+on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 0x5EED0002
+WORKLOADS = {
+    # name: (channels per GPU, samples per channel, M, ntaps, fused mixer)
+    "cfg2": dict(channels=256, n=1 << 24, M=16, ntaps=255, mix=False,
+                 desc="cfg2: decimate-by-16 255-tap polyphase FIR, 256 ch x 16Mi cs16 samples per GPU"),
+    "ddc16": dict(channels=256, n=1 << 24, M=16, ntaps=255, mix=True,
+                  desc="ddc16: NCO mix fused into decimate-by-16 255-tap FIR, 256 ch x 16Mi per GPU"),
+    "smoke": dict(channels=8, n=1 << 18, M=16, ntaps=255, mix=False, desc="smoke: 8 ch x 256Ki"),
+}
+BYTES_PER_OUT = lambda M: 4 * M + 4  # cs16 in + cs16 out per output sample
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [v.strip() for v in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_run(w, steps: int, warmup: int, cores: int, target_cpu_seconds: float = 16.0):
+    """Times the unmodified reference (oracle/_ref) on a bounded sample of the workload."""
+    import oracle as O
+    r = O.ref()
+    kind = "reference"
+    if r is None:
+        raise RuntimeError("oracle/_ref is not built (run `make -C oracle` where /root/reference exists)")
+    M, nt = w["M"], w["ntaps"]
+    taps = O.design_lowpass_taps(nt, M)
+    # ~1 Msample/s out per core for /16, 255 taps: size the sample for ~16 s CPU work
+    est_out_per_core_s = 0.97e6 * 255.0 / max(nt, 1)
+    total_out = target_cpu_seconds * est_out_per_core_s
+    ch = min(w["channels"], 2 * cores)
+    block = 1 << 16
+    n = int(total_out * M / ch) // block * block
+    n = max(block, min(n, w["n"]))
+    c = O.corc()
+    x = np.stack([c.synth(SEED, k, 0, n, 2) for k in range(ch)])
+    lo = (-1 + 2 * (np.arange(ch) + 0.5) / ch).astype(np.float32) if w["mix"] else None
+    times = []
+    for i in range(warmup + steps):
+        secs, _ = r.bench_bank(1 if w["mix"] else 0, x, block, cores, M, taps, lo_freq=lo)
+        if i >= warmup:
+            times.append(secs)
+    n_out = ch * (n // M)
+    t = float(np.mean(times))
+    return dict(value=n_out / t / 1e6, unit="Msamples/s", cores=cores, kind=kind,
+                sample=f"{ch} channels x {n} samples (/{M}, {nt} taps), {r.build_info()}, "
+                       f"{cores} threads, 64Ki-sample streaming blocks, mean of {len(times)} runs",
+                seconds=t), t
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 IMAD kernel, 2 tcgen05 kernel")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cores = os.cpu_count() or 1
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    base = {"metric": "output Msamples/s", "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic",
+            "config": {"workload": w["desc"], "channels_per_gpu": w["channels"], "samples_per_channel": w["n"],
+                       "decimation": w["M"], "taps": w["ntaps"], "nco_mix": w["mix"],
+                       "sharding": "contiguous channel batches per rank, no collective",
+                       "l2": "16 GiB batch per step >> 126 MB L2 (no flush needed)"}}
+
+    # ------------------------------------------------------------------------------------------
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        res, t = cpu_reference_run(w, args.steps, args.warmup, cores)
+        line = dict(base, impl="reference", value=res["value"], ms_per_step=t * 1e3, cpu_baseline=res,
+                    e2e={"value": res["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                    gpu_launches=0)
+        line["config"]["note"] = "CPU reference arm: each step is the bounded sample described in cpu_baseline.sample"
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------------------------------
+    import torch
+    import oracle as O          # tap design + cpu_baseline leg only
+    import srcdsp_b200 as S
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: srcdsp_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    C, n, M, nt = w["channels"], w["n"], w["M"], w["ntaps"]
+    from srcdsp_b200.sharding import channel_shard
+    my_ch = channel_shard(C * world, world, rank)  # weak scaling: 256 channels per GPU
+    taps = O.design_lowpass_taps(nt, M)
+    x = torch.empty((C, n, 2), dtype=torch.int16, device="cuda")
+    y = torch.empty((C, n // M, 2), dtype=torch.int16, device="cuda")
+    S.synth_fill(x, SEED, ch0=my_ch.start, amp_shift=2)
+    dec = S.FilterDnsamplingFir(M, taps, channels=C, device=local_rank, obsolete=True)
+    dec.set_kernel(args.kernel)
+    chain = dec
+    if w["mix"]:
+        mix = S.Mixer(channels=C, device=local_rank)
+        mix.setFrequency((-1 + 2 * (np.arange(my_ch.start, my_ch.stop) + 0.5) / (C * world)).astype(np.float32))
+        chain = S.Ddc(mix, dec)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        chain.step(x, out=y)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = S.launch_count()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs[0].record()
+    for i in range(args.steps):
+        chain.step(x, out=y)
+        evs[i + 1].record()
+    barrier()
+    launches = S.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = evs[0].elapsed_time(evs[-1])
+    step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    n_out_total = C * (n // M) * world
+    value = n_out_total * args.steps / (total_ms * 1e-3) / 1e6
+
+    # roofline of the dominant kernel (dec_fir_kernel: one launch per step; the history kernel that
+    # shares the step is ~2 us).  Algorithmic bytes per launch = 68 B/output x outputs per launch.
+    peak, peak_src = peaks()
+    k_ms = float(np.mean(step_ms))
+    alg_bytes = BYTES_PER_OUT(M) * C * (n // M)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(args.workload)
+    roof = {"bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+            "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / peak, "traffic": traffic,
+            "kernel": "dec_fir_kernel", "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+            "kernel_ms": k_ms,
+            "imad_note": "int16 x int32-tap FIR is INT32-multiply bound, not HBM bound: 2*taps IMAD per output "
+                         "(SURVEY.md 8(d)); imad_frac below is against 148 SM x 64 IMAD/clk x sm_max_mhz"}
+    if clocks and clocks.get("sm_max_mhz"):
+        imad_peak = 148 * 64 * clocks["sm_max_mhz"] * 1e6
+        roof["imad_frac"] = (2 * nt * C * (n // M)) / (k_ms * 1e-3) / imad_peak
+
+    # ---- e2e: public API with pinned HOST buffers, H2D + kernels + D2H inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        try:
+            hin = S.PinnedBuffer(C, n)
+            hout = S.PinnedBuffer(C, n // M)
+            S._capi.check(S.lib().srcdsp_memcpy(local_rank, hin.array.ctypes.data, x.data_ptr(), C * n * 4))
+            del x
+            torch.cuda.empty_cache()
+            dec.reset()
+            chain.step(hin.array[:, : M * 4096], out=hout.array[:, :4096])  # warm the staging buffers
+            dec.reset()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                chain.step(hin.array, out=hout.array)  # returns when the output is in host memory
+            barrier()
+            dt = time.perf_counter() - t0
+            tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            if dist:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+            e2e = {"value": n_out_total * args.e2e_steps / dt / 1e6, "unit": "Msamples/s",
+                   "h2d_bytes_per_step": C * n * 4, "d2h_bytes_per_step": C * (n // M) * 4,
+                   "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
+                   "api": "FilterDnsamplingFir.step(host numpy view of pinned memory) -> srcdsp_dec_step"}
+            hin.free()
+            hout.free()
+        except Exception as ex:  # report, never fake
+            e2e = {"value": None, "unit": "Msamples/s", "error": str(ex)[:200]}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            cpu, _ = cpu_reference_run(w, 2, 1, cores)
+        except Exception as ex:
+            cpu = {"value": None, "error": str(ex)[:200]}
+
+    if rank == 0:
+        line = dict(base, value=value, ms_per_step=total_ms / args.steps, roofline=roof, cpu_baseline=cpu, e2e=e2e,
+                    clocks=clocks, gpu_launches=int(launches), impl="ours")
+        print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

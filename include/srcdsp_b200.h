@@ -1,0 +1,163 @@
+/*
+ * srcdsp_b200.h -- C ABI of the B200-native SrcDsp DDC hot path (libsrcdsp_b200.so).
+ *
+ * The reference (dogjin/SrcDsp) has no FFI boundary: its "interface" is the public API of three
+ * header-only class templates.  This ABI is what the drop-in classes in include/srcdsp/ (mixers.h, ...)
+ * forward to; each entry point cites the reference member it replaces (file:line into the
+ * reference checkout).  Template parameters of the reference (M, L, N) are runtime arguments.
+ *
+ * Conventions
+ *   - every function returns an int status: 0 = SRCDSP_OK, negative = SRCDSP_E_*;
+ *     srcdsp_last_error() returns a thread-local message for the last failure.  Nothing throws.
+ *   - a handle is a BANK of `channels` independent streams that share taps (the reference
+ *     models a channel as one object; a bank with channels == 1 is exactly one object).
+ *   - samples are interleaved I/Q int16 (byte-identical to std::vector<std::complex<int16_t>>
+ *     ::data()); a bank buffer is channel-major: channel c starts at ptr + 2*c*stride int16
+ *     (stride in complex samples).  Pointers may be device, pinned-host or pageable-host memory
+ *     (detected with cudaPointerGetAttributes); host buffers are staged through a chunked
+ *     H2D -> kernel -> D2H pipeline.  Input and output must be the same kind.
+ *   - one host thread per handle at a time (same contract as the reference objects); different
+ *     handles are independent.  step() with host buffers returns when the output is complete;
+ *     with device buffers it is asynchronous on the handle's stream (srcdsp_*_sync to wait).
+ *   - there is NO CPU fallback: every step runs hand-written sm_100a kernels or fails.
+ */
+#ifndef SRCDSP_B200_H
+#define SRCDSP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRCDSP_OK 0
+#define SRCDSP_E_INVALID (-1) /* bad argument / handle                                         */
+#define SRCDSP_E_SIZE (-2)    /* a size precondition the reference assert()s on is violated    */
+#define SRCDSP_E_CUDA (-3)    /* CUDA runtime error (message in srcdsp_last_error)            */
+#define SRCDSP_E_NOMEM (-4)
+#define SRCDSP_E_STATE (-5)   /* e.g. step() before coefficients were set                      */
+#define SRCDSP_E_NOGPU (-6)   /* no sm_100 device / driver: the library refuses to run        */
+
+typedef struct srcdsp_mixer_s *srcdsp_mixer_t;
+typedef struct srcdsp_dec_s *srcdsp_dec_t;
+typedef struct srcdsp_up_s *srcdsp_up_t;
+typedef struct srcdsp_ddc_s *srcdsp_ddc_t;
+
+/* ------------------------------------------------------------------------------------------ */
+/* library                                                                                    */
+const char *srcdsp_last_error(void);
+int srcdsp_version(void);
+int srcdsp_device_count(int *count);
+/* kernel launch counter (all handles, this process): used by bench.py for "gpu_launches". */
+uint64_t srcdsp_launch_count(void);
+
+/* pinned host memory for zero-staging transfers, and plain device memory */
+int srcdsp_host_alloc(void **ptr, size_t bytes);
+int srcdsp_host_free(void *ptr);
+int srcdsp_device_alloc(int device, void **ptr, size_t bytes);
+int srcdsp_device_free(int device, void *ptr);
+int srcdsp_memcpy(int device, void *dst, const void *src, size_t bytes); /* any <-> any, sync */
+
+/* synthetic multi-channel complex baseband, counter-based: sample n of channel c depends only
+ * on (seed, ch0 + c, n0 + n); oracle/srcdsp_oracle.c:orc_synth_fill is the host twin.
+ * d_iq: device pointer, [channels][stride] complex int16.  stream may be NULL. */
+int srcdsp_synth_fill(int device, void *stream, int16_t *d_iq, size_t stride, int channels,
+                      size_t n_per_ch, uint32_t seed, uint32_t ch0, uint64_t n0, int amp_shift);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Mixer bank -- dsptl::Mixer<complex<int16_t>, complex<int16_t>, int16_t, N>                 */
+/* ctor: mixers.h:149-160 (sine table of n_table entries, amplitude 16383, phase = freq = 0)  */
+int srcdsp_mixer_create(srcdsp_mixer_t *h, int device, int channels, unsigned n_table);
+int srcdsp_mixer_destroy(srcdsp_mixer_t h);
+/* _Mixer::setFrequency  mixers.h:51-67   (ch = -1: all channels; |lo_freq| <= 1 else E_SIZE) */
+int srcdsp_mixer_set_frequency(srcdsp_mixer_t h, int ch, float lo_freq);
+/* per-channel frequencies in one call: lo_freq[channels]                                      */
+int srcdsp_mixer_set_frequencies(srcdsp_mixer_t h, const float *lo_freq);
+/* _Mixer::reset         mixers.h:76-81                                                        */
+int srcdsp_mixer_reset(srcdsp_mixer_t h, int ch, float lo_freq);
+/* _Mixer::adjustFrequency mixers.h:91-98 (phase continuous)                                   */
+int srcdsp_mixer_adjust_frequency(srcdsp_mixer_t h, int ch, float adjust);
+/* Mixer::step           mixers.h:168-188.  out may alias in.                                  */
+int srcdsp_mixer_step(srcdsp_mixer_t h, const int16_t *in_iq, size_t in_stride, int16_t *out_iq,
+                      size_t out_stride, size_t n_per_ch);
+/* streaming state (the reference's protected phi / freq / nominalFreq): checkpoint, migration */
+int srcdsp_mixer_get_state(srcdsp_mixer_t h, int ch, int *phi, int *freq, float *nominal);
+int srcdsp_mixer_set_state(srcdsp_mixer_t h, int ch, int phi, int freq, float nominal);
+int srcdsp_mixer_set_stream(srcdsp_mixer_t h, void *cuda_stream);
+int srcdsp_mixer_sync(srcdsp_mixer_t h);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Decimator bank -- dsptl::FilterDnsamplingFir<cs16, cs16, cs32, int32_t, M>                 */
+/* default ctor: dsptl_dnsampling_filters.h:81-83 (no taps yet; step() -> SRCDSP_E_STATE)      */
+int srcdsp_dec_create(srcdsp_dec_t *h, int device, int channels, int M);
+int srcdsp_dec_destroy(srcdsp_dec_t h);
+/* setCoeffs: dsptl_dnsampling_filters.h:114-134 when require_multiple_of_m != 0 (ntaps % M
+ * must be 0, else E_SIZE, the reference assert :122); ctor of the obsolete twin
+ * dnsampling_filters.h:83-97 when 0 (any ntaps >= 1).  Zeroes the history (history.resize on a
+ * fresh object) and leftShift, computes coeffScaling = floor(log2(sum |c|)).
+ * NB the reference keeps old history entries when setCoeffs is called again with a different
+ * size; this ABI clears it (documented difference). */
+int srcdsp_dec_set_coeffs(srcdsp_dec_t h, const int32_t *taps, int ntaps, int require_multiple_of_m);
+/* setLeftShiftBy2: dsptl_dnsampling_filters.h:63 */
+int srcdsp_dec_set_left_shift(srcdsp_dec_t h, int left_shift);
+/* reset: dsptl_dnsampling_filters.h:55-59 */
+int srcdsp_dec_reset(srcdsp_dec_t h);
+/* step: dsptl_dnsampling_filters.h:172-220 == dnsampling_filters.h:128-172.
+ * n_in_per_ch % M must be 0 (E_SIZE; the reference assert :181).  Writes n_in_per_ch / M
+ * samples per channel.  Blocks shorter than ntaps-1 are allowed (the reference reads out of
+ * bounds there); the history then is the last ntaps-1 samples of history ++ input. */
+int srcdsp_dec_step(srcdsp_dec_t h, const int16_t *in_iq, size_t in_stride, size_t n_in_per_ch,
+                    int16_t *out_iq, size_t out_stride);
+int srcdsp_dec_get_coeff_scaling(srcdsp_dec_t h, int *coeff_scaling);
+/* history of one channel, oldest first, ntaps-1 complex samples (host pointers) */
+int srcdsp_dec_get_state(srcdsp_dec_t h, int ch, int16_t *history_iq, size_t *n_samples);
+int srcdsp_dec_set_state(srcdsp_dec_t h, int ch, const int16_t *history_iq, size_t n_samples);
+int srcdsp_dec_set_stream(srcdsp_dec_t h, void *cuda_stream);
+int srcdsp_dec_sync(srcdsp_dec_t h);
+/* kernel selection: 0 = automatic, 1 = force the INT32-FMA (IMAD) kernel, 2 = force the
+ * tcgen05 int8 Toeplitz kernel (E_STATE at step if the taps do not fit it). */
+int srcdsp_dec_set_kernel(srcdsp_dec_t h, int kind);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Fused DDC chain: mixer -> dec1 [-> dec2].  One call == the separate steps, bit for bit:     */
+/*   mixer.step(in, t0); dec1.step(t0, t1); dec2.step(t1, out);                               */
+/* (mixers.h:168-188 feeding dsptl_dnsampling_filters.h:172-220 twice).  The NCO mix is fused  */
+/* into the first decimator's load stage.  mixer may be NULL (dec1 -> dec2 only); dec2 may be  */
+/* NULL.  The handles stay owned by the caller and keep their streaming state.                */
+int srcdsp_ddc_create(srcdsp_ddc_t *h, srcdsp_mixer_t mixer, srcdsp_dec_t dec1, srcdsp_dec_t dec2);
+int srcdsp_ddc_destroy(srcdsp_ddc_t h);
+int srcdsp_ddc_step(srcdsp_ddc_t h, const int16_t *in_iq, size_t in_stride, size_t n_in_per_ch,
+                    int16_t *out_iq, size_t out_stride);
+int srcdsp_ddc_set_stream(srcdsp_ddc_t h, void *cuda_stream);
+int srcdsp_ddc_sync(srcdsp_ddc_t h);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Upsampler bank -- dsptl::FilterUpsamplingFir<cs16, cs16, cs32, int32_t, L>                 */
+/* ctor with empty taps: upsampling_filters.h:89-96 */
+int srcdsp_up_create(srcdsp_up_t *h, int device, int channels, int L);
+int srcdsp_up_destroy(srcdsp_up_t h);
+/* setCoefficients: upsampling_filters.h:107-126 (ntaps >= 1 and ntaps % L == 0, else E_SIZE).
+ * Like the reference it does NOT clear the history when the size is unchanged. */
+int srcdsp_up_set_coefficients(srcdsp_up_t h, const int32_t *taps, int ntaps);
+/* reset: upsampling_filters.h:50-55 */
+int srcdsp_up_reset(srcdsp_up_t h);
+/* step: shift_mode 0 = vector overload upsampling_filters.h:149-233 (shift 15 - round(log2 L)),
+ *       shift_mode 1 = iterator overload :240-323 (shift 0).
+ * Writes L * (n_in_per_ch + (flush ? getLength()/L : 0)) samples per channel. */
+int srcdsp_up_step(srcdsp_up_t h, const int16_t *in_iq, size_t in_stride, size_t n_in_per_ch,
+                   int16_t *out_iq, size_t out_stride, int flush, int shift_mode);
+/* getLength / getImpLength / getUpsamplingRatio: upsampling_filters.h:57-67 */
+int srcdsp_up_get_length(srcdsp_up_t h, int *length);
+int srcdsp_up_get_imp_length(srcdsp_up_t h, int *imp_length);
+int srcdsp_up_get_ratio(srcdsp_up_t h, int *ratio);
+/* history of one channel in age order, oldest first, ntaps/L - 1 complex samples */
+int srcdsp_up_get_state(srcdsp_up_t h, int ch, int16_t *history_iq, size_t *n_samples);
+int srcdsp_up_set_state(srcdsp_up_t h, int ch, const int16_t *history_iq, size_t n_samples);
+int srcdsp_up_set_stream(srcdsp_up_t h, void *cuda_stream);
+int srcdsp_up_sync(srcdsp_up_t h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRCDSP_B200_H */

@@ -1,0 +1,1272 @@
+// capi.cu -- host side of libsrcdsp_b200.so: the extern "C" layer declared in
+// include/srcdsp_b200.h.  Owns device state (taps, carried history, NCO phase), picks kernel
+// instantiations, and stages host buffers through a chunked H2D -> kernel -> D2H pipeline.
+// There is no CPU compute path in this file: every step launches sm_100a kernels or fails.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels_dec.cuh"
+#include "kernels_up.cuh"
+
+namespace srcdsp {
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+std::string &last_error_ref()
+{
+    static thread_local std::string s;
+    return s;
+}
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    last_error_ref() = buf;
+    return code;
+}
+
+static std::atomic<uint64_t> g_launches{0};
+static inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+#define SRCDSP_LAUNCH_CHECK()                                                                     \
+    do {                                                                                          \
+        cudaError_t _e = cudaGetLastError();                                                      \
+        if (_e != cudaSuccess)                                                                    \
+            return fail(SRCDSP_E_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \
+                        __FILE__, __LINE__);                                                      \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool changed = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) {
+            cudaSetDevice(dev);
+            changed = true;
+        }
+    }
+    ~DeviceGuard()
+    {
+        if (changed) cudaSetDevice(prev);
+    }
+};
+
+static int check_device(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(SRCDSP_E_NOGPU, "no CUDA device available (%s): libsrcdsp_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n) return fail(SRCDSP_E_INVALID, "device %d out of range [0, %d)", device, n);
+    cudaDeviceProp prop;
+    SRCDSP_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(SRCDSP_E_NOGPU, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    return SRCDSP_OK;
+}
+
+static bool is_device_ptr(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// ---------------------------------------------------------------------------------------------
+// bank base: device, stream, host-staging pipeline
+// ---------------------------------------------------------------------------------------------
+constexpr int NBUF = 3;
+constexpr size_t STAGE_TARGET_BYTES = 48u << 20;  // per chunk, larger of in/out
+
+struct Bank {
+    int device = 0;
+    int C = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    // host staging
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_h2d[NBUF] = {}, ev_comp[NBUF] = {}, ev_d2h[NBUF] = {};
+    uint32_t *d_in[NBUF] = {}, *d_out[NBUF] = {};
+    size_t cap_in = 0, cap_out = 0;  // words per buffer
+
+    int init(int dev, int channels)
+    {
+        SRCDSP_TRY(check_device(dev));
+        if (channels < 1) return fail(SRCDSP_E_INVALID, "channels must be >= 1 (got %d)", channels);
+        device = dev;
+        C = channels;
+        DeviceGuard g(device);
+        SRCDSP_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        own_stream = true;
+        return SRCDSP_OK;
+    }
+
+    int set_stream(void *s)
+    {
+        DeviceGuard g(device);
+        SRCDSP_CUDA(cudaStreamSynchronize(stream));
+        if (own_stream) cudaStreamDestroy(stream);
+        own_stream = false;
+        if (s == nullptr) {
+            SRCDSP_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+            own_stream = true;
+        } else {
+            stream = static_cast<cudaStream_t>(s);
+        }
+        return SRCDSP_OK;
+    }
+
+    int sync()
+    {
+        DeviceGuard g(device);
+        SRCDSP_CUDA(cudaStreamSynchronize(stream));
+        return SRCDSP_OK;
+    }
+
+    int ensure_staging(size_t words_in, size_t words_out)
+    {
+        if (!s_h2d) {
+            SRCDSP_CUDA(cudaStreamCreateWithFlags(&s_h2d, cudaStreamNonBlocking));
+            SRCDSP_CUDA(cudaStreamCreateWithFlags(&s_d2h, cudaStreamNonBlocking));
+            for (int k = 0; k < NBUF; ++k) {
+                SRCDSP_CUDA(cudaEventCreateWithFlags(&ev_h2d[k], cudaEventDisableTiming));
+                SRCDSP_CUDA(cudaEventCreateWithFlags(&ev_comp[k], cudaEventDisableTiming));
+                SRCDSP_CUDA(cudaEventCreateWithFlags(&ev_d2h[k], cudaEventDisableTiming));
+            }
+        }
+        if (words_in > cap_in) {
+            for (int k = 0; k < NBUF; ++k) {
+                if (d_in[k]) cudaFree(d_in[k]);
+                d_in[k] = nullptr;
+                SRCDSP_CUDA(cudaMalloc(&d_in[k], words_in * 4));
+            }
+            cap_in = words_in;
+        }
+        if (words_out > cap_out) {
+            for (int k = 0; k < NBUF; ++k) {
+                if (d_out[k]) cudaFree(d_out[k]);
+                d_out[k] = nullptr;
+                SRCDSP_CUDA(cudaMalloc(&d_out[k], words_out * 4));
+            }
+            cap_out = words_out;
+        }
+        return SRCDSP_OK;
+    }
+
+    void release()
+    {
+        DeviceGuard g(device);
+        if (stream) cudaStreamSynchronize(stream);
+        for (int k = 0; k < NBUF; ++k) {
+            if (d_in[k]) cudaFree(d_in[k]);
+            if (d_out[k]) cudaFree(d_out[k]);
+            if (ev_h2d[k]) cudaEventDestroy(ev_h2d[k]);
+            if (ev_comp[k]) cudaEventDestroy(ev_comp[k]);
+            if (ev_d2h[k]) cudaEventDestroy(ev_d2h[k]);
+        }
+        if (s_h2d) cudaStreamDestroy(s_h2d);
+        if (s_d2h) cudaStreamDestroy(s_d2h);
+        if (own_stream && stream) cudaStreamDestroy(stream);
+        stream = nullptr;
+    }
+};
+
+// Runs `fn(d_in, in_stride, n_chunk, d_out, out_stride, last)` over consecutive chunks of a host
+// buffer.  Outputs per chunk: n_chunk * num / den (+ tail_out on the last chunk).
+template <class Fn>
+static int staged_run(Bank &b, const int16_t *in, size_t in_stride, size_t n_in, int16_t *out,
+                      size_t out_stride, size_t quantum, size_t num, size_t den, size_t tail_out, Fn fn)
+{
+    DeviceGuard g(b.device);
+    const size_t C = (size_t)b.C;
+    // chunk length in input samples per channel
+    const size_t per_in = 4 * C, per_out = 4 * C * num / den + 1;
+    size_t chunk = STAGE_TARGET_BYTES / (per_in > per_out ? per_in : per_out);
+    if (chunk >= n_in) chunk = n_in;
+    chunk -= chunk % quantum;
+    if (chunk == 0) chunk = (n_in < quantum) ? n_in : quantum;
+    const size_t n_chunks = n_in == 0 ? 1 : (n_in + chunk - 1) / chunk;
+    const size_t in_pitch = (chunk + 3) & ~(size_t)3;                           // words, 16-byte rows
+    const size_t out_pitch = ((chunk * num / den + tail_out) + 3) & ~(size_t)3;
+    SRCDSP_TRY(b.ensure_staging(in_pitch * C + 4, out_pitch * C + 4));
+    // order the copy streams behind whatever is already queued on the compute stream
+    SRCDSP_CUDA(cudaEventRecord(b.ev_comp[0], b.stream));
+    SRCDSP_CUDA(cudaStreamWaitEvent(b.s_h2d, b.ev_comp[0], 0));
+
+    const uint32_t *hin = reinterpret_cast<const uint32_t *>(in);
+    uint32_t *hout = reinterpret_cast<uint32_t *>(out);
+    for (size_t i = 0; i < n_chunks; ++i) {
+        const int k = (int)(i % NBUF);
+        const size_t off = i * chunk;
+        const size_t len = (off + chunk <= n_in) ? chunk : n_in - off;
+        const bool last = (i + 1 == n_chunks);
+        const size_t ooff = off * num / den;
+        const size_t olen = len * num / den + (last ? tail_out : 0);
+        if (i >= NBUF) {
+            SRCDSP_CUDA(cudaStreamWaitEvent(b.s_h2d, b.ev_comp[k], 0));   // d_in[k] consumed
+            SRCDSP_CUDA(cudaStreamWaitEvent(b.stream, b.ev_d2h[k], 0));   // d_out[k] drained
+        }
+        if (len)
+            SRCDSP_CUDA(cudaMemcpy2DAsync(b.d_in[k], in_pitch * 4, hin + off, in_stride * 4, len * 4, C,
+                                          cudaMemcpyHostToDevice, b.s_h2d));
+        SRCDSP_CUDA(cudaEventRecord(b.ev_h2d[k], b.s_h2d));
+        SRCDSP_CUDA(cudaStreamWaitEvent(b.stream, b.ev_h2d[k], 0));
+        SRCDSP_TRY(fn(b.d_in[k], in_pitch, len, b.d_out[k], out_pitch, last));
+        SRCDSP_CUDA(cudaEventRecord(b.ev_comp[k], b.stream));
+        SRCDSP_CUDA(cudaStreamWaitEvent(b.s_d2h, b.ev_comp[k], 0));
+        if (olen)
+            SRCDSP_CUDA(cudaMemcpy2DAsync(hout + ooff, out_stride * 4, b.d_out[k], out_pitch * 4, olen * 4, C,
+                                          cudaMemcpyDeviceToHost, b.s_d2h));
+        SRCDSP_CUDA(cudaEventRecord(b.ev_d2h[k], b.s_d2h));
+    }
+    SRCDSP_CUDA(cudaStreamSynchronize(b.s_d2h));
+    SRCDSP_CUDA(cudaStreamSynchronize(b.stream));
+    return SRCDSP_OK;
+}
+
+static int classify(const void *in, const void *out, bool *on_device)
+{
+    const bool di = is_device_ptr(in), dout = is_device_ptr(out);
+    if (di != dout)
+        return fail(SRCDSP_E_INVALID, "input and output must both be device or both be host pointers");
+    *on_device = di;
+    return SRCDSP_OK;
+}
+
+static inline bool aligned16(const void *p, size_t stride_words)
+{
+    return ((uintptr_t)p % 16 == 0) && (stride_words % 4 == 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// mixer bank
+// ---------------------------------------------------------------------------------------------
+struct MixerBank : Bank {
+    unsigned n_table = 4096;
+    uint32_t *d_cs = nullptr;  // packed (cos, sin)
+    int *d_phi[2] = {nullptr, nullptr};
+    int *d_freq = nullptr;
+    int cur = 0;
+    bool dirty = true;
+    std::vector<int> h_phi, h_freq;
+    std::vector<float> h_nominal;
+
+    PhaseMod pm() const
+    {
+        PhaseMod m;
+        m.n_table = n_table;
+        m.mask = (n_table & (n_table - 1)) == 0 ? n_table - 1 : 0;
+        return m;
+    }
+
+    // _Mixer::setFrequency, mixers.h:51-67 (float arithmetic, round half away from zero)
+    static int quantise(float lo, unsigned N)
+    {
+        int16_t f;
+        if (lo >= 0)
+            f = static_cast<int16_t>(roundf(lo * N / 2));
+        else {
+            f = static_cast<int16_t>(roundf(N - roundf(-lo * N / 2)));
+            if (f == static_cast<int16_t>(N)) f = 0;
+        }
+        return f;
+    }
+
+    int create(int dev, int channels, unsigned N)
+    {
+        if (N < 4 || N > 16384) return fail(SRCDSP_E_INVALID, "n_table must be in [4, 16384] (int16 phase), got %u", N);
+        SRCDSP_TRY(init(dev, channels));
+        n_table = N;
+        DeviceGuard g(device);
+        // Mixer ctor, mixers.h:149-160: T[k] = (int16) (16383 * sin(2 pi k / N)), truncating cast
+        const double pi = 3.141592653589793238462643383279502884197169399375105820974944592307816406286;
+        std::vector<int16_t> T(N);
+        const int16_t mx = (INT16_MAX >> 1);
+        for (unsigned k = 0; k < N; ++k) T[k] = static_cast<int16_t>(mx * sin(2 * pi * static_cast<double>(k) / N));
+        std::vector<uint32_t> cs(N);
+        for (unsigned k = 0; k < N; ++k)
+            cs[k] = (uint32_t)(uint16_t)T[(k + N / 4) % N] | ((uint32_t)(uint16_t)T[k] << 16);
+        SRCDSP_CUDA(cudaMalloc(&d_cs, N * 4));
+        SRCDSP_CUDA(cudaMemcpy(d_cs, cs.data(), N * 4, cudaMemcpyHostToDevice));
+        SRCDSP_CUDA(cudaMalloc(&d_phi[0], C * sizeof(int)));
+        SRCDSP_CUDA(cudaMalloc(&d_phi[1], C * sizeof(int)));
+        SRCDSP_CUDA(cudaMalloc(&d_freq, C * sizeof(int)));
+        h_phi.assign(C, 0);
+        h_freq.assign(C, 0);
+        h_nominal.assign(C, 0.f);
+        dirty = true;
+        return SRCDSP_OK;
+    }
+
+    int upload_if_dirty()
+    {
+        if (!dirty) return SRCDSP_OK;
+        // pageable sources: the driver stages them before returning, so the vectors may change
+        SRCDSP_CUDA(cudaMemcpyAsync(d_phi[cur], h_phi.data(), C * sizeof(int), cudaMemcpyHostToDevice, stream));
+        SRCDSP_CUDA(cudaMemcpyAsync(d_freq, h_freq.data(), C * sizeof(int), cudaMemcpyHostToDevice, stream));
+        dirty = false;
+        return SRCDSP_OK;
+    }
+
+    // host mirror of "phi advanced by n samples" (mixers.h:177 applied n times)
+    void advance(size_t n)
+    {
+        const unsigned long long nm = n % n_table;
+        for (int c = 0; c < C; ++c)
+            h_phi[c] = (int)(((unsigned long long)h_phi[c] + nm * (unsigned long long)h_freq[c]) % n_table);
+        cur ^= 1;
+    }
+
+    int step_device(const uint32_t *in, size_t in_stride, uint32_t *out, size_t out_stride, size_t n)
+    {
+        DeviceGuard g(device);
+        SRCDSP_TRY(upload_if_dirty());
+        const bool vec = aligned16(in, in_stride) && aligned16(out, out_stride);
+        long long work = vec ? (long long)((n + 3) / 4) : (long long)n;
+        int bx = (int)std::min<long long>((work + 255) / 256, (148ll * 16 + C - 1) / C);
+        if (bx < 1) bx = 1;
+        dim3 grid(bx, C);
+        if (vec)
+            mixer_kernel<true><<<grid, 256, 0, stream>>>(in, in_stride, out, out_stride, (long long)n, d_cs,
+                                                         d_phi[cur], d_phi[cur ^ 1], d_freq, pm());
+        else
+            mixer_kernel<false><<<grid, 256, 0, stream>>>(in, in_stride, out, out_stride, (long long)n, d_cs,
+                                                          d_phi[cur], d_phi[cur ^ 1], d_freq, pm());
+        SRCDSP_LAUNCH_CHECK();
+        count_launch();
+        advance(n);
+        return SRCDSP_OK;
+    }
+
+    void destroy()
+    {
+        DeviceGuard g(device);
+        release();
+        if (d_cs) cudaFree(d_cs);
+        if (d_phi[0]) cudaFree(d_phi[0]);
+        if (d_phi[1]) cudaFree(d_phi[1]);
+        if (d_freq) cudaFree(d_freq);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// decimator bank
+// ---------------------------------------------------------------------------------------------
+struct DecBank : Bank {
+    int M = 1;
+    int ntaps = 0;
+    int H = 0;  // ntaps - 1
+    int Qp = 0, JP = 0;
+    int coeff_scaling = 0;
+    int left_shift = 0;
+    int kernel_kind = 0;
+    std::vector<int32_t> taps;
+    int32_t *d_taps_poly = nullptr;
+    uint32_t *d_hist[2] = {nullptr, nullptr};
+    int cur = 0;
+    size_t smem_bytes = 0;
+
+    int set_coeffs(const int32_t *t, int n, int require_multiple)
+    {
+        if (!t || n < 1) return fail(SRCDSP_E_SIZE, "ntaps must be >= 1");
+        if (require_multiple && n % M != 0)
+            return fail(SRCDSP_E_SIZE, "ntaps (%d) must be a multiple of M (%d) [dsptl_dnsampling_filters.h:122]", n, M);
+        DeviceGuard g(device);
+        SRCDSP_CUDA(cudaStreamSynchronize(stream));
+        // coeffScaling: dsptl_dnsampling_filters.h:126-132
+        double sum = 0;
+        for (int k = 0; k < n; ++k) sum += std::abs(t[k]);
+        if (!(sum >= 1)) return fail(SRCDSP_E_SIZE, "sum |taps| must be >= 1 (coeffScaling = floor(log2(sum)))");
+        const int cs = static_cast<int>(floor(log2(sum)));
+
+        const int newH = n - 1;
+        const int q = (n + M - 1) / M;
+        const int newQp = (q + DEC_QC - 1) / DEC_QC * DEC_QC;
+        std::vector<int32_t> poly((size_t)M * newQp, 0);
+        for (int k = 0; k < n; ++k) poly[(size_t)(k % M) * newQp + k / M] = t[k];
+        int32_t *nd = nullptr;
+        SRCDSP_CUDA(cudaMalloc(&nd, poly.size() * 4));
+        SRCDSP_CUDA(cudaMemcpy(nd, poly.data(), poly.size() * 4, cudaMemcpyHostToDevice));
+        // history.resize(n-1) (dsptl_dnsampling_filters.h:127): keeps the first min(old,new)
+        // entries, value-initialises the rest
+        uint32_t *nh[2] = {nullptr, nullptr};
+        const size_t hw = (size_t)C * (newH > 0 ? newH : 1);
+        for (int k = 0; k < 2; ++k) {
+            SRCDSP_CUDA(cudaMalloc(&nh[k], hw * 4));
+            SRCDSP_CUDA(cudaMemset(nh[k], 0, hw * 4));
+        }
+        if (d_hist[cur] && H > 0 && newH > 0) {
+            const int keep = H < newH ? H : newH;
+            SRCDSP_CUDA(cudaMemcpy2D(nh[0], (size_t)newH * 4, d_hist[cur], (size_t)H * 4, (size_t)keep * 4, C,
+                                     cudaMemcpyDeviceToDevice));
+        }
+        if (d_taps_poly) cudaFree(d_taps_poly);
+        if (d_hist[0]) cudaFree(d_hist[0]);
+        if (d_hist[1]) cudaFree(d_hist[1]);
+        d_taps_poly = nd;
+        d_hist[0] = nh[0];
+        d_hist[1] = nh[1];
+        cur = 0;
+        taps.assign(t, t + n);
+        ntaps = n;
+        H = newH;
+        Qp = newQp;
+        const int Jlen = DEC_TB + Qp;
+        JP = (Jlen + 7) / 8 * 8;
+        while (JP % 32 != 8) JP += 8;
+        smem_bytes = ((size_t)M * Qp + (size_t)M * JP) * 4;
+        coeff_scaling = cs;
+        left_shift = 0;
+        if (smem_bytes > 227 * 1024)
+            return fail(SRCDSP_E_SIZE, "M=%d with %d taps needs %zu bytes of shared memory per CTA (> 227 KB)", M, n,
+                        smem_bytes);
+        return SRCDSP_OK;
+    }
+
+    int reset()
+    {
+        if (!d_hist[0]) return SRCDSP_OK;
+        DeviceGuard g(device);
+        SRCDSP_CUDA(cudaMemsetAsync(d_hist[cur], 0, (size_t)C * (H > 0 ? H : 1) * 4, stream));
+        return SRCDSP_OK;
+    }
+
+    int shift_now(unsigned *s) const
+    {
+        const int sh = coeff_scaling - left_shift;
+        if (sh < 0 || sh > 31)
+            return fail(SRCDSP_E_STATE, "coeffScaling - leftShift = %d is outside [0, 31] (undefined in the reference)", sh);
+        *s = (unsigned)sh;
+        return SRCDSP_OK;
+    }
+
+    // mixer == nullptr: plain decimator.  Device pointers only.
+    int step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint32_t *out, size_t out_stride,
+                    MixerBank *mixer);
+
+    void destroy()
+    {
+        DeviceGuard g(device);
+        release();
+        if (d_taps_poly) cudaFree(d_taps_poly);
+        if (d_hist[0]) cudaFree(d_hist[0]);
+        if (d_hist[1]) cudaFree(d_hist[1]);
+    }
+};
+
+template <int MT, bool MIX>
+static int launch_dec(const DecParams &P, int grid, size_t smem, cudaStream_t stream)
+{
+    static thread_local int configured_dev = -1;
+    static thread_local size_t configured_smem = 0;
+    int dev;
+    cudaGetDevice(&dev);
+    if (configured_dev != dev || smem > configured_smem) {
+        SRCDSP_CUDA(cudaFuncSetAttribute(dec_fir_kernel<MT, MIX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024));
+        configured_dev = dev;
+        configured_smem = 227 * 1024;
+    }
+    dec_fir_kernel<MT, MIX><<<grid, DEC_NT, smem, stream>>>(P);
+    SRCDSP_LAUNCH_CHECK();
+    count_launch();
+    return SRCDSP_OK;
+}
+
+template <bool MIX>
+static int launch_dec_m(const DecParams &P, int grid, size_t smem, cudaStream_t stream)
+{
+    switch (P.M) {
+    case 1: return launch_dec<1, MIX>(P, grid, smem, stream);
+    case 2: return launch_dec<2, MIX>(P, grid, smem, stream);
+    case 3: return launch_dec<3, MIX>(P, grid, smem, stream);
+    case 4: return launch_dec<4, MIX>(P, grid, smem, stream);
+    case 5: return launch_dec<5, MIX>(P, grid, smem, stream);
+    case 8: return launch_dec<8, MIX>(P, grid, smem, stream);
+    case 10: return launch_dec<10, MIX>(P, grid, smem, stream);
+    case 16: return launch_dec<16, MIX>(P, grid, smem, stream);
+    case 32: return launch_dec<32, MIX>(P, grid, smem, stream);
+    default: return launch_dec<0, MIX>(P, grid, smem, stream);
+    }
+}
+
+int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint32_t *out, size_t out_stride,
+                         MixerBank *mixer)
+{
+    if (ntaps == 0) return fail(SRCDSP_E_STATE, "decimator has no coefficients (call srcdsp_dec_set_coeffs)");
+    if (n_in % (size_t)M != 0)
+        return fail(SRCDSP_E_SIZE, "n_in (%zu) must be a multiple of M (%d) [dsptl_dnsampling_filters.h:181]", n_in, M);
+    if (n_in == 0) return SRCDSP_OK;
+    DeviceGuard g(device);
+    DecParams P{};
+    SRCDSP_TRY(shift_now(&P.shift));
+    P.in = in;
+    P.out = out;
+    P.in_stride = in_stride;
+    P.out_stride = out_stride;
+    P.n_in = (long long)n_in;
+    P.n_out = (long long)(n_in / (size_t)M);
+    P.M = M;
+    P.ntaps = ntaps;
+    P.Qp = Qp;
+    P.JP = JP;
+    P.taps_poly = d_taps_poly;
+    P.hist_in = d_hist[cur];
+    P.H = H;
+    P.tiles_per_ch = (int)((P.n_out + DEC_TB - 1) / DEC_TB);
+    P.vec_in = aligned16(in, in_stride);
+    P.vec_out = aligned16(out, out_stride);
+    const long long grid = (long long)P.tiles_per_ch * C;
+    if (grid > 0x7fffffffll) return fail(SRCDSP_E_SIZE, "step too large: %lld tiles", grid);
+    dim3 hgrid((unsigned)std::max(1, std::min((H + 255) / 256, 64)), (unsigned)C);
+    if (mixer) {
+        if (mixer->C != C || mixer->device != device)
+            return fail(SRCDSP_E_INVALID, "mixer and decimator banks must have the same channels and device");
+        // the mixer's pending uploads must be ordered on *this* stream
+        cudaStream_t ms = mixer->stream;
+        mixer->stream = stream;
+        int st = mixer->upload_if_dirty();
+        mixer->stream = ms;
+        SRCDSP_TRY(st);
+        P.cs_table = mixer->d_cs;
+        P.phi = mixer->d_phi[mixer->cur];
+        P.freq = mixer->d_freq;
+        P.pm = mixer->pm();
+        SRCDSP_TRY(launch_dec_m<true>(P, (int)grid, smem_bytes, stream));
+        dec_history_kernel<true><<<hgrid, 256, 0, stream>>>(in, in_stride, (long long)n_in, d_hist[cur], d_hist[cur ^ 1],
+                                                            H, mixer->d_cs, mixer->d_phi[mixer->cur],
+                                                            mixer->d_phi[mixer->cur ^ 1], mixer->d_freq, mixer->pm());
+        SRCDSP_LAUNCH_CHECK();
+        count_launch();
+        mixer->advance(n_in);
+    } else {
+        SRCDSP_TRY(launch_dec_m<false>(P, (int)grid, smem_bytes, stream));
+        dec_history_kernel<false><<<hgrid, 256, 0, stream>>>(in, in_stride, (long long)n_in, d_hist[cur],
+                                                             d_hist[cur ^ 1], H, nullptr, nullptr, nullptr, nullptr,
+                                                             PhaseMod{1, 0});
+        SRCDSP_LAUNCH_CHECK();
+        count_launch();
+    }
+    cur ^= 1;
+    return SRCDSP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused DDC chain
+// ---------------------------------------------------------------------------------------------
+struct DdcChain {
+    MixerBank *mixer = nullptr;
+    DecBank *d1 = nullptr, *d2 = nullptr;
+    uint32_t *d_mid = nullptr;  // [C][mid_pitch] stage-1 output when d2 is present
+    size_t mid_cap = 0;
+
+    int step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint32_t *out, size_t out_stride)
+    {
+        const size_t Mt = (size_t)d1->M * (d2 ? (size_t)d2->M : 1);
+        if (n_in % Mt != 0)
+            return fail(SRCDSP_E_SIZE, "n_in (%zu) must be a multiple of the total decimation %zu", n_in, Mt);
+        if (!d2) return d1->step_device(in, in_stride, n_in, out, out_stride, mixer);
+        DeviceGuard g(d1->device);
+        const size_t n_mid = n_in / (size_t)d1->M;
+        const size_t pitch = (n_mid + 3) & ~(size_t)3;
+        if (pitch * d1->C > mid_cap) {
+            SRCDSP_CUDA(cudaStreamSynchronize(d1->stream));
+            if (d_mid) cudaFree(d_mid);
+            d_mid = nullptr;
+            SRCDSP_CUDA(cudaMalloc(&d_mid, pitch * d1->C * 4 + 16));
+            mid_cap = pitch * d1->C;
+        }
+        SRCDSP_TRY(d1->step_device(in, in_stride, n_in, d_mid, pitch, mixer));
+        // stage 2 runs on stage 1's stream so that it is ordered behind it
+        cudaStream_t s2 = d2->stream;
+        d2->stream = d1->stream;
+        int st = d2->step_device(d_mid, pitch, n_mid, out, out_stride, nullptr);
+        d2->stream = s2;
+        return st;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// upsampler bank
+// ---------------------------------------------------------------------------------------------
+struct UpBank : Bank {
+    int L = 1;
+    int ntaps = 0, H = 0, Hp = 0, G = 0;
+    int length = 0, imp_length = 0, left_shift_factor = 0;
+    unsigned long long top = 0;  // the reference's insertion index (only matters across setCoefficients)
+    int32_t *d_taps_poly = nullptr;
+    uint32_t *d_hist[2] = {nullptr, nullptr};  // [C][H] age order, [H-1] newest, [0] stale slot
+    int cur = 0;
+    size_t smem_bytes = 0;
+
+    int set_coefficients(const int32_t *t, int n)
+    {
+        if (!t || n < 1) return fail(SRCDSP_E_SIZE, "taps must not be empty [upsampling_filters.h:110]");
+        if (n % L != 0) return fail(SRCDSP_E_SIZE, "ntaps (%d) must be a multiple of L (%d) [upsampling_filters.h:113]", n, L);
+        DeviceGuard g(device);
+        SRCDSP_CUDA(cudaStreamSynchronize(stream));
+        const int newH = n / L;
+        const int newHp = (newH + UP_HC - 1) / UP_HC * UP_HC;
+        const int HP = newHp + 4;
+        std::vector<int32_t> poly((size_t)L * HP, 0);
+        for (int k = 0; k < n; ++k) poly[(size_t)(k % L) * HP + k / L] = t[k];
+        int len = n;
+        while (len > 0 && t[len - 1] == 0) --len;  // upsampling_filters.h:122-123
+        if (len == 0) return fail(SRCDSP_E_SIZE, "all taps are zero (the reference reads coeff[-1] here)");
+        int32_t *nd = nullptr;
+        SRCDSP_CUDA(cudaMalloc(&nd, poly.size() * 4));
+        SRCDSP_CUDA(cudaMemcpy(nd, poly.data(), poly.size() * 4, cudaMemcpyHostToDevice));
+        if (newH != H) {
+            // buffer.resize(newH) on the RAW circular buffer with `top` unchanged
+            // (upsampling_filters.h:118): rebuild the raw buffer from age order, resize, re-age.
+            std::vector<uint32_t> nh((size_t)C * newH, 0);
+            if (H > 0 && d_hist[cur]) {
+                std::vector<uint32_t> oh((size_t)C * H);
+                SRCDSP_CUDA(cudaMemcpy(oh.data(), d_hist[cur], oh.size() * 4, cudaMemcpyDeviceToHost));
+                const int tp = (int)(top % (unsigned long long)H);
+                if (tp >= newH) {
+                    cudaFree(nd);
+                    return fail(SRCDSP_E_STATE,
+                                "setCoefficients shrinks the buffer below the insertion index (top=%d, new size %d): "
+                                "the reference writes out of bounds here; call reset() first", tp, newH);
+                }
+                std::vector<uint32_t> raw(std::max(H, newH));
+                for (int c = 0; c < C; ++c) {
+                    std::fill(raw.begin(), raw.end(), 0u);
+                    for (int k = 0; k < H; ++k) raw[(tp + k) % H] = oh[(size_t)c * H + k];
+                    for (int k = 0; k < newH; ++k) nh[(size_t)c * newH + k] = raw[(tp + k) % newH];
+                }
+                top = (unsigned long long)tp;
+            }
+            uint32_t *b0 = nullptr, *b1 = nullptr;
+            SRCDSP_CUDA(cudaMalloc(&b0, nh.size() * 4));
+            SRCDSP_CUDA(cudaMalloc(&b1, nh.size() * 4));
+            SRCDSP_CUDA(cudaMemcpy(b0, nh.data(), nh.size() * 4, cudaMemcpyHostToDevice));
+            if (d_hist[0]) cudaFree(d_hist[0]);
+            if (d_hist[1]) cudaFree(d_hist[1]);
+            d_hist[0] = b0;
+            d_hist[1] = b1;
+            cur = 0;
+        }
+        if (d_taps_poly) cudaFree(d_taps_poly);
+        d_taps_poly = nd;
+        ntaps = n;
+        H = newH;
+        Hp = newHp;
+        G = UP_NT / L;
+        length = len;
+        imp_length = n;
+        left_shift_factor = static_cast<int>(round(log2((double)L)));  // upsampling_filters.h:120
+        const int span = G * UP_R * UP_NI;
+        smem_bytes = ((size_t)L * HP + (size_t)span + Hp + 8) * 4;
+        if (smem_bytes > 227 * 1024)
+            return fail(SRCDSP_E_SIZE, "L=%d with %d taps needs %zu bytes of shared memory per CTA", L, n, smem_bytes);
+        return SRCDSP_OK;
+    }
+
+    int reset()
+    {
+        top = 0;
+        if (!d_hist[0]) return SRCDSP_OK;
+        DeviceGuard g(device);
+        SRCDSP_CUDA(cudaMemsetAsync(d_hist[cur], 0, (size_t)C * H * 4, stream));
+        return SRCDSP_OK;
+    }
+
+    int step_device(const uint32_t *in, size_t in_stride, size_t n_in, size_t n_flush, uint32_t *out,
+                    size_t out_stride, int shift_mode)
+    {
+        if (ntaps == 0) return fail(SRCDSP_E_STATE, "upsampler has no coefficients [upsampling_filters.h:155]");
+        const size_t n_tot = n_in + n_flush;
+        if (n_tot == 0) return SRCDSP_OK;
+        DeviceGuard g(device);
+        UpParams P{};
+        const int sh = shift_mode == 0 ? 15 - left_shift_factor : 0;  // :189 vs :244
+        if (sh < 0) return fail(SRCDSP_E_STATE, "15 - round(log2 L) < 0 (undefined in the reference)");
+        P.shift = (unsigned)sh;
+        P.in = in;
+        P.out = out;
+        P.in_stride = in_stride;
+        P.out_stride = out_stride;
+        P.n_in = (long long)n_in;
+        P.n_tot = (long long)n_tot;
+        P.L = L;
+        P.H = H;
+        P.Hp = Hp;
+        P.G = G;
+        P.taps_poly = d_taps_poly;
+        P.hist_in = d_hist[cur];
+        P.vec_in = aligned16(in, in_stride);
+        const int span = G * UP_R * UP_NI;
+        P.tiles_per_ch = (int)((n_tot + span - 1) / span);
+        const long long grid = (long long)P.tiles_per_ch * C;
+        if (grid > 0x7fffffffll) return fail(SRCDSP_E_SIZE, "step too large: %lld tiles", grid);
+        if (smem_bytes > 48 * 1024)
+            SRCDSP_CUDA(cudaFuncSetAttribute(up_fir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        up_fir_kernel<<<(int)grid, UP_NT, smem_bytes, stream>>>(P);
+        SRCDSP_LAUNCH_CHECK();
+        dim3 hgrid((unsigned)std::max(1, std::min((H + 255) / 256, 64)), (unsigned)C);
+        up_history_kernel<<<hgrid, 256, 0, stream>>>(in, in_stride, (long long)n_in, (long long)n_tot, d_hist[cur],
+                                                     d_hist[cur ^ 1], H);
+        SRCDSP_LAUNCH_CHECK();
+        count_launch(2);
+        cur ^= 1;
+        top += n_tot;
+        return SRCDSP_OK;
+    }
+
+    void destroy()
+    {
+        DeviceGuard g(device);
+        release();
+        if (d_taps_poly) cudaFree(d_taps_poly);
+        if (d_hist[0]) cudaFree(d_hist[0]);
+        if (d_hist[1]) cudaFree(d_hist[1]);
+    }
+};
+
+}  // namespace srcdsp
+
+// =============================================================================================
+// extern "C"
+// =============================================================================================
+using namespace srcdsp;
+
+struct srcdsp_mixer_s : MixerBank {};
+struct srcdsp_dec_s : DecBank {};
+struct srcdsp_up_s : UpBank {};
+struct srcdsp_ddc_s : DdcChain {};
+
+#define CHECK_HANDLE(h)                                                   \
+    do {                                                                  \
+        if (!(h)) return fail(SRCDSP_E_INVALID, "%s: null handle", __func__); \
+    } while (0)
+
+extern "C" {
+
+const char *srcdsp_last_error(void) { return last_error_ref().c_str(); }
+int srcdsp_version(void) { return 100; }
+uint64_t srcdsp_launch_count(void) { return g_launches.load(); }
+
+int srcdsp_device_count(int *count)
+{
+    if (!count) return fail(SRCDSP_E_INVALID, "count is null");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *count = 0;
+        return fail(SRCDSP_E_NOGPU, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *count = n;
+    return SRCDSP_OK;
+}
+
+int srcdsp_host_alloc(void **ptr, size_t bytes)
+{
+    if (!ptr) return fail(SRCDSP_E_INVALID, "ptr is null");
+    SRCDSP_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable));
+    return SRCDSP_OK;
+}
+int srcdsp_host_free(void *ptr)
+{
+    SRCDSP_CUDA(cudaFreeHost(ptr));
+    return SRCDSP_OK;
+}
+int srcdsp_device_alloc(int device, void **ptr, size_t bytes)
+{
+    if (!ptr) return fail(SRCDSP_E_INVALID, "ptr is null");
+    SRCDSP_TRY(check_device(device));
+    DeviceGuard g(device);
+    SRCDSP_CUDA(cudaMalloc(ptr, bytes ? bytes : 1));
+    return SRCDSP_OK;
+}
+int srcdsp_device_free(int device, void *ptr)
+{
+    DeviceGuard g(device);
+    SRCDSP_CUDA(cudaFree(ptr));
+    return SRCDSP_OK;
+}
+int srcdsp_memcpy(int device, void *dst, const void *src, size_t bytes)
+{
+    DeviceGuard g(device);
+    SRCDSP_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDefault));
+    return SRCDSP_OK;
+}
+
+int srcdsp_synth_fill(int device, void *stream, int16_t *d_iq, size_t stride, int channels, size_t n_per_ch,
+                      uint32_t seed, uint32_t ch0, uint64_t n0, int amp_shift)
+{
+    SRCDSP_TRY(check_device(device));
+    if (!d_iq || channels < 1 || amp_shift < 0 || amp_shift > 15) return fail(SRCDSP_E_INVALID, "bad synth arguments");
+    if (!is_device_ptr(d_iq)) return fail(SRCDSP_E_INVALID, "srcdsp_synth_fill needs a device pointer");
+    if (n_per_ch == 0) return SRCDSP_OK;
+    DeviceGuard g(device);
+    int bx = (int)std::min<size_t>((n_per_ch + 255) / 256, 1024);
+    synth_kernel<<<dim3(bx, channels), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<uint32_t *>(d_iq), stride, (long long)n_per_ch, seed, ch0, n0, amp_shift);
+    SRCDSP_LAUNCH_CHECK();
+    count_launch();
+    return SRCDSP_OK;
+}
+
+// ---- mixer ------------------------------------------------------------------------------------
+int srcdsp_mixer_create(srcdsp_mixer_t *h, int device, int channels, unsigned n_table)
+{
+    if (!h) return fail(SRCDSP_E_INVALID, "handle pointer is null");
+    *h = nullptr;
+    srcdsp_mixer_s *m = new (std::nothrow) srcdsp_mixer_s();
+    if (!m) return fail(SRCDSP_E_NOMEM, "out of host memory");
+    int st = m->create(device, channels, n_table);
+    if (st != SRCDSP_OK) {
+        m->destroy();
+        delete m;
+        return st;
+    }
+    *h = m;
+    return SRCDSP_OK;
+}
+int srcdsp_mixer_destroy(srcdsp_mixer_t h)
+{
+    if (!h) return SRCDSP_OK;
+    h->destroy();
+    delete h;
+    return SRCDSP_OK;
+}
+static int mixer_for_channels(srcdsp_mixer_t h, int ch, int *c0, int *c1)
+{
+    CHECK_HANDLE(h);
+    if (ch < -1 || ch >= h->C) return fail(SRCDSP_E_INVALID, "channel %d out of range", ch);
+    *c0 = ch < 0 ? 0 : ch;
+    *c1 = ch < 0 ? h->C : ch + 1;
+    return SRCDSP_OK;
+}
+int srcdsp_mixer_set_frequency(srcdsp_mixer_t h, int ch, float lo)
+{
+    int c0, c1;
+    SRCDSP_TRY(mixer_for_channels(h, ch, &c0, &c1));
+    if (!(lo <= 1 && lo >= -1)) return fail(SRCDSP_E_SIZE, "loFreq %g outside [-1, 1] [mixers.h:54]", (double)lo);
+    const int f = MixerBank::quantise(lo, h->n_table);
+    for (int c = c0; c < c1; ++c) {
+        h->h_nominal[c] = lo;
+        h->h_freq[c] = f;
+    }
+    h->dirty = true;
+    return SRCDSP_OK;
+}
+int srcdsp_mixer_set_frequencies(srcdsp_mixer_t h, const float *lo)
+{
+    CHECK_HANDLE(h);
+    if (!lo) return fail(SRCDSP_E_INVALID, "lo_freq is null");
+    for (int c = 0; c < h->C; ++c)
+        if (!(lo[c] <= 1 && lo[c] >= -1)) return fail(SRCDSP_E_SIZE, "loFreq[%d] = %g outside [-1, 1]", c, (double)lo[c]);
+    for (int c = 0; c < h->C; ++c) {
+        h->h_nominal[c] = lo[c];
+        h->h_freq[c] = MixerBank::quantise(lo[c], h->n_table);
+    }
+    h->dirty = true;
+    return SRCDSP_OK;
+}
+int srcdsp_mixer_reset(srcdsp_mixer_t h, int ch, float lo)
+{
+    int c0, c1;
+    SRCDSP_TRY(mixer_for_channels(h, ch, &c0, &c1));
+    if (!(lo <= 1 && lo >= -1)) return fail(SRCDSP_E_SIZE, "loFreq %g outside [-1, 1] [mixers.h:54]", (double)lo);
+    for (int c = c0; c < c1; ++c) h->h_phi[c] = 0;
+    return srcdsp_mixer_set_frequency(h, ch, lo);
+}
+int srcdsp_mixer_adjust_frequency(srcdsp_mixer_t h, int ch, float adjust)
+{
+    int c0, c1;
+    SRCDSP_TRY(mixer_for_channels(h, ch, &c0, &c1));
+    for (int c = c0; c < c1; ++c) {
+        float nf = h->h_nominal[c];  // mixers.h:91-98
+        nf += adjust;
+        if (nf > 1) nf -= 2;
+        if (nf < -1) nf += 2;
+        if (!(nf <= 1 && nf >= -1)) return fail(SRCDSP_E_SIZE, "adjusted frequency %g outside [-1, 1]", (double)nf);
+        h->h_nominal[c] = nf;
+        h->h_freq[c] = MixerBank::quantise(nf, h->n_table);
+    }
+    h->dirty = true;
+    return SRCDSP_OK;
+}
+int srcdsp_mixer_get_state(srcdsp_mixer_t h, int ch, int *phi, int *freq, float *nominal)
+{
+    CHECK_HANDLE(h);
+    if (ch < 0 || ch >= h->C) return fail(SRCDSP_E_INVALID, "channel %d out of range", ch);
+    if (phi) *phi = h->h_phi[ch];
+    if (freq) *freq = h->h_freq[ch];
+    if (nominal) *nominal = h->h_nominal[ch];
+    return SRCDSP_OK;
+}
+int srcdsp_mixer_set_state(srcdsp_mixer_t h, int ch, int phi, int freq, float nominal)
+{
+    CHECK_HANDLE(h);
+    if (ch < 0 || ch >= h->C) return fail(SRCDSP_E_INVALID, "channel %d out of range", ch);
+    if (phi < 0 || phi >= (int)h->n_table || freq < 0 || freq >= (int)h->n_table)
+        return fail(SRCDSP_E_INVALID, "phi/freq must be in [0, n_table)");
+    h->h_phi[ch] = phi;
+    h->h_freq[ch] = freq;
+    h->h_nominal[ch] = nominal;
+    h->dirty = true;
+    return SRCDSP_OK;
+}
+int srcdsp_mixer_step(srcdsp_mixer_t h, const int16_t *in, size_t in_stride, int16_t *out, size_t out_stride,
+                      size_t n)
+{
+    CHECK_HANDLE(h);
+    if (n == 0) return SRCDSP_OK;
+    if (!in || !out) return fail(SRCDSP_E_INVALID, "null buffer");
+    if (h->C > 1 && (in_stride < n || out_stride < n)) return fail(SRCDSP_E_SIZE, "stride smaller than n_per_ch");
+    bool dev;
+    SRCDSP_TRY(classify(in, out, &dev));
+    if (dev)
+        return h->step_device(reinterpret_cast<const uint32_t *>(in), in_stride, reinterpret_cast<uint32_t *>(out),
+                              out_stride, n);
+    return staged_run(*h, in, in_stride, n, out, out_stride, 1, 1, 1, 0,
+                      [&](const uint32_t *di, size_t dis, size_t len, uint32_t *dout, size_t dos, bool) {
+                          return len ? h->step_device(di, dis, dout, dos, len) : SRCDSP_OK;
+                      });
+}
+int srcdsp_mixer_set_stream(srcdsp_mixer_t h, void *s)
+{
+    CHECK_HANDLE(h);
+    return h->set_stream(s);
+}
+int srcdsp_mixer_sync(srcdsp_mixer_t h)
+{
+    CHECK_HANDLE(h);
+    return h->sync();
+}
+
+// ---- decimator --------------------------------------------------------------------------------
+int srcdsp_dec_create(srcdsp_dec_t *h, int device, int channels, int M)
+{
+    if (!h) return fail(SRCDSP_E_INVALID, "handle pointer is null");
+    *h = nullptr;
+    if (M < 1 || M > 4096) return fail(SRCDSP_E_INVALID, "M must be in [1, 4096] (got %d)", M);
+    srcdsp_dec_s *d = new (std::nothrow) srcdsp_dec_s();
+    if (!d) return fail(SRCDSP_E_NOMEM, "out of host memory");
+    int st = d->init(device, channels);
+    if (st != SRCDSP_OK) {
+        delete d;
+        return st;
+    }
+    d->M = M;
+    *h = d;
+    return SRCDSP_OK;
+}
+int srcdsp_dec_destroy(srcdsp_dec_t h)
+{
+    if (!h) return SRCDSP_OK;
+    h->destroy();
+    delete h;
+    return SRCDSP_OK;
+}
+int srcdsp_dec_set_coeffs(srcdsp_dec_t h, const int32_t *taps, int ntaps, int require_multiple_of_m)
+{
+    CHECK_HANDLE(h);
+    return h->set_coeffs(taps, ntaps, require_multiple_of_m);
+}
+int srcdsp_dec_set_left_shift(srcdsp_dec_t h, int s)
+{
+    CHECK_HANDLE(h);
+    h->left_shift = s;
+    return SRCDSP_OK;
+}
+int srcdsp_dec_reset(srcdsp_dec_t h)
+{
+    CHECK_HANDLE(h);
+    return h->reset();
+}
+int srcdsp_dec_get_coeff_scaling(srcdsp_dec_t h, int *cs)
+{
+    CHECK_HANDLE(h);
+    if (!cs) return fail(SRCDSP_E_INVALID, "null pointer");
+    if (h->ntaps == 0) return fail(SRCDSP_E_STATE, "no coefficients");
+    *cs = h->coeff_scaling;
+    return SRCDSP_OK;
+}
+int srcdsp_dec_set_kernel(srcdsp_dec_t h, int kind)
+{
+    CHECK_HANDLE(h);
+    if (kind < 0 || kind > 2) return fail(SRCDSP_E_INVALID, "kernel kind must be 0, 1 or 2");
+    h->kernel_kind = kind;
+    return SRCDSP_OK;
+}
+int srcdsp_dec_step(srcdsp_dec_t h, const int16_t *in, size_t in_stride, size_t n_in, int16_t *out,
+                    size_t out_stride)
+{
+    CHECK_HANDLE(h);
+    if (h->ntaps == 0) return fail(SRCDSP_E_STATE, "decimator has no coefficients (call srcdsp_dec_set_coeffs)");
+    if (n_in % (size_t)h->M != 0)
+        return fail(SRCDSP_E_SIZE, "n_in (%zu) must be a multiple of M (%d) [dsptl_dnsampling_filters.h:181]", n_in, h->M);
+    if (n_in == 0) return SRCDSP_OK;
+    if (!in || !out) return fail(SRCDSP_E_INVALID, "null buffer");
+    if (h->C > 1 && (in_stride < n_in || out_stride < n_in / h->M)) return fail(SRCDSP_E_SIZE, "stride smaller than block");
+    bool dev;
+    SRCDSP_TRY(classify(in, out, &dev));
+    if (dev)
+        return h->step_device(reinterpret_cast<const uint32_t *>(in), in_stride, n_in,
+                              reinterpret_cast<uint32_t *>(out), out_stride, nullptr);
+    return staged_run(*h, in, in_stride, n_in, out, out_stride, (size_t)h->M, 1, (size_t)h->M, 0,
+                      [&](const uint32_t *di, size_t dis, size_t len, uint32_t *dout, size_t dos, bool) {
+                          return h->step_device(di, dis, len, dout, dos, nullptr);
+                      });
+}
+static int hist_io(Bank &b, uint32_t *d_hist, int H, int ch, int16_t *get, const int16_t *set, size_t *n)
+{
+    if (ch < 0 || ch >= b.C) return fail(SRCDSP_E_INVALID, "channel %d out of range", ch);
+    DeviceGuard g(b.device);
+    SRCDSP_CUDA(cudaStreamSynchronize(b.stream));
+    if (get) {
+        if (n) *n = (size_t)H;
+        if (H > 0) SRCDSP_CUDA(cudaMemcpy(get, d_hist + (size_t)ch * H, (size_t)H * 4, cudaMemcpyDeviceToHost));
+    } else {
+        if (!n || *n != (size_t)H) return fail(SRCDSP_E_SIZE, "state must hold exactly %d samples", H);
+        if (H > 0) SRCDSP_CUDA(cudaMemcpy(d_hist + (size_t)ch * H, set, (size_t)H * 4, cudaMemcpyHostToDevice));
+    }
+    return SRCDSP_OK;
+}
+int srcdsp_dec_get_state(srcdsp_dec_t h, int ch, int16_t *hist, size_t *n)
+{
+    CHECK_HANDLE(h);
+    if (h->ntaps == 0) return fail(SRCDSP_E_STATE, "no coefficients");
+    if (!hist) {
+        if (n) *n = (size_t)h->H;
+        return SRCDSP_OK;
+    }
+    return hist_io(*h, h->d_hist[h->cur], h->H, ch, hist, nullptr, n);
+}
+int srcdsp_dec_set_state(srcdsp_dec_t h, int ch, const int16_t *hist, size_t n)
+{
+    CHECK_HANDLE(h);
+    if (h->ntaps == 0) return fail(SRCDSP_E_STATE, "no coefficients");
+    if (!hist && h->H > 0) return fail(SRCDSP_E_INVALID, "null state");
+    return hist_io(*h, h->d_hist[h->cur], h->H, ch, nullptr, hist, &n);
+}
+int srcdsp_dec_set_stream(srcdsp_dec_t h, void *s)
+{
+    CHECK_HANDLE(h);
+    return h->set_stream(s);
+}
+int srcdsp_dec_sync(srcdsp_dec_t h)
+{
+    CHECK_HANDLE(h);
+    return h->sync();
+}
+
+// ---- fused DDC chain ----------------------------------------------------------------------------
+int srcdsp_ddc_create(srcdsp_ddc_t *h, srcdsp_mixer_t mixer, srcdsp_dec_t dec1, srcdsp_dec_t dec2)
+{
+    if (!h) return fail(SRCDSP_E_INVALID, "handle pointer is null");
+    *h = nullptr;
+    if (!dec1) return fail(SRCDSP_E_INVALID, "dec1 is required");
+    if (mixer && (mixer->C != dec1->C || mixer->device != dec1->device))
+        return fail(SRCDSP_E_INVALID, "mixer and dec1 must have the same channels and device");
+    if (dec2 && (dec2->C != dec1->C || dec2->device != dec1->device))
+        return fail(SRCDSP_E_INVALID, "dec1 and dec2 must have the same channels and device");
+    srcdsp_ddc_s *d = new (std::nothrow) srcdsp_ddc_s();
+    if (!d) return fail(SRCDSP_E_NOMEM, "out of host memory");
+    d->mixer = mixer;
+    d->d1 = dec1;
+    d->d2 = dec2;
+    // one stream for the whole chain so that phase / history ping-pong stays ordered
+    if (mixer) mixer->set_stream(dec1->stream);
+    if (dec2) dec2->set_stream(dec1->stream);
+    *h = d;
+    return SRCDSP_OK;
+}
+int srcdsp_ddc_destroy(srcdsp_ddc_t h)
+{
+    if (!h) return SRCDSP_OK;
+    if (h->d_mid) {
+        DeviceGuard g(h->d1->device);
+        cudaStreamSynchronize(h->d1->stream);
+        cudaFree(h->d_mid);
+    }
+    delete h;
+    return SRCDSP_OK;
+}
+int srcdsp_ddc_step(srcdsp_ddc_t h, const int16_t *in, size_t in_stride, size_t n_in, int16_t *out,
+                    size_t out_stride)
+{
+    CHECK_HANDLE(h);
+    const size_t Mt = (size_t)h->d1->M * (h->d2 ? (size_t)h->d2->M : 1);
+    if (h->d1->ntaps == 0 || (h->d2 && h->d2->ntaps == 0)) return fail(SRCDSP_E_STATE, "a decimator has no coefficients");
+    if (n_in % Mt != 0) return fail(SRCDSP_E_SIZE, "n_in (%zu) must be a multiple of the total decimation %zu", n_in, Mt);
+    if (n_in == 0) return SRCDSP_OK;
+    if (!in || !out) return fail(SRCDSP_E_INVALID, "null buffer");
+    if (h->d1->C > 1 && (in_stride < n_in || out_stride < n_in / Mt)) return fail(SRCDSP_E_SIZE, "stride smaller than block");
+    bool dev;
+    SRCDSP_TRY(classify(in, out, &dev));
+    if (dev)
+        return h->step_device(reinterpret_cast<const uint32_t *>(in), in_stride, n_in,
+                              reinterpret_cast<uint32_t *>(out), out_stride);
+    return staged_run(*h->d1, in, in_stride, n_in, out, out_stride, Mt, 1, Mt, 0,
+                      [&](const uint32_t *di, size_t dis, size_t len, uint32_t *dout, size_t dos, bool) {
+                          return h->step_device(di, dis, len, dout, dos);
+                      });
+}
+int srcdsp_ddc_set_stream(srcdsp_ddc_t h, void *s)
+{
+    CHECK_HANDLE(h);
+    SRCDSP_TRY(h->d1->set_stream(s));
+    if (h->mixer) SRCDSP_TRY(h->mixer->set_stream(h->d1->stream));
+    if (h->d2) SRCDSP_TRY(h->d2->set_stream(h->d1->stream));
+    return SRCDSP_OK;
+}
+int srcdsp_ddc_sync(srcdsp_ddc_t h)
+{
+    CHECK_HANDLE(h);
+    return h->d1->sync();
+}
+
+// ---- upsampler ----------------------------------------------------------------------------------
+int srcdsp_up_create(srcdsp_up_t *h, int device, int channels, int L)
+{
+    if (!h) return fail(SRCDSP_E_INVALID, "handle pointer is null");
+    *h = nullptr;
+    if (L < 1 || L > UP_NT) return fail(SRCDSP_E_INVALID, "L must be in [1, %d] (got %d)", UP_NT, L);
+    srcdsp_up_s *u = new (std::nothrow) srcdsp_up_s();
+    if (!u) return fail(SRCDSP_E_NOMEM, "out of host memory");
+    int st = u->init(device, channels);
+    if (st != SRCDSP_OK) {
+        delete u;
+        return st;
+    }
+    u->L = L;
+    *h = u;
+    return SRCDSP_OK;
+}
+int srcdsp_up_destroy(srcdsp_up_t h)
+{
+    if (!h) return SRCDSP_OK;
+    h->destroy();
+    delete h;
+    return SRCDSP_OK;
+}
+int srcdsp_up_set_coefficients(srcdsp_up_t h, const int32_t *taps, int ntaps)
+{
+    CHECK_HANDLE(h);
+    return h->set_coefficients(taps, ntaps);
+}
+int srcdsp_up_reset(srcdsp_up_t h)
+{
+    CHECK_HANDLE(h);
+    return h->reset();
+}
+int srcdsp_up_step(srcdsp_up_t h, const int16_t *in, size_t in_stride, size_t n_in, int16_t *out,
+                   size_t out_stride, int flush, int shift_mode)
+{
+    CHECK_HANDLE(h);
+    if (h->ntaps == 0) return fail(SRCDSP_E_STATE, "upsampler has no coefficients [upsampling_filters.h:155]");
+    if (shift_mode != 0 && shift_mode != 1) return fail(SRCDSP_E_INVALID, "shift_mode must be 0 or 1");
+    const size_t L = (size_t)h->L;
+    const size_t n_flush = flush ? (size_t)h->length / L : 0;  // upsampling_filters.h:199
+    const size_t n_tot = n_in + n_flush;
+    if (n_tot == 0) return SRCDSP_OK;
+    if (!out || (!in && n_in)) return fail(SRCDSP_E_INVALID, "null buffer");
+    if (h->C > 1 && (in_stride < n_in || out_stride < n_tot * L)) return fail(SRCDSP_E_SIZE, "stride smaller than block");
+    bool dev;
+    if (n_in) {
+        SRCDSP_TRY(classify(in, out, &dev));
+    } else {
+        dev = is_device_ptr(out);
+    }
+    if (dev)
+        return h->step_device(reinterpret_cast<const uint32_t *>(in), in_stride, n_in, n_flush,
+                              reinterpret_cast<uint32_t *>(out), out_stride, shift_mode);
+    return staged_run(*h, in, in_stride, n_in, out, out_stride, 1, L, 1, n_flush * L,
+                      [&](const uint32_t *di, size_t dis, size_t len, uint32_t *dout, size_t dos, bool last) {
+                          return h->step_device(di, dis, len, last ? n_flush : 0, dout, dos, shift_mode);
+                      });
+}
+int srcdsp_up_get_length(srcdsp_up_t h, int *v)
+{
+    CHECK_HANDLE(h);
+    if (!v) return fail(SRCDSP_E_INVALID, "null pointer");
+    *v = h->length;
+    return SRCDSP_OK;
+}
+int srcdsp_up_get_imp_length(srcdsp_up_t h, int *v)
+{
+    CHECK_HANDLE(h);
+    if (!v) return fail(SRCDSP_E_INVALID, "null pointer");
+    *v = h->imp_length;
+    return SRCDSP_OK;
+}
+int srcdsp_up_get_ratio(srcdsp_up_t h, int *v)
+{
+    CHECK_HANDLE(h);
+    if (!v) return fail(SRCDSP_E_INVALID, "null pointer");
+    *v = h->L;
+    return SRCDSP_OK;
+}
+// the public state is the H-1 samples the next outputs depend on, oldest first
+int srcdsp_up_get_state(srcdsp_up_t h, int ch, int16_t *hist, size_t *n)
+{
+    CHECK_HANDLE(h);
+    if (h->ntaps == 0) return fail(SRCDSP_E_STATE, "no coefficients");
+    if (!hist) {
+        if (n) *n = (size_t)(h->H - 1);
+        return SRCDSP_OK;
+    }
+    if (ch < 0 || ch >= h->C) return fail(SRCDSP_E_INVALID, "channel %d out of range", ch);
+    DeviceGuard g(h->device);
+    SRCDSP_CUDA(cudaStreamSynchronize(h->stream));
+    if (n) *n = (size_t)(h->H - 1);
+    if (h->H > 1)
+        SRCDSP_CUDA(cudaMemcpy(hist, h->d_hist[h->cur] + (size_t)ch * h->H + 1, (size_t)(h->H - 1) * 4,
+                               cudaMemcpyDeviceToHost));
+    return SRCDSP_OK;
+}
+int srcdsp_up_set_state(srcdsp_up_t h, int ch, const int16_t *hist, size_t n)
+{
+    CHECK_HANDLE(h);
+    if (h->ntaps == 0) return fail(SRCDSP_E_STATE, "no coefficients");
+    if (ch < 0 || ch >= h->C) return fail(SRCDSP_E_INVALID, "channel %d out of range", ch);
+    if (n != (size_t)(h->H - 1)) return fail(SRCDSP_E_SIZE, "state must hold exactly %d samples", h->H - 1);
+    DeviceGuard g(h->device);
+    SRCDSP_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->H > 1)
+        SRCDSP_CUDA(cudaMemcpy(h->d_hist[h->cur] + (size_t)ch * h->H + 1, hist, (size_t)(h->H - 1) * 4,
+                               cudaMemcpyHostToDevice));
+    return SRCDSP_OK;
+}
+int srcdsp_up_set_stream(srcdsp_up_t h, void *s)
+{
+    CHECK_HANDLE(h);
+    return h->set_stream(s);
+}
+int srcdsp_up_sync(srcdsp_up_t h)
+{
+    CHECK_HANDLE(h);
+    return h->sync();
+}
+
+}  // extern "C"

@@ -1,0 +1,111 @@
+// common.cuh -- shared device helpers and host-side error plumbing for libsrcdsp_b200.
+//
+// Arithmetic contract (bit-exact with the reference):
+//   limitScale16  (dsp_complex.cpp:63-73): arithmetic >> then symmetric clamp to +-32767
+//   limitScale<>  (dsp_complex.h:83-108) : arithmetic >> then clamp to [-32768, 32767]
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/srcdsp_b200.h"
+
+namespace srcdsp {
+
+// ---------------------------------------------------------------------------------------------
+// host: thread-local error message + status helpers
+// ---------------------------------------------------------------------------------------------
+std::string &last_error_ref();
+int fail(int code, const char *fmt, ...);
+
+#define SRCDSP_CUDA(expr)                                                                        \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess)                                                                   \
+            return ::srcdsp::fail(SRCDSP_E_CUDA, "%s failed: %s (%s:%d)", #expr,                 \
+                                  cudaGetErrorString(_e), __FILE__, __LINE__);                   \
+    } while (0)
+
+#define SRCDSP_TRY(expr)                 \
+    do {                                 \
+        int _s = (expr);                 \
+        if (_s != SRCDSP_OK) return _s;  \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+// packed sample word: low half = I (re), high half = Q (im), little endian == cs16 in memory
+__device__ __forceinline__ int sx_lo(uint32_t w)
+{
+    int r;
+    // PRMT with sign replication: bytes {b0, b1, sign(b1), sign(b1)}  (ALU pipe, 1 instruction)
+    asm("prmt.b32 %0, %1, 0, 0x9910;" : "=r"(r) : "r"(w));
+    return r;
+}
+__device__ __forceinline__ int sx_hi(uint32_t w) { return ((int)w) >> 16; }
+
+__device__ __forceinline__ uint32_t pack_iq(int re, int im)
+{
+    uint32_t r;
+    // bytes {re.b0, re.b1, im.b0, im.b1}
+    asm("prmt.b32 %0, %1, %2, 0x5410;" : "=r"(r) : "r"(re), "r"(im));
+    return r;
+}
+
+// limitScale16 per component: symmetric clamp
+__device__ __forceinline__ int clamp_sym(int v) { return min(max(v, -32767), 32767); }
+// limitScale<cs16> per component: asymmetric clamp
+__device__ __forceinline__ int clamp_asym(int v) { return min(max(v, -32768), 32767); }
+
+template <bool SYM>
+__device__ __forceinline__ uint32_t scale_pack(int re, int im, unsigned shift)
+{
+    re >>= shift;
+    im >>= shift;
+    if (SYM) {
+        re = clamp_sym(re);
+        im = clamp_sym(im);
+    } else {
+        re = clamp_asym(re);
+        im = clamp_asym(im);
+    }
+    return pack_iq(re, im);
+}
+
+// One NCO mix: mixers.h:175-176.  cs = packed (cos, sin) = (T[(phi + N/4) % N], T[phi]).
+__device__ __forceinline__ uint32_t mix_sample(uint32_t x, uint32_t cs)
+{
+    const int xr = sx_lo(x), xi = sx_hi(x);
+    const int c = sx_lo(cs), s = sx_hi(cs);
+    const int r = xr * c - xi * s;   // dsp_complex.cpp:31-37
+    const int i = xi * c + s * xr;
+    return scale_pack<true>(r, i, 14);
+}
+
+// phase of sample n of a block that started at phase phi0: (phi0 + n * freq) mod N
+struct PhaseMod {
+    unsigned n_table;
+    unsigned mask;  // n_table - 1 when n_table is a power of two, else 0
+    __device__ __forceinline__ unsigned operator()(unsigned v) const
+    {
+        return mask ? (v & mask) : (v % n_table);
+    }
+};
+
+// counter-based synthetic sample (host twin: oracle/srcdsp_oracle.c:orc_hash32)
+__host__ __device__ __forceinline__ uint32_t hash32(uint32_t seed, uint32_t channel, uint64_t n)
+{
+    uint32_t x = seed ^ (channel * 0x9E3779B1u) ^ ((uint32_t)n * 0x85EBCA6Bu) ^
+                 ((uint32_t)(n >> 32) * 0xC2B2AE35u);
+    x ^= x >> 16;
+    x *= 0x7FEB352Du;
+    x ^= x >> 15;
+    x *= 0x846CA68Bu;
+    x ^= x >> 16;
+    return x;
+}
+
+}  // namespace srcdsp

@@ -1,0 +1,217 @@
+// kernels_up.cuh -- batched polyphase interpolating FIR (K4) and the stand-alone NCO mixer.
+//
+// Upsampler: replaces the loop nest of FilterUpsamplingFir::step (upsampling_filters.h:163-194,
+// flush :196-231, iterator overload :252-284):
+//
+//   out[j*L + p] = limitScale<cs16>( sum_{i<H} c[p + i*L] * xx[j - i], shift ),  H = Nt / L,
+//   xx = history ++ x ++ (n_flush zeros)
+//
+// The reference's circular buffer + `top` is kept in AGE ORDER on the device (a[0..H-1],
+// a[H-1] newest, a[0] the stale slot the next insert overwrites); only age order is observable.
+//
+// One thread owns one output phase p and 8 consecutive input positions j (sliding-window reuse
+// of the input in registers, the H taps of its phase in registers); lanes of a warp run over
+// p fastest so that each store instruction writes runs of L consecutive output samples.
+#pragma once
+
+#include "common.cuh"
+
+namespace srcdsp {
+
+constexpr int UP_NT = 128;
+constexpr int UP_R = 8;   // consecutive inputs per thread per iteration
+constexpr int UP_NI = 8;  // iterations per CTA (CTA span = (UP_NT / L) * UP_R * UP_NI inputs)
+constexpr int UP_HC = 8;  // taps per phase per inner iteration
+
+struct UpParams {
+    const uint32_t *in;
+    uint32_t *out;
+    size_t in_stride, out_stride;
+    long long n_in;   // real input samples per channel
+    long long n_tot;  // n_in + n_flush
+    int L;
+    int H;            // taps per phase = Nt / L
+    int Hp;           // H rounded up to a multiple of UP_HC
+    int G;            // j-groups per CTA = UP_NT / L
+    const int32_t *taps_poly;  // [L][Hp + 4]: tp[p][i] = c[p + i*L], zero padded
+    const uint32_t *hist_in;   // [C][H] age order
+    unsigned shift;
+    int tiles_per_ch;
+    int vec_in;
+};
+
+__global__ void __launch_bounds__(UP_NT) up_fir_kernel(const UpParams P)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int L = P.L, Hp = P.Hp, HP = Hp + 4;
+    const int span = P.G * UP_R * UP_NI;     // inputs per CTA
+    int32_t *tp = reinterpret_cast<int32_t *>(smem);  // [L][HP]
+    uint32_t *xs = smem + L * HP;                      // [span + Hp + 8]
+
+    const int tid = threadIdx.x;
+    const int ch = blockIdx.x / P.tiles_per_ch;
+    const int tile = blockIdx.x - ch * P.tiles_per_ch;
+    const long long J0 = (long long)tile * span;
+    const uint32_t *x = P.in + (size_t)ch * P.in_stride;
+    const uint32_t *hist = P.hist_in + (size_t)ch * P.H;
+
+    for (int i = tid; i < L * HP; i += UP_NT) tp[i] = P.taps_poly[i];
+
+    // xs[col] = xx[J0 - Hp + col], col in [0, span + Hp)
+    const int n_cols = span + Hp;
+    const long long n_lo = J0 - Hp;  // multiple of 8: 16-byte aligned when vec_in
+    for (int g = tid; g < (n_cols >> 2); g += UP_NT) {
+        const long long n0 = n_lo + 4ll * g;
+        uint4 q;
+        if (P.vec_in && n0 >= 0 && n0 + 4 <= P.n_in) {
+            q = __ldg(reinterpret_cast<const uint4 *>(x + n0));
+        } else {
+            uint32_t v[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const long long n = n0 + s;
+                uint32_t w = 0;
+                if (n >= 0) {
+                    if (n < P.n_in) w = __ldg(x + n);
+                } else if (n >= -(long long)P.H) {
+                    w = __ldg(hist + (P.H + n));
+                }
+                v[s] = w;
+            }
+            q = make_uint4(v[0], v[1], v[2], v[3]);
+        }
+        reinterpret_cast<uint4 *>(xs)[g] = q;
+    }
+    __syncthreads();
+
+    const int p = tid % L;
+    const int jg = tid / L;
+    if (jg >= P.G) return;
+    const int32_t *tpr = tp + p * HP;
+    uint32_t *o = P.out + (size_t)ch * P.out_stride;
+
+    for (int it = 0; it < UP_NI; ++it) {
+        const int jr = (it * P.G + jg) * UP_R;  // first input (relative to J0) of this thread
+        if (J0 + jr >= P.n_tot) break;
+        int ar[UP_R], ai[UP_R];
+#pragma unroll
+        for (int r = 0; r < UP_R; ++r) ar[r] = ai[r] = 0;
+        for (int i0 = 0; i0 < Hp; i0 += UP_HC) {
+            // sample for (r, u): xx[J0 + jr + r - i0 - u] = xs[jr - i0 - 8 + Hp + (8 + r - u)]
+            const int cb = jr - i0 - 8 + Hp;
+            uint32_t w[16];
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                const uint4 q = *reinterpret_cast<const uint4 *>(xs + cb + 4 * c4);
+                w[4 * c4 + 0] = q.x, w[4 * c4 + 1] = q.y, w[4 * c4 + 2] = q.z, w[4 * c4 + 3] = q.w;
+            }
+            int c[UP_HC];
+            {
+                const int4 c0 = *reinterpret_cast<const int4 *>(tpr + i0);
+                const int4 c1 = *reinterpret_cast<const int4 *>(tpr + i0 + 4);
+                c[0] = c0.x, c[1] = c0.y, c[2] = c0.z, c[3] = c0.w;
+                c[4] = c1.x, c[5] = c1.y, c[6] = c1.z, c[7] = c1.w;
+            }
+            int re[16], im[16];
+#pragma unroll
+            for (int e = 1; e < 16; ++e) {
+                re[e] = sx_lo(w[e]);
+                im[e] = sx_hi(w[e]);
+            }
+#pragma unroll
+            for (int u = 0; u < UP_HC; ++u) {
+#pragma unroll
+                for (int r = 0; r < UP_R; ++r) {
+                    ar[r] += c[u] * re[8 + r - u];
+                    ai[r] += c[u] * im[8 + r - u];
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < UP_R; ++r) {
+            const long long j = J0 + jr + r;
+            if (j < P.n_tot) o[j * L + p] = scale_pack<false>(ar[r], ai[r], P.shift);
+        }
+    }
+}
+
+// New age-ordered history a'[k] = xx[n_tot - H + k], k < H  (xx includes the flush zeros).
+__global__ void up_history_kernel(const uint32_t *__restrict__ in, size_t in_stride, long long n_in,
+                                  long long n_tot, const uint32_t *__restrict__ hist_in,
+                                  uint32_t *__restrict__ hist_out, int H)
+{
+    const int ch = blockIdx.y;
+    const uint32_t *x = in + (size_t)ch * in_stride;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < H; k += gridDim.x * blockDim.x) {
+        const long long n = n_tot - H + k;
+        uint32_t w = 0;
+        if (n >= 0) {
+            if (n < n_in) w = __ldg(x + n);
+        } else {
+            w = hist_in[(size_t)ch * H + (H + n)];
+        }
+        hist_out[(size_t)ch * H + k] = w;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stand-alone mixer: Mixer::step (mixers.h:168-188).  HBM bound: 4 B in + 4 B out per sample.
+// out may alias in (each thread reads its samples before writing them).
+// ---------------------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(256) mixer_kernel(const uint32_t *in, size_t in_stride, uint32_t *out,
+                                                    size_t out_stride, long long n,
+                                                    const uint32_t *__restrict__ cs_table,
+                                                    const int *__restrict__ phi, int *__restrict__ phi_out,
+                                                    const int *__restrict__ freq, PhaseMod pm)
+{
+    const int ch = blockIdx.y;
+    const uint32_t *x = in + (size_t)ch * in_stride;
+    uint32_t *y = out + (size_t)ch * out_stride;
+    const unsigned ph0 = (unsigned)phi[ch], fr = (unsigned)freq[ch];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (VEC) {
+        const long long n4 = n >> 2;
+        for (long long g = t0; g < n4; g += stride) {
+            const uint4 q = reinterpret_cast<const uint4 *>(x)[g];
+            uint32_t v[4] = {q.x, q.y, q.z, q.w};
+            const unsigned nm = pm.mask ? ((unsigned)(4 * g) & pm.mask)
+                                        : (unsigned)((4 * g) % (long long)pm.n_table);
+            const unsigned pb = ph0 + nm * fr;  // < 2^32: nm, fr < n_table <= 32768
+#pragma unroll
+            for (int s = 0; s < 4; ++s) v[s] = mix_sample(v[s], __ldg(cs_table + pm(pb + s * fr)));
+            reinterpret_cast<uint4 *>(y)[g] = make_uint4(v[0], v[1], v[2], v[3]);
+        }
+        for (long long k = (n4 << 2) + t0; k < n; k += stride) {
+            const unsigned nm = pm.mask ? ((unsigned)k & pm.mask) : (unsigned)(k % (long long)pm.n_table);
+            y[k] = mix_sample(x[k], __ldg(cs_table + pm(ph0 + nm * fr)));
+        }
+    } else {
+        for (long long k = t0; k < n; k += stride) {
+            const unsigned nm = pm.mask ? ((unsigned)k & pm.mask) : (unsigned)(k % (long long)pm.n_table);
+            y[k] = mix_sample(x[k], __ldg(cs_table + pm(ph0 + nm * fr)));
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const unsigned nm = (unsigned)(n % (long long)pm.n_table);
+        phi_out[ch] = (int)pm(ph0 + nm * fr);
+    }
+}
+
+// synthetic complex baseband (host twin: oracle/srcdsp_oracle.c:orc_synth_fill)
+__global__ void synth_kernel(uint32_t *out, size_t stride, long long n, uint32_t seed, uint32_t ch0,
+                             unsigned long long n0, int amp_shift)
+{
+    const int ch = blockIdx.y;
+    uint32_t *y = out + (size_t)ch * stride;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += step) {
+        const uint32_t h = hash32(seed, ch0 + ch, n0 + (unsigned long long)k);
+        const int re = ((int)(short)(h & 0xFFFFu)) >> amp_shift;
+        const int im = ((int)(short)(h >> 16)) >> amp_shift;
+        y[k] = pack_iq(re, im);
+    }
+}
+
+}  // namespace srcdsp

@@ -1,0 +1,180 @@
+"""CPU tests of the parity oracle: known answers from the reference, the three
+restatements against each other, against the compiled reference when present, and against the
+committed golden fixtures (generated from the compiled reference)."""
+import numpy as np
+import pytest
+
+import oracle as O
+from cases import load_golden, run_oracle
+
+CASES, GOLD = load_golden()
+
+
+def const_iq(n, re, im):
+    return np.tile(np.array([[re, im]], np.int16), (n, 1))
+
+
+# ---- known-answer tests produced by the compiled reference during the survey ----
+def test_kat_decimator_dc_floor(corc):
+    out, _ = corc.dec_step([100] * 63, 8, const_iq(1024, 1000, -500))
+    assert tuple(out[-1]) == (1538, -770)  # arithmetic shift floors toward -inf
+
+
+def test_kat_decimator_impulse(corc):
+    taps = [10 * (k + 1) for k in range(63)]
+    x = np.zeros((128, 2), np.int16)
+    x[0] = (20000, -20000)
+    out, _ = corc.dec_step(taps, 8, x)
+    exp = [(12, -13), (109, -110), (207, -208), (305, -306), (402, -403), (500, -501), (598, -599), (695, -696), (0, 0)]
+    assert [tuple(v) for v in out[:9]] == exp
+
+
+def test_kat_upsampler_dc(corc):
+    taps = [4096] * 63 + [0]
+    out, _ = corc.up_step(taps, 8, const_iq(64, 1000, -500))
+    last = out[-8:]
+    assert all(tuple(v) == (8000, -4000) for v in last[:7]) and tuple(last[7]) == (7000, -3500)
+    assert corc.up_length(taps) == 63
+    out_it, _ = corc.up_step(taps, 8, const_iq(64, 1000, -500), shift_mode=1)
+    assert tuple(out_it[-8]) == (32767, -32768)  # asymmetric limitScale<> clamp
+    fl, _ = corc.up_step(taps, 8, const_iq(512, 1000, -500), flush=True)
+    assert fl.shape[0] == 4096 + 56
+
+
+def test_kat_mixer(corc):
+    assert corc.mixer_set_frequency(-0.3217) == 3437
+    T = corc.mixer_table()
+    assert (T[1], T[1024], T[3072]) == (25, 16383, -16383)
+    x = np.array([[1, 0], [1000, -500], [-1, 0], [32767, 32767]], np.int16)
+    y, _ = corc.mixer_step(x, 0, 0)
+    assert [tuple(v) for v in y] == [(0, 0), (999, -500), (-1, 0), (32765, 32765)]
+    y, _ = corc.mixer_step(const_iq(5, 16384, 0), 0, corc.mixer_set_frequency(0.5))
+    assert [tuple(v) for v in y] == [(16383, 0), (0, 16383), (-16383, 0), (0, -16383), (16383, 0)]
+    y, _ = corc.mixer_step(const_iq(3, 16384, 0), 0, corc.mixer_set_frequency(-0.5))
+    assert [tuple(v) for v in y] == [(16383, 0), (0, -16383), (-16383, 0)]
+
+
+def test_mixer_frequency_quantisation(corc):
+    for f in [0.0, 1.0, -1.0, 0.5, -0.5, 1e-5, -1e-5, -0.000244, 0.99999, -0.99999, 0.3333, -0.7071]:
+        fr = corc.mixer_set_frequency(f)
+        assert fr == O.np_mixer_set_frequency(f)
+        assert 0 <= fr < 4096
+
+
+# ---- C restatement vs numpy restatement on random full-scale input --------------------------------
+@pytest.mark.parametrize("M,nt", [(8, 63), (16, 255), (4, 1023), (3, 31), (1, 17), (16, 256), (5, 7)])
+def test_c_vs_numpy_decimator(corc, M, nt):
+    rng = np.random.default_rng(M * 1000 + nt)
+    taps = rng.integers(-400, 400, nt).astype(np.int32)
+    h = hn = None
+    for _ in range(3):
+        n = M * int(rng.integers(nt // M + 1, nt // M + 60))
+        x = rng.integers(-32768, 32768, (n, 2)).astype(np.int16)
+        a, h = corc.dec_step(taps, M, x, h, 1)
+        b, hn = O.np_dec_step(taps, M, x, hn, 1)
+        assert np.array_equal(a, b) and np.array_equal(h, hn)
+
+
+def test_decimator_short_blocks_equal_one_block(corc):
+    """Blocks shorter than ntaps-1 (undefined in the reference) behave like one long call."""
+    rng = np.random.default_rng(7)
+    taps = rng.integers(-400, 400, 63).astype(np.int32)
+    x = rng.integers(-32768, 32768, (8 * 40, 2)).astype(np.int16)
+    whole, hw = corc.dec_step(taps, 8, x)
+    parts, h = [], None
+    for b in range(0, x.shape[0], 16):
+        y, h = corc.dec_step(taps, 8, x[b:b + 16], h)
+        parts.append(y)
+    assert np.array_equal(whole, np.concatenate(parts)) and np.array_equal(hw, h)
+
+
+@pytest.mark.parametrize("L,nt", [(8, 64), (8, 128), (3, 30), (2, 8), (1, 5), (16, 64)])
+def test_c_vs_numpy_upsampler(corc, L, nt):
+    rng = np.random.default_rng(L * 1000 + nt)
+    taps = rng.integers(-6000, 6000, nt).astype(np.int32)
+    taps[-1] = 0
+    for sm in (0, 1):
+        h = hn = None
+        for blk in range(3):
+            x = rng.integers(-32768, 32768, (int(rng.integers(1, 200)), 2)).astype(np.int16)
+            a, h = corc.up_step(taps, L, x, h, blk == 2, sm)
+            b, hn = O.np_up_step(taps, L, x, hn, blk == 2, sm)
+            assert np.array_equal(a, b) and np.array_equal(h, hn)
+
+
+def test_c_vs_numpy_mixer_and_synth(corc):
+    x = corc.synth(0x5EED0001, 3, 2**33 + 5, 5000, 0)
+    assert np.array_equal(x, O.np_synth(0x5EED0001, 3, 2**33 + 5, 5000, 0))
+    assert np.array_equal(corc.synth(1, 0, 0, 100, 2), O.np_synth(1, 0, 0, 100, 2))
+    for f in (0.0, -0.3217, 0.5, 0.999):
+        fr = corc.mixer_set_frequency(f)
+        a, pa = corc.mixer_step(x, 17, fr)
+        b, pb = O.np_mixer_step(x, 17, fr)
+        assert np.array_equal(a, b) and pa == pb
+
+
+# ---- restatement vs the compiled reference ------------------------------------------------------
+@pytest.mark.parametrize("M,nt", [(8, 63), (16, 255), (4, 1023), (2, 9), (1, 33), (32, 64)])
+def test_oracle_vs_reference_decimator(corc, reflib, M, nt):
+    rng = np.random.default_rng(nt)
+    taps = rng.integers(-300, 300, nt).astype(np.int32)
+    d = O.RefDecimator(reflib, M, taps)
+    d.setLeftShiftBy2(1)
+    h = None
+    for _ in range(3):
+        n = M * ((nt + int(rng.integers(0, 700))) // M + 1)
+        x = rng.integers(-32768, 32768, (n, 2)).astype(np.int16)
+        y, h = corc.dec_step(taps, M, x, h, 1)
+        assert np.array_equal(d.step(x), y)
+
+
+def test_reference_new_header_asserts_on_taps(reflib):
+    with pytest.raises(ValueError):
+        O.RefDecimator(reflib, 8, [1] * 63, variant=1)  # dsptl_dnsampling_filters.h:122
+    a = O.RefDecimator(reflib, 8, [100] * 64, variant=1).step(const_iq(1024, 1000, -500))
+    b = O.RefDecimator(reflib, 8, [100] * 64, variant=0).step(const_iq(1024, 1000, -500))
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("L,nt", [(8, 64), (8, 128), (3, 30), (16, 64)])
+def test_oracle_vs_reference_upsampler(corc, reflib, L, nt):
+    rng = np.random.default_rng(nt + L)
+    taps = rng.integers(-6000, 6000, nt).astype(np.int32)
+    taps[-2:] = 0
+    for sm in (0, 1):
+        u = O.RefUpsampler(reflib, L, taps)
+        assert u.getLength() == corc.up_length(taps) and u.getImpLength() == nt
+        h = None
+        for blk in range(3):
+            x = rng.integers(-32768, 32768, (int(rng.integers(1, 300)), 2)).astype(np.int16)
+            y, h = corc.up_step(taps, L, x, h, blk == 2, sm)
+            assert np.array_equal(u.step(x, blk == 2, sm), y)
+
+
+def test_oracle_vs_reference_mixer_fir(corc, reflib):
+    rng = np.random.default_rng(5)
+    x = rng.integers(-32768, 32768, (3000, 2)).astype(np.int16)
+    for f in (0.0, 0.5, -0.5, -0.3217, 1.0, -1.0, -1e-5):
+        m = O.RefMixer(reflib)
+        m.setFrequency(f)
+        fr = corc.mixer_set_frequency(f)
+        assert fr == m.freq
+        y, phi = corc.mixer_step(x, 0, fr)
+        assert np.array_equal(m.step(x), y) and phi == m.phi
+    taps = rng.integers(-300, 300, 33).astype(np.int32)
+    fir, h = O.RefFir(reflib, taps), None
+    for _ in range(2):
+        y, h = corc.fir_step(taps, x[:500], h)
+        assert np.array_equal(fir.step(x[:500]), y)
+
+
+# ---- golden fixtures (generated from the compiled reference, tests/golden/make_golden.py) -------
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_oracle_matches_golden(corc, case):
+    assert np.array_equal(run_oracle(case), GOLD[case["name"]])
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_golden_is_current_reference_output(reflib, case):
+    import make_golden as MG
+    assert np.array_equal(MG.run_reference(case), GOLD[case["name"]])

@@ -1,0 +1,123 @@
+"""Host-side multi-GPU logic on CPU: channel sharding and time slicing with halo,
+including a world_size-2 gloo run that checks the sharded result equals the unsharded one."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+import oracle as O
+from srcdsp_b200.sharding import chain_halo, channel_shard, time_slices
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_channel_shard_partitions():
+    for C in (1, 7, 256, 1024, 1000):
+        for W in (1, 2, 3, 4, 8):
+            got = [c for r in range(W) for c in channel_shard(C, W, r)]
+            assert got == list(range(C))
+            sizes = [len(channel_shard(C, W, r)) for r in range(W)]
+            assert max(sizes) - min(sizes) <= 1
+    assert list(channel_shard(1024, 8, 3)) == list(range(384, 512))
+
+
+def test_time_slices_cover_and_align():
+    sl = time_slices(1 << 20, 8, [1023], [4])
+    assert sum(s.length for s in sl) == 1 << 20 and sl[0].warmup == 0
+    for a, b in zip(sl, sl[1:]):
+        assert a.start + a.length == b.start and b.start % 4 == 0 and b.warmup >= 1022 and b.warmup % 4 == 0
+    assert chain_halo([63, 63], [8, 4]) == 62 + 62 * 8
+    sl = time_slices(32 * 1000, 3, [63, 63], [8, 4])
+    assert all(s.start % 32 == 0 and s.length % 32 == 0 and s.warmup % 32 == 0 for s in sl)
+
+
+def _sliced_ddc(corc, x, slices, f, t1, M1, t2, M2):
+    """Each slice is processed independently (as one rank would): warm-up block, then the slice."""
+    outs = []
+    fr = corc.mixer_set_frequency(f)
+    for s in slices:
+        phi = s.nco_phase(0, fr, 4096)
+        h1 = h2 = None
+        lo = s.start - s.warmup
+        if s.warmup:
+            y, phi = corc.mixer_step(x[lo:s.start], phi, fr)
+            y, h1 = corc.dec_step(t1, M1, y, h1)
+            _, h2 = corc.dec_step(t2, M2, y, h2)
+        y, phi = corc.mixer_step(x[s.start:s.start + s.length], phi, fr)
+        y, h1 = corc.dec_step(t1, M1, y, h1)
+        y, h2 = corc.dec_step(t2, M2, y, h2)
+        assert y.shape[0] == s.out_length
+        outs.append(y)
+    return np.concatenate(outs)
+
+
+def test_time_sliced_chain_equals_sequential(corc):
+    """Slicing one long stream with a warm-up halo is bit-exact (the contract the GPU time-slice
+    path relies on), checked on the oracle."""
+    n = 32 * 600
+    x = corc.synth(0x5EED0005, 0, 0, n, 0)
+    t1, t2 = O.design_lowpass_taps(63, 8), O.design_lowpass_taps(63, 4)
+    f = -0.3217
+    whole = _sliced_ddc(corc, x, time_slices(n, 1, [63, 63], [8, 4]), f, t1, 8, t2, 4)
+    for W in (2, 3, 8):
+        assert np.array_equal(_sliced_ddc(corc, x, time_slices(n, W, [63, 63], [8, 4]), f, t1, 8, t2, 4), whole)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    import oracle as OO
+    from srcdsp_b200.sharding import channel_shard as cs
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    C, n, M = 6, 8 * 64, 8
+    taps = OO.design_lowpass_taps(63, 8)
+    c = OO.corc()
+    mine = cs(C, world, rank)
+    chk = 0
+    for ch in mine:  # each rank filters only its own channels: no data-path collective
+        y, _ = c.dec_step(taps, M, c.synth(0x5EED0003, ch, 0, n, 0))
+        chk += int(y.astype(np.int64).sum()) + 31 * ch
+    # the only communication is the measurement plumbing bench.py uses: barrier + max/sum reduce
+    dist.barrier()
+    t = torch.tensor([float(rank + 1)])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    units = torch.tensor([len(mine) * (n // M)], dtype=torch.int64)
+    dist.all_reduce(units, op=dist.ReduceOp.SUM)
+    s = torch.tensor([chk], dtype=torch.int64)
+    dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        q.put((t.item(), units.item(), s.item()))
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_channel_sharding(corc):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    tmax, units, chk = q.get(timeout=120)
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    C, n, M = 6, 8 * 64, 8
+    taps = O.design_lowpass_taps(63, 8)
+    ref = 0
+    for ch in range(C):
+        y, _ = corc.dec_step(taps, M, corc.synth(0x5EED0003, ch, 0, n, 0))
+        ref += int(y.astype(np.int64).sum()) + 31 * ch
+    assert tmax == 2.0 and units == C * (n // M) and chk == ref
