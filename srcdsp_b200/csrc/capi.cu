@@ -127,8 +127,12 @@ struct Bank {
     int set_stream(void *s)
     {
         DeviceGuard g(device);
-        SRCDSP_CUDA(cudaStreamSynchronize(stream));
-        if (own_stream) cudaStreamDestroy(stream);
+        // a borrowed stream may already be gone (e.g. the chain's leader replaced it): only an
+        // owned stream is drained and destroyed here
+        if (own_stream) {
+            SRCDSP_CUDA(cudaStreamSynchronize(stream));
+            cudaStreamDestroy(stream);
+        }
         own_stream = false;
         if (s == nullptr) {
             SRCDSP_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -179,7 +183,9 @@ struct Bank {
     void release()
     {
         DeviceGuard g(device);
-        if (stream) cudaStreamSynchronize(stream);
+        // a borrowed stream may already have been destroyed by its owner; cudaFree below
+        // synchronises the device before releasing memory, so no work can still touch it
+        if (own_stream && stream) cudaStreamSynchronize(stream);
         for (int k = 0; k < NBUF; ++k) {
             if (d_in[k]) cudaFree(d_in[k]);
             if (d_out[k]) cudaFree(d_out[k]);
@@ -388,6 +394,7 @@ struct DecBank : Bank {
     uint32_t *d_hist[2] = {nullptr, nullptr};
     int cur = 0;
     size_t smem_bytes = 0;
+    int nt_threads = DEC_NT;  // threads per CTA of the FIR kernel; tile = 8 * nt_threads outputs
 
     int set_coeffs(const int32_t *t, int n, int require_multiple)
     {
@@ -405,6 +412,23 @@ struct DecBank : Bank {
         const int newH = n - 1;
         const int q = (n + M - 1) / M;
         const int newQp = (q + DEC_QC - 1) / DEC_QC * DEC_QC;
+        // tile size: the largest CTA (128/64/32 threads x 8 outputs) whose polyphase-transposed
+        // tile lets three CTAs share an SM; large M falls back to whatever still fits 227 KB
+        int nthr = 0, newJP = 0;
+        size_t newSmem = 0;
+        for (int pass = 0; pass < 2 && !nthr; ++pass) {
+            for (int cand = DEC_NT; cand >= 32; cand >>= 1) {
+                int jp = (cand * DEC_R + newQp + 7) / 8 * 8;
+                while (jp % 32 != 8) jp += 8;
+                const size_t sm = ((size_t)M * newQp + (size_t)M * jp) * 4;
+                if (sm <= (pass == 0 ? (size_t)72 * 1024 : (size_t)227 * 1024)) {
+                    nthr = cand, newJP = jp, newSmem = sm;
+                    break;
+                }
+            }
+        }
+        if (!nthr)
+            return fail(SRCDSP_E_SIZE, "M=%d with %d taps does not fit the 227 KB shared-memory tile", M, n);
         std::vector<int32_t> poly((size_t)M * newQp, 0);
         for (int k = 0; k < n; ++k) poly[(size_t)(k % M) * newQp + k / M] = t[k];
         int32_t *nd = nullptr;
@@ -434,15 +458,11 @@ struct DecBank : Bank {
         ntaps = n;
         H = newH;
         Qp = newQp;
-        const int Jlen = DEC_TB + Qp;
-        JP = (Jlen + 7) / 8 * 8;
-        while (JP % 32 != 8) JP += 8;
-        smem_bytes = ((size_t)M * Qp + (size_t)M * JP) * 4;
+        JP = newJP;
+        nt_threads = nthr;
+        smem_bytes = newSmem;
         coeff_scaling = cs;
         left_shift = 0;
-        if (smem_bytes > 227 * 1024)
-            return fail(SRCDSP_E_SIZE, "M=%d with %d taps needs %zu bytes of shared memory per CTA (> 227 KB)", M, n,
-                        smem_bytes);
         return SRCDSP_OK;
     }
 
@@ -478,7 +498,7 @@ struct DecBank : Bank {
 };
 
 template <int MT, bool MIX>
-static int launch_dec(const DecParams &P, int grid, size_t smem, cudaStream_t stream)
+static int launch_dec(const DecParams &P, int grid, int threads, size_t smem, cudaStream_t stream)
 {
     static thread_local int configured_dev = -1;
     static thread_local size_t configured_smem = 0;
@@ -490,26 +510,26 @@ static int launch_dec(const DecParams &P, int grid, size_t smem, cudaStream_t st
         configured_dev = dev;
         configured_smem = 227 * 1024;
     }
-    dec_fir_kernel<MT, MIX><<<grid, DEC_NT, smem, stream>>>(P);
+    dec_fir_kernel<MT, MIX><<<grid, threads, smem, stream>>>(P);
     SRCDSP_LAUNCH_CHECK();
     count_launch();
     return SRCDSP_OK;
 }
 
 template <bool MIX>
-static int launch_dec_m(const DecParams &P, int grid, size_t smem, cudaStream_t stream)
+static int launch_dec_m(const DecParams &P, int grid, int threads, size_t smem, cudaStream_t stream)
 {
     switch (P.M) {
-    case 1: return launch_dec<1, MIX>(P, grid, smem, stream);
-    case 2: return launch_dec<2, MIX>(P, grid, smem, stream);
-    case 3: return launch_dec<3, MIX>(P, grid, smem, stream);
-    case 4: return launch_dec<4, MIX>(P, grid, smem, stream);
-    case 5: return launch_dec<5, MIX>(P, grid, smem, stream);
-    case 8: return launch_dec<8, MIX>(P, grid, smem, stream);
-    case 10: return launch_dec<10, MIX>(P, grid, smem, stream);
-    case 16: return launch_dec<16, MIX>(P, grid, smem, stream);
-    case 32: return launch_dec<32, MIX>(P, grid, smem, stream);
-    default: return launch_dec<0, MIX>(P, grid, smem, stream);
+    case 1: return launch_dec<1, MIX>(P, grid, threads, smem, stream);
+    case 2: return launch_dec<2, MIX>(P, grid, threads, smem, stream);
+    case 3: return launch_dec<3, MIX>(P, grid, threads, smem, stream);
+    case 4: return launch_dec<4, MIX>(P, grid, threads, smem, stream);
+    case 5: return launch_dec<5, MIX>(P, grid, threads, smem, stream);
+    case 8: return launch_dec<8, MIX>(P, grid, threads, smem, stream);
+    case 10: return launch_dec<10, MIX>(P, grid, threads, smem, stream);
+    case 16: return launch_dec<16, MIX>(P, grid, threads, smem, stream);
+    case 32: return launch_dec<32, MIX>(P, grid, threads, smem, stream);
+    default: return launch_dec<0, MIX>(P, grid, threads, smem, stream);
     }
 }
 
@@ -536,7 +556,8 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
     P.taps_poly = d_taps_poly;
     P.hist_in = d_hist[cur];
     P.H = H;
-    P.tiles_per_ch = (int)((P.n_out + DEC_TB - 1) / DEC_TB);
+    const int TB = nt_threads * DEC_R;
+    P.tiles_per_ch = (int)((P.n_out + TB - 1) / TB);
     P.vec_in = aligned16(in, in_stride);
     P.vec_out = aligned16(out, out_stride);
     const long long grid = (long long)P.tiles_per_ch * C;
@@ -555,7 +576,7 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
         P.phi = mixer->d_phi[mixer->cur];
         P.freq = mixer->d_freq;
         P.pm = mixer->pm();
-        SRCDSP_TRY(launch_dec_m<true>(P, (int)grid, smem_bytes, stream));
+        SRCDSP_TRY(launch_dec_m<true>(P, (int)grid, nt_threads, smem_bytes, stream));
         dec_history_kernel<true><<<hgrid, 256, 0, stream>>>(in, in_stride, (long long)n_in, d_hist[cur], d_hist[cur ^ 1],
                                                             H, mixer->d_cs, mixer->d_phi[mixer->cur],
                                                             mixer->d_phi[mixer->cur ^ 1], mixer->d_freq, mixer->pm());
@@ -563,7 +584,7 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
         count_launch();
         mixer->advance(n_in);
     } else {
-        SRCDSP_TRY(launch_dec_m<false>(P, (int)grid, smem_bytes, stream));
+        SRCDSP_TRY(launch_dec_m<false>(P, (int)grid, nt_threads, smem_bytes, stream));
         dec_history_kernel<false><<<hgrid, 256, 0, stream>>>(in, in_stride, (long long)n_in, d_hist[cur],
                                                              d_hist[cur ^ 1], H, nullptr, nullptr, nullptr, nullptr,
                                                              PhaseMod{1, 0});
@@ -968,7 +989,7 @@ int srcdsp_dec_create(srcdsp_dec_t *h, int device, int channels, int M)
 {
     if (!h) return fail(SRCDSP_E_INVALID, "handle pointer is null");
     *h = nullptr;
-    if (M < 1 || M > 4096) return fail(SRCDSP_E_INVALID, "M must be in [1, 4096] (got %d)", M);
+    if (M < 1 || M > 1024) return fail(SRCDSP_E_INVALID, "M must be in [1, 1024] (got %d)", M);
     srcdsp_dec_s *d = new (std::nothrow) srcdsp_dec_s();
     if (!d) return fail(SRCDSP_E_NOMEM, "out of host memory");
     int st = d->init(device, channels);

@@ -25,10 +25,10 @@
 
 namespace srcdsp {
 
-constexpr int DEC_NT = 128;  // threads per CTA
+constexpr int DEC_NT = 128;  // max threads per CTA (blockDim.x is 128, 64 or 32: large M shrinks the tile)
 constexpr int DEC_R = 8;     // consecutive outputs per thread
 constexpr int DEC_QC = 8;    // taps per polyphase branch handled per inner iteration
-constexpr int DEC_TB = DEC_NT * DEC_R;
+constexpr int DEC_FB = 8;    // independent 16-byte loads in flight per thread while staging a tile
 
 struct DecParams {
     const uint32_t *in;      // [C][in_stride] packed cs16
@@ -70,19 +70,21 @@ __global__ void __launch_bounds__(DEC_NT) dec_fir_kernel(const DecParams P)
     uint32_t *xp = smem + M * Qp;                     // [M][JP]
 
     const int tid = threadIdx.x;
+    const int NT = blockDim.x;
+    const int TB = NT * DEC_R;  // outputs per tile
     const int ch = blockIdx.x / P.tiles_per_ch;
     const int tile = blockIdx.x - ch * P.tiles_per_ch;
-    const long long I0 = (long long)tile * DEC_TB;  // first output of the tile
+    const long long I0 = (long long)tile * TB;  // first output of the tile
     const uint32_t *x = P.in + (size_t)ch * P.in_stride;
     const uint32_t *hist = P.hist_in + (size_t)ch * P.H;
 
     // ---- stage taps --------------------------------------------------------------------------
-    for (int i = tid; i < M * Qp; i += DEC_NT) tp[i] = P.taps_poly[i];
+    for (int i = tid; i < M * Qp; i += NT) tp[i] = P.taps_poly[i];
 
     // ---- stage the input tile, polyphase transposed (+ fused NCO mix) -------------------------
     // column j_rel of row p holds sample n = (j_lo + j_rel)*M - p, j_lo = I0 - Qp.
     // The tile covers u = n - n_base in [0, Jlen*M), n_base = j_lo*M - (M-1).
-    const int Jlen = DEC_TB + Qp;
+    const int Jlen = TB + Qp;
     const long long n_base = (I0 - Qp) * M - (M - 1);
     // groups of 4 consecutive samples; g0 keeps the global address 16-byte aligned
     const int mis = (int)(((n_base % 4) + 4) % 4);  // n_base - mis is a multiple of 4
@@ -99,45 +101,60 @@ __global__ void __launch_bounds__(DEC_NT) dec_fir_kernel(const DecParams P)
         phi_base = (unsigned)(((unsigned long long)P.phi[ch] + (unsigned long long)nbm * fr) % nt);
     }
 
-    for (int g = tid; g < n_groups; g += DEC_NT) {
-        const long long n0 = n_base - mis + 4ll * g;
-        uint32_t v[4];
-        if (P.vec_in && n0 >= 0 && n0 + 4 <= P.n_in) {
-            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(x + n0));
-            v[0] = q.x, v[1] = q.y, v[2] = q.z, v[3] = q.w;
-            if (MIX) {
+    // Loads are issued in batches of DEC_FB independent 16-byte requests per thread before any of
+    // them is consumed, so that one DRAM round trip is paid per batch, not per group.
+    for (int gb = tid; gb < n_groups; gb += NT * DEC_FB) {
+        uint4 q[DEC_FB];
+        bool fast[DEC_FB];
 #pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    const unsigned ph = P.pm(phi_base + (unsigned)(4 * g + s) * fr);
-                    v[s] = mix_sample(v[s], __ldg(P.cs_table + ph));
-                }
-            }
-        } else {
-#pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                const long long n = n0 + s;
-                uint32_t w = 0;
-                if (n >= 0) {
-                    if (n < P.n_in) {
-                        w = __ldg(x + n);
-                        if (MIX) {
-                            const unsigned ph = P.pm(phi_base + (unsigned)(4 * g + s) * fr);
-                            w = mix_sample(w, __ldg(P.cs_table + ph));
-                        }
-                    }
-                } else if (n >= -(long long)P.H) {
-                    w = __ldg(hist + (P.H + n));  // already mixed when it was input
-                }
-                v[s] = w;
-            }
+        for (int k = 0; k < DEC_FB; ++k) {
+            const int g = gb + k * NT;
+            const long long n0 = n_base - mis + 4ll * g;
+            fast[k] = P.vec_in && g < n_groups && n0 >= 0 && n0 + 4 <= P.n_in;
+            if (fast[k]) q[k] = __ldg(reinterpret_cast<const uint4 *>(x + n0));
         }
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            const int u = 4 * g + s - mis;
-            if (u >= 0 && u < Jlen * M) {
-                const int j = u / M;
-                const int p = M - 1 - (u - j * M);
-                xp[p * JP + swz_col(j)] = v[s];
+        for (int k = 0; k < DEC_FB; ++k) {
+            const int g = gb + k * NT;
+            if (g >= n_groups) break;
+            const long long n0 = n_base - mis + 4ll * g;
+            uint32_t v[4];
+            if (fast[k]) {
+                v[0] = q[k].x, v[1] = q[k].y, v[2] = q[k].z, v[3] = q[k].w;
+                if (MIX) {
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        const unsigned ph = P.pm(phi_base + (unsigned)(4 * g + s) * fr);
+                        v[s] = mix_sample(v[s], __ldg(P.cs_table + ph));
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const long long n = n0 + s;
+                    uint32_t w = 0;
+                    if (n >= 0) {
+                        if (n < P.n_in) {
+                            w = __ldg(x + n);
+                            if (MIX) {
+                                const unsigned ph = P.pm(phi_base + (unsigned)(4 * g + s) * fr);
+                                w = mix_sample(w, __ldg(P.cs_table + ph));
+                            }
+                        }
+                    } else if (n >= -(long long)P.H) {
+                        w = __ldg(hist + (P.H + n));  // already mixed when it was input
+                    }
+                    v[s] = w;
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const int u = 4 * g + s - mis;
+                if (u >= 0 && u < Jlen * M) {
+                    const int j = u / M;
+                    const int p = M - 1 - (u - j * M);
+                    xp[p * JP + swz_col(j)] = v[s];
+                }
             }
         }
     }
