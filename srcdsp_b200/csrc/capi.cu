@@ -16,6 +16,7 @@
 
 #include "common.cuh"
 #include "kernels_dec.cuh"
+#include "kernels_dec_tc.cuh"
 #include "kernels_up.cuh"
 
 namespace srcdsp {
@@ -395,6 +396,16 @@ struct DecBank : Bank {
     int cur = 0;
     size_t smem_bytes = 0;
     int nt_threads = DEC_NT;  // threads per CTA of the FIR kernel; tile = 8 * nt_threads outputs
+    // tcgen05 int8 Toeplitz path (kernels_dec_tc.cuh)
+    bool tc_ok = false;
+    const char *tc_why = "no coefficients";
+    TcParams tc{};
+    uint8_t *d_master = nullptr;
+    int *d_error = nullptr;
+    size_t tc_smem = 0;
+    int sm_count = 148;
+
+    int prepare_tc();
 
     int set_coeffs(const int32_t *t, int n, int require_multiple)
     {
@@ -463,7 +474,7 @@ struct DecBank : Bank {
         smem_bytes = newSmem;
         coeff_scaling = cs;
         left_shift = 0;
-        return SRCDSP_OK;
+        return prepare_tc();
     }
 
     int reset()
@@ -494,8 +505,108 @@ struct DecBank : Bank {
         if (d_taps_poly) cudaFree(d_taps_poly);
         if (d_hist[0]) cudaFree(d_hist[0]);
         if (d_hist[1]) cudaFree(d_hist[1]);
+        if (d_master) cudaFree(d_master);
+        if (d_error) cudaFree(d_error);
     }
 };
+
+// Builds the resident Toeplitz "master" operand and the per-K-step table of the tensor-core
+// kernel (see kernels_dec_tc.cuh for the layout).  Sets tc_ok = false (with a reason) when the
+// taps / ratio do not fit it; the IMAD kernel then handles every case.
+int DecBank::prepare_tc()
+{
+    tc_ok = false;
+    if (d_master) {
+        cudaFree(d_master);
+        d_master = nullptr;
+    }
+    if (M > TC_MAX_KSTEPS) { tc_why = "M > 64"; return SRCDSP_OK; }
+    // signed base-256 digits of every tap: c = sum_pl 256^pl * d_pl, d_pl in [-128, 127]
+    int P = 1;
+    std::vector<std::vector<int8_t>> dig(4, std::vector<int8_t>(ntaps, 0));
+    for (int k = 0; k < ntaps; ++k) {
+        long long c = taps[k];
+        for (int pl = 0; pl < 4; ++pl) {
+            long long d = ((c + 128) & 255) - 128;
+            dig[pl][k] = (int8_t)d;
+            c = (c - d) / 256;
+            if (d != 0 && pl + 1 > P) P = pl + 1;
+        }
+        if (c != 0) P = 5;
+    }
+    if (P > 3) { tc_why = "taps need more than 3 signed byte digits (|c| >= 2^23)"; return SRCDSP_OK; }
+    const int G = 32 * M;
+    const int J = 1 + (ntaps - 1 + G - 1) / G;
+    if (J > TC_MAX_J) { tc_why = "filter spans more than 16 row-blocks"; return SRCDSP_OK; }
+    // residues r = (32 * kc) mod M, one master per distinct residue
+    std::vector<int> res_of_kc(M), res_list;
+    for (int kc = 0; kc < M; ++kc) {
+        const int r = (32 * kc) % M;
+        int idx = -1;
+        for (size_t i = 0; i < res_list.size(); ++i)
+            if (res_list[i] == r) idx = (int)i;
+        if (idx < 0) {
+            idx = (int)res_list.size();
+            res_list.push_back(r);
+        }
+        res_of_kc[kc] = idx;
+    }
+    const int a_rows = 128 * J + 136;
+    const size_t master_bytes = res_list.size() * (size_t)a_rows * 32;
+    const int rbp = 2 * (TC_NRB + J - 1) + 1;
+    const size_t smem = ((master_bytes + 127) & ~(size_t)127) + (size_t)TC_STAGES * 64 * rbp + 256;
+    if (smem > 227 * 1024) { tc_why = "Toeplitz master + stages exceed 227 KB of shared memory"; return SRCDSP_OK; }
+    std::vector<uint8_t> img(master_bytes, 0);
+    for (size_t ri = 0; ri < res_list.size(); ++ri) {
+        uint8_t *base = img.data() + ri * (size_t)a_rows * 32;
+        for (int row = 4; row < a_rows; ++row) {
+            const int u = (row - 4) / 4 - 32, w = (row - 4) % 4;
+            if (w >= P) continue;
+            for (int t = 0; t < 32; ++t) {
+                const long long k = (long long)M * u - t - res_list[ri];
+                if (k < 0 || k >= ntaps) continue;
+                // SWIZZLE_NONE K-major image: [kc = t / 16][row][t % 16]
+                base[(size_t)(t / 16) * a_rows * 16 + (size_t)row * 16 + (t % 16)] = (uint8_t)dig[w][k];
+            }
+        }
+    }
+    DeviceGuard g(device);
+    SRCDSP_CUDA(cudaMalloc(&d_master, master_bytes));
+    SRCDSP_CUDA(cudaMemcpy(d_master, img.data(), master_bytes, cudaMemcpyHostToDevice));
+    if (!d_error) {
+        SRCDSP_CUDA(cudaMalloc(&d_error, sizeof(int)));
+        SRCDSP_CUDA(cudaMemset(d_error, 0, sizeof(int)));
+    }
+    tc = TcParams{};
+    tc.M = M;
+    tc.G = G;
+    tc.J = J;
+    tc.master = d_master;
+    tc.master_bytes = (int)master_bytes;
+    tc.a_rows = a_rows;
+    tc.rbp = rbp;
+    tc.error_flag = d_error;
+    for (int kc = 0; kc < M; ++kc) {
+        const int a = (32 * kc) / M, r = (32 * kc) % M;
+        TcKstep &ks = tc.ks[kc];
+        ks.a_row = 4 * (32 - a) + 4;
+        ks.res_off = res_of_kc[kc] * a_rows * 32;
+        ks.jmask = 0;
+        for (int j = 0; j < J; ++j) {
+            const long long kmax = (long long)M * (31 + 32 * j - a) - r;
+            const long long kmin = (long long)M * (32 * j - a) - r - 31;
+            if (kmax >= 0 && kmin <= ntaps - 1) ks.jmask |= 1u << j;
+        }
+    }
+    tc_smem = smem;
+    cudaDeviceProp prop;
+    SRCDSP_CUDA(cudaGetDeviceProperties(&prop, device));
+    sm_count = prop.multiProcessorCount;
+    SRCDSP_CUDA(cudaFuncSetAttribute(dec_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
+    tc_ok = true;
+    tc_why = "";
+    return SRCDSP_OK;
+}
 
 template <int MT, bool MIX>
 static int launch_dec(const DecParams &P, int grid, int threads, size_t smem, cudaStream_t stream)
@@ -584,7 +695,33 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
         count_launch();
         mixer->advance(n_in);
     } else {
-        SRCDSP_TRY(launch_dec_m<false>(P, (int)grid, nt_threads, smem_bytes, stream));
+        // kernel choice: the tcgen05 Toeplitz kernel when the taps fit it and there are enough
+        // 4096-output tiles to occupy the machine; the IMAD kernel otherwise
+        const long long tc_tiles = (long long)C * ((P.n_out + TC_NRB * TC_BOUT - 1) / (TC_NRB * TC_BOUT));
+        bool use_tc = tc_ok && (kernel_kind == 2 || (kernel_kind == 0 && tc_tiles >= sm_count / 2));
+        if (kernel_kind == 2 && !tc_ok)
+            return fail(SRCDSP_E_STATE, "tcgen05 kernel forced but not applicable: %s", tc_why);
+        if (use_tc) {
+            TcParams T = tc;
+            T.in = in;
+            T.out = out;
+            T.in_stride = in_stride;
+            T.out_stride = out_stride;
+            T.n_in = P.n_in;
+            T.n_out = P.n_out;
+            T.tiles_per_ch = (int)(tc_tiles / C);
+            T.total_tiles = tc_tiles;
+            T.hist_in = d_hist[cur];
+            T.H = H;
+            T.shift = P.shift;
+            T.vec_in = P.vec_in;
+            const int tgrid = (int)std::min<long long>(tc_tiles, sm_count);
+            dec_tc_kernel<<<tgrid, TC_THREADS, tc_smem, stream>>>(T);
+            SRCDSP_LAUNCH_CHECK();
+            count_launch();
+        } else {
+            SRCDSP_TRY(launch_dec_m<false>(P, (int)grid, nt_threads, smem_bytes, stream));
+        }
         dec_history_kernel<false><<<hgrid, 256, 0, stream>>>(in, in_stride, (long long)n_in, d_hist[cur],
                                                              d_hist[cur ^ 1], H, nullptr, nullptr, nullptr, nullptr,
                                                              PhaseMod{1, 0});

@@ -1,0 +1,432 @@
+// kernels_dec_tc.cuh -- polyphase decimating FIR as an EXACT int8 Toeplitz GEMM on the 5th-gen
+// tensor cores (tcgen05.mma kind::i8, accumulators in TMEM).  Same contract as dec_fir_kernel:
+//
+//   out[i] = limitScale16( sum_{k<Nt} c[k] * xx[i*M - k], shift )      (bit-exact, mod 2^32)
+//
+// Why: the INT32 multiply pipe caps the CUDA-core kernel at 2*Nt IMAD per output (36.5 G out/s for
+// /16, 255 taps); the same sum split into byte planes is an int8 GEMM that the
+// tensor cores finish fast enough for HBM to become the limit.
+//
+// Decomposition (all exact):
+//   sample component v (int16)  = 256 * hi + lo,   hi = v >> 8 (s8),  lo = v & 255 (u8)
+//   tap c[k]                    = sum_{pl<P} 256^pl * d_pl[k],  d_pl in [-128,127] (signed digits)
+//   sum_k c[k] v[.]             = sum_w 256^w * D_w,   D_w = sum_{pl+sp=w} sum_k d_pl[k] * plane_sp[.]
+//
+// GEMM shape per tile (one channel, 128 row-blocks of G = 32*M samples, 4096 outputs):
+//   D[rho, n] += A[rho, t] * B[n, t]          M=128 rows, N=256 columns, K=32 bytes per MMA
+//   B (samples): row n = (row-block m, component re/im), K = 32 consecutive samples of one byte
+//       plane -> SWIZZLE_NONE K-major, rows linear at 16-byte pitch, so the operand for "lag j"
+//       (previous row-blocks) is the same shared-memory tile with the start address moved back
+//       by 2*j rows.
+//   A (taps):   row rho = 4*b + w (output b of the row-block, weight slot w), one resident
+//       "master" Toeplitz matrix T[4u + w, t] = d_w[M*u - t - r]; every (K-step, lag) operand is
+//       the master with the start address moved by 4*(32*j - a) rows, and the operand for the hi
+//       byte plane is the same moved back by ONE row (weight slot w -> w+1).
+//   (the linear-address behaviour of SWIZZLE_NONE descriptors is checked by tools/umma_probe.cu)
+//
+// Warp roles (448 threads, 1 CTA / SM, persistent over tiles):
+//   warps 0-3  epilogue: tcgen05.ld 32x32b, combine the 4 weight slots with 2 shuffles,
+//              >> shift, symmetric clamp, pack, store
+//   warp  4    TMEM alloc + single-thread MMA issue, tcgen05.commit -> mbarriers
+//   warp  5    halo producer (the J-1 row-blocks in front of the tile)
+//   warps 6-13 producers: LDG.128 (coalesced) -> PRMT byte-plane split -> STS.128 into the stage
+#pragma once
+
+#include "common.cuh"
+
+namespace srcdsp {
+
+constexpr int TC_NRB = 128;              // row-blocks per tile (MMA N = 2 * NRB)
+constexpr int TC_BOUT = 32;              // outputs per row-block
+constexpr int TC_THREADS = 448;
+constexpr int TC_PROD_WARP0 = 6;         // first main producer warp
+constexpr int TC_NPROD = 256;            // main producer threads
+constexpr int TC_STAGES = 6;
+constexpr int TC_MAX_KSTEPS = 64;        // M <= 64
+constexpr int TC_MAX_J = 16;
+constexpr int TC_PREFETCH = 2;           // K-steps a producer thread loads ahead of the one it stores
+
+struct TcKstep {
+    int a_row;        // master row of (b = 0, w = 0) for lag 0:  4 * (32 - a) + 4 guard rows
+    int res_off;      // byte offset of the residue's master inside the A region
+    unsigned jmask;   // bit j set: lag j contributes
+};
+
+struct TcParams {
+    const uint32_t *in;
+    uint32_t *out;
+    size_t in_stride, out_stride;
+    long long n_in, n_out;
+    int M;            // decimation ratio == K-steps per row-block
+    int G;            // 32 * M samples per row-block
+    int J;            // lags: 1 + ceil((Nt-1)/G)
+    int tiles_per_ch;
+    long long total_tiles;
+    const uint8_t *master;   // device image of the A region
+    int master_bytes;
+    int a_rows;              // rows per (residue, kc) chunk  -> LBO_A = a_rows * 16
+    int rbp;                 // padded rows per (plane, kc) chunk of a stage (odd) -> LBO_B = rbp * 16
+    const uint32_t *hist_in;
+    int H;
+    unsigned shift;
+    int vec_in;
+    int *error_flag;
+    TcKstep ks[TC_MAX_KSTEPS];
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded spin: a protocol bug must surface as an error, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int *error_flag)
+{
+    uint32_t done = 0;
+    long long t0 = 0;
+    for (uint32_t spins = 0; !done; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!done && (spins & 1023) == 1023) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > 4000000000ll) {  // ~2 s
+                if (error_flag) atomicExch(error_flag, 1);
+                __trap();
+            }
+        }
+    }
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes)
+{
+    // SWIZZLE_NONE, K-major: start >> 4 | LBO >> 4 << 16 | SBO(128 B) >> 4 << 32 | version 1 << 46
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ uint32_t umma_idesc_i8(int a_signed, int b_signed, int m, int n)
+{
+    // c_format S32 (2) @4, a_format @7, b_format @10 (0 = u8, 1 = s8), K-major both, N>>3 @17, M>>4 @24
+    return (2u << 4) | ((uint32_t)a_signed << 7) | ((uint32_t)b_signed << 10) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+
+// 16 consecutive samples (4 x uint4, bytes re_lo re_hi im_lo im_hi per sample) -> 4 byte planes
+__device__ __forceinline__ void split_planes(const uint4 (&q)[4], uint4 &re_lo, uint4 &re_hi, uint4 &im_lo, uint4 &im_hi)
+{
+    uint32_t o[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t w0 = q[i].x, w1 = q[i].y, w2 = q[i].z, w3 = q[i].w;
+        const uint32_t a = prmt(w0, w1, 0x5140);  // {w0.b0, w1.b0, w0.b1, w1.b1} = re_lo x2, re_hi x2
+        const uint32_t b = prmt(w2, w3, 0x5140);
+        const uint32_t c = prmt(w0, w1, 0x7362);  // {w0.b2, w1.b2, w0.b3, w1.b3} = im_lo x2, im_hi x2
+        const uint32_t d = prmt(w2, w3, 0x7362);
+        o[0][i] = prmt(a, b, 0x5410);  // re_lo of 4 samples
+        o[1][i] = prmt(a, b, 0x7632);  // re_hi
+        o[2][i] = prmt(c, d, 0x5410);  // im_lo
+        o[3][i] = prmt(c, d, 0x7632);  // im_hi
+    }
+    re_lo = make_uint4(o[0][0], o[0][1], o[0][2], o[0][3]);
+    re_hi = make_uint4(o[1][0], o[1][1], o[1][2], o[1][3]);
+    im_lo = make_uint4(o[2][0], o[2][1], o[2][2], o[2][3]);
+    im_hi = make_uint4(o[3][0], o[3][1], o[3][2], o[3][3]);
+}
+
+// generic sample fetch: history for n < 0, zero outside [−H, n_in)
+__device__ __forceinline__ uint32_t tc_sample(const uint32_t *x, const uint32_t *hist, int H, long long n_in, long long n)
+{
+    if (n >= 0) return n < n_in ? __ldg(x + n) : 0u;
+    return n >= -(long long)H ? __ldg(hist + (H + n)) : 0u;
+}
+
+struct TcTask {
+    uint4 q[4];
+    bool fast;
+};
+
+__device__ __forceinline__ void tc_task_load(TcTask &t, const TcParams &P, const uint32_t *x, const uint32_t *hist,
+                                             long long n0)
+{
+    t.fast = P.vec_in && n0 >= 0 && n0 + 16 <= P.n_in;
+    if (t.fast) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(x + n0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t.q[i] = __ldg(p + i);
+    }
+}
+
+__device__ __forceinline__ void tc_task_store(TcTask &t, const TcParams &P, const uint32_t *x, const uint32_t *hist,
+                                              long long n0, uint8_t *stage, int row_re, int half)
+{
+    if (!t.fast) {
+        uint32_t v[16];
+#pragma unroll
+        for (int s = 0; s < 16; ++s) v[s] = tc_sample(x, hist, P.H, P.n_in, n0 + s);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t.q[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
+    uint4 re_lo, re_hi, im_lo, im_hi;
+    split_planes(t.q, re_lo, re_hi, im_lo, im_hi);
+    const int chunk = P.rbp * 16;             // bytes per (plane, kc) chunk
+    uint8_t *lo = stage + half * chunk + row_re * 16;
+    uint8_t *hi = lo + 2 * chunk;
+    *reinterpret_cast<uint4 *>(lo) = re_lo;
+    *reinterpret_cast<uint4 *>(lo + 16) = im_lo;
+    *reinterpret_cast<uint4 *>(hi) = re_hi;
+    *reinterpret_cast<uint4 *>(hi + 16) = im_hi;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_constant__ TcParams P)
+{
+    extern __shared__ __align__(128) uint8_t tc_smem_raw[];
+    uint8_t *smem = tc_smem_raw;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int J = P.J;
+    const int stage_bytes = 4 * P.rbp * 16;  // 2 planes x 2 kc chunks
+    uint8_t *a_smem = smem;
+    uint8_t *stages = smem + ((P.master_bytes + 127) & ~127);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(stages + TC_STAGES * stage_bytes);
+    // bars: full[NS], empty[NS], tmem_full[2], tmem_empty[2]
+    const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * TC_STAGES;
+    const uint32_t bar_tfull = bar_empty + 8 * TC_STAGES, bar_tempty = bar_tfull + 16;
+    __shared__ uint32_t tmem_base_s;
+
+    // ---- setup ------------------------------------------------------------------------------
+    for (int i = tid; i < P.master_bytes / 16; i += TC_THREADS)
+        reinterpret_cast<uint4 *>(a_smem)[i] = __ldg(reinterpret_cast<const uint4 *>(P.master) + i);
+    // rows of the stages that no producer ever writes (the padding row) must be defined: zero all
+    for (int i = tid; i < TC_STAGES * stage_bytes / 16; i += TC_THREADS)
+        reinterpret_cast<uint4 *>(stages)[i] = make_uint4(0, 0, 0, 0);
+    fence_async_smem();
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, TC_NPROD + 32);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_tfull + 8 * a, 1);
+            mbar_init(bar_tempty + 8 * a, 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    const long long first_tile = blockIdx.x, tile_step = gridDim.x;
+    const int KS = P.M;  // K-steps per tile
+
+    if (warp >= 5) {
+        // =====================================================================================
+        // producers: main (warps 6..13, one task per thread per K-step) and halo (warp 5)
+        // =====================================================================================
+        const bool is_halo = (warp == 5);
+        const int ptid = tid - TC_PROD_WARP0 * 32;
+        // task -> (row-block, 64-byte half).  lanes 2r, 2r+1 share a 128-byte segment.
+        const int half = lane & 1;
+        const int rbi = is_halo ? (lane >> 1) - (J - 1) : (ptid >> 1);
+        const bool active = is_halo ? (lane < 2 * (J - 1)) : true;
+        const int row_re = 2 * (rbi + (J - 1));
+
+        // flattened step counter over (tile, K-step); a register ring of TC_PREFETCH+1 tasks
+        long long n_my_tiles = (P.total_tiles - first_tile + tile_step - 1) / tile_step;
+        if (n_my_tiles < 0) n_my_tiles = 0;
+        const long long total_steps = n_my_tiles * KS;
+        TcTask ring[TC_PREFETCH + 1];
+
+        auto step_coords = [&](long long gs, const uint32_t *&x, const uint32_t *&hist, long long &n0) {
+            const long long tile = first_tile + (gs / KS) * tile_step;
+            const int kc = (int)(gs % KS);
+            const int ch = (int)(tile / P.tiles_per_ch);
+            const long long tt = tile - (long long)ch * P.tiles_per_ch;
+            x = P.in + (size_t)ch * P.in_stride;
+            hist = P.hist_in + (size_t)ch * P.H;
+            n0 = (tt * TC_NRB + rbi) * (long long)P.G + 32 * kc + 16 * half;
+        };
+
+#pragma unroll
+        for (int k = 0; k < TC_PREFETCH; ++k) {
+            if (active && k < total_steps) {
+                const uint32_t *x, *hist;
+                long long n0;
+                step_coords(k, x, hist, n0);
+                tc_task_load(ring[k], P, x, hist, n0);
+            }
+        }
+        int stage = 0;
+        uint32_t phase = 0;
+        for (long long gs0 = 0; gs0 < total_steps; gs0 += TC_PREFETCH + 1) {
+#pragma unroll
+            for (int r = 0; r <= TC_PREFETCH; ++r) {
+                const long long gs = gs0 + r;
+                if (gs < total_steps) {
+                    // prefetch step gs + PREFETCH into ring slot (r + PREFETCH) % (PREFETCH + 1)
+                    if (active && gs + TC_PREFETCH < total_steps) {
+                        const uint32_t *x, *hist;
+                        long long n0;
+                        step_coords(gs + TC_PREFETCH, x, hist, n0);
+                        tc_task_load(ring[(r + TC_PREFETCH) % (TC_PREFETCH + 1)], P, x, hist, n0);
+                    }
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1, P.error_flag);
+                    if (active) {
+                        const uint32_t *x, *hist;
+                        long long n0;
+                        step_coords(gs, x, hist, n0);
+                        tc_task_store(ring[r], P, x, hist, n0, stages + stage * stage_bytes, row_re, half);
+                    }
+                    fence_async_smem();
+                    mbar_arrive(bar_full + 8 * stage);
+                    if (++stage == TC_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // =====================================================================================
+        // MMA issuer (one thread)
+        // =====================================================================================
+        if (lane == 0) {
+            const uint32_t idesc_lo = umma_idesc_i8(1, 0, 128, 2 * TC_NRB);  // taps s8 x lo plane u8
+            const uint32_t idesc_hi = umma_idesc_i8(1, 1, 128, 2 * TC_NRB);  // taps s8 x hi plane s8
+            const uint32_t a_base = smem_u32(a_smem), s_base = smem_u32(stages);
+            const uint32_t lbo_a = P.a_rows * 16, lbo_b = P.rbp * 16;
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t acc_phase[2] = {0, 0};
+            int acc = 0;
+            for (long long tile = first_tile; tile < P.total_tiles; tile += tile_step) {
+                mbar_wait(bar_tempty + 8 * acc, acc_phase[acc] ^ 1, P.error_flag);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * (2 * TC_NRB);
+                uint32_t accumulate = 0;
+                for (int kc = 0; kc < KS; ++kc) {
+                    mbar_wait(bar_full + 8 * stage, phase, P.error_flag);
+                    tc_fence_after();
+                    const TcKstep ks = P.ks[kc];
+                    const uint32_t sb = s_base + stage * stage_bytes;
+                    for (int j = 0; j < J; ++j) {
+                        if (!((ks.jmask >> j) & 1)) continue;
+                        const uint32_t a_addr = a_base + ks.res_off + (ks.a_row + 128 * j) * 16;
+                        const uint32_t b_addr = sb + 2 * (J - 1 - j) * 16;
+                        umma_i8(d_tmem, umma_desc(a_addr, lbo_a), umma_desc(b_addr, lbo_b), idesc_lo, accumulate);
+                        accumulate = 1;
+                        // hi byte plane: weight slot + 1  ==  master moved back by one row
+                        umma_i8(d_tmem, umma_desc(a_addr - 16, lbo_a), umma_desc(b_addr + 2 * lbo_b, lbo_b), idesc_hi, 1);
+                    }
+                    tc_commit(bar_empty + 8 * stage);  // frees the stage when these MMAs have read it
+                    if (++stage == TC_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                tc_commit(bar_tfull + 8 * acc);
+                acc_phase[acc] ^= 1;
+                acc ^= 1;
+            }
+        }
+    } else {
+        // =====================================================================================
+        // epilogue warps 0..3: TMEM lanes 32*warp .. 32*warp+31  ->  rho = 4*b + w
+        // =====================================================================================
+        const int w = lane & 3;
+        const int b = 8 * warp + (lane >> 2);
+        uint32_t acc_phase[2] = {0, 0};
+        int acc = 0;
+        for (long long tile = first_tile; tile < P.total_tiles; tile += tile_step) {
+            const int ch = (int)(tile / P.tiles_per_ch);
+            const long long tt = tile - (long long)ch * P.tiles_per_ch;
+            uint32_t *o = P.out + (size_t)ch * P.out_stride;
+            mbar_wait(bar_tfull + 8 * acc, acc_phase[acc], P.error_flag);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(32 * warp) << 16) + acc * (2 * TC_NRB);
+#pragma unroll 1
+            for (int c0 = 0; c0 < 2 * TC_NRB; c0 += 32) {
+                uint32_t v[32];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                    "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+                      "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+                      "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+                      "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(t_addr + c0));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                // sum_w 256^w * D_w over the 4 lanes of the quad (mod 2^32, exactly the int32 wrap)
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    uint32_t s = v[c] << (8 * w);
+                    s += __shfl_xor_sync(0xffffffffu, s, 1);
+                    s += __shfl_xor_sync(0xffffffffu, s, 2);
+                    v[c] = s;
+                }
+                // lane w finalises the row-blocks m = c0/2 + 4*i + w of this chunk
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    // select v[2*(4*i + w)], v[2*(4*i + w) + 1] without dynamic register indexing
+                    uint32_t re = v[8 * i], im = v[8 * i + 1];
+                    if (w == 1) re = v[8 * i + 2], im = v[8 * i + 3];
+                    if (w == 2) re = v[8 * i + 4], im = v[8 * i + 5];
+                    if (w == 3) re = v[8 * i + 6], im = v[8 * i + 7];
+                    const int m = (c0 >> 1) + 4 * i + w;
+                    const long long idx = (tt * TC_NRB + m) * TC_BOUT + b;
+                    if (idx < P.n_out) o[idx] = scale_pack<true>((int)re, (int)im, P.shift);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(bar_tempty + 8 * acc);
+            acc_phase[acc] ^= 1;
+            acc ^= 1;
+        }
+    }
+
+    // ---- teardown ---------------------------------------------------------------------------
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+    }
+}
+
+}  // namespace srcdsp

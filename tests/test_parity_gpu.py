@@ -297,3 +297,53 @@ def test_cfg2_full_size_spot_and_split_invariance(S, corc):
     # checksum of checksums against the oracle on one full channel prefix
     e, _ = corc.dec_step(taps, M, corc.synth(0x5EED0002, 100, 0, 1 << 18, 2))
     assert np.array_equal(yh[1][: (1 << 18) // M], e)
+
+
+# ---- tcgen05 int8 Toeplitz kernel (forced with set_kernel(2)) ----------------------------------------
+@pytest.mark.parametrize("M,nt,amp", [(16, 255, 400), (16, 256, 30000), (8, 63, 2000), (4, 1023, 300), (2, 9, 100),
+                                      (1, 33, 8000), (3, 31, 500), (5, 50, 500), (10, 90, 100000), (12, 255, 2 ** 22),
+                                      (32, 64, 127), (64, 300, 500), (16, 17, 1)])
+def test_tc_decimator_sweep(S, corc, M, nt, amp):
+    """The tensor-core path is exact for every ratio / length / tap magnitude it accepts, across
+    streaming blocks (history), ragged tile ends and several channels (persistent tile loop)."""
+    rng = np.random.default_rng(M * 7919 + nt)
+    taps = rng.integers(-amp, amp + 1, nt).astype(np.int32)
+    taps[0] = amp
+    C = 3
+    d = S.FilterDnsamplingFir(M, taps, channels=C, obsolete=True)
+    d.set_kernel(2)
+    hs = [None] * C
+    for blk, n_out in enumerate([4096 * 2 + 77, 5, 4096, 1300]):
+        n = n_out * M
+        x = rng.integers(-32768, 32768, (C, n, 2)).astype(np.int16)
+        got = host(d.step(dev(x))) if blk % 2 == 0 else d.step(x)
+        for c in range(C):
+            exp, hs[c] = corc.dec_step(taps, M, x[c], hs[c])
+            assert np.array_equal(got[c], exp), (M, nt, blk, c)
+
+
+def test_tc_matches_imad_on_unaligned_buffers(S, corc):
+    import torch
+    rng = np.random.default_rng(99)
+    C, M, nt, n = 4, 16, 255, 16 * 9000
+    taps = O.design_lowpass_taps(nt, M)
+    big = torch.from_numpy(rng.integers(-32768, 32768, (C, n + 7, 2)).astype(np.int16)).cuda()
+    x = big[:, 3: 3 + n]  # 12-byte offset: the 16-byte fast path is off
+    outs = []
+    for kind in (1, 2):
+        d = S.FilterDnsamplingFir(M, taps, channels=C, obsolete=True)
+        d.set_kernel(kind)
+        outs.append(host(d.step(x)))
+    assert np.array_equal(outs[0], outs[1])
+    e, _ = corc.dec_step(taps, M, host(x[2]))
+    assert np.array_equal(outs[1][2], e)
+
+
+def test_tc_rejects_what_it_cannot_do(S):
+    d = S.FilterDnsamplingFir(8, [2 ** 24] * 16, obsolete=True)  # needs 4 signed byte digits
+    d.set_kernel(2)
+    with pytest.raises(S.SrcDspError) as ei:
+        d.step(np.zeros((64, 2), np.int16))
+    assert ei.value.code == -5
+    d.set_kernel(0)  # automatic selection falls back to the IMAD kernel
+    d.step(np.zeros((64, 2), np.int16))
