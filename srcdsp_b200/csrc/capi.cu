@@ -698,7 +698,7 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
         // kernel choice: the tcgen05 Toeplitz kernel when the taps fit it and there are enough
         // 4096-output tiles to occupy the machine; the IMAD kernel otherwise
         const long long tc_tiles = (long long)C * ((P.n_out + TC_NRB * TC_BOUT - 1) / (TC_NRB * TC_BOUT));
-        bool use_tc = tc_ok && (kernel_kind == 2 || (kernel_kind == 0 && tc_tiles >= sm_count / 2));
+        bool use_tc = tc_ok && tc_tiles < 0x7fffffffll && (kernel_kind == 2 || (kernel_kind == 0 && tc_tiles >= sm_count / 2));
         if (kernel_kind == 2 && !tc_ok)
             return fail(SRCDSP_E_STATE, "tcgen05 kernel forced but not applicable: %s", tc_why);
         if (use_tc) {

@@ -44,7 +44,7 @@ constexpr int TC_NPROD = 256;            // main producer threads
 constexpr int TC_STAGES = 6;
 constexpr int TC_MAX_KSTEPS = 64;        // M <= 64
 constexpr int TC_MAX_J = 16;
-constexpr int TC_PREFETCH = 2;           // K-steps a producer thread loads ahead of the one it stores
+constexpr int TC_PREFETCH = 3;           // K-steps a producer thread loads ahead of the one it stores
 
 struct TcKstep {
     int a_row;        // master row of (b = 0, w = 0) for lag 0:  4 * (32 - a) + 4 guard rows
@@ -265,58 +265,66 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
         const bool active = is_halo ? (lane < 2 * (J - 1)) : true;
         const int row_re = 2 * (rbi + (J - 1));
 
-        // flattened step counter over (tile, K-step); a register ring of TC_PREFETCH+1 tasks
-        long long n_my_tiles = (P.total_tiles - first_tile + tile_step - 1) / tile_step;
-        if (n_my_tiles < 0) n_my_tiles = 0;
-        const long long total_steps = n_my_tiles * KS;
-        TcTask ring[TC_PREFETCH + 1];
-
-        auto step_coords = [&](long long gs, const uint32_t *&x, const uint32_t *&hist, long long &n0) {
-            const long long tile = first_tile + (gs / KS) * tile_step;
-            const int kc = (int)(gs % KS);
-            const int ch = (int)(tile / P.tiles_per_ch);
-            const long long tt = tile - (long long)ch * P.tiles_per_ch;
-            x = P.in + (size_t)ch * P.in_stride;
-            hist = P.hist_in + (size_t)ch * P.H;
-            n0 = (tt * TC_NRB + rbi) * (long long)P.G + 32 * kc + 16 * half;
+        // Two cursors walk the same (tile, K-step) sequence: `ld` runs TC_PREFETCH steps ahead and
+        // issues the global loads into a register ring, `st` splits + stores the step whose stage
+        // has been released.  Cursors advance incrementally (one 32-bit division per tile).
+        struct Cursor {
+            long long tile;
+            int kc;
+            const uint32_t *x, *hist;
+            long long nbase;  // sample index of this thread's 16-sample piece at kc = 0
         };
-
+        auto seek = [&](Cursor &c) {
+            if (c.tile < P.total_tiles) {
+                const unsigned t = (unsigned)c.tile;
+                const unsigned ch = t / (unsigned)P.tiles_per_ch;
+                const unsigned tt = t - ch * (unsigned)P.tiles_per_ch;
+                c.x = P.in + (size_t)ch * P.in_stride;
+                c.hist = P.hist_in + (size_t)ch * P.H;
+                c.nbase = ((long long)tt * TC_NRB + rbi) * (long long)P.G + 16 * half;
+            }
+        };
+        auto advance = [&](Cursor &c) {
+            if (++c.kc == KS) {
+                c.kc = 0;
+                c.tile += tile_step;
+                seek(c);
+            }
+        };
+        Cursor ld{first_tile, 0, nullptr, nullptr, 0}, st{first_tile, 0, nullptr, nullptr, 0};
+        seek(ld);
+        seek(st);
+        TcTask ring[TC_PREFETCH + 1];
 #pragma unroll
         for (int k = 0; k < TC_PREFETCH; ++k) {
-            if (active && k < total_steps) {
-                const uint32_t *x, *hist;
-                long long n0;
-                step_coords(k, x, hist, n0);
-                tc_task_load(ring[k], P, x, hist, n0);
+            if (ld.tile < P.total_tiles) {
+                if (active) tc_task_load(ring[k], P, ld.x, ld.hist, ld.nbase + 32 * ld.kc);
+                advance(ld);
             }
         }
         int stage = 0;
         uint32_t phase = 0;
-        for (long long gs0 = 0; gs0 < total_steps; gs0 += TC_PREFETCH + 1) {
+        while (st.tile < P.total_tiles) {
 #pragma unroll
             for (int r = 0; r <= TC_PREFETCH; ++r) {
-                const long long gs = gs0 + r;
-                if (gs < total_steps) {
-                    // prefetch step gs + PREFETCH into ring slot (r + PREFETCH) % (PREFETCH + 1)
-                    if (active && gs + TC_PREFETCH < total_steps) {
-                        const uint32_t *x, *hist;
-                        long long n0;
-                        step_coords(gs + TC_PREFETCH, x, hist, n0);
-                        tc_task_load(ring[(r + TC_PREFETCH) % (TC_PREFETCH + 1)], P, x, hist, n0);
+                if (st.tile < P.total_tiles) {
+                    if (ld.tile < P.total_tiles) {
+                        if (active)
+                            tc_task_load(ring[(r + TC_PREFETCH) % (TC_PREFETCH + 1)], P, ld.x, ld.hist,
+                                         ld.nbase + 32 * ld.kc);
+                        advance(ld);
                     }
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1, P.error_flag);
-                    if (active) {
-                        const uint32_t *x, *hist;
-                        long long n0;
-                        step_coords(gs, x, hist, n0);
-                        tc_task_store(ring[r], P, x, hist, n0, stages + stage * stage_bytes, row_re, half);
-                    }
+                    if (active)
+                        tc_task_store(ring[r], P, st.x, st.hist, st.nbase + 32 * st.kc, stages + stage * stage_bytes,
+                                      row_re, half);
                     fence_async_smem();
                     mbar_arrive(bar_full + 8 * stage);
                     if (++stage == TC_STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
+                    advance(st);
                 }
             }
         }
@@ -331,10 +339,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
             const uint32_t lbo_a = P.a_rows * 16, lbo_b = P.rbp * 16;
             int stage = 0;
             uint32_t phase = 0;
-            uint32_t acc_phase[2] = {0, 0};
+            uint32_t acc_phases = 0;  // bit a: parity of accumulator buffer a
             int acc = 0;
             for (long long tile = first_tile; tile < P.total_tiles; tile += tile_step) {
-                mbar_wait(bar_tempty + 8 * acc, acc_phase[acc] ^ 1, P.error_flag);
+                mbar_wait(bar_tempty + 8 * acc, ((acc_phases >> acc) & 1) ^ 1, P.error_flag);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * (2 * TC_NRB);
                 uint32_t accumulate = 0;
@@ -359,7 +367,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
                     }
                 }
                 tc_commit(bar_tfull + 8 * acc);
-                acc_phase[acc] ^= 1;
+                acc_phases ^= 1u << acc;
                 acc ^= 1;
             }
         }
@@ -369,13 +377,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
         // =====================================================================================
         const int w = lane & 3;
         const int b = 8 * warp + (lane >> 2);
-        uint32_t acc_phase[2] = {0, 0};
+        uint32_t acc_phases = 0;
         int acc = 0;
         for (long long tile = first_tile; tile < P.total_tiles; tile += tile_step) {
             const int ch = (int)(tile / P.tiles_per_ch);
             const long long tt = tile - (long long)ch * P.tiles_per_ch;
             uint32_t *o = P.out + (size_t)ch * P.out_stride;
-            mbar_wait(bar_tfull + 8 * acc, acc_phase[acc], P.error_flag);
+            mbar_wait(bar_tfull + 8 * acc, (acc_phases >> acc) & 1, P.error_flag);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(32 * warp) << 16) + acc * (2 * TC_NRB);
 #pragma unroll 1
@@ -415,7 +423,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
             }
             tc_fence_before();
             mbar_arrive(bar_tempty + 8 * acc);
-            acc_phase[acc] ^= 1;
+            acc_phases ^= 1u << acc;
             acc ^= 1;
         }
     }
