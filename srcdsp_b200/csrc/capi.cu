@@ -715,6 +715,15 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
             T.H = H;
             T.shift = P.shift;
             T.vec_in = P.vec_in;
+            T.rb_stride = T.G;
+            T.kc_stride = 32;
+            if (const char *dbg = getenv("SRCDSP_TC_DEBUG")) {  // timing experiments only (wrong results)
+                T.debug = atoi(dbg);
+                if (T.debug & 16) {  // contiguous 128-byte lines per K-step instead of a 4*G-byte stride
+                    T.rb_stride = 32;
+                    T.kc_stride = 32 * TC_NRB;
+                }
+            }
             const int tgrid = (int)std::min<long long>(tc_tiles, sm_count);
             dec_tc_kernel<<<tgrid, TC_THREADS, tc_smem, stream>>>(T);
             SRCDSP_LAUNCH_CHECK();

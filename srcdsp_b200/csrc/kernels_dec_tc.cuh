@@ -24,12 +24,13 @@
 //       byte plane is the same moved back by ONE row (weight slot w -> w+1).
 //   (the linear-address behaviour of SWIZZLE_NONE descriptors is checked by tools/umma_probe.cu)
 //
-// Warp roles (448 threads, 1 CTA / SM, persistent over tiles):
+// Warp roles (416 threads, 1 CTA / SM, persistent over tiles):
 //   warps 0-3  epilogue: tcgen05.ld 32x32b, combine the 4 weight slots with 2 shuffles,
 //              >> shift, symmetric clamp, pack, store
 //   warp  4    TMEM alloc + single-thread MMA issue, tcgen05.commit -> mbarriers
-//   warp  5    halo producer (the J-1 row-blocks in front of the tile)
-//   warps 6-13 producers: LDG.128 (coalesced) -> PRMT byte-plane split -> STS.128 into the stage
+//   warps 5-12 producers: warp k owns every 8th K-step and shared-memory stage k, so that no
+//              warp sits on the critical path of every K-step: LDG.128 (8 lanes per 128-byte
+//              line, two batches of 8 loads in flight per lane) -> PRMT byte-plane split -> STS.32
 #pragma once
 
 #include "common.cuh"
@@ -38,13 +39,13 @@ namespace srcdsp {
 
 constexpr int TC_NRB = 128;              // row-blocks per tile (MMA N = 2 * NRB)
 constexpr int TC_BOUT = 32;              // outputs per row-block
-constexpr int TC_THREADS = 448;
-constexpr int TC_PROD_WARP0 = 6;         // first main producer warp
-constexpr int TC_NPROD = 256;            // main producer threads
-constexpr int TC_STAGES = 6;
+constexpr int TC_NPW = 8;                // producer warps; warp k owns K-steps k, k+8, ... and stage k
+constexpr int TC_PROD_WARP0 = 5;         // first producer warp
+constexpr int TC_THREADS = 32 * (TC_PROD_WARP0 + TC_NPW);
+constexpr int TC_STAGES = TC_NPW;
+constexpr int TC_BATCH = 8;              // 16-byte loads in flight per lane per batch (2 batches in flight)
 constexpr int TC_MAX_KSTEPS = 64;        // M <= 64
 constexpr int TC_MAX_J = 16;
-constexpr int TC_PREFETCH = 3;           // K-steps a producer thread loads ahead of the one it stores
 
 struct TcKstep {
     int a_row;        // master row of (b = 0, w = 0) for lag 0:  4 * (32 - a) + 4 guard rows
@@ -71,6 +72,8 @@ struct TcParams {
     unsigned shift;
     int vec_in;
     int *error_flag;
+    int rb_stride, kc_stride;  // samples between row-blocks / K-steps (G and 32; timing experiments permute them)
+    int debug;  // timing experiments only (results become wrong): 1 = skip the MMAs, 4 = skip the epilogue math
     TcKstep ks[TC_MAX_KSTEPS];
 };
 
@@ -142,28 +145,6 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
     return r;
 }
 
-// 16 consecutive samples (4 x uint4, bytes re_lo re_hi im_lo im_hi per sample) -> 4 byte planes
-__device__ __forceinline__ void split_planes(const uint4 (&q)[4], uint4 &re_lo, uint4 &re_hi, uint4 &im_lo, uint4 &im_hi)
-{
-    uint32_t o[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const uint32_t w0 = q[i].x, w1 = q[i].y, w2 = q[i].z, w3 = q[i].w;
-        const uint32_t a = prmt(w0, w1, 0x5140);  // {w0.b0, w1.b0, w0.b1, w1.b1} = re_lo x2, re_hi x2
-        const uint32_t b = prmt(w2, w3, 0x5140);
-        const uint32_t c = prmt(w0, w1, 0x7362);  // {w0.b2, w1.b2, w0.b3, w1.b3} = im_lo x2, im_hi x2
-        const uint32_t d = prmt(w2, w3, 0x7362);
-        o[0][i] = prmt(a, b, 0x5410);  // re_lo of 4 samples
-        o[1][i] = prmt(a, b, 0x7632);  // re_hi
-        o[2][i] = prmt(c, d, 0x5410);  // im_lo
-        o[3][i] = prmt(c, d, 0x7632);  // im_hi
-    }
-    re_lo = make_uint4(o[0][0], o[0][1], o[0][2], o[0][3]);
-    re_hi = make_uint4(o[1][0], o[1][1], o[1][2], o[1][3]);
-    im_lo = make_uint4(o[2][0], o[2][1], o[2][2], o[2][3]);
-    im_hi = make_uint4(o[3][0], o[3][1], o[3][2], o[3][3]);
-}
-
 // generic sample fetch: history for n < 0, zero outside [−H, n_in)
 __device__ __forceinline__ uint32_t tc_sample(const uint32_t *x, const uint32_t *hist, int H, long long n_in, long long n)
 {
@@ -171,41 +152,102 @@ __device__ __forceinline__ uint32_t tc_sample(const uint32_t *x, const uint32_t 
     return n >= -(long long)H ? __ldg(hist + (H + n)) : 0u;
 }
 
-struct TcTask {
-    uint4 q[4];
-    bool fast;
+__device__ __forceinline__ uint4 ldg_stream(const uint4 *p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+    return v;
+}
+
+// 4 consecutive samples -> one 32-bit word per byte plane
+__device__ __forceinline__ void split4(const uint4 q, uint32_t &re_lo, uint32_t &re_hi, uint32_t &im_lo, uint32_t &im_hi)
+{
+    const uint32_t a = prmt(q.x, q.y, 0x5140);  // {w0.b0, w1.b0, w0.b1, w1.b1}
+    const uint32_t b = prmt(q.z, q.w, 0x5140);
+    const uint32_t c = prmt(q.x, q.y, 0x7362);  // {w0.b2, w1.b2, w0.b3, w1.b3}
+    const uint32_t d = prmt(q.z, q.w, 0x7362);
+    re_lo = prmt(a, b, 0x5410);
+    re_hi = prmt(a, b, 0x7632);
+    im_lo = prmt(c, d, 0x5410);
+    im_hi = prmt(c, d, 0x7632);
+}
+
+// A batch = TC_BATCH iterations; iteration `it` covers row-blocks rb_first + 4*it + (lane >> 3),
+// each lane one 16-byte piece (4 samples), so that 8 lanes read one whole 128-byte line.
+struct TcBatch {
+    uint4 q[TC_BATCH];
+    unsigned fast;  // bit it: q[it] holds data loaded on the aligned fast path; ~0u: interior batch
 };
 
-__device__ __forceinline__ void tc_task_load(TcTask &t, const TcParams &P, const uint32_t *x, const uint32_t *hist,
-                                             long long n0)
+// Interior batch (warp-uniform decision): every row-block and sample of the batch is inside the
+// block and 16-byte aligned -> straight-line code, no per-iteration predicates.
+__device__ __forceinline__ void tc_batch_load_fast(TcBatch &t, const uint32_t *p, size_t stride_words)
 {
-    t.fast = P.vec_in && n0 >= 0 && n0 + 16 <= P.n_in;
-    if (t.fast) {
-        const uint4 *p = reinterpret_cast<const uint4 *>(x + n0);
+    t.fast = ~0u;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) t.q[i] = __ldg(p + i);
+    for (int it = 0; it < TC_BATCH; ++it) t.q[it] = ldg_stream(reinterpret_cast<const uint4 *>(p + it * stride_words));
+}
+
+__device__ __forceinline__ void tc_batch_store_fast(const TcBatch &t, uint8_t *lo, uint8_t *hi)
+{
+#pragma unroll
+    for (int it = 0; it < TC_BATCH; ++it) {
+        uint32_t re_lo, re_hi, im_lo, im_hi;
+        split4(t.q[it], re_lo, re_hi, im_lo, im_hi);
+        *reinterpret_cast<uint32_t *>(lo + it * 128) = re_lo;   // 4 row-blocks further = 8 rows = 128 bytes
+        *reinterpret_cast<uint32_t *>(lo + it * 128 + 16) = im_lo;
+        *reinterpret_cast<uint32_t *>(hi + it * 128) = re_hi;
+        *reinterpret_cast<uint32_t *>(hi + it * 128 + 16) = im_hi;
     }
 }
 
-__device__ __forceinline__ void tc_task_store(TcTask &t, const TcParams &P, const uint32_t *x, const uint32_t *hist,
-                                              long long n0, uint8_t *stage, int row_re, int half)
+// n0: sample index of (row-block rb_first + (lane >> 3), this lane's piece, this K-step)
+__device__ __forceinline__ void tc_batch_load(TcBatch &t, const TcParams &P, const uint32_t *x, long long n0,
+                                              int rb, int rb_lo, int rb_hi, int nit)
 {
-    if (!t.fast) {
-        uint32_t v[16];
+    t.fast = 0;
 #pragma unroll
-        for (int s = 0; s < 16; ++s) v[s] = tc_sample(x, hist, P.H, P.n_in, n0 + s);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) t.q[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    for (int it = 0; it < TC_BATCH; ++it) {
+        if (it >= nit) break;
+        const long long n = n0 + (long long)it * 4 * P.rb_stride;
+        const int r = rb + 4 * it;
+        if (r >= rb_lo && r < rb_hi && P.vec_in && n >= 0 && n + 4 <= P.n_in) {
+            t.q[it] = ldg_stream(reinterpret_cast<const uint4 *>(x + n));
+            t.fast |= 1u << it;
+        }
     }
-    uint4 re_lo, re_hi, im_lo, im_hi;
-    split_planes(t.q, re_lo, re_hi, im_lo, im_hi);
-    const int chunk = P.rbp * 16;             // bytes per (plane, kc) chunk
-    uint8_t *lo = stage + half * chunk + row_re * 16;
-    uint8_t *hi = lo + 2 * chunk;
-    *reinterpret_cast<uint4 *>(lo) = re_lo;
-    *reinterpret_cast<uint4 *>(lo + 16) = im_lo;
-    *reinterpret_cast<uint4 *>(hi) = re_hi;
-    *reinterpret_cast<uint4 *>(hi + 16) = im_hi;
+}
+
+// dst: stage address of (plane lo, this lane's kc chunk, re row of row-block rb, this lane's word)
+__device__ __forceinline__ void tc_batch_store(TcBatch &t, const TcParams &P, const uint32_t *x, const uint32_t *hist,
+                                               long long n0, int rb, int rb_lo, int rb_hi, int nit, uint8_t *dst)
+{
+    const int chunk = P.rbp * 16;  // bytes per (plane, kc) chunk
+#pragma unroll
+    for (int it = 0; it < TC_BATCH; ++it) {
+        if (it >= nit) break;
+        const int r = rb + 4 * it;
+        if (r >= rb_lo && r < rb_hi) {
+            uint4 q = t.q[it];
+            if (!((t.fast >> it) & 1)) {
+                const long long n = n0 + (long long)it * 4 * P.rb_stride;
+                q.x = tc_sample(x, hist, P.H, P.n_in, n);
+                q.y = tc_sample(x, hist, P.H, P.n_in, n + 1);
+                q.z = tc_sample(x, hist, P.H, P.n_in, n + 2);
+                q.w = tc_sample(x, hist, P.H, P.n_in, n + 3);
+            }
+            uint32_t re_lo, re_hi, im_lo, im_hi;
+            split4(q, re_lo, re_hi, im_lo, im_hi);
+            uint8_t *lo = dst + it * (8 * 16);  // 4 row-blocks further = 8 rows
+            uint8_t *hi = lo + 2 * chunk;
+            *reinterpret_cast<uint32_t *>(lo) = re_lo;
+            *reinterpret_cast<uint32_t *>(lo + 16) = im_lo;
+            *reinterpret_cast<uint32_t *>(hi) = re_hi;
+            *reinterpret_cast<uint32_t *>(hi + 16) = im_hi;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_constant__ TcParams P)
@@ -232,12 +274,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
     fence_async_smem();
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
-            mbar_init(bar_full + 8 * s, TC_NPROD + 32);
+            mbar_init(bar_full + 8 * s, 1);  // the owning producer warp
             mbar_init(bar_empty + 8 * s, 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(bar_tfull + 8 * a, 1);
-            mbar_init(bar_tempty + 8 * a, 128);
+            mbar_init(bar_tempty + 8 * a, 4);  // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -253,26 +295,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
     const long long first_tile = blockIdx.x, tile_step = gridDim.x;
     const int KS = P.M;  // K-steps per tile
 
-    if (warp >= 5) {
+    if (warp >= TC_PROD_WARP0) {
         // =====================================================================================
-        // producers: main (warps 6..13, one task per thread per K-step) and halo (warp 5)
+        // producers: warp pw owns K-steps pw, pw + 8, ... of the flattened (tile, K-step) sequence
+        // and shared-memory stage pw.  A step is HB halo + 4 main batches of 8 iterations.
         // =====================================================================================
-        const bool is_halo = (warp == 5);
-        const int ptid = tid - TC_PROD_WARP0 * 32;
-        // task -> (row-block, 64-byte half).  lanes 2r, 2r+1 share a 128-byte segment.
-        const int half = lane & 1;
-        const int rbi = is_halo ? (lane >> 1) - (J - 1) : (ptid >> 1);
-        const bool active = is_halo ? (lane < 2 * (J - 1)) : true;
-        const int row_re = 2 * (rbi + (J - 1));
+        const int pw = warp - TC_PROD_WARP0;
+        const int piece = lane & 7, grp = lane >> 3;
+        const int halo_it = (J - 1 + 3) >> 2;            // iterations that cover the J-1 halo row-blocks
+        const int NB = 4 + (halo_it > 0 ? 1 : 0);        // batches per step
+        uint8_t *stage_base = stages + pw * stage_bytes;
+        const uint32_t my_full = bar_full + 8 * pw, my_empty = bar_empty + 8 * pw;
+        const int chunk = P.rbp * 16;
 
-        // Two cursors walk the same (tile, K-step) sequence: `ld` runs TC_PREFETCH steps ahead and
-        // issues the global loads into a register ring, `st` splits + stores the step whose stage
-        // has been released.  Cursors advance incrementally (one 32-bit division per tile).
         struct Cursor {
             long long tile;
-            int kc;
+            int kc, b;
             const uint32_t *x, *hist;
-            long long nbase;  // sample index of this thread's 16-sample piece at kc = 0
+            long long row0;  // (tt * NRB) * G + 4 * piece : sample index of row-block 0, this piece
         };
         auto seek = [&](Cursor &c) {
             if (c.tile < P.total_tiles) {
@@ -281,48 +321,91 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
                 const unsigned tt = t - ch * (unsigned)P.tiles_per_ch;
                 c.x = P.in + (size_t)ch * P.in_stride;
                 c.hist = P.hist_in + (size_t)ch * P.H;
-                c.nbase = ((long long)tt * TC_NRB + rbi) * (long long)P.G + 16 * half;
+                c.row0 = (long long)tt * TC_NRB * (long long)P.G + 4 * piece;
             }
         };
         auto advance = [&](Cursor &c) {
-            if (++c.kc == KS) {
-                c.kc = 0;
-                c.tile += tile_step;
-                seek(c);
+            if (++c.b == NB) {
+                c.b = 0;
+                c.kc += TC_NPW;
+                if (c.kc >= KS) {
+                    do {
+                        c.kc -= KS;
+                        c.tile += tile_step;
+                    } while (c.kc >= KS);
+                    seek(c);
+                }
             }
         };
-        Cursor ld{first_tile, 0, nullptr, nullptr, 0}, st{first_tile, 0, nullptr, nullptr, 0};
+        // first row-block of batch b for this lane, and the lowest valid row-block of that batch
+        auto batch_rb = [&](int b, int &rb, int &rb_lo, int &rb_hi) {
+            if (halo_it > 0 && b == 0) {
+                rb = -4 * halo_it + grp;
+                rb_lo = -(J - 1);
+                rb_hi = 0;
+            } else {
+                rb = 32 * (b - (halo_it > 0 ? 1 : 0)) + grp;
+                rb_lo = 0;
+                rb_hi = TC_NRB;
+            }
+        };
+        const size_t it_stride = (size_t)4 * P.rb_stride;
+        // warp-uniform: batch b of the cursor's step lies completely inside [0, n_in) (main batches only)
+        auto interior = [&](const Cursor &c) {
+            if (halo_it > 0 && c.b == 0) return false;
+            const int mb = c.b - (halo_it > 0 ? 1 : 0);
+            const long long last = c.row0 - 4 * piece + (long long)(32 * mb + 31) * P.rb_stride + P.kc_stride * c.kc + 32;
+            return P.vec_in && last <= P.n_in;
+        };
+        auto do_load = [&](TcBatch &t, const Cursor &c) {
+            int rb, rb_lo, rb_hi;
+            batch_rb(c.b, rb, rb_lo, rb_hi);
+            const long long n0 = c.row0 + (long long)rb * P.rb_stride + P.kc_stride * c.kc;
+            if (interior(c))
+                tc_batch_load_fast(t, c.x + n0, it_stride);
+            else
+                tc_batch_load(t, P, c.x, n0, rb, rb_lo, rb_hi, (halo_it > 0 && c.b == 0) ? halo_it : TC_BATCH);
+        };
+        Cursor ld{first_tile, pw, 0, nullptr, nullptr, 0}, st{first_tile, pw, 0, nullptr, nullptr, 0};
+        while (ld.kc >= KS) {
+            ld.kc -= KS;
+            ld.tile += tile_step;
+        }
+        st.kc = ld.kc;
+        st.tile = ld.tile;
         seek(ld);
         seek(st);
-        TcTask ring[TC_PREFETCH + 1];
-#pragma unroll
-        for (int k = 0; k < TC_PREFETCH; ++k) {
-            if (ld.tile < P.total_tiles) {
-                if (active) tc_task_load(ring[k], P, ld.x, ld.hist, ld.nbase + 32 * ld.kc);
-                advance(ld);
-            }
+        TcBatch ring[2];
+        if (ld.tile < P.total_tiles) {
+            do_load(ring[0], ld);
+            advance(ld);
         }
-        int stage = 0;
-        uint32_t phase = 0;
+        uint32_t parity = 1;  // first wait on a fresh "empty" barrier passes
         while (st.tile < P.total_tiles) {
 #pragma unroll
-            for (int r = 0; r <= TC_PREFETCH; ++r) {
+            for (int r = 0; r < 2; ++r) {
                 if (st.tile < P.total_tiles) {
                     if (ld.tile < P.total_tiles) {
-                        if (active)
-                            tc_task_load(ring[(r + TC_PREFETCH) % (TC_PREFETCH + 1)], P, ld.x, ld.hist,
-                                         ld.nbase + 32 * ld.kc);
+                        do_load(ring[r ^ 1], ld);
                         advance(ld);
                     }
-                    mbar_wait(bar_empty + 8 * stage, phase ^ 1, P.error_flag);
-                    if (active)
-                        tc_task_store(ring[r], P, st.x, st.hist, st.nbase + 32 * st.kc, stages + stage * stage_bytes,
-                                      row_re, half);
-                    fence_async_smem();
-                    mbar_arrive(bar_full + 8 * stage);
-                    if (++stage == TC_STAGES) {
-                        stage = 0;
-                        phase ^= 1;
+                    if (st.b == 0) mbar_wait(my_empty, parity, P.error_flag);
+                    int rb, rb_lo, rb_hi;
+                    batch_rb(st.b, rb, rb_lo, rb_hi);
+                    uint8_t *dst = stage_base + (piece >> 2) * chunk + 2 * (rb + (J - 1)) * 16 + (piece & 3) * 4;
+                    if (ring[r].fast == ~0u)
+                        tc_batch_store_fast(ring[r], dst, dst + 2 * chunk);
+                    else
+                        tc_batch_store(ring[r], P, st.x, st.hist,
+                                       st.row0 + (long long)rb * P.rb_stride + P.kc_stride * st.kc, rb, rb_lo, rb_hi,
+                                       (halo_it > 0 && st.b == 0) ? halo_it : TC_BATCH, dst);
+                    if (st.b == NB - 1) {
+                        // every writer fences its generic-proxy stores towards the async proxy (the
+                        // MMA reads shared memory through it); one arrival per warp
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(my_full);
+                        parity ^= 1;
                     }
                     advance(st);
                 }
@@ -352,7 +435,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
                     const TcKstep ks = P.ks[kc];
                     const uint32_t sb = s_base + stage * stage_bytes;
                     for (int j = 0; j < J; ++j) {
-                        if (!((ks.jmask >> j) & 1)) continue;
+                        if (!((ks.jmask >> j) & 1) || (P.debug & 1)) continue;
                         const uint32_t a_addr = a_base + ks.res_off + (ks.a_row + 128 * j) * 16;
                         const uint32_t b_addr = sb + 2 * (J - 1 - j) * 16;
                         umma_i8(d_tmem, umma_desc(a_addr, lbo_a), umma_desc(b_addr, lbo_b), idesc_lo, accumulate);
@@ -387,7 +470,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
             tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(32 * warp) << 16) + acc * (2 * TC_NRB);
 #pragma unroll 1
-            for (int c0 = 0; c0 < 2 * TC_NRB; c0 += 32) {
+            for (int c0 = 0; c0 < ((P.debug & 4) ? 0 : 2 * TC_NRB); c0 += 32) {
                 uint32_t v[32];
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -422,7 +505,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
                 }
             }
             tc_fence_before();
-            mbar_arrive(bar_tempty + 8 * acc);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
             acc_phases ^= 1u << acc;
             acc ^= 1;
         }
