@@ -554,8 +554,11 @@ int DecBank::prepare_tc()
     const int a_rows = 128 * J + 136;
     const size_t master_bytes = res_list.size() * (size_t)a_rows * 32;
     const int rbp = 2 * (TC_NRB + J - 1) + 1;
-    const size_t smem = ((master_bytes + 127) & ~(size_t)127) + (size_t)TC_STAGES * 64 * rbp + 256;
-    if (smem > 227 * 1024) { tc_why = "Toeplitz master + stages exceed 227 KB of shared memory"; return SRCDSP_OK; }
+    const size_t fixed = ((master_bytes + 127) & ~(size_t)127) + 512;
+    int n_stages = (int)(((size_t)227 * 1024 - fixed) / ((size_t)64 * rbp));
+    if (fixed > (size_t)227 * 1024 || n_stages < TC_NPW + 1) { tc_why = "Toeplitz master + stages exceed 227 KB of shared memory"; return SRCDSP_OK; }
+    if (n_stages > TC_MAX_STAGES) n_stages = TC_MAX_STAGES;
+    const size_t smem = fixed + (size_t)n_stages * 64 * rbp;
     std::vector<uint8_t> img(master_bytes, 0);
     for (size_t ri = 0; ri < res_list.size(); ++ri) {
         uint8_t *base = img.data() + ri * (size_t)a_rows * 32;
@@ -585,6 +588,7 @@ int DecBank::prepare_tc()
     tc.master_bytes = (int)master_bytes;
     tc.a_rows = a_rows;
     tc.rbp = rbp;
+    tc.n_stages = n_stages;
     tc.error_flag = d_error;
     for (int kc = 0; kc < M; ++kc) {
         const int a = (32 * kc) / M, r = (32 * kc) % M;
@@ -602,7 +606,10 @@ int DecBank::prepare_tc()
     cudaDeviceProp prop;
     SRCDSP_CUDA(cudaGetDeviceProperties(&prop, device));
     sm_count = prop.multiProcessorCount;
-    SRCDSP_CUDA(cudaFuncSetAttribute(dec_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
+    SRCDSP_CUDA(cudaFuncSetAttribute(dec_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
+    SRCDSP_CUDA(cudaFuncSetAttribute(dec_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
+    SRCDSP_CUDA(cudaFuncSetAttribute(dec_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
+    SRCDSP_CUDA(cudaFuncSetAttribute(dec_tc_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
     tc_ok = true;
     tc_why = "";
     return SRCDSP_OK;
@@ -725,7 +732,12 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
                 }
             }
             const int tgrid = (int)std::min<long long>(tc_tiles, sm_count);
-            dec_tc_kernel<<<tgrid, TC_THREADS, tc_smem, stream>>>(T);
+            switch (T.debug & 10) {  // 2 / 8: timing-experiment instantiations (wrong results)
+            case 2: dec_tc_kernel<2><<<tgrid, TC_THREADS, tc_smem, stream>>>(T); break;
+            case 8: dec_tc_kernel<8><<<tgrid, TC_THREADS, tc_smem, stream>>>(T); break;
+            case 10: dec_tc_kernel<10><<<tgrid, TC_THREADS, tc_smem, stream>>>(T); break;
+            default: dec_tc_kernel<0><<<tgrid, TC_THREADS, tc_smem, stream>>>(T); break;
+            }
             SRCDSP_LAUNCH_CHECK();
             count_launch();
         } else {

@@ -39,10 +39,10 @@ namespace srcdsp {
 
 constexpr int TC_NRB = 128;              // row-blocks per tile (MMA N = 2 * NRB)
 constexpr int TC_BOUT = 32;              // outputs per row-block
-constexpr int TC_NPW = 8;                // producer warps; warp k owns K-steps k, k+8, ... and stage k
+constexpr int TC_NPW = 7;                // producer warps; warp k owns K-steps k, k+8, ... and stage k
 constexpr int TC_PROD_WARP0 = 5;         // first producer warp
 constexpr int TC_THREADS = 32 * (TC_PROD_WARP0 + TC_NPW);
-constexpr int TC_STAGES = TC_NPW;
+constexpr int TC_MAX_STAGES = 12;         // stage ring is decoupled from the producer warps: step gs -> stage gs % n_stages
 constexpr int TC_BATCH = 8;              // 16-byte loads in flight per lane per batch (2 batches in flight)
 constexpr int TC_MAX_KSTEPS = 64;        // M <= 64
 constexpr int TC_MAX_J = 16;
@@ -67,6 +67,7 @@ struct TcParams {
     int master_bytes;
     int a_rows;              // rows per (residue, kc) chunk  -> LBO_A = a_rows * 16
     int rbp;                 // padded rows per (plane, kc) chunk of a stage (odd) -> LBO_B = rbp * 16
+    int n_stages;            // shared-memory stages (TC_NPW < n_stages <= TC_MAX_STAGES)
     const uint32_t *hist_in;
     int H;
     unsigned shift;
@@ -97,9 +98,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int *er
     long long t0 = 0;
     for (uint32_t spins = 0; !done; ++spins) {
         asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
             : "=r"(done)
-            : "r"(bar), "r"(parity)
+            : "r"(bar), "r"(parity), "r"(20000u)  // suspend-time hint (ns): fewer wake-ups while idle
             : "memory");
         if (!done && (spins & 1023) == 1023) {
             const long long now = clock64();
@@ -137,6 +138,12 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t d
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
         "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 {
@@ -183,24 +190,37 @@ struct TcBatch {
 
 // Interior batch (warp-uniform decision): every row-block and sample of the batch is inside the
 // block and 16-byte aligned -> straight-line code, no per-iteration predicates.
+template <int DBG>
 __device__ __forceinline__ void tc_batch_load_fast(TcBatch &t, const uint32_t *p, size_t stride_words)
 {
     t.fast = ~0u;
 #pragma unroll
-    for (int it = 0; it < TC_BATCH; ++it) t.q[it] = ldg_stream(reinterpret_cast<const uint4 *>(p + it * stride_words));
+    for (int it = 0; it < TC_BATCH; ++it) {
+        if (DBG & 2)
+            t.q[it] = make_uint4(it, 2, 3, 4);  // timing experiment: no global loads
+        else
+            t.q[it] = ldg_stream(reinterpret_cast<const uint4 *>(p + it * stride_words));
+    }
 }
 
+template <int DBG>
 __device__ __forceinline__ void tc_batch_store_fast(const TcBatch &t, uint8_t *lo, uint8_t *hi)
 {
+    uint32_t sink = 0;
 #pragma unroll
     for (int it = 0; it < TC_BATCH; ++it) {
         uint32_t re_lo, re_hi, im_lo, im_hi;
         split4(t.q[it], re_lo, re_hi, im_lo, im_hi);
+        if (DBG & 8) {  // timing experiment: no shared-memory stores
+            sink ^= re_lo ^ re_hi ^ im_lo ^ im_hi;
+            continue;
+        }
         *reinterpret_cast<uint32_t *>(lo + it * 128) = re_lo;   // 4 row-blocks further = 8 rows = 128 bytes
         *reinterpret_cast<uint32_t *>(lo + it * 128 + 16) = im_lo;
         *reinterpret_cast<uint32_t *>(hi + it * 128) = re_hi;
         *reinterpret_cast<uint32_t *>(hi + it * 128 + 16) = im_hi;
     }
+    if ((DBG & 8) && sink == 0x12345678u) *reinterpret_cast<uint32_t *>(lo) = sink;
 }
 
 // n0: sample index of (row-block rb_first + (lane >> 3), this lane's piece, this K-step)
@@ -250,6 +270,7 @@ __device__ __forceinline__ void tc_batch_store(TcBatch &t, const TcParams &P, co
     }
 }
 
+template <int DBG>
 __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_constant__ TcParams P)
 {
     extern __shared__ __align__(128) uint8_t tc_smem_raw[];
@@ -259,21 +280,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
     const int stage_bytes = 4 * P.rbp * 16;  // 2 planes x 2 kc chunks
     uint8_t *a_smem = smem;
     uint8_t *stages = smem + ((P.master_bytes + 127) & ~127);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(stages + TC_STAGES * stage_bytes);
+    const int NS = P.n_stages;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(stages + NS * stage_bytes);
     // bars: full[NS], empty[NS], tmem_full[2], tmem_empty[2]
-    const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * TC_STAGES;
-    const uint32_t bar_tfull = bar_empty + 8 * TC_STAGES, bar_tempty = bar_tfull + 16;
+    const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * TC_MAX_STAGES;
+    const uint32_t bar_tfull = bar_empty + 8 * TC_MAX_STAGES, bar_tempty = bar_tfull + 16;
     __shared__ uint32_t tmem_base_s;
 
     // ---- setup ------------------------------------------------------------------------------
     for (int i = tid; i < P.master_bytes / 16; i += TC_THREADS)
         reinterpret_cast<uint4 *>(a_smem)[i] = __ldg(reinterpret_cast<const uint4 *>(P.master) + i);
     // rows of the stages that no producer ever writes (the padding row) must be defined: zero all
-    for (int i = tid; i < TC_STAGES * stage_bytes / 16; i += TC_THREADS)
+    for (int i = tid; i < NS * stage_bytes / 16; i += TC_THREADS)
         reinterpret_cast<uint4 *>(stages)[i] = make_uint4(0, 0, 0, 0);
     fence_async_smem();
     if (tid == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) {
+        for (int s = 0; s < NS; ++s) {
             mbar_init(bar_full + 8 * s, 1);  // the owning producer warp
             mbar_init(bar_empty + 8 * s, 1);
         }
@@ -304,8 +326,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
         const int piece = lane & 7, grp = lane >> 3;
         const int halo_it = (J - 1 + 3) >> 2;            // iterations that cover the J-1 halo row-blocks
         const int NB = 4 + (halo_it > 0 ? 1 : 0);        // batches per step
-        uint8_t *stage_base = stages + pw * stage_bytes;
-        const uint32_t my_full = bar_full + 8 * pw, my_empty = bar_empty + 8 * pw;
         const int chunk = P.rbp * 16;
 
         struct Cursor {
@@ -362,7 +382,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
             batch_rb(c.b, rb, rb_lo, rb_hi);
             const long long n0 = c.row0 + (long long)rb * P.rb_stride + P.kc_stride * c.kc;
             if (interior(c))
-                tc_batch_load_fast(t, c.x + n0, it_stride);
+                tc_batch_load_fast<DBG>(t, c.x + n0, it_stride);
             else
                 tc_batch_load(t, P, c.x, n0, rb, rb_lo, rb_hi, (halo_it > 0 && c.b == 0) ? halo_it : TC_BATCH);
         };
@@ -380,6 +400,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
             do_load(ring[0], ld);
             advance(ld);
         }
+        int stage = pw;       // step gs = pw + k * TC_NPW uses stage gs % NS
         uint32_t parity = 1;  // first wait on a fresh "empty" barrier passes
         while (st.tile < P.total_tiles) {
 #pragma unroll
@@ -389,12 +410,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
                         do_load(ring[r ^ 1], ld);
                         advance(ld);
                     }
-                    if (st.b == 0) mbar_wait(my_empty, parity, P.error_flag);
+                    if (st.b == 0) mbar_wait(bar_empty + 8 * stage, parity, P.error_flag);
+                    uint8_t *stage_base = stages + stage * stage_bytes;
                     int rb, rb_lo, rb_hi;
                     batch_rb(st.b, rb, rb_lo, rb_hi);
                     uint8_t *dst = stage_base + (piece >> 2) * chunk + 2 * (rb + (J - 1)) * 16 + (piece & 3) * 4;
                     if (ring[r].fast == ~0u)
-                        tc_batch_store_fast(ring[r], dst, dst + 2 * chunk);
+                        tc_batch_store_fast<DBG>(ring[r], dst, dst + 2 * chunk);
                     else
                         tc_batch_store(ring[r], P, st.x, st.hist,
                                        st.row0 + (long long)rb * P.rb_stride + P.kc_stride * st.kc, rb, rb_lo, rb_hi,
@@ -404,8 +426,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
                         // MMA reads shared memory through it); one arrival per warp
                         fence_async_smem();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(my_full);
-                        parity ^= 1;
+                        if (lane == 0) mbar_arrive(bar_full + 8 * stage);
+                        stage += TC_NPW;
+                        if (stage >= NS) {
+                            stage -= NS;
+                            parity ^= 1;
+                        }
                     }
                     advance(st);
                 }
@@ -415,11 +441,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
         // =====================================================================================
         // MMA issuer (one thread)
         // =====================================================================================
-        if (lane == 0) {
+        // The whole warp walks the loop (warp-uniform control flow and operands, so descriptors
+        // stay in uniform registers); one elected lane issues the MMAs and the commits.
+        {
             const uint32_t idesc_lo = umma_idesc_i8(1, 0, 128, 2 * TC_NRB);  // taps s8 x lo plane u8
             const uint32_t idesc_hi = umma_idesc_i8(1, 1, 128, 2 * TC_NRB);  // taps s8 x hi plane s8
             const uint32_t a_base = smem_u32(a_smem), s_base = smem_u32(stages);
             const uint32_t lbo_a = P.a_rows * 16, lbo_b = P.rbp * 16;
+            // descriptor = constant high part | (address >> 4)
+            const uint64_t desc_a0 = umma_desc(0, lbo_a), desc_b0 = umma_desc(0, lbo_b);
             int stage = 0;
             uint32_t phase = 0;
             uint32_t acc_phases = 0;  // bit a: parity of accumulator buffer a
@@ -432,24 +462,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
                 for (int kc = 0; kc < KS; ++kc) {
                     mbar_wait(bar_full + 8 * stage, phase, P.error_flag);
                     tc_fence_after();
-                    const TcKstep ks = P.ks[kc];
+                    const int a_row = P.ks[kc].a_row, res_off = P.ks[kc].res_off;
+                    const unsigned jmask = (P.debug & 1) ? 0u : P.ks[kc].jmask;
                     const uint32_t sb = s_base + stage * stage_bytes;
-                    for (int j = 0; j < J; ++j) {
-                        if (!((ks.jmask >> j) & 1) || (P.debug & 1)) continue;
-                        const uint32_t a_addr = a_base + ks.res_off + (ks.a_row + 128 * j) * 16;
-                        const uint32_t b_addr = sb + 2 * (J - 1 - j) * 16;
-                        umma_i8(d_tmem, umma_desc(a_addr, lbo_a), umma_desc(b_addr, lbo_b), idesc_lo, accumulate);
-                        accumulate = 1;
-                        // hi byte plane: weight slot + 1  ==  master moved back by one row
-                        umma_i8(d_tmem, umma_desc(a_addr - 16, lbo_a), umma_desc(b_addr + 2 * lbo_b, lbo_b), idesc_hi, 1);
+                    if (elect_one()) {
+                        for (int j = 0; j < J; ++j) {
+                            if (!((jmask >> j) & 1)) continue;
+                            const uint32_t a_addr = a_base + res_off + (a_row + 128 * j) * 16;
+                            const uint32_t b_addr = sb + 2 * (J - 1 - j) * 16;
+                            umma_i8(d_tmem, desc_a0 | (a_addr >> 4), desc_b0 | (b_addr >> 4), idesc_lo, accumulate);
+                            // hi byte plane: weight slot + 1  ==  master moved back by one row
+                            umma_i8(d_tmem, desc_a0 | ((a_addr - 16) >> 4), desc_b0 | ((b_addr + 2 * lbo_b) >> 4),
+                                    idesc_hi, 1);
+                            accumulate = 1;
+                        }
+                        tc_commit(bar_empty + 8 * stage);  // frees the stage when these MMAs have read it
+                        if (kc == KS - 1) tc_commit(bar_tfull + 8 * acc);
                     }
-                    tc_commit(bar_empty + 8 * stage);  // frees the stage when these MMAs have read it
-                    if (++stage == TC_STAGES) {
+                    accumulate |= (jmask != 0);
+                    __syncwarp();
+                    if (++stage == NS) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                tc_commit(bar_tfull + 8 * acc);
                 acc_phases ^= 1u << acc;
                 acc ^= 1;
             }
