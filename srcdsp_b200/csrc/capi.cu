@@ -553,10 +553,11 @@ int DecBank::prepare_tc()
     }
     const int a_rows = 128 * J + 136;
     const size_t master_bytes = res_list.size() * (size_t)a_rows * 32;
-    const int rbp = 2 * (TC_NRB + J - 1) + 1;
+    const int front_pad = 2 * (4 * ((J - 1 + 3) / 4) - (J - 1));
+    const int rbp = (front_pad + 2 * (TC_NRB + J - 1)) | 1;  // odd: conflict-free byte-plane stores
     const size_t fixed = ((master_bytes + 127) & ~(size_t)127) + 512;
     int n_stages = (int)(((size_t)227 * 1024 - fixed) / ((size_t)64 * rbp));
-    if (fixed > (size_t)227 * 1024 || n_stages < TC_NPW + 1) { tc_why = "Toeplitz master + stages exceed 227 KB of shared memory"; return SRCDSP_OK; }
+    if (fixed > (size_t)227 * 1024 || n_stages < TC_OWNERS + 1) { tc_why = "Toeplitz master + stages exceed 227 KB of shared memory"; return SRCDSP_OK; }
     if (n_stages > TC_MAX_STAGES) n_stages = TC_MAX_STAGES;
     const size_t smem = fixed + (size_t)n_stages * 64 * rbp;
     std::vector<uint8_t> img(master_bytes, 0);
@@ -577,8 +578,8 @@ int DecBank::prepare_tc()
     SRCDSP_CUDA(cudaMalloc(&d_master, master_bytes));
     SRCDSP_CUDA(cudaMemcpy(d_master, img.data(), master_bytes, cudaMemcpyHostToDevice));
     if (!d_error) {
-        SRCDSP_CUDA(cudaMalloc(&d_error, sizeof(int)));
-        SRCDSP_CUDA(cudaMemset(d_error, 0, sizeof(int)));
+        SRCDSP_CUDA(cudaMalloc(&d_error, 128));  // [0] error flag, [2..] wait-cycle counters of the timing variants
+        SRCDSP_CUDA(cudaMemset(d_error, 0, 128));
     }
     tc = TcParams{};
     tc.M = M;
@@ -588,6 +589,7 @@ int DecBank::prepare_tc()
     tc.master_bytes = (int)master_bytes;
     tc.a_rows = a_rows;
     tc.rbp = rbp;
+    tc.front_pad = front_pad;
     tc.n_stages = n_stages;
     tc.error_flag = d_error;
     for (int kc = 0; kc < M; ++kc) {
@@ -610,6 +612,7 @@ int DecBank::prepare_tc()
     SRCDSP_CUDA(cudaFuncSetAttribute(dec_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
     SRCDSP_CUDA(cudaFuncSetAttribute(dec_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
     SRCDSP_CUDA(cudaFuncSetAttribute(dec_tc_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
+    SRCDSP_CUDA(cudaFuncSetAttribute(dec_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
     tc_ok = true;
     tc_why = "";
     return SRCDSP_OK;
@@ -732,6 +735,13 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
                 }
             }
             const int tgrid = (int)std::min<long long>(tc_tiles, sm_count);
+            if (T.debug & 32) {  // wait-cycle accounting variant; counters printed at the next launch
+                unsigned long long c[8];
+                cudaMemcpy(c, d_error + 2, sizeof c, cudaMemcpyDeviceToHost);
+                fprintf(stderr, "tc counters (cycles summed over CTAs): prod total %llu wait_empty %llu fence %llu | mma total %llu wait_full %llu wait_tempty %llu | epi total %llu wait_tfull %llu\n", c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7]);
+                cudaMemset(d_error + 2, 0, sizeof c);
+                dec_tc_kernel<16><<<tgrid, TC_THREADS, tc_smem, stream>>>(T);
+            } else
             switch (T.debug & 10) {  // 2 / 8: timing-experiment instantiations (wrong results)
             case 2: dec_tc_kernel<2><<<tgrid, TC_THREADS, tc_smem, stream>>>(T); break;
             case 8: dec_tc_kernel<8><<<tgrid, TC_THREADS, tc_smem, stream>>>(T); break;

@@ -39,11 +39,13 @@ namespace srcdsp {
 
 constexpr int TC_NRB = 128;              // row-blocks per tile (MMA N = 2 * NRB)
 constexpr int TC_BOUT = 32;              // outputs per row-block
-constexpr int TC_NPW = 7;                // producer warps; warp k owns K-steps k, k+8, ... and stage k
+constexpr int TC_NPW = 16;               // producer warps: HBM streaming scales with warps, not with loads per warp (tools/ldbench.cu)
+constexpr int TC_SPLIT = 2;              // warps sharing one K-step (half of the row-blocks each)
+constexpr int TC_OWNERS = TC_NPW / TC_SPLIT;  // K-steps being staged concurrently
 constexpr int TC_PROD_WARP0 = 5;         // first producer warp
 constexpr int TC_THREADS = 32 * (TC_PROD_WARP0 + TC_NPW);
 constexpr int TC_MAX_STAGES = 12;         // stage ring is decoupled from the producer warps: step gs -> stage gs % n_stages
-constexpr int TC_BATCH = 8;              // 16-byte loads in flight per lane per batch (2 batches in flight)
+constexpr int TC_BATCH = 8;              // 16-byte loads per lane per batch (4 row-blocks per iteration)
 constexpr int TC_MAX_KSTEPS = 64;        // M <= 64
 constexpr int TC_MAX_J = 16;
 
@@ -67,6 +69,7 @@ struct TcParams {
     int master_bytes;
     int a_rows;              // rows per (residue, kc) chunk  -> LBO_A = a_rows * 16
     int rbp;                 // padded rows per (plane, kc) chunk of a stage (odd) -> LBO_B = rbp * 16
+    int front_pad;           // unused rows in front of every chunk: 2 * (4*ceil((J-1)/4) - (J-1))
     int n_stages;            // shared-memory stages (TC_NPW < n_stages <= TC_MAX_STAGES)
     const uint32_t *hist_in;
     int H;
@@ -110,6 +113,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int *er
                 __trap();
             }
         }
+    }
+}
+// DBG & 16: per-role wait-cycle accounting into P.error_flag[1..] (timing experiments)
+template <int DBG>
+__device__ __forceinline__ void mbar_wait_acc(uint32_t bar, uint32_t parity, int *error_flag, long long &acc)
+{
+    if (DBG & 16) {
+        const long long t0 = clock64();
+        mbar_wait(bar, parity, error_flag);
+        acc += clock64() - t0;
+    } else {
+        mbar_wait(bar, parity, error_flag);
     }
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -181,92 +196,76 @@ __device__ __forceinline__ void split4(const uint4 q, uint32_t &re_lo, uint32_t 
     im_hi = prmt(c, d, 0x7632);
 }
 
-// A batch = TC_BATCH iterations; iteration `it` covers row-blocks rb_first + 4*it + (lane >> 3),
-// each lane one 16-byte piece (4 samples), so that 8 lanes read one whole 128-byte line.
+// A batch = up to TC_BATCH iterations; iteration `it` covers row-blocks rb + 4*it (rb includes
+// the lane's group lane >> 3), each lane one 16-byte piece (4 samples): 8 lanes read one whole
+// 128-byte line.
 struct TcBatch {
     uint4 q[TC_BATCH];
-    unsigned fast;  // bit it: q[it] holds data loaded on the aligned fast path; ~0u: interior batch
+    bool fast;  // q[] holds prefetched data; otherwise the batch is done by tc_batch_generic at store time
 };
 
-// Interior batch (warp-uniform decision): every row-block and sample of the batch is inside the
-// block and 16-byte aligned -> straight-line code, no per-iteration predicates.
+// Interior batch (warp-uniform decision): straight-line, no per-iteration predicates.
 template <int DBG>
-__device__ __forceinline__ void tc_batch_load_fast(TcBatch &t, const uint32_t *p, size_t stride_words)
+__device__ __forceinline__ void tc_batch_load_fast(TcBatch &t, const uint32_t *p, size_t stride_words, int nit)
 {
-    t.fast = ~0u;
+    t.fast = true;
 #pragma unroll
     for (int it = 0; it < TC_BATCH; ++it) {
-        if (DBG & 2)
-            t.q[it] = make_uint4(it, 2, 3, 4);  // timing experiment: no global loads
-        else
-            t.q[it] = ldg_stream(reinterpret_cast<const uint4 *>(p + it * stride_words));
+        if (it < nit) {
+            if (DBG & 2)
+                t.q[it] = make_uint4(it, 2, 3, 4);  // timing experiment: no global loads
+            else
+                t.q[it] = ldg_stream(reinterpret_cast<const uint4 *>(p + it * stride_words));
+        }
     }
 }
 
 template <int DBG>
-__device__ __forceinline__ void tc_batch_store_fast(const TcBatch &t, uint8_t *lo, uint8_t *hi)
+__device__ __forceinline__ void tc_batch_store_fast(const TcBatch &t, uint8_t *lo, uint8_t *hi, int nit)
 {
     uint32_t sink = 0;
 #pragma unroll
     for (int it = 0; it < TC_BATCH; ++it) {
-        uint32_t re_lo, re_hi, im_lo, im_hi;
-        split4(t.q[it], re_lo, re_hi, im_lo, im_hi);
-        if (DBG & 8) {  // timing experiment: no shared-memory stores
-            sink ^= re_lo ^ re_hi ^ im_lo ^ im_hi;
-            continue;
+        if (it < nit) {
+            uint32_t re_lo, re_hi, im_lo, im_hi;
+            split4(t.q[it], re_lo, re_hi, im_lo, im_hi);
+            if (DBG & 8) {  // timing experiment: no shared-memory stores
+                sink ^= re_lo ^ re_hi ^ im_lo ^ im_hi;
+                continue;
+            }
+            *reinterpret_cast<uint32_t *>(lo + it * 128) = re_lo;  // 4 row-blocks further = 8 rows = 128 bytes
+            *reinterpret_cast<uint32_t *>(lo + it * 128 + 16) = im_lo;
+            *reinterpret_cast<uint32_t *>(hi + it * 128) = re_hi;
+            *reinterpret_cast<uint32_t *>(hi + it * 128 + 16) = im_hi;
         }
-        *reinterpret_cast<uint32_t *>(lo + it * 128) = re_lo;   // 4 row-blocks further = 8 rows = 128 bytes
-        *reinterpret_cast<uint32_t *>(lo + it * 128 + 16) = im_lo;
-        *reinterpret_cast<uint32_t *>(hi + it * 128) = re_hi;
-        *reinterpret_cast<uint32_t *>(hi + it * 128 + 16) = im_hi;
     }
     if ((DBG & 8) && sink == 0x12345678u) *reinterpret_cast<uint32_t *>(lo) = sink;
 }
 
-// n0: sample index of (row-block rb_first + (lane >> 3), this lane's piece, this K-step)
-__device__ __forceinline__ void tc_batch_load(TcBatch &t, const TcParams &P, const uint32_t *x, long long n0,
-                                              int rb, int rb_lo, int rb_hi, int nit)
-{
-    t.fast = 0;
-#pragma unroll
-    for (int it = 0; it < TC_BATCH; ++it) {
-        if (it >= nit) break;
-        const long long n = n0 + (long long)it * 4 * P.rb_stride;
-        const int r = rb + 4 * it;
-        if (r >= rb_lo && r < rb_hi && P.vec_in && n >= 0 && n + 4 <= P.n_in) {
-            t.q[it] = ldg_stream(reinterpret_cast<const uint4 *>(x + n));
-            t.fast |= 1u << it;
-        }
-    }
-}
-
-// dst: stage address of (plane lo, this lane's kc chunk, re row of row-block rb, this lane's word)
-__device__ __forceinline__ void tc_batch_store(TcBatch &t, const TcParams &P, const uint32_t *x, const uint32_t *hist,
-                                               long long n0, int rb, int rb_lo, int rb_hi, int nit, uint8_t *dst)
+// Edge batches (history in front of the block, ragged end, unaligned buffers): scalar, checked,
+// not prefetched.  Out of line to keep the hot loop small.
+// n0: sample index of (row-block rb, this lane's piece, this K-step); dst: its (plane lo, re) word.
+__device__ __noinline__ void tc_batch_generic(const TcParams &P, const uint32_t *x, const uint32_t *hist, long long n0,
+                                              int rb, int rb_lo, int rb_hi, int nit, uint8_t *dst)
 {
     const int chunk = P.rbp * 16;  // bytes per (plane, kc) chunk
-#pragma unroll
-    for (int it = 0; it < TC_BATCH; ++it) {
-        if (it >= nit) break;
+    for (int it = 0; it < nit; ++it) {
         const int r = rb + 4 * it;
-        if (r >= rb_lo && r < rb_hi) {
-            uint4 q = t.q[it];
-            if (!((t.fast >> it) & 1)) {
-                const long long n = n0 + (long long)it * 4 * P.rb_stride;
-                q.x = tc_sample(x, hist, P.H, P.n_in, n);
-                q.y = tc_sample(x, hist, P.H, P.n_in, n + 1);
-                q.z = tc_sample(x, hist, P.H, P.n_in, n + 2);
-                q.w = tc_sample(x, hist, P.H, P.n_in, n + 3);
-            }
-            uint32_t re_lo, re_hi, im_lo, im_hi;
-            split4(q, re_lo, re_hi, im_lo, im_hi);
-            uint8_t *lo = dst + it * (8 * 16);  // 4 row-blocks further = 8 rows
-            uint8_t *hi = lo + 2 * chunk;
-            *reinterpret_cast<uint32_t *>(lo) = re_lo;
-            *reinterpret_cast<uint32_t *>(lo + 16) = im_lo;
-            *reinterpret_cast<uint32_t *>(hi) = re_hi;
-            *reinterpret_cast<uint32_t *>(hi + 16) = im_hi;
-        }
+        if (r < rb_lo || r >= rb_hi) continue;
+        const long long n = n0 + (long long)it * 4 * P.rb_stride;
+        uint4 q;
+        q.x = tc_sample(x, hist, P.H, P.n_in, n);
+        q.y = tc_sample(x, hist, P.H, P.n_in, n + 1);
+        q.z = tc_sample(x, hist, P.H, P.n_in, n + 2);
+        q.w = tc_sample(x, hist, P.H, P.n_in, n + 3);
+        uint32_t re_lo, re_hi, im_lo, im_hi;
+        split4(q, re_lo, re_hi, im_lo, im_hi);
+        uint8_t *lo = dst + it * 128;
+        uint8_t *hi = lo + 2 * chunk;
+        *reinterpret_cast<uint32_t *>(lo) = re_lo;
+        *reinterpret_cast<uint32_t *>(lo + 16) = im_lo;
+        *reinterpret_cast<uint32_t *>(hi) = re_hi;
+        *reinterpret_cast<uint32_t *>(hi + 16) = im_hi;
     }
 }
 
@@ -296,7 +295,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
     fence_async_smem();
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) {
-            mbar_init(bar_full + 8 * s, 1);  // the owning producer warp
+            mbar_init(bar_full + 8 * s, TC_SPLIT);  // the producer warps sharing the K-step
             mbar_init(bar_empty + 8 * s, 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -319,123 +318,105 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
 
     if (warp >= TC_PROD_WARP0) {
         // =====================================================================================
-        // producers: warp pw owns K-steps pw, pw + 8, ... of the flattened (tile, K-step) sequence
-        // and shared-memory stage pw.  A step is HB halo + 4 main batches of 8 iterations.
+        // producers.  Owner o = pw / TC_SPLIT stages K-steps o, o + TC_OWNERS, ... of the flattened
+        // (tile, K-step) sequence (step gs -> stage gs % NS); its TC_SPLIT warps take half of the
+        // 128 row-blocks each (warp 0 of the owner also the J-1 halo row-blocks in front of the
+        // tile).  A warp has few loads in flight (hardware limit, tools/ldbench.cu), so HBM is
+        // covered by the NUMBER of producer warps; the code per warp is a plain load -> split ->
+        // store loop with everything non-trivial hoisted to once per K-step.
         // =====================================================================================
         const int pw = warp - TC_PROD_WARP0;
+        const int owner = pw / TC_SPLIT, part = pw % TC_SPLIT;
+        long long w_wait = 0, w_fence = 0;
+        const long long w_t0 = clock64();
         const int piece = lane & 7, grp = lane >> 3;
-        const int halo_it = (J - 1 + 3) >> 2;            // iterations that cover the J-1 halo row-blocks
-        const int NB = 4 + (halo_it > 0 ? 1 : 0);        // batches per step
+        const int halo_it = (part == 0) ? (J - 1 + 3) >> 2 : 0;  // iterations of the halo batch of this warp
+        constexpr int ROWS_PER_WARP = TC_NRB / TC_SPLIT;
+        constexpr int MAIN_BATCHES = ROWS_PER_WARP / (4 * TC_BATCH);
         const int chunk = P.rbp * 16;
+        const size_t it_stride = (size_t)4 * P.rb_stride;  // words between iterations of a batch
+        const int row_first = part * ROWS_PER_WARP;        // first main row-block of this warp
 
-        struct Cursor {
-            long long tile;
-            int kc, b;
-            const uint32_t *x, *hist;
-            long long row0;  // (tt * NRB) * G + 4 * piece : sample index of row-block 0, this piece
-        };
-        auto seek = [&](Cursor &c) {
-            if (c.tile < P.total_tiles) {
-                const unsigned t = (unsigned)c.tile;
-                const unsigned ch = t / (unsigned)P.tiles_per_ch;
-                const unsigned tt = t - ch * (unsigned)P.tiles_per_ch;
-                c.x = P.in + (size_t)ch * P.in_stride;
-                c.hist = P.hist_in + (size_t)ch * P.H;
-                c.row0 = (long long)tt * TC_NRB * (long long)P.G + 4 * piece;
+        long long tile = first_tile;
+        int kc = owner;
+        while (kc >= KS && tile < P.total_tiles) {
+            kc -= KS;
+            tile += tile_step;
+        }
+        long long cur_tile = -1;
+        const uint32_t *x = nullptr, *hist = nullptr;
+        long long tile0 = 0;
+        int stage = owner % NS;  // step gs uses stage gs % NS
+        uint32_t parity = 1;     // first wait on a fresh "empty" barrier passes
+        TcBatch t;
+        while (tile < P.total_tiles) {
+            if (tile != cur_tile) {  // one division per tile
+                const unsigned tl = (unsigned)tile;
+                const unsigned ch = tl / (unsigned)P.tiles_per_ch;
+                const unsigned tt = tl - ch * (unsigned)P.tiles_per_ch;
+                x = P.in + (size_t)ch * P.in_stride;
+                hist = P.hist_in + (size_t)ch * P.H;
+                tile0 = (long long)tt * TC_NRB * (long long)P.G;
+                cur_tile = tile;
             }
-        };
-        auto advance = [&](Cursor &c) {
-            if (++c.b == NB) {
-                c.b = 0;
-                c.kc += TC_NPW;
-                if (c.kc >= KS) {
-                    do {
-                        c.kc -= KS;
-                        c.tile += tile_step;
-                    } while (c.kc >= KS);
-                    seek(c);
+            const long long col = tile0 + (long long)P.kc_stride * kc + 4 * piece;  // sample of (row 0, piece)
+            const bool fast_main = P.vec_in && col - 4 * piece + (long long)(TC_NRB - 1) * P.rb_stride + 32 <= P.n_in;
+            const bool fast_halo = P.vec_in && tile0 > 0;  // the previous tile of the same block exists
+
+            mbar_wait_acc<DBG>(bar_empty + 8 * stage, parity, P.error_flag, w_wait);
+            // (plane lo, this lane's kc chunk, re row of row-block rb, this lane's word) for rb = grp;
+            // rows are shifted by front_pad so that the unused lanes of a prefetched halo batch
+            // (row-blocks below -(J-1)) land in padding instead of out of bounds
+            uint8_t *dst0 = stages + stage * stage_bytes + (piece >> 2) * chunk +
+                            (P.front_pad + 2 * (grp + (J - 1))) * 16 + (piece & 3) * 4;
+            if (halo_it > 0) {
+                const int rb = -4 * halo_it + grp;
+                uint8_t *dst = dst0 - 4 * halo_it * 32;
+                if (fast_halo) {
+                    tc_batch_load_fast<DBG>(t, x + (col + (long long)rb * P.rb_stride), it_stride, halo_it);
+                    tc_batch_store_fast<DBG>(t, dst, dst + 2 * chunk, halo_it);
+                } else {
+                    tc_batch_generic(P, x, hist, col + (long long)rb * P.rb_stride, rb, -(J - 1), 0, halo_it, dst);
                 }
             }
-        };
-        // first row-block of batch b for this lane, and the lowest valid row-block of that batch
-        auto batch_rb = [&](int b, int &rb, int &rb_lo, int &rb_hi) {
-            if (halo_it > 0 && b == 0) {
-                rb = -4 * halo_it + grp;
-                rb_lo = -(J - 1);
-                rb_hi = 0;
+#pragma unroll 1
+            for (int mb = 0; mb < MAIN_BATCHES; ++mb) {
+                const int rb = row_first + 4 * TC_BATCH * mb + grp;
+                uint8_t *dst = dst0 + (rb - grp) * 32;
+                if (fast_main) {
+                    tc_batch_load_fast<DBG>(t, x + (col + (long long)rb * P.rb_stride), it_stride, TC_BATCH);
+                    tc_batch_store_fast<DBG>(t, dst, dst + 2 * chunk, TC_BATCH);
+                } else {
+                    tc_batch_generic(P, x, hist, col + (long long)rb * P.rb_stride, rb, 0, TC_NRB, TC_BATCH, dst);
+                }
+            }
+            // every writer fences its generic-proxy stores towards the async proxy (the MMA reads
+            // shared memory through it); one arrival per warp
+            if (DBG & 16) {
+                const long long f0 = clock64();
+                fence_async_smem();
+                w_fence += clock64() - f0;
             } else {
-                rb = 32 * (b - (halo_it > 0 ? 1 : 0)) + grp;
-                rb_lo = 0;
-                rb_hi = TC_NRB;
+                fence_async_smem();
             }
-        };
-        const size_t it_stride = (size_t)4 * P.rb_stride;
-        // warp-uniform: batch b of the cursor's step lies completely inside [0, n_in) (main batches only)
-        auto interior = [&](const Cursor &c) {
-            if (halo_it > 0 && c.b == 0) return false;
-            const int mb = c.b - (halo_it > 0 ? 1 : 0);
-            const long long last = c.row0 - 4 * piece + (long long)(32 * mb + 31) * P.rb_stride + P.kc_stride * c.kc + 32;
-            return P.vec_in && last <= P.n_in;
-        };
-        auto do_load = [&](TcBatch &t, const Cursor &c) {
-            int rb, rb_lo, rb_hi;
-            batch_rb(c.b, rb, rb_lo, rb_hi);
-            const long long n0 = c.row0 + (long long)rb * P.rb_stride + P.kc_stride * c.kc;
-            if (interior(c))
-                tc_batch_load_fast<DBG>(t, c.x + n0, it_stride);
-            else
-                tc_batch_load(t, P, c.x, n0, rb, rb_lo, rb_hi, (halo_it > 0 && c.b == 0) ? halo_it : TC_BATCH);
-        };
-        Cursor ld{first_tile, pw, 0, nullptr, nullptr, 0}, st{first_tile, pw, 0, nullptr, nullptr, 0};
-        while (ld.kc >= KS) {
-            ld.kc -= KS;
-            ld.tile += tile_step;
-        }
-        st.kc = ld.kc;
-        st.tile = ld.tile;
-        seek(ld);
-        seek(st);
-        TcBatch ring[2];
-        if (ld.tile < P.total_tiles) {
-            do_load(ring[0], ld);
-            advance(ld);
-        }
-        int stage = pw;       // step gs = pw + k * TC_NPW uses stage gs % NS
-        uint32_t parity = 1;  // first wait on a fresh "empty" barrier passes
-        while (st.tile < P.total_tiles) {
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                if (st.tile < P.total_tiles) {
-                    if (ld.tile < P.total_tiles) {
-                        do_load(ring[r ^ 1], ld);
-                        advance(ld);
-                    }
-                    if (st.b == 0) mbar_wait(bar_empty + 8 * stage, parity, P.error_flag);
-                    uint8_t *stage_base = stages + stage * stage_bytes;
-                    int rb, rb_lo, rb_hi;
-                    batch_rb(st.b, rb, rb_lo, rb_hi);
-                    uint8_t *dst = stage_base + (piece >> 2) * chunk + 2 * (rb + (J - 1)) * 16 + (piece & 3) * 4;
-                    if (ring[r].fast == ~0u)
-                        tc_batch_store_fast<DBG>(ring[r], dst, dst + 2 * chunk);
-                    else
-                        tc_batch_store(ring[r], P, st.x, st.hist,
-                                       st.row0 + (long long)rb * P.rb_stride + P.kc_stride * st.kc, rb, rb_lo, rb_hi,
-                                       (halo_it > 0 && st.b == 0) ? halo_it : TC_BATCH, dst);
-                    if (st.b == NB - 1) {
-                        // every writer fences its generic-proxy stores towards the async proxy (the
-                        // MMA reads shared memory through it); one arrival per warp
-                        fence_async_smem();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_full + 8 * stage);
-                        stage += TC_NPW;
-                        if (stage >= NS) {
-                            stage -= NS;
-                            parity ^= 1;
-                        }
-                    }
-                    advance(st);
-                }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_full + 8 * stage);
+            stage += TC_OWNERS;
+            while (stage >= NS) {
+                stage -= NS;
+                parity ^= 1;
             }
+            kc += TC_OWNERS;
+            while (kc >= KS) {
+                kc -= KS;
+                tile += tile_step;
+            }
+        }
+        if ((DBG & 16) && lane == 0) {
+            unsigned long long *cnt = reinterpret_cast<unsigned long long *>(P.error_flag + 2);
+            atomicAdd(cnt + 0, (unsigned long long)(clock64() - w_t0));  // producer total
+            atomicAdd(cnt + 1, (unsigned long long)w_wait);               // producer waiting for an empty stage
+            atomicAdd(cnt + 2, (unsigned long long)w_fence);              // producer in fence.proxy.async
         }
     } else if (warp == 4) {
         // =====================================================================================
@@ -454,13 +435,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
             uint32_t phase = 0;
             uint32_t acc_phases = 0;  // bit a: parity of accumulator buffer a
             int acc = 0;
+            long long m_full = 0, m_tempty = 0;
+            const long long m_t0 = clock64();
             for (long long tile = first_tile; tile < P.total_tiles; tile += tile_step) {
-                mbar_wait(bar_tempty + 8 * acc, ((acc_phases >> acc) & 1) ^ 1, P.error_flag);
+                mbar_wait_acc<DBG>(bar_tempty + 8 * acc, ((acc_phases >> acc) & 1) ^ 1, P.error_flag, m_tempty);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * (2 * TC_NRB);
                 uint32_t accumulate = 0;
                 for (int kc = 0; kc < KS; ++kc) {
-                    mbar_wait(bar_full + 8 * stage, phase, P.error_flag);
+                    mbar_wait_acc<DBG>(bar_full + 8 * stage, phase, P.error_flag, m_full);
                     tc_fence_after();
                     const int a_row = P.ks[kc].a_row, res_off = P.ks[kc].res_off;
                     const unsigned jmask = (P.debug & 1) ? 0u : P.ks[kc].jmask;
@@ -469,7 +452,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
                         for (int j = 0; j < J; ++j) {
                             if (!((jmask >> j) & 1)) continue;
                             const uint32_t a_addr = a_base + res_off + (a_row + 128 * j) * 16;
-                            const uint32_t b_addr = sb + 2 * (J - 1 - j) * 16;
+                            const uint32_t b_addr = sb + (P.front_pad + 2 * (J - 1 - j)) * 16;
                             umma_i8(d_tmem, desc_a0 | (a_addr >> 4), desc_b0 | (b_addr >> 4), idesc_lo, accumulate);
                             // hi byte plane: weight slot + 1  ==  master moved back by one row
                             umma_i8(d_tmem, desc_a0 | ((a_addr - 16) >> 4), desc_b0 | ((b_addr + 2 * lbo_b) >> 4),
@@ -489,6 +472,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
                 acc_phases ^= 1u << acc;
                 acc ^= 1;
             }
+            if ((DBG & 16) && lane == 0) {
+                unsigned long long *cnt = reinterpret_cast<unsigned long long *>(P.error_flag + 2);
+                atomicAdd(cnt + 3, (unsigned long long)(clock64() - m_t0));  // MMA warp total
+                atomicAdd(cnt + 4, (unsigned long long)m_full);               // MMA waiting for a full stage
+                atomicAdd(cnt + 5, (unsigned long long)m_tempty);             // MMA waiting for a free accumulator
+            }
         }
     } else {
         // =====================================================================================
@@ -496,13 +485,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
         // =====================================================================================
         const int w = lane & 3;
         const int b = 8 * warp + (lane >> 2);
+        long long e_wait = 0;
+        const long long e_t0 = clock64();
         uint32_t acc_phases = 0;
         int acc = 0;
         for (long long tile = first_tile; tile < P.total_tiles; tile += tile_step) {
             const int ch = (int)(tile / P.tiles_per_ch);
             const long long tt = tile - (long long)ch * P.tiles_per_ch;
             uint32_t *o = P.out + (size_t)ch * P.out_stride;
-            mbar_wait(bar_tfull + 8 * acc, (acc_phases >> acc) & 1, P.error_flag);
+            mbar_wait_acc<DBG>(bar_tfull + 8 * acc, (acc_phases >> acc) & 1, P.error_flag, e_wait);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(32 * warp) << 16) + acc * (2 * TC_NRB);
 #pragma unroll 1
@@ -546,8 +537,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
             acc_phases ^= 1u << acc;
             acc ^= 1;
         }
+        if ((DBG & 16) && lane == 0) {
+            unsigned long long *cnt = reinterpret_cast<unsigned long long *>(P.error_flag + 2);
+            atomicAdd(cnt + 6, (unsigned long long)(clock64() - e_t0));  // epilogue warp total
+            atomicAdd(cnt + 7, (unsigned long long)e_wait);               // epilogue waiting for accumulators
+        }
     }
 
+    if ((DBG & 16) && warp < 4 && lane == 0) {
+        unsigned long long *cnt = reinterpret_cast<unsigned long long *>(P.error_flag + 2);
+        // NB e_t0 / e_wait only exist in the epilogue branch; recorded there
+    }
     // ---- teardown ---------------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
