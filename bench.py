@@ -223,8 +223,9 @@ def main():
     n_out_total = C * (n // M) * world
     value = n_out_total * args.steps / (total_ms * 1e-3) / 1e6
 
-    # roofline of the dominant kernel (dec_fir_kernel: one launch per step; the history kernel that
-    # shares the step is ~2 us).  Algorithmic bytes per launch = 68 B/output x outputs per launch.
+    # roofline of the dominant kernel (the decimating-FIR kernel: one launch per step; the history
+    # kernel that shares the step is ~2 us).  Algorithmic bytes per launch = (4*M + 4) B/output x
+    # outputs per launch (68 B/output for cfg2).
     peak, peak_src = peaks()
     k_ms = float(np.mean(step_ms))
     alg_bytes = BYTES_PER_OUT(M) * C * (n // M)
@@ -234,10 +235,11 @@ def main():
         traffic = json.load(open(tp)).get(args.workload)
     roof = {"bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
             "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / peak, "traffic": traffic,
-            "kernel": "dec_fir_kernel", "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+            "kernel": dec.last_kernel, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
             "kernel_ms": k_ms,
-            "imad_note": "int16 x int32-tap FIR is INT32-multiply bound, not HBM bound: 2*taps IMAD per output "
-                         "(SURVEY.md 8(d)); imad_frac below is against 148 SM x 64 IMAD/clk x sm_max_mhz"}
+            "imad_note": "imad_frac = the same work counted as 2*taps INT32 multiply-adds per output against "
+                         "148 SM x 64 IMAD/clk x sm_max_mhz: the ceiling of any CUDA-core kernel (SURVEY.md 8(d)); "
+                         "the tcgen05 int8 kernel is not bound by it"}
     if clocks and clocks.get("sm_max_mhz"):
         imad_peak = 148 * 64 * clocks["sm_max_mhz"] * 1e6
         roof["imad_frac"] = (2 * nt * C * (n // M)) / (k_ms * 1e-3) / imad_peak

@@ -96,8 +96,8 @@ int srcdsp_dec_destroy(srcdsp_dec_t h);
  * must be 0, else E_SIZE, the reference assert :122); ctor of the obsolete twin
  * dnsampling_filters.h:83-97 when 0 (any ntaps >= 1).  Zeroes the history (history.resize on a
  * fresh object) and leftShift, computes coeffScaling = floor(log2(sum |c|)).
- * NB the reference keeps old history entries when setCoeffs is called again with a different
- * size; this ABI clears it (documented difference). */
+ * Called again on a live object it behaves like the reference's history.resize(ntaps-1): the
+ * first min(old, new) history entries are kept, the rest are zero. */
 int srcdsp_dec_set_coeffs(srcdsp_dec_t h, const int32_t *taps, int ntaps, int require_multiple_of_m);
 /* setLeftShiftBy2: dsptl_dnsampling_filters.h:63 */
 int srcdsp_dec_set_left_shift(srcdsp_dec_t h, int left_shift);
@@ -118,6 +118,8 @@ int srcdsp_dec_sync(srcdsp_dec_t h);
 /* kernel selection: 0 = automatic, 1 = force the INT32-FMA (IMAD) kernel, 2 = force the
  * tcgen05 int8 Toeplitz kernel (E_STATE at step if the taps do not fit it). */
 int srcdsp_dec_set_kernel(srcdsp_dec_t h, int kind);
+/* which FIR kernel the last step launched: 0 none yet, 1 IMAD (dec_fir_kernel), 2 tcgen05 (dec_tc_kernel) */
+int srcdsp_dec_get_last_kernel(srcdsp_dec_t h, int *kind);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Fused DDC chain: mixer -> dec1 [-> dec2].  One call == the separate steps, bit for bit:     */

@@ -196,6 +196,12 @@ class FilterDnsamplingFir(_Handle):
         check(lib().srcdsp_dec_set_kernel(self._h, kind))
 
     @property
+    def last_kernel(self) -> str:
+        v = C.c_int()
+        check(lib().srcdsp_dec_get_last_kernel(self._h, C.byref(v)))
+        return {0: "none", 1: "dec_fir_kernel (IMAD)", 2: "dec_tc_kernel (tcgen05 int8)"}[v.value]
+
+    @property
     def coeffScaling(self) -> int:
         v = C.c_int()
         check(lib().srcdsp_dec_get_coeff_scaling(self._h, C.byref(v)))

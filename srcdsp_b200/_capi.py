@@ -58,6 +58,7 @@ PROTOTYPES = {
     "srcdsp_dec_set_stream": (C.c_int, [_vp, _vp]),
     "srcdsp_dec_sync": (C.c_int, [_vp]),
     "srcdsp_dec_set_kernel": (C.c_int, [_vp, C.c_int]),
+    "srcdsp_dec_get_last_kernel": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     # fused chain
     "srcdsp_ddc_create": (C.c_int, [C.POINTER(_vp), _vp, _vp, _vp]),
     "srcdsp_ddc_destroy": (C.c_int, [_vp]),

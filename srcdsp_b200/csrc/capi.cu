@@ -390,6 +390,7 @@ struct DecBank : Bank {
     int coeff_scaling = 0;
     int left_shift = 0;
     int kernel_kind = 0;
+    int last_kernel = 0;
     std::vector<int32_t> taps;
     int32_t *d_taps_poly = nullptr;
     uint32_t *d_hist[2] = {nullptr, nullptr};
@@ -698,6 +699,7 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
         P.freq = mixer->d_freq;
         P.pm = mixer->pm();
         SRCDSP_TRY(launch_dec_m<true>(P, (int)grid, nt_threads, smem_bytes, stream));
+        last_kernel = 1;
         dec_history_kernel<true><<<hgrid, 256, 0, stream>>>(in, in_stride, (long long)n_in, d_hist[cur], d_hist[cur ^ 1],
                                                             H, mixer->d_cs, mixer->d_phi[mixer->cur],
                                                             mixer->d_phi[mixer->cur ^ 1], mixer->d_freq, mixer->pm());
@@ -750,8 +752,10 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
             }
             SRCDSP_LAUNCH_CHECK();
             count_launch();
+            last_kernel = 2;
         } else {
             SRCDSP_TRY(launch_dec_m<false>(P, (int)grid, nt_threads, smem_bytes, stream));
+            last_kernel = 1;
         }
         dec_history_kernel<false><<<hgrid, 256, 0, stream>>>(in, in_stride, (long long)n_in, d_hist[cur],
                                                              d_hist[cur ^ 1], H, nullptr, nullptr, nullptr, nullptr,
@@ -1205,6 +1209,13 @@ int srcdsp_dec_set_kernel(srcdsp_dec_t h, int kind)
     CHECK_HANDLE(h);
     if (kind < 0 || kind > 2) return fail(SRCDSP_E_INVALID, "kernel kind must be 0, 1 or 2");
     h->kernel_kind = kind;
+    return SRCDSP_OK;
+}
+int srcdsp_dec_get_last_kernel(srcdsp_dec_t h, int *kind)
+{
+    CHECK_HANDLE(h);
+    if (!kind) return fail(SRCDSP_E_INVALID, "null pointer");
+    *kind = h->last_kernel;
     return SRCDSP_OK;
 }
 int srcdsp_dec_step(srcdsp_dec_t h, const int16_t *in, size_t in_stride, size_t n_in, int16_t *out,
