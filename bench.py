@@ -35,14 +35,37 @@ sys.path.insert(0, ROOT)
 
 SEED = 0x5EED0002
 WORKLOADS = {
-    # name: (channels per GPU, samples per channel, M, ntaps, fused mixer)
-    "cfg2": dict(channels=256, n=1 << 24, M=16, ntaps=255, mix=False,
+    # kind: dec = decimator, ddc = NCO mix + decimator, ddc2 = mix + two decimators, up = interpolator
+    "cfg2": dict(kind="dec", channels=256, n=1 << 24, M=16, ntaps=255, mix=False,
                  desc="cfg2: decimate-by-16 255-tap polyphase FIR, 256 ch x 16Mi cs16 samples per GPU"),
-    "ddc16": dict(channels=256, n=1 << 24, M=16, ntaps=255, mix=True,
+    "ddc16": dict(kind="ddc", channels=256, n=1 << 24, M=16, ntaps=255, mix=True,
                   desc="ddc16: NCO mix fused into decimate-by-16 255-tap FIR, 256 ch x 16Mi per GPU"),
-    "smoke": dict(channels=8, n=1 << 18, M=16, ntaps=255, mix=False, desc="smoke: 8 ch x 256Ki"),
+    "cfg1": dict(kind="ddc", channels=1, n=1 << 20, M=8, ntaps=63, mix=True,
+                 desc="cfg1: NCO mix + decimate-by-8 63-tap FIR, 1 ch x 1Mi samples"),
+    "cfg3": dict(kind="ddc2", channels=1024, n=1 << 22, M=8, ntaps=63, M2=4, ntaps2=63, mix=True,
+                 desc="cfg3: NCO mix + /8 (63 taps) + /4 (63 taps), 1024 ch x 4Mi samples (per GPU when weak scaling)"),
+    "cfg4": dict(kind="up", channels=256, n=1 << 20, M=8, ntaps=64, mix=False,
+                 desc="cfg4: interpolate-by-8 64-tap FIR, 256 ch x 1Mi input samples (8Mi out) per step"),
+    "cfg5": dict(kind="dec", channels=1, n=1 << 29, M=4, ntaps=1023, mix=False,
+                 desc="cfg5 slice: decimate-by-4 1023-tap FIR, one stream slice of 512Mi samples per GPU"),
+    "smoke": dict(kind="dec", channels=8, n=1 << 18, M=16, ntaps=255, mix=False, desc="smoke: 8 ch x 256Ki"),
 }
-BYTES_PER_OUT = lambda M: 4 * M + 4  # cs16 in + cs16 out per output sample
+
+
+def bytes_per_out(w):
+    """Algorithmic HBM bytes per output sample: cs16 in + cs16 out (+ the stage-1
+    output written and re-read for the two-stage chain)."""
+    if w["kind"] == "up":
+        return 4.0 + 4.0 / w["M"]
+    if w["kind"] == "ddc2":
+        return 4.0 * w["M"] * w["M2"] + 4.0 + 8.0 * w["M2"]
+    return 4.0 * w["M"] + 4.0
+
+
+def out_per_in(w):
+    if w["kind"] == "up":
+        return float(w["M"])
+    return 1.0 / (w["M"] * w.get("M2", 1))
 
 
 def peaks():
@@ -94,7 +117,7 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
-def cpu_reference_run(w, steps: int, warmup: int, cores: int, target_cpu_seconds: float = 16.0):
+def cpu_reference_run(w, steps: int, warmup: int, cores: int, target_cpu_seconds: float = 20.0):
     """Times the unmodified reference (oracle/_ref) on a bounded sample of the workload."""
     import oracle as O
     r = O.ref()
@@ -102,26 +125,30 @@ def cpu_reference_run(w, steps: int, warmup: int, cores: int, target_cpu_seconds
     if r is None:
         raise RuntimeError("oracle/_ref is not built (run `make -C oracle` where /root/reference exists)")
     M, nt = w["M"], w["ntaps"]
-    taps = O.design_lowpass_taps(nt, M)
-    # ~1 Msample/s out per core for /16, 255 taps: size the sample for ~16 s CPU work
-    est_out_per_core_s = 0.97e6 * 255.0 / max(nt, 1)
-    total_out = target_cpu_seconds * est_out_per_core_s
+    up = w["kind"] == "up"
+    taps = O.design_interp_taps(nt, M) if up else O.design_lowpass_taps(nt, M)
+    taps2 = O.design_lowpass_taps(w["ntaps2"], w["M2"]) if w["kind"] == "ddc2" else None
     ch = min(w["channels"], 2 * cores)
     block = 1 << 16
-    n = int(total_out * M / ch) // block * block
-    n = max(block, min(n, w["n"]))
     c = O.corc()
-    x = np.stack([c.synth(SEED, k, 0, n, 2) for k in range(ch)])
     lo = (-1 + 2 * (np.arange(ch) + 0.5) / ch).astype(np.float32) if w["mix"] else None
+    kind = {"dec": 0, "ddc": 1, "ddc2": 2, "up": 3}[w["kind"]]
+    # pilot run on one 64Ki block per channel sizes the sample for ~target_cpu_seconds of CPU work
+    xp = np.stack([c.synth(SEED, k, 0, block, 2) for k in range(ch)])
+    tp, _ = r.bench_bank(kind, xp, block, cores, M, taps, w.get("M2", 1), taps2, lo_freq=lo)
+    wall = target_cpu_seconds / cores
+    n = int(block * max(1.0, wall / max(tp, 1e-6))) // block * block
+    n = max(block, min(n, w["n"], (2 << 30) // (4 * ch) // block * block))
+    x = np.stack([c.synth(SEED, k, 0, n, 2) for k in range(ch)])
     times = []
     for i in range(warmup + steps):
-        secs, _ = r.bench_bank(1 if w["mix"] else 0, x, block, cores, M, taps, lo_freq=lo)
+        secs, _ = r.bench_bank(kind, x, block, cores, M, taps, w.get("M2", 1), taps2, lo_freq=lo)
         if i >= warmup:
             times.append(secs)
-    n_out = ch * (n // M)
+    n_out = int(ch * n * out_per_in(w))
     t = float(np.mean(times))
     return dict(value=n_out / t / 1e6, unit="Msamples/s", cores=cores, kind=kind,
-                sample=f"{ch} channels x {n} samples (/{M}, {nt} taps), {r.build_info()}, "
+                sample=f"{ch} channels x {n} input samples of {w['desc'].split(':')[0]}, {r.build_info()}, "
                        f"{cores} threads, 64Ki-sample streaming blocks, mean of {len(times)} runs",
                 seconds=t), t
 
@@ -149,7 +176,7 @@ def main():
             "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
             "config": {"workload": w["desc"], "channels_per_gpu": w["channels"], "samples_per_channel": w["n"],
-                       "decimation": w["M"], "taps": w["ntaps"], "nco_mix": w["mix"],
+                       "ratio": w["M"], "taps": w["ntaps"], "nco_mix": w["mix"],
                        "sharding": "contiguous channel batches per rank, no collective",
                        "l2": "16 GiB batch per step >> 126 MB L2 (no flush needed)"}}
 
@@ -181,17 +208,27 @@ def main():
     C, n, M, nt = w["channels"], w["n"], w["M"], w["ntaps"]
     from srcdsp_b200.sharding import channel_shard
     my_ch = channel_shard(C * world, world, rank)  # weak scaling: 256 channels per GPU
-    taps = O.design_lowpass_taps(nt, M)
+    n_out = int(n * out_per_in(w))
     x = torch.empty((C, n, 2), dtype=torch.int16, device="cuda")
-    y = torch.empty((C, n // M, 2), dtype=torch.int16, device="cuda")
+    y = torch.empty((C, n_out, 2), dtype=torch.int16, device="cuda")
     S.synth_fill(x, SEED, ch0=my_ch.start, amp_shift=2)
-    dec = S.FilterDnsamplingFir(M, taps, channels=C, device=local_rank, obsolete=True)
-    dec.set_kernel(args.kernel)
-    chain = dec
-    if w["mix"]:
-        mix = S.Mixer(channels=C, device=local_rank)
-        mix.setFrequency((-1 + 2 * (np.arange(my_ch.start, my_ch.stop) + 0.5) / (C * world)).astype(np.float32))
-        chain = S.Ddc(mix, dec)
+    dec = None
+    if w["kind"] == "up":
+        chain = S.FilterUpsamplingFir(M, O.design_interp_taps(nt, M), channels=C, device=local_rank)
+        stateful = [chain]
+    else:
+        dec = S.FilterDnsamplingFir(M, O.design_lowpass_taps(nt, M), channels=C, device=local_rank, obsolete=True)
+        dec.set_kernel(args.kernel)
+        chain, stateful = dec, [dec]
+        if w["mix"]:
+            mix = S.Mixer(channels=C, device=local_rank)
+            mix.setFrequency((-1 + 2 * (np.arange(my_ch.start, my_ch.stop) + 0.5) / (C * world)).astype(np.float32))
+            dec2 = None
+            if w["kind"] == "ddc2":
+                dec2 = S.FilterDnsamplingFir(w["M2"], O.design_lowpass_taps(w["ntaps2"], w["M2"]), channels=C,
+                                             device=local_rank, obsolete=True)
+                stateful.append(dec2)
+            chain = S.Ddc(mix, dec, dec2)
 
     def barrier():
         torch.cuda.synchronize()
@@ -220,7 +257,7 @@ def main():
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
-    n_out_total = C * (n // M) * world
+    n_out_total = C * n_out * world
     value = n_out_total * args.steps / (total_ms * 1e-3) / 1e6
 
     # roofline of the dominant kernel (the decimating-FIR kernel: one launch per step; the history
@@ -228,34 +265,36 @@ def main():
     # outputs per launch (68 B/output for cfg2).
     peak, peak_src = peaks()
     k_ms = float(np.mean(step_ms))
-    alg_bytes = BYTES_PER_OUT(M) * C * (n // M)
+    alg_bytes = bytes_per_out(w) * C * n_out
     traffic = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get(args.workload)
     roof = {"bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
             "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / peak, "traffic": traffic,
-            "kernel": dec.last_kernel, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+            "kernel": dec.last_kernel if dec is not None else "up_fir_kernel", "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
             "kernel_ms": k_ms,
             "imad_note": "imad_frac = the same work counted as 2*taps INT32 multiply-adds per output against "
                          "148 SM x 64 IMAD/clk x sm_max_mhz: the ceiling of any CUDA-core kernel (SURVEY.md 8(d)); "
                          "the tcgen05 int8 kernel is not bound by it"}
     if clocks and clocks.get("sm_max_mhz"):
         imad_peak = 148 * 64 * clocks["sm_max_mhz"] * 1e6
-        roof["imad_frac"] = (2 * nt * C * (n // M)) / (k_ms * 1e-3) / imad_peak
+        macs = {"dec": 2 * nt, "ddc": 2 * nt + 4 * M, "up": 2 * nt / M,
+                "ddc2": w.get("M2", 1) * (2 * nt + 4 * M) + 2 * w.get("ntaps2", 0)}[w["kind"]]
+        roof["imad_frac"] = macs * C * n_out / (k_ms * 1e-3) / imad_peak
 
     # ---- e2e: public API with pinned HOST buffers, H2D + kernels + D2H inside the timed region ----
     e2e = None
     if not args.no_e2e:
         try:
             hin = S.PinnedBuffer(C, n)
-            hout = S.PinnedBuffer(C, n // M)
+            hout = S.PinnedBuffer(C, n_out)
             S._capi.check(S.lib().srcdsp_memcpy(local_rank, hin.array.ctypes.data, x.data_ptr(), C * n * 4))
             del x
             torch.cuda.empty_cache()
-            dec.reset()
-            chain.step(hin.array[:, : M * 4096], out=hout.array[:, :4096])  # warm the staging buffers
-            dec.reset()
+            chain.step(hin.array, out=hout.array)  # warm the staging buffers
+            for f in stateful:
+                f.reset()
             barrier()
             t0 = time.perf_counter()
             for _ in range(args.e2e_steps):
@@ -267,9 +306,9 @@ def main():
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = float(tt.item())
             e2e = {"value": n_out_total * args.e2e_steps / dt / 1e6, "unit": "Msamples/s",
-                   "h2d_bytes_per_step": C * n * 4, "d2h_bytes_per_step": C * (n // M) * 4,
+                   "h2d_bytes_per_step": C * n * 4, "d2h_bytes_per_step": C * n_out * 4,
                    "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
-                   "api": "FilterDnsamplingFir.step(host numpy view of pinned memory) -> srcdsp_dec_step"}
+                   "api": type(chain).__name__ + ".step(host numpy view of pinned memory) -> C ABI step"}
             hin.free()
             hout.free()
         except Exception as ex:  # report, never fake

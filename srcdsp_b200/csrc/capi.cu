@@ -403,10 +403,22 @@ struct DecBank : Bank {
     TcParams tc{};
     uint8_t *d_master = nullptr;
     int *d_error = nullptr;
-    size_t tc_smem = 0;
+    size_t tc_fixed = 0;  // master + barriers
     int sm_count = 148;
 
     int prepare_tc();
+    // shared-memory plan of the tensor-core kernel for a given NCO table size (0: no fused mixer)
+    int tc_layout(int table_bytes, int *n_stages, size_t *smem) const
+    {
+        const size_t avail = (size_t)226 * 1024;
+        if (tc_fixed + (size_t)table_bytes > avail) return SRCDSP_E_SIZE;
+        int ns = (int)((avail - tc_fixed - (size_t)table_bytes) / ((size_t)64 * tc.rbp));
+        if (ns < TC_OWNERS + 1) return SRCDSP_E_SIZE;
+        if (ns > TC_MAX_STAGES) ns = TC_MAX_STAGES;
+        if (n_stages) *n_stages = ns;
+        if (smem) *smem = tc_fixed + (size_t)table_bytes + (size_t)ns * 64 * tc.rbp;
+        return SRCDSP_OK;
+    }
 
     int set_coeffs(const int32_t *t, int n, int require_multiple)
     {
@@ -556,11 +568,9 @@ int DecBank::prepare_tc()
     const size_t master_bytes = res_list.size() * (size_t)a_rows * 32;
     const int front_pad = 2 * (4 * ((J - 1 + 3) / 4) - (J - 1));
     const int rbp = (front_pad + 2 * (TC_NRB + J - 1)) | 1;  // odd: conflict-free byte-plane stores
-    const size_t fixed = ((master_bytes + 127) & ~(size_t)127) + 512;
-    int n_stages = (int)(((size_t)227 * 1024 - fixed) / ((size_t)64 * rbp));
-    if (fixed > (size_t)227 * 1024 || n_stages < TC_OWNERS + 1) { tc_why = "Toeplitz master + stages exceed 227 KB of shared memory"; return SRCDSP_OK; }
-    if (n_stages > TC_MAX_STAGES) n_stages = TC_MAX_STAGES;
-    const size_t smem = fixed + (size_t)n_stages * 64 * rbp;
+    tc_fixed = ((master_bytes + 127) & ~(size_t)127) + 512;
+    tc.rbp = rbp;  // tc_layout needs it
+    if (tc_layout(0, nullptr, nullptr) != SRCDSP_OK) { tc_why = "Toeplitz master + stages exceed 227 KB of shared memory"; return SRCDSP_OK; }
     std::vector<uint8_t> img(master_bytes, 0);
     for (size_t ri = 0; ri < res_list.size(); ++ri) {
         uint8_t *base = img.data() + ri * (size_t)a_rows * 32;
@@ -591,7 +601,6 @@ int DecBank::prepare_tc()
     tc.a_rows = a_rows;
     tc.rbp = rbp;
     tc.front_pad = front_pad;
-    tc.n_stages = n_stages;
     tc.error_flag = d_error;
     for (int kc = 0; kc < M; ++kc) {
         const int a = (32 * kc) / M, r = (32 * kc) % M;
@@ -605,15 +614,16 @@ int DecBank::prepare_tc()
             if (kmax >= 0 && kmin <= ntaps - 1) ks.jmask |= 1u << j;
         }
     }
-    tc_smem = smem;
     cudaDeviceProp prop;
     SRCDSP_CUDA(cudaGetDeviceProperties(&prop, device));
     sm_count = prop.multiProcessorCount;
-    SRCDSP_CUDA(cudaFuncSetAttribute(dec_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
-    SRCDSP_CUDA(cudaFuncSetAttribute(dec_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
-    SRCDSP_CUDA(cudaFuncSetAttribute(dec_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
-    SRCDSP_CUDA(cudaFuncSetAttribute(dec_tc_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
-    SRCDSP_CUDA(cudaFuncSetAttribute(dec_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem));
+    const int max_smem = 226 * 1024;  // 227 KB minus the kernel's static shared memory
+    SRCDSP_CUDA(cudaFuncSetAttribute(dec_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    SRCDSP_CUDA(cudaFuncSetAttribute(dec_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    SRCDSP_CUDA(cudaFuncSetAttribute(dec_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    SRCDSP_CUDA(cudaFuncSetAttribute(dec_tc_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    SRCDSP_CUDA(cudaFuncSetAttribute(dec_tc_kernel<10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    SRCDSP_CUDA(cudaFuncSetAttribute(dec_tc_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     tc_ok = true;
     tc_why = "";
     return SRCDSP_OK;
@@ -685,6 +695,22 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
     const long long grid = (long long)P.tiles_per_ch * C;
     if (grid > 0x7fffffffll) return fail(SRCDSP_E_SIZE, "step too large: %lld tiles", grid);
     dim3 hgrid((unsigned)std::max(1, std::min((H + 255) / 256, 64)), (unsigned)C);
+    // kernel choice: the tcgen05 Toeplitz kernel when the taps fit it and there are enough
+    // 4096-output tiles to occupy the machine; the IMAD kernel otherwise
+    const long long tc_tiles = (long long)C * ((P.n_out + TC_NRB * TC_BOUT - 1) / (TC_NRB * TC_BOUT));
+    int tc_stages = 0;
+    size_t tc_smem = 0;
+    bool use_tc = tc_ok && tc_tiles < 0x7fffffffll && (kernel_kind == 2 || (kernel_kind == 0 && tc_tiles >= sm_count / 2));
+    const char *why = tc_why;
+    if (use_tc && mixer) {
+        const PhaseMod pm = mixer->pm();
+        if (!pm.mask) use_tc = false, why = "fused mixer needs a power-of-two sine table";
+    }
+    if (use_tc && tc_layout(mixer ? (int)mixer->n_table * 4 : 0, &tc_stages, &tc_smem) != SRCDSP_OK)
+        use_tc = false, why = "sine table + Toeplitz master + stages exceed 227 KB of shared memory";
+    if (kernel_kind == 2 && !use_tc)
+        return fail(SRCDSP_E_STATE, "tcgen05 kernel forced but not applicable: %s", tc_ok ? why : tc_why);
+
     if (mixer) {
         if (mixer->C != C || mixer->device != device)
             return fail(SRCDSP_E_INVALID, "mixer and decimator banks must have the same channels and device");
@@ -698,8 +724,67 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
         P.phi = mixer->d_phi[mixer->cur];
         P.freq = mixer->d_freq;
         P.pm = mixer->pm();
+    }
+    if (use_tc) {
+        TcParams T = tc;
+        T.in = in;
+        T.out = out;
+        T.in_stride = in_stride;
+        T.out_stride = out_stride;
+        T.n_in = P.n_in;
+        T.n_out = P.n_out;
+        T.tiles_per_ch = (int)(tc_tiles / C);
+        T.total_tiles = tc_tiles;
+        T.hist_in = d_hist[cur];
+        T.H = H;
+        T.shift = P.shift;
+        T.vec_in = P.vec_in;
+        T.n_stages = tc_stages;
+        T.rb_stride = T.G;
+        T.kc_stride = 32;
+        if (mixer) {
+            T.cs_table = mixer->d_cs;
+            T.phi = P.phi;
+            T.freq = P.freq;
+            T.mix_mask = P.pm.mask;
+            T.table_bytes = (int)mixer->n_table * 4;
+        }
+        const int tgrid = (int)std::min<long long>(tc_tiles, sm_count);
+        const char *dbg = getenv("SRCDSP_TC_DEBUG");  // timing experiments only (wrong results)
+        if (dbg && !mixer) {
+            T.debug = atoi(dbg);
+            if (T.debug & 16) {  // contiguous 128-byte lines per K-step instead of a 4*G-byte stride
+                T.rb_stride = 32;
+                T.kc_stride = 32 * TC_NRB;
+            }
+        }
+        if (mixer) {
+            dec_tc_kernel<0, true><<<tgrid, TC_THREADS, tc_smem, stream>>>(T);
+        } else if (T.debug & 32) {  // wait-cycle accounting variant; counters printed at the next launch
+            unsigned long long c[8];
+            cudaMemcpy(c, d_error + 2, sizeof c, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "tc counters (cycles summed over CTAs): prod total %llu wait_empty %llu fence %llu | mma total %llu wait_full %llu wait_tempty %llu | epi total %llu wait_tfull %llu\n", c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7]);
+            cudaMemset(d_error + 2, 0, sizeof c);
+            dec_tc_kernel<16, false><<<tgrid, TC_THREADS, tc_smem, stream>>>(T);
+        } else {
+            switch (T.debug & 10) {  // 2 / 8: timing-experiment instantiations (wrong results)
+            case 2: dec_tc_kernel<2, false><<<tgrid, TC_THREADS, tc_smem, stream>>>(T); break;
+            case 8: dec_tc_kernel<8, false><<<tgrid, TC_THREADS, tc_smem, stream>>>(T); break;
+            case 10: dec_tc_kernel<10, false><<<tgrid, TC_THREADS, tc_smem, stream>>>(T); break;
+            default: dec_tc_kernel<0, false><<<tgrid, TC_THREADS, tc_smem, stream>>>(T); break;
+            }
+        }
+        SRCDSP_LAUNCH_CHECK();
+        count_launch();
+        last_kernel = 2;
+    } else if (mixer) {
         SRCDSP_TRY(launch_dec_m<true>(P, (int)grid, nt_threads, smem_bytes, stream));
         last_kernel = 1;
+    } else {
+        SRCDSP_TRY(launch_dec_m<false>(P, (int)grid, nt_threads, smem_bytes, stream));
+        last_kernel = 1;
+    }
+    if (mixer) {
         dec_history_kernel<true><<<hgrid, 256, 0, stream>>>(in, in_stride, (long long)n_in, d_hist[cur], d_hist[cur ^ 1],
                                                             H, mixer->d_cs, mixer->d_phi[mixer->cur],
                                                             mixer->d_phi[mixer->cur ^ 1], mixer->d_freq, mixer->pm());
@@ -707,56 +792,6 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
         count_launch();
         mixer->advance(n_in);
     } else {
-        // kernel choice: the tcgen05 Toeplitz kernel when the taps fit it and there are enough
-        // 4096-output tiles to occupy the machine; the IMAD kernel otherwise
-        const long long tc_tiles = (long long)C * ((P.n_out + TC_NRB * TC_BOUT - 1) / (TC_NRB * TC_BOUT));
-        bool use_tc = tc_ok && tc_tiles < 0x7fffffffll && (kernel_kind == 2 || (kernel_kind == 0 && tc_tiles >= sm_count / 2));
-        if (kernel_kind == 2 && !tc_ok)
-            return fail(SRCDSP_E_STATE, "tcgen05 kernel forced but not applicable: %s", tc_why);
-        if (use_tc) {
-            TcParams T = tc;
-            T.in = in;
-            T.out = out;
-            T.in_stride = in_stride;
-            T.out_stride = out_stride;
-            T.n_in = P.n_in;
-            T.n_out = P.n_out;
-            T.tiles_per_ch = (int)(tc_tiles / C);
-            T.total_tiles = tc_tiles;
-            T.hist_in = d_hist[cur];
-            T.H = H;
-            T.shift = P.shift;
-            T.vec_in = P.vec_in;
-            T.rb_stride = T.G;
-            T.kc_stride = 32;
-            if (const char *dbg = getenv("SRCDSP_TC_DEBUG")) {  // timing experiments only (wrong results)
-                T.debug = atoi(dbg);
-                if (T.debug & 16) {  // contiguous 128-byte lines per K-step instead of a 4*G-byte stride
-                    T.rb_stride = 32;
-                    T.kc_stride = 32 * TC_NRB;
-                }
-            }
-            const int tgrid = (int)std::min<long long>(tc_tiles, sm_count);
-            if (T.debug & 32) {  // wait-cycle accounting variant; counters printed at the next launch
-                unsigned long long c[8];
-                cudaMemcpy(c, d_error + 2, sizeof c, cudaMemcpyDeviceToHost);
-                fprintf(stderr, "tc counters (cycles summed over CTAs): prod total %llu wait_empty %llu fence %llu | mma total %llu wait_full %llu wait_tempty %llu | epi total %llu wait_tfull %llu\n", c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7]);
-                cudaMemset(d_error + 2, 0, sizeof c);
-                dec_tc_kernel<16><<<tgrid, TC_THREADS, tc_smem, stream>>>(T);
-            } else
-            switch (T.debug & 10) {  // 2 / 8: timing-experiment instantiations (wrong results)
-            case 2: dec_tc_kernel<2><<<tgrid, TC_THREADS, tc_smem, stream>>>(T); break;
-            case 8: dec_tc_kernel<8><<<tgrid, TC_THREADS, tc_smem, stream>>>(T); break;
-            case 10: dec_tc_kernel<10><<<tgrid, TC_THREADS, tc_smem, stream>>>(T); break;
-            default: dec_tc_kernel<0><<<tgrid, TC_THREADS, tc_smem, stream>>>(T); break;
-            }
-            SRCDSP_LAUNCH_CHECK();
-            count_launch();
-            last_kernel = 2;
-        } else {
-            SRCDSP_TRY(launch_dec_m<false>(P, (int)grid, nt_threads, smem_bytes, stream));
-            last_kernel = 1;
-        }
         dec_history_kernel<false><<<hgrid, 256, 0, stream>>>(in, in_stride, (long long)n_in, d_hist[cur],
                                                              d_hist[cur ^ 1], H, nullptr, nullptr, nullptr, nullptr,
                                                              PhaseMod{1, 0});

@@ -85,6 +85,19 @@ __device__ __forceinline__ uint32_t mix_sample(uint32_t x, uint32_t cs)
     return scale_pack<true>(r, i, 14);
 }
 
+// Same arithmetic with the packed saturate: cvt.pack.sat gives [-32768, 32767] per half, the
+// per-half signed max with -32767 restores limitScale16's symmetric clamp (dsp_complex.cpp:63-73).
+__device__ __forceinline__ uint32_t mix_sample_packed(uint32_t x, uint32_t cs)
+{
+    const int xr = sx_lo(x), xi = sx_hi(x);
+    const int c = sx_lo(cs), s = sx_hi(cs);
+    const int r = (xr * c - xi * s) >> 14;
+    const int i = (xi * c + s * xr) >> 14;
+    uint32_t p;
+    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(p) : "r"(i), "r"(r));  // {hi = sat(i), lo = sat(r)}
+    return __vmaxs2(p, 0x80018001u);
+}
+
 // phase of sample n of a block that started at phase phi0: (phi0 + n * freq) mod N
 struct PhaseMod {
     unsigned n_table;

@@ -76,6 +76,11 @@ struct TcParams {
     unsigned shift;
     int vec_in;
     int *error_flag;
+    // fused NCO mix (MIX instantiation): packed (cos, sin) table of n_table = mix_mask + 1 entries (power of two)
+    const uint32_t *cs_table;
+    const int *phi, *freq;   // [C] phase at sample 0 of this step, frequency
+    unsigned mix_mask;
+    int table_bytes;         // bytes of the shared-memory copy of the table (0 without MIX)
     int rb_stride, kc_stride;  // samples between row-blocks / K-steps (G and 32; timing experiments permute them)
     int debug;  // timing experiments only (results become wrong): 1 = skip the MMAs, 4 = skip the epilogue math
     TcKstep ks[TC_MAX_KSTEPS];
@@ -173,6 +178,16 @@ __device__ __forceinline__ uint32_t tc_sample(const uint32_t *x, const uint32_t 
     if (n >= 0) return n < n_in ? __ldg(x + n) : 0u;
     return n >= -(long long)H ? __ldg(hist + (H + n)) : 0u;
 }
+// same with the NCO mix applied to block samples (history is already mixed); ph0/fr: channel phase at
+// sample 0 and frequency, table in global memory (edge path only)
+__device__ __forceinline__ uint32_t tc_sample_mix(const TcParams &P, const uint32_t *x, const uint32_t *hist, long long n,
+                                                  unsigned ph0, unsigned fr)
+{
+    const uint32_t w = tc_sample(x, hist, P.H, P.n_in, n);
+    if (n < 0 || n >= P.n_in) return w;
+    const unsigned ph = (ph0 + ((unsigned)n & P.mix_mask) * fr) & P.mix_mask;
+    return mix_sample_packed(w, __ldg(P.cs_table + ph));
+}
 
 __device__ __forceinline__ uint4 ldg_stream(const uint4 *p)
 {
@@ -220,15 +235,26 @@ __device__ __forceinline__ void tc_batch_load_fast(TcBatch &t, const uint32_t *p
     }
 }
 
-template <int DBG>
-__device__ __forceinline__ void tc_batch_store_fast(const TcBatch &t, uint8_t *lo, uint8_t *hi, int nit)
+// MIX: tab = shared-memory copy of the packed (cos, sin) table, ph = phase of this lane's first
+// sample of iteration 0, fr = channel frequency, dph = phase step between iterations (4 row-blocks)
+template <int DBG, bool MIX>
+__device__ __forceinline__ void tc_batch_store_fast(const TcBatch &t, uint8_t *lo, uint8_t *hi, int nit, const uint32_t *tab,
+                                                    unsigned ph, unsigned fr, unsigned dph, unsigned mask)
 {
     uint32_t sink = 0;
 #pragma unroll
     for (int it = 0; it < TC_BATCH; ++it) {
         if (it < nit) {
             uint32_t re_lo, re_hi, im_lo, im_hi;
-            split4(t.q[it], re_lo, re_hi, im_lo, im_hi);
+            uint4 q = t.q[it];
+            if (MIX) {  // mixers.h:172-177 on the 4 samples of this piece, then the same byte-plane split
+                const unsigned p0 = (ph + it * dph) & mask;
+                q.x = mix_sample_packed(q.x, tab[p0]);
+                q.y = mix_sample_packed(q.y, tab[(p0 + fr) & mask]);
+                q.z = mix_sample_packed(q.z, tab[(p0 + 2 * fr) & mask]);
+                q.w = mix_sample_packed(q.w, tab[(p0 + 3 * fr) & mask]);
+            }
+            split4(q, re_lo, re_hi, im_lo, im_hi);
             if (DBG & 8) {  // timing experiment: no shared-memory stores
                 sink ^= re_lo ^ re_hi ^ im_lo ^ im_hi;
                 continue;
@@ -246,7 +272,8 @@ __device__ __forceinline__ void tc_batch_store_fast(const TcBatch &t, uint8_t *l
 // not prefetched.  Out of line to keep the hot loop small.
 // n0: sample index of (row-block rb, this lane's piece, this K-step); dst: its (plane lo, re) word.
 __device__ __noinline__ void tc_batch_generic(const TcParams &P, const uint32_t *x, const uint32_t *hist, long long n0,
-                                              int rb, int rb_lo, int rb_hi, int nit, uint8_t *dst)
+                                              int rb, int rb_lo, int rb_hi, int nit, uint8_t *dst, bool mix, unsigned ph0,
+                                              unsigned fr)
 {
     const int chunk = P.rbp * 16;  // bytes per (plane, kc) chunk
     for (int it = 0; it < nit; ++it) {
@@ -254,10 +281,17 @@ __device__ __noinline__ void tc_batch_generic(const TcParams &P, const uint32_t 
         if (r < rb_lo || r >= rb_hi) continue;
         const long long n = n0 + (long long)it * 4 * P.rb_stride;
         uint4 q;
-        q.x = tc_sample(x, hist, P.H, P.n_in, n);
-        q.y = tc_sample(x, hist, P.H, P.n_in, n + 1);
-        q.z = tc_sample(x, hist, P.H, P.n_in, n + 2);
-        q.w = tc_sample(x, hist, P.H, P.n_in, n + 3);
+        if (mix) {
+            q.x = tc_sample_mix(P, x, hist, n, ph0, fr);
+            q.y = tc_sample_mix(P, x, hist, n + 1, ph0, fr);
+            q.z = tc_sample_mix(P, x, hist, n + 2, ph0, fr);
+            q.w = tc_sample_mix(P, x, hist, n + 3, ph0, fr);
+        } else {
+            q.x = tc_sample(x, hist, P.H, P.n_in, n);
+            q.y = tc_sample(x, hist, P.H, P.n_in, n + 1);
+            q.z = tc_sample(x, hist, P.H, P.n_in, n + 2);
+            q.w = tc_sample(x, hist, P.H, P.n_in, n + 3);
+        }
         uint32_t re_lo, re_hi, im_lo, im_hi;
         split4(q, re_lo, re_hi, im_lo, im_hi);
         uint8_t *lo = dst + it * 128;
@@ -269,7 +303,7 @@ __device__ __noinline__ void tc_batch_generic(const TcParams &P, const uint32_t 
     }
 }
 
-template <int DBG>
+template <int DBG, bool MIX>
 __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_constant__ TcParams P)
 {
     extern __shared__ __align__(128) uint8_t tc_smem_raw[];
@@ -278,7 +312,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
     const int J = P.J;
     const int stage_bytes = 4 * P.rbp * 16;  // 2 planes x 2 kc chunks
     uint8_t *a_smem = smem;
-    uint8_t *stages = smem + ((P.master_bytes + 127) & ~127);
+    uint32_t *tab_smem = reinterpret_cast<uint32_t *>(smem + ((P.master_bytes + 127) & ~127));
+    uint8_t *stages = reinterpret_cast<uint8_t *>(tab_smem) + P.table_bytes;
     const int NS = P.n_stages;
     uint64_t *bars = reinterpret_cast<uint64_t *>(stages + NS * stage_bytes);
     // bars: full[NS], empty[NS], tmem_full[2], tmem_empty[2]
@@ -289,6 +324,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
     // ---- setup ------------------------------------------------------------------------------
     for (int i = tid; i < P.master_bytes / 16; i += TC_THREADS)
         reinterpret_cast<uint4 *>(a_smem)[i] = __ldg(reinterpret_cast<const uint4 *>(P.master) + i);
+    if (MIX)
+        for (int i = tid; i < P.table_bytes / 4; i += TC_THREADS) tab_smem[i] = __ldg(P.cs_table + i);
     // rows of the stages that no producer ever writes (the padding row) must be defined: zero all
     for (int i = tid; i < NS * stage_bytes / 16; i += TC_THREADS)
         reinterpret_cast<uint4 *>(stages)[i] = make_uint4(0, 0, 0, 0);
@@ -346,6 +383,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
         long long cur_tile = -1;
         const uint32_t *x = nullptr, *hist = nullptr;
         long long tile0 = 0;
+        unsigned ph0 = 0, fr = 0, dph = 0;  // MIX: channel phase at sample 0, frequency, phase step per iteration
         int stage = owner % NS;  // step gs uses stage gs % NS
         uint32_t parity = 1;     // first wait on a fresh "empty" barrier passes
         TcBatch t;
@@ -358,6 +396,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
                 hist = P.hist_in + (size_t)ch * P.H;
                 tile0 = (long long)tt * TC_NRB * (long long)P.G;
                 cur_tile = tile;
+                if (MIX) {
+                    ph0 = (unsigned)P.phi[ch];
+                    fr = (unsigned)P.freq[ch];
+                    dph = (((unsigned)(4 * P.rb_stride) & P.mix_mask) * fr) & P.mix_mask;
+                }
             }
             const long long col = tile0 + (long long)P.kc_stride * kc + 4 * piece;  // sample of (row 0, piece)
             const bool fast_main = P.vec_in && col - 4 * piece + (long long)(TC_NRB - 1) * P.rb_stride + 32 <= P.n_in;
@@ -374,9 +417,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
                 uint8_t *dst = dst0 - 4 * halo_it * 32;
                 if (fast_halo) {
                     tc_batch_load_fast<DBG>(t, x + (col + (long long)rb * P.rb_stride), it_stride, halo_it);
-                    tc_batch_store_fast<DBG>(t, dst, dst + 2 * chunk, halo_it);
+                    tc_batch_store_fast<DBG, MIX>(t, dst, dst + 2 * chunk, halo_it, tab_smem,
+                                                  (ph0 + ((unsigned)(col + (long long)rb * P.rb_stride) & P.mix_mask) * fr) & P.mix_mask,
+                                                  fr, dph, P.mix_mask);
                 } else {
-                    tc_batch_generic(P, x, hist, col + (long long)rb * P.rb_stride, rb, -(J - 1), 0, halo_it, dst);
+                    tc_batch_generic(P, x, hist, col + (long long)rb * P.rb_stride, rb, -(J - 1), 0, halo_it, dst, MIX, ph0, fr);
                 }
             }
 #pragma unroll 1
@@ -385,9 +430,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
                 uint8_t *dst = dst0 + (rb - grp) * 32;
                 if (fast_main) {
                     tc_batch_load_fast<DBG>(t, x + (col + (long long)rb * P.rb_stride), it_stride, TC_BATCH);
-                    tc_batch_store_fast<DBG>(t, dst, dst + 2 * chunk, TC_BATCH);
+                    tc_batch_store_fast<DBG, MIX>(t, dst, dst + 2 * chunk, TC_BATCH, tab_smem,
+                                                  (ph0 + ((unsigned)(col + (long long)rb * P.rb_stride) & P.mix_mask) * fr) & P.mix_mask,
+                                                  fr, dph, P.mix_mask);
                 } else {
-                    tc_batch_generic(P, x, hist, col + (long long)rb * P.rb_stride, rb, 0, TC_NRB, TC_BATCH, dst);
+                    tc_batch_generic(P, x, hist, col + (long long)rb * P.rb_stride, rb, 0, TC_NRB, TC_BATCH, dst, MIX, ph0, fr);
                 }
             }
             // every writer fences its generic-proxy stores towards the async proxy (the MMA reads

@@ -347,3 +347,58 @@ def test_tc_rejects_what_it_cannot_do(S):
     assert ei.value.code == -5
     d.set_kernel(0)  # automatic selection falls back to the IMAD kernel
     d.step(np.zeros((64, 2), np.int16))
+
+
+@pytest.mark.parametrize("M,nt,n_table", [(16, 255, 4096), (8, 63, 4096), (4, 200, 1024), (2, 50, 4096), (3, 31, 256)])
+def test_tc_fused_mixer(S, corc, M, nt, n_table):
+    """NCO mix fused into the tensor-core kernel's load stage == Mixer::step then decimator::step."""
+    rng = np.random.default_rng(M * 31 + nt)
+    taps = O.design_lowpass_taps(nt, M)
+    C = 3
+    fs = np.array([-0.3217, 0.5, 0.0371], np.float32)
+    m = S.Mixer(n_table=n_table, channels=C)
+    m.setFrequency(fs)
+    d = S.FilterDnsamplingFir(M, taps, channels=C, obsolete=True)
+    d.set_kernel(2)
+    chain = S.Ddc(m, d)
+    st = [(0, None)] * C
+    for blk, n_out in enumerate([4096 * 2 + 33, 7, 4096 + 1500]):
+        x = rng.integers(-32768, 32768, (C, n_out * M, 2)).astype(np.int16)
+        if blk == 2:
+            m.adjustFrequency(0.0101, ch=1)
+            fs[1] = corc.mixer_adjust_nominal(float(fs[1]), 0.0101)
+        got = host(chain.step(dev(x))) if blk % 2 == 0 else chain.step(x)
+        assert d.last_kernel.startswith("dec_tc")
+        for c in range(C):
+            phi, h = st[c]
+            y, phi = corc.mixer_step(x[c], phi, corc.mixer_set_frequency(float(fs[c]), n_table), n_table)
+            y, h = corc.dec_step(taps, M, y, h)
+            st[c] = (phi, h)
+            assert np.array_equal(got[c], y), (M, nt, blk, c)
+            assert m.state(c)[0] == phi
+
+
+def test_tc_two_stage_chain(S, corc):
+    """cfg-3 shape with the tensor-core kernel in both stages (mix fused into stage 1)."""
+    rng = np.random.default_rng(77)
+    C, n = 4, 32 * 4096 * 2
+    t1, t2 = O.design_lowpass_taps(63, 8), O.design_lowpass_taps(63, 4)
+    fs = (-1 + 2 * (np.arange(C) + 0.5) / C).astype(np.float32)
+    m = S.Mixer(channels=C)
+    m.setFrequency(fs)
+    d1 = S.FilterDnsamplingFir(8, t1, channels=C, obsolete=True)
+    d2 = S.FilterDnsamplingFir(4, t2, channels=C, obsolete=True)
+    d1.set_kernel(2)
+    d2.set_kernel(2)
+    chain = S.Ddc(m, d1, d2)
+    st = [(0, None, None)] * C
+    for blk in range(2):
+        x = rng.integers(-32768, 32768, (C, n, 2)).astype(np.int16)
+        got = host(chain.step(dev(x)))
+        for c in range(C):
+            phi, h1, h2 = st[c]
+            y, phi = corc.mixer_step(x[c], phi, corc.mixer_set_frequency(float(fs[c])))
+            y, h1 = corc.dec_step(t1, 8, y, h1)
+            y, h2 = corc.dec_step(t2, 4, y, h2)
+            st[c] = (phi, h1, h2)
+            assert np.array_equal(got[c], y), (blk, c)
