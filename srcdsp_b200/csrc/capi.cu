@@ -551,34 +551,58 @@ int DecBank::prepare_tc()
     const int G = 32 * M;
     const int J = 1 + (ntaps - 1 + G - 1) / G;
     if (J > TC_MAX_J) { tc_why = "filter spans more than 16 row-blocks"; return SRCDSP_OK; }
-    // residues r = (32 * kc) mod M, one master per distinct residue
-    std::vector<int> res_of_kc(M), res_list;
-    for (int kc = 0; kc < M; ++kc) {
-        const int r = (32 * kc) % M;
-        int idx = -1;
-        for (size_t i = 0; i < res_list.size(); ++i)
-            if (res_list[i] == r) idx = (int)i;
-        if (idx < 0) {
-            idx = (int)res_list.size();
-            res_list.push_back(r);
-        }
-        res_of_kc[kc] = idx;
-    }
-    const int a_rows = 128 * J + 136;
-    const size_t master_bytes = res_list.size() * (size_t)a_rows * 32;
+    // One resident "master" Toeplitz image per distinct tap alignment.  Preferred layout ("grouped"):
+    // row = 32*(v>>3) + 8*w + (v&7) (+32 guard rows), the 4 weight slots of an output 8 rows apart, so
+    // that the epilogue needs no shuffles; a K-step whose output shift is a needs the copy with
+    // s = a mod 8.  Fallback ("interleaved"): row = 4*v + w (+4 guard rows), one copy per residue r.
     const int front_pad = 2 * (4 * ((J - 1 + 3) / 4) - (J - 1));
     const int rbp = (front_pad + 2 * (TC_NRB + J - 1)) | 1;  // odd: conflict-free byte-plane stores
-    tc_fixed = ((master_bytes + 127) & ~(size_t)127) + 512;
     tc.rbp = rbp;  // tc_layout needs it
-    if (tc_layout(0, nullptr, nullptr) != SRCDSP_OK) { tc_why = "Toeplitz master + stages exceed 227 KB of shared memory"; return SRCDSP_OK; }
+    std::vector<int> copy_of_kc(M);
+    std::vector<std::pair<int, int>> copies;  // (s, r)
+    int grouped = 1, a_rows = 0;
+    size_t master_bytes = 0;
+    for (; grouped >= 0; --grouped) {
+        copies.clear();
+        for (int kc = 0; kc < M; ++kc) {
+            const int a = (32 * kc) / M, r = (32 * kc) % M;
+            const std::pair<int, int> key(grouped ? a % 8 : 0, r);
+            int idx = -1;
+            for (size_t i = 0; i < copies.size(); ++i)
+                if (copies[i] == key) idx = (int)i;
+            if (idx < 0) {
+                idx = (int)copies.size();
+                copies.push_back(key);
+            }
+            copy_of_kc[kc] = idx;
+        }
+        a_rows = grouped ? 128 * J + 32 + 128 + 64 : 128 * J + 136;
+        master_bytes = copies.size() * (size_t)a_rows * 32;
+        tc_fixed = ((master_bytes + 127) & ~(size_t)127) + 512;
+        if (tc_layout(16384, nullptr, nullptr) == SRCDSP_OK) break;  // leave room for a 4096-entry sine table
+        if (!grouped && tc_layout(0, nullptr, nullptr) == SRCDSP_OK) break;
+    }
+    if (grouped < 0) { tc_why = "Toeplitz master + stages exceed the shared memory of one SM"; return SRCDSP_OK; }
     std::vector<uint8_t> img(master_bytes, 0);
-    for (size_t ri = 0; ri < res_list.size(); ++ri) {
-        uint8_t *base = img.data() + ri * (size_t)a_rows * 32;
-        for (int row = 4; row < a_rows; ++row) {
-            const int u = (row - 4) / 4 - 32, w = (row - 4) % 4;
+    const int OFF = 32;
+    for (size_t ci = 0; ci < copies.size(); ++ci) {
+        uint8_t *base = img.data() + ci * (size_t)a_rows * 32;
+        const int s8 = copies[ci].first, r = copies[ci].second;
+        const int guard = grouped ? 32 : 4;
+        for (int row = guard; row < a_rows; ++row) {
+            int v, w;
+            if (grouped) {
+                const int q = row - guard;
+                v = 8 * (q / 32) + (q % 8);
+                w = (q % 32) / 8;
+            } else {
+                v = (row - guard) / 4;
+                w = (row - guard) % 4;
+            }
             if (w >= P) continue;
+            const int u = v - s8 - OFF;
             for (int t = 0; t < 32; ++t) {
-                const long long k = (long long)M * u - t - res_list[ri];
+                const long long k = (long long)M * u - t - r;
                 if (k < 0 || k >= ntaps) continue;
                 // SWIZZLE_NONE K-major image: [kc = t / 16][row][t % 16]
                 base[(size_t)(t / 16) * a_rows * 16 + (size_t)row * 16 + (t % 16)] = (uint8_t)dig[w][k];
@@ -601,12 +625,14 @@ int DecBank::prepare_tc()
     tc.a_rows = a_rows;
     tc.rbp = rbp;
     tc.front_pad = front_pad;
+    tc.grouped = grouped;
     tc.error_flag = d_error;
     for (int kc = 0; kc < M; ++kc) {
         const int a = (32 * kc) / M, r = (32 * kc) % M;
         TcKstep &ks = tc.ks[kc];
-        ks.a_row = 4 * (32 - a) + 4;
-        ks.res_off = res_of_kc[kc] * a_rows * 32;
+        // master row of (b = 0, slot 0, lag 0): v0 = OFF - a + s  (a multiple of 8 when grouped)
+        ks.a_row = grouped ? 4 * (OFF - 8 * (a / 8)) + 32 : 4 * (OFF - a) + 4;
+        ks.res_off = copy_of_kc[kc] * a_rows * 32;
         ks.jmask = 0;
         for (int j = 0; j < J; ++j) {
             const long long kmax = (long long)M * (31 + 32 * j - a) - r;

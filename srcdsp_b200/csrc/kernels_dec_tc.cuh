@@ -70,6 +70,8 @@ struct TcParams {
     int a_rows;              // rows per (residue, kc) chunk  -> LBO_A = a_rows * 16
     int rbp;                 // padded rows per (plane, kc) chunk of a stage (odd) -> LBO_B = rbp * 16
     int front_pad;           // unused rows in front of every chunk: 2 * (4*ceil((J-1)/4) - (J-1))
+    int grouped;             // A-row layout: 0: rho = 4*b + w (shuffle epilogue); 1: rho = 32*(b>>3) + 8*w + (b&7)
+                             // (weight slots 8 rows apart -> one thread holds all slots of an output, 16x256b loads)
     int n_stages;            // shared-memory stages (TC_NPW < n_stages <= TC_MAX_STAGES)
     const uint32_t *hist_in;
     int H;
@@ -478,6 +480,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
             const uint32_t lbo_a = P.a_rows * 16, lbo_b = P.rbp * 16;
             // descriptor = constant high part | (address >> 4)
             const uint64_t desc_a0 = umma_desc(0, lbo_a), desc_b0 = umma_desc(0, lbo_b);
+            const uint32_t hi_shift = P.grouped ? 128 : 16;  // one weight slot: 8 rows / 1 row
             int stage = 0;
             uint32_t phase = 0;
             uint32_t acc_phases = 0;  // bit a: parity of accumulator buffer a
@@ -501,8 +504,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
                             const uint32_t a_addr = a_base + res_off + (a_row + 128 * j) * 16;
                             const uint32_t b_addr = sb + (P.front_pad + 2 * (J - 1 - j)) * 16;
                             umma_i8(d_tmem, desc_a0 | (a_addr >> 4), desc_b0 | (b_addr >> 4), idesc_lo, accumulate);
-                            // hi byte plane: weight slot + 1  ==  master moved back by one row
-                            umma_i8(d_tmem, desc_a0 | ((a_addr - 16) >> 4), desc_b0 | ((b_addr + 2 * lbo_b) >> 4),
+                            // hi byte plane: weight slot + 1  ==  master moved back by one slot
+                            umma_i8(d_tmem, desc_a0 | ((a_addr - hi_shift) >> 4), desc_b0 | ((b_addr + 2 * lbo_b) >> 4),
                                     idesc_hi, 1);
                             accumulate = 1;
                         }
@@ -543,6 +546,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
             mbar_wait_acc<DBG>(bar_tfull + 8 * acc, (acc_phases >> acc) & 1, P.error_flag, e_wait);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(32 * warp) << 16) + acc * (2 * TC_NRB);
+            if (P.grouped) {
+                // weight slots of output b sit 8 TMEM lanes apart: a 16x256b load hands one thread the
+                // slots {0,1} (lanes 0-15 of the warp's quadrant) or {2,3} (lanes 16-31) of output
+                // b = 8*warp + lane/4 for the column pairs (re, im) of 4 row-blocks -> no shuffles
+#pragma unroll 1
+                for (int c0 = 0; c0 < ((P.debug & 4) ? 0 : 2 * TC_NRB); c0 += 32) {
+                    uint32_t a[16], h[16];
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+                        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                        : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]),
+                          "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]),
+                          "=r"(a[15])
+                        : "r"(t_addr + c0));
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+                        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                        : "=r"(h[0]), "=r"(h[1]), "=r"(h[2]), "=r"(h[3]), "=r"(h[4]), "=r"(h[5]), "=r"(h[6]), "=r"(h[7]),
+                          "=r"(h[8]), "=r"(h[9]), "=r"(h[10]), "=r"(h[11]), "=r"(h[12]), "=r"(h[13]), "=r"(h[14]),
+                          "=r"(h[15])
+                        : "r"(t_addr + (16u << 16) + c0));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        // sum_w 256^w * D_w (mod 2^32, exactly the reference's int32 wrap)
+                        const uint32_t re = a[4 * k] + (a[4 * k + 2] << 8) + (h[4 * k] << 16) + (h[4 * k + 2] << 24);
+                        const uint32_t im = a[4 * k + 1] + (a[4 * k + 3] << 8) + (h[4 * k + 1] << 16) + (h[4 * k + 3] << 24);
+                        const int m = (c0 >> 1) + 4 * k + (lane & 3);
+                        const long long idx = (tt * TC_NRB + m) * TC_BOUT + b;
+                        if (idx < P.n_out) o[idx] = scale_pack<true>((int)re, (int)im, P.shift);
+                    }
+                }
+            } else {
 #pragma unroll 1
             for (int c0 = 0; c0 < ((P.debug & 4) ? 0 : 2 * TC_NRB); c0 += 32) {
                 uint32_t v[32];
@@ -577,6 +613,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
                     const long long idx = (tt * TC_NRB + m) * TC_BOUT + b;
                     if (idx < P.n_out) o[idx] = scale_pack<true>((int)re, (int)im, P.shift);
                 }
+            }
             }
             tc_fence_before();
             __syncwarp();
