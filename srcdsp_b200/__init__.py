@@ -25,7 +25,7 @@ import numpy as np
 from . import _capi
 from ._capi import SrcDspError, check, lib
 
-__all__ = ["Mixer", "FilterDnsamplingFir", "FilterUpsamplingFir", "Ddc", "SrcDspError",
+__all__ = ["Mixer", "FilterDnsamplingFir", "FilterFir", "FilterUpsamplingFir", "Ddc", "SrcDspError",
            "synth_fill", "launch_count", "device_count", "PinnedBuffer"]
 
 
@@ -235,6 +235,20 @@ class FilterDnsamplingFir(_Handle):
 
     def sync(self):
         check(lib().srcdsp_dec_sync(self._h))
+
+
+class FilterFir(FilterDnsamplingFir):
+    """Non-decimating FIR bank (reference filters.h:42-169): in age order
+    it is the M = 1 decimator with `limitScale16(y, coeffScaling)`; setCoeffs clears the history."""
+
+    def __init__(self, firCoeff: Optional[Sequence[int]] = None, channels: int = 1, device: int = 0):
+        super().__init__(1, None, channels, device, obsolete=True)
+        if firCoeff is not None:
+            self.setCoeffs(firCoeff)
+
+    def setCoeffs(self, firCoeff):
+        super().setCoeffs(firCoeff)
+        self.reset()  # filters.h:96
 
 
 # ----------------------------------------------------------------------------------------------

@@ -43,6 +43,12 @@ def run_oracle(case):
             y, h = c.dec_step(MG.taps_for(case), case["M"], x[pos:pos + b], h, case["left_shift"])
             outs.append(y)
             pos += b
+    elif k == "fir":
+        h = None
+        for b in case["blocks"]:
+            y, h = c.fir_step(MG.taps_for(case), x[pos:pos + b], h)
+            outs.append(y)
+            pos += b
     elif k == "ddc":
         phi, fr, h1, h2 = 0, c.mixer_set_frequency(case["f"]), None, None
         for b in case["blocks"]:
@@ -82,6 +88,11 @@ def run_product(case, to_buf=lambda a: a, from_buf=lambda a: a, fused=True):
         d.setLeftShiftBy2(case["left_shift"])
         for b in case["blocks"]:
             outs.append(from_buf(d.step(to_buf(x[pos:pos + b]))))
+            pos += b
+    elif k == "fir":
+        f = S.FilterFir(MG.taps_for(case))
+        for b in case["blocks"]:
+            outs.append(from_buf(f.step(to_buf(x[pos:pos + b]))))
             pos += b
     elif k == "ddc":
         m = S.Mixer()

@@ -13,6 +13,7 @@
 #include "mixers.h"
 #include "dnsampling_filters.h"   // obsolete twin: accepts 63 taps (SURVEY.md section 0 trap (i))
 #include "upsampling_filters.h"
+#include "filters.h"
 
 typedef std::complex<int16_t> cs16;
 typedef std::complex<int32_t> cs32;
@@ -83,6 +84,20 @@ int main()
     up.step(small, dst.begin() + 8);
     std::printf("iterator overload %016llx guard %d %d\n", (unsigned long long)checksum(dst), (int)dst[0].real(),
                 (int)dst[dst.size() - 1].imag());
+    // non-decimating FIR (filters.h), two blocks with carried history, then new taps (history cleared)
+    FilterFir<cs16, cs16, cs32, int32_t> fir(lowpass(33, 4, 9000.0));
+    std::vector<cs16> f1(1000), f2(1000);
+    for (size_t n = 0; n < 2000; ++n) {
+        const uint32_t h = hash32(0x5EED0007u, 0, n);
+        (n < 1000 ? f1[n] : f2[n - 1000]) = cs16((int16_t)(h & 0xFFFF), (int16_t)(h >> 16));
+    }
+    std::vector<cs16> g1(1000), g2(1000);
+    fir.step(f1, g1);
+    fir.step(f2, g2);
+    fir.setCoeffs(lowpass(33, 2, 20000.0));  // same length: the reference keeps `top`, a shorter filter would index out of bounds
+    fir.step(f1, f1);  // in place
+    std::printf("fir %016llx %016llx %016llx\n", (unsigned long long)checksum(g1), (unsigned long long)checksum(g2),
+                (unsigned long long)checksum(f1));
     dec1.reset();
     mixer.reset(0.25f);
     std::vector<cs16> in2(64, cs16(1000, -500)), m2(64), o2(8);

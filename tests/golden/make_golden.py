@@ -24,6 +24,7 @@ CASES = [
     dict(name="dec16_255_cfg2", kind="dec", seed=0x5EED0002, n=32768, blocks=[16384, 16384], M=16, ntaps=255, left_shift=0),
     dict(name="dec4_1023_cfg5", kind="dec", seed=0x5EED0005, n=16384, blocks=[8192, 8192], M=4, ntaps=1023, left_shift=0),
     dict(name="dec3_31_ls1", kind="dec", seed=0x5EED0006, n=6144, blocks=[3072, 1536, 1536], M=3, ntaps=31, left_shift=1),
+    dict(name="fir_33", kind="fir", seed=0x5EED0007, n=4096, blocks=[1000, 3096], ntaps=33),
     dict(name="ddc_mix_dec8_63", kind="ddc", seed=0x5EED0011, n=16384, blocks=[8192, 8192], f=-0.3217,
          M1=8, ntaps1=63, M2=0, ntaps2=0),
     dict(name="ddc_mix_8x4_cfg3", kind="ddc", seed=0x5EED0003, n=32768, blocks=[16384, 16384], f=0.1234,
@@ -42,6 +43,8 @@ def taps_for(case, which=""):
         if case["shift_mode"] == 1:
             t = (t // 8).astype(np.int32)  # iterator overload has shift 0: keep it out of saturation
         return t
+    if case["kind"] == "fir":
+        return O.design_lowpass_taps(case["ntaps"], 4)
     nt, M = case["ntaps" + which], case["M" + which]
     return O.design_lowpass_taps(nt, M)
 
@@ -65,6 +68,11 @@ def run_reference(case):
         d.setLeftShiftBy2(case["left_shift"])
         for b in case["blocks"]:
             outs.append(d.step(x[pos:pos + b]))
+            pos += b
+    elif k == "fir":
+        f = O.RefFir(r, taps_for(case))
+        for b in case["blocks"]:
+            outs.append(f.step(x[pos:pos + b]))
             pos += b
     elif k == "ddc":
         m = O.RefMixer(r)

@@ -402,3 +402,50 @@ def test_tc_two_stage_chain(S, corc):
             y, h2 = corc.dec_step(t2, 4, y, h2)
             st[c] = (phi, h1, h2)
             assert np.array_equal(got[c], y), (blk, c)
+
+
+def test_filter_fir(S, corc):
+    """FilterFir (filters.h, SURVEY 8(f) #1) == the M = 1 decimator; setCoeffs clears the history."""
+    rng = np.random.default_rng(8)
+    taps = O.design_lowpass_taps(33, 4)
+    f = S.FilterFir(taps, channels=2)
+    h = [None, None]
+    for blk, n in enumerate([1000, 37, 5000]):
+        x = rng.integers(-32768, 32768, (2, n, 2)).astype(np.int16)
+        got = host(f.step(dev(x))) if blk % 2 else f.step(x)
+        for c in range(2):
+            e, h[c] = corc.fir_step(taps, x[c], h[c])
+            assert np.array_equal(got[c], e)
+    f.setCoeffs(taps)  # filters.h:96 reset()
+    x = rng.integers(-32768, 32768, (2, 500, 2)).astype(np.int16)
+    e, _ = corc.fir_step(taps, x[1])
+    assert np.array_equal(f.step(x)[1], e)
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_time_sliced_stream_equals_sequential(S, corc, kernel):
+    """cfg-5 shape in miniature: one long stream cut into slices that are processed independently
+    (as different GPUs would), each after a warm-up halo with the NCO phase set in closed form,
+    gives exactly the sequential result (SURVEY.md 8(e))."""
+    from srcdsp_b200.sharding import time_slices
+    M, nt = 4, 1023
+    taps = O.design_lowpass_taps(nt, M)
+    n = M * 4096 * 6
+    x = corc.synth(0x5EED0005, 0, 0, n, 0)
+    f = -0.3217
+    fr = corc.mixer_set_frequency(f)
+    y, _ = corc.mixer_step(x, 0, fr)
+    whole, _ = corc.dec_step(taps, M, y)
+    outs = []
+    for s in time_slices(n, 3, [nt], [M]):
+        m = S.Mixer()
+        m.setFrequency(f)
+        m.set_state(0, s.nco_phase(0, fr, 4096), fr, f)
+        d = S.FilterDnsamplingFir(M, taps, obsolete=True)
+        d.set_kernel(kernel)
+        chain = S.Ddc(m, d)
+        if s.warmup:
+            chain.step(dev(x[s.start - s.warmup: s.start]))  # outputs discarded
+        outs.append(host(chain.step(dev(x[s.start: s.start + s.length]))))
+        assert outs[-1].shape[0] == s.out_length
+    assert np.array_equal(np.concatenate(outs), whole)
