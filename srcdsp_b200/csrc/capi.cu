@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "kernels_dec.cuh"
 #include "kernels_dec_tc.cuh"
+#include "kernels_dec_tma.cuh"
 #include "kernels_up.cuh"
 
 namespace srcdsp {
@@ -268,6 +269,26 @@ static inline bool aligned16(const void *p, size_t stride_words)
     return ((uintptr_t)p % 16 == 0) && (stride_words % 4 == 0);
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (the library links the
+// static CUDA runtime only, not libcuda)
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeFn tensor_map_encoder()
+{
+    static TensorMapEncodeFn fn = []() -> TensorMapEncodeFn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return (TensorMapEncodeFn)p;
+    }();
+    return fn;
+}
+
 // ---------------------------------------------------------------------------------------------
 // mixer bank
 // ---------------------------------------------------------------------------------------------
@@ -417,6 +438,25 @@ struct DecBank : Bank {
         if (ns > TC_MAX_STAGES) ns = TC_MAX_STAGES;
         if (n_stages) *n_stages = ns;
         if (smem) *smem = tc_fixed + (size_t)table_bytes + (size_t)ns * 64 * tc.rbp;
+        return SRCDSP_OK;
+    }
+
+    // shared-memory plan of the TMA-fed variant: byte-plane stages only decouple the converters from
+    // the MMAs (3 are enough), everything else goes to the raw ring = the bytes in flight from HBM
+    int tma_layout(int table_bytes, int *n_raw, int *n_stages, size_t *smem) const
+    {
+        const size_t avail = (size_t)226 * 1024;
+        const size_t split = (size_t)64 * tc.rbp;
+        const size_t rawb = (size_t)(4 * ((tc.J - 1 + 3) / 4) + TC_NRB) * 128;
+        if (tc_fixed + (size_t)table_bytes + 2 * split + 2 * rawb > avail) return SRCDSP_E_SIZE;
+        int ns = 3;
+        if (tc_fixed + (size_t)table_bytes + ns * split + 3 * rawb > avail) ns = 2;
+        int nr = (int)((avail - tc_fixed - (size_t)table_bytes - ns * split) / rawb);
+        if (nr > 8) nr = 8;  // more bytes in flight than ~128 KB per SM lowers the HBM rate (tools/tmabench.cu)
+        if (nr < 2) return SRCDSP_E_SIZE;
+        if (n_raw) *n_raw = nr;
+        if (n_stages) *n_stages = ns;
+        if (smem) *smem = tc_fixed + (size_t)table_bytes + ns * split + nr * rawb;
         return SRCDSP_OK;
     }
 
@@ -578,7 +618,7 @@ int DecBank::prepare_tc()
         }
         a_rows = grouped ? 128 * J + 32 + 128 + 64 : 128 * J + 136;
         master_bytes = copies.size() * (size_t)a_rows * 32;
-        tc_fixed = ((master_bytes + 127) & ~(size_t)127) + 512;
+        tc_fixed = ((master_bytes + 127) & ~(size_t)127) + 512;  // + mbarriers (at most 416 B)
         if (tc_layout(16384, nullptr, nullptr) == SRCDSP_OK) break;  // leave room for a 4096-entry sine table
         if (!grouped && tc_layout(0, nullptr, nullptr) == SRCDSP_OK) break;
     }
@@ -650,6 +690,11 @@ int DecBank::prepare_tc()
     SRCDSP_CUDA(cudaFuncSetAttribute(dec_tc_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     SRCDSP_CUDA(cudaFuncSetAttribute(dec_tc_kernel<10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     SRCDSP_CUDA(cudaFuncSetAttribute(dec_tc_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    SRCDSP_CUDA(cudaFuncSetAttribute(dec_tma_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    SRCDSP_CUDA(cudaFuncSetAttribute(dec_tma_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    SRCDSP_CUDA(cudaFuncSetAttribute(dec_tma_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    SRCDSP_CUDA(cudaFuncSetAttribute(dec_tma_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    SRCDSP_CUDA(cudaFuncSetAttribute(dec_tma_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     tc_ok = true;
     tc_why = "";
     return SRCDSP_OK;
@@ -726,15 +771,22 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
     const long long tc_tiles = (long long)C * ((P.n_out + TC_NRB * TC_BOUT - 1) / (TC_NRB * TC_BOUT));
     int tc_stages = 0;
     size_t tc_smem = 0;
-    bool use_tc = tc_ok && tc_tiles < 0x7fffffffll && (kernel_kind == 2 || (kernel_kind == 0 && tc_tiles >= sm_count / 2));
+    bool use_tc = tc_ok && tc_tiles < 0x7fffffffll && (kernel_kind >= 2 || (kernel_kind == 0 && tc_tiles >= sm_count / 2));
     const char *why = tc_why;
     if (use_tc && mixer) {
         const PhaseMod pm = mixer->pm();
         if (!pm.mask) use_tc = false, why = "fused mixer needs a power-of-two sine table";
     }
-    if (use_tc && tc_layout(mixer ? (int)mixer->n_table * 4 : 0, &tc_stages, &tc_smem) != SRCDSP_OK)
+    // TMA-fed variant: needs 16-byte aligned rows and at least one whole row-block in the tensor
+    const int tbl_bytes = mixer ? (int)mixer->n_table * 4 : 0;
+    const long long rows_full = (long long)(n_in / (size_t)(32 * M));
+    int tma_raw = 0, tma_stages = 0;
+    size_t tma_smem = 0;
+    bool use_tma = use_tc && kernel_kind != 3 && P.vec_in && rows_full >= 1 && rows_full < 0x7fffffffll && tensor_map_encoder() &&
+                   !getenv("SRCDSP_NO_TMA") && tma_layout(tbl_bytes, &tma_raw, &tma_stages, &tma_smem) == SRCDSP_OK;
+    if (use_tc && !use_tma && tc_layout(tbl_bytes, &tc_stages, &tc_smem) != SRCDSP_OK)
         use_tc = false, why = "sine table + Toeplitz master + stages exceed 227 KB of shared memory";
-    if (kernel_kind == 2 && !use_tc)
+    if (kernel_kind >= 2 && !use_tc)
         return fail(SRCDSP_E_STATE, "tcgen05 kernel forced but not applicable: %s", tc_ok ? why : tc_why);
 
     if (mixer) {
@@ -777,14 +829,52 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
         }
         const int tgrid = (int)std::min<long long>(tc_tiles, sm_count);
         const char *dbg = getenv("SRCDSP_TC_DEBUG");  // timing experiments only (wrong results)
-        if (dbg && !mixer) {
+        if (dbg && (!mixer || use_tma)) {
             T.debug = atoi(dbg);
-            if (T.debug & 16) {  // contiguous 128-byte lines per K-step instead of a 4*G-byte stride
+            if ((T.debug & 16) && !use_tma) {  // contiguous 128-byte lines per K-step instead of a 4*G-byte stride
                 T.rb_stride = 32;
                 T.kc_stride = 32 * TC_NRB;
             }
         }
-        if (mixer) {
+        if (use_tma) {
+            TmaExtra X{};
+            X.n_raw = tma_raw;
+            X.n_conv = mixer ? TMA_MAX_CONV : 8;
+            if (const char *e = getenv("SRCDSP_TMA_CONV")) X.n_conv = std::max(1, std::min(atoi(e), TMA_MAX_CONV));
+            if (const char *e = getenv("SRCDSP_TMA_RAW")) X.n_raw = std::max(2, std::min(atoi(e), tma_raw));
+            X.raw_rows = 4 * ((T.J - 1 + 3) / 4) + TC_NRB;
+            X.box_rows = T.J - 1 + TC_NRB;
+            X.rows_full = rows_full;
+            T.n_stages = tma_stages;
+            // the input as a tensor [C][rows_full][G] of 32-bit words (one complex int16 sample each)
+            CUtensorMap map;
+            const cuuint64_t gdim[3] = {(cuuint64_t)T.G, (cuuint64_t)rows_full, (cuuint64_t)C};
+            const cuuint64_t gstr[2] = {(cuuint64_t)T.G * 4,
+                                        C > 1 ? (cuuint64_t)in_stride * 4 : (cuuint64_t)rows_full * T.G * 4};
+            const cuuint32_t box[3] = {32, (cuuint32_t)X.box_rows, 1};
+            const cuuint32_t estr[3] = {1, 1, 1};
+            const CUresult cr = tensor_map_encoder()(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)in, gdim, gstr, box, estr,
+                                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (cr != CUDA_SUCCESS) return fail(SRCDSP_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
+            const int threads = 32 * (TMA_CONV_WARP0 + X.n_conv);
+            if (T.debug & 32) {  // wait-cycle accounting variant; counters printed at the next launch
+                unsigned long long c[8];
+                cudaMemcpy(c, d_error + 2, sizeof c, cudaMemcpyDeviceToHost);
+                fprintf(stderr, "tma counters (cycles summed over CTAs): conv total %llu wait_split_empty %llu wait_raw_full %llu | mma total %llu wait_full %llu wait_tempty %llu | epi total %llu wait_tfull %llu\n", c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7]);
+                cudaMemset(d_error + 2, 0, sizeof c);
+                if (mixer)
+                    dec_tma_kernel<16, true><<<tgrid, threads, tma_smem, stream>>>(T, X, map);
+                else
+                    dec_tma_kernel<16, false><<<tgrid, threads, tma_smem, stream>>>(T, X, map);
+            } else if (mixer) {
+                dec_tma_kernel<0, true><<<tgrid, threads, tma_smem, stream>>>(T, X, map);
+            } else if (T.debug & 2) {
+                dec_tma_kernel<2, false><<<tgrid, threads, tma_smem, stream>>>(T, X, map);
+            } else {
+                dec_tma_kernel<0, false><<<tgrid, threads, tma_smem, stream>>>(T, X, map);
+            }
+        } else if (mixer) {
             dec_tc_kernel<0, true><<<tgrid, TC_THREADS, tc_smem, stream>>>(T);
         } else if (T.debug & 32) {  // wait-cycle accounting variant; counters printed at the next launch
             unsigned long long c[8];
@@ -802,7 +892,7 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
         }
         SRCDSP_LAUNCH_CHECK();
         count_launch();
-        last_kernel = 2;
+        last_kernel = use_tma ? 3 : 2;
     } else if (mixer) {
         SRCDSP_TRY(launch_dec_m<true>(P, (int)grid, nt_threads, smem_bytes, stream));
         last_kernel = 1;
@@ -1268,7 +1358,7 @@ int srcdsp_dec_get_coeff_scaling(srcdsp_dec_t h, int *cs)
 int srcdsp_dec_set_kernel(srcdsp_dec_t h, int kind)
 {
     CHECK_HANDLE(h);
-    if (kind < 0 || kind > 2) return fail(SRCDSP_E_INVALID, "kernel kind must be 0, 1 or 2");
+    if (kind < 0 || kind > 3) return fail(SRCDSP_E_INVALID, "kernel kind must be 0, 1, 2 or 3");
     h->kernel_kind = kind;
     return SRCDSP_OK;
 }

@@ -305,6 +305,195 @@ __device__ __noinline__ void tc_batch_generic(const TcParams &P, const uint32_t 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Roles shared by the two tensor-core kernels (dec_tc_kernel: LDG producers; dec_tma_kernel in
+// kernels_dec_tma.cuh: TMA-fed raw ring + converter warps).  "stages" is the ring of byte-plane
+// sample stages the MMAs read; full / empty are its mbarriers.
+// ---------------------------------------------------------------------------------------------
+struct TcRole {
+    uint8_t *a_smem, *stages;
+    int stage_bytes, NS, J, KS, warp, lane;
+    uint32_t bar_full, bar_empty, bar_tfull, bar_tempty, tmem_base;
+    long long first_tile, tile_step;
+};
+
+// MMA issuer (one warp, one elected lane issues)
+template <int DBG>
+__device__ __forceinline__ void tc_mma_role(const TcParams &P, const TcRole &R)
+{
+    uint8_t *const a_smem = R.a_smem, *const stages = R.stages;
+    const int stage_bytes = R.stage_bytes, NS = R.NS, J = R.J, KS = R.KS, warp = R.warp, lane = R.lane;
+    const uint32_t bar_full = R.bar_full, bar_empty = R.bar_empty, bar_tfull = R.bar_tfull, bar_tempty = R.bar_tempty;
+    const uint32_t tmem_base = R.tmem_base;
+    const long long first_tile = R.first_tile, tile_step = R.tile_step;
+    (void)a_smem, (void)stages, (void)stage_bytes, (void)NS, (void)J, (void)KS, (void)warp, (void)lane;
+    (void)bar_full, (void)bar_empty, (void)bar_tfull, (void)bar_tempty, (void)tmem_base;
+    // The whole warp walks the loop (warp-uniform control flow and operands, so descriptors
+    // stay in uniform registers); one elected lane issues the MMAs and the commits.
+    {
+        const uint32_t idesc_lo = umma_idesc_i8(1, 0, 128, 2 * TC_NRB);  // taps s8 x lo plane u8
+        const uint32_t idesc_hi = umma_idesc_i8(1, 1, 128, 2 * TC_NRB);  // taps s8 x hi plane s8
+        const uint32_t a_base = smem_u32(a_smem), s_base = smem_u32(stages);
+        const uint32_t lbo_a = P.a_rows * 16, lbo_b = P.rbp * 16;
+        // descriptor = constant high part | (address >> 4)
+        const uint64_t desc_a0 = umma_desc(0, lbo_a), desc_b0 = umma_desc(0, lbo_b);
+        const uint32_t hi_shift = P.grouped ? 128 : 16;  // one weight slot: 8 rows / 1 row
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t acc_phases = 0;  // bit a: parity of accumulator buffer a
+        int acc = 0;
+        long long m_full = 0, m_tempty = 0;
+        const long long m_t0 = clock64();
+        for (long long tile = first_tile; tile < P.total_tiles; tile += tile_step) {
+            mbar_wait_acc<DBG>(bar_tempty + 8 * acc, ((acc_phases >> acc) & 1) ^ 1, P.error_flag, m_tempty);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * (2 * TC_NRB);
+            uint32_t accumulate = 0;
+            for (int kc = 0; kc < KS; ++kc) {
+                mbar_wait_acc<DBG>(bar_full + 8 * stage, phase, P.error_flag, m_full);
+                tc_fence_after();
+                const int a_row = P.ks[kc].a_row, res_off = P.ks[kc].res_off;
+                const unsigned jmask = (P.debug & 1) ? 0u : P.ks[kc].jmask;
+                const uint32_t sb = s_base + stage * stage_bytes;
+                if (elect_one()) {
+                    for (int j = 0; j < J; ++j) {
+                        if (!((jmask >> j) & 1)) continue;
+                        const uint32_t a_addr = a_base + res_off + (a_row + 128 * j) * 16;
+                        const uint32_t b_addr = sb + (P.front_pad + 2 * (J - 1 - j)) * 16;
+                        umma_i8(d_tmem, desc_a0 | (a_addr >> 4), desc_b0 | (b_addr >> 4), idesc_lo, accumulate);
+                        // hi byte plane: weight slot + 1  ==  master moved back by one slot
+                        umma_i8(d_tmem, desc_a0 | ((a_addr - hi_shift) >> 4), desc_b0 | ((b_addr + 2 * lbo_b) >> 4),
+                                idesc_hi, 1);
+                        accumulate = 1;
+                    }
+                    tc_commit(bar_empty + 8 * stage);  // frees the stage when these MMAs have read it
+                    if (kc == KS - 1) tc_commit(bar_tfull + 8 * acc);
+                }
+                accumulate |= (jmask != 0);
+                __syncwarp();
+                if (++stage == NS) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            acc_phases ^= 1u << acc;
+            acc ^= 1;
+        }
+        if ((DBG & 16) && lane == 0) {
+            unsigned long long *cnt = reinterpret_cast<unsigned long long *>(P.error_flag + 2);
+            atomicAdd(cnt + 3, (unsigned long long)(clock64() - m_t0));  // MMA warp total
+            atomicAdd(cnt + 4, (unsigned long long)m_full);               // MMA waiting for a full stage
+            atomicAdd(cnt + 5, (unsigned long long)m_tempty);             // MMA waiting for a free accumulator
+        }
+    }
+}
+
+// epilogue warps 0..3: TMEM lanes 32*warp .. 32*warp+31
+template <int DBG>
+__device__ __forceinline__ void tc_epilogue_role(const TcParams &P, const TcRole &R)
+{
+    uint8_t *const a_smem = R.a_smem, *const stages = R.stages;
+    const int stage_bytes = R.stage_bytes, NS = R.NS, J = R.J, KS = R.KS, warp = R.warp, lane = R.lane;
+    const uint32_t bar_full = R.bar_full, bar_empty = R.bar_empty, bar_tfull = R.bar_tfull, bar_tempty = R.bar_tempty;
+    const uint32_t tmem_base = R.tmem_base;
+    const long long first_tile = R.first_tile, tile_step = R.tile_step;
+    (void)a_smem, (void)stages, (void)stage_bytes, (void)NS, (void)J, (void)KS, (void)warp, (void)lane;
+    (void)bar_full, (void)bar_empty, (void)bar_tfull, (void)bar_tempty, (void)tmem_base;
+    const int w = lane & 3;
+    const int b = 8 * warp + (lane >> 2);
+    long long e_wait = 0;
+    const long long e_t0 = clock64();
+    uint32_t acc_phases = 0;
+    int acc = 0;
+    for (long long tile = first_tile; tile < P.total_tiles; tile += tile_step) {
+        const int ch = (int)(tile / P.tiles_per_ch);
+        const long long tt = tile - (long long)ch * P.tiles_per_ch;
+        uint32_t *o = P.out + (size_t)ch * P.out_stride;
+        mbar_wait_acc<DBG>(bar_tfull + 8 * acc, (acc_phases >> acc) & 1, P.error_flag, e_wait);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + ((uint32_t)(32 * warp) << 16) + acc * (2 * TC_NRB);
+        if (P.grouped) {
+            // weight slots of output b sit 8 TMEM lanes apart: a 16x256b load hands one thread the
+            // slots {0,1} (lanes 0-15 of the warp's quadrant) or {2,3} (lanes 16-31) of output
+            // b = 8*warp + lane/4 for the column pairs (re, im) of 4 row-blocks -> no shuffles
+#pragma unroll 1
+            for (int c0 = 0; c0 < ((P.debug & 4) ? 0 : 2 * TC_NRB); c0 += 32) {
+                uint32_t a[16], h[16];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+                    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                    : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]),
+                      "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]),
+                      "=r"(a[15])
+                    : "r"(t_addr + c0));
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+                    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                    : "=r"(h[0]), "=r"(h[1]), "=r"(h[2]), "=r"(h[3]), "=r"(h[4]), "=r"(h[5]), "=r"(h[6]), "=r"(h[7]),
+                      "=r"(h[8]), "=r"(h[9]), "=r"(h[10]), "=r"(h[11]), "=r"(h[12]), "=r"(h[13]), "=r"(h[14]),
+                      "=r"(h[15])
+                    : "r"(t_addr + (16u << 16) + c0));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    // sum_w 256^w * D_w (mod 2^32, exactly the reference's int32 wrap)
+                    const uint32_t re = a[4 * k] + (a[4 * k + 2] << 8) + (h[4 * k] << 16) + (h[4 * k + 2] << 24);
+                    const uint32_t im = a[4 * k + 1] + (a[4 * k + 3] << 8) + (h[4 * k + 1] << 16) + (h[4 * k + 3] << 24);
+                    const int m = (c0 >> 1) + 4 * k + (lane & 3);
+                    const long long idx = (tt * TC_NRB + m) * TC_BOUT + b;
+                    if (idx < P.n_out) o[idx] = scale_pack<true>((int)re, (int)im, P.shift);
+                }
+            }
+        } else {
+#pragma unroll 1
+        for (int c0 = 0; c0 < ((P.debug & 4) ? 0 : 2 * TC_NRB); c0 += 32) {
+            uint32_t v[32];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+                  "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+                  "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+                  "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(t_addr + c0));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            // sum_w 256^w * D_w over the 4 lanes of the quad (mod 2^32, exactly the int32 wrap)
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                uint32_t s = v[c] << (8 * w);
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                v[c] = s;
+            }
+            // lane w finalises the row-blocks m = c0/2 + 4*i + w of this chunk
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                // select v[2*(4*i + w)], v[2*(4*i + w) + 1] without dynamic register indexing
+                uint32_t re = v[8 * i], im = v[8 * i + 1];
+                if (w == 1) re = v[8 * i + 2], im = v[8 * i + 3];
+                if (w == 2) re = v[8 * i + 4], im = v[8 * i + 5];
+                if (w == 3) re = v[8 * i + 6], im = v[8 * i + 7];
+                const int m = (c0 >> 1) + 4 * i + w;
+                const long long idx = (tt * TC_NRB + m) * TC_BOUT + b;
+                if (idx < P.n_out) o[idx] = scale_pack<true>((int)re, (int)im, P.shift);
+            }
+        }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+        acc_phases ^= 1u << acc;
+        acc ^= 1;
+    }
+    if ((DBG & 16) && lane == 0) {
+        unsigned long long *cnt = reinterpret_cast<unsigned long long *>(P.error_flag + 2);
+        atomicAdd(cnt + 6, (unsigned long long)(clock64() - e_t0));  // epilogue warp total
+        atomicAdd(cnt + 7, (unsigned long long)e_wait);               // epilogue waiting for accumulators
+    }
+}
+
 template <int DBG, bool MIX>
 __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_constant__ TcParams P)
 {
@@ -354,6 +543,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
 
     const long long first_tile = blockIdx.x, tile_step = gridDim.x;
     const int KS = P.M;  // K-steps per tile
+    const TcRole role{a_smem, stages, stage_bytes, NS, J, KS, warp, lane, bar_full, bar_empty, bar_tfull, bar_tempty, tmem_base,
+                      first_tile, tile_step};
 
     if (warp >= TC_PROD_WARP0) {
         // =====================================================================================
@@ -471,167 +662,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
         // =====================================================================================
         // MMA issuer (one thread)
         // =====================================================================================
-        // The whole warp walks the loop (warp-uniform control flow and operands, so descriptors
-        // stay in uniform registers); one elected lane issues the MMAs and the commits.
-        {
-            const uint32_t idesc_lo = umma_idesc_i8(1, 0, 128, 2 * TC_NRB);  // taps s8 x lo plane u8
-            const uint32_t idesc_hi = umma_idesc_i8(1, 1, 128, 2 * TC_NRB);  // taps s8 x hi plane s8
-            const uint32_t a_base = smem_u32(a_smem), s_base = smem_u32(stages);
-            const uint32_t lbo_a = P.a_rows * 16, lbo_b = P.rbp * 16;
-            // descriptor = constant high part | (address >> 4)
-            const uint64_t desc_a0 = umma_desc(0, lbo_a), desc_b0 = umma_desc(0, lbo_b);
-            const uint32_t hi_shift = P.grouped ? 128 : 16;  // one weight slot: 8 rows / 1 row
-            int stage = 0;
-            uint32_t phase = 0;
-            uint32_t acc_phases = 0;  // bit a: parity of accumulator buffer a
-            int acc = 0;
-            long long m_full = 0, m_tempty = 0;
-            const long long m_t0 = clock64();
-            for (long long tile = first_tile; tile < P.total_tiles; tile += tile_step) {
-                mbar_wait_acc<DBG>(bar_tempty + 8 * acc, ((acc_phases >> acc) & 1) ^ 1, P.error_flag, m_tempty);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * (2 * TC_NRB);
-                uint32_t accumulate = 0;
-                for (int kc = 0; kc < KS; ++kc) {
-                    mbar_wait_acc<DBG>(bar_full + 8 * stage, phase, P.error_flag, m_full);
-                    tc_fence_after();
-                    const int a_row = P.ks[kc].a_row, res_off = P.ks[kc].res_off;
-                    const unsigned jmask = (P.debug & 1) ? 0u : P.ks[kc].jmask;
-                    const uint32_t sb = s_base + stage * stage_bytes;
-                    if (elect_one()) {
-                        for (int j = 0; j < J; ++j) {
-                            if (!((jmask >> j) & 1)) continue;
-                            const uint32_t a_addr = a_base + res_off + (a_row + 128 * j) * 16;
-                            const uint32_t b_addr = sb + (P.front_pad + 2 * (J - 1 - j)) * 16;
-                            umma_i8(d_tmem, desc_a0 | (a_addr >> 4), desc_b0 | (b_addr >> 4), idesc_lo, accumulate);
-                            // hi byte plane: weight slot + 1  ==  master moved back by one slot
-                            umma_i8(d_tmem, desc_a0 | ((a_addr - hi_shift) >> 4), desc_b0 | ((b_addr + 2 * lbo_b) >> 4),
-                                    idesc_hi, 1);
-                            accumulate = 1;
-                        }
-                        tc_commit(bar_empty + 8 * stage);  // frees the stage when these MMAs have read it
-                        if (kc == KS - 1) tc_commit(bar_tfull + 8 * acc);
-                    }
-                    accumulate |= (jmask != 0);
-                    __syncwarp();
-                    if (++stage == NS) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
-                }
-                acc_phases ^= 1u << acc;
-                acc ^= 1;
-            }
-            if ((DBG & 16) && lane == 0) {
-                unsigned long long *cnt = reinterpret_cast<unsigned long long *>(P.error_flag + 2);
-                atomicAdd(cnt + 3, (unsigned long long)(clock64() - m_t0));  // MMA warp total
-                atomicAdd(cnt + 4, (unsigned long long)m_full);               // MMA waiting for a full stage
-                atomicAdd(cnt + 5, (unsigned long long)m_tempty);             // MMA waiting for a free accumulator
-            }
-        }
+        tc_mma_role<DBG>(P, role);
     } else {
         // =====================================================================================
         // epilogue warps 0..3: TMEM lanes 32*warp .. 32*warp+31  ->  rho = 4*b + w
         // =====================================================================================
-        const int w = lane & 3;
-        const int b = 8 * warp + (lane >> 2);
-        long long e_wait = 0;
-        const long long e_t0 = clock64();
-        uint32_t acc_phases = 0;
-        int acc = 0;
-        for (long long tile = first_tile; tile < P.total_tiles; tile += tile_step) {
-            const int ch = (int)(tile / P.tiles_per_ch);
-            const long long tt = tile - (long long)ch * P.tiles_per_ch;
-            uint32_t *o = P.out + (size_t)ch * P.out_stride;
-            mbar_wait_acc<DBG>(bar_tfull + 8 * acc, (acc_phases >> acc) & 1, P.error_flag, e_wait);
-            tc_fence_after();
-            const uint32_t t_addr = tmem_base + ((uint32_t)(32 * warp) << 16) + acc * (2 * TC_NRB);
-            if (P.grouped) {
-                // weight slots of output b sit 8 TMEM lanes apart: a 16x256b load hands one thread the
-                // slots {0,1} (lanes 0-15 of the warp's quadrant) or {2,3} (lanes 16-31) of output
-                // b = 8*warp + lane/4 for the column pairs (re, im) of 4 row-blocks -> no shuffles
-#pragma unroll 1
-                for (int c0 = 0; c0 < ((P.debug & 4) ? 0 : 2 * TC_NRB); c0 += 32) {
-                    uint32_t a[16], h[16];
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
-                        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                        : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]),
-                          "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]),
-                          "=r"(a[15])
-                        : "r"(t_addr + c0));
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
-                        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                        : "=r"(h[0]), "=r"(h[1]), "=r"(h[2]), "=r"(h[3]), "=r"(h[4]), "=r"(h[5]), "=r"(h[6]), "=r"(h[7]),
-                          "=r"(h[8]), "=r"(h[9]), "=r"(h[10]), "=r"(h[11]), "=r"(h[12]), "=r"(h[13]), "=r"(h[14]),
-                          "=r"(h[15])
-                        : "r"(t_addr + (16u << 16) + c0));
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        // sum_w 256^w * D_w (mod 2^32, exactly the reference's int32 wrap)
-                        const uint32_t re = a[4 * k] + (a[4 * k + 2] << 8) + (h[4 * k] << 16) + (h[4 * k + 2] << 24);
-                        const uint32_t im = a[4 * k + 1] + (a[4 * k + 3] << 8) + (h[4 * k + 1] << 16) + (h[4 * k + 3] << 24);
-                        const int m = (c0 >> 1) + 4 * k + (lane & 3);
-                        const long long idx = (tt * TC_NRB + m) * TC_BOUT + b;
-                        if (idx < P.n_out) o[idx] = scale_pack<true>((int)re, (int)im, P.shift);
-                    }
-                }
-            } else {
-#pragma unroll 1
-            for (int c0 = 0; c0 < ((P.debug & 4) ? 0 : 2 * TC_NRB); c0 += 32) {
-                uint32_t v[32];
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-                    "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
-                      "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
-                      "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
-                      "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(t_addr + c0));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                // sum_w 256^w * D_w over the 4 lanes of the quad (mod 2^32, exactly the int32 wrap)
-#pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    uint32_t s = v[c] << (8 * w);
-                    s += __shfl_xor_sync(0xffffffffu, s, 1);
-                    s += __shfl_xor_sync(0xffffffffu, s, 2);
-                    v[c] = s;
-                }
-                // lane w finalises the row-blocks m = c0/2 + 4*i + w of this chunk
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    // select v[2*(4*i + w)], v[2*(4*i + w) + 1] without dynamic register indexing
-                    uint32_t re = v[8 * i], im = v[8 * i + 1];
-                    if (w == 1) re = v[8 * i + 2], im = v[8 * i + 3];
-                    if (w == 2) re = v[8 * i + 4], im = v[8 * i + 5];
-                    if (w == 3) re = v[8 * i + 6], im = v[8 * i + 7];
-                    const int m = (c0 >> 1) + 4 * i + w;
-                    const long long idx = (tt * TC_NRB + m) * TC_BOUT + b;
-                    if (idx < P.n_out) o[idx] = scale_pack<true>((int)re, (int)im, P.shift);
-                }
-            }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-            acc_phases ^= 1u << acc;
-            acc ^= 1;
-        }
-        if ((DBG & 16) && lane == 0) {
-            unsigned long long *cnt = reinterpret_cast<unsigned long long *>(P.error_flag + 2);
-            atomicAdd(cnt + 6, (unsigned long long)(clock64() - e_t0));  // epilogue warp total
-            atomicAdd(cnt + 7, (unsigned long long)e_wait);               // epilogue waiting for accumulators
-        }
+        tc_epilogue_role<DBG>(P, role);
     }
 
-    if ((DBG & 16) && warp < 4 && lane == 0) {
-        unsigned long long *cnt = reinterpret_cast<unsigned long long *>(P.error_flag + 2);
-        // NB e_t0 / e_wait only exist in the epilogue branch; recorded there
-    }
     // ---- teardown ---------------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();

@@ -1,0 +1,287 @@
+// kernels_dec_tma.cuh -- the tcgen05 int8 Toeplitz decimator (kernels_dec_tc.cuh) fed by TMA.
+//
+// Same GEMM, same resident tap "master", same epilogue as dec_tc_kernel; what changes is how the
+// samples reach the byte-plane stages.  dec_tc_kernel's producers load global memory into
+// registers, so HBM latency is covered only by the number of producer warps (6.1 TB/s ceiling for
+// the 128-bytes-per-2-KB K-step pattern, tools/ldbench.cu).  Here one thread issues a 3-D TMA box
+// per K-step -- (32 samples) x (J-1 halo + 128 row-blocks) x (1 channel) of the raw interleaved
+// int16 stream -- into a ring of RAW stages (the bytes in flight no longer cost registers or
+// warps: 7.4 TB/s with the same pattern, tools/tmabench.cu), and converter warps turn a raw
+// stage into a byte-plane stage: LDS.128 -> (NCO mix) -> 8 PRMT -> 4 STS.32, all on-chip.
+//
+//   warps 0-3   epilogue            (tc_epilogue_role)
+//   warp  4     MMA issuer + TMEM   (tc_mma_role)
+//   warp  5     TMA issuer (one lane)
+//   warps 6..   converters: every warp takes every n_conv-th group of 4 rows of every K-step
+//
+// Edges (rare): rows in front of the block come from the carried history and the ragged last
+// row-block is not part of the TMA tensor; the TMA box zero-fills both and the converters patch
+// those rows straight from global memory (tc_sample, the same code dec_tc_kernel uses).
+#pragma once
+
+#include <cuda.h>
+
+#include "kernels_dec_tc.cuh"
+
+namespace srcdsp {
+
+constexpr int TMA_CONV_WARP0 = 6;
+constexpr int TMA_MAX_CONV = 16;
+constexpr int TMA_MAX_THREADS = 32 * (TMA_CONV_WARP0 + TMA_MAX_CONV);
+constexpr int TMA_MAX_RAW = 12;
+
+struct TmaExtra {
+    int n_raw;        // raw stages
+    int n_conv;       // converter warps
+    int raw_rows;     // rows of a raw stage: 4 * ceil((J-1)/4) + 128 (the box lands at row raw_rows - box_rows)
+    int box_rows;     // J - 1 + 128
+    long long rows_full;  // floor(n_in / G): row-blocks that are part of the TMA tensor
+};
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+        : "memory");
+}
+
+template <bool MIX>
+__device__ __forceinline__ void tma_convert_store(uint4 q, uint8_t *dst, int hi_off, const uint32_t *tab, unsigned p0, unsigned fr,
+                                                  unsigned mask)
+{
+    if (MIX) {  // mixers.h:172-177 on the 4 samples of this piece
+        q.x = mix_sample_packed(q.x, tab[p0]);
+        q.y = mix_sample_packed(q.y, tab[(p0 + fr) & mask]);
+        q.z = mix_sample_packed(q.z, tab[(p0 + 2 * fr) & mask]);
+        q.w = mix_sample_packed(q.w, tab[(p0 + 3 * fr) & mask]);
+    }
+    uint32_t re_lo, re_hi, im_lo, im_hi;
+    split4(q, re_lo, re_hi, im_lo, im_hi);
+    *reinterpret_cast<uint32_t *>(dst) = re_lo;
+    *reinterpret_cast<uint32_t *>(dst + 16) = im_lo;
+    *reinterpret_cast<uint32_t *>(dst + hi_off) = re_hi;
+    *reinterpret_cast<uint32_t *>(dst + hi_off + 16) = im_hi;
+}
+
+template <int DBG, bool MIX>
+__global__ void __launch_bounds__(TMA_MAX_THREADS, 1)
+    dec_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TmaExtra X, const __grid_constant__ CUtensorMap in_map)
+{
+    extern __shared__ __align__(128) uint8_t tc_smem_raw[];
+    uint8_t *smem = tc_smem_raw;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int J = P.J;
+    const int stage_bytes = 4 * P.rbp * 16;  // byte-plane stage: 2 planes x 2 kc chunks
+    const int raw_bytes = X.raw_rows * 128;
+    const int NS = P.n_stages, NR = X.n_raw, NCW = X.n_conv;
+    uint8_t *a_smem = smem;
+    uint32_t *tab_smem = reinterpret_cast<uint32_t *>(smem + ((P.master_bytes + 127) & ~127));
+    uint8_t *raw = reinterpret_cast<uint8_t *>(tab_smem) + P.table_bytes;
+    uint8_t *stages = raw + NR * raw_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(stages + NS * stage_bytes);
+    // bars: full[TC_MAX_STAGES], empty[TC_MAX_STAGES], tmem_full[2], tmem_empty[2], raw_full[TMA_MAX_RAW], raw_empty[TMA_MAX_RAW]
+    const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * TC_MAX_STAGES;
+    const uint32_t bar_tfull = bar_empty + 8 * TC_MAX_STAGES, bar_tempty = bar_tfull + 16;
+    const uint32_t bar_rfull = bar_tempty + 16, bar_rempty = bar_rfull + 8 * TMA_MAX_RAW;
+    __shared__ uint32_t tmem_base_s;
+
+    // ---- setup ------------------------------------------------------------------------------
+    for (int i = tid; i < P.master_bytes / 16; i += blockDim.x)
+        reinterpret_cast<uint4 *>(a_smem)[i] = __ldg(reinterpret_cast<const uint4 *>(P.master) + i);
+    if (MIX)
+        for (int i = tid; i < P.table_bytes / 4; i += blockDim.x) tab_smem[i] = __ldg(P.cs_table + i);
+    // padding rows of both rings must be defined: zero everything once
+    for (int i = tid; i < (NR * raw_bytes + NS * stage_bytes) / 16; i += blockDim.x)
+        reinterpret_cast<uint4 *>(raw)[i] = make_uint4(0, 0, 0, 0);
+    fence_async_smem();
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(bar_full + 8 * s, NCW);  // one arrival per converter warp
+            mbar_init(bar_empty + 8 * s, 1);   // tcgen05.commit
+        }
+        for (int s = 0; s < NR; ++s) {
+            mbar_init(bar_rfull + 8 * s, 1);   // expect_tx arrival + the box's bytes
+            mbar_init(bar_rempty + 8 * s, NCW);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_tfull + 8 * a, 1);
+            mbar_init(bar_tempty + 8 * a, 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    const long long first_tile = blockIdx.x, tile_step = gridDim.x;
+    const int KS = P.M;
+    const TcRole role{a_smem, stages, stage_bytes, NS, J, KS, warp, lane, bar_full, bar_empty, bar_tfull, bar_tempty, tmem_base,
+                      first_tile, tile_step};
+
+    if (warp >= TMA_CONV_WARP0) {
+        // =====================================================================================
+        // converters: raw stage (rows of 32 interleaved samples) -> byte-plane stage
+        // =====================================================================================
+        const int cw = warp - TMA_CONV_WARP0;
+        const int piece = lane & 7, grp = lane >> 3;
+        const int chunk = P.rbp * 16;
+        const int halo_rows4 = X.raw_rows - TC_NRB;   // 4 * ceil((J-1)/4)
+        const int NQ = X.raw_rows / 4;                // groups of 4 rows per stage
+        // raw row i (0 .. raw_rows) holds row-block rb = i - halo_rows4; its byte-plane rows are
+        // front_pad + 2 * (rb + J - 1) = 2 * i (+1 for im)  [front_pad = 2 * (halo_rows4 - (J - 1))]
+        const int src_lane = grp * 128 + piece * 16;
+        const int dst_lane = (piece >> 2) * chunk + grp * 32 + (piece & 3) * 4;
+        const int hi_off = 2 * chunk;
+        int rs = 0, ss = 0;
+        uint32_t rpar = 0, spar = 1;  // first wait on a fresh "empty" barrier passes
+        int rot = cw;                 // rotates the warp -> row-group assignment so that the odd group averages out
+        long long w_wait_raw = 0, w_wait_split = 0;
+        const long long w_t0 = clock64();
+        for (long long tile = first_tile; tile < P.total_tiles; tile += tile_step) {
+            const unsigned tl = (unsigned)tile;
+            const unsigned ch = tl / (unsigned)P.tiles_per_ch;
+            const unsigned tt = tl - ch * (unsigned)P.tiles_per_ch;
+            const uint32_t *x = P.in + (size_t)ch * P.in_stride;
+            const uint32_t *hist = P.hist_in + (size_t)ch * P.H;
+            const long long tile0 = (long long)tt * TC_NRB * (long long)P.G;  // sample of (row-block 0, K-step 0)
+            // rows the TMA tensor does not hold: history in front of the block, everything from the ragged row-block on
+            const bool edge = (tt == 0 && J > 1) || ((long long)(tt + 1) * TC_NRB > X.rows_full);
+            unsigned ph0 = 0, fr = 0, dph = 0;
+            if (MIX) {
+                ph0 = (unsigned)P.phi[ch];
+                fr = (unsigned)P.freq[ch];
+                dph = (((unsigned)(4 * NCW * P.G) & P.mix_mask) * fr) & P.mix_mask;  // phase step between a warp's row groups
+            }
+            for (int kc = 0; kc < KS; ++kc) {
+                mbar_wait_acc<DBG>(bar_rfull + 8 * rs, rpar, P.error_flag, w_wait_raw);
+                mbar_wait_acc<DBG>(bar_empty + 8 * ss, spar, P.error_flag, w_wait_split);
+                const uint8_t *src = raw + rs * raw_bytes + src_lane;
+                uint8_t *dst = stages + ss * stage_bytes + dst_lane;
+                // sample index of (raw row grp, this lane's piece) of this K-step
+                const long long n_row0 = tile0 + (long long)(grp - halo_rows4) * P.G + 32 * kc + 4 * piece;
+                if (!edge) {
+                    unsigned ph = 0;
+                    if (MIX) ph = (ph0 + ((unsigned)(n_row0 + (long long)4 * rot * P.G) & P.mix_mask) * fr) & P.mix_mask;
+                    int q = rot;
+                    // two row groups per iteration: independent LDS / PRMT / STS chains
+                    for (; q + NCW < NQ; q += 2 * NCW) {
+                        const uint4 v0 = *reinterpret_cast<const uint4 *>(src + q * 512);
+                        const uint4 v1 = *reinterpret_cast<const uint4 *>(src + (q + NCW) * 512);
+                        tma_convert_store<MIX>(v0, dst + q * 128, hi_off, tab_smem, ph, fr, P.mix_mask);
+                        tma_convert_store<MIX>(v1, dst + (q + NCW) * 128, hi_off, tab_smem, (ph + dph) & P.mix_mask, fr, P.mix_mask);
+                        if (MIX) ph = (ph + 2 * dph) & P.mix_mask;
+                    }
+                    if (q < NQ) {
+                        const uint4 v0 = *reinterpret_cast<const uint4 *>(src + q * 512);
+                        tma_convert_store<MIX>(v0, dst + q * 128, hi_off, tab_smem, ph, fr, P.mix_mask);
+                    }
+                } else {
+                    for (int q = rot; q < NQ; q += NCW) {
+                        const int rb = 4 * q + grp - halo_rows4;
+                        const long long n = n_row0 + (long long)4 * q * P.G;
+                        uint4 v;
+                        if (rb < -(J - 1)) {
+                            v = make_uint4(0, 0, 0, 0);  // padding rows in front of the halo: never read by an MMA
+                        } else if (n < 0 || (long long)(tt * TC_NRB) + rb >= X.rows_full) {
+                            // carried history (already mixed) / ragged end: straight from global memory
+                            if (MIX) {
+                                v.x = tc_sample_mix(P, x, hist, n, ph0, fr);
+                                v.y = tc_sample_mix(P, x, hist, n + 1, ph0, fr);
+                                v.z = tc_sample_mix(P, x, hist, n + 2, ph0, fr);
+                                v.w = tc_sample_mix(P, x, hist, n + 3, ph0, fr);
+                            } else {
+                                v.x = tc_sample(x, hist, P.H, P.n_in, n);
+                                v.y = tc_sample(x, hist, P.H, P.n_in, n + 1);
+                                v.z = tc_sample(x, hist, P.H, P.n_in, n + 2);
+                                v.w = tc_sample(x, hist, P.H, P.n_in, n + 3);
+                            }
+                            tma_convert_store<false>(v, dst + q * 128, hi_off, tab_smem, 0, 0, 0);
+                            continue;
+                        } else {
+                            v = *reinterpret_cast<const uint4 *>(src + q * 512);
+                        }
+                        const unsigned ph = MIX ? (ph0 + ((unsigned)n & P.mix_mask) * fr) & P.mix_mask : 0u;
+                        tma_convert_store<MIX>(v, dst + q * 128, hi_off, tab_smem, ph, fr, P.mix_mask);
+                    }
+                }
+                // the MMA reads shared memory through the async proxy: fence this warp's stores, then
+                // one arrival per warp on both rings
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(bar_full + 8 * ss);
+                    mbar_arrive(bar_rempty + 8 * rs);
+                }
+                if (++rs == NR) {
+                    rs = 0;
+                    rpar ^= 1;
+                }
+                if (++ss == NS) {
+                    ss = 0;
+                    spar ^= 1;
+                }
+                if (++rot == NCW) rot = 0;
+            }
+        }
+        if ((DBG & 16) && lane == 0) {
+            unsigned long long *cnt = reinterpret_cast<unsigned long long *>(P.error_flag + 2);
+            atomicAdd(cnt + 0, (unsigned long long)(clock64() - w_t0));  // converter total
+            atomicAdd(cnt + 1, (unsigned long long)w_wait_split);         // waiting for a free byte-plane stage
+            atomicAdd(cnt + 2, (unsigned long long)w_wait_raw);           // waiting for a raw stage (TMA / HBM)
+        }
+    } else if (warp == 5) {
+        // =====================================================================================
+        // TMA issuer: one box per K-step = 32 samples x (J-1 + 128) row-blocks of one channel
+        // =====================================================================================
+        if (lane == 0) {
+            const int pad_bytes = (X.raw_rows - X.box_rows) * 128;
+            const uint32_t box_bytes = (uint32_t)X.box_rows * 128;
+            const uint32_t raw_u32 = smem_u32(raw);
+            int rs = 0;
+            uint32_t rpar = 1;
+            for (long long tile = first_tile; tile < P.total_tiles; tile += tile_step) {
+                const unsigned tl = (unsigned)tile;
+                const unsigned ch = tl / (unsigned)P.tiles_per_ch;
+                const unsigned tt = tl - ch * (unsigned)P.tiles_per_ch;
+                const int row0 = (int)tt * TC_NRB - (J - 1);  // negative / beyond the end: zero-filled by the TMA unit
+                for (int kc = 0; kc < KS; ++kc) {
+                    mbar_wait(bar_rempty + 8 * rs, rpar, P.error_flag);
+                    if (!(DBG & 2)) {
+                        mbar_expect_tx(bar_rfull + 8 * rs, box_bytes);
+                        tma_load_3d(raw_u32 + rs * raw_bytes + pad_bytes, &in_map, 32 * kc, row0, (int)ch, bar_rfull + 8 * rs);
+                    } else {  // timing experiment: no global loads
+                        mbar_arrive(bar_rfull + 8 * rs);
+                    }
+                    if (++rs == NR) {
+                        rs = 0;
+                        rpar ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 4) {
+        tc_mma_role<DBG>(P, role);
+    } else {
+        tc_epilogue_role<DBG>(P, role);
+    }
+
+    // ---- teardown ---------------------------------------------------------------------------
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+    }
+}
+
+}  // namespace srcdsp

@@ -303,7 +303,8 @@ def test_cfg2_full_size_spot_and_split_invariance(S, corc):
 @pytest.mark.parametrize("M,nt,amp", [(16, 255, 400), (16, 256, 30000), (8, 63, 2000), (4, 1023, 300), (2, 9, 100),
                                       (1, 33, 8000), (3, 31, 500), (5, 50, 500), (10, 90, 100000), (12, 255, 2 ** 22),
                                       (32, 64, 127), (64, 300, 500), (16, 17, 1)])
-def test_tc_decimator_sweep(S, corc, M, nt, amp):
+@pytest.mark.parametrize("kind", [2, 3])
+def test_tc_decimator_sweep(S, corc, M, nt, amp, kind):
     """The tensor-core path is exact for every ratio / length / tap magnitude it accepts, across
     streaming blocks (history), ragged tile ends and several channels (persistent tile loop)."""
     rng = np.random.default_rng(M * 7919 + nt)
@@ -311,12 +312,15 @@ def test_tc_decimator_sweep(S, corc, M, nt, amp):
     taps[0] = amp
     C = 3
     d = S.FilterDnsamplingFir(M, taps, channels=C, obsolete=True)
-    d.set_kernel(2)
+    d.set_kernel(kind)
     hs = [None] * C
-    for blk, n_out in enumerate([4096 * 2 + 77, 5, 4096, 1300]):
+    for blk, n_out in enumerate([4096 * 2 + 77, 5, 4096, 1300, 4096 * 3]):
         n = n_out * M
         x = rng.integers(-32768, 32768, (C, n, 2)).astype(np.int16)
         got = host(d.step(dev(x))) if blk % 2 == 0 else d.step(x)
+        # kind 2 is fed by TMA whenever a whole row-block (32 outputs) exists and the channel rows are
+        # 16-byte aligned, kind 3 never
+        assert d.last_kernel.startswith("dec_tma" if kind == 2 and n_out >= 32 and n % 4 == 0 else "dec_tc"), d.last_kernel
         for c in range(C):
             exp, hs[c] = corc.dec_step(taps, M, x[c], hs[c])
             assert np.array_equal(got[c], exp), (M, nt, blk, c)
@@ -330,11 +334,13 @@ def test_tc_matches_imad_on_unaligned_buffers(S, corc):
     big = torch.from_numpy(rng.integers(-32768, 32768, (C, n + 7, 2)).astype(np.int16)).cuda()
     x = big[:, 3: 3 + n]  # 12-byte offset: the 16-byte fast path is off
     outs = []
-    for kind in (1, 2):
+    for kind in (1, 2, 3):
         d = S.FilterDnsamplingFir(M, taps, channels=C, obsolete=True)
         d.set_kernel(kind)
         outs.append(host(d.step(x)))
+        assert d.last_kernel.startswith("dec_tc" if kind > 1 else "dec_fir")  # no TMA on unaligned rows
     assert np.array_equal(outs[0], outs[1])
+    assert np.array_equal(outs[0], outs[2])
     e, _ = corc.dec_step(taps, M, host(x[2]))
     assert np.array_equal(outs[1][2], e)
 
@@ -350,7 +356,8 @@ def test_tc_rejects_what_it_cannot_do(S):
 
 
 @pytest.mark.parametrize("M,nt,n_table", [(16, 255, 4096), (8, 63, 4096), (4, 200, 1024), (2, 50, 4096), (3, 31, 256)])
-def test_tc_fused_mixer(S, corc, M, nt, n_table):
+@pytest.mark.parametrize("kind", [2, 3])
+def test_tc_fused_mixer(S, corc, M, nt, n_table, kind):
     """NCO mix fused into the tensor-core kernel's load stage == Mixer::step then decimator::step."""
     rng = np.random.default_rng(M * 31 + nt)
     taps = O.design_lowpass_taps(nt, M)
@@ -359,16 +366,16 @@ def test_tc_fused_mixer(S, corc, M, nt, n_table):
     m = S.Mixer(n_table=n_table, channels=C)
     m.setFrequency(fs)
     d = S.FilterDnsamplingFir(M, taps, channels=C, obsolete=True)
-    d.set_kernel(2)
+    d.set_kernel(kind)
     chain = S.Ddc(m, d)
     st = [(0, None)] * C
-    for blk, n_out in enumerate([4096 * 2 + 33, 7, 4096 + 1500]):
+    for blk, n_out in enumerate([4096 * 2 + 33, 7, 4096 + 1500, 4096 * 2]):
         x = rng.integers(-32768, 32768, (C, n_out * M, 2)).astype(np.int16)
         if blk == 2:
             m.adjustFrequency(0.0101, ch=1)
             fs[1] = corc.mixer_adjust_nominal(float(fs[1]), 0.0101)
         got = host(chain.step(dev(x))) if blk % 2 == 0 else chain.step(x)
-        assert d.last_kernel.startswith("dec_tc")
+        assert d.last_kernel.startswith("dec_tma" if kind == 2 and n_out >= 32 and (n_out * M) % 4 == 0 else "dec_tc")
         for c in range(C):
             phi, h = st[c]
             y, phi = corc.mixer_step(x[c], phi, corc.mixer_set_frequency(float(fs[c]), n_table), n_table)
@@ -422,7 +429,7 @@ def test_filter_fir(S, corc):
     assert np.array_equal(f.step(x)[1], e)
 
 
-@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("kernel", [1, 2, 3])
 def test_time_sliced_stream_equals_sequential(S, corc, kernel):
     """cfg-5 shape in miniature: one long stream cut into slices that are processed independently
     (as different GPUs would), each after a warm-up halo with the NCO phase set in closed form,
