@@ -449,8 +449,10 @@ struct DecBank : Bank {
         const size_t split = (size_t)64 * tc.rbp;
         const size_t rawb = (size_t)(4 * ((tc.J - 1 + 3) / 4) + TC_NRB) * 128;
         if (tc_fixed + (size_t)table_bytes + 2 * split + 2 * rawb > avail) return SRCDSP_E_SIZE;
-        int ns = 3;
-        if (tc_fixed + (size_t)table_bytes + ns * split + 3 * rawb > avail) ns = 2;
+        // byte-plane stages: one per converter group being filled + 2 for the MMAs; the rest of the
+        // shared memory is the raw ring = the bytes in flight from HBM (at least 4 stages wanted)
+        int ns = 4;
+        while (ns > 2 && tc_fixed + (size_t)table_bytes + ns * split + 4 * rawb > avail) --ns;
         int nr = (int)((avail - tc_fixed - (size_t)table_bytes - ns * split) / rawb);
         if (nr > 8) nr = 8;  // more bytes in flight than ~128 KB per SM lowers the HBM rate (tools/tmabench.cu)
         if (nr < 2) return SRCDSP_E_SIZE;
@@ -601,7 +603,7 @@ int DecBank::prepare_tc()
     std::vector<int> copy_of_kc(M);
     std::vector<std::pair<int, int>> copies;  // (s, r)
     int grouped = 1, a_rows = 0;
-    size_t master_bytes = 0;
+    size_t master_bytes = 0, image_bytes = 0;
     for (; grouped >= 0; --grouped) {
         copies.clear();
         for (int kc = 0; kc < M; ++kc) {
@@ -617,7 +619,9 @@ int DecBank::prepare_tc()
             copy_of_kc[kc] = idx;
         }
         a_rows = grouped ? 128 * J + 32 + 128 + 64 : 128 * J + 136;
-        master_bytes = copies.size() * (size_t)a_rows * 32;
+        image_bytes = copies.size() * (size_t)a_rows * 32;
+        // the MMA plan behind the image: M headers of 8 B, then one 16-byte entry per (K-step, lag) + 1 pad
+        master_bytes = image_bytes + (((size_t)M * 8 + 15) & ~(size_t)15) + ((size_t)M * J + 1) * 16;
         tc_fixed = ((master_bytes + 127) & ~(size_t)127) + 512;  // + mbarriers (at most 416 B)
         if (tc_layout(16384, nullptr, nullptr) == SRCDSP_OK) break;  // leave room for a 4096-entry sine table
         if (!grouped && tc_layout(0, nullptr, nullptr) == SRCDSP_OK) break;
@@ -649,6 +653,36 @@ int DecBank::prepare_tc()
             }
         }
     }
+    // MMA plan (tc_mma_role): operand addresses >> 4, A relative to the master, B relative to the stage
+    const int plan_hdr_off = (int)image_bytes;
+    const int plan_ent_off = plan_hdr_off + (int)((((size_t)M * 8 + 15) & ~(size_t)15));
+    {
+        uint32_t *hdr = reinterpret_cast<uint32_t *>(img.data() + plan_hdr_off);
+        uint32_t *ent = reinterpret_cast<uint32_t *>(img.data() + plan_ent_off);
+        const int hi_shift = grouped ? 128 : 16;  // one weight slot: 8 rows / 1 row
+        uint32_t n_ent = 0;
+        for (int kc = 0; kc < M; ++kc) {
+            const int a = (32 * kc) / M, r = (32 * kc) % M;
+            const int a_row = grouped ? 4 * (OFF - 8 * (a / 8)) + 32 : 4 * (OFF - a) + 4;
+            const int res_off = copy_of_kc[kc] * a_rows * 32;
+            hdr[2 * kc] = n_ent;
+            uint32_t cnt = 0;
+            for (int j = 0; j < J; ++j) {
+                const long long kmax = (long long)M * (31 + 32 * j - a) - r;
+                const long long kmin = (long long)M * (32 * j - a) - r - 31;
+                if (!(kmax >= 0 && kmin <= ntaps - 1)) continue;
+                const int a_addr = res_off + (a_row + 128 * j) * 16;
+                const int b_addr = (front_pad + 2 * (J - 1 - j)) * 16;
+                ent[4 * n_ent + 0] = (uint32_t)a_addr >> 4;
+                ent[4 * n_ent + 1] = (uint32_t)(a_addr - hi_shift) >> 4;
+                ent[4 * n_ent + 2] = (uint32_t)b_addr >> 4;
+                ent[4 * n_ent + 3] = (uint32_t)(b_addr + 2 * rbp * 16) >> 4;
+                ++n_ent;
+                ++cnt;
+            }
+            hdr[2 * kc + 1] = cnt;
+        }
+    }
     DeviceGuard g(device);
     SRCDSP_CUDA(cudaMalloc(&d_master, master_bytes));
     SRCDSP_CUDA(cudaMemcpy(d_master, img.data(), master_bytes, cudaMemcpyHostToDevice));
@@ -662,6 +696,8 @@ int DecBank::prepare_tc()
     tc.J = J;
     tc.master = d_master;
     tc.master_bytes = (int)master_bytes;
+    tc.plan_hdr_off = plan_hdr_off;
+    tc.plan_ent_off = plan_ent_off;
     tc.a_rows = a_rows;
     tc.rbp = rbp;
     tc.front_pad = front_pad;
@@ -839,9 +875,13 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
         if (use_tma) {
             TmaExtra X{};
             X.n_raw = tma_raw;
-            X.n_conv = mixer ? TMA_MAX_CONV : 8;
+            X.n_conv = TMA_MAX_CONV;
+            X.n_groups = tma_stages >= 4 ? 2 : 1;
             if (const char *e = getenv("SRCDSP_TMA_CONV")) X.n_conv = std::max(1, std::min(atoi(e), TMA_MAX_CONV));
+            if (const char *e = getenv("SRCDSP_TMA_GROUPS")) X.n_groups = std::max(1, atoi(e));
             if (const char *e = getenv("SRCDSP_TMA_RAW")) X.n_raw = std::max(2, std::min(atoi(e), tma_raw));
+            X.n_groups = std::min(X.n_groups, std::min(X.n_raw, std::max(1, tma_stages - 1)));
+            while (X.n_conv % X.n_groups) --X.n_groups;
             X.raw_rows = 4 * ((T.J - 1 + 3) / 4) + TC_NRB;
             X.box_rows = T.J - 1 + TC_NRB;
             X.rows_full = rows_full;
@@ -859,9 +899,9 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
             if (cr != CUDA_SUCCESS) return fail(SRCDSP_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
             const int threads = 32 * (TMA_CONV_WARP0 + X.n_conv);
             if (T.debug & 32) {  // wait-cycle accounting variant; counters printed at the next launch
-                unsigned long long c[8];
+                unsigned long long c[10];
                 cudaMemcpy(c, d_error + 2, sizeof c, cudaMemcpyDeviceToHost);
-                fprintf(stderr, "tma counters (cycles summed over CTAs): conv total %llu wait_split_empty %llu wait_raw_full %llu | mma total %llu wait_full %llu wait_tempty %llu | epi total %llu wait_tfull %llu\n", c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7]);
+                fprintf(stderr, "tma counters (cycles summed over CTAs): conv total %llu wait_split_empty %llu wait_raw_full %llu fence %llu arrive %llu | mma total %llu wait_full %llu wait_tempty %llu | epi total %llu wait_tfull %llu\n", c[0], c[1], c[2], c[8], c[9], c[3], c[4], c[5], c[6], c[7]);
                 cudaMemset(d_error + 2, 0, sizeof c);
                 if (mixer)
                     dec_tma_kernel<16, true><<<tgrid, threads, tma_smem, stream>>>(T, X, map);

@@ -65,8 +65,10 @@ struct TcParams {
     int J;            // lags: 1 + ceil((Nt-1)/G)
     int tiles_per_ch;
     long long total_tiles;
-    const uint8_t *master;   // device image of the A region
+    const uint8_t *master;   // device image of the A region (+ the MMA plan behind it)
     int master_bytes;
+    int plan_hdr_off, plan_ent_off;  // byte offsets of the MMA plan inside the image: per K-step {first entry, count},
+                                     // per (K-step, lag) entry the 4 operand addresses >> 4 (see tc_mma_role)
     int a_rows;              // rows per (residue, kc) chunk  -> LBO_A = a_rows * 16
     int rbp;                 // padded rows per (plane, kc) chunk of a stage (odd) -> LBO_B = rbp * 16
     int front_pad;           // unused rows in front of every chunk: 2 * (4*ceil((J-1)/4) - (J-1))
@@ -108,9 +110,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int *er
     long long t0 = 0;
     for (uint32_t spins = 0; !done; ++spins) {
         asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
             : "=r"(done)
-            : "r"(bar), "r"(parity), "r"(20000u)  // suspend-time hint (ns): fewer wake-ups while idle
+            : "r"(bar), "r"(parity)  // no suspend-time hint: with few stages every wake-up is on the critical path
             : "memory");
         if (!done && (spins & 1023) == 1023) {
             const long long now = clock64();
@@ -330,20 +332,36 @@ __device__ __forceinline__ void tc_mma_role(const TcParams &P, const TcRole &R)
     (void)bar_full, (void)bar_empty, (void)bar_tfull, (void)bar_tempty, (void)tmem_base;
     // The whole warp walks the loop (warp-uniform control flow and operands, so descriptors
     // stay in uniform registers); one elected lane issues the MMAs and the commits.
+    //
+    // The issuing thread is a serial resource: everything address-like is precomputed on the host
+    // into the "MMA plan" that sits behind the master image in shared memory (per K-step a header
+    // {first entry, count}, per contributing lag one entry {A lo, A hi, B lo, B hi} of operand
+    // addresses >> 4, A relative to the master, B relative to the sample stage), and the plan of
+    // the next K-step is fetched before this one's barrier wait.  Per K-step that leaves: wait,
+    // fence, a handful of adds, the MMAs, the commit.
     {
         const uint32_t idesc_lo = umma_idesc_i8(1, 0, 128, 2 * TC_NRB);  // taps s8 x lo plane u8
         const uint32_t idesc_hi = umma_idesc_i8(1, 1, 128, 2 * TC_NRB);  // taps s8 x hi plane s8
         const uint32_t a_base = smem_u32(a_smem), s_base = smem_u32(stages);
-        const uint32_t lbo_a = P.a_rows * 16, lbo_b = P.rbp * 16;
-        // descriptor = constant high part | (address >> 4)
-        const uint64_t desc_a0 = umma_desc(0, lbo_a), desc_b0 = umma_desc(0, lbo_b);
-        const uint32_t hi_shift = P.grouped ? 128 : 16;  // one weight slot: 8 rows / 1 row
+        // descriptor = {high word: SBO 128 B, version 1} {low word: LBO >> 4 << 16 | address >> 4}
+        const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+        const uint32_t a_const = (a_base >> 4) + (((uint32_t)P.a_rows * 16 >> 4) << 16);
+        const uint32_t b_const = (s_base >> 4) + (((uint32_t)P.rbp * 16 >> 4) << 16);
+        const uint32_t stage16 = (uint32_t)stage_bytes >> 4;
+        const uint2 *plan_hdr = reinterpret_cast<const uint2 *>(a_smem + P.plan_hdr_off);
+        const uint4 *plan_ent = reinterpret_cast<const uint4 *>(a_smem + P.plan_ent_off);
+        const bool no_mma = P.debug & 1, no_hi = P.debug & 64;
+        auto desc = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | lo; };
         int stage = 0;
+        uint32_t sb16 = 0;  // (stage * stage_bytes) >> 4
         uint32_t phase = 0;
         uint32_t acc_phases = 0;  // bit a: parity of accumulator buffer a
         int acc = 0;
         long long m_full = 0, m_tempty = 0;
         const long long m_t0 = clock64();
+        // plan of the first K-step (the entry table is padded, so the second load is always in bounds)
+        uint2 hdr = plan_hdr[0];
+        uint4 e0 = plan_ent[hdr.x], e1 = plan_ent[hdr.x + 1];
         for (long long tile = first_tile; tile < P.total_tiles; tile += tile_step) {
             mbar_wait_acc<DBG>(bar_tempty + 8 * acc, ((acc_phases >> acc) & 1) ^ 1, P.error_flag, m_tempty);
             tc_fence_after();
@@ -352,27 +370,36 @@ __device__ __forceinline__ void tc_mma_role(const TcParams &P, const TcRole &R)
             for (int kc = 0; kc < KS; ++kc) {
                 mbar_wait_acc<DBG>(bar_full + 8 * stage, phase, P.error_flag, m_full);
                 tc_fence_after();
-                const int a_row = P.ks[kc].a_row, res_off = P.ks[kc].res_off;
-                const unsigned jmask = (P.debug & 1) ? 0u : P.ks[kc].jmask;
-                const uint32_t sb = s_base + stage * stage_bytes;
+                const uint32_t cnt = no_mma ? 0u : hdr.y;
+                const uint32_t bs = b_const + sb16;
                 if (elect_one()) {
-                    for (int j = 0; j < J; ++j) {
-                        if (!((jmask >> j) & 1)) continue;
-                        const uint32_t a_addr = a_base + res_off + (a_row + 128 * j) * 16;
-                        const uint32_t b_addr = sb + (P.front_pad + 2 * (J - 1 - j)) * 16;
-                        umma_i8(d_tmem, desc_a0 | (a_addr >> 4), desc_b0 | (b_addr >> 4), idesc_lo, accumulate);
+                    if (cnt > 0) {
+                        umma_i8(d_tmem, desc(a_const + e0.x), desc(bs + e0.z), idesc_lo, accumulate);
                         // hi byte plane: weight slot + 1  ==  master moved back by one slot
-                        umma_i8(d_tmem, desc_a0 | ((a_addr - hi_shift) >> 4), desc_b0 | ((b_addr + 2 * lbo_b) >> 4),
-                                idesc_hi, 1);
-                        accumulate = 1;
+                        if (!no_hi) umma_i8(d_tmem, desc(a_const + e0.y), desc(bs + e0.w), idesc_hi, 1);
+                    }
+                    if (cnt > 1) {
+                        umma_i8(d_tmem, desc(a_const + e1.x), desc(bs + e1.z), idesc_lo, 1);
+                        if (!no_hi) umma_i8(d_tmem, desc(a_const + e1.y), desc(bs + e1.w), idesc_hi, 1);
+                    }
+                    for (uint32_t i = 2; i < cnt; ++i) {
+                        const uint4 e = plan_ent[hdr.x + i];
+                        umma_i8(d_tmem, desc(a_const + e.x), desc(bs + e.z), idesc_lo, 1);
+                        if (!no_hi) umma_i8(d_tmem, desc(a_const + e.y), desc(bs + e.w), idesc_hi, 1);
                     }
                     tc_commit(bar_empty + 8 * stage);  // frees the stage when these MMAs have read it
                     if (kc == KS - 1) tc_commit(bar_tfull + 8 * acc);
                 }
-                accumulate |= (jmask != 0);
+                accumulate |= (cnt != 0);
                 __syncwarp();
+                // next K-step's plan: in flight while the tensor pipe works and the next barrier is awaited
+                hdr = plan_hdr[kc + 1 == KS ? 0 : kc + 1];
+                e0 = plan_ent[hdr.x];
+                e1 = plan_ent[hdr.x + 1];
+                sb16 += stage16;
                 if (++stage == NS) {
                     stage = 0;
+                    sb16 = 0;
                     phase ^= 1;
                 }
             }

@@ -12,7 +12,8 @@
 //   warps 0-3   epilogue            (tc_epilogue_role)
 //   warp  4     MMA issuer + TMEM   (tc_mma_role)
 //   warp  5     TMA issuer (one lane)
-//   warps 6..   converters: every warp takes every n_conv-th group of 4 rows of every K-step
+//   warps 6..   converters in n_groups groups: a group takes every n_groups-th K-step, each of its
+//               warps every (n_conv / n_groups)-th group of 4 rows of it
 //
 // Edges (rare): rows in front of the block come from the carried history and the ragged last
 // row-block is not part of the TMA tensor; the TMA box zero-fills both and the converters patch
@@ -33,6 +34,7 @@ constexpr int TMA_MAX_RAW = 12;
 struct TmaExtra {
     int n_raw;        // raw stages
     int n_conv;       // converter warps
+    int n_groups;     // converter groups (n_conv % n_groups == 0, n_groups <= min(n_raw, n_stages - 1))
     int raw_rows;     // rows of a raw stage: 4 * ceil((J-1)/4) + 128 (the box lands at row raw_rows - box_rows)
     int box_rows;     // J - 1 + 128
     long long rows_full;  // floor(n_in / G): row-blocks that are part of the TMA tensor
@@ -101,12 +103,12 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1)
     fence_async_smem();
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) {
-            mbar_init(bar_full + 8 * s, NCW);  // one arrival per converter warp
+            mbar_init(bar_full + 8 * s, NCW / X.n_groups);  // one arrival per converter warp of the K-step's group
             mbar_init(bar_empty + 8 * s, 1);   // tcgen05.commit
         }
         for (int s = 0; s < NR; ++s) {
             mbar_init(bar_rfull + 8 * s, 1);   // expect_tx arrival + the box's bytes
-            mbar_init(bar_rempty + 8 * s, NCW);
+            mbar_init(bar_rempty + 8 * s, NCW / X.n_groups);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(bar_tfull + 8 * a, 1);
@@ -132,7 +134,13 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1)
         // =====================================================================================
         // converters: raw stage (rows of 32 interleaved samples) -> byte-plane stage
         // =====================================================================================
+        // The warps form n_groups groups; group g converts K-steps g, g + n_groups, ... of the CTA's
+        // flattened (tile, K-step) sequence, its W warps share the row groups of such a K-step.  A warp's
+        // per-K-step overhead (two barrier waits, proxy fence, two arrivals) is then paid once per
+        // n_groups K-steps, and the groups' K-steps overlap in time.
         const int cw = warp - TMA_CONV_WARP0;
+        const int NG = X.n_groups, W = NCW / NG;
+        const int g = cw / W, wi = cw - g * W;
         const int piece = lane & 7, grp = lane >> 3;
         const int chunk = P.rbp * 16;
         const int halo_rows4 = X.raw_rows - TC_NRB;   // 4 * ceil((J-1)/4)
@@ -142,102 +150,137 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1)
         const int src_lane = grp * 128 + piece * 16;
         const int dst_lane = (piece >> 2) * chunk + grp * 32 + (piece & 3) * 4;
         const int hi_off = 2 * chunk;
-        int rs = 0, ss = 0;
+        constexpr int QB = 5;  // row groups in flight per warp (registers): covers 33..36 row groups with 8 warps
+        int rs = g % NR, ss = g % NS;
         uint32_t rpar = 0, spar = 1;  // first wait on a fresh "empty" barrier passes
-        int rot = cw;                 // rotates the warp -> row-group assignment so that the odd group averages out
-        long long w_wait_raw = 0, w_wait_split = 0;
+        int rot = wi;                 // rotates the warp -> row-group assignment so that the odd group averages out
+        long long w_wait_raw = 0, w_wait_split = 0, w_fence = 0, w_arrive = 0;
         const long long w_t0 = clock64();
-        for (long long tile = first_tile; tile < P.total_tiles; tile += tile_step) {
-            const unsigned tl = (unsigned)tile;
-            const unsigned ch = tl / (unsigned)P.tiles_per_ch;
-            const unsigned tt = tl - ch * (unsigned)P.tiles_per_ch;
-            const uint32_t *x = P.in + (size_t)ch * P.in_stride;
-            const uint32_t *hist = P.hist_in + (size_t)ch * P.H;
-            const long long tile0 = (long long)tt * TC_NRB * (long long)P.G;  // sample of (row-block 0, K-step 0)
-            // rows the TMA tensor does not hold: history in front of the block, everything from the ragged row-block on
-            const bool edge = (tt == 0 && J > 1) || ((long long)(tt + 1) * TC_NRB > X.rows_full);
-            unsigned ph0 = 0, fr = 0, dph = 0;
-            if (MIX) {
-                ph0 = (unsigned)P.phi[ch];
-                fr = (unsigned)P.freq[ch];
-                dph = (((unsigned)(4 * NCW * P.G) & P.mix_mask) * fr) & P.mix_mask;  // phase step between a warp's row groups
+        long long tile = first_tile, cur_tile = -1, tile0 = 0;
+        int kc = g;
+        while (kc >= KS && tile < P.total_tiles) {
+            kc -= KS;
+            tile += tile_step;
+        }
+        const uint32_t *x = nullptr, *hist = nullptr;
+        unsigned tt = 0, ph0 = 0, fr = 0, dph = 0;
+        bool edge = false;
+        while (tile < P.total_tiles) {
+            if (tile != cur_tile) {  // one division per tile
+                const unsigned tl = (unsigned)tile;
+                const unsigned ch = tl / (unsigned)P.tiles_per_ch;
+                tt = tl - ch * (unsigned)P.tiles_per_ch;
+                x = P.in + (size_t)ch * P.in_stride;
+                hist = P.hist_in + (size_t)ch * P.H;
+                tile0 = (long long)tt * TC_NRB * (long long)P.G;  // sample of (row-block 0, K-step 0)
+                // rows the TMA tensor does not hold: history in front of the block, everything from the ragged row-block on
+                edge = (tt == 0 && J > 1) || ((long long)(tt + 1) * TC_NRB > X.rows_full);
+                if (MIX) {
+                    ph0 = (unsigned)P.phi[ch];
+                    fr = (unsigned)P.freq[ch];
+                    dph = (((unsigned)(4 * W * P.G) & P.mix_mask) * fr) & P.mix_mask;  // phase step between a warp's row groups
+                }
+                cur_tile = tile;
             }
-            for (int kc = 0; kc < KS; ++kc) {
-                mbar_wait_acc<DBG>(bar_rfull + 8 * rs, rpar, P.error_flag, w_wait_raw);
-                mbar_wait_acc<DBG>(bar_empty + 8 * ss, spar, P.error_flag, w_wait_split);
-                const uint8_t *src = raw + rs * raw_bytes + src_lane;
-                uint8_t *dst = stages + ss * stage_bytes + dst_lane;
-                // sample index of (raw row grp, this lane's piece) of this K-step
-                const long long n_row0 = tile0 + (long long)(grp - halo_rows4) * P.G + 32 * kc + 4 * piece;
-                if (!edge) {
+            mbar_wait_acc<DBG>(bar_rfull + 8 * rs, rpar, P.error_flag, w_wait_raw);
+            mbar_wait_acc<DBG>(bar_empty + 8 * ss, spar, P.error_flag, w_wait_split);
+            const uint8_t *src = raw + rs * raw_bytes + src_lane;
+            uint8_t *dst = stages + ss * stage_bytes + dst_lane;
+            // sample index of (raw row grp, this lane's piece) of this K-step
+            const long long n_row0 = tile0 + (long long)(grp - halo_rows4) * P.G + 32 * kc + 4 * piece;
+            if (P.debug & 8) {
+                // timing experiment: barriers only
+            } else if (!edge) {
+                for (int q0 = rot; q0 < NQ; q0 += QB * W) {
+                    // all loads of the batch first: one shared-memory latency per batch
+                    uint4 v[QB];
+#pragma unroll
+                    for (int i = 0; i < QB; ++i)
+                        if (q0 + i * W < NQ) v[i] = *reinterpret_cast<const uint4 *>(src + (q0 + i * W) * 512);
                     unsigned ph = 0;
-                    if (MIX) ph = (ph0 + ((unsigned)(n_row0 + (long long)4 * rot * P.G) & P.mix_mask) * fr) & P.mix_mask;
-                    int q = rot;
-                    // two row groups per iteration: independent LDS / PRMT / STS chains
-                    for (; q + NCW < NQ; q += 2 * NCW) {
-                        const uint4 v0 = *reinterpret_cast<const uint4 *>(src + q * 512);
-                        const uint4 v1 = *reinterpret_cast<const uint4 *>(src + (q + NCW) * 512);
-                        tma_convert_store<MIX>(v0, dst + q * 128, hi_off, tab_smem, ph, fr, P.mix_mask);
-                        tma_convert_store<MIX>(v1, dst + (q + NCW) * 128, hi_off, tab_smem, (ph + dph) & P.mix_mask, fr, P.mix_mask);
-                        if (MIX) ph = (ph + 2 * dph) & P.mix_mask;
-                    }
-                    if (q < NQ) {
-                        const uint4 v0 = *reinterpret_cast<const uint4 *>(src + q * 512);
-                        tma_convert_store<MIX>(v0, dst + q * 128, hi_off, tab_smem, ph, fr, P.mix_mask);
-                    }
-                } else {
-                    for (int q = rot; q < NQ; q += NCW) {
-                        const int rb = 4 * q + grp - halo_rows4;
-                        const long long n = n_row0 + (long long)4 * q * P.G;
-                        uint4 v;
-                        if (rb < -(J - 1)) {
-                            v = make_uint4(0, 0, 0, 0);  // padding rows in front of the halo: never read by an MMA
-                        } else if (n < 0 || (long long)(tt * TC_NRB) + rb >= X.rows_full) {
-                            // carried history (already mixed) / ragged end: straight from global memory
-                            if (MIX) {
-                                v.x = tc_sample_mix(P, x, hist, n, ph0, fr);
-                                v.y = tc_sample_mix(P, x, hist, n + 1, ph0, fr);
-                                v.z = tc_sample_mix(P, x, hist, n + 2, ph0, fr);
-                                v.w = tc_sample_mix(P, x, hist, n + 3, ph0, fr);
-                            } else {
-                                v.x = tc_sample(x, hist, P.H, P.n_in, n);
-                                v.y = tc_sample(x, hist, P.H, P.n_in, n + 1);
-                                v.z = tc_sample(x, hist, P.H, P.n_in, n + 2);
-                                v.w = tc_sample(x, hist, P.H, P.n_in, n + 3);
-                            }
-                            tma_convert_store<false>(v, dst + q * 128, hi_off, tab_smem, 0, 0, 0);
-                            continue;
-                        } else {
-                            v = *reinterpret_cast<const uint4 *>(src + q * 512);
+                    if (MIX) ph = (ph0 + ((unsigned)(n_row0 + (long long)4 * q0 * P.G) & P.mix_mask) * fr) & P.mix_mask;
+#pragma unroll
+                    for (int i = 0; i < QB; ++i) {
+                        if (q0 + i * W < NQ) {
+                            tma_convert_store<MIX>(v[i], dst + (q0 + i * W) * 128, hi_off, tab_smem, ph, fr, P.mix_mask);
+                            if (MIX) ph = (ph + dph) & P.mix_mask;
                         }
-                        const unsigned ph = MIX ? (ph0 + ((unsigned)n & P.mix_mask) * fr) & P.mix_mask : 0u;
-                        tma_convert_store<MIX>(v, dst + q * 128, hi_off, tab_smem, ph, fr, P.mix_mask);
                     }
                 }
-                // the MMA reads shared memory through the async proxy: fence this warp's stores, then
-                // one arrival per warp on both rings
-                fence_async_smem();
+            } else {
+                for (int q = rot; q < NQ; q += W) {
+                    const int rb = 4 * q + grp - halo_rows4;
+                    const long long n = n_row0 + (long long)4 * q * P.G;
+                    uint4 v;
+                    if (rb < -(J - 1)) {
+                        v = make_uint4(0, 0, 0, 0);  // padding rows in front of the halo: never read by an MMA
+                    } else if (n < 0 || (long long)(tt * TC_NRB) + rb >= X.rows_full) {
+                        // carried history (already mixed) / ragged end: straight from global memory
+                        if (MIX) {
+                            v.x = tc_sample_mix(P, x, hist, n, ph0, fr);
+                            v.y = tc_sample_mix(P, x, hist, n + 1, ph0, fr);
+                            v.z = tc_sample_mix(P, x, hist, n + 2, ph0, fr);
+                            v.w = tc_sample_mix(P, x, hist, n + 3, ph0, fr);
+                        } else {
+                            v.x = tc_sample(x, hist, P.H, P.n_in, n);
+                            v.y = tc_sample(x, hist, P.H, P.n_in, n + 1);
+                            v.z = tc_sample(x, hist, P.H, P.n_in, n + 2);
+                            v.w = tc_sample(x, hist, P.H, P.n_in, n + 3);
+                        }
+                        tma_convert_store<false>(v, dst + q * 128, hi_off, tab_smem, 0, 0, 0);
+                        continue;
+                    } else {
+                        v = *reinterpret_cast<const uint4 *>(src + q * 512);
+                    }
+                    const unsigned ph = MIX ? (ph0 + ((unsigned)n & P.mix_mask) * fr) & P.mix_mask : 0u;
+                    tma_convert_store<MIX>(v, dst + q * 128, hi_off, tab_smem, ph, fr, P.mix_mask);
+                }
+            }
+            // the MMA reads shared memory through the async proxy: fence this warp's stores, then
+            // one arrival per warp on both rings
+            if (DBG & 16) {
+                const long long f0 = clock64();
+                if (!(P.debug & 128)) fence_async_smem();
+                const long long f1 = clock64();
                 __syncwarp();
                 if (lane == 0) {
                     mbar_arrive(bar_full + 8 * ss);
                     mbar_arrive(bar_rempty + 8 * rs);
                 }
-                if (++rs == NR) {
-                    rs = 0;
-                    rpar ^= 1;
+                w_fence += f1 - f0;
+                w_arrive += clock64() - f1;
+            } else {
+                if (!(P.debug & 128)) fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(bar_full + 8 * ss);
+                    mbar_arrive(bar_rempty + 8 * rs);
                 }
-                if (++ss == NS) {
-                    ss = 0;
-                    spar ^= 1;
-                }
-                if (++rot == NCW) rot = 0;
             }
+            rs += NG;
+            if (rs >= NR) {
+                rs -= NR;
+                rpar ^= 1;
+            }
+            ss += NG;
+            if (ss >= NS) {
+                ss -= NS;
+                spar ^= 1;
+            }
+            kc += NG;
+            while (kc >= KS) {
+                kc -= KS;
+                tile += tile_step;
+            }
+            if (++rot == W) rot = 0;
         }
         if ((DBG & 16) && lane == 0) {
             unsigned long long *cnt = reinterpret_cast<unsigned long long *>(P.error_flag + 2);
             atomicAdd(cnt + 0, (unsigned long long)(clock64() - w_t0));  // converter total
             atomicAdd(cnt + 1, (unsigned long long)w_wait_split);         // waiting for a free byte-plane stage
             atomicAdd(cnt + 2, (unsigned long long)w_wait_raw);           // waiting for a raw stage (TMA / HBM)
+            atomicAdd(cnt + 8, (unsigned long long)w_fence);              // fence.proxy.async
+            atomicAdd(cnt + 9, (unsigned long long)w_arrive);             // syncwarp + arrivals
         }
     } else if (warp == 5) {
         // =====================================================================================
