@@ -48,6 +48,7 @@ WORKLOADS = {
                  desc="cfg4: interpolate-by-8 64-tap FIR, 256 ch x 1Mi input samples (8Mi out) per step"),
     "cfg5": dict(kind="dec", channels=1, n=1 << 29, M=4, ntaps=1023, mix=False,
                  desc="cfg5 slice: decimate-by-4 1023-tap FIR, one stream slice of 512Mi samples per GPU"),
+    "mid": dict(kind="dec", channels=64, n=1 << 22, M=16, ntaps=255, mix=False, desc="mid: 64 ch x 4Mi, /16, 255 taps"),
     "smoke": dict(kind="dec", channels=8, n=1 << 18, M=16, ntaps=255, mix=False, desc="smoke: 8 ch x 256Ki"),
 }
 

@@ -423,7 +423,9 @@ struct DecBank : Bank {
     const char *tc_why = "no coefficients";
     TcParams tc{};
     uint8_t *d_master = nullptr;
-    int *d_error = nullptr;
+    int *d_error = nullptr;  // wait-cycle counters of the timing variants (device)
+    int *h_diag = nullptr;   // mapped host memory: record of a timed-out barrier wait (survives the trap)
+    int *d_diag = nullptr;
     size_t tc_fixed = 0;  // master + barriers
     int sm_count = 148;
 
@@ -443,15 +445,17 @@ struct DecBank : Bank {
 
     // shared-memory plan of the TMA-fed variant: byte-plane stages only decouple the converters from
     // the MMAs (3 are enough), everything else goes to the raw ring = the bytes in flight from HBM
-    int tma_layout(int table_bytes, int *n_raw, int *n_stages, size_t *smem) const
+    int tma_layout(int table_bytes, int groups, int *n_raw, int *n_stages, size_t *smem) const
     {
         const size_t avail = (size_t)226 * 1024;
         const size_t split = (size_t)64 * tc.rbp;
         const size_t rawb = (size_t)(4 * ((tc.J - 1 + 3) / 4) + TC_NRB) * 128;
         if (tc_fixed + (size_t)table_bytes + 2 * split + 2 * rawb > avail) return SRCDSP_E_SIZE;
-        // byte-plane stages: one per converter group being filled + 2 for the MMAs; the rest of the
+        // byte-plane stages: one per converter group being filled + 1 for the MMAs; the rest of the
         // shared memory is the raw ring = the bytes in flight from HBM (at least 4 stages wanted)
-        int ns = 4;
+        int ns = groups + 1;
+        if (const char *e = getenv("SRCDSP_TMA_STAGES"))
+            if (atoi(e) > 0) ns = std::max(2, std::min(atoi(e), TC_MAX_STAGES));
         while (ns > 2 && tc_fixed + (size_t)table_bytes + ns * split + 4 * rawb > avail) --ns;
         int nr = (int)((avail - tc_fixed - (size_t)table_bytes - ns * split) / rawb);
         if (nr > 8) nr = 8;  // more bytes in flight than ~128 KB per SM lowers the HBM rate (tools/tmabench.cu)
@@ -562,6 +566,7 @@ struct DecBank : Bank {
         if (d_hist[1]) cudaFree(d_hist[1]);
         if (d_master) cudaFree(d_master);
         if (d_error) cudaFree(d_error);
+        if (h_diag) cudaFreeHost(h_diag);
     }
 };
 
@@ -687,8 +692,11 @@ int DecBank::prepare_tc()
     SRCDSP_CUDA(cudaMalloc(&d_master, master_bytes));
     SRCDSP_CUDA(cudaMemcpy(d_master, img.data(), master_bytes, cudaMemcpyHostToDevice));
     if (!d_error) {
-        SRCDSP_CUDA(cudaMalloc(&d_error, 128));  // [0] error flag, [2..] wait-cycle counters of the timing variants
+        SRCDSP_CUDA(cudaMalloc(&d_error, 128));
         SRCDSP_CUDA(cudaMemset(d_error, 0, 128));
+        SRCDSP_CUDA(cudaHostAlloc(&h_diag, 64, cudaHostAllocMapped));
+        memset(h_diag, 0, 64);
+        SRCDSP_CUDA(cudaHostGetDevicePointer(&d_diag, h_diag, 0));
     }
     tc = TcParams{};
     tc.M = M;
@@ -702,7 +710,8 @@ int DecBank::prepare_tc()
     tc.rbp = rbp;
     tc.front_pad = front_pad;
     tc.grouped = grouped;
-    tc.error_flag = d_error;
+    tc.error_flag = d_diag;
+    tc.counters = d_error;
     for (int kc = 0; kc < M; ++kc) {
         const int a = (32 * kc) / M, r = (32 * kc) % M;
         TcKstep &ks = tc.ks[kc];
@@ -726,11 +735,15 @@ int DecBank::prepare_tc()
     SRCDSP_CUDA(cudaFuncSetAttribute(dec_tc_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     SRCDSP_CUDA(cudaFuncSetAttribute(dec_tc_kernel<10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     SRCDSP_CUDA(cudaFuncSetAttribute(dec_tc_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    SRCDSP_CUDA(cudaFuncSetAttribute(dec_tma_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    SRCDSP_CUDA(cudaFuncSetAttribute(dec_tma_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    SRCDSP_CUDA(cudaFuncSetAttribute(dec_tma_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    SRCDSP_CUDA(cudaFuncSetAttribute(dec_tma_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    SRCDSP_CUDA(cudaFuncSetAttribute(dec_tma_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+#define SRCDSP_TMA_ATTR(D, MX)                                                                                             \
+    SRCDSP_CUDA(cudaFuncSetAttribute(dec_tma_kernel<D, MX, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));    \
+    SRCDSP_CUDA(cudaFuncSetAttribute(dec_tma_kernel<D, MX, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))
+    SRCDSP_TMA_ATTR(0, false);
+    SRCDSP_TMA_ATTR(0, true);
+    SRCDSP_TMA_ATTR(2, false);
+    SRCDSP_TMA_ATTR(16, false);
+    SRCDSP_TMA_ATTR(16, true);
+#undef SRCDSP_TMA_ATTR
     tc_ok = true;
     tc_why = "";
     return SRCDSP_OK;
@@ -776,6 +789,9 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
                          MixerBank *mixer)
 {
     if (ntaps == 0) return fail(SRCDSP_E_STATE, "decimator has no coefficients (call srcdsp_dec_set_coeffs)");
+    if (h_diag && h_diag[0])
+        return fail(SRCDSP_E_CUDA, "a tensor-core kernel timed out waiting on mbarrier 0x%x (parity %d, CTA %d, thread %d) and trapped",
+                    h_diag[1], h_diag[2], h_diag[3], h_diag[4]);
     if (n_in % (size_t)M != 0)
         return fail(SRCDSP_E_SIZE, "n_in (%zu) must be a multiple of M (%d) [dsptl_dnsampling_filters.h:181]", n_in, M);
     if (n_in == 0) return SRCDSP_OK;
@@ -818,8 +834,16 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
     const long long rows_full = (long long)(n_in / (size_t)(32 * M));
     int tma_raw = 0, tma_stages = 0;
     size_t tma_smem = 0;
-    bool use_tma = use_tc && kernel_kind != 3 && P.vec_in && rows_full >= 1 && rows_full < 0x7fffffffll && tensor_map_encoder() &&
-                   !getenv("SRCDSP_NO_TMA") && tma_layout(tbl_bytes, &tma_raw, &tma_stages, &tma_smem) == SRCDSP_OK;
+    const bool have_map = use_tc && P.vec_in && rows_full >= 1 && rows_full < 0x7fffffffll && tensor_map_encoder() != nullptr;
+    // converter warps: groups of W warps, one K-step per group at a time
+    // defaults from sweeps on cfg2 / ddc16 (256 ch x 16 Mi, /16, 255 taps): W = 4; plain decimator 2 groups + 3 byte-plane
+    // stages (the raw ring gets the rest), fused mixer 3 groups + 4 stages (more ALU work per K-step)
+    int tma_w = 4, tma_groups = mixer ? 3 : 2;
+    if (const char *e = getenv("SRCDSP_TMA_W")) tma_w = atoi(e) == 8 ? 8 : 4;
+    if (const char *e = getenv("SRCDSP_TMA_GROUPS")) tma_groups = std::max(1, atoi(e));
+    tma_groups = std::min(tma_groups, TMA_MAX_CONV / tma_w);
+    bool use_tma = have_map && kernel_kind != 3 && !getenv("SRCDSP_NO_TMA") &&
+                   tma_layout(tbl_bytes, tma_groups, &tma_raw, &tma_stages, &tma_smem) == SRCDSP_OK;
     if (use_tc && !use_tma && tc_layout(tbl_bytes, &tc_stages, &tc_smem) != SRCDSP_OK)
         use_tc = false, why = "sine table + Toeplitz master + stages exceed 227 KB of shared memory";
     if (kernel_kind >= 2 && !use_tc)
@@ -872,62 +896,78 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
                 T.kc_stride = 32 * TC_NRB;
             }
         }
-        if (use_tma) {
-            TmaExtra X{};
-            X.n_raw = tma_raw;
-            X.n_conv = TMA_MAX_CONV;
-            X.n_groups = tma_stages >= 4 ? 2 : 1;
-            if (const char *e = getenv("SRCDSP_TMA_CONV")) X.n_conv = std::max(1, std::min(atoi(e), TMA_MAX_CONV));
-            if (const char *e = getenv("SRCDSP_TMA_GROUPS")) X.n_groups = std::max(1, atoi(e));
-            if (const char *e = getenv("SRCDSP_TMA_RAW")) X.n_raw = std::max(2, std::min(atoi(e), tma_raw));
-            X.n_groups = std::min(X.n_groups, std::min(X.n_raw, std::max(1, tma_stages - 1)));
-            while (X.n_conv % X.n_groups) --X.n_groups;
-            X.raw_rows = 4 * ((T.J - 1 + 3) / 4) + TC_NRB;
-            X.box_rows = T.J - 1 + TC_NRB;
-            X.rows_full = rows_full;
-            T.n_stages = tma_stages;
-            // the input as a tensor [C][rows_full][G] of 32-bit words (one complex int16 sample each)
-            CUtensorMap map;
+        // the input as a tensor [C][rows_full][G] of 32-bit words (one complex int16 sample each); a box is one
+        // K-step of one tile: 32 samples x (J-1 halo + 128) row-blocks x 1 channel
+        CUtensorMap map;
+        memset(&map, 0, sizeof map);
+        if (have_map) {
             const cuuint64_t gdim[3] = {(cuuint64_t)T.G, (cuuint64_t)rows_full, (cuuint64_t)C};
             const cuuint64_t gstr[2] = {(cuuint64_t)T.G * 4,
                                         C > 1 ? (cuuint64_t)in_stride * 4 : (cuuint64_t)rows_full * T.G * 4};
-            const cuuint32_t box[3] = {32, (cuuint32_t)X.box_rows, 1};
+            const cuuint32_t box[3] = {32, (cuuint32_t)(T.J - 1 + TC_NRB), 1};
             const cuuint32_t estr[3] = {1, 1, 1};
             const CUresult cr = tensor_map_encoder()(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)in, gdim, gstr, box, estr,
                                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (cr != CUDA_SUCCESS) return fail(SRCDSP_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
+            if (!use_tma) {  // register-staged producers + TMA prefetch into L2
+                T.pf_dist = T.n_stages + 12;
+                if (const char *e = getenv("SRCDSP_PF_DIST")) T.pf_dist = std::max(0, atoi(e));
+            }
+        }
+        if (use_tma) {
+            TmaExtra X{};
+            X.n_raw = tma_raw;
+            if (const char *e = getenv("SRCDSP_TMA_RAW")) X.n_raw = std::max(2, std::min(atoi(e), tma_raw));
+            tma_groups = std::max(1, std::min(tma_groups, std::min(X.n_raw, tma_stages - 1)));
+            // A raw stage must always be converted by the same group: TMA boxes complete out of order, so a
+            // different group could reach the stage's next use before the previous use has even landed
+            // and pass its parity wait one phase early.  n_raw = a multiple of the group count.
+            X.n_raw -= X.n_raw % tma_groups;
+            X.n_conv = tma_w * tma_groups;
+            X.raw_rows = 4 * ((T.J - 1 + 3) / 4) + TC_NRB;
+            X.box_rows = T.J - 1 + TC_NRB;
+            X.rows_full = rows_full;
+            T.n_stages = tma_stages;
             const int threads = 32 * (TMA_CONV_WARP0 + X.n_conv);
             if (T.debug & 32) {  // wait-cycle accounting variant; counters printed at the next launch
                 unsigned long long c[10];
-                cudaMemcpy(c, d_error + 2, sizeof c, cudaMemcpyDeviceToHost);
+                cudaMemcpy(c, d_error, sizeof c, cudaMemcpyDeviceToHost);
                 fprintf(stderr, "tma counters (cycles summed over CTAs): conv total %llu wait_split_empty %llu wait_raw_full %llu fence %llu arrive %llu | mma total %llu wait_full %llu wait_tempty %llu | epi total %llu wait_tfull %llu\n", c[0], c[1], c[2], c[8], c[9], c[3], c[4], c[5], c[6], c[7]);
-                cudaMemset(d_error + 2, 0, sizeof c);
+                cudaMemset(d_error, 0, sizeof c);
+#define SRCDSP_TMA_LAUNCH(D, MX)                                                         \
+    do {                                                                                 \
+        if (tma_w == 8)                                                                  \
+            dec_tma_kernel<D, MX, 8><<<tgrid, threads, tma_smem, stream>>>(T, X, map);   \
+        else                                                                             \
+            dec_tma_kernel<D, MX, 4><<<tgrid, threads, tma_smem, stream>>>(T, X, map);   \
+    } while (0)
                 if (mixer)
-                    dec_tma_kernel<16, true><<<tgrid, threads, tma_smem, stream>>>(T, X, map);
+                    SRCDSP_TMA_LAUNCH(16, true);
                 else
-                    dec_tma_kernel<16, false><<<tgrid, threads, tma_smem, stream>>>(T, X, map);
+                    SRCDSP_TMA_LAUNCH(16, false);
             } else if (mixer) {
-                dec_tma_kernel<0, true><<<tgrid, threads, tma_smem, stream>>>(T, X, map);
+                SRCDSP_TMA_LAUNCH(0, true);
             } else if (T.debug & 2) {
-                dec_tma_kernel<2, false><<<tgrid, threads, tma_smem, stream>>>(T, X, map);
+                SRCDSP_TMA_LAUNCH(2, false);
             } else {
-                dec_tma_kernel<0, false><<<tgrid, threads, tma_smem, stream>>>(T, X, map);
+                SRCDSP_TMA_LAUNCH(0, false);
             }
+#undef SRCDSP_TMA_LAUNCH
         } else if (mixer) {
-            dec_tc_kernel<0, true><<<tgrid, TC_THREADS, tc_smem, stream>>>(T);
+            dec_tc_kernel<0, true><<<tgrid, TC_THREADS, tc_smem, stream>>>(T, map);
         } else if (T.debug & 32) {  // wait-cycle accounting variant; counters printed at the next launch
             unsigned long long c[8];
-            cudaMemcpy(c, d_error + 2, sizeof c, cudaMemcpyDeviceToHost);
+            cudaMemcpy(c, d_error, sizeof c, cudaMemcpyDeviceToHost);
             fprintf(stderr, "tc counters (cycles summed over CTAs): prod total %llu wait_empty %llu fence %llu | mma total %llu wait_full %llu wait_tempty %llu | epi total %llu wait_tfull %llu\n", c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7]);
-            cudaMemset(d_error + 2, 0, sizeof c);
-            dec_tc_kernel<16, false><<<tgrid, TC_THREADS, tc_smem, stream>>>(T);
+            cudaMemset(d_error, 0, sizeof c);
+            dec_tc_kernel<16, false><<<tgrid, TC_THREADS, tc_smem, stream>>>(T, map);
         } else {
             switch (T.debug & 10) {  // 2 / 8: timing-experiment instantiations (wrong results)
-            case 2: dec_tc_kernel<2, false><<<tgrid, TC_THREADS, tc_smem, stream>>>(T); break;
-            case 8: dec_tc_kernel<8, false><<<tgrid, TC_THREADS, tc_smem, stream>>>(T); break;
-            case 10: dec_tc_kernel<10, false><<<tgrid, TC_THREADS, tc_smem, stream>>>(T); break;
-            default: dec_tc_kernel<0, false><<<tgrid, TC_THREADS, tc_smem, stream>>>(T); break;
+            case 2: dec_tc_kernel<2, false><<<tgrid, TC_THREADS, tc_smem, stream>>>(T, map); break;
+            case 8: dec_tc_kernel<8, false><<<tgrid, TC_THREADS, tc_smem, stream>>>(T, map); break;
+            case 10: dec_tc_kernel<10, false><<<tgrid, TC_THREADS, tc_smem, stream>>>(T, map); break;
+            default: dec_tc_kernel<0, false><<<tgrid, TC_THREADS, tc_smem, stream>>>(T, map); break;
             }
         }
         SRCDSP_LAUNCH_CHECK();

@@ -75,6 +75,17 @@ __device__ __forceinline__ uint32_t scale_pack(int re, int im, unsigned shift)
     return pack_iq(re, im);
 }
 
+// limitScale16 of a complex value with the packed saturate: cvt.pack.sat clamps each half to
+// [-32768, 32767], the per-half signed max with -32767 restores the symmetric clamp (dsp_complex.cpp:63-73)
+__device__ __forceinline__ uint32_t scale_pack_sym_sat(int re, int im, unsigned shift)
+{
+    re >>= shift;
+    im >>= shift;
+    uint32_t p;
+    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(p) : "r"(im), "r"(re));  // {hi = sat(im), lo = sat(re)}
+    return __vmaxs2(p, 0x80018001u);
+}
+
 // One NCO mix: mixers.h:175-176.  cs = packed (cos, sin) = (T[(phi + N/4) % N], T[phi]).
 __device__ __forceinline__ uint32_t mix_sample(uint32_t x, uint32_t cs)
 {

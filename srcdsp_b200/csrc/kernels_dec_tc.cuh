@@ -33,6 +33,8 @@
 //              line, two batches of 8 loads in flight per lane) -> PRMT byte-plane split -> STS.32
 #pragma once
 
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace srcdsp {
@@ -43,9 +45,10 @@ constexpr int TC_NPW = 16;               // producer warps: HBM streaming scales
 constexpr int TC_SPLIT = 2;              // warps sharing one K-step (half of the row-blocks each)
 constexpr int TC_OWNERS = TC_NPW / TC_SPLIT;  // K-steps being staged concurrently
 constexpr int TC_PROD_WARP0 = 5;         // first producer warp
-constexpr int TC_THREADS = 32 * (TC_PROD_WARP0 + TC_NPW);
+constexpr int TC_PF_WARP = TC_PROD_WARP0 + TC_NPW;  // L2 prefetch issuer (one lane)
+constexpr int TC_THREADS = 32 * (TC_PF_WARP + 1);
 constexpr int TC_MAX_STAGES = 12;         // stage ring is decoupled from the producer warps: step gs -> stage gs % n_stages
-constexpr int TC_BATCH = 8;              // 16-byte loads per lane per batch (4 row-blocks per iteration)
+constexpr int TC_BATCH = 4;              // 16-byte loads per lane per batch (4 row-blocks per iteration); two batches in flight
 constexpr int TC_MAX_KSTEPS = 64;        // M <= 64
 constexpr int TC_MAX_J = 16;
 
@@ -79,13 +82,15 @@ struct TcParams {
     int H;
     unsigned shift;
     int vec_in;
-    int *error_flag;
+    int *error_flag;         // mapped host memory: [0] set by a timed-out barrier wait, [1..4] which one
+    int *counters;           // device memory: wait-cycle counters of the timing variants
     // fused NCO mix (MIX instantiation): packed (cos, sin) table of n_table = mix_mask + 1 entries (power of two)
     const uint32_t *cs_table;
     const int *phi, *freq;   // [C] phase at sample 0 of this step, frequency
     unsigned mix_mask;
     int table_bytes;         // bytes of the shared-memory copy of the table (0 without MIX)
     int rb_stride, kc_stride;  // samples between row-blocks / K-steps (G and 32; timing experiments permute them)
+    int pf_dist;  // dec_tc_kernel: K-steps the L2 prefetcher runs ahead of the MMAs (0: no prefetch, no tensor map)
     int debug;  // timing experiments only (results become wrong): 1 = skip the MMAs, 4 = skip the epilogue math
     TcKstep ks[TC_MAX_KSTEPS];
 };
@@ -103,25 +108,41 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Bounded spin: a protocol bug must surface as an error, never as a hung GPU.
+// Bounded wait: a protocol bug must surface as an error, never as a hung GPU.  The loop is two
+// instructions while the phase is incomplete (try_wait suspends the thread for up to the hint, so
+// waiting warps leave the issue slots to the working ones); 2^24 failed attempts (>= 0.3 s even if
+// every attempt returned at once) raise the error flag and trap.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int *error_flag)
 {
-    uint32_t done = 0;
-    long long t0 = 0;
-    for (uint32_t spins = 0; !done; ++spins) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)  // no suspend-time hint: with few stages every wake-up is on the critical path
-            : "memory");
-        if (!done && (spins & 1023) == 1023) {
-            const long long now = clock64();
-            if (t0 == 0) t0 = now;
-            if (now - t0 > 4000000000ll) {  // ~2 s
-                if (error_flag) atomicExch(error_flag, 1);
-                __trap();
-            }
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .u32 n;\n\t"
+        "mov.u32 n, 0;\n\t"
+        "mov.u32 %0, 1;\n"
+        "MBAR_WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "@p bra MBAR_WAIT_DONE;\n\t"
+        "add.u32 n, n, 1;\n\t"
+        "setp.lt.u32 p, n, 0x1000000;\n\t"
+        "@p bra MBAR_WAIT_LOOP;\n\t"
+        "mov.u32 %0, 0;\n"
+        "MBAR_WAIT_DONE:\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(1000u)  // suspend-time hint (ns)
+        : "memory");
+    if (!ok) {
+        // error_flag points into mapped host memory: the record survives the trap that kills the context
+        if (error_flag && atomicExch(error_flag, 1) == 0) {
+            error_flag[1] = (int)bar;
+            error_flag[2] = (int)parity;
+            error_flag[3] = (int)blockIdx.x;
+            error_flag[4] = (int)threadIdx.x;
+            __threadfence_system();
         }
+        __trap();
     }
 }
 // DBG & 16: per-role wait-cycle accounting into P.error_flag[1..] (timing experiments)
@@ -317,6 +338,7 @@ struct TcRole {
     int stage_bytes, NS, J, KS, warp, lane;
     uint32_t bar_full, bar_empty, bar_tfull, bar_tempty, tmem_base;
     long long first_tile, tile_step;
+    uint32_t progress;  // != 0: shared-memory word that receives the number of K-steps issued so far (L2 prefetch pacing)
 };
 
 // MMA issuer (one warp, one elected lane issues)
@@ -358,6 +380,7 @@ __device__ __forceinline__ void tc_mma_role(const TcParams &P, const TcRole &R)
         uint32_t acc_phases = 0;  // bit a: parity of accumulator buffer a
         int acc = 0;
         long long m_full = 0, m_tempty = 0;
+        uint32_t steps_done = 0;
         const long long m_t0 = clock64();
         // plan of the first K-step (the entry table is padded, so the second load is always in bounds)
         uint2 hdr = plan_hdr[0];
@@ -389,6 +412,7 @@ __device__ __forceinline__ void tc_mma_role(const TcParams &P, const TcRole &R)
                     }
                     tc_commit(bar_empty + 8 * stage);  // frees the stage when these MMAs have read it
                     if (kc == KS - 1) tc_commit(bar_tfull + 8 * acc);
+                    if (R.progress) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(R.progress), "r"(++steps_done) : "memory");
                 }
                 accumulate |= (cnt != 0);
                 __syncwarp();
@@ -407,7 +431,7 @@ __device__ __forceinline__ void tc_mma_role(const TcParams &P, const TcRole &R)
             acc ^= 1;
         }
         if ((DBG & 16) && lane == 0) {
-            unsigned long long *cnt = reinterpret_cast<unsigned long long *>(P.error_flag + 2);
+            unsigned long long *cnt = reinterpret_cast<unsigned long long *>(P.counters);
             atomicAdd(cnt + 3, (unsigned long long)(clock64() - m_t0));  // MMA warp total
             atomicAdd(cnt + 4, (unsigned long long)m_full);               // MMA waiting for a full stage
             atomicAdd(cnt + 5, (unsigned long long)m_tempty);             // MMA waiting for a free accumulator
@@ -433,8 +457,8 @@ __device__ __forceinline__ void tc_epilogue_role(const TcParams &P, const TcRole
     uint32_t acc_phases = 0;
     int acc = 0;
     for (long long tile = first_tile; tile < P.total_tiles; tile += tile_step) {
-        const int ch = (int)(tile / P.tiles_per_ch);
-        const long long tt = tile - (long long)ch * P.tiles_per_ch;
+        const unsigned ch = (unsigned)tile / (unsigned)P.tiles_per_ch;  // total_tiles < 2^31 (host check)
+        const long long tt = (long long)((unsigned)tile - ch * (unsigned)P.tiles_per_ch);
         uint32_t *o = P.out + (size_t)ch * P.out_stride;
         mbar_wait_acc<DBG>(bar_tfull + 8 * acc, (acc_phases >> acc) & 1, P.error_flag, e_wait);
         tc_fence_after();
@@ -443,6 +467,9 @@ __device__ __forceinline__ void tc_epilogue_role(const TcParams &P, const TcRole
             // weight slots of output b sit 8 TMEM lanes apart: a 16x256b load hands one thread the
             // slots {0,1} (lanes 0-15 of the warp's quadrant) or {2,3} (lanes 16-31) of output
             // b = 8*warp + lane/4 for the column pairs (re, im) of 4 row-blocks -> no shuffles
+            const long long idx_lane = (tt * TC_NRB + (lane & 3)) * TC_BOUT + b;  // output index for c0 = 0, k = 0
+            uint32_t *o_lane = o + idx_lane;
+            const bool full_tile = (tt + 1) * (long long)(TC_NRB * TC_BOUT) <= P.n_out;
 #pragma unroll 1
             for (int c0 = 0; c0 < ((P.debug & 4) ? 0 : 2 * TC_NRB); c0 += 32) {
                 uint32_t a[16], h[16];
@@ -461,14 +488,15 @@ __device__ __forceinline__ void tc_epilogue_role(const TcParams &P, const TcRole
                       "=r"(h[15])
                     : "r"(t_addr + (16u << 16) + c0));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                // this lane's outputs of the chunk: row-blocks m = c0/2 + 4*k + (lane & 3), output b
+                uint32_t *op = o_lane + c0 * (TC_BOUT / 2);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     // sum_w 256^w * D_w (mod 2^32, exactly the reference's int32 wrap)
                     const uint32_t re = a[4 * k] + (a[4 * k + 2] << 8) + (h[4 * k] << 16) + (h[4 * k + 2] << 24);
                     const uint32_t im = a[4 * k + 1] + (a[4 * k + 3] << 8) + (h[4 * k + 1] << 16) + (h[4 * k + 3] << 24);
-                    const int m = (c0 >> 1) + 4 * k + (lane & 3);
-                    const long long idx = (tt * TC_NRB + m) * TC_BOUT + b;
-                    if (idx < P.n_out) o[idx] = scale_pack<true>((int)re, (int)im, P.shift);
+                    const uint32_t word = scale_pack_sym_sat((int)re, (int)im, P.shift);
+                    if (full_tile || idx_lane + (c0 / 2 + 4 * k) * TC_BOUT < P.n_out) op[4 * k * TC_BOUT] = word;
                 }
             }
         } else {
@@ -515,14 +543,14 @@ __device__ __forceinline__ void tc_epilogue_role(const TcParams &P, const TcRole
         acc ^= 1;
     }
     if ((DBG & 16) && lane == 0) {
-        unsigned long long *cnt = reinterpret_cast<unsigned long long *>(P.error_flag + 2);
+        unsigned long long *cnt = reinterpret_cast<unsigned long long *>(P.counters);
         atomicAdd(cnt + 6, (unsigned long long)(clock64() - e_t0));  // epilogue warp total
         atomicAdd(cnt + 7, (unsigned long long)e_wait);               // epilogue waiting for accumulators
     }
 }
 
 template <int DBG, bool MIX>
-__global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_constant__ TcParams P)
+__global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_constant__ TcParams P, const __grid_constant__ CUtensorMap in_map)
 {
     extern __shared__ __align__(128) uint8_t tc_smem_raw[];
     uint8_t *smem = tc_smem_raw;
@@ -538,6 +566,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
     const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * TC_MAX_STAGES;
     const uint32_t bar_tfull = bar_empty + 8 * TC_MAX_STAGES, bar_tempty = bar_tfull + 16;
     __shared__ uint32_t tmem_base_s;
+    __shared__ uint32_t progress_s;
+    if (tid == 0) progress_s = 0;
 
     // ---- setup ------------------------------------------------------------------------------
     for (int i = tid; i < P.master_bytes / 16; i += TC_THREADS)
@@ -571,9 +601,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
     const long long first_tile = blockIdx.x, tile_step = gridDim.x;
     const int KS = P.M;  // K-steps per tile
     const TcRole role{a_smem, stages, stage_bytes, NS, J, KS, warp, lane, bar_full, bar_empty, bar_tfull, bar_tempty, tmem_base,
-                      first_tile, tile_step};
+                      first_tile, tile_step, P.pf_dist > 0 ? smem_u32(&progress_s) : 0u};
 
-    if (warp >= TC_PROD_WARP0) {
+    if (warp == TC_PF_WARP) {
+        // =====================================================================================
+        // L2 prefetcher: the producers' register-staged loads cannot keep enough bytes in flight to
+        // cover HBM latency (tools/ldbench.cu); one TMA prefetch per K-step -- the same box the
+        // producers are going to read, pf_dist K-steps ahead of the MMAs -- turns their loads into
+        // L2 hits.  No shared memory, no barrier: pacing follows the MMA warp's progress word.
+        // =====================================================================================
+        if (lane == 0 && P.pf_dist > 0) {
+            const uint32_t prog = smem_u32(&progress_s);
+            uint32_t gs = 0;
+            for (long long tile = first_tile; tile < P.total_tiles; tile += tile_step) {
+                const unsigned tl = (unsigned)tile;
+                const unsigned ch = tl / (unsigned)P.tiles_per_ch;
+                const unsigned tt = tl - ch * (unsigned)P.tiles_per_ch;
+                const int row0 = (int)tt * TC_NRB - (J - 1);
+                for (int kc = 0; kc < KS; ++kc, ++gs) {
+                    for (;;) {
+                        uint32_t done;
+                        asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(done) : "r"(prog) : "memory");
+                        if ((int)(gs - done) <= P.pf_dist) break;
+                        __nanosleep(100);
+                    }
+                    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(&in_map), "r"(32 * kc),
+                                 "r"(row0), "r"((int)ch)
+                                 : "memory");
+                }
+            }
+        }
+    } else if (warp >= TC_PROD_WARP0) {
         // =====================================================================================
         // producers.  Owner o = pw / TC_SPLIT stages K-steps o, o + TC_OWNERS, ... of the flattened
         // (tile, K-step) sequence (step gs -> stage gs % NS); its TC_SPLIT warps take half of the
@@ -606,7 +664,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
         unsigned ph0 = 0, fr = 0, dph = 0;  // MIX: channel phase at sample 0, frequency, phase step per iteration
         int stage = owner % NS;  // step gs uses stage gs % NS
         uint32_t parity = 1;     // first wait on a fresh "empty" barrier passes
-        TcBatch t;
         while (tile < P.total_tiles) {
             if (tile != cur_tile) {  // one division per tile
                 const unsigned tl = (unsigned)tile;
@@ -626,35 +683,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
             const bool fast_main = P.vec_in && col - 4 * piece + (long long)(TC_NRB - 1) * P.rb_stride + 32 <= P.n_in;
             const bool fast_halo = P.vec_in && tile0 > 0;  // the previous tile of the same block exists
 
-            mbar_wait_acc<DBG>(bar_empty + 8 * stage, parity, P.error_flag, w_wait);
             // (plane lo, this lane's kc chunk, re row of row-block rb, this lane's word) for rb = grp;
             // rows are shifted by front_pad so that the unused lanes of a prefetched halo batch
             // (row-blocks below -(J-1)) land in padding instead of out of bounds
             uint8_t *dst0 = stages + stage * stage_bytes + (piece >> 2) * chunk +
                             (P.front_pad + 2 * (grp + (J - 1))) * 16 + (piece & 3) * 4;
-            if (halo_it > 0) {
-                const int rb = -4 * halo_it + grp;
-                uint8_t *dst = dst0 - 4 * halo_it * 32;
-                if (fast_halo) {
-                    tc_batch_load_fast<DBG>(t, x + (col + (long long)rb * P.rb_stride), it_stride, halo_it);
-                    tc_batch_store_fast<DBG, MIX>(t, dst, dst + 2 * chunk, halo_it, tab_smem,
-                                                  (ph0 + ((unsigned)(col + (long long)rb * P.rb_stride) & P.mix_mask) * fr) & P.mix_mask,
-                                                  fr, dph, P.mix_mask);
-                } else {
-                    tc_batch_generic(P, x, hist, col + (long long)rb * P.rb_stride, rb, -(J - 1), 0, halo_it, dst, MIX, ph0, fr);
-                }
-            }
-#pragma unroll 1
-            for (int mb = 0; mb < MAIN_BATCHES; ++mb) {
-                const int rb = row_first + 4 * TC_BATCH * mb + grp;
+            // This warp's batches of the K-step: b = -1 (the halo rows, first warp of the owner only),
+            // 0 .. MAIN_BATCHES-1.  Two register slots: the loads of batch b + 1 are in flight while
+            // batch b is mixed / split / stored, and the first loads are issued before the wait for the
+            // stage, so only one load latency per K-step is exposed.
+            auto issue = [&](TcBatch &t, int b) {
+                const int rb = b < 0 ? -4 * halo_it + grp : row_first + 4 * TC_BATCH * b + grp;
+                t.fast = b < 0 ? fast_halo : fast_main;
+                if (t.fast) tc_batch_load_fast<DBG>(t, x + (col + (long long)rb * P.rb_stride), it_stride, b < 0 ? halo_it : TC_BATCH);
+            };
+            auto finish = [&](const TcBatch &t, int b) {
+                const int rb = b < 0 ? -4 * halo_it + grp : row_first + 4 * TC_BATCH * b + grp;
+                const int nit = b < 0 ? halo_it : TC_BATCH;
                 uint8_t *dst = dst0 + (rb - grp) * 32;
-                if (fast_main) {
-                    tc_batch_load_fast<DBG>(t, x + (col + (long long)rb * P.rb_stride), it_stride, TC_BATCH);
-                    tc_batch_store_fast<DBG, MIX>(t, dst, dst + 2 * chunk, TC_BATCH, tab_smem,
-                                                  (ph0 + ((unsigned)(col + (long long)rb * P.rb_stride) & P.mix_mask) * fr) & P.mix_mask,
-                                                  fr, dph, P.mix_mask);
-                } else {
-                    tc_batch_generic(P, x, hist, col + (long long)rb * P.rb_stride, rb, 0, TC_NRB, TC_BATCH, dst, MIX, ph0, fr);
+                const long long n0 = col + (long long)rb * P.rb_stride;
+                if (t.fast)
+                    tc_batch_store_fast<DBG, MIX>(t, dst, dst + 2 * chunk, nit, tab_smem,
+                                                  (ph0 + ((unsigned)n0 & P.mix_mask) * fr) & P.mix_mask, fr, dph, P.mix_mask);
+                else
+                    tc_batch_generic(P, x, hist, n0, rb, b < 0 ? -(J - 1) : 0, b < 0 ? 0 : TC_NRB, nit, dst, MIX, ph0, fr);
+            };
+            TcBatch slot[2];
+            const int b_first = halo_it > 0 ? -1 : 0;
+            issue(slot[0], b_first);
+            mbar_wait_acc<DBG>(bar_empty + 8 * stage, parity, P.error_flag, w_wait);
+#pragma unroll
+            for (int i = 0; i < 1 + MAIN_BATCHES; ++i) {
+                const int b = b_first + i;
+                if (b < MAIN_BATCHES) {
+                    if (b + 1 < MAIN_BATCHES) issue(slot[(i + 1) & 1], b + 1);
+                    finish(slot[i & 1], b);
                 }
             }
             // every writer fences its generic-proxy stores towards the async proxy (the MMA reads
@@ -680,7 +743,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
             }
         }
         if ((DBG & 16) && lane == 0) {
-            unsigned long long *cnt = reinterpret_cast<unsigned long long *>(P.error_flag + 2);
+            unsigned long long *cnt = reinterpret_cast<unsigned long long *>(P.counters);
             atomicAdd(cnt + 0, (unsigned long long)(clock64() - w_t0));  // producer total
             atomicAdd(cnt + 1, (unsigned long long)w_wait);               // producer waiting for an empty stage
             atomicAdd(cnt + 2, (unsigned long long)w_fence);              // producer in fence.proxy.async

@@ -12,8 +12,8 @@
 //   warps 0-3   epilogue            (tc_epilogue_role)
 //   warp  4     MMA issuer + TMEM   (tc_mma_role)
 //   warp  5     TMA issuer (one lane)
-//   warps 6..   converters in n_groups groups: a group takes every n_groups-th K-step, each of its
-//               warps every (n_conv / n_groups)-th group of 4 rows of it
+//   warps 6..   converters in groups of W warps: a group takes every (n_conv / W)-th K-step, each of
+//               its warps every W-th group of 4 rows of it
 //
 // Edges (rare): rows in front of the block come from the carried history and the ragged last
 // row-block is not part of the TMA tensor; the TMA box zero-fills both and the converters patch
@@ -33,8 +33,7 @@ constexpr int TMA_MAX_RAW = 12;
 
 struct TmaExtra {
     int n_raw;        // raw stages
-    int n_conv;       // converter warps
-    int n_groups;     // converter groups (n_conv % n_groups == 0, n_groups <= min(n_raw, n_stages - 1))
+    int n_conv;       // converter warps = W * groups (W = the kernel's template parameter; groups <= min(n_raw, n_stages - 1))
     int raw_rows;     // rows of a raw stage: 4 * ceil((J-1)/4) + 128 (the box lands at row raw_rows - box_rows)
     int box_rows;     // J - 1 + 128
     long long rows_full;  // floor(n_in / G): row-blocks that are part of the TMA tensor
@@ -52,6 +51,72 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
         : "memory");
 }
 
+// shared-window (32-bit) accesses with compile-time offsets: the converters' hot loop is nothing but
+// these, and generic pointers cost a window-base recomputation per access
+template <int OFF>
+__device__ __forceinline__ uint4 lds128(uint32_t a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+%5];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a), "n"(OFF));
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0+%2], %1;" ::"r"(a), "r"(v), "n"(OFF) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+
+// NCO mix of the 4 samples of a piece (mixers.h:172-177); tab = shared address of the packed (cos, sin)
+// table, ph4 / fr4 / mask4 = phase of the first sample, frequency, N - 1, all times 4 (byte offsets)
+__device__ __forceinline__ void tma_mix4(uint4 &q, uint32_t tab, unsigned ph4, unsigned fr4, unsigned mask4)
+{
+    const uint32_t c0 = lds32(tab + ph4);
+    const uint32_t c1 = lds32(tab + ((ph4 + fr4) & mask4));
+    const uint32_t c2 = lds32(tab + ((ph4 + 2 * fr4) & mask4));
+    const uint32_t c3 = lds32(tab + ((ph4 + 3 * fr4) & mask4));
+    q.x = mix_sample_packed(q.x, c0);
+    q.y = mix_sample_packed(q.y, c1);
+    q.z = mix_sample_packed(q.z, c2);
+    q.w = mix_sample_packed(q.w, c3);
+}
+
+// one group of 4 rows: this lane's 16-byte piece -> its 4 byte-plane words
+template <int DST_OFF>
+__device__ __forceinline__ void tma_split_store(const uint4 q, uint32_t dst_lo, uint32_t dst_hi)
+{
+    uint32_t re_lo, re_hi, im_lo, im_hi;
+    split4(q, re_lo, re_hi, im_lo, im_hi);
+    sts32<DST_OFF>(dst_lo, re_lo);
+    sts32<DST_OFF + 16>(dst_lo, im_lo);
+    sts32<DST_OFF>(dst_hi, re_hi);
+    sts32<DST_OFF + 16>(dst_hi, im_hi);
+}
+
+// 4 row groups W apart (this warp's share of 4 * W groups): all loads first, then mix / split / store
+template <bool MIX, int W>
+__device__ __forceinline__ void tma_convert4(uint32_t src, uint32_t dst_lo, uint32_t dst_hi, uint32_t tab, unsigned ph4, unsigned dph4,
+                                             unsigned fr4, unsigned mask4)
+{
+    uint4 v0 = lds128<0>(src), v1 = lds128<W * 512>(src), v2 = lds128<2 * W * 512>(src), v3 = lds128<3 * W * 512>(src);
+    if (MIX) {
+        tma_mix4(v0, tab, ph4, fr4, mask4);
+        tma_mix4(v1, tab, (ph4 + dph4) & mask4, fr4, mask4);
+        tma_mix4(v2, tab, (ph4 + 2 * dph4) & mask4, fr4, mask4);
+        tma_mix4(v3, tab, (ph4 + 3 * dph4) & mask4, fr4, mask4);
+    }
+    tma_split_store<0>(v0, dst_lo, dst_hi);
+    tma_split_store<W * 128>(v1, dst_lo, dst_hi);
+    tma_split_store<2 * W * 128>(v2, dst_lo, dst_hi);
+    tma_split_store<3 * W * 128>(v3, dst_lo, dst_hi);
+}
+
+// generic-pointer variant for the edge path
 template <bool MIX>
 __device__ __forceinline__ void tma_convert_store(uint4 q, uint8_t *dst, int hi_off, const uint32_t *tab, unsigned p0, unsigned fr,
                                                   unsigned mask)
@@ -70,7 +135,8 @@ __device__ __forceinline__ void tma_convert_store(uint4 q, uint8_t *dst, int hi_
     *reinterpret_cast<uint32_t *>(dst + hi_off + 16) = im_hi;
 }
 
-template <int DBG, bool MIX>
+// W = converter warps per group (4 or 8): each takes 32 / W of the 32 main row groups of a K-step
+template <int DBG, bool MIX, int W>
 __global__ void __launch_bounds__(TMA_MAX_THREADS, 1)
     dec_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TmaExtra X, const __grid_constant__ CUtensorMap in_map)
 {
@@ -103,12 +169,12 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1)
     fence_async_smem();
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) {
-            mbar_init(bar_full + 8 * s, NCW / X.n_groups);  // one arrival per converter warp of the K-step's group
+            mbar_init(bar_full + 8 * s, W);  // one arrival per converter warp of the K-step's group
             mbar_init(bar_empty + 8 * s, 1);   // tcgen05.commit
         }
         for (int s = 0; s < NR; ++s) {
             mbar_init(bar_rfull + 8 * s, 1);   // expect_tx arrival + the box's bytes
-            mbar_init(bar_rempty + 8 * s, NCW / X.n_groups);
+            mbar_init(bar_rempty + 8 * s, W);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(bar_tfull + 8 * a, 1);
@@ -128,32 +194,38 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1)
     const long long first_tile = blockIdx.x, tile_step = gridDim.x;
     const int KS = P.M;
     const TcRole role{a_smem, stages, stage_bytes, NS, J, KS, warp, lane, bar_full, bar_empty, bar_tfull, bar_tempty, tmem_base,
-                      first_tile, tile_step};
+                      first_tile, tile_step, 0u};
 
     if (warp >= TMA_CONV_WARP0) {
         // =====================================================================================
         // converters: raw stage (rows of 32 interleaved samples) -> byte-plane stage
         // =====================================================================================
-        // The warps form n_groups groups; group g converts K-steps g, g + n_groups, ... of the CTA's
+        // The warps form NG = n_conv / W groups; group g converts K-steps g, g + NG, ... of the CTA's
         // flattened (tile, K-step) sequence, its W warps share the row groups of such a K-step.  A warp's
         // per-K-step overhead (two barrier waits, proxy fence, two arrivals) is then paid once per
-        // n_groups K-steps, and the groups' K-steps overlap in time.
+        // NG K-steps, and the groups' K-steps overlap in time.
         const int cw = warp - TMA_CONV_WARP0;
-        const int NG = X.n_groups, W = NCW / NG;
+        const int NG = NCW / W;
         const int g = cw / W, wi = cw - g * W;
         const int piece = lane & 7, grp = lane >> 3;
         const int chunk = P.rbp * 16;
         const int halo_rows4 = X.raw_rows - TC_NRB;   // 4 * ceil((J-1)/4)
-        const int NQ = X.raw_rows / 4;                // groups of 4 rows per stage
+        const int HQ = halo_rows4 / 4;                // row groups in front of the tile (halo + padding rows)
+        const int NQ = X.raw_rows / 4;                // row groups per stage
         // raw row i (0 .. raw_rows) holds row-block rb = i - halo_rows4; its byte-plane rows are
         // front_pad + 2 * (rb + J - 1) = 2 * i (+1 for im)  [front_pad = 2 * (halo_rows4 - (J - 1))]
         const int src_lane = grp * 128 + piece * 16;
         const int dst_lane = (piece >> 2) * chunk + grp * 32 + (piece & 3) * 4;
         const int hi_off = 2 * chunk;
-        constexpr int QB = 5;  // row groups in flight per warp (registers): covers 33..36 row groups with 8 warps
+        // main row groups of this warp: HQ + wi + W * i, i < 32 / W; the HQ groups in front go to one warp
+        // of the group in turn
+        const uint32_t src_main = smem_u32(raw) + (HQ + wi) * 512 + src_lane;
+        const uint32_t dst_main = smem_u32(stages) + (HQ + wi) * 128 + dst_lane;
+        const uint32_t tab_u32 = smem_u32(tab_smem);
+        const unsigned mask4 = P.mix_mask << 2;
         int rs = g % NR, ss = g % NS;
         uint32_t rpar = 0, spar = 1;  // first wait on a fresh "empty" barrier passes
-        int rot = wi;                 // rotates the warp -> row-group assignment so that the odd group averages out
+        int halo_turn = 0;
         long long w_wait_raw = 0, w_wait_split = 0, w_fence = 0, w_arrive = 0;
         const long long w_t0 = clock64();
         long long tile = first_tile, cur_tile = -1, tile0 = 0;
@@ -163,7 +235,7 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1)
             tile += tile_step;
         }
         const uint32_t *x = nullptr, *hist = nullptr;
-        unsigned tt = 0, ph0 = 0, fr = 0, dph = 0;
+        unsigned tt = 0, ph0 = 0, fr = 0, fr4 = 0, dph4 = 0, ph_lane = 0;
         bool edge = false;
         while (tile < P.total_tiles) {
             if (tile != cur_tile) {  // one division per tile
@@ -178,37 +250,42 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1)
                 if (MIX) {
                     ph0 = (unsigned)P.phi[ch];
                     fr = (unsigned)P.freq[ch];
-                    dph = (((unsigned)(4 * W * P.G) & P.mix_mask) * fr) & P.mix_mask;  // phase step between a warp's row groups
+                    fr4 = fr << 2;
+                    dph4 = ((((unsigned)(4 * W * P.G) & P.mix_mask) * fr) & P.mix_mask) << 2;  // between a warp's row groups
+                    // phase of (row-block 4 * wi + grp, K-step 0, this lane's piece)
+                    ph_lane = (ph0 + ((unsigned)(tile0 + (long long)(4 * wi + grp) * P.G + 4 * piece) & P.mix_mask) * fr) & P.mix_mask;
                 }
                 cur_tile = tile;
             }
             mbar_wait_acc<DBG>(bar_rfull + 8 * rs, rpar, P.error_flag, w_wait_raw);
             mbar_wait_acc<DBG>(bar_empty + 8 * ss, spar, P.error_flag, w_wait_split);
-            const uint8_t *src = raw + rs * raw_bytes + src_lane;
-            uint8_t *dst = stages + ss * stage_bytes + dst_lane;
-            // sample index of (raw row grp, this lane's piece) of this K-step
-            const long long n_row0 = tile0 + (long long)(grp - halo_rows4) * P.G + 32 * kc + 4 * piece;
             if (P.debug & 8) {
                 // timing experiment: barriers only
             } else if (!edge) {
-                for (int q0 = rot; q0 < NQ; q0 += QB * W) {
-                    // all loads of the batch first: one shared-memory latency per batch
-                    uint4 v[QB];
-#pragma unroll
-                    for (int i = 0; i < QB; ++i)
-                        if (q0 + i * W < NQ) v[i] = *reinterpret_cast<const uint4 *>(src + (q0 + i * W) * 512);
-                    unsigned ph = 0;
-                    if (MIX) ph = (ph0 + ((unsigned)(n_row0 + (long long)4 * q0 * P.G) & P.mix_mask) * fr) & P.mix_mask;
-#pragma unroll
-                    for (int i = 0; i < QB; ++i) {
-                        if (q0 + i * W < NQ) {
-                            tma_convert_store<MIX>(v[i], dst + (q0 + i * W) * 128, hi_off, tab_smem, ph, fr, P.mix_mask);
-                            if (MIX) ph = (ph + dph) & P.mix_mask;
-                        }
+                const uint32_t src = src_main + rs * raw_bytes;
+                const uint32_t dst = dst_main + ss * stage_bytes;
+                const unsigned ph4 = MIX ? ((ph_lane + ((unsigned)(32 * kc) & P.mix_mask) * fr) & P.mix_mask) << 2 : 0u;
+                tma_convert4<MIX, W>(src, dst, dst + hi_off, tab_u32, ph4, dph4, fr4, mask4);
+                if (W == 4)
+                    tma_convert4<MIX, W>(src + 16 * 512, dst + 16 * 128, dst + 16 * 128 + hi_off, tab_u32, (ph4 + 4 * dph4) & mask4, dph4,
+                                         fr4, mask4);
+                if (HQ > 0 && wi == halo_turn) {
+                    // the row groups in front of the tile (the previous tile's last row-blocks)
+                    const uint8_t *hsrc = raw + rs * raw_bytes + src_lane;
+                    uint8_t *hdst = stages + ss * stage_bytes + dst_lane;
+                    for (int q = 0; q < HQ; ++q) {
+                        const uint4 v = *reinterpret_cast<const uint4 *>(hsrc + q * 512);
+                        const long long n = tile0 + (long long)(4 * q + grp - halo_rows4) * P.G + 32 * kc + 4 * piece;
+                        const unsigned ph = MIX ? (ph0 + ((unsigned)n & P.mix_mask) * fr) & P.mix_mask : 0u;
+                        tma_convert_store<MIX>(v, hdst + q * 128, hi_off, tab_smem, ph, fr, P.mix_mask);
                     }
                 }
             } else {
-                for (int q = rot; q < NQ; q += W) {
+                const uint8_t *src = raw + rs * raw_bytes + src_lane;
+                uint8_t *dst = stages + ss * stage_bytes + dst_lane;
+                // sample index of (raw row grp, this lane's piece) of this K-step
+                const long long n_row0 = tile0 + (long long)(grp - halo_rows4) * P.G + 32 * kc + 4 * piece;
+                for (int q = wi; q < NQ; q += W) {
                     const int rb = 4 * q + grp - halo_rows4;
                     const long long n = n_row0 + (long long)4 * q * P.G;
                     uint4 v;
@@ -272,10 +349,10 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1)
                 kc -= KS;
                 tile += tile_step;
             }
-            if (++rot == W) rot = 0;
+            if (++halo_turn == W) halo_turn = 0;
         }
         if ((DBG & 16) && lane == 0) {
-            unsigned long long *cnt = reinterpret_cast<unsigned long long *>(P.error_flag + 2);
+            unsigned long long *cnt = reinterpret_cast<unsigned long long *>(P.counters);
             atomicAdd(cnt + 0, (unsigned long long)(clock64() - w_t0));  // converter total
             atomicAdd(cnt + 1, (unsigned long long)w_wait_split);         // waiting for a free byte-plane stage
             atomicAdd(cnt + 2, (unsigned long long)w_wait_raw);           // waiting for a raw stage (TMA / HBM)

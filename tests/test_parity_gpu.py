@@ -345,6 +345,41 @@ def test_tc_matches_imad_on_unaligned_buffers(S, corc):
     assert np.array_equal(outs[1][2], e)
 
 
+@pytest.mark.parametrize("w,groups,stages,raw", [(4, 3, 0, 0), (4, 2, 0, 0), (4, 4, 0, 0), (8, 2, 0, 0), (8, 1, 0, 0), (4, 3, 4, 0),
+                                                 (4, 2, 5, 4), (4, 2, 3, 3)])
+@pytest.mark.parametrize("mix", [False, True])
+def test_tma_pipeline_shapes_match_imad(S, monkeypatch, w, groups, stages, raw, mix):
+    """Every converter-group / ring-depth shape of the TMA-fed kernel gives the IMAD kernel's output when each
+    CTA walks many tiles (7 per CTA here): the rings wrap, groups overtake each other, TMA boxes land out of order."""
+    import torch
+    C, M, nt, n = 32, 16, 255, 1 << 21
+    taps = O.design_lowpass_taps(nt, M)
+    x = torch.empty((C, n, 2), dtype=torch.int16, device="cuda")
+    S.synth_fill(x, 0x5EED00AA)
+    outs = []
+    for kind in (1, 2):
+        if kind == 2:
+            monkeypatch.setenv("SRCDSP_TMA_W", str(w))
+            monkeypatch.setenv("SRCDSP_TMA_GROUPS", str(groups))
+            if stages:
+                monkeypatch.setenv("SRCDSP_TMA_STAGES", str(stages))
+            if raw:
+                monkeypatch.setenv("SRCDSP_TMA_RAW", str(raw))
+        d = S.FilterDnsamplingFir(M, taps, channels=C, obsolete=True)
+        d.set_kernel(kind)
+        chain = d
+        if mix:
+            m = S.Mixer(channels=C)
+            m.setFrequency((-1 + 2 * (np.arange(C) + 0.5) / C).astype(np.float32))
+            chain = S.Ddc(m, d)
+        for rep in range(3):  # carried history + repeated launches
+            y = chain.step(x)
+        torch.cuda.synchronize()
+        outs.append(y)
+        assert d.last_kernel.startswith("dec_tma" if kind == 2 else "dec_fir")
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_tc_rejects_what_it_cannot_do(S):
     d = S.FilterDnsamplingFir(8, [2 ** 24] * 16, obsolete=True)  # needs 4 signed byte digits
     d.set_kernel(2)

@@ -1,8 +1,5 @@
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-B="python bench.py --workload cfg2 --steps 10 --no-e2e --no-cpu"
-$B 2>&1 | python tools/benchline.py
-for d in 10 14 1 2 4; do echo "debug=$d"; SRCDSP_TC_DEBUG=$d $B 2>&1 | python tools/benchline.py; done
-for cg in "8 2" "12 2" "12 3" "16 1"; do set -- $cg; echo "conv=$1 groups=$2"; SRCDSP_TMA_CONV=$1 SRCDSP_TMA_GROUPS=$2 $B 2>&1 | python tools/benchline.py; done
-python bench.py --workload cfg2 --kernel 3 --steps 10 --no-e2e --no-cpu 2>&1 | python tools/benchline.py
-python bench.py --workload ddc16 --steps 10 --no-e2e --no-cpu 2>&1 | python tools/benchline.py
-SRCDSP_TC_DEBUG=32 python bench.py --workload cfg2 --steps 3 --no-e2e --no-cpu 2>&1 | tail -2 | head -1
+for w in cfg2 ddc16 cfg3 cfg5 cfg1; do python bench.py --workload $w --steps 10 --no-e2e --no-cpu 2>&1 | python tools/benchline.py | tail -1 | cut -c1-150; done
+CMD="python bench.py --workload ddc16 --steps 1 --warmup 3 --no-e2e --no-cpu"
+$CMD > gpurun_out/plain_tma_mix.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:dec_tma_kernel -s 3 -c 1 -f -o gpurun_out/prof_r1_dec_tma_mix_v1 $CMD > gpurun_out/ncu_tma_mix.log 2>&1
+tail -2 gpurun_out/ncu_tma_mix.log
