@@ -920,6 +920,7 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
             X.n_raw = tma_raw;
             if (const char *e = getenv("SRCDSP_TMA_RAW")) X.n_raw = std::max(2, std::min(atoi(e), tma_raw));
             tma_groups = std::max(1, std::min(tma_groups, std::min(X.n_raw, tma_stages - 1)));
+            tma_groups = std::min(tma_groups, M);  // every group must see every tile (per-channel rebuild barrier of the fused mixer)
             // A raw stage must always be converted by the same group: TMA boxes complete out of order, so a
             // different group could reach the stage's next use before the previous use has even landed
             // and pass its parity wait one phase early.  n_raw = a multiple of the group count.

@@ -337,7 +337,7 @@ struct TcRole {
     uint8_t *a_smem, *stages;
     int stage_bytes, NS, J, KS, warp, lane;
     uint32_t bar_full, bar_empty, bar_tfull, bar_tempty, tmem_base;
-    long long first_tile, tile_step;
+    long long first_tile, tile_step, tile_end;  // this CTA's tiles: first_tile, first_tile + tile_step, ... < tile_end
     uint32_t progress;  // != 0: shared-memory word that receives the number of K-steps issued so far (L2 prefetch pacing)
 };
 
@@ -385,7 +385,7 @@ __device__ __forceinline__ void tc_mma_role(const TcParams &P, const TcRole &R)
         // plan of the first K-step (the entry table is padded, so the second load is always in bounds)
         uint2 hdr = plan_hdr[0];
         uint4 e0 = plan_ent[hdr.x], e1 = plan_ent[hdr.x + 1];
-        for (long long tile = first_tile; tile < P.total_tiles; tile += tile_step) {
+        for (long long tile = first_tile; tile < R.tile_end; tile += tile_step) {
             mbar_wait_acc<DBG>(bar_tempty + 8 * acc, ((acc_phases >> acc) & 1) ^ 1, P.error_flag, m_tempty);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * (2 * TC_NRB);
@@ -456,7 +456,7 @@ __device__ __forceinline__ void tc_epilogue_role(const TcParams &P, const TcRole
     const long long e_t0 = clock64();
     uint32_t acc_phases = 0;
     int acc = 0;
-    for (long long tile = first_tile; tile < P.total_tiles; tile += tile_step) {
+    for (long long tile = first_tile; tile < R.tile_end; tile += tile_step) {
         const unsigned ch = (unsigned)tile / (unsigned)P.tiles_per_ch;  // total_tiles < 2^31 (host check)
         const long long tt = (long long)((unsigned)tile - ch * (unsigned)P.tiles_per_ch);
         uint32_t *o = P.out + (size_t)ch * P.out_stride;
@@ -598,10 +598,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
-    const long long first_tile = blockIdx.x, tile_step = gridDim.x;
+    // a CTA walks a contiguous run of tiles (consecutive tiles of a channel: the halo rows of a tile are the
+    // previous tile's last rows, still in L2; the fused mixer's per-channel state changes rarely)
+    const long long first_tile = P.total_tiles * blockIdx.x / gridDim.x, tile_end = P.total_tiles * (blockIdx.x + 1) / gridDim.x;
+    const long long tile_step = 1;
     const int KS = P.M;  // K-steps per tile
     const TcRole role{a_smem, stages, stage_bytes, NS, J, KS, warp, lane, bar_full, bar_empty, bar_tfull, bar_tempty, tmem_base,
-                      first_tile, tile_step, P.pf_dist > 0 ? smem_u32(&progress_s) : 0u};
+                      first_tile, tile_step, tile_end, P.pf_dist > 0 ? smem_u32(&progress_s) : 0u};
 
     if (warp == TC_PF_WARP) {
         // =====================================================================================
@@ -613,7 +616,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
         if (lane == 0 && P.pf_dist > 0) {
             const uint32_t prog = smem_u32(&progress_s);
             uint32_t gs = 0;
-            for (long long tile = first_tile; tile < P.total_tiles; tile += tile_step) {
+            for (long long tile = first_tile; tile < tile_end; tile += tile_step) {
                 const unsigned tl = (unsigned)tile;
                 const unsigned ch = tl / (unsigned)P.tiles_per_ch;
                 const unsigned tt = tl - ch * (unsigned)P.tiles_per_ch;
@@ -654,7 +657,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
 
         long long tile = first_tile;
         int kc = owner;
-        while (kc >= KS && tile < P.total_tiles) {
+        while (kc >= KS && tile < tile_end) {
             kc -= KS;
             tile += tile_step;
         }
@@ -664,7 +667,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
         unsigned ph0 = 0, fr = 0, dph = 0;  // MIX: channel phase at sample 0, frequency, phase step per iteration
         int stage = owner % NS;  // step gs uses stage gs % NS
         uint32_t parity = 1;     // first wait on a fresh "empty" barrier passes
-        while (tile < P.total_tiles) {
+        while (tile < tile_end) {
             if (tile != cur_tile) {  // one division per tile
                 const unsigned tl = (unsigned)tile;
                 const unsigned ch = tl / (unsigned)P.tiles_per_ch;

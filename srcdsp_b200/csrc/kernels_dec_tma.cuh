@@ -72,18 +72,18 @@ __device__ __forceinline__ uint32_t lds32(uint32_t a)
     return v;
 }
 
-// NCO mix of the 4 samples of a piece (mixers.h:172-177); tab = shared address of the packed (cos, sin)
-// table, ph4 / fr4 / mask4 = phase of the first sample, frequency, N - 1, all times 4 (byte offsets)
-__device__ __forceinline__ void tma_mix4(uint4 &q, uint32_t tab, unsigned ph4, unsigned fr4, unsigned mask4)
+// NCO mix of the 4 samples of a piece (mixers.h:172-177).  lo = shared address of the channel's local-
+// oscillator sequence in TIME order, lo[n] = (cos, sin) of phase (phi0 + n * freq) mod N for n < N (it has
+// period N): the 4 samples of a piece take one conflict-free LDS.128 instead of 4 gathers from the sine
+// table, whose stride (the channel frequency) makes the lanes collide on a few banks.
+// idx4 = byte offset of the piece's first sample, (n mod N) * 4.
+__device__ __forceinline__ void tma_mix4(uint4 &q, uint32_t lo, unsigned idx4)
 {
-    const uint32_t c0 = lds32(tab + ph4);
-    const uint32_t c1 = lds32(tab + ((ph4 + fr4) & mask4));
-    const uint32_t c2 = lds32(tab + ((ph4 + 2 * fr4) & mask4));
-    const uint32_t c3 = lds32(tab + ((ph4 + 3 * fr4) & mask4));
-    q.x = mix_sample_packed(q.x, c0);
-    q.y = mix_sample_packed(q.y, c1);
-    q.z = mix_sample_packed(q.z, c2);
-    q.w = mix_sample_packed(q.w, c3);
+    const uint4 c = lds128<0>(lo + idx4);
+    q.x = mix_sample_packed(q.x, c.x);
+    q.y = mix_sample_packed(q.y, c.y);
+    q.z = mix_sample_packed(q.z, c.z);
+    q.w = mix_sample_packed(q.w, c.w);
 }
 
 // one group of 4 rows: this lane's 16-byte piece -> its 4 byte-plane words
@@ -100,15 +100,15 @@ __device__ __forceinline__ void tma_split_store(const uint4 q, uint32_t dst_lo, 
 
 // 4 row groups W apart (this warp's share of 4 * W groups): all loads first, then mix / split / store
 template <bool MIX, int W>
-__device__ __forceinline__ void tma_convert4(uint32_t src, uint32_t dst_lo, uint32_t dst_hi, uint32_t tab, unsigned ph4, unsigned dph4,
-                                             unsigned fr4, unsigned mask4)
+__device__ __forceinline__ void tma_convert4(uint32_t src, uint32_t dst_lo, uint32_t dst_hi, uint32_t lo, unsigned idx4, unsigned didx4,
+                                             unsigned mask4)
 {
     uint4 v0 = lds128<0>(src), v1 = lds128<W * 512>(src), v2 = lds128<2 * W * 512>(src), v3 = lds128<3 * W * 512>(src);
     if (MIX) {
-        tma_mix4(v0, tab, ph4, fr4, mask4);
-        tma_mix4(v1, tab, (ph4 + dph4) & mask4, fr4, mask4);
-        tma_mix4(v2, tab, (ph4 + 2 * dph4) & mask4, fr4, mask4);
-        tma_mix4(v3, tab, (ph4 + 3 * dph4) & mask4, fr4, mask4);
+        tma_mix4(v0, lo, idx4);
+        tma_mix4(v1, lo, (idx4 + didx4) & mask4);
+        tma_mix4(v2, lo, (idx4 + 2 * didx4) & mask4);
+        tma_mix4(v3, lo, (idx4 + 3 * didx4) & mask4);
     }
     tma_split_store<0>(v0, dst_lo, dst_hi);
     tma_split_store<W * 128>(v1, dst_lo, dst_hi);
@@ -116,7 +116,7 @@ __device__ __forceinline__ void tma_convert4(uint32_t src, uint32_t dst_lo, uint
     tma_split_store<3 * W * 128>(v3, dst_lo, dst_hi);
 }
 
-// generic-pointer variant for the edge path
+// generic-pointer variant for the edge path (tab = the oscillator sequence, p0 = n mod N, fr = 1)
 template <bool MIX>
 __device__ __forceinline__ void tma_convert_store(uint4 q, uint8_t *dst, int hi_off, const uint32_t *tab, unsigned p0, unsigned fr,
                                                   unsigned mask)
@@ -161,8 +161,7 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1)
     // ---- setup ------------------------------------------------------------------------------
     for (int i = tid; i < P.master_bytes / 16; i += blockDim.x)
         reinterpret_cast<uint4 *>(a_smem)[i] = __ldg(reinterpret_cast<const uint4 *>(P.master) + i);
-    if (MIX)
-        for (int i = tid; i < P.table_bytes / 4; i += blockDim.x) tab_smem[i] = __ldg(P.cs_table + i);
+    // (MIX: tab_smem holds the current channel's oscillator sequence; the converters build it)
     // padding rows of both rings must be defined: zero everything once
     for (int i = tid; i < (NR * raw_bytes + NS * stage_bytes) / 16; i += blockDim.x)
         reinterpret_cast<uint4 *>(raw)[i] = make_uint4(0, 0, 0, 0);
@@ -191,10 +190,13 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1)
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
-    const long long first_tile = blockIdx.x, tile_step = gridDim.x;
+    // a CTA walks a contiguous run of tiles (consecutive tiles of a channel: the halo rows of a tile are the
+    // previous tile's last rows, still in L2; the fused mixer's per-channel sequence changes rarely)
+    const long long first_tile = P.total_tiles * blockIdx.x / gridDim.x, tile_end = P.total_tiles * (blockIdx.x + 1) / gridDim.x;
+    const long long tile_step = 1;
     const int KS = P.M;
     const TcRole role{a_smem, stages, stage_bytes, NS, J, KS, warp, lane, bar_full, bar_empty, bar_tfull, bar_tempty, tmem_base,
-                      first_tile, tile_step, 0u};
+                      first_tile, tile_step, tile_end, 0u};
 
     if (warp >= TMA_CONV_WARP0) {
         // =====================================================================================
@@ -230,14 +232,15 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1)
         const long long w_t0 = clock64();
         long long tile = first_tile, cur_tile = -1, tile0 = 0;
         int kc = g;
-        while (kc >= KS && tile < P.total_tiles) {
+        while (kc >= KS && tile < tile_end) {
             kc -= KS;
             tile += tile_step;
         }
         const uint32_t *x = nullptr, *hist = nullptr;
-        unsigned tt = 0, ph0 = 0, fr = 0, fr4 = 0, dph4 = 0, ph_lane = 0;
+        unsigned tt = 0, ph0 = 0, fr = 0, didx4 = 0, n_lane = 0;
+        int cur_ch = -1;
         bool edge = false;
-        while (tile < P.total_tiles) {
+        while (tile < tile_end) {
             if (tile != cur_tile) {  // one division per tile
                 const unsigned tl = (unsigned)tile;
                 const unsigned ch = tl / (unsigned)P.tiles_per_ch;
@@ -248,12 +251,21 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1)
                 // rows the TMA tensor does not hold: history in front of the block, everything from the ragged row-block on
                 edge = (tt == 0 && J > 1) || ((long long)(tt + 1) * TC_NRB > X.rows_full);
                 if (MIX) {
-                    ph0 = (unsigned)P.phi[ch];
-                    fr = (unsigned)P.freq[ch];
-                    fr4 = fr << 2;
-                    dph4 = ((((unsigned)(4 * W * P.G) & P.mix_mask) * fr) & P.mix_mask) << 2;  // between a warp's row groups
-                    // phase of (row-block 4 * wi + grp, K-step 0, this lane's piece)
-                    ph_lane = (ph0 + ((unsigned)(tile0 + (long long)(4 * wi + grp) * P.G + 4 * piece) & P.mix_mask) * fr) & P.mix_mask;
+                    if ((int)ch != cur_ch) {
+                        // new channel: all converter warps rebuild the oscillator sequence lo[n] = T[(phi0 + n * freq) mod N]
+                        // (rare: a CTA walks consecutive tiles).  Every group passes here once per tile, so the counts
+                        // match; the first barrier waits until no warp reads the previous channel's sequence any more.
+                        ph0 = (unsigned)P.phi[ch];
+                        fr = (unsigned)P.freq[ch];
+                        asm volatile("bar.sync 1, %0;" ::"r"(NCW * 32) : "memory");
+                        for (unsigned i = cw * 32 + lane; i <= P.mix_mask; i += NCW * 32)
+                            tab_smem[i] = __ldg(P.cs_table + ((ph0 + i * fr) & P.mix_mask));
+                        asm volatile("bar.sync 1, %0;" ::"r"(NCW * 32) : "memory");
+                        cur_ch = (int)ch;
+                    }
+                    didx4 = ((unsigned)(4 * W * P.G) & P.mix_mask) << 2;  // between a warp's row groups
+                    // sample index mod N of (row-block 4 * wi + grp, K-step 0, this lane's piece)
+                    n_lane = (unsigned)(tile0 + (long long)(4 * wi + grp) * P.G + 4 * piece) & P.mix_mask;
                 }
                 cur_tile = tile;
             }
@@ -264,11 +276,11 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1)
             } else if (!edge) {
                 const uint32_t src = src_main + rs * raw_bytes;
                 const uint32_t dst = dst_main + ss * stage_bytes;
-                const unsigned ph4 = MIX ? ((ph_lane + ((unsigned)(32 * kc) & P.mix_mask) * fr) & P.mix_mask) << 2 : 0u;
-                tma_convert4<MIX, W>(src, dst, dst + hi_off, tab_u32, ph4, dph4, fr4, mask4);
+                const unsigned idx4 = MIX ? ((n_lane + 32 * kc) & P.mix_mask) << 2 : 0u;
+                tma_convert4<MIX, W>(src, dst, dst + hi_off, tab_u32, idx4, didx4, mask4);
                 if (W == 4)
-                    tma_convert4<MIX, W>(src + 16 * 512, dst + 16 * 128, dst + 16 * 128 + hi_off, tab_u32, (ph4 + 4 * dph4) & mask4, dph4,
-                                         fr4, mask4);
+                    tma_convert4<MIX, W>(src + 16 * 512, dst + 16 * 128, dst + 16 * 128 + hi_off, tab_u32, (idx4 + 4 * didx4) & mask4, didx4,
+                                         mask4);
                 if (HQ > 0 && wi == halo_turn) {
                     // the row groups in front of the tile (the previous tile's last row-blocks)
                     const uint8_t *hsrc = raw + rs * raw_bytes + src_lane;
@@ -276,8 +288,7 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1)
                     for (int q = 0; q < HQ; ++q) {
                         const uint4 v = *reinterpret_cast<const uint4 *>(hsrc + q * 512);
                         const long long n = tile0 + (long long)(4 * q + grp - halo_rows4) * P.G + 32 * kc + 4 * piece;
-                        const unsigned ph = MIX ? (ph0 + ((unsigned)n & P.mix_mask) * fr) & P.mix_mask : 0u;
-                        tma_convert_store<MIX>(v, hdst + q * 128, hi_off, tab_smem, ph, fr, P.mix_mask);
+                        tma_convert_store<MIX>(v, hdst + q * 128, hi_off, tab_smem, (unsigned)n & P.mix_mask, 1u, P.mix_mask);
                     }
                 }
             } else {
@@ -309,8 +320,7 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1)
                     } else {
                         v = *reinterpret_cast<const uint4 *>(src + q * 512);
                     }
-                    const unsigned ph = MIX ? (ph0 + ((unsigned)n & P.mix_mask) * fr) & P.mix_mask : 0u;
-                    tma_convert_store<MIX>(v, dst + q * 128, hi_off, tab_smem, ph, fr, P.mix_mask);
+                    tma_convert_store<MIX>(v, dst + q * 128, hi_off, tab_smem, (unsigned)n & P.mix_mask, 1u, P.mix_mask);
                 }
             }
             // the MMA reads shared memory through the async proxy: fence this warp's stores, then
@@ -369,7 +379,7 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1)
             const uint32_t raw_u32 = smem_u32(raw);
             int rs = 0;
             uint32_t rpar = 1;
-            for (long long tile = first_tile; tile < P.total_tiles; tile += tile_step) {
+            for (long long tile = first_tile; tile < tile_end; tile += tile_step) {
                 const unsigned tl = (unsigned)tile;
                 const unsigned ch = tl / (unsigned)P.tiles_per_ch;
                 const unsigned tt = tl - ch * (unsigned)P.tiles_per_ch;
