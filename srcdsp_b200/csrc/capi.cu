@@ -841,7 +841,7 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
     int tma_w = 4, tma_groups = mixer ? 3 : 2;
     if (const char *e = getenv("SRCDSP_TMA_W")) tma_w = atoi(e) == 8 ? 8 : 4;
     if (const char *e = getenv("SRCDSP_TMA_GROUPS")) tma_groups = std::max(1, atoi(e));
-    tma_groups = std::min(tma_groups, TMA_MAX_CONV / tma_w);
+    tma_groups = std::min(tma_groups, (mixer ? TMA_MAX_CONV_MIX : TMA_MAX_CONV) / tma_w);
     bool use_tma = have_map && kernel_kind != 3 && !getenv("SRCDSP_NO_TMA") &&
                    tma_layout(tbl_bytes, tma_groups, &tma_raw, &tma_stages, &tma_smem) == SRCDSP_OK;
     if (use_tc && !use_tma && tc_layout(tbl_bytes, &tc_stages, &tc_smem) != SRCDSP_OK)

@@ -30,6 +30,7 @@ constexpr int TMA_CONV_WARP0 = 6;
 constexpr int TMA_MAX_CONV = 16;
 constexpr int TMA_MAX_THREADS = 32 * (TMA_CONV_WARP0 + TMA_MAX_CONV);
 constexpr int TMA_MAX_RAW = 12;
+constexpr int TMA_MAX_CONV_MIX = 12;  // fused mixer: fewer warps, more registers each (the mix keeps many values live)
 
 struct TmaExtra {
     int n_raw;        // raw stages
@@ -116,6 +117,43 @@ __device__ __forceinline__ void tma_convert4(uint32_t src, uint32_t dst_lo, uint
     tma_split_store<3 * W * 128>(v3, dst_lo, dst_hi);
 }
 
+// Same with ONE oscillator piece for all 4 row groups: when the distance between a warp's row groups
+// (4 * W * G samples) is a multiple of the table size N -- the usual case, e.g. N = 4096 with W * M a
+// multiple of 32 -- the groups see the same oscillator values, which are then fetched and unpacked once
+// per K-step instead of once per piece.
+struct MixPiece {
+    int c[4], s[4];
+};
+__device__ __forceinline__ uint32_t mix_sample_unpacked(uint32_t x, int c, int s)
+{
+    const int xr = sx_lo(x), xi = sx_hi(x);
+    const int r = (xr * c - xi * s) >> 14;  // dsp_complex.cpp:31-37, mixers.h:175-176
+    const int i = (xi * c + s * xr) >> 14;
+    uint32_t p;
+    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(p) : "r"(i), "r"(r));
+    return __vmaxs2(p, 0x80018001u);  // limitScale16's symmetric clamp (dsp_complex.cpp:63-73)
+}
+__device__ __forceinline__ void tma_mix4_same(uint4 &q, const MixPiece &m)
+{
+    q.x = mix_sample_unpacked(q.x, m.c[0], m.s[0]);
+    q.y = mix_sample_unpacked(q.y, m.c[1], m.s[1]);
+    q.z = mix_sample_unpacked(q.z, m.c[2], m.s[2]);
+    q.w = mix_sample_unpacked(q.w, m.c[3], m.s[3]);
+}
+template <int W>
+__device__ __forceinline__ void tma_convert4_same(uint32_t src, uint32_t dst_lo, uint32_t dst_hi, const MixPiece &m)
+{
+    uint4 v0 = lds128<0>(src), v1 = lds128<W * 512>(src), v2 = lds128<2 * W * 512>(src), v3 = lds128<3 * W * 512>(src);
+    tma_mix4_same(v0, m);
+    tma_mix4_same(v1, m);
+    tma_mix4_same(v2, m);
+    tma_mix4_same(v3, m);
+    tma_split_store<0>(v0, dst_lo, dst_hi);
+    tma_split_store<W * 128>(v1, dst_lo, dst_hi);
+    tma_split_store<2 * W * 128>(v2, dst_lo, dst_hi);
+    tma_split_store<3 * W * 128>(v3, dst_lo, dst_hi);
+}
+
 // generic-pointer variant for the edge path (tab = the oscillator sequence, p0 = n mod N, fr = 1)
 template <bool MIX>
 __device__ __forceinline__ void tma_convert_store(uint4 q, uint8_t *dst, int hi_off, const uint32_t *tab, unsigned p0, unsigned fr,
@@ -137,7 +175,7 @@ __device__ __forceinline__ void tma_convert_store(uint4 q, uint8_t *dst, int hi_
 
 // W = converter warps per group (4 or 8): each takes 32 / W of the 32 main row groups of a K-step
 template <int DBG, bool MIX, int W>
-__global__ void __launch_bounds__(TMA_MAX_THREADS, 1)
+__global__ void __launch_bounds__(MIX ? 32 * (TMA_CONV_WARP0 + TMA_MAX_CONV_MIX) : TMA_MAX_THREADS, 1)
     dec_tma_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TmaExtra X, const __grid_constant__ CUtensorMap in_map)
 {
     extern __shared__ __align__(128) uint8_t tc_smem_raw[];
@@ -277,10 +315,21 @@ __global__ void __launch_bounds__(TMA_MAX_THREADS, 1)
                 const uint32_t src = src_main + rs * raw_bytes;
                 const uint32_t dst = dst_main + ss * stage_bytes;
                 const unsigned idx4 = MIX ? ((n_lane + 32 * kc) & P.mix_mask) << 2 : 0u;
-                tma_convert4<MIX, W>(src, dst, dst + hi_off, tab_u32, idx4, didx4, mask4);
-                if (W == 4)
-                    tma_convert4<MIX, W>(src + 16 * 512, dst + 16 * 128, dst + 16 * 128 + hi_off, tab_u32, (idx4 + 4 * didx4) & mask4, didx4,
-                                         mask4);
+                if (MIX && didx4 == 0) {
+                    const uint4 cs = lds128<0>(tab_u32 + idx4);
+                    MixPiece m;
+                    m.c[0] = sx_lo(cs.x), m.s[0] = sx_hi(cs.x);
+                    m.c[1] = sx_lo(cs.y), m.s[1] = sx_hi(cs.y);
+                    m.c[2] = sx_lo(cs.z), m.s[2] = sx_hi(cs.z);
+                    m.c[3] = sx_lo(cs.w), m.s[3] = sx_hi(cs.w);
+                    tma_convert4_same<W>(src, dst, dst + hi_off, m);
+                    if (W == 4) tma_convert4_same<W>(src + 16 * 512, dst + 16 * 128, dst + 16 * 128 + hi_off, m);
+                } else {
+                    tma_convert4<MIX, W>(src, dst, dst + hi_off, tab_u32, idx4, didx4, mask4);
+                    if (W == 4)
+                        tma_convert4<MIX, W>(src + 16 * 512, dst + 16 * 128, dst + 16 * 128 + hi_off, tab_u32, (idx4 + 4 * didx4) & mask4,
+                                             didx4, mask4);
+                }
                 if (HQ > 0 && wi == halo_turn) {
                     // the row groups in front of the tile (the previous tile's last row-blocks)
                     const uint8_t *hsrc = raw + rs * raw_bytes + src_lane;
