@@ -1,3 +1,5 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-for cfg in "4 3 0" "4 3 5" "4 2 3" "8 1 3"; do set -- $cfg; echo "ddc16 W=$1 groups=$2 stages=$3"; SRCDSP_TMA_W=$1 SRCDSP_TMA_GROUPS=$2 SRCDSP_TMA_STAGES=$3 python bench.py --workload ddc16 --steps 10 --no-e2e --no-cpu 2>&1 | python tools/benchline.py | tail -1 | cut -c1-120; done
-python bench.py --workload cfg3 --steps 10 --no-e2e --no-cpu 2>&1 | python tools/benchline.py | tail -1 | cut -c1-150
+python bench.py --steps 20 --warmup 3 > gpurun_out/bench_r1_cfg2.json 2> gpurun_out/bench_r1_cfg2.err; tail -c 400 gpurun_out/bench_r1_cfg2.err
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_r1_reference.json 2>> gpurun_out/bench_r1_cfg2.err
+CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu"
+$CMD > gpurun_out/plain_launches.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1_tma.csv $CMD > gpurun_out/ncu_launches.log 2>&1
+python tools/benchline.py < gpurun_out/bench_r1_cfg2.json; python tools/benchline.py < gpurun_out/bench_r1_reference.json
