@@ -830,7 +830,8 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
         if (!pm.mask) use_tc = false, why = "fused mixer needs a power-of-two sine table";
     }
     // TMA-fed variant: needs 16-byte aligned rows and at least one whole row-block in the tensor
-    const int tbl_bytes = mixer ? (int)mixer->n_table * 4 : 0;
+    const int tbl_bytes = mixer ? (int)mixer->n_table * 4 : 0;      // LDG variant: copy of the packed (cos, sin) table
+    const int tma_tbl_bytes = mixer ? (int)mixer->n_table * 8 : 0;  // TMA variant: oscillator sequence, two digit words per sample
     const long long rows_full = (long long)(n_in / (size_t)(32 * M));
     int tma_raw = 0, tma_stages = 0;
     size_t tma_smem = 0;
@@ -843,7 +844,7 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
     if (const char *e = getenv("SRCDSP_TMA_GROUPS")) tma_groups = std::max(1, atoi(e));
     tma_groups = std::min(tma_groups, (mixer ? TMA_MAX_CONV_MIX : TMA_MAX_CONV) / tma_w);
     bool use_tma = have_map && kernel_kind != 3 && !getenv("SRCDSP_NO_TMA") &&
-                   tma_layout(tbl_bytes, tma_groups, &tma_raw, &tma_stages, &tma_smem) == SRCDSP_OK;
+                   tma_layout(tma_tbl_bytes, tma_groups, &tma_raw, &tma_stages, &tma_smem) == SRCDSP_OK;
     if (use_tc && !use_tma && tc_layout(tbl_bytes, &tc_stages, &tc_smem) != SRCDSP_OK)
         use_tc = false, why = "sine table + Toeplitz master + stages exceed 227 KB of shared memory";
     if (kernel_kind >= 2 && !use_tc)
@@ -921,15 +922,14 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
             if (const char *e = getenv("SRCDSP_TMA_RAW")) X.n_raw = std::max(2, std::min(atoi(e), tma_raw));
             tma_groups = std::max(1, std::min(tma_groups, std::min(X.n_raw, tma_stages - 1)));
             tma_groups = std::min(tma_groups, M);  // every group must see every tile (per-channel rebuild barrier of the fused mixer)
-            // A raw stage must always be converted by the same group: TMA boxes complete out of order, so a
-            // different group could reach the stage's next use before the previous use has even landed
-            // and pass its parity wait one phase early.  n_raw = a multiple of the group count.
-            X.n_raw -= X.n_raw % tma_groups;
+            // a raw stage that different groups convert in turn needs an extra wait (see the converters)
+            X.shared_raw = (X.n_raw % tma_groups) != 0;
             X.n_conv = tma_w * tma_groups;
             X.raw_rows = 4 * ((T.J - 1 + 3) / 4) + TC_NRB;
             X.box_rows = T.J - 1 + TC_NRB;
             X.rows_full = rows_full;
             T.n_stages = tma_stages;
+            T.table_bytes = tma_tbl_bytes;
             const int threads = 32 * (TMA_CONV_WARP0 + X.n_conv);
             if (T.debug & 32) {  // wait-cycle accounting variant; counters printed at the next launch
                 unsigned long long c[10];

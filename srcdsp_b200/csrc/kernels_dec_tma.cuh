@@ -35,6 +35,7 @@ constexpr int TMA_MAX_CONV_MIX = 12;  // fused mixer: fewer warps, more register
 struct TmaExtra {
     int n_raw;        // raw stages
     int n_conv;       // converter warps = W * groups (W = the kernel's template parameter; groups <= min(n_raw, n_stages - 1))
+    int shared_raw;   // n_raw % groups != 0: a raw stage is converted by different groups in turn
     int raw_rows;     // rows of a raw stage: 4 * ceil((J-1)/4) + 128 (the box lands at row raw_rows - box_rows)
     int box_rows;     // J - 1 + 128
     long long rows_full;  // floor(n_in / G): row-blocks that are part of the TMA tensor
@@ -73,18 +74,49 @@ __device__ __forceinline__ uint32_t lds32(uint32_t a)
     return v;
 }
 
-// NCO mix of the 4 samples of a piece (mixers.h:172-177).  lo = shared address of the channel's local-
-// oscillator sequence in TIME order, lo[n] = (cos, sin) of phase (phi0 + n * freq) mod N for n < N (it has
-// period N): the 4 samples of a piece take one conflict-free LDS.128 instead of 4 gathers from the sine
-// table, whose stride (the channel frequency) makes the lanes collide on a few banks.
-// idx4 = byte offset of the piece's first sample, (n mod N) * 4.
-__device__ __forceinline__ void tma_mix4(uint4 &q, uint32_t lo, unsigned idx4)
+// NCO mix (mixers.h:172-177) on the integer dot-product pipe.  The sample word is already the packed pair
+// (re, im) that dp2a takes; the oscillator value is kept as signed byte digits, cos = 256 * c1 + c0 etc.:
+//   Bre = bytes {c0, n0, c1, n1}  (n = -sin):  xr*cos - xi*sin = dp2a.lo(x, Bre) + 256 * dp2a.hi(x, Bre)
+//   Bim = bytes {s0, c0, s1, c1}            :  xr*sin + xi*cos = dp2a.lo(x, Bim) + 256 * dp2a.hi(x, Bim)
+// exactly the int32 products of dsp_complex.cpp:31-37, with no unpacking of x or of the table entry: the
+// multiply pipe (IMAD / IDP, 64 lanes/clk) takes 6 instructions per sample and the ALU pipe (PRMT / SHF / I2IP /
+// VIMNMX, also 64 lanes/clk, the binding one -- tools/pipebench.cu) only the 2 shifts, the saturating pack and
+// the symmetric clamp (+ the 2 PRMT of the byte-plane split).
+__device__ __forceinline__ uint32_t mix_sample_dp2a(uint32_t x, uint32_t bre, uint32_t bim)
 {
-    const uint4 c = lds128<0>(lo + idx4);
-    q.x = mix_sample_packed(q.x, c.x);
-    q.y = mix_sample_packed(q.y, c.y);
-    q.z = mix_sample_packed(q.z, c.z);
-    q.w = mix_sample_packed(q.w, c.w);
+    const int r = __dp2a_lo((int)x, (int)bre, __dp2a_hi((int)x, (int)bre, 0) * 256) >> 14;
+    const int i = __dp2a_lo((int)x, (int)bim, __dp2a_hi((int)x, (int)bim, 0) * 256) >> 14;
+    uint32_t p;
+    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(p) : "r"(i), "r"(r));  // {hi = sat(i), lo = sat(r)}
+    return __vmaxs2(p, 0x80018001u);  // limitScale16's symmetric clamp (dsp_complex.cpp:63-73)
+}
+// digits of one table entry cs = packed (cos, sin)
+__device__ __forceinline__ void mix_digits(uint32_t cs, uint32_t &bre, uint32_t &bim)
+{
+    const int c = sx_lo(cs), s = sx_hi(cs), n = -s;
+    const int c0 = ((c + 128) & 255) - 128, c1 = (c - c0) >> 8;
+    const int s0 = ((s + 128) & 255) - 128, s1 = (s - s0) >> 8;
+    const int n0 = ((n + 128) & 255) - 128, n1 = (n - n0) >> 8;
+    bre = (uint32_t)(c0 & 255) | ((uint32_t)(n0 & 255) << 8) | ((uint32_t)(c1 & 255) << 16) | ((uint32_t)(n1 & 255) << 24);
+    bim = (uint32_t)(s0 & 255) | ((uint32_t)(c0 & 255) << 8) | ((uint32_t)(s1 & 255) << 16) | ((uint32_t)(c1 & 255) << 24);
+}
+
+// The 4 samples of a piece.  lo = shared address of the channel's oscillator sequence in TIME order: two
+// arrays of N words, Bre[n] and Bim[n] for phase (phi0 + n * freq) mod N, n < N (the sequence has period N).
+// A piece takes two conflict-free LDS.128 instead of 4 gathers from the sine table, whose stride (the channel
+// frequency) makes the lanes collide on a few banks.  idx4 = (n mod N) * 4 of the piece's first sample.
+__device__ __forceinline__ void tma_mix4_with(uint4 &q, const uint4 &a, const uint4 &b)
+{
+    q.x = mix_sample_dp2a(q.x, a.x, b.x);
+    q.y = mix_sample_dp2a(q.y, a.y, b.y);
+    q.z = mix_sample_dp2a(q.z, a.z, b.z);
+    q.w = mix_sample_dp2a(q.w, a.w, b.w);
+}
+__device__ __forceinline__ void tma_mix4(uint4 &q, uint32_t lo, unsigned idx4, unsigned im_off)
+{
+    const uint4 a = lds128<0>(lo + idx4);
+    const uint4 b = lds128<0>(lo + im_off + idx4);
+    tma_mix4_with(q, a, b);
 }
 
 // one group of 4 rows: this lane's 16-byte piece -> its 4 byte-plane words
@@ -106,10 +138,10 @@ __device__ __forceinline__ void tma_convert4(uint32_t src, uint32_t dst_lo, uint
 {
     uint4 v0 = lds128<0>(src), v1 = lds128<W * 512>(src), v2 = lds128<2 * W * 512>(src), v3 = lds128<3 * W * 512>(src);
     if (MIX) {
-        tma_mix4(v0, lo, idx4);
-        tma_mix4(v1, lo, (idx4 + didx4) & mask4);
-        tma_mix4(v2, lo, (idx4 + 2 * didx4) & mask4);
-        tma_mix4(v3, lo, (idx4 + 3 * didx4) & mask4);
+        tma_mix4(v0, lo, idx4, mask4 + 4);
+        tma_mix4(v1, lo, (idx4 + didx4) & mask4, mask4 + 4);
+        tma_mix4(v2, lo, (idx4 + 2 * didx4) & mask4, mask4 + 4);
+        tma_mix4(v3, lo, (idx4 + 3 * didx4) & mask4, mask4 + 4);
     }
     tma_split_store<0>(v0, dst_lo, dst_hi);
     tma_split_store<W * 128>(v1, dst_lo, dst_hi);
@@ -122,24 +154,9 @@ __device__ __forceinline__ void tma_convert4(uint32_t src, uint32_t dst_lo, uint
 // multiple of 32 -- the groups see the same oscillator values, which are then fetched and unpacked once
 // per K-step instead of once per piece.
 struct MixPiece {
-    int c[4], s[4];
+    uint4 re, im;  // Bre / Bim digit words of the 4 samples of the piece
 };
-__device__ __forceinline__ uint32_t mix_sample_unpacked(uint32_t x, int c, int s)
-{
-    const int xr = sx_lo(x), xi = sx_hi(x);
-    const int r = (xr * c - xi * s) >> 14;  // dsp_complex.cpp:31-37, mixers.h:175-176
-    const int i = (xi * c + s * xr) >> 14;
-    uint32_t p;
-    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(p) : "r"(i), "r"(r));
-    return __vmaxs2(p, 0x80018001u);  // limitScale16's symmetric clamp (dsp_complex.cpp:63-73)
-}
-__device__ __forceinline__ void tma_mix4_same(uint4 &q, const MixPiece &m)
-{
-    q.x = mix_sample_unpacked(q.x, m.c[0], m.s[0]);
-    q.y = mix_sample_unpacked(q.y, m.c[1], m.s[1]);
-    q.z = mix_sample_unpacked(q.z, m.c[2], m.s[2]);
-    q.w = mix_sample_unpacked(q.w, m.c[3], m.s[3]);
-}
+__device__ __forceinline__ void tma_mix4_same(uint4 &q, const MixPiece &m) { tma_mix4_with(q, m.re, m.im); }
 template <int W>
 __device__ __forceinline__ void tma_convert4_same(uint32_t src, uint32_t dst_lo, uint32_t dst_hi, const MixPiece &m)
 {
@@ -154,16 +171,16 @@ __device__ __forceinline__ void tma_convert4_same(uint32_t src, uint32_t dst_lo,
     tma_split_store<3 * W * 128>(v3, dst_lo, dst_hi);
 }
 
-// generic-pointer variant for the edge path (tab = the oscillator sequence, p0 = n mod N, fr = 1)
+// generic-pointer variant for the edge path (tab = the oscillator sequence Bre[N] ++ Bim[N], p0 = n mod N)
 template <bool MIX>
-__device__ __forceinline__ void tma_convert_store(uint4 q, uint8_t *dst, int hi_off, const uint32_t *tab, unsigned p0, unsigned fr,
-                                                  unsigned mask)
+__device__ __forceinline__ void tma_convert_store(uint4 q, uint8_t *dst, int hi_off, const uint32_t *tab, unsigned p0, unsigned mask)
 {
     if (MIX) {  // mixers.h:172-177 on the 4 samples of this piece
-        q.x = mix_sample_packed(q.x, tab[p0]);
-        q.y = mix_sample_packed(q.y, tab[(p0 + fr) & mask]);
-        q.z = mix_sample_packed(q.z, tab[(p0 + 2 * fr) & mask]);
-        q.w = mix_sample_packed(q.w, tab[(p0 + 3 * fr) & mask]);
+        const uint32_t *im = tab + mask + 1;
+        q.x = mix_sample_dp2a(q.x, tab[p0], im[p0]);
+        q.y = mix_sample_dp2a(q.y, tab[(p0 + 1) & mask], im[(p0 + 1) & mask]);
+        q.z = mix_sample_dp2a(q.z, tab[(p0 + 2) & mask], im[(p0 + 2) & mask]);
+        q.w = mix_sample_dp2a(q.w, tab[(p0 + 3) & mask], im[(p0 + 3) & mask]);
     }
     uint32_t re_lo, re_hi, im_lo, im_hi;
     split4(q, re_lo, re_hi, im_lo, im_hi);
@@ -296,8 +313,12 @@ __global__ void __launch_bounds__(MIX ? 32 * (TMA_CONV_WARP0 + TMA_MAX_CONV_MIX)
                         ph0 = (unsigned)P.phi[ch];
                         fr = (unsigned)P.freq[ch];
                         asm volatile("bar.sync 1, %0;" ::"r"(NCW * 32) : "memory");
-                        for (unsigned i = cw * 32 + lane; i <= P.mix_mask; i += NCW * 32)
-                            tab_smem[i] = __ldg(P.cs_table + ((ph0 + i * fr) & P.mix_mask));
+                        for (unsigned i = cw * 32 + lane; i <= P.mix_mask; i += NCW * 32) {
+                            uint32_t bre, bim;
+                            mix_digits(__ldg(P.cs_table + ((ph0 + i * fr) & P.mix_mask)), bre, bim);
+                            tab_smem[i] = bre;
+                            tab_smem[P.mix_mask + 1 + i] = bim;
+                        }
                         asm volatile("bar.sync 1, %0;" ::"r"(NCW * 32) : "memory");
                         cur_ch = (int)ch;
                     }
@@ -307,6 +328,11 @@ __global__ void __launch_bounds__(MIX ? 32 * (TMA_CONV_WARP0 + TMA_MAX_CONV_MIX)
                 }
                 cur_tile = tile;
             }
+            // A raw stage shared by several groups (n_raw not a multiple of the group count): TMA boxes land out
+            // of order, so another group's previous use of this stage may not even have landed yet, and the
+            // parity wait below would then pass a whole phase early.  Waiting first until that use has been
+            // released (the phase before ours of the "empty" barrier; passes at once on a fresh barrier) closes it.
+            if (X.shared_raw) mbar_wait_acc<DBG>(bar_rempty + 8 * rs, rpar ^ 1, P.error_flag, w_wait_raw);
             mbar_wait_acc<DBG>(bar_rfull + 8 * rs, rpar, P.error_flag, w_wait_raw);
             mbar_wait_acc<DBG>(bar_empty + 8 * ss, spar, P.error_flag, w_wait_split);
             if (P.debug & 8) {
@@ -316,12 +342,9 @@ __global__ void __launch_bounds__(MIX ? 32 * (TMA_CONV_WARP0 + TMA_MAX_CONV_MIX)
                 const uint32_t dst = dst_main + ss * stage_bytes;
                 const unsigned idx4 = MIX ? ((n_lane + 32 * kc) & P.mix_mask) << 2 : 0u;
                 if (MIX && didx4 == 0) {
-                    const uint4 cs = lds128<0>(tab_u32 + idx4);
                     MixPiece m;
-                    m.c[0] = sx_lo(cs.x), m.s[0] = sx_hi(cs.x);
-                    m.c[1] = sx_lo(cs.y), m.s[1] = sx_hi(cs.y);
-                    m.c[2] = sx_lo(cs.z), m.s[2] = sx_hi(cs.z);
-                    m.c[3] = sx_lo(cs.w), m.s[3] = sx_hi(cs.w);
+                    m.re = lds128<0>(tab_u32 + idx4);
+                    m.im = lds128<0>(tab_u32 + mask4 + 4 + idx4);
                     tma_convert4_same<W>(src, dst, dst + hi_off, m);
                     if (W == 4) tma_convert4_same<W>(src + 16 * 512, dst + 16 * 128, dst + 16 * 128 + hi_off, m);
                 } else {
@@ -337,7 +360,7 @@ __global__ void __launch_bounds__(MIX ? 32 * (TMA_CONV_WARP0 + TMA_MAX_CONV_MIX)
                     for (int q = 0; q < HQ; ++q) {
                         const uint4 v = *reinterpret_cast<const uint4 *>(hsrc + q * 512);
                         const long long n = tile0 + (long long)(4 * q + grp - halo_rows4) * P.G + 32 * kc + 4 * piece;
-                        tma_convert_store<MIX>(v, hdst + q * 128, hi_off, tab_smem, (unsigned)n & P.mix_mask, 1u, P.mix_mask);
+                        tma_convert_store<MIX>(v, hdst + q * 128, hi_off, tab_smem, (unsigned)n & P.mix_mask, P.mix_mask);
                     }
                 }
             } else {
@@ -364,12 +387,12 @@ __global__ void __launch_bounds__(MIX ? 32 * (TMA_CONV_WARP0 + TMA_MAX_CONV_MIX)
                             v.z = tc_sample(x, hist, P.H, P.n_in, n + 2);
                             v.w = tc_sample(x, hist, P.H, P.n_in, n + 3);
                         }
-                        tma_convert_store<false>(v, dst + q * 128, hi_off, tab_smem, 0, 0, 0);
+                        tma_convert_store<false>(v, dst + q * 128, hi_off, tab_smem, 0, 0);
                         continue;
                     } else {
                         v = *reinterpret_cast<const uint4 *>(src + q * 512);
                     }
-                    tma_convert_store<MIX>(v, dst + q * 128, hi_off, tab_smem, (unsigned)n & P.mix_mask, 1u, P.mix_mask);
+                    tma_convert_store<MIX>(v, dst + q * 128, hi_off, tab_smem, (unsigned)n & P.mix_mask, P.mix_mask);
                 }
             }
             // the MMA reads shared memory through the async proxy: fence this warp's stores, then
