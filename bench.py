@@ -49,6 +49,8 @@ WORKLOADS = {
     "cfg5": dict(kind="dec", channels=1, n=1 << 29, M=4, ntaps=1023, mix=False,
                  desc="cfg5 slice: decimate-by-4 1023-tap FIR, one stream slice of 512Mi samples per GPU"),
     "mid": dict(kind="dec", channels=64, n=1 << 22, M=16, ntaps=255, mix=False, desc="mid: 64 ch x 4Mi, /16, 255 taps"),
+    "fifo": dict(kind="fifo", channels=1, n=1 << 22, M=16, ntaps=255, mix=False, blocks=24,
+                 desc="fifo: one stream through FifoWithTimeTrack (pinned ring, 16Mi samples) -> decimate-by-16 255-tap FIR, 4Mi-sample blocks"),
     "smoke": dict(kind="dec", channels=8, n=1 << 18, M=16, ntaps=255, mix=False, desc="smoke: 8 ch x 256Ki"),
 }
 
@@ -154,6 +156,64 @@ def cpu_reference_run(w, steps: int, warmup: int, cores: int, target_cpu_seconds
                 seconds=t), t
 
 
+def fifo_stream_bench(args, w, base, S, O, torch, device):
+    """a producer thread writes time-stamped blocks into the pinned FifoWithTimeTrack, the
+    consumer takes zero-copy segments of the ring and runs the decimator on them (H2D DMA straight from the ring,
+    D2H of the outputs).  End-to-end by construction: value == e2e."""
+    n, M, nt, blocks = w["n"], w["M"], w["ntaps"], w["blocks"]
+    fifo = S.FifoWithTimeTrack(4 * n, 1e8)
+    dec = S.FilterDnsamplingFir(M, O.design_lowpass_taps(nt, M), channels=1, device=device, obsolete=True)
+    src = S.PinnedBuffer(1, n)
+    src.array[0] = O.corc().synth(SEED, 0, 0, n, 2)
+    out = S.PinnedBuffer(1, n // M)
+    total = args.warmup + args.steps * blocks
+    state = {"written": 0, "stop": False}
+
+    def producer():
+        for b in range(total):
+            while state["written"] - state.get("read", 0) >= 3 and not state["stop"]:
+                time.sleep(0)
+            fifo.write(src.array[0], seconds=b, fracSeconds=0.0)
+            state["written"] = b + 1
+
+    th = threading.Thread(target=producer, daemon=True)
+    th.start()
+    start, done, t0 = 1, 0, None
+    sampler = ClockSampler(device)
+    for b in range(total):
+        if b == args.warmup:
+            torch.cuda.synchronize()
+            sampler.start()
+            l0 = S.launch_count()
+            t0 = time.perf_counter()
+        while state["written"] <= b:
+            time.sleep(0)
+        err, st, segs = fifo.readSegments(n, start)
+        assert not err and st == start, (err, st, start)
+        pos = 0
+        for sgm in segs:  # one piece, or two when the block wraps around the end of the ring (multiples of M here)
+            dec.step(sgm, out=out.array[0, pos // M: (pos + sgm.shape[0]) // M])
+            pos += sgm.shape[0]
+        start += n
+        state["read"] = b + 1
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    launches = S.launch_count() - l0
+    state["stop"] = True
+    th.join()
+    n_out = args.steps * blocks * (n // M)
+    value = n_out / dt / 1e6
+    line = dict(base, value=value, ms_per_step=dt / args.steps * 1e3, roofline=None, cpu_baseline=None,
+                e2e={"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": blocks * n * 4, "d2h_bytes_per_step": blocks * n // M * 4,
+                     "api": "FifoWithTimeTrack.write (producer thread) -> readSegments -> FilterDnsamplingFir.step(pinned ring views)"},
+                clocks=clocks, gpu_launches=int(launches), impl="ours")
+    line["config"]["note"] = (f"one step = {blocks} blocks of {n} samples; host memcpy into the ring + PCIe bound, "
+                              f"ring pinned: {fifo.pinned}")
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -208,6 +268,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     C, n, M, nt = w["channels"], w["n"], w["M"], w["ntaps"]
+    if w["kind"] == "fifo":
+        return fifo_stream_bench(args, w, base, S, O, torch, local_rank)
     from srcdsp_b200.sharding import channel_shard
     my_ch = channel_shard(C * world, world, rank)  # weak scaling: 256 channels per GPU
     n_out = int(n * out_per_in(w))

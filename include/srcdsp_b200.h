@@ -43,6 +43,7 @@ typedef struct srcdsp_mixer_s *srcdsp_mixer_t;
 typedef struct srcdsp_dec_s *srcdsp_dec_t;
 typedef struct srcdsp_up_s *srcdsp_up_t;
 typedef struct srcdsp_ddc_s *srcdsp_ddc_t;
+typedef struct srcdsp_fifo_s *srcdsp_fifo_t;
 
 /* ------------------------------------------------------------------------------------------ */
 /* library                                                                                    */
@@ -160,6 +161,34 @@ int srcdsp_up_get_state(srcdsp_up_t h, int ch, int16_t *history_iq, size_t *n_sa
 int srcdsp_up_set_state(srcdsp_up_t h, int ch, const int16_t *history_iq, size_t n_samples);
 int srcdsp_up_set_stream(srcdsp_up_t h, void *cuda_stream);
 int srcdsp_up_sync(srcdsp_up_t h);
+
+/* ------------------------------------------------------------------------------------------ */
+/* FifoWithTimeTrack<T, N> -- buffers.h:58-459: single-writer / single-reader ring with sample  */
+/* time stamps, here in PINNED host memory so that a block can be DMA'd straight out of the    */
+/* ring.  Elements are opaque (elem_bytes each).  Host code only; falls    */
+/* back to ordinary memory when there is no CUDA device (bookkeeping, not compute).            */
+/* ctor: buffers.h:62-65 */
+int srcdsp_fifo_create(srcdsp_fifo_t *h, size_t elem_bytes, size_t capacity, double sampling_frequency);
+int srcdsp_fifo_destroy(srcdsp_fifo_t h);
+int srcdsp_fifo_is_pinned(srcdsp_fifo_t h);
+/* write: buffers.h:139-217 (n < capacity, else E_SIZE -- the reference asserts) */
+int srcdsp_fifo_write(srcdsp_fifo_t h, const void *in, size_t n, unsigned seconds, double frac_seconds);
+/* read: buffers.h:284-352.  *start may be moved up to the first available time point (the reference
+ * warns on stderr); *error = the reference's return value: 1 when [start, start+n) is not available. */
+int srcdsp_fifo_read(srcdsp_fifo_t h, void *out, size_t n, uint64_t *start, int *error);
+/* the same range without the copy: at most two contiguous pieces of the (pinned) ring */
+int srcdsp_fifo_segments(srcdsp_fifo_t h, size_t n, uint64_t *start, const void **p0, size_t *n0, const void **p1,
+                         size_t *n1, int *error);
+/* count: buffers.h:361-377; reset: :262-276; getAbsoluteTime: :396-459 */
+int srcdsp_fifo_count(srcdsp_fifo_t h, size_t *count);
+int srcdsp_fifo_reset(srcdsp_fifo_t h);
+int srcdsp_fifo_get_absolute_time(srcdsp_fifo_t h, uint64_t time_point, double frac_time_point, unsigned *seconds,
+                                  double *frac_seconds);
+/* writePtr, timeStart, timeEnd, rolloverFlag: what dumpInfo prints (buffers.h:227-251) */
+int srcdsp_fifo_get_state(srcdsp_fifo_t h, size_t *write_ptr, uint64_t *time_start, uint64_t *time_end, int *rollover);
+/* test hook: move the time counters (e.g. next to the 64-bit rollover) */
+int srcdsp_fifo_set_time(srcdsp_fifo_t h, uint64_t time_start, uint64_t time_end);
+const void *srcdsp_fifo_storage(srcdsp_fifo_t h);
 
 #ifdef __cplusplus
 }

@@ -193,6 +193,27 @@ class _RefLib:
         L.ref_bench_bank.argtypes = [C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_int, _i16p, _i16p,
                                      C.c_int, _i32p, C.c_int, C.c_int, _i32p, C.c_int, _f32p]
         L.ref_build_info.restype = C.c_char_p
+        # fifo, binary files, correlator
+        L.ref_fifo_create.restype = vp
+        L.ref_fifo_create.argtypes = [C.c_size_t, C.c_double]
+        L.ref_fifo_destroy.argtypes = [vp]
+        L.ref_fifo_write.argtypes = [vp, _i16p, C.c_size_t, C.c_uint, C.c_double]
+        L.ref_fifo_read.argtypes = [vp, _i16p, C.c_size_t, C.POINTER(C.c_uint64)]
+        L.ref_fifo_count.restype = C.c_size_t
+        L.ref_fifo_count.argtypes = [vp]
+        L.ref_fifo_reset.argtypes = [vp]
+        L.ref_fifo_abs_time.argtypes = [vp, C.c_uint64, C.c_double, C.POINTER(C.c_uint), C.POINTER(C.c_double)]
+        L.ref_save_binary.argtypes = [C.c_char_p, _i16p, C.c_size_t]
+        L.ref_read_binary.restype = C.c_size_t
+        L.ref_read_binary.argtypes = [C.c_char_p, _i16p, C.c_size_t, C.c_size_t]
+        L.ref_corr_create.restype = vp
+        L.ref_corr_create.argtypes = [C.c_int, C.c_int]
+        L.ref_corr_destroy.argtypes = [vp]
+        L.ref_corr_set_pattern.argtypes = [vp, _i32p, C.c_double]
+        L.ref_corr_reset.argtypes = [vp]
+        L.ref_corr_step.argtypes = [vp, _i16p, C.c_size_t, C.POINTER(C.c_int)]
+        L.ref_corr_bits.argtypes = [vp, _i16p, C.c_size_t]
+        L.ref_corr_status.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_int)]
 
     def build_info(self) -> str:
         return self.lib.ref_build_info().decode()
@@ -343,6 +364,117 @@ class RefUpsampler:
 
 
 _ref = {}
+
+
+class RefFifo:
+    """The reference's FifoWithTimeTrack<cs16, N> (capacities compiled into ref_harness.cpp: 16, 100, 1024, 65536)."""
+
+    def __init__(self, lib: _RefLib, capacity: int, fs: float = 0.0):
+        self._l = lib.lib
+        self._h = self._l.ref_fifo_create(capacity, fs)
+        if not self._h:
+            raise ValueError(f"ref_harness.cpp has no FifoWithTimeTrack<cs16, {capacity}>")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._l.ref_fifo_destroy(self._h)
+            self._h = None
+
+    def write(self, x, seconds=0, frac=0.0):
+        x = np.ascontiguousarray(x, np.int16).reshape(-1, 2)
+        self._l.ref_fifo_write(self._h, _p16(x), x.shape[0], seconds, frac)
+
+    def read(self, n, start):
+        out = np.zeros((n, 2), np.int16)
+        st = C.c_uint64(start)
+        err = self._l.ref_fifo_read(self._h, _p16(out), n, C.byref(st))
+        return bool(err), st.value, (None if err else out)
+
+    def count(self):
+        return int(self._l.ref_fifo_count(self._h))
+
+    def reset(self):
+        self._l.ref_fifo_reset(self._h)
+
+    def getAbsoluteTime(self, tp, frac=0.0):
+        s, f = C.c_uint(), C.c_double()
+        self._l.ref_fifo_abs_time(self._h, tp, frac, C.byref(s), C.byref(f))
+        return s.value, f.value
+
+
+class PyFifo:
+    """Plain-Python restatement of FifoWithTimeTrack's bookkeeping (buffers.h:139-217, 262-276, 284-352,
+    361-377, 396-459).  TEST INFRASTRUCTURE ONLY."""
+    U64 = (1 << 64) - 1
+
+    def __init__(self, capacity: int, fs: float = 0.0):
+        self.N, self.fs = capacity, fs
+        self.storage = np.zeros((capacity, 2), np.int16)
+        self.writePtr = self.timeStart = self.timeEnd = 0
+        self.rollover = False
+        self.ref = (0, 0, 0.0)
+
+    def write(self, x, seconds=0, frac=0.0):  # buffers.h:139-217
+        x = np.asarray(x, np.int16).reshape(-1, 2)
+        n, N = x.shape[0], self.N
+        assert n < N
+        idx = (self.writePtr + np.arange(n)) % N
+        self.storage[idx] = x
+        self.writePtr = (self.writePtr + n) % N
+        diff = self.U64 - self.timeEnd
+        self.ref = ((self.timeEnd + 1) & self.U64, seconds, frac)
+        if diff >= n:
+            self.timeEnd += n
+        else:
+            self.timeEnd = n - diff
+            self.rollover = True
+        if not self.rollover:
+            self.timeStart = self.timeEnd - N + 1 if (self.timeEnd - self.timeStart + 1) > N else 1
+        else:
+            d2 = self.U64 - self.timeStart
+            self.timeStart = self.timeStart + n if d2 >= n else n - d2
+            self.rollover = False
+
+    def read(self, n, start):  # buffers.h:284-352
+        if start < self.timeStart:
+            start = self.timeStart
+        if ((start + n - 1) & self.U64) > self.timeEnd:
+            return True, start, None
+        sp = (self.writePtr + self.N - (self.timeEnd - start) - 1) % self.N
+        return False, start, self.storage[(sp + np.arange(n)) % self.N].copy()
+
+    def count(self):  # buffers.h:361-377
+        if not self.rollover:
+            return ((self.timeEnd - self.timeStart) + 1) & self.U64
+        return ((self.U64 - self.timeStart) + self.timeEnd + 1) & self.U64
+
+    def reset(self):  # buffers.h:262-276
+        self.writePtr = self.timeStart = self.timeEnd = 0
+        self.rollover = False
+
+    def getAbsoluteTime(self, tp, frac=0.0):  # buffers.h:396-459
+        import math
+        d = (tp - self.ref[0]) & self.U64
+        if d >= 1 << 63:
+            d -= 1 << 64
+        td = d / self.fs
+        ti = int(math.floor(td))
+        s = (self.ref[1] + ti) & 0xFFFFFFFF
+        fr = self.ref[2] + (td - math.floor(td)) + frac / self.fs
+        t = int(fr)
+        return (s + t) & 0xFFFFFFFF, fr - t
+
+
+def ref_save_binary(lib: _RefLib, path: str, x: np.ndarray):
+    x = np.ascontiguousarray(x, np.int16).reshape(-1, 2)
+    lib.lib.ref_save_binary(path.encode(), _p16(x), x.shape[0])
+
+
+def ref_read_binary(lib: _RefLib, path: str, cap: int, prefill: int = 0) -> np.ndarray:
+    """What the reference's readBinarySamples leaves in a vector that held `prefill` elements (7, -7)."""
+    out = np.zeros((cap, 2), np.int16)
+    n = lib.lib.ref_read_binary(path.encode(), _p16(out), cap, prefill)
+    return out[: min(n, cap)], n
 
 
 def ref(opt: str = "O2"):

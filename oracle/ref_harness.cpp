@@ -11,6 +11,9 @@
  *   (obsolete twin, no taps%M assert)                         dnsampling_filters.h:43-172
  *   dsptl::FilterUpsamplingFir<cs16,cs16,cs32,int32_t,L>      upsampling_filters.h:35-323
  *   FilterFir<cs16,cs16,cs32,int32_t>                         filters.h:42-169
+ *   dsptl::FifoWithTimeTrack<cs16,N>                          buffers.h:58-459
+ *   dsptl::saveBinarySamples / readBinarySamples              dsptl_files.h:57-109, 250-262
+ *   dsptl::FixedPatternCorrelator<int16_t,int32_t,N,S>        correlators.h:54-303
  *
  * The two decimator headers share an include guard and a class name, so the obsolete one is
  * included inside namespace ref_obsolete (its std/dsp_complex includes are already satisfied).
@@ -39,6 +42,9 @@ namespace ref_obsolete {
 #include "mixers.h"
 #include "upsampling_filters.h"
 #include "filters.h"
+#include "buffers.h"
+#include "dsptl_files.h"
+#include "correlators.h"
 
 typedef std::complex<int16_t> cs16;
 typedef std::complex<int32_t> cs32;
@@ -332,6 +338,138 @@ double ref_bench_bank(int kind, int C, size_t n_per_ch, size_t block_len, int n_
     }
     return secs;
 }
+
+// ---------------------------------------------------------------------------------------------
+// FifoWithTimeTrack<cs16, N> for the capacities the tests use (N is a template parameter)
+extern "C++" {
+struct FifoBase {
+    virtual ~FifoBase() {}
+    virtual void write(std::vector<cs16> &in, unsigned s, double f) = 0;
+    virtual bool read(std::vector<cs16> &out, uint64_t &start) = 0;
+    virtual size_t count() = 0;
+    virtual void reset() = 0;
+    virtual std::pair<unsigned, double> abs_time(uint64_t tp, double f) = 0;
+};
+template <size_t N>
+struct FifoImpl : FifoBase {
+    dsptl::FifoWithTimeTrack<cs16, N> f;
+    explicit FifoImpl(double fs) : f(fs) {}
+    void write(std::vector<cs16> &in, unsigned s, double fr) override { f.write(in, s, fr); }
+    bool read(std::vector<cs16> &out, uint64_t &start) override { return f.read(out, start); }
+    size_t count() override { return f.count(); }
+    void reset() override { f.reset(); }
+    std::pair<unsigned, double> abs_time(uint64_t tp, double fr) override { return f.getAbsoluteTime(tp, fr); }
+};
+}  // extern "C++"
+
+void *ref_fifo_create(size_t capacity, double fs)
+{
+    switch (capacity) {
+    case 16: return new FifoImpl<16>(fs);
+    case 100: return new FifoImpl<100>(fs);
+    case 1024: return new FifoImpl<1024>(fs);
+    case 65536: return new FifoImpl<65536>(fs);
+    default: return nullptr;
+    }
+}
+void ref_fifo_destroy(void *h) { delete static_cast<FifoBase *>(h); }
+void ref_fifo_write(void *h, const int16_t *iq, size_t n, unsigned s, double f)
+{
+    std::vector<cs16> v(n);
+    if (n) std::memcpy(v.data(), iq, n * sizeof(cs16));
+    static_cast<FifoBase *>(h)->write(v, s, f);
+}
+int ref_fifo_read(void *h, int16_t *iq, size_t n, uint64_t *start)
+{
+    std::vector<cs16> v(n);
+    const bool err = static_cast<FifoBase *>(h)->read(v, *start);
+    if (!err) std::memcpy(iq, v.data(), n * sizeof(cs16));
+    return err ? 1 : 0;
+}
+size_t ref_fifo_count(void *h) { return static_cast<FifoBase *>(h)->count(); }
+void ref_fifo_reset(void *h) { static_cast<FifoBase *>(h)->reset(); }
+void ref_fifo_abs_time(void *h, uint64_t tp, double f, unsigned *s, double *fr)
+{
+    auto r = static_cast<FifoBase *>(h)->abs_time(tp, f);
+    *s = r.first;
+    *fr = r.second;
+}
+
+// ---------------------------------------------------------------------------------------------
+// binary sample files (dsptl_files.h)
+void ref_save_binary(const char *path, const int16_t *iq, size_t n)
+{
+    std::vector<cs16> v(n);
+    if (n) std::memcpy(v.data(), iq, n * sizeof(cs16));
+    std::ofstream os(path, std::ios::binary);
+    dsptl::saveBinarySamples(v, os);
+}
+// returns the number of elements readBinarySamples produced when appending to `prefill` existing elements
+size_t ref_read_binary(const char *path, int16_t *iq, size_t cap, size_t prefill)
+{
+    std::vector<cs16> v(prefill, cs16(7, -7));
+    std::ifstream is(path, std::ios::binary);
+    dsptl::readBinarySamples(is, v);
+    const size_t n = v.size() < cap ? v.size() : cap;
+    if (n) std::memcpy(iq, v.data(), n * sizeof(cs16));
+    return v.size();
+}
+
+// ---------------------------------------------------------------------------------------------
+// FixedPatternCorrelator<int16_t, int32_t, N, S>
+extern "C++" {
+struct CorrBase {
+    virtual ~CorrBase() {}
+    virtual void set_pattern(const int32_t *iq, double thr) = 0;
+    virtual bool step(const std::vector<cs16> &in, int &idx) = 0;
+    virtual void reset() = 0;
+    virtual std::vector<cs16> bits() = 0;
+    virtual void status(uint32_t *energy3, uint32_t *corr3, uint32_t *coeffs_energy, int *coeff_scaling) = 0;
+};
+template <size_t N, size_t S>
+struct CorrImpl : CorrBase {
+    dsptl::FixedPatternCorrelator<int16_t, int32_t, N, S> c;
+    void set_pattern(const int32_t *iq, double thr) override
+    {
+        std::array<cs32, N> p;
+        for (size_t k = 0; k < N; ++k) p[k] = cs32(iq[2 * k], iq[2 * k + 1]);
+        c.setPattern(p, thr);
+    }
+    bool step(const std::vector<cs16> &in, int &idx) override { return c.step(in, idx); }
+    void reset() override { c.reset(); }
+    std::vector<cs16> bits() override { return c.getRefBitSamples(); }
+    void status(uint32_t *e3, uint32_t *c3, uint32_t *ce, int *cs) override
+    {
+        auto st = c.getStatus();
+        for (int k = 0; k < 3; ++k) e3[k] = st.energyValue[k], c3[k] = st.corrValue[k];
+        *ce = st.coeffsEnergy;
+        *cs = st.coeffScaling;
+    }
+};
+}  // extern "C++"
+void *ref_corr_create(int N, int S)
+{
+    if (N == 32 && S == 4) return new CorrImpl<32, 4>();
+    if (N == 16 && S == 2) return new CorrImpl<16, 2>();
+    if (N == 8 && S == 1) return new CorrImpl<8, 1>();
+    if (N == 64 && S == 8) return new CorrImpl<64, 8>();
+    return nullptr;
+}
+void ref_corr_destroy(void *h) { delete static_cast<CorrBase *>(h); }
+void ref_corr_set_pattern(void *h, const int32_t *iq, double thr) { static_cast<CorrBase *>(h)->set_pattern(iq, thr); }
+void ref_corr_reset(void *h) { static_cast<CorrBase *>(h)->reset(); }
+int ref_corr_step(void *h, const int16_t *iq, size_t n, int *corr_index)
+{
+    std::vector<cs16> v(n);
+    if (n) std::memcpy(v.data(), iq, n * sizeof(cs16));
+    return static_cast<CorrBase *>(h)->step(v, *corr_index) ? 1 : 0;
+}
+void ref_corr_bits(void *h, int16_t *iq, size_t n)
+{
+    auto b = static_cast<CorrBase *>(h)->bits();
+    std::memcpy(iq, b.data(), (b.size() < n ? b.size() : n) * sizeof(cs16));
+}
+void ref_corr_status(void *h, uint32_t *e3, uint32_t *c3, uint32_t *ce, int *cs) { static_cast<CorrBase *>(h)->status(e3, c3, ce, cs); }
 
 const char *ref_build_info()
 {

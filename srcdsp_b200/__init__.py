@@ -26,7 +26,8 @@ from . import _capi
 from ._capi import SrcDspError, check, lib
 
 __all__ = ["Mixer", "FilterDnsamplingFir", "FilterFir", "FilterUpsamplingFir", "Ddc", "SrcDspError",
-           "synth_fill", "launch_count", "device_count", "PinnedBuffer"]
+           "synth_fill", "launch_count", "device_count", "PinnedBuffer", "FifoWithTimeTrack", "saveBinarySamples",
+           "readBinarySamples"]
 
 
 # ----------------------------------------------------------------------------------------------
@@ -392,3 +393,92 @@ class PinnedBuffer:
             self.free()
         except Exception:
             pass
+
+
+# ----------------------------------------------------------------------------------------------
+# the stages either side of the GPU path
+# ----------------------------------------------------------------------------------------------
+class FifoWithTimeTrack(_Handle):
+    """dsptl::FifoWithTimeTrack<std::complex<int16_t>, N> (buffers.h:58-459): single-writer /
+    single-reader ring with sample time stamps, in pinned host memory (srcdsp_fifo_*).  Elements are
+    complex int16 samples, numpy int16 [n, 2]."""
+    _destroy = "srcdsp_fifo_destroy"
+
+    def __init__(self, capacity: int, samplingFrequency: float = 0.0):
+        super().__init__()
+        self.capacity = int(capacity)
+        check(lib().srcdsp_fifo_create(C.byref(self._h), 4, self.capacity, float(samplingFrequency)))
+
+    @property
+    def pinned(self) -> bool:
+        return bool(lib().srcdsp_fifo_is_pinned(self._h))
+
+    def write(self, x: np.ndarray, seconds: int = 0, fracSeconds: float = 0.0):
+        x = np.ascontiguousarray(x, dtype=np.int16).reshape(-1, 2)
+        check(lib().srcdsp_fifo_write(self._h, x.ctypes.data, x.shape[0], int(seconds), float(fracSeconds)))
+
+    def read(self, n: int, start: int):
+        """Returns (error, start, samples): `error` is the reference's return value (True: range not
+        available; samples is then None), `start` the possibly adjusted first time point."""
+        out = np.empty((n, 2), np.int16)
+        st, err = C.c_uint64(start), C.c_int()
+        check(lib().srcdsp_fifo_read(self._h, out.ctypes.data, n, C.byref(st), C.byref(err)))
+        return bool(err.value), st.value, (None if err.value else out)
+
+    def readSegments(self, n: int, start: int):
+        """Zero-copy read: (error, start, [views of the pinned ring]) -- at most two pieces."""
+        st, err = C.c_uint64(start), C.c_int()
+        p0, p1, n0, n1 = C.c_void_p(), C.c_void_p(), C.c_size_t(), C.c_size_t()
+        check(lib().srcdsp_fifo_segments(self._h, n, C.byref(st), C.byref(p0), C.byref(n0), C.byref(p1), C.byref(n1),
+                                         C.byref(err)))
+        segs = []
+        for p, k in ((p0, n0.value), (p1, n1.value)):
+            if k:
+                buf = (C.c_int16 * (2 * k)).from_address(p.value)
+                segs.append(np.frombuffer(buf, dtype=np.int16).reshape(k, 2))
+        return bool(err.value), st.value, segs
+
+    def count(self) -> int:
+        n = C.c_size_t()
+        check(lib().srcdsp_fifo_count(self._h, C.byref(n)))
+        return n.value
+
+    def reset(self):
+        check(lib().srcdsp_fifo_reset(self._h))
+
+    def getAbsoluteTime(self, timePoint: int, fracTimePoint: float = 0.0):
+        s, f = C.c_uint(), C.c_double()
+        check(lib().srcdsp_fifo_get_absolute_time(self._h, int(timePoint), float(fracTimePoint), C.byref(s), C.byref(f)))
+        return s.value, f.value
+
+    def state(self):
+        """(writePtr, timeStart, timeEnd, rolloverFlag): what dumpInfo prints."""
+        wp, ts, te, ro = C.c_size_t(), C.c_uint64(), C.c_uint64(), C.c_int()
+        check(lib().srcdsp_fifo_get_state(self._h, C.byref(wp), C.byref(ts), C.byref(te), C.byref(ro)))
+        return wp.value, ts.value, te.value, bool(ro.value)
+
+    def _set_time(self, timeStart: int, timeEnd: int):
+        check(lib().srcdsp_fifo_set_time(self._h, int(timeStart), int(timeEnd)))
+
+
+def saveBinarySamples(x: np.ndarray, path: str):
+    """dsptl::saveBinarySamples (dsptl_files.h:101-109): raw interleaved I/Q, no header."""
+    np.ascontiguousarray(x, dtype=np.int16).reshape(-1, 2).tofile(path)
+
+
+def readBinarySamples(path: str, out: Optional[np.ndarray] = None, exact: bool = False) -> np.ndarray:
+    """dsptl::readBinarySamples (dsptl_files.h:250-262) for complex int16.  Like the reference it APPENDS to
+    `out` (its `out.empty()` is a no-op) and, unless exact=True, adds one element after the last complete
+    sample: the reference's `while (is)` loop pushes once more with the values the failed read left behind
+    (the last sample, with the bytes of a trailing partial sample on top; (0, 0) for an empty file)."""
+    raw = np.fromfile(path, dtype=np.uint8)
+    n = raw.size // 4
+    x = raw[: 4 * n].view(np.int16).reshape(n, 2).copy()
+    if not exact:
+        last = (x[-1].copy() if n else np.zeros(2, np.int16)).view(np.uint8)
+        rest = raw[4 * n:]
+        last[: rest.size] = rest  # istream::read stores the bytes of a trailing partial sample it did get
+        x = np.concatenate([x, last.view(np.int16)[None, :]])
+    if out is not None and len(out):
+        x = np.concatenate([np.asarray(out, np.int16).reshape(-1, 2), x])
+    return x

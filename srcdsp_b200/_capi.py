@@ -78,6 +78,20 @@ PROTOTYPES = {
     "srcdsp_up_set_state": (C.c_int, [_vp, C.c_int, _i16p, _sz]),
     "srcdsp_up_set_stream": (C.c_int, [_vp, _vp]),
     "srcdsp_up_sync": (C.c_int, [_vp]),
+    # fifo (buffers.h)
+    "srcdsp_fifo_create": (C.c_int, [C.POINTER(_vp), _sz, _sz, C.c_double]),
+    "srcdsp_fifo_destroy": (C.c_int, [_vp]),
+    "srcdsp_fifo_is_pinned": (C.c_int, [_vp]),
+    "srcdsp_fifo_write": (C.c_int, [_vp, _vp, _sz, C.c_uint, C.c_double]),
+    "srcdsp_fifo_read": (C.c_int, [_vp, _vp, _sz, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
+    "srcdsp_fifo_segments": (C.c_int, [_vp, _sz, C.POINTER(C.c_uint64), C.POINTER(_vp), C.POINTER(_sz), C.POINTER(_vp),
+                                       C.POINTER(_sz), C.POINTER(C.c_int)]),
+    "srcdsp_fifo_count": (C.c_int, [_vp, C.POINTER(_sz)]),
+    "srcdsp_fifo_reset": (C.c_int, [_vp]),
+    "srcdsp_fifo_get_absolute_time": (C.c_int, [_vp, C.c_uint64, C.c_double, C.POINTER(C.c_uint), C.POINTER(C.c_double)]),
+    "srcdsp_fifo_get_state": (C.c_int, [_vp, C.POINTER(_sz), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
+    "srcdsp_fifo_set_time": (C.c_int, [_vp, C.c_uint64, C.c_uint64]),
+    "srcdsp_fifo_storage": (_vp, [_vp]),
 }
 
 _lib = None

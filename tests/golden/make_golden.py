@@ -101,3 +101,12 @@ if __name__ == "__main__":
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden.npz")
     np.savez_compressed(path, **arrays)
     print("wrote", path, os.path.getsize(path), "bytes; reference build:", O.ref().build_info())
+    # FifoWithTimeTrack<cs16, 1024>: a scripted trace of operations and the reference's answers
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_fifo_files as T
+    cap, seed = 1024, 11
+    ops = T._script(seed, cap, 500)
+    res = T._run(O.RefFifo(O.ref(), cap, 48000.0), ops, seed)
+    tp = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fifo_trace.npz")
+    np.savez_compressed(tp, capacity=cap, seed=seed, ops=np.array(ops, dtype=object), results=np.array(res, dtype=object))
+    print("wrote", tp, os.path.getsize(tp), "bytes,", len(ops), "operations")

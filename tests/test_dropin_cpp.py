@@ -9,14 +9,16 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "cpp", "user_chain.cpp")
 GOLDEN = os.path.join(ROOT, "tests", "golden", "user_chain.txt")
+SRC_STREAM = os.path.join(ROOT, "tests", "cpp", "user_stream.cpp")       # buffers.h + dsptl_files.h
+GOLDEN_STREAM = os.path.join(ROOT, "tests", "golden", "user_stream.txt")
 REF = "/root/reference"
 BUILD = os.path.join(ROOT, "build", "tests")
 
 
-def _compile_dropin(out):
+def _compile_dropin(out, src=SRC):
     os.makedirs(BUILD, exist_ok=True)
     lib = os.path.join(ROOT, "srcdsp_b200", "lib")
-    cmd = ["g++", "-std=gnu++11", "-O1", "-I" + os.path.join(ROOT, "include", "srcdsp"), SRC, "-o", out,
+    cmd = ["g++", "-std=gnu++11", "-O1", "-I" + os.path.join(ROOT, "include", "srcdsp"), src, "-o", out,
            "-L" + lib, "-lsrcdsp_b200", "-Wl,-rpath," + lib]
     subprocess.run(cmd, check=True, capture_output=True, text=True)
 
@@ -45,3 +47,26 @@ def test_dropin_build_prints_the_reference_output(built_lib):
     _compile_dropin(exe)
     out = subprocess.run([exe], check=True, capture_output=True, text=True, timeout=300).stdout
     assert out == open(GOLDEN).read()
+
+
+def test_stream_program_reference_build_matches_committed_golden(tmp_path):
+    """Pins tests/golden/user_stream.txt to the unmodified reference (build container only)."""
+    if not os.path.exists(os.path.join(REF, "buffers.h")):
+        pytest.skip("no /root/reference here")
+    os.makedirs(BUILD, exist_ok=True)
+    exe = os.path.join(BUILD, "user_stream_ref")
+    subprocess.run(["g++", "-std=gnu++11", "-O2", "-w", "-pthread", "-I" + REF, SRC_STREAM, "-o", exe], check=True,
+                   capture_output=True, text=True)
+    out = subprocess.run([exe, str(tmp_path / "ref.iq")], check=True, capture_output=True, text=True).stdout
+    if os.environ.get("SRCDSP_REGEN_GOLDEN"):
+        open(GOLDEN_STREAM, "w").write(out)
+    assert out == open(GOLDEN_STREAM).read()
+
+
+def test_stream_program_dropin_build_prints_the_reference_output(built_lib, tmp_path):
+    """FifoWithTimeTrack + binary files through the drop-in headers: host logic, runs with or without a GPU
+    (the ring is pinned when there is one)."""
+    exe = os.path.join(BUILD, "user_stream_gpu")
+    _compile_dropin(exe, SRC_STREAM)
+    out = subprocess.run([exe, str(tmp_path / "gpu.iq")], check=True, capture_output=True, text=True, timeout=120).stdout
+    assert out == open(GOLDEN_STREAM).read()
