@@ -44,6 +44,7 @@ typedef struct srcdsp_dec_s *srcdsp_dec_t;
 typedef struct srcdsp_up_s *srcdsp_up_t;
 typedef struct srcdsp_ddc_s *srcdsp_ddc_t;
 typedef struct srcdsp_fifo_s *srcdsp_fifo_t;
+typedef struct srcdsp_corr_s *srcdsp_corr_t;
 
 /* ------------------------------------------------------------------------------------------ */
 /* library                                                                                    */
@@ -189,6 +190,29 @@ int srcdsp_fifo_get_state(srcdsp_fifo_t h, size_t *write_ptr, uint64_t *time_sta
 /* test hook: move the time counters (e.g. next to the 64-bit rollover) */
 int srcdsp_fifo_set_time(srcdsp_fifo_t h, uint64_t time_start, uint64_t time_end);
 const void *srcdsp_fifo_storage(srcdsp_fifo_t h);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Correlator bank -- dsptl::FixedPatternCorrelator<int16_t, int32_t, N, S>  correlators.h:54-303 */
+/* (the stage behind the DDC): N-point correlation with a fixed pattern over */
+/* every S-th sample, 3-point peak test against the signal energy, stops at the first peak.      */
+/* ctor: correlators.h:124-133 (N <= 256, N * S <= 16384) */
+int srcdsp_corr_create(srcdsp_corr_t *h, int device, int channels, int N, int S);
+int srcdsp_corr_destroy(srcdsp_corr_t h);
+/* setPattern: correlators.h:167-194 -- pattern_iq = N complex int32 (not conjugated); E_SIZE when the
+ * energy exceeds 1073217600 (the reference asserts) */
+int srcdsp_corr_set_pattern(srcdsp_corr_t h, const int32_t *pattern_iq, double threshold_coeff);
+/* reset: correlators.h:143-155 */
+int srcdsp_corr_reset(srcdsp_corr_t h);
+/* step: correlators.h:209-303 per channel.  found[ch] = the return value, corr_index[ch] = corrIndex (only
+ * written when found).  Like the reference, the samples behind the detection are not consumed and the
+ * detection sample's slot is reused by the next call.  Synchronous (found / corr_index are host arrays). */
+int srcdsp_corr_step(srcdsp_corr_t h, const int16_t *in_iq, size_t in_stride, size_t n_per_ch, int *found, int *corr_index);
+/* getRefBitSamples: correlators.h:311-316 -- N complex int16 (host) */
+int srcdsp_corr_get_ref_bit_samples(srcdsp_corr_t h, int ch, int16_t *bits_iq);
+/* getStatus: correlators.h:58-82 (energyValue[3], corrValue[3], coeffsEnergy, coeffScaling, thresholdFactor) */
+int srcdsp_corr_get_status(srcdsp_corr_t h, int ch, uint32_t *energy_value3, uint32_t *corr_value3, uint32_t *coeffs_energy,
+                           int *coeff_scaling, double *threshold_factor);
+int srcdsp_corr_set_stream(srcdsp_corr_t h, void *cuda_stream);
 
 #ifdef __cplusplus
 }

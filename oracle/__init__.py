@@ -143,6 +143,90 @@ class _COracle:
 _corc = None
 
 
+class _OrcCorr(C.Structure):
+    _fields_ = [("N", C.c_int), ("S", C.c_int), ("top", C.c_int), ("coeff_scaling", C.c_int),
+                ("coeffs_energy", C.c_uint32), ("corr_value", C.c_uint32 * 3), ("energy_value", C.c_uint32 * 3),
+                ("threshold_factor", C.c_double), ("history", C.c_void_p), ("coeffs", C.c_void_p), ("bits", C.c_void_p)]
+
+
+class OrcCorrelator:
+    """Sequential C restatement of FixedPatternCorrelator<int16_t, int32_t, N, S> (oracle/srcdsp_oracle.c)."""
+
+    def __init__(self, oracle: "_COracle", N: int = 32, S: int = 4):
+        self._l = oracle.lib
+        self._l.orc_corr_step.argtypes = [C.POINTER(_OrcCorr), _i16p, C.c_size_t, C.POINTER(C.c_int)]
+        self._l.orc_corr_set_pattern.argtypes = [C.POINTER(_OrcCorr), _i32p, C.c_double]
+        self._c = _OrcCorr()
+        self.N, self.S = N, S
+        assert self._l.orc_corr_init(C.byref(self._c), N, S) == 0
+
+    def __del__(self):
+        if getattr(self, "_c", None) is not None and self._c.history:
+            self._l.orc_corr_free(C.byref(self._c))
+
+    def setPattern(self, pattern, thresholdCoeff=0.8):
+        p = np.ascontiguousarray(pattern, np.int32).reshape(self.N, 2)
+        if self._l.orc_corr_set_pattern(C.byref(self._c), _p32(p), thresholdCoeff) != 0:
+            raise ValueError("pattern energy above 1073217600 (correlators.h:183)")
+
+    def reset(self):
+        self._l.orc_corr_reset(C.byref(self._c))
+
+    def step(self, x):
+        x = np.ascontiguousarray(x, np.int16).reshape(-1, 2)
+        idx = C.c_int(0)
+        found = self._l.orc_corr_step(C.byref(self._c), _p16(x), x.shape[0], C.byref(idx))
+        return bool(found), idx.value
+
+    def getRefBitSamples(self):
+        return np.ctypeslib.as_array((C.c_int16 * (2 * self.N)).from_address(self._c.bits)).reshape(self.N, 2).copy()
+
+    def getStatus(self):
+        return dict(energyValue=list(self._c.energy_value), corrValue=list(self._c.corr_value),
+                    coeffsEnergy=self._c.coeffs_energy, coeffScaling=self._c.coeff_scaling,
+                    thresholdFactor=self._c.threshold_factor)
+
+
+class RefCorrelator:
+    """The reference's FixedPatternCorrelator<int16_t, int32_t, N, S> ((N, S) compiled into ref_harness.cpp:
+    (32, 4), (16, 2), (8, 1), (64, 8))."""
+
+    def __init__(self, lib: "_RefLib", N: int = 32, S: int = 4):
+        self._l, self.N = lib.lib, N
+        self._h = self._l.ref_corr_create(N, S)
+        if not self._h:
+            raise ValueError(f"ref_harness.cpp has no FixedPatternCorrelator<.., {N}, {S}>")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._l.ref_corr_destroy(self._h)
+            self._h = None
+
+    def setPattern(self, pattern, thresholdCoeff=0.8):
+        p = np.ascontiguousarray(pattern, np.int32).reshape(self.N, 2)
+        self._l.ref_corr_set_pattern(self._h, _p32(p), thresholdCoeff)
+
+    def reset(self):
+        self._l.ref_corr_reset(self._h)
+
+    def step(self, x):
+        x = np.ascontiguousarray(x, np.int16).reshape(-1, 2)
+        idx = C.c_int(0)
+        found = self._l.ref_corr_step(self._h, _p16(x), x.shape[0], C.byref(idx))
+        return bool(found), idx.value
+
+    def getRefBitSamples(self):
+        out = np.zeros((self.N, 2), np.int16)
+        self._l.ref_corr_bits(self._h, _p16(out), self.N)
+        return out
+
+    def getStatus(self):
+        e, c = (C.c_uint32 * 3)(), (C.c_uint32 * 3)()
+        ce, cs = C.c_uint32(), C.c_int()
+        self._l.ref_corr_status(self._h, e, c, C.byref(ce), C.byref(cs))
+        return dict(energyValue=list(e), corrValue=list(c), coeffsEnergy=ce.value, coeffScaling=cs.value)
+
+
 def corc() -> _COracle:
     global _corc
     if _corc is None:

@@ -196,3 +196,105 @@ void orc_up_step(const int32_t *taps, int ntaps, int L, unsigned shift, int16_t 
     memmove(history_iq, xx + 2 * n_tot, Hm1 * 2 * sizeof(int16_t));
     free(xx);
 }
+
+/* ---- FixedPatternCorrelator<int16_t, int32_t, N, S> --------------------------
+ * Sequential restatement with the reference's own state: circular history of N*S slots + insertion
+ * index `top`, the two 3-deep registers, the bit samples.  correlators.h:143-155 (reset), :167-194
+ * (setPattern), :209-303 (step).  All sums are mod 2^32 (the reference's int32_t / uint32_t). */
+void orc_corr_reset(orc_corr_t *c)
+{
+    c->top = 0;
+    memset(c->corr_value, 0, sizeof c->corr_value);
+    memset(c->energy_value, 0, sizeof c->energy_value);
+    memset(c->history, 0, sizeof(int32_t) * 2 * (size_t)c->N * (size_t)c->S);
+    memset(c->bits, 0, sizeof(int16_t) * 2 * (size_t)c->N);
+}
+
+int orc_corr_init(orc_corr_t *c, int N, int S)
+{
+    memset(c, 0, sizeof *c);
+    c->N = N;
+    c->S = S;
+    c->history = (int32_t *)calloc((size_t)2 * N * S, sizeof(int32_t));
+    c->coeffs = (int32_t *)calloc((size_t)2 * N, sizeof(int32_t));
+    c->bits = (int16_t *)calloc((size_t)2 * N, sizeof(int16_t));
+    if (!c->history || !c->coeffs || !c->bits) return -1;
+    orc_corr_reset(c);
+    return 0;
+}
+
+void orc_corr_free(orc_corr_t *c)
+{
+    free(c->history);
+    free(c->coeffs);
+    free(c->bits);
+    memset(c, 0, sizeof *c);
+}
+
+int orc_corr_set_pattern(orc_corr_t *c, const int32_t *pattern_iq, double threshold_coeff)
+{
+    double tmp = 0;
+    for (int k = 0; k < c->N; ++k) {
+        c->coeffs[2 * k] = pattern_iq[2 * k];
+        c->coeffs[2 * k + 1] = -pattern_iq[2 * k + 1]; /* conjugate, :172-176 */
+        const uint32_t e = (uint32_t)c->coeffs[2 * k] * (uint32_t)c->coeffs[2 * k] +
+                           (uint32_t)c->coeffs[2 * k + 1] * (uint32_t)c->coeffs[2 * k + 1];
+        tmp += (double)(int32_t)e;
+    }
+    if (!(tmp <= 1073217600.0)) return -1; /* assert at :183 */
+    c->coeffs_energy = (uint32_t)tmp;
+    c->threshold_factor = threshold_coeff * sqrt((double)c->coeffs_energy);
+    c->coeff_scaling = (int)floor(log2(sqrt((double)c->coeffs_energy)));
+    return 0;
+}
+
+int orc_corr_step(orc_corr_t *c, const int16_t *in_iq, size_t n, int *corr_index)
+{
+    const int N = c->N, S = c->S, H = N * S;
+    for (size_t index = 0; index < n; ++index) {
+        c->history[2 * c->top] = in_iq[2 * index];
+        c->history[2 * c->top + 1] = in_iq[2 * index + 1];
+        uint32_t re = 0, im = 0, en = 0;
+        c->energy_value[2] = c->energy_value[1];
+        c->energy_value[1] = c->energy_value[0];
+        /* every S-th slot: downwards from top (newest -> coeffs[N-1-k]), then the wrapped part (:226-235) */
+        int k, h;
+        for (k = 0; (h = c->top - k * S) >= 0; ++k) {
+            const uint32_t xr = (uint32_t)c->history[2 * h], xi = (uint32_t)c->history[2 * h + 1];
+            const uint32_t cr = (uint32_t)c->coeffs[2 * (N - 1 - k)], ci = (uint32_t)c->coeffs[2 * (N - 1 - k) + 1];
+            re += xr * cr - xi * ci;
+            im += xr * ci + xi * cr;
+            en += xr * xr + xi * xi;
+        }
+        for (k = 0; (h = c->top + (k + 1) * S) < H; ++k) {
+            const uint32_t xr = (uint32_t)c->history[2 * h], xi = (uint32_t)c->history[2 * h + 1];
+            const uint32_t cr = (uint32_t)c->coeffs[2 * k], ci = (uint32_t)c->coeffs[2 * k + 1];
+            re += xr * cr - xi * ci;
+            im += xr * ci + xi * cr;
+            en += xr * xr + xi * xi;
+        }
+        const int32_t sr = (int32_t)re >> c->coeff_scaling, si = (int32_t)im >> c->coeff_scaling; /* scale32 */
+        c->energy_value[0] = en >> (c->coeff_scaling / 2);
+        c->corr_value[2] = c->corr_value[1];
+        c->corr_value[1] = c->corr_value[0];
+        c->corr_value[0] = (uint32_t)(sr >> 2) * (uint32_t)(sr >> 2) + (uint32_t)(si >> 2) * (uint32_t)(si >> 2);
+        if (c->corr_value[1] > c->corr_value[2] && c->corr_value[1] > c->corr_value[0]) {
+            const double corr = sqrt((double)c->corr_value[1]), energy = sqrt((double)c->energy_value[1]);
+            if (corr > energy * 2.7 && energy > 300) {
+                *corr_index = (int)index - 1;
+                const int new_top = c->top > 0 ? c->top - 1 : H - 1;
+                for (k = 0; (h = new_top - k * S) >= 0; ++k) {
+                    c->bits[2 * (N - 1 - k)] = (int16_t)c->history[2 * h];
+                    c->bits[2 * (N - 1 - k) + 1] = (int16_t)c->history[2 * h + 1];
+                }
+                for (k = 0; (h = new_top + (k + 1) * S) < H; ++k) {
+                    c->bits[2 * k] = (int16_t)c->history[2 * h];
+                    c->bits[2 * k + 1] = (int16_t)c->history[2 * h + 1];
+                }
+                return 1; /* the break at :292: top is not advanced */
+            }
+        }
+        c->top = (c->top + 1) % H;
+    }
+    return 0;
+}

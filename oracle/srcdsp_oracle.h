@@ -58,6 +58,22 @@ int orc_up_length(const int32_t *taps, int ntaps); /* ntaps minus trailing zero 
 void orc_up_step(const int32_t *taps, int ntaps, int L, unsigned shift, int16_t *history_iq,
                  const int16_t *in_iq, size_t n_in, size_t n_flush, int16_t *out_iq);
 
+/* ---- correlator: correlators.h:143-155, :167-194, :209-303 ---- */
+typedef struct {
+    int N, S, top, coeff_scaling;
+    uint32_t coeffs_energy, corr_value[3], energy_value[3];
+    double threshold_factor;
+    int32_t *history; /* [N*S][2] circular */
+    int32_t *coeffs;  /* [N][2] conjugated pattern */
+    int16_t *bits;    /* [N][2] */
+} orc_corr_t;
+int orc_corr_init(orc_corr_t *c, int N, int S);
+void orc_corr_free(orc_corr_t *c);
+void orc_corr_reset(orc_corr_t *c);
+int orc_corr_set_pattern(orc_corr_t *c, const int32_t *pattern_iq, double threshold_coeff); /* -1: energy assert */
+/* returns 1 and *corr_index when a peak was found (the rest of the block is not consumed) */
+int orc_corr_step(orc_corr_t *c, const int16_t *in_iq, size_t n, int *corr_index);
+
 /* ---- shared scalar helpers: dsp_complex.cpp:63-73, dsp_complex.h:83-108 ---- */
 int16_t orc_limit_scale16(int32_t v, unsigned shift);     /* symmetric  +-32767        */
 int16_t orc_limit_scale_asym(int32_t v, unsigned shift);  /* [-32768, 32767]           */

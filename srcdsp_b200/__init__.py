@@ -27,7 +27,7 @@ from ._capi import SrcDspError, check, lib
 
 __all__ = ["Mixer", "FilterDnsamplingFir", "FilterFir", "FilterUpsamplingFir", "Ddc", "SrcDspError",
            "synth_fill", "launch_count", "device_count", "PinnedBuffer", "FifoWithTimeTrack", "saveBinarySamples",
-           "readBinarySamples"]
+           "readBinarySamples", "FixedPatternCorrelator"]
 
 
 # ----------------------------------------------------------------------------------------------
@@ -482,3 +482,47 @@ def readBinarySamples(path: str, out: Optional[np.ndarray] = None, exact: bool =
     if out is not None and len(out):
         x = np.concatenate([np.asarray(out, np.int16).reshape(-1, 2), x])
     return x
+
+
+class FixedPatternCorrelator(_Handle):
+    """dsptl::FixedPatternCorrelator<int16_t, int32_t, N, S> (correlators.h:54-303): the stage behind the DDC.
+    A bank of `channels` independent correlators sharing one pattern."""
+    _destroy = "srcdsp_corr_destroy"
+
+    def __init__(self, N: int = 32, S: int = 4, channels: int = 1, device: int = 0):
+        super().__init__()
+        self.N, self.S, self.channels = N, S, channels
+        check(lib().srcdsp_corr_create(C.byref(self._h), device, channels, N, S))
+
+    def setPattern(self, pattern, thresholdCoeff: float = 0.8):
+        """pattern: N complex values as int32 [N, 2] (the replica of the wanted signal, not conjugated)."""
+        p = np.ascontiguousarray(pattern, dtype=np.int32).reshape(self.N, 2)
+        check(lib().srcdsp_corr_set_pattern(self._h, p.ctypes.data_as(C.POINTER(C.c_int32)), float(thresholdCoeff)))
+
+    def reset(self):
+        check(lib().srcdsp_corr_reset(self._h))
+
+    def step(self, x):
+        """x: [n, 2] / [C, n, 2] int16 (numpy or torch CUDA).  Returns (found, corrIndex) -- scalars for a single
+        channel given a 2-D block, arrays [C] otherwise.  corrIndex is only meaningful where found."""
+        b = _Buf(x, self.channels)
+        self._bind_stream(b, "srcdsp_corr_set_stream")
+        found = (C.c_int * self.channels)()
+        idx = (C.c_int * self.channels)()
+        check(lib().srcdsp_corr_step(self._h, b.ptr, b.stride, b.n, found, idx))
+        f, i = np.array(found[:], dtype=bool), np.array(idx[:], dtype=np.int64)
+        if self.channels == 1 and b.squeeze:
+            return bool(f[0]), int(i[0])
+        return f, i
+
+    def getRefBitSamples(self, ch: int = 0) -> np.ndarray:
+        out = np.zeros((self.N, 2), np.int16)
+        check(lib().srcdsp_corr_get_ref_bit_samples(self._h, ch, out.ctypes.data))
+        return out
+
+    def getStatus(self, ch: int = 0) -> dict:
+        e, c = (C.c_uint32 * 3)(), (C.c_uint32 * 3)()
+        ce, cs, tf = C.c_uint32(), C.c_int(), C.c_double()
+        check(lib().srcdsp_corr_get_status(self._h, ch, e, c, C.byref(ce), C.byref(cs), C.byref(tf)))
+        return dict(energyValue=list(e), corrValue=list(c), coeffsEnergy=ce.value, coeffScaling=cs.value,
+                    thresholdFactor=tf.value)

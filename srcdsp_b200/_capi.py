@@ -92,6 +92,16 @@ PROTOTYPES = {
     "srcdsp_fifo_get_state": (C.c_int, [_vp, C.POINTER(_sz), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
     "srcdsp_fifo_set_time": (C.c_int, [_vp, C.c_uint64, C.c_uint64]),
     "srcdsp_fifo_storage": (_vp, [_vp]),
+    # correlator (correlators.h)
+    "srcdsp_corr_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_int]),
+    "srcdsp_corr_destroy": (C.c_int, [_vp]),
+    "srcdsp_corr_set_pattern": (C.c_int, [_vp, _i32p, C.c_double]),
+    "srcdsp_corr_reset": (C.c_int, [_vp]),
+    "srcdsp_corr_step": (C.c_int, [_vp, _i16p, _sz, _sz, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "srcdsp_corr_get_ref_bit_samples": (C.c_int, [_vp, C.c_int, _i16p]),
+    "srcdsp_corr_get_status": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                         C.POINTER(C.c_int), C.POINTER(C.c_double)]),
+    "srcdsp_corr_set_stream": (C.c_int, [_vp, _vp]),
 }
 
 _lib = None

@@ -19,6 +19,7 @@
 #include "kernels_dec_tc.cuh"
 #include "kernels_dec_tma.cuh"
 #include "kernels_up.cuh"
+#include "kernels_corr.cuh"
 
 namespace srcdsp {
 
@@ -1180,10 +1181,160 @@ struct UpBank : Bank {
 // =============================================================================================
 using namespace srcdsp;
 
+// ---------------------------------------------------------------------------------------------
+// correlator bank (correlators.h)
+// ---------------------------------------------------------------------------------------------
+struct CorrBank : Bank {
+    int N = 0, S = 0, H = 0;
+    bool has_pattern = false;
+    uint32_t coeffs_energy = 0;
+    int coeff_scaling = 0;
+    double threshold_factor = 0;
+    int *d_coef = nullptr;
+    uint32_t *d_hist[2] = {nullptr, nullptr};
+    uint32_t *d_reg[2] = {nullptr, nullptr};
+    int cur = 0;
+    int *d_found = nullptr;
+    uint32_t *d_bits = nullptr;
+    unsigned long long *d_cnt = nullptr;
+    uint32_t *d_scratch = nullptr;  // device copy of a host input block
+    size_t scratch_words = 0;
+    std::vector<int> h_found;
+
+    int create(int dev, int channels, int n, int s)
+    {
+        if (n < 1 || n > CORR_MAX_N || s < 1 || (long long)n * s > 16384)
+            return fail(SRCDSP_E_SIZE, "correlator: need 1 <= N <= %d, S >= 1, N * S <= 16384 (got N=%d S=%d)", CORR_MAX_N, n, s);
+        SRCDSP_TRY(init(dev, channels));
+        N = n, S = s, H = n * s - 1;
+        DeviceGuard g(device);
+        const size_t hw = (size_t)C * (H > 0 ? H : 1);
+        SRCDSP_CUDA(cudaMalloc(&d_coef, (size_t)2 * N * sizeof(int)));
+        for (int k = 0; k < 2; ++k) {
+            SRCDSP_CUDA(cudaMalloc(&d_hist[k], hw * 4));
+            SRCDSP_CUDA(cudaMalloc(&d_reg[k], (size_t)C * 6 * 4));
+        }
+        SRCDSP_CUDA(cudaMalloc(&d_found, (size_t)C * sizeof(int)));
+        SRCDSP_CUDA(cudaMalloc(&d_bits, (size_t)C * N * 4));
+        SRCDSP_CUDA(cudaMalloc(&d_cnt, (size_t)C * 8));
+        h_found.resize(C);
+        SRCDSP_CUDA(cudaFuncSetAttribute(corr_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        return reset();
+    }
+
+    // correlators.h:143-155
+    int reset()
+    {
+        DeviceGuard g(device);
+        SRCDSP_CUDA(cudaMemsetAsync(d_hist[cur], 0, (size_t)C * (H > 0 ? H : 1) * 4, stream));
+        SRCDSP_CUDA(cudaMemsetAsync(d_reg[cur], 0, (size_t)C * 6 * 4, stream));
+        SRCDSP_CUDA(cudaMemsetAsync(d_bits, 0, (size_t)C * N * 4, stream));
+        SRCDSP_CUDA(cudaMemsetAsync(d_cnt, 0, (size_t)C * 8, stream));
+        return SRCDSP_OK;
+    }
+
+    // correlators.h:167-194: conjugate, energy (asserted <= 1073217600), threshold factor, coeffScaling
+    int set_pattern(const int32_t *iq, double threshold_coeff)
+    {
+        if (!iq) return fail(SRCDSP_E_INVALID, "pattern is null");
+        std::vector<int> c(2 * N);
+        double tmp = 0;
+        for (int k = 0; k < N; ++k) {
+            c[2 * k] = iq[2 * k];
+            c[2 * k + 1] = -iq[2 * k + 1];
+            tmp += (double)((int32_t)(c[2 * k] * c[2 * k] + c[2 * k + 1] * c[2 * k + 1]));  // int32 arithmetic like the reference
+        }
+        if (!(tmp <= 1073217600.0))
+            return fail(SRCDSP_E_SIZE, "pattern energy %.0f exceeds 1073217600: each value must be below 13 bits [correlators.h:183]", tmp);
+        if (!(tmp >= 1)) return fail(SRCDSP_E_SIZE, "pattern energy must be >= 1 (coeffScaling = floor(log2(sqrt(energy))))");
+        DeviceGuard g(device);
+        SRCDSP_CUDA(cudaStreamSynchronize(stream));
+        SRCDSP_CUDA(cudaMemcpy(d_coef, c.data(), c.size() * sizeof(int), cudaMemcpyHostToDevice));
+        coeffs_energy = static_cast<uint32_t>(tmp);
+        threshold_factor = threshold_coeff * sqrt((double)coeffs_energy);
+        coeff_scaling = static_cast<int>(floor(log2(sqrt((double)coeffs_energy))));
+        has_pattern = true;
+        return SRCDSP_OK;
+    }
+
+    // step: correlators.h:209-303 for every channel; found[ch] / corr_index[ch] = the reference's return value / corrIndex
+    int step(const int16_t *in, size_t in_stride, size_t n, int *found, int *corr_index)
+    {
+        if (!has_pattern) return fail(SRCDSP_E_STATE, "correlator has no pattern (call srcdsp_corr_set_pattern)");
+        if (!found || !corr_index) return fail(SRCDSP_E_INVALID, "found / corr_index are null");
+        if (n > 0x7ffffff0u) return fail(SRCDSP_E_SIZE, "correlator block too long (int indices, correlators.h:211)");
+        for (int c = 0; c < C; ++c) found[c] = 0;
+        if (n == 0) return SRCDSP_OK;
+        DeviceGuard g(device);
+        const uint32_t *d_in = reinterpret_cast<const uint32_t *>(in);
+        size_t stride = in_stride;
+        if (!is_device_ptr(in)) {
+            const size_t pitch = (n + 3) & ~(size_t)3;
+            if (pitch * C > scratch_words) {
+                SRCDSP_CUDA(cudaStreamSynchronize(stream));
+                if (d_scratch) cudaFree(d_scratch);
+                d_scratch = nullptr;
+                SRCDSP_CUDA(cudaMalloc(&d_scratch, pitch * C * 4));
+                scratch_words = pitch * C;
+            }
+            SRCDSP_CUDA(cudaMemcpy2DAsync(d_scratch, pitch * 4, in, in_stride * 4, n * 4, C, cudaMemcpyHostToDevice, stream));
+            d_in = d_scratch;
+            stride = pitch;
+        }
+        CorrParams P{};
+        P.in = d_in;
+        P.in_stride = stride;
+        P.n = (int)n;
+        P.N = N, P.S = S, P.H = H;
+        P.coef = d_coef;
+        P.hist_in = d_hist[cur];
+        P.hist_out = d_hist[cur ^ 1];
+        P.reg_in = d_reg[cur];
+        P.reg_out = d_reg[cur ^ 1];
+        P.found = d_found;
+        P.bits = d_bits;
+        P.cnt = d_cnt;
+        P.coeff_scaling = coeff_scaling;
+        SRCDSP_CUDA(cudaMemsetAsync(d_found, 0x7f, (size_t)C * sizeof(int), stream));  // 0x7f7f7f7f > any index
+        const int halo = (N - 1) * S + 2;
+        const size_t smem = ((size_t)halo + CORR_THREADS + 2 * N + 2 * (CORR_THREADS + 2)) * 4;
+        dim3 grid((unsigned)((n + CORR_THREADS - 1) / CORR_THREADS), (unsigned)C);
+        corr_scan_kernel<<<grid, CORR_THREADS, smem, stream>>>(P);
+        SRCDSP_LAUNCH_CHECK();
+        corr_finish_kernel<<<C, CORR_THREADS, 0, stream>>>(P);
+        SRCDSP_LAUNCH_CHECK();
+        count_launch(2);
+        SRCDSP_CUDA(cudaMemcpyAsync(h_found.data(), d_found, (size_t)C * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        SRCDSP_CUDA(cudaStreamSynchronize(stream));
+        cur ^= 1;
+        for (int c = 0; c < C; ++c) {
+            found[c] = h_found[c] < (int)n;
+            if (found[c]) corr_index[c] = h_found[c] - 1;  // "-1 to refer to the previous sample", correlators.h:269
+        }
+        return SRCDSP_OK;
+    }
+
+    void destroy()
+    {
+        DeviceGuard g(device);
+        release();
+        if (d_coef) cudaFree(d_coef);
+        for (int k = 0; k < 2; ++k) {
+            if (d_hist[k]) cudaFree(d_hist[k]);
+            if (d_reg[k]) cudaFree(d_reg[k]);
+        }
+        if (d_found) cudaFree(d_found);
+        if (d_bits) cudaFree(d_bits);
+        if (d_cnt) cudaFree(d_cnt);
+        if (d_scratch) cudaFree(d_scratch);
+    }
+};
+
 struct srcdsp_mixer_s : MixerBank {};
 struct srcdsp_dec_s : DecBank {};
 struct srcdsp_up_s : UpBank {};
 struct srcdsp_ddc_s : DdcChain {};
+struct srcdsp_corr_s : CorrBank {};
 
 #define CHECK_HANDLE(h)                                                   \
     do {                                                                  \
@@ -1699,6 +1850,76 @@ int srcdsp_up_sync(srcdsp_up_t h)
 {
     CHECK_HANDLE(h);
     return h->sync();
+}
+
+
+// ---- correlator ---------------------------------------------------------------------------------
+int srcdsp_corr_create(srcdsp_corr_t *h, int device, int channels, int N, int S)
+{
+    if (!h) return fail(SRCDSP_E_INVALID, "handle pointer is null");
+    srcdsp_corr_s *b = new (std::nothrow) srcdsp_corr_s;
+    if (!b) return fail(SRCDSP_E_NOMEM, "out of memory");
+    int st = b->create(device, channels, N, S);
+    if (st != SRCDSP_OK) {
+        delete b;
+        return st;
+    }
+    *h = b;
+    return SRCDSP_OK;
+}
+int srcdsp_corr_destroy(srcdsp_corr_t h)
+{
+    if (!h) return SRCDSP_OK;
+    h->destroy();
+    delete h;
+    return SRCDSP_OK;
+}
+int srcdsp_corr_set_pattern(srcdsp_corr_t h, const int32_t *pattern_iq, double threshold_coeff)
+{
+    CHECK_HANDLE(h);
+    return h->set_pattern(pattern_iq, threshold_coeff);
+}
+int srcdsp_corr_reset(srcdsp_corr_t h)
+{
+    CHECK_HANDLE(h);
+    return h->reset();
+}
+int srcdsp_corr_step(srcdsp_corr_t h, const int16_t *in_iq, size_t in_stride, size_t n_per_ch, int *found, int *corr_index)
+{
+    CHECK_HANDLE(h);
+    return h->step(in_iq, in_stride, n_per_ch, found, corr_index);
+}
+int srcdsp_corr_get_ref_bit_samples(srcdsp_corr_t h, int ch, int16_t *bits_iq)
+{
+    CHECK_HANDLE(h);
+    if (ch < 0 || ch >= h->C || !bits_iq) return fail(SRCDSP_E_INVALID, "bad channel or null pointer");
+    DeviceGuard g(h->device);
+    SRCDSP_CUDA(cudaStreamSynchronize(h->stream));
+    SRCDSP_CUDA(cudaMemcpy(bits_iq, h->d_bits + (size_t)ch * h->N, (size_t)h->N * 4, cudaMemcpyDeviceToHost));
+    return SRCDSP_OK;
+}
+int srcdsp_corr_get_status(srcdsp_corr_t h, int ch, uint32_t *energy_value3, uint32_t *corr_value3, uint32_t *coeffs_energy,
+                           int *coeff_scaling, double *threshold_factor)
+{
+    CHECK_HANDLE(h);
+    if (ch < 0 || ch >= h->C) return fail(SRCDSP_E_INVALID, "bad channel");
+    DeviceGuard g(h->device);
+    uint32_t r[6];
+    SRCDSP_CUDA(cudaStreamSynchronize(h->stream));
+    SRCDSP_CUDA(cudaMemcpy(r, h->d_reg[h->cur] + (size_t)ch * 6, sizeof r, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 3; ++k) {
+        if (corr_value3) corr_value3[k] = r[k];
+        if (energy_value3) energy_value3[k] = r[3 + k];
+    }
+    if (coeffs_energy) *coeffs_energy = h->coeffs_energy;
+    if (coeff_scaling) *coeff_scaling = h->coeff_scaling;
+    if (threshold_factor) *threshold_factor = h->threshold_factor;
+    return SRCDSP_OK;
+}
+int srcdsp_corr_set_stream(srcdsp_corr_t h, void *cuda_stream)
+{
+    CHECK_HANDLE(h);
+    return h->set_stream(cuda_stream);
 }
 
 }  // extern "C"

@@ -110,3 +110,14 @@ if __name__ == "__main__":
     tp = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fifo_trace.npz")
     np.savez_compressed(tp, capacity=cap, seed=seed, ops=np.array(ops, dtype=object), results=np.array(res, dtype=object))
     print("wrote", tp, os.path.getsize(tp), "bytes,", len(ops), "operations")
+    # FixedPatternCorrelator: the reference's trace on two small cases
+    import test_correlator as TC
+    gold = {}
+    for seed, N, S, n, blocks in [(21, 32, 4, 5000, [1200, 1800, 2000]), (22, 16, 2, 3000, [700, 300, 2000])]:
+        pat, x, _ = TC.make_case(seed, N, S, n)
+        rc = O.RefCorrelator(O.ref(), N, S)
+        rc.setPattern(pat)
+        gold[f"corr_{N}_{S}"] = np.array(dict(N=N, S=S, pattern=pat, x=x, blocks=blocks, trace=TC.run_blocks(rc, x, blocks)), dtype=object)
+    cp = os.path.join(os.path.dirname(os.path.abspath(__file__)), "correlator.npz")
+    np.savez_compressed(cp, **gold)
+    print("wrote", cp, os.path.getsize(cp), "bytes")

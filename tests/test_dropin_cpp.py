@@ -70,3 +70,29 @@ def test_stream_program_dropin_build_prints_the_reference_output(built_lib, tmp_
     _compile_dropin(exe, SRC_STREAM)
     out = subprocess.run([exe, str(tmp_path / "gpu.iq")], check=True, capture_output=True, text=True, timeout=120).stdout
     assert out == open(GOLDEN_STREAM).read()
+
+
+SRC_CORR = os.path.join(ROOT, "tests", "cpp", "user_corr.cpp")             # correlators.h
+GOLDEN_CORR = os.path.join(ROOT, "tests", "golden", "user_corr.txt")
+
+
+def test_corr_program_reference_build_matches_committed_golden():
+    if not os.path.exists(os.path.join(REF, "correlators.h")):
+        pytest.skip("no /root/reference here")
+    os.makedirs(BUILD, exist_ok=True)
+    exe = os.path.join(BUILD, "user_corr_ref")
+    subprocess.run(["g++", "-std=gnu++11", "-O2", "-w", "-I" + REF, SRC_CORR, os.path.join(REF, "dsp_complex.cpp"), "-o", exe],
+                   check=True, capture_output=True, text=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    if os.environ.get("SRCDSP_REGEN_GOLDEN"):
+        open(GOLDEN_CORR, "w").write(out)
+    assert out == open(GOLDEN_CORR).read()
+    assert "found 1" in out
+
+
+@pytest.mark.gpu
+def test_corr_program_dropin_build_prints_the_reference_output(built_lib):
+    exe = os.path.join(BUILD, "user_corr_gpu")
+    _compile_dropin(exe, SRC_CORR)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True, timeout=300).stdout
+    assert out == open(GOLDEN_CORR).read()
