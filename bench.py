@@ -49,6 +49,8 @@ WORKLOADS = {
     "cfg5": dict(kind="dec", channels=1, n=1 << 29, M=4, ntaps=1023, mix=False,
                  desc="cfg5 slice: decimate-by-4 1023-tap FIR, one stream slice of 512Mi samples per GPU"),
     "mid": dict(kind="dec", channels=64, n=1 << 22, M=16, ntaps=255, mix=False, desc="mid: 64 ch x 4Mi, /16, 255 taps"),
+    "corr": dict(kind="corr", channels=256, n=1 << 22, M=1, ntaps=32, mix=False, S=4,
+                 desc="corr: FixedPatternCorrelator<int16,int32,32,4> bank, 256 ch x 4Mi samples of noise (no peak: full scan)"),
     "fifo": dict(kind="fifo", channels=1, n=1 << 22, M=16, ntaps=255, mix=False, blocks=24,
                  desc="fifo: one stream through FifoWithTimeTrack (pinned ring, 16Mi samples) -> decimate-by-16 255-tap FIR, 4Mi-sample blocks"),
     "smoke": dict(kind="dec", channels=8, n=1 << 18, M=16, ntaps=255, mix=False, desc="smoke: 8 ch x 256Ki"),
@@ -214,6 +216,43 @@ def fifo_stream_bench(args, w, base, S, O, torch, device):
     return 0
 
 
+def corr_bench(args, w, base, S, torch, device):
+    """the correlator bank scanning device-resident noise (no detection, so every sample is
+    visited).  Metric here is INPUT Msamples/s; algorithmic bytes = 4 B per input sample (the scan only reads)."""
+    C, n, N, St = w["channels"], w["n"], w["ntaps"], w["S"]
+    x = torch.empty((C, n, 2), dtype=torch.int16, device="cuda")
+    S.synth_fill(x, SEED, amp_shift=6)  # +-512: stays below the correlator's energy > 300 / 2.7x threshold
+    rng = np.random.default_rng(7)
+    corr = S.FixedPatternCorrelator(N, St, channels=C, device=device)
+    corr.setPattern(((rng.integers(0, 2, (N, 2)) * 2 - 1) * 1500).astype(np.int32))
+    for _ in range(args.warmup):
+        f, _ = corr.step(x)
+    assert not f.any(), "the benchmark input must not contain a peak"
+    torch.cuda.synchronize()
+    sampler = ClockSampler(device)
+    sampler.start()
+    l0 = S.launch_count()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    evs[0].record()
+    for _ in range(args.steps):
+        corr.step(x)
+    evs[1].record()
+    torch.cuda.synchronize()
+    ms = evs[0].elapsed_time(evs[1]) / args.steps
+    clocks = sampler.stop()
+    peak, peak_src = peaks()
+    alg = 4.0 * C * n
+    line = dict(base, metric="input Msamples/s", value=C * n / (ms * 1e-3) / 1e6, ms_per_step=ms,
+                roofline={"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                          "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "corr_scan_kernel",
+                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "kernel_ms": ms,
+                          "note": "step() is synchronous (it returns found / corrIndex): ms includes the 1 KB D2H of the result; "
+                                  "2*N = 64 complex multiply-adds + 64 energy terms per sample put the scan on the IMAD pipe"},
+                cpu_baseline=None, e2e=None, clocks=clocks, gpu_launches=int(S.launch_count() - l0), impl="ours")
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -270,6 +309,8 @@ def main():
     C, n, M, nt = w["channels"], w["n"], w["M"], w["ntaps"]
     if w["kind"] == "fifo":
         return fifo_stream_bench(args, w, base, S, O, torch, local_rank)
+    if w["kind"] == "corr":
+        return corr_bench(args, w, base, S, torch, local_rank)
     from srcdsp_b200.sharding import channel_shard
     my_ch = channel_shard(C * world, world, rank)  # weak scaling: 256 channels per GPU
     n_out = int(n * out_per_in(w))

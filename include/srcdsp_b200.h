@@ -195,7 +195,7 @@ const void *srcdsp_fifo_storage(srcdsp_fifo_t h);
 /* Correlator bank -- dsptl::FixedPatternCorrelator<int16_t, int32_t, N, S>  correlators.h:54-303 */
 /* (the stage behind the DDC): N-point correlation with a fixed pattern over */
 /* every S-th sample, 3-point peak test against the signal energy, stops at the first peak.      */
-/* ctor: correlators.h:124-133 (N <= 256, N * S <= 16384) */
+/* ctor: correlators.h:124-133 (N <= 256, N * S <= 8192) */
 int srcdsp_corr_create(srcdsp_corr_t *h, int device, int channels, int N, int S);
 int srcdsp_corr_destroy(srcdsp_corr_t h);
 /* setPattern: correlators.h:167-194 -- pattern_iq = N complex int32 (not conjugated); E_SIZE when the

@@ -1203,8 +1203,8 @@ struct CorrBank : Bank {
 
     int create(int dev, int channels, int n, int s)
     {
-        if (n < 1 || n > CORR_MAX_N || s < 1 || (long long)n * s > 16384)
-            return fail(SRCDSP_E_SIZE, "correlator: need 1 <= N <= %d, S >= 1, N * S <= 16384 (got N=%d S=%d)", CORR_MAX_N, n, s);
+        if (n < 1 || n > CORR_MAX_N || s < 1 || (long long)n * s > 8192)
+            return fail(SRCDSP_E_SIZE, "correlator: need 1 <= N <= %d, S >= 1, N * S <= 8192 (got N=%d S=%d)", CORR_MAX_N, n, s);
         SRCDSP_TRY(init(dev, channels));
         N = n, S = s, H = n * s - 1;
         DeviceGuard g(device);
@@ -1218,7 +1218,7 @@ struct CorrBank : Bank {
         SRCDSP_CUDA(cudaMalloc(&d_bits, (size_t)C * N * 4));
         SRCDSP_CUDA(cudaMalloc(&d_cnt, (size_t)C * 8));
         h_found.resize(C);
-        SRCDSP_CUDA(cudaFuncSetAttribute(corr_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        SRCDSP_CUDA(cudaFuncSetAttribute(corr_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
         return reset();
     }
 
@@ -1297,7 +1297,7 @@ struct CorrBank : Bank {
         P.coeff_scaling = coeff_scaling;
         SRCDSP_CUDA(cudaMemsetAsync(d_found, 0x7f, (size_t)C * sizeof(int), stream));  // 0x7f7f7f7f > any index
         const int halo = (N - 1) * S + 2;
-        const size_t smem = ((size_t)halo + CORR_THREADS + 2 * N + 2 * (CORR_THREADS + 2)) * 4;
+        const size_t smem = (3 * ((size_t)halo + CORR_THREADS) + 2 * N + 2 * (CORR_THREADS + 2)) * 4;
         dim3 grid((unsigned)((n + CORR_THREADS - 1) / CORR_THREADS), (unsigned)C);
         corr_scan_kernel<<<grid, CORR_THREADS, smem, stream>>>(P);
         SRCDSP_LAUNCH_CHECK();

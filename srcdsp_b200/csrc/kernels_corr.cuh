@@ -69,35 +69,58 @@ __device__ __forceinline__ bool corr_is_peak(uint32_t c_prev2, uint32_t c_mid, u
     return corr > energy * 2.7 && energy > 300;
 }
 
-// grid (tiles, C): every thread one sample; the block stages its samples (+ halo) and the pattern in shared memory
+// grid (tiles, C): every thread one sample.  The block stages its samples (+ halo) in shared memory already
+// unpacked to (re, im) int32 pairs together with |x|^2, so that the N-tap loop is one LDS.64 + one LDS.32 +
+// four IMAD + one IADD per tap (the unpacking and the squares would otherwise be redone N times per sample).
 __global__ void __launch_bounds__(CORR_THREADS) corr_scan_kernel(const CorrParams P)
 {
     extern __shared__ uint32_t corr_smem[];
     const int N = P.N, S = P.S, H = P.H;
     const int halo = (N - 1) * S + 2;  // the two preceding points of the 3-point test are computed here as well
-    uint32_t *xs = corr_smem;                               // [halo + CORR_THREADS]
-    int *cf = reinterpret_cast<int *>(xs + halo + CORR_THREADS);  // [2N]
-    uint32_t *cvs = reinterpret_cast<uint32_t *>(cf + 2 * N);     // [CORR_THREADS + 2]
+    const int W = halo + CORR_THREADS;
+    int2 *xs = reinterpret_cast<int2 *>(corr_smem);                 // [W] (re, im)
+    uint32_t *es = reinterpret_cast<uint32_t *>(xs + W);            // [W] re^2 + im^2 (mod 2^32)
+    int *cf = reinterpret_cast<int *>(es + W);                      // [2N], stored newest-first: cf[2j] = coef of x[t - jS]
+    uint32_t *cvs = reinterpret_cast<uint32_t *>(cf + 2 * N);       // [CORR_THREADS + 2]
     uint32_t *evs = cvs + CORR_THREADS + 2;
     const int ch = blockIdx.y;
     const int t0 = blockIdx.x * CORR_THREADS;
     const uint32_t *x = P.in + (size_t)ch * P.in_stride;
     const uint32_t *hist = P.hist_in + (size_t)ch * H;
-    for (int i = threadIdx.x; i < halo + CORR_THREADS; i += CORR_THREADS) {
+    for (int i = threadIdx.x; i < W; i += CORR_THREADS) {
         const int t = t0 - halo + i;
-        xs[i] = t < P.n ? corr_sample(x, hist, H, t) : 0u;
+        const uint32_t w = t < P.n ? corr_sample(x, hist, H, t) : 0u;
+        const int xr = sx_lo(w), xi = sx_hi(w);
+        xs[i] = make_int2(xr, xi);
+        es[i] = (uint32_t)(xr * xr + xi * xi);
     }
-    for (int i = threadIdx.x; i < 2 * N; i += CORR_THREADS) cf[i] = P.coef[i];
+    for (int j = threadIdx.x; j < N; j += CORR_THREADS) {
+        cf[2 * j] = P.coef[2 * (N - 1 - j)];
+        cf[2 * j + 1] = P.coef[2 * (N - 1 - j) + 1];
+    }
     __syncthreads();
-    auto at = [&](int t) { return xs[t - (t0 - halo)]; };
     // points t0-2 .. t0+255 (the first two by threads 0, 1 as extra work); points before the block start come
     // from the carried registers: t = -1 -> corrValue[0], t = -2 -> corrValue[1]
     for (int i = threadIdx.x; i < CORR_THREADS + 2; i += CORR_THREADS) {
         const int t = t0 - 2 + i;
         uint32_t cv = 0, ev = 0;
-        if (t >= 0 && t < P.n)
-            corr_point(at, cf, N, S, t, P.coeff_scaling, cv, ev);
-        else if (t < 0) {
+        if (t >= 0 && t < P.n) {
+            int re = 0, im = 0;
+            uint32_t e = 0;
+            const int base = t - (t0 - halo);  // index of sample t in the staged window
+#pragma unroll 4
+            for (int j = 0; j < N; ++j) {
+                const int2 v = xs[base - j * S];
+                const int cr = cf[2 * j], ci = cf[2 * j + 1];
+                re += v.x * cr - v.y * ci;  // std::complex<int32_t> product, wraps like the reference
+                im += v.x * ci + v.y * cr;
+                e += es[base - j * S];
+            }
+            re >>= P.coeff_scaling;  // scale32, dsp_complex.cpp:43-46
+            im >>= P.coeff_scaling;
+            ev = e >> (P.coeff_scaling / 2);
+            cv = (uint32_t)((re >> 2) * (re >> 2) + (im >> 2) * (im >> 2));
+        } else if (t < 0) {
             cv = P.reg_in[ch * 6 + (-1 - t)];
             ev = P.reg_in[ch * 6 + 3 + (-1 - t)];
         }
