@@ -424,6 +424,15 @@ def main():
     e2e = None
     if not args.no_e2e:
         try:
+            # every rank pins its whole batch (17 GiB for cfg2); with many ranks on one host check that it fits
+            try:
+                import psutil
+                need = world * (C * n + C * n_out) * 4
+                if psutil.virtual_memory().available < 1.3 * need:
+                    raise MemoryError(f"host has {psutil.virtual_memory().available >> 30} GiB available, "
+                                      f"{need >> 30} GiB of pinned staging needed for {world} ranks")
+            except ImportError:
+                pass
             hin = S.PinnedBuffer(C, n)
             hout = S.PinnedBuffer(C, n_out)
             S._capi.check(S.lib().srcdsp_memcpy(local_rank, hin.array.ctypes.data, x.data_ptr(), C * n * 4))

@@ -86,6 +86,17 @@ __device__ __forceinline__ uint32_t scale_pack_sym_sat(int re, int im, unsigned 
     return __vmaxs2(p, 0x80018001u);
 }
 
+// limitScale<cs16> of a complex value (dsp_complex.h:83-108): arithmetic >> then clamp to [-32768, 32767] per
+// component -- exactly what the saturating pack does
+__device__ __forceinline__ uint32_t scale_pack_asym_sat(int re, int im, unsigned shift)
+{
+    re >>= shift;
+    im >>= shift;
+    uint32_t p;
+    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(p) : "r"(im), "r"(re));  // {hi = sat(im), lo = sat(re)}
+    return p;
+}
+
 // One NCO mix: mixers.h:175-176.  cs = packed (cos, sin) = (T[(phi + N/4) % N], T[phi]).
 __device__ __forceinline__ uint32_t mix_sample(uint32_t x, uint32_t cs)
 {

@@ -127,10 +127,15 @@ __global__ void __launch_bounds__(UP_NT) up_fir_kernel(const UpParams P)
                 }
             }
         }
+        // outputs of (j, p) for the thread's UP_R consecutive inputs: one pointer, stride L
+        uint32_t *op = o + (J0 + jr) * L + p;
+        if (J0 + jr + UP_R <= P.n_tot) {
 #pragma unroll
-        for (int r = 0; r < UP_R; ++r) {
-            const long long j = J0 + jr + r;
-            if (j < P.n_tot) o[j * L + p] = scale_pack<false>(ar[r], ai[r], P.shift);
+            for (int r = 0; r < UP_R; ++r) op[r * L] = scale_pack_asym_sat(ar[r], ai[r], P.shift);
+        } else {
+#pragma unroll
+            for (int r = 0; r < UP_R; ++r)
+                if (J0 + jr + r < P.n_tot) op[r * L] = scale_pack_asym_sat(ar[r], ai[r], P.shift);
         }
     }
 }
