@@ -380,6 +380,38 @@ def test_tma_pipeline_shapes_match_imad(S, monkeypatch, w, groups, stages, raw, 
     assert torch.equal(outs[0], outs[1])
 
 
+@pytest.mark.parametrize("mix", [False, True])
+def test_tma_strided_channel_rows_and_output_views(S, corc, mix):
+    """Channel rows that are views into wider buffers (in_stride > n, out_stride > n_out, 16-byte aligned):
+    the TMA tensor map carries the stride; neighbouring memory is not touched."""
+    import torch
+    rng = np.random.default_rng(31)
+    C, M, nt, n, pad = 3, 16, 255, 16 * 4096 * 3, 64
+    taps = O.design_lowpass_taps(nt, M)
+    big = torch.from_numpy(rng.integers(-32768, 32768, (C, n + pad, 2)).astype(np.int16)).cuda()
+    x = big[:, 32: 32 + n]                               # 128-byte offset, stride n + pad
+    obig = torch.full((C, n // M + 40, 2), 12345, dtype=torch.int16, device="cuda")
+    y = obig[:, 8: 8 + n // M]
+    d = S.FilterDnsamplingFir(M, taps, channels=C, obsolete=True)
+    d.set_kernel(2)
+    chain, fs = d, None
+    if mix:
+        m = S.Mixer(channels=C)
+        fs = np.array([-0.25, 0.125, 0.7], np.float32)
+        m.setFrequency(fs)
+        chain = S.Ddc(m, d)
+    chain.step(x, out=y)
+    assert d.last_kernel.startswith("dec_tma")
+    yh, xh, oh = host(y), host(x), host(obig)
+    for c in range(C):
+        e = xh[c]
+        if mix:
+            e, _ = corc.mixer_step(e, 0, corc.mixer_set_frequency(float(fs[c])))
+        e, _ = corc.dec_step(taps, M, e)
+        assert np.array_equal(yh[c], e)
+    assert (oh[:, :8] == 12345).all() and (oh[:, 8 + n // M:] == 12345).all()
+
+
 def test_tc_rejects_what_it_cannot_do(S):
     d = S.FilterDnsamplingFir(8, [2 ** 24] * 16, obsolete=True)  # needs 4 signed byte digits
     d.set_kernel(2)
