@@ -49,6 +49,8 @@ WORKLOADS = {
     "cfg5": dict(kind="dec", channels=1, n=1 << 29, M=4, ntaps=1023, mix=False,
                  desc="cfg5 slice: decimate-by-4 1023-tap FIR, one stream slice of 512Mi samples per GPU"),
     "mid": dict(kind="dec", channels=64, n=1 << 22, M=16, ntaps=255, mix=False, desc="mid: 64 ch x 4Mi, /16, 255 taps"),
+    "mix": dict(kind="mix", channels=256, n=1 << 24, M=1, ntaps=0, mix=True,
+                desc="mix: stand-alone NCO mixer (mixers.h Mixer::step), 256 ch x 16Mi samples"),
     "corr": dict(kind="corr", channels=256, n=1 << 22, M=1, ntaps=32, mix=False, S=4,
                  desc="corr: FixedPatternCorrelator<int16,int32,32,4> bank, 256 ch x 4Mi samples of noise (no peak: full scan)"),
     "fifo": dict(kind="fifo", channels=1, n=1 << 22, M=16, ntaps=255, mix=False, blocks=24,
@@ -62,6 +64,8 @@ def bytes_per_out(w):
     output written and re-read for the two-stage chain)."""
     if w["kind"] == "up":
         return 4.0 + 4.0 / w["M"]
+    if w["kind"] == "mix":
+        return 8.0
     if w["kind"] == "ddc2":
         return 4.0 * w["M"] * w["M2"] + 4.0 + 8.0 * w["M2"]
     return 4.0 * w["M"] + 4.0
@@ -301,6 +305,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: srcdsp_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    from srcdsp_b200.sharding import bind_to_gpu_numa_node
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None  # pinned staging next to the GPU
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -318,7 +324,11 @@ def main():
     y = torch.empty((C, n_out, 2), dtype=torch.int16, device="cuda")
     S.synth_fill(x, SEED, ch0=my_ch.start, amp_shift=2)
     dec = None
-    if w["kind"] == "up":
+    if w["kind"] == "mix":
+        chain = S.Mixer(channels=C, device=local_rank)
+        chain.setFrequency((-1 + 2 * (np.arange(my_ch.start, my_ch.stop) + 0.5) / (C * world)).astype(np.float32))
+        stateful = [chain]
+    elif w["kind"] == "up":
         chain = S.FilterUpsamplingFir(M, O.design_interp_taps(nt, M), channels=C, device=local_rank)
         stateful = [chain]
     else:
@@ -377,14 +387,14 @@ def main():
         traffic = json.load(open(tp)).get(args.workload)
     roof = {"bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
             "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / peak, "traffic": traffic,
-            "kernel": dec.last_kernel if dec is not None else "up_fir_kernel", "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+            "kernel": dec.last_kernel if dec is not None else ("mixer_kernel" if w["kind"] == "mix" else "up_fir_kernel"), "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
             "kernel_ms": k_ms,
             "imad_note": "imad_frac = the same work counted as 2*taps INT32 multiply-adds per output against "
                          "148 SM x 64 IMAD/clk x sm_max_mhz: the ceiling of any CUDA-core kernel (SURVEY.md 8(d)); "
                          "the tcgen05 int8 kernel is not bound by it"}
     if clocks and clocks.get("sm_max_mhz"):
         imad_peak = 148 * 64 * clocks["sm_max_mhz"] * 1e6
-        macs = {"dec": 2 * nt, "ddc": 2 * nt + 4 * M, "up": 2 * nt / M,
+        macs = {"dec": 2 * nt, "ddc": 2 * nt + 4 * M, "up": 2 * nt / M, "mix": 4,
                 "ddc2": w.get("M2", 1) * (2 * nt + 4 * M) + 2 * w.get("ntaps2", 0)}[w["kind"]]
         roof["imad_frac"] = macs * C * n_out / (k_ms * 1e-3) / imad_peak
 
@@ -455,6 +465,8 @@ def main():
                    "h2d_bytes_per_step": C * n * 4, "d2h_bytes_per_step": C * n_out * 4,
                    "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
                    "api": type(chain).__name__ + ".step(host numpy view of pinned memory) -> C ABI step"}
+            if numa:
+                e2e["numa_binding_rank0"] = numa
             hin.free()
             hout.free()
         except Exception as ex:  # report, never fake

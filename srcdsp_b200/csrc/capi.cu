@@ -378,7 +378,15 @@ struct MixerBank : Bank {
         int bx = (int)std::min<long long>((work + 255) / 256, (148ll * 16 + C - 1) / C);
         if (bx < 1) bx = 1;
         dim3 grid(bx, C);
-        if (vec)
+        const PhaseMod m = pm();
+        if (vec && m.mask && n_table <= 8192 && n >= 4 * (size_t)n_table) {
+            // power-of-two table and a block worth building the per-channel oscillator sequence for
+            const int per_ch = (int)std::max<long long>(1, std::min<long long>((148ll * 6 + C - 1) / C, (long long)(n / (4 * (size_t)n_table))));
+            const size_t smem = (size_t)n_table * 8;
+            if (smem > 48 * 1024) SRCDSP_CUDA(cudaFuncSetAttribute(mixer_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            mixer_seq_kernel<<<dim3(per_ch, C), MIXSEQ_THREADS, smem, stream>>>(in, in_stride, out, out_stride, (long long)n, d_cs,
+                                                                               d_phi[cur], d_phi[cur ^ 1], d_freq, m.mask);
+        } else if (vec)
             mixer_kernel<true><<<grid, 256, 0, stream>>>(in, in_stride, out, out_stride, (long long)n, d_cs,
                                                          d_phi[cur], d_phi[cur ^ 1], d_freq, pm());
         else

@@ -120,6 +120,33 @@ __device__ __forceinline__ uint32_t mix_sample_packed(uint32_t x, uint32_t cs)
     return __vmaxs2(p, 0x80018001u);
 }
 
+// NCO mix (mixers.h:172-177) on the integer dot-product pipe.  The sample word is already the packed pair
+// (re, im) that dp2a takes; the oscillator value is kept as signed byte digits, cos = 256 * c1 + c0 etc.:
+//   Bre = bytes {c0, n0, c1, n1}  (n = -sin):  xr*cos - xi*sin = dp2a.lo(x, Bre) + 256 * dp2a.hi(x, Bre)
+//   Bim = bytes {s0, c0, s1, c1}            :  xr*sin + xi*cos = dp2a.lo(x, Bim) + 256 * dp2a.hi(x, Bim)
+// exactly the int32 products of dsp_complex.cpp:31-37, with no unpacking of x or of the table entry: the
+// multiply pipe (IMAD / IDP, 64 lanes/clk) takes 6 instructions per sample and the ALU pipe (PRMT / SHF / I2IP /
+// VIMNMX, also 64 lanes/clk, the binding one -- tools/pipebench.cu) only the 2 shifts, the saturating pack and
+// the symmetric clamp (+ the 2 PRMT of the byte-plane split).
+__device__ __forceinline__ uint32_t mix_sample_dp2a(uint32_t x, uint32_t bre, uint32_t bim)
+{
+    const int r = __dp2a_lo((int)x, (int)bre, __dp2a_hi((int)x, (int)bre, 0) * 256) >> 14;
+    const int i = __dp2a_lo((int)x, (int)bim, __dp2a_hi((int)x, (int)bim, 0) * 256) >> 14;
+    uint32_t p;
+    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(p) : "r"(i), "r"(r));  // {hi = sat(i), lo = sat(r)}
+    return __vmaxs2(p, 0x80018001u);  // limitScale16's symmetric clamp (dsp_complex.cpp:63-73)
+}
+// digits of one table entry cs = packed (cos, sin)
+__device__ __forceinline__ void mix_digits(uint32_t cs, uint32_t &bre, uint32_t &bim)
+{
+    const int c = sx_lo(cs), s = sx_hi(cs), n = -s;
+    const int c0 = ((c + 128) & 255) - 128, c1 = (c - c0) >> 8;
+    const int s0 = ((s + 128) & 255) - 128, s1 = (s - s0) >> 8;
+    const int n0 = ((n + 128) & 255) - 128, n1 = (n - n0) >> 8;
+    bre = (uint32_t)(c0 & 255) | ((uint32_t)(n0 & 255) << 8) | ((uint32_t)(c1 & 255) << 16) | ((uint32_t)(n1 & 255) << 24);
+    bim = (uint32_t)(s0 & 255) | ((uint32_t)(c0 & 255) << 8) | ((uint32_t)(s1 & 255) << 16) | ((uint32_t)(c1 & 255) << 24);
+}
+
 // phase of sample n of a block that started at phase phi0: (phi0 + n * freq) mod N
 struct PhaseMod {
     unsigned n_table;

@@ -204,6 +204,65 @@ __global__ void __launch_bounds__(256) mixer_kernel(const uint32_t *in, size_t i
     }
 }
 
+// Same with the oscillator as a per-channel sequence in TIME order (power-of-two tables, 16-byte aligned
+// rows): the CTA builds seq[n] = digits of T[(phi0 + n * freq) mod N], n < N, in shared memory once and then
+// streams its share of the channel -- LDG.128, two conflict-free LDS.128 for the 4 oscillator values, dp2a mix,
+// STG.128.  The table gather of mixer_kernel has a lane stride equal to the channel frequency: with evenly
+// spaced channel frequencies most lanes collide on a few lines / banks (2.1 TB/s); this form is HBM bound.
+constexpr int MIXSEQ_THREADS = 256;
+__global__ void __launch_bounds__(MIXSEQ_THREADS) mixer_seq_kernel(const uint32_t *in, size_t in_stride, uint32_t *out,
+                                                                   size_t out_stride, long long n,
+                                                                   const uint32_t *__restrict__ cs_table,
+                                                                   const int *__restrict__ phi, int *__restrict__ phi_out,
+                                                                   const int *__restrict__ freq, unsigned mask)
+{
+    extern __shared__ __align__(16) uint32_t seq[];  // Bre[N] ++ Bim[N]
+    const int ch = blockIdx.y;
+    const unsigned ph0 = (unsigned)phi[ch], fr = (unsigned)freq[ch];
+    const unsigned N = mask + 1;
+    for (unsigned i = threadIdx.x; i < N; i += MIXSEQ_THREADS) {
+        uint32_t bre, bim;
+        mix_digits(__ldg(cs_table + ((ph0 + i * fr) & mask)), bre, bim);
+        seq[i] = bre;
+        seq[N + i] = bim;
+    }
+    __syncthreads();
+    const uint4 *x = reinterpret_cast<const uint4 *>(in + (size_t)ch * in_stride);
+    uint4 *y = reinterpret_cast<uint4 *>(out + (size_t)ch * out_stride);
+    const long long n4 = n >> 2;
+    const long long per = (n4 + gridDim.x - 1) / gridDim.x;  // groups of 4 samples per CTA: a contiguous run
+    const long long g0 = (long long)blockIdx.x * per, g1 = g0 + per < n4 ? g0 + per : n4;
+    auto mix4 = [&](uint4 q, long long g) {
+        const unsigned idx = (unsigned)(4 * g) & mask;
+        const uint4 a = *reinterpret_cast<const uint4 *>(seq + idx);
+        const uint4 b = *reinterpret_cast<const uint4 *>(seq + N + idx);
+        q.x = mix_sample_dp2a(q.x, a.x, b.x);
+        q.y = mix_sample_dp2a(q.y, a.y, b.y);
+        q.z = mix_sample_dp2a(q.z, a.z, b.z);
+        q.w = mix_sample_dp2a(q.w, a.w, b.w);
+        __stcs(y + g, q);
+    };
+    constexpr int U = 4;  // 16-byte loads in flight per thread
+    long long g = g0 + threadIdx.x;
+    for (; g + (U - 1) * MIXSEQ_THREADS < g1; g += U * MIXSEQ_THREADS) {
+        uint4 q[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) q[u] = __ldcs(x + g + u * MIXSEQ_THREADS);
+#pragma unroll
+        for (int u = 0; u < U; ++u) mix4(q[u], g + u * MIXSEQ_THREADS);
+    }
+    for (; g < g1; g += MIXSEQ_THREADS) mix4(__ldcs(x + g), g);
+    if (blockIdx.x == 0) {
+        const uint32_t *xs = in + (size_t)ch * in_stride;
+        uint32_t *ys = out + (size_t)ch * out_stride;
+        for (long long k = (n4 << 2) + threadIdx.x; k < n; k += MIXSEQ_THREADS) {
+            const unsigned i = (unsigned)k & mask;
+            ys[k] = mix_sample_dp2a(xs[k], seq[i], seq[N + i]);
+        }
+        if (threadIdx.x == 0) phi_out[ch] = (int)((ph0 + ((unsigned)n & mask) * fr) & mask);
+    }
+}
+
 // synthetic complex baseband (host twin: oracle/srcdsp_oracle.c:orc_synth_fill)
 __global__ void synth_kernel(uint32_t *out, size_t stride, long long n, uint32_t seed, uint32_t ch0,
                              unsigned long long n0, int amp_shift)
