@@ -328,13 +328,21 @@ __global__ void __launch_bounds__(MIX ? 32 * (TMA_CONV_WARP0 + TMA_MAX_CONV_MIX)
                                              didx4, mask4);
                 }
                 if (HQ > 0 && wi == halo_turn) {
-                    // the row groups in front of the tile (the previous tile's last row-blocks)
-                    const uint8_t *hsrc = raw + rs * raw_bytes + src_lane;
-                    uint8_t *hdst = stages + ss * stage_bytes + dst_lane;
+                    // the row groups in front of the tile (the previous tile's last row-blocks): same shared-space
+                    // code as the main groups -- this warp is the K-step's straggler
+                    uint32_t hsrc = src - (HQ + wi) * 512, hdst = dst - (HQ + wi) * 128;
+                    // (n mod N) * 4 of (raw row grp, this lane's piece): halo_rows4 row-blocks before row-block grp
+                    unsigned hidx4 = 0;
+                    if (MIX)
+                        hidx4 = ((unsigned)(tile0 + (long long)(grp - halo_rows4) * P.G + 32 * kc + 4 * piece) & P.mix_mask) << 2;
+                    const unsigned hstep4 = ((unsigned)(4 * P.G) & P.mix_mask) << 2;
                     for (int q = 0; q < HQ; ++q) {
-                        const uint4 v = *reinterpret_cast<const uint4 *>(hsrc + q * 512);
-                        const long long n = tile0 + (long long)(4 * q + grp - halo_rows4) * P.G + 32 * kc + 4 * piece;
-                        tma_convert_store<MIX>(v, hdst + q * 128, hi_off, tab_smem, (unsigned)n & P.mix_mask, P.mix_mask);
+                        uint4 v = lds128<0>(hsrc);
+                        if (MIX) tma_mix4(v, tab_u32, hidx4, mask4 + 4);
+                        tma_split_store<0>(v, hdst, hdst + hi_off);
+                        hsrc += 512;
+                        hdst += 128;
+                        hidx4 = (hidx4 + hstep4) & mask4;
                     }
                 }
             } else {
