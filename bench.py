@@ -40,6 +40,8 @@ WORKLOADS = {
                  desc="cfg2: decimate-by-16 255-tap polyphase FIR, 256 ch x 16Mi cs16 samples per GPU"),
     "ddc16": dict(kind="ddc", channels=256, n=1 << 24, M=16, ntaps=255, mix=True,
                   desc="ddc16: NCO mix fused into decimate-by-16 255-tap FIR, 256 ch x 16Mi per GPU"),
+    "ddc8": dict(kind="ddc", channels=1024, n=1 << 22, M=8, ntaps=63, mix=True,
+                 desc="ddc8: NCO mix fused into decimate-by-8 63-tap FIR, 1024 ch x 4Mi per GPU (stage 1 of cfg3)"),
     "cfg1": dict(kind="ddc", channels=1, n=1 << 20, M=8, ntaps=63, mix=True,
                  desc="cfg1: NCO mix + decimate-by-8 63-tap FIR, 1 ch x 1Mi samples"),
     "cfg3": dict(kind="ddc2", channels=1024, n=1 << 22, M=8, ntaps=63, M2=4, ntaps2=63, mix=True,

@@ -430,8 +430,11 @@ struct DecBank : Bank {
     // tcgen05 int8 Toeplitz path (kernels_dec_tc.cuh)
     bool tc_ok = false;
     const char *tc_why = "no coefficients";
-    TcParams tc{};
-    uint8_t *d_master = nullptr;
+    // register-staged variant / TMA variant / TMA variant with the fused mixer (each with its own master layout)
+    TcParams tc{}, tc_tma{}, tc_tma_mix{};
+    bool tma_ok = false, tma_mix_ok = false;
+    uint8_t *d_master = nullptr, *d_master_tma = nullptr, *d_master_tma_mix = nullptr;
+    size_t tc_fixed_tma = 0, tc_fixed_tma_mix = 0;
     int *d_error = nullptr;  // wait-cycle counters of the timing variants (device)
     int *h_diag = nullptr;   // mapped host memory: record of a timed-out barrier wait (survives the trap)
     int *d_diag = nullptr;
@@ -454,24 +457,24 @@ struct DecBank : Bank {
 
     // shared-memory plan of the TMA-fed variant: byte-plane stages only decouple the converters from
     // the MMAs (3 are enough), everything else goes to the raw ring = the bytes in flight from HBM
-    int tma_layout(int table_bytes, int groups, int *n_raw, int *n_stages, size_t *smem) const
+    int tma_layout(size_t fixed, int table_bytes, int groups, int *n_raw, int *n_stages, size_t *smem) const
     {
         const size_t avail = (size_t)226 * 1024;
-        const size_t split = (size_t)64 * tc.rbp;
-        const size_t rawb = (size_t)(4 * ((tc.J - 1 + 3) / 4) + TC_NRB) * 128;
-        if (tc_fixed + (size_t)table_bytes + 2 * split + 2 * rawb > avail) return SRCDSP_E_SIZE;
+        const size_t split = (size_t)64 * tc_tma.rbp;
+        const size_t rawb = (size_t)(4 * ((tc_tma.J - 1 + 3) / 4) + TC_NRB) * 128;
+        if (fixed + (size_t)table_bytes + 2 * split + 2 * rawb > avail) return SRCDSP_E_SIZE;
         // byte-plane stages: one per converter group being filled + 1 for the MMAs; the rest of the
         // shared memory is the raw ring = the bytes in flight from HBM (at least 4 stages wanted)
         int ns = groups + 1;
         if (const char *e = getenv("SRCDSP_TMA_STAGES"))
             if (atoi(e) > 0) ns = std::max(2, std::min(atoi(e), TC_MAX_STAGES));
-        while (ns > 2 && tc_fixed + (size_t)table_bytes + ns * split + 4 * rawb > avail) --ns;
-        int nr = (int)((avail - tc_fixed - (size_t)table_bytes - ns * split) / rawb);
+        while (ns > 2 && fixed + (size_t)table_bytes + ns * split + 4 * rawb > avail) --ns;
+        int nr = (int)((avail - fixed - (size_t)table_bytes - ns * split) / rawb);
         if (nr > 8) nr = 8;  // more bytes in flight than ~128 KB per SM lowers the HBM rate (tools/tmabench.cu)
         if (nr < 2) return SRCDSP_E_SIZE;
         if (n_raw) *n_raw = nr;
         if (n_stages) *n_stages = ns;
-        if (smem) *smem = tc_fixed + (size_t)table_bytes + ns * split + nr * rawb;
+        if (smem) *smem = fixed + (size_t)table_bytes + ns * split + nr * rawb;
         return SRCDSP_OK;
     }
 
@@ -574,6 +577,8 @@ struct DecBank : Bank {
         if (d_hist[0]) cudaFree(d_hist[0]);
         if (d_hist[1]) cudaFree(d_hist[1]);
         if (d_master) cudaFree(d_master);
+        if (d_master_tma) cudaFree(d_master_tma);
+        if (d_master_tma_mix) cudaFree(d_master_tma_mix);
         if (d_error) cudaFree(d_error);
         if (h_diag) cudaFreeHost(h_diag);
     }
@@ -584,10 +589,18 @@ struct DecBank : Bank {
 // taps / ratio do not fit it; the IMAD kernel then handles every case.
 int DecBank::prepare_tc()
 {
-    tc_ok = false;
+    tc_ok = tma_ok = tma_mix_ok = false;
     if (d_master) {
         cudaFree(d_master);
         d_master = nullptr;
+    }
+    if (d_master_tma) {
+        cudaFree(d_master_tma);
+        d_master_tma = nullptr;
+    }
+    if (d_master_tma_mix) {
+        cudaFree(d_master_tma_mix);
+        d_master_tma_mix = nullptr;
     }
     if (M > TC_MAX_KSTEPS) { tc_why = "M > 64"; return SRCDSP_OK; }
     // signed base-256 digits of every tap: c = sum_pl 256^pl * d_pl, d_pl in [-128, 127]
@@ -613,7 +626,25 @@ int DecBank::prepare_tc()
     // s = a mod 8.  Fallback ("interleaved"): row = 4*v + w (+4 guard rows), one copy per residue r.
     const int front_pad = 2 * (4 * ((J - 1 + 3) / 4) - (J - 1));
     const int rbp = (front_pad + 2 * (TC_NRB + J - 1)) | 1;  // odd: conflict-free byte-plane stores
-    tc.rbp = rbp;  // tc_layout needs it
+    tc.rbp = tc_tma.rbp = rbp;  // the layout planners need rbp and J
+    tc.J = tc_tma.J = J;
+    if (!d_error) {
+        DeviceGuard g0(device);
+        SRCDSP_CUDA(cudaMalloc(&d_error, 128));
+        SRCDSP_CUDA(cudaMemset(d_error, 0, 128));
+        SRCDSP_CUDA(cudaHostAlloc(&h_diag, 64, cudaHostAllocMapped));
+        memset(h_diag, 0, 64);
+        SRCDSP_CUDA(cudaHostGetDevicePointer(&d_diag, h_diag, 0));
+    }
+    // The two kernels have different shared-memory budgets (the TMA variant needs few byte-plane stages, the
+    // register-staged one at least TC_OWNERS + 1), so each gets the best master layout that fits ITS budget:
+    // variant 0 = dec_tc_kernel (tc), 1 = dec_tma_kernel (tc_tma), 2 = dec_tma_kernel with the fused mixer (tc_tma_mix).
+    auto build_variant = [&](int variant) -> int {
+        TcParams &T = variant == 2 ? tc_tma_mix : variant ? tc_tma : tc;
+        uint8_t *&d_img = variant == 2 ? d_master_tma_mix : variant ? d_master_tma : d_master;
+        size_t &fixed = variant == 2 ? tc_fixed_tma_mix : variant ? tc_fixed_tma : tc_fixed;
+        bool &ok = variant == 2 ? tma_mix_ok : variant ? tma_ok : tc_ok;
+        ok = false;
     std::vector<int> copy_of_kc(M);
     std::vector<std::pair<int, int>> copies;  // (s, r)
     int grouped = 1, a_rows = 0;
@@ -636,11 +667,25 @@ int DecBank::prepare_tc()
         image_bytes = copies.size() * (size_t)a_rows * 32;
         // the MMA plan behind the image: M headers of 8 B, then one 16-byte entry per (K-step, lag) + 1 pad
         master_bytes = image_bytes + (((size_t)M * 8 + 15) & ~(size_t)15) + ((size_t)M * J + 1) * 16;
-        tc_fixed = ((master_bytes + 127) & ~(size_t)127) + 512;  // + mbarriers (at most 416 B)
-        if (tc_layout(16384, nullptr, nullptr) == SRCDSP_OK) break;  // leave room for a 4096-entry sine table
-        if (!grouped && tc_layout(0, nullptr, nullptr) == SRCDSP_OK) break;
+        fixed = ((master_bytes + 127) & ~(size_t)127) + 512;  // + mbarriers (at most 416 B)
+        if (variant) {
+            // grouped (shuffle-free epilogue, but several master copies) when enough raw stages remain: 4 for the
+            // plain decimator; 6 next to the fused mixer's oscillator sequence (32 KB for N = 4096), whose
+            // converters are slower and need the deeper ring more than the cheaper epilogue.  Otherwise the
+            // interleaved layout, when it fits at all.
+            int nr = 0;
+            const int table = variant == 2 ? 32768 : 0, want = variant == 2 ? 6 : 4;
+            if (tma_layout(fixed, table, variant == 2 ? 3 : 2, &nr, nullptr, nullptr) == SRCDSP_OK && nr >= want) break;
+            if (!grouped && tma_layout(fixed, table, 1, nullptr, nullptr, nullptr) == SRCDSP_OK) break;
+        } else {
+            if (tc_layout(16384, nullptr, nullptr) == SRCDSP_OK) break;  // leave room for a 4096-entry sine table
+            if (!grouped && tc_layout(0, nullptr, nullptr) == SRCDSP_OK) break;
+        }
     }
-    if (grouped < 0) { tc_why = "Toeplitz master + stages exceed the shared memory of one SM"; return SRCDSP_OK; }
+    if (grouped < 0) {
+        if (!variant) tc_why = "Toeplitz master + stages exceed the shared memory of one SM";
+        return SRCDSP_OK;
+    }
     std::vector<uint8_t> img(master_bytes, 0);
     const int OFF = 32;
     for (size_t ci = 0; ci < copies.size(); ++ci) {
@@ -698,32 +743,25 @@ int DecBank::prepare_tc()
         }
     }
     DeviceGuard g(device);
-    SRCDSP_CUDA(cudaMalloc(&d_master, master_bytes));
-    SRCDSP_CUDA(cudaMemcpy(d_master, img.data(), master_bytes, cudaMemcpyHostToDevice));
-    if (!d_error) {
-        SRCDSP_CUDA(cudaMalloc(&d_error, 128));
-        SRCDSP_CUDA(cudaMemset(d_error, 0, 128));
-        SRCDSP_CUDA(cudaHostAlloc(&h_diag, 64, cudaHostAllocMapped));
-        memset(h_diag, 0, 64);
-        SRCDSP_CUDA(cudaHostGetDevicePointer(&d_diag, h_diag, 0));
-    }
-    tc = TcParams{};
-    tc.M = M;
-    tc.G = G;
-    tc.J = J;
-    tc.master = d_master;
-    tc.master_bytes = (int)master_bytes;
-    tc.plan_hdr_off = plan_hdr_off;
-    tc.plan_ent_off = plan_ent_off;
-    tc.a_rows = a_rows;
-    tc.rbp = rbp;
-    tc.front_pad = front_pad;
-    tc.grouped = grouped;
-    tc.error_flag = d_diag;
-    tc.counters = d_error;
+    SRCDSP_CUDA(cudaMalloc(&d_img, master_bytes));
+    SRCDSP_CUDA(cudaMemcpy(d_img, img.data(), master_bytes, cudaMemcpyHostToDevice));
+    T = TcParams{};
+    T.M = M;
+    T.G = G;
+    T.J = J;
+    T.master = d_img;
+    T.master_bytes = (int)master_bytes;
+    T.plan_hdr_off = plan_hdr_off;
+    T.plan_ent_off = plan_ent_off;
+    T.a_rows = a_rows;
+    T.rbp = rbp;
+    T.front_pad = front_pad;
+    T.grouped = grouped;
+    T.error_flag = d_diag;
+    T.counters = d_error;
     for (int kc = 0; kc < M; ++kc) {
         const int a = (32 * kc) / M, r = (32 * kc) % M;
-        TcKstep &ks = tc.ks[kc];
+        TcKstep &ks = T.ks[kc];
         // master row of (b = 0, slot 0, lag 0): v0 = OFF - a + s  (a multiple of 8 when grouped)
         ks.a_row = grouped ? 4 * (OFF - 8 * (a / 8)) + 32 : 4 * (OFF - a) + 4;
         ks.res_off = copy_of_kc[kc] * a_rows * 32;
@@ -734,6 +772,13 @@ int DecBank::prepare_tc()
             if (kmax >= 0 && kmin <= ntaps - 1) ks.jmask |= 1u << j;
         }
     }
+        ok = true;
+        return SRCDSP_OK;
+    };
+    SRCDSP_TRY(build_variant(0));
+    SRCDSP_TRY(build_variant(1));
+    SRCDSP_TRY(build_variant(2));
+    if (!tc_ok) return SRCDSP_OK;
     cudaDeviceProp prop;
     SRCDSP_CUDA(cudaGetDeviceProperties(&prop, device));
     sm_count = prop.multiProcessorCount;
@@ -753,7 +798,6 @@ int DecBank::prepare_tc()
     SRCDSP_TMA_ATTR(16, false);
     SRCDSP_TMA_ATTR(16, true);
 #undef SRCDSP_TMA_ATTR
-    tc_ok = true;
     tc_why = "";
     return SRCDSP_OK;
 }
@@ -852,8 +896,9 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
     if (const char *e = getenv("SRCDSP_TMA_W")) tma_w = atoi(e) == 8 ? 8 : 4;
     if (const char *e = getenv("SRCDSP_TMA_GROUPS")) tma_groups = std::max(1, atoi(e));
     tma_groups = std::min(tma_groups, (mixer ? TMA_MAX_CONV_MIX : TMA_MAX_CONV) / tma_w);
-    bool use_tma = have_map && kernel_kind != 3 && !getenv("SRCDSP_NO_TMA") &&
-                   tma_layout(tma_tbl_bytes, tma_groups, &tma_raw, &tma_stages, &tma_smem) == SRCDSP_OK;
+    bool use_tma = have_map && (mixer ? tma_mix_ok : tma_ok) && kernel_kind != 3 && !getenv("SRCDSP_NO_TMA") &&
+                   tma_layout(mixer ? tc_fixed_tma_mix : tc_fixed_tma, tma_tbl_bytes, tma_groups, &tma_raw, &tma_stages,
+                              &tma_smem) == SRCDSP_OK;
     if (use_tc && !use_tma && tc_layout(tbl_bytes, &tc_stages, &tc_smem) != SRCDSP_OK)
         use_tc = false, why = "sine table + Toeplitz master + stages exceed 227 KB of shared memory";
     if (kernel_kind >= 2 && !use_tc)
@@ -874,7 +919,7 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
         P.pm = mixer->pm();
     }
     if (use_tc) {
-        TcParams T = tc;
+        TcParams T = use_tma ? (mixer ? tc_tma_mix : tc_tma) : tc;
         T.in = in;
         T.out = out;
         T.in_stride = in_stride;
@@ -940,6 +985,9 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
             T.n_stages = tma_stages;
             T.table_bytes = tma_tbl_bytes;
             const int threads = 32 * (TMA_CONV_WARP0 + X.n_conv);
+            if (getenv("SRCDSP_TMA_VERBOSE"))
+                fprintf(stderr, "dec_tma_kernel: M=%d J=%d grouped=%d master=%d B table=%d B raw=%d split=%d W=%d groups=%d shared_raw=%d smem=%zu\n",
+                        T.M, T.J, T.grouped, T.master_bytes, T.table_bytes, X.n_raw, T.n_stages, tma_w, tma_groups, X.shared_raw, tma_smem);
             if (T.debug & 32) {  // wait-cycle accounting variant; counters printed at the next launch
                 unsigned long long c[10];
                 cudaMemcpy(c, d_error, sizeof c, cudaMemcpyDeviceToHost);
