@@ -670,11 +670,16 @@ int DecBank::prepare_tc()
         fixed = ((master_bytes + 127) & ~(size_t)127) + 512;  // + mbarriers (at most 416 B)
         if (variant) {
             // grouped (shuffle-free epilogue, but several master copies) when enough raw stages remain: 4 for the
-            // plain decimator; 6 next to the fused mixer's oscillator sequence (32 KB for N = 4096), whose
-            // converters are slower and need the deeper ring more than the cheaper epilogue.  Otherwise the
+            // plain decimator; 5 next to the fused mixer's oscillator sequence (32 KB for N = 4096), whose
+            // converters are slower and need the deeper ring more than the cheaper epilogue (sweeps on ddc16 / ddc8:
+            // /16 is faster interleaved with 6 raw stages, /8 grouped with 5).  Otherwise the
             // interleaved layout, when it fits at all.
             int nr = 0;
-            const int table = variant == 2 ? 32768 : 0, want = variant == 2 ? 6 : 4;
+            const int table = variant == 2 ? 32768 : 0, want = variant == 2 ? 5 : 4;
+            if (const char *e = getenv("SRCDSP_TMA_GROUPED")) {  // tuning override
+                if ((atoi(e) != 0) == (grouped != 0) && tma_layout(fixed, table, 1, nullptr, nullptr, nullptr) == SRCDSP_OK) break;
+                continue;
+            }
             if (tma_layout(fixed, table, variant == 2 ? 3 : 2, &nr, nullptr, nullptr) == SRCDSP_OK && nr >= want) break;
             if (!grouped && tma_layout(fixed, table, 1, nullptr, nullptr, nullptr) == SRCDSP_OK) break;
         } else {
@@ -973,7 +978,8 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
         if (use_tma) {
             TmaExtra X{};
             X.n_raw = tma_raw;
-            if (const char *e = getenv("SRCDSP_TMA_RAW")) X.n_raw = std::max(2, std::min(atoi(e), tma_raw));
+            if (const char *e = getenv("SRCDSP_TMA_RAW"))
+                if (atoi(e) > 0) X.n_raw = std::max(2, std::min(atoi(e), tma_raw));
             tma_groups = std::max(1, std::min(tma_groups, std::min(X.n_raw, tma_stages - 1)));
             tma_groups = std::min(tma_groups, M);  // every group must see every tile (per-channel rebuild barrier of the fused mixer)
             // a raw stage that different groups convert in turn needs an extra wait (see the converters)
