@@ -457,11 +457,11 @@ struct DecBank : Bank {
 
     // shared-memory plan of the TMA-fed variant: byte-plane stages only decouple the converters from
     // the MMAs (3 are enough), everything else goes to the raw ring = the bytes in flight from HBM
-    int tma_layout(size_t fixed, int table_bytes, int groups, int *n_raw, int *n_stages, size_t *smem) const
+    int tma_layout(const TcParams &T, size_t fixed, int table_bytes, int groups, int *n_raw, int *n_stages, size_t *smem) const
     {
         const size_t avail = (size_t)226 * 1024;
-        const size_t split = (size_t)64 * tc_tma.rbp;
-        const size_t rawb = (size_t)(4 * ((tc_tma.J - 1 + 3) / 4) + TC_NRB) * 128;
+        const size_t split = (size_t)64 * T.rbp;
+        const size_t rawb = (size_t)(4 * ((T.J - 1 + 3) / 4) + T.nrb) * 128;
         if (fixed + (size_t)table_bytes + 2 * split + 2 * rawb > avail) return SRCDSP_E_SIZE;
         // byte-plane stages: one per converter group being filled + 1 for the MMAs; the rest of the
         // shared memory is the raw ring = the bytes in flight from HBM (at least 4 stages wanted)
@@ -590,18 +590,12 @@ struct DecBank : Bank {
 int DecBank::prepare_tc()
 {
     tc_ok = tma_ok = tma_mix_ok = false;
-    if (d_master) {
-        cudaFree(d_master);
-        d_master = nullptr;
-    }
-    if (d_master_tma) {
-        cudaFree(d_master_tma);
-        d_master_tma = nullptr;
-    }
-    if (d_master_tma_mix) {
-        cudaFree(d_master_tma_mix);
-        d_master_tma_mix = nullptr;
-    }
+    uint8_t **imgs[3] = {&d_master, &d_master_tma, &d_master_tma_mix};
+    for (auto pp : imgs)
+        if (*pp) {
+            cudaFree(*pp);
+            *pp = nullptr;
+        }
     if (M > TC_MAX_KSTEPS) { tc_why = "M > 64"; return SRCDSP_OK; }
     // signed base-256 digits of every tap: c = sum_pl 256^pl * d_pl, d_pl in [-128, 127]
     int P = 1;
@@ -617,17 +611,7 @@ int DecBank::prepare_tc()
         if (c != 0) P = 5;
     }
     if (P > 3) { tc_why = "taps need more than 3 signed byte digits (|c| >= 2^23)"; return SRCDSP_OK; }
-    const int G = 32 * M;
-    const int J = 1 + (ntaps - 1 + G - 1) / G;
-    if (J > TC_MAX_J) { tc_why = "filter spans more than 16 row-blocks"; return SRCDSP_OK; }
-    // One resident "master" Toeplitz image per distinct tap alignment.  Preferred layout ("grouped"):
-    // row = 32*(v>>3) + 8*w + (v&7) (+32 guard rows), the 4 weight slots of an output 8 rows apart, so
-    // that the epilogue needs no shuffles; a K-step whose output shift is a needs the copy with
-    // s = a mod 8.  Fallback ("interleaved"): row = 4*v + w (+4 guard rows), one copy per residue r.
-    const int front_pad = 2 * (4 * ((J - 1 + 3) / 4) - (J - 1));
-    const int rbp = (front_pad + 2 * (TC_NRB + J - 1)) | 1;  // odd: conflict-free byte-plane stores
-    tc.rbp = tc_tma.rbp = rbp;  // the layout planners need rbp and J
-    tc.J = tc_tma.J = J;
+    if (1 + (ntaps - 1 + 32 * M - 1) / (32 * M) > TC_MAX_J) { tc_why = "filter spans more than 16 row-blocks"; return SRCDSP_OK; }
     if (!d_error) {
         DeviceGuard g0(device);
         SRCDSP_CUDA(cudaMalloc(&d_error, 128));
@@ -636,153 +620,180 @@ int DecBank::prepare_tc()
         memset(h_diag, 0, 64);
         SRCDSP_CUDA(cudaHostGetDevicePointer(&d_diag, h_diag, 0));
     }
-    // The two kernels have different shared-memory budgets (the TMA variant needs few byte-plane stages, the
+    // "p2" tile geometry for the TMA variants: when every tap fits 2 signed digits, half of the 4 weight-slot rows
+    // of each MMA are zero.  With 64 outputs x 2 digit slots per row-block (row-blocks of 64*M samples, 64 of them
+    // per tile) and the two byte planes accumulating into separate column halves, all 128 rows work and the filter
+    // spans half as many row-blocks: ~1.8x fewer MMA cycles per output for long filters (the tensor pipe binds
+    // there: /4 with 1023 taps).  Short filters lose more to the doubled K-step count than they gain, so it is
+    // used from 4 lags on (SRCDSP_TMA_P2 = 0 / 1 overrides).
+    bool want_p2 = P <= 2 && 2 * M <= TC_MAX_KSTEPS && 1 + (ntaps - 1 + 32 * M - 1) / (32 * M) >= 4;
+    if (const char *e = getenv("SRCDSP_TMA_P2")) want_p2 = atoi(e) != 0 && P <= 2 && 2 * M <= TC_MAX_KSTEPS;
+
+    // One resident "master" Toeplitz image per distinct tap alignment.  S = weight slots per output (4, or the 2
+    // digit slots in p2 mode).  Preferred layout ("grouped"): row = 8*S*(v>>3) + 8*w + (v&7) (+ 8*S guard rows), the
+    // slots of an output 8 rows apart, so that the epilogue needs no shuffles; a K-step whose output shift is a
+    // needs the copy with s = a mod 8.  Fallback ("interleaved", 4 slots only): row = 4*v + w (+4 guard rows), one copy
+    // per residue r.
+    // The kernels have different shared-memory budgets (the TMA variant needs few byte-plane stages, the
     // register-staged one at least TC_OWNERS + 1), so each gets the best master layout that fits ITS budget:
     // variant 0 = dec_tc_kernel (tc), 1 = dec_tma_kernel (tc_tma), 2 = dec_tma_kernel with the fused mixer (tc_tma_mix).
-    auto build_variant = [&](int variant) -> int {
+    auto build_variant = [&](int variant, bool p2) -> int {
         TcParams &T = variant == 2 ? tc_tma_mix : variant ? tc_tma : tc;
         uint8_t *&d_img = variant == 2 ? d_master_tma_mix : variant ? d_master_tma : d_master;
         size_t &fixed = variant == 2 ? tc_fixed_tma_mix : variant ? tc_fixed_tma : tc_fixed;
         bool &ok = variant == 2 ? tma_mix_ok : variant ? tma_ok : tc_ok;
         ok = false;
-    std::vector<int> copy_of_kc(M);
-    std::vector<std::pair<int, int>> copies;  // (s, r)
-    int grouped = 1, a_rows = 0;
-    size_t master_bytes = 0, image_bytes = 0;
-    for (; grouped >= 0; --grouped) {
-        copies.clear();
-        for (int kc = 0; kc < M; ++kc) {
-            const int a = (32 * kc) / M, r = (32 * kc) % M;
-            const std::pair<int, int> key(grouped ? a % 8 : 0, r);
-            int idx = -1;
-            for (size_t i = 0; i < copies.size(); ++i)
-                if (copies[i] == key) idx = (int)i;
-            if (idx < 0) {
-                idx = (int)copies.size();
-                copies.push_back(key);
+        const int nrb = p2 ? 64 : TC_NRB, bout = p2 ? 64 : TC_BOUT, S = p2 ? 2 : 4;
+        const int G = bout * M, ksteps = G / 32;
+        const int J = 1 + (ntaps - 1 + G - 1) / G;
+        const int OFF = bout;  // a = (32 * kc) / M < bout
+        const int front_pad = 2 * (4 * ((J - 1 + 3) / 4) - (J - 1));
+        const int rbp = (front_pad + 2 * (nrb + J - 1)) | 1;  // odd: conflict-free byte-plane stores
+        T = TcParams{};
+        T.rbp = rbp, T.J = J, T.nrb = nrb;  // the layout planners need these
+        std::vector<int> copy_of_kc(ksteps);
+        std::vector<std::pair<int, int>> copies;  // (s, r)
+        int grouped = 1, a_rows = 0;
+        size_t master_bytes = 0, image_bytes = 0;
+        for (; grouped >= (p2 ? 1 : 0); --grouped) {
+            copies.clear();
+            for (int kc = 0; kc < ksteps; ++kc) {
+                const int a = (32 * kc) / M, r = (32 * kc) % M;
+                const std::pair<int, int> key(grouped ? a % 8 : 0, r);
+                int idx = -1;
+                for (size_t i = 0; i < copies.size(); ++i)
+                    if (copies[i] == key) idx = (int)i;
+                if (idx < 0) {
+                    idx = (int)copies.size();
+                    copies.push_back(key);
+                }
+                copy_of_kc[kc] = idx;
             }
-            copy_of_kc[kc] = idx;
-        }
-        a_rows = grouped ? 128 * J + 32 + 128 + 64 : 128 * J + 136;
-        image_bytes = copies.size() * (size_t)a_rows * 32;
-        // the MMA plan behind the image: M headers of 8 B, then one 16-byte entry per (K-step, lag) + 1 pad
-        master_bytes = image_bytes + (((size_t)M * 8 + 15) & ~(size_t)15) + ((size_t)M * J + 1) * 16;
-        fixed = ((master_bytes + 127) & ~(size_t)127) + 512;  // + mbarriers (at most 416 B)
-        if (variant) {
-            // grouped (shuffle-free epilogue, but several master copies) when enough raw stages remain: 4 for the
-            // plain decimator; 5 next to the fused mixer's oscillator sequence (32 KB for N = 4096), whose
-            // converters are slower and need the deeper ring more than the cheaper epilogue (sweeps on ddc16 / ddc8:
-            // /16 is faster interleaved with 6 raw stages, /8 grouped with 5).  Otherwise the
-            // interleaved layout, when it fits at all.
-            int nr = 0;
-            const int table = variant == 2 ? 32768 : 0, want = variant == 2 ? 5 : 4;
-            if (const char *e = getenv("SRCDSP_TMA_GROUPED")) {  // tuning override
-                if ((atoi(e) != 0) == (grouped != 0) && tma_layout(fixed, table, 1, nullptr, nullptr, nullptr) == SRCDSP_OK) break;
-                continue;
-            }
-            if (tma_layout(fixed, table, variant == 2 ? 3 : 2, &nr, nullptr, nullptr) == SRCDSP_OK && nr >= want) break;
-            if (!grouped && tma_layout(fixed, table, 1, nullptr, nullptr, nullptr) == SRCDSP_OK) break;
-        } else {
-            if (tc_layout(16384, nullptr, nullptr) == SRCDSP_OK) break;  // leave room for a 4096-entry sine table
-            if (!grouped && tc_layout(0, nullptr, nullptr) == SRCDSP_OK) break;
-        }
-    }
-    if (grouped < 0) {
-        if (!variant) tc_why = "Toeplitz master + stages exceed the shared memory of one SM";
-        return SRCDSP_OK;
-    }
-    std::vector<uint8_t> img(master_bytes, 0);
-    const int OFF = 32;
-    for (size_t ci = 0; ci < copies.size(); ++ci) {
-        uint8_t *base = img.data() + ci * (size_t)a_rows * 32;
-        const int s8 = copies[ci].first, r = copies[ci].second;
-        const int guard = grouped ? 32 : 4;
-        for (int row = guard; row < a_rows; ++row) {
-            int v, w;
-            if (grouped) {
-                const int q = row - guard;
-                v = 8 * (q / 32) + (q % 8);
-                w = (q % 32) / 8;
+            // rows: guard + S * OFF (shift range) + 128 per lag + slack
+            a_rows = grouped ? 128 * J + 8 * S + S * OFF + 64 : 128 * J + 136;
+            image_bytes = copies.size() * (size_t)a_rows * 32;
+            // the MMA plan behind the image: one 8-byte header per K-step, then one 16-byte entry per (K-step, lag) + 1 pad
+            master_bytes = image_bytes + (((size_t)ksteps * 8 + 15) & ~(size_t)15) + ((size_t)ksteps * J + 1) * 16;
+            fixed = ((master_bytes + 127) & ~(size_t)127) + 512;  // + mbarriers (at most 416 B)
+            if (variant) {
+                // grouped (shuffle-free epilogue, but several master copies) when enough raw stages remain: 4 for the
+                // plain decimator; 5 next to the fused mixer's oscillator sequence (32 KB for N = 4096), whose
+                // converters are slower and need the deeper ring more than the cheaper epilogue (sweeps on ddc16 / ddc8:
+                // /16 is faster interleaved with 6 raw stages, /8 grouped with 5).  Otherwise the interleaved layout,
+                // when it fits at all.
+                int nr = 0;
+                const int table = variant == 2 ? 32768 : 0, want = variant == 2 ? 5 : 4;
+                if (const char *e = getenv("SRCDSP_TMA_GROUPED")) {  // tuning override
+                    if (((atoi(e) != 0) || p2) == (grouped != 0) && tma_layout(T, fixed, table, 1, nullptr, nullptr, nullptr) == SRCDSP_OK) break;
+                    continue;
+                }
+                if (tma_layout(T, fixed, table, variant == 2 ? 3 : 2, &nr, nullptr, nullptr) == SRCDSP_OK && (nr >= want || p2)) break;
+                if (!grouped && tma_layout(T, fixed, table, 1, nullptr, nullptr, nullptr) == SRCDSP_OK) break;
             } else {
-                v = (row - guard) / 4;
-                w = (row - guard) % 4;
-            }
-            if (w >= P) continue;
-            const int u = v - s8 - OFF;
-            for (int t = 0; t < 32; ++t) {
-                const long long k = (long long)M * u - t - r;
-                if (k < 0 || k >= ntaps) continue;
-                // SWIZZLE_NONE K-major image: [kc = t / 16][row][t % 16]
-                base[(size_t)(t / 16) * a_rows * 16 + (size_t)row * 16 + (t % 16)] = (uint8_t)dig[w][k];
+                tc.rbp = rbp;  // tc_layout reads it
+                if (tc_layout(16384, nullptr, nullptr) == SRCDSP_OK) break;  // leave room for a 4096-entry sine table
+                if (!grouped && tc_layout(0, nullptr, nullptr) == SRCDSP_OK) break;
             }
         }
-    }
-    // MMA plan (tc_mma_role): operand addresses >> 4, A relative to the master, B relative to the stage
-    const int plan_hdr_off = (int)image_bytes;
-    const int plan_ent_off = plan_hdr_off + (int)((((size_t)M * 8 + 15) & ~(size_t)15));
-    {
-        uint32_t *hdr = reinterpret_cast<uint32_t *>(img.data() + plan_hdr_off);
-        uint32_t *ent = reinterpret_cast<uint32_t *>(img.data() + plan_ent_off);
-        const int hi_shift = grouped ? 128 : 16;  // one weight slot: 8 rows / 1 row
-        uint32_t n_ent = 0;
-        for (int kc = 0; kc < M; ++kc) {
+        if (grouped < (p2 ? 1 : 0)) {
+            if (!variant) tc_why = "Toeplitz master + stages exceed the shared memory of one SM";
+            return SRCDSP_OK;
+        }
+        std::vector<uint8_t> img(master_bytes, 0);
+        const int guard = grouped ? 8 * S : 4;
+        for (size_t ci = 0; ci < copies.size(); ++ci) {
+            uint8_t *base = img.data() + ci * (size_t)a_rows * 32;
+            const int s8 = copies[ci].first, r = copies[ci].second;
+            for (int row = guard; row < a_rows; ++row) {
+                int v, w;
+                if (grouped) {
+                    const int q = row - guard;
+                    v = 8 * (q / (8 * S)) + (q % 8);
+                    w = (q % (8 * S)) / 8;
+                } else {
+                    v = (row - guard) / 4;
+                    w = (row - guard) % 4;
+                }
+                if (w >= P) continue;
+                const int u = v - s8 - OFF;
+                for (int t = 0; t < 32; ++t) {
+                    const long long k = (long long)M * u - t - r;
+                    if (k < 0 || k >= ntaps) continue;
+                    // SWIZZLE_NONE K-major image: [kc = t / 16][row][t % 16]
+                    base[(size_t)(t / 16) * a_rows * 16 + (size_t)row * 16 + (t % 16)] = (uint8_t)dig[w][k];
+                }
+            }
+        }
+        // per K-step: master row of (b = 0, slot 0, lag 0), v0 = OFF - a + s (a multiple of 8 when grouped), and the lags
+        // whose taps reach this K-step's samples
+        auto a_row_of = [&](int a) { return grouped ? S * (OFF - 8 * (a / 8)) + guard : 4 * (OFF - a) + 4; };
+        auto lag_active = [&](int a, int r, int j) {
+            const long long kmax = (long long)M * (bout - 1 + bout * j - a) - r;
+            const long long kmin = (long long)M * (bout * j - a) - r - 31;
+            return kmax >= 0 && kmin <= ntaps - 1;
+        };
+        // MMA plan (tc_mma_role): operand addresses >> 4, A relative to the master, B relative to the stage
+        const int plan_hdr_off = (int)image_bytes;
+        const int plan_ent_off = plan_hdr_off + (int)((((size_t)ksteps * 8 + 15) & ~(size_t)15));
+        {
+            uint32_t *hdr = reinterpret_cast<uint32_t *>(img.data() + plan_hdr_off);
+            uint32_t *ent = reinterpret_cast<uint32_t *>(img.data() + plan_ent_off);
+            // hi byte plane: one weight slot up = 8 rows (grouped) / 1 row (interleaved) back; p2: same rows, own columns
+            const int hi_shift = p2 ? 0 : grouped ? 128 : 16;
+            uint32_t n_ent = 0;
+            for (int kc = 0; kc < ksteps; ++kc) {
+                const int a = (32 * kc) / M, r = (32 * kc) % M;
+                const int res_off = copy_of_kc[kc] * a_rows * 32;
+                hdr[2 * kc] = n_ent;
+                uint32_t cnt = 0;
+                for (int j = 0; j < J; ++j) {
+                    if (!lag_active(a, r, j)) continue;
+                    const int a_addr = res_off + (a_row_of(a) + 128 * j) * 16;
+                    const int b_addr = (front_pad + 2 * (J - 1 - j)) * 16;
+                    ent[4 * n_ent + 0] = (uint32_t)a_addr >> 4;
+                    ent[4 * n_ent + 1] = (uint32_t)(a_addr - hi_shift) >> 4;
+                    ent[4 * n_ent + 2] = (uint32_t)b_addr >> 4;
+                    ent[4 * n_ent + 3] = (uint32_t)(b_addr + 2 * rbp * 16) >> 4;
+                    ++n_ent;
+                    ++cnt;
+                }
+                hdr[2 * kc + 1] = cnt;
+            }
+        }
+        DeviceGuard g(device);
+        SRCDSP_CUDA(cudaMalloc(&d_img, master_bytes));
+        SRCDSP_CUDA(cudaMemcpy(d_img, img.data(), master_bytes, cudaMemcpyHostToDevice));
+        T.M = M;
+        T.G = G;
+        T.p2 = p2;
+        T.ksteps = ksteps;
+        T.master = d_img;
+        T.master_bytes = (int)master_bytes;
+        T.plan_hdr_off = plan_hdr_off;
+        T.plan_ent_off = plan_ent_off;
+        T.a_rows = a_rows;
+        T.front_pad = front_pad;
+        T.grouped = grouped;
+        T.error_flag = d_diag;
+        T.counters = d_error;
+        for (int kc = 0; kc < ksteps && kc < TC_MAX_KSTEPS; ++kc) {
             const int a = (32 * kc) / M, r = (32 * kc) % M;
-            const int a_row = grouped ? 4 * (OFF - 8 * (a / 8)) + 32 : 4 * (OFF - a) + 4;
-            const int res_off = copy_of_kc[kc] * a_rows * 32;
-            hdr[2 * kc] = n_ent;
-            uint32_t cnt = 0;
-            for (int j = 0; j < J; ++j) {
-                const long long kmax = (long long)M * (31 + 32 * j - a) - r;
-                const long long kmin = (long long)M * (32 * j - a) - r - 31;
-                if (!(kmax >= 0 && kmin <= ntaps - 1)) continue;
-                const int a_addr = res_off + (a_row + 128 * j) * 16;
-                const int b_addr = (front_pad + 2 * (J - 1 - j)) * 16;
-                ent[4 * n_ent + 0] = (uint32_t)a_addr >> 4;
-                ent[4 * n_ent + 1] = (uint32_t)(a_addr - hi_shift) >> 4;
-                ent[4 * n_ent + 2] = (uint32_t)b_addr >> 4;
-                ent[4 * n_ent + 3] = (uint32_t)(b_addr + 2 * rbp * 16) >> 4;
-                ++n_ent;
-                ++cnt;
-            }
-            hdr[2 * kc + 1] = cnt;
+            TcKstep &ks = T.ks[kc];
+            ks.a_row = a_row_of(a);
+            ks.res_off = copy_of_kc[kc] * a_rows * 32;
+            ks.jmask = 0;
+            for (int j = 0; j < J; ++j)
+                if (lag_active(a, r, j)) ks.jmask |= 1u << j;
         }
-    }
-    DeviceGuard g(device);
-    SRCDSP_CUDA(cudaMalloc(&d_img, master_bytes));
-    SRCDSP_CUDA(cudaMemcpy(d_img, img.data(), master_bytes, cudaMemcpyHostToDevice));
-    T = TcParams{};
-    T.M = M;
-    T.G = G;
-    T.J = J;
-    T.master = d_img;
-    T.master_bytes = (int)master_bytes;
-    T.plan_hdr_off = plan_hdr_off;
-    T.plan_ent_off = plan_ent_off;
-    T.a_rows = a_rows;
-    T.rbp = rbp;
-    T.front_pad = front_pad;
-    T.grouped = grouped;
-    T.error_flag = d_diag;
-    T.counters = d_error;
-    for (int kc = 0; kc < M; ++kc) {
-        const int a = (32 * kc) / M, r = (32 * kc) % M;
-        TcKstep &ks = T.ks[kc];
-        // master row of (b = 0, slot 0, lag 0): v0 = OFF - a + s  (a multiple of 8 when grouped)
-        ks.a_row = grouped ? 4 * (OFF - 8 * (a / 8)) + 32 : 4 * (OFF - a) + 4;
-        ks.res_off = copy_of_kc[kc] * a_rows * 32;
-        ks.jmask = 0;
-        for (int j = 0; j < J; ++j) {
-            const long long kmax = (long long)M * (31 + 32 * j - a) - r;
-            const long long kmin = (long long)M * (32 * j - a) - r - 31;
-            if (kmax >= 0 && kmin <= ntaps - 1) ks.jmask |= 1u << j;
-        }
-    }
         ok = true;
         return SRCDSP_OK;
     };
-    SRCDSP_TRY(build_variant(0));
-    SRCDSP_TRY(build_variant(1));
-    SRCDSP_TRY(build_variant(2));
+    SRCDSP_TRY(build_variant(0, false));
+    for (int variant = 1; variant <= 2; ++variant) {
+        // p2 first where it pays; the 4-slot geometry when its master does not fit next to the rings
+        if (want_p2) SRCDSP_TRY(build_variant(variant, true));
+        if (!(variant == 2 ? tma_mix_ok : tma_ok)) SRCDSP_TRY(build_variant(variant, false));
+    }
     if (!tc_ok) return SRCDSP_OK;
     cudaDeviceProp prop;
     SRCDSP_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -887,23 +898,29 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
         const PhaseMod pm = mixer->pm();
         if (!pm.mask) use_tc = false, why = "fused mixer needs a power-of-two sine table";
     }
-    // TMA-fed variant: needs 16-byte aligned rows and at least one whole row-block in the tensor
+    // TMA-fed variant: needs 16-byte aligned rows and at least one whole row-block in the tensor (row-blocks of
+    // G samples: 32 * M, or 64 * M in p2 mode -- the variants have their own tile geometry)
     const int tbl_bytes = mixer ? (int)mixer->n_table * 4 : 0;      // LDG variant: copy of the packed (cos, sin) table
     const int tma_tbl_bytes = mixer ? (int)mixer->n_table * 8 : 0;  // TMA variant: oscillator sequence, two digit words per sample
-    const long long rows_full = (long long)(n_in / (size_t)(32 * M));
+    const TcParams &Ttma = mixer ? tc_tma_mix : tc_tma;
+    const bool tma_built = mixer ? tma_mix_ok : tma_ok;
+    const long long rows_tma = tma_built ? (long long)(n_in / (size_t)Ttma.G) : 0;
     int tma_raw = 0, tma_stages = 0;
     size_t tma_smem = 0;
-    const bool have_map = use_tc && P.vec_in && rows_full >= 1 && rows_full < 0x7fffffffll && tensor_map_encoder() != nullptr;
+    const bool can_map = use_tc && P.vec_in && tensor_map_encoder() != nullptr;
     // converter warps: groups of W warps, one K-step per group at a time
     // defaults from sweeps on cfg2 / ddc16 (256 ch x 16 Mi, /16, 255 taps): W = 4; plain decimator 2 groups + 3 byte-plane
     // stages (the raw ring gets the rest), fused mixer 3 groups + 4 stages (more ALU work per K-step)
     int tma_w = 4, tma_groups = mixer ? 3 : 2;
     if (const char *e = getenv("SRCDSP_TMA_W")) tma_w = atoi(e) == 8 ? 8 : 4;
+    if (tma_built && Ttma.p2) tma_w = 4;  // 16 main row groups per K-step: 4 per warp
     if (const char *e = getenv("SRCDSP_TMA_GROUPS")) tma_groups = std::max(1, atoi(e));
     tma_groups = std::min(tma_groups, (mixer ? TMA_MAX_CONV_MIX : TMA_MAX_CONV) / tma_w);
-    bool use_tma = have_map && (mixer ? tma_mix_ok : tma_ok) && kernel_kind != 3 && !getenv("SRCDSP_NO_TMA") &&
-                   tma_layout(mixer ? tc_fixed_tma_mix : tc_fixed_tma, tma_tbl_bytes, tma_groups, &tma_raw, &tma_stages,
+    bool use_tma = can_map && tma_built && rows_tma >= 1 && rows_tma < 0x7fffffffll && kernel_kind != 3 && !getenv("SRCDSP_NO_TMA") &&
+                   tma_layout(Ttma, mixer ? tc_fixed_tma_mix : tc_fixed_tma, tma_tbl_bytes, tma_groups, &tma_raw, &tma_stages,
                               &tma_smem) == SRCDSP_OK;
+    const long long rows_full = use_tma ? rows_tma : (long long)(n_in / (size_t)(32 * M));
+    const bool have_map = can_map && rows_full >= 1 && rows_full < 0x7fffffffll;
     if (use_tc && !use_tma && tc_layout(tbl_bytes, &tc_stages, &tc_smem) != SRCDSP_OK)
         use_tc = false, why = "sine table + Toeplitz master + stages exceed 227 KB of shared memory";
     if (kernel_kind >= 2 && !use_tc)
@@ -957,14 +974,14 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
             }
         }
         // the input as a tensor [C][rows_full][G] of 32-bit words (one complex int16 sample each); a box is one
-        // K-step of one tile: 32 samples x (J-1 halo + 128) row-blocks x 1 channel
+        // K-step of one tile: 32 samples x (J-1 halo + nrb) row-blocks x 1 channel
         CUtensorMap map;
         memset(&map, 0, sizeof map);
         if (have_map) {
             const cuuint64_t gdim[3] = {(cuuint64_t)T.G, (cuuint64_t)rows_full, (cuuint64_t)C};
             const cuuint64_t gstr[2] = {(cuuint64_t)T.G * 4,
                                         C > 1 ? (cuuint64_t)in_stride * 4 : (cuuint64_t)rows_full * T.G * 4};
-            const cuuint32_t box[3] = {32, (cuuint32_t)(T.J - 1 + TC_NRB), 1};
+            const cuuint32_t box[3] = {32, (cuuint32_t)(T.J - 1 + T.nrb), 1};
             const cuuint32_t estr[3] = {1, 1, 1};
             const CUresult cr = tensor_map_encoder()(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)in, gdim, gstr, box, estr,
                                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -981,19 +998,19 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
             if (const char *e = getenv("SRCDSP_TMA_RAW"))
                 if (atoi(e) > 0) X.n_raw = std::max(2, std::min(atoi(e), tma_raw));
             tma_groups = std::max(1, std::min(tma_groups, std::min(X.n_raw, tma_stages - 1)));
-            tma_groups = std::min(tma_groups, M);  // every group must see every tile (per-channel rebuild barrier of the fused mixer)
+            tma_groups = std::min(tma_groups, T.ksteps);  // every group must see every tile (per-channel rebuild barrier of the fused mixer)
             // a raw stage that different groups convert in turn needs an extra wait (see the converters)
             X.shared_raw = (X.n_raw % tma_groups) != 0;
             X.n_conv = tma_w * tma_groups;
-            X.raw_rows = 4 * ((T.J - 1 + 3) / 4) + TC_NRB;
-            X.box_rows = T.J - 1 + TC_NRB;
+            X.raw_rows = 4 * ((T.J - 1 + 3) / 4) + T.nrb;
+            X.box_rows = T.J - 1 + T.nrb;
             X.rows_full = rows_full;
             T.n_stages = tma_stages;
             T.table_bytes = tma_tbl_bytes;
             const int threads = 32 * (TMA_CONV_WARP0 + X.n_conv);
             if (getenv("SRCDSP_TMA_VERBOSE"))
-                fprintf(stderr, "dec_tma_kernel: M=%d J=%d grouped=%d master=%d B table=%d B raw=%d split=%d W=%d groups=%d shared_raw=%d smem=%zu\n",
-                        T.M, T.J, T.grouped, T.master_bytes, T.table_bytes, X.n_raw, T.n_stages, tma_w, tma_groups, X.shared_raw, tma_smem);
+                fprintf(stderr, "dec_tma_kernel: M=%d p2=%d J=%d grouped=%d master=%d B table=%d B raw=%d split=%d W=%d groups=%d shared_raw=%d smem=%zu\n",
+                        T.M, T.p2, T.J, T.grouped, T.master_bytes, T.table_bytes, X.n_raw, T.n_stages, tma_w, tma_groups, X.shared_raw, tma_smem);
             if (T.debug & 32) {  // wait-cycle accounting variant; counters printed at the next launch
                 unsigned long long c[10];
                 cudaMemcpy(c, d_error, sizeof c, cudaMemcpyDeviceToHost);

@@ -63,7 +63,11 @@ struct TcParams {
     uint32_t *out;
     size_t in_stride, out_stride;
     long long n_in, n_out;
-    int M;            // decimation ratio == K-steps per row-block
+    int nrb;          // row-blocks per tile: TC_NRB (128), or 64 in "p2" mode
+    int p2;           // p2 mode (taps of at most 2 digits): 64 outputs x 2 digit slots per row-block, the two byte planes
+                      // accumulate into separate halves of the accumulator (128 columns each) and meet in the epilogue
+    int ksteps;       // K-steps per tile: M, or 2 * M in p2 mode (row-blocks of 64 * M samples)
+    int M;            // decimation ratio
     int G;            // 32 * M samples per row-block
     int J;            // lags: 1 + ceil((Nt-1)/G)
     int tiles_per_ch;
@@ -362,8 +366,9 @@ __device__ __forceinline__ void tc_mma_role(const TcParams &P, const TcRole &R)
     // the next K-step is fetched before this one's barrier wait.  Per K-step that leaves: wait,
     // fence, a handful of adds, the MMAs, the commit.
     {
-        const uint32_t idesc_lo = umma_idesc_i8(1, 0, 128, 2 * TC_NRB);  // taps s8 x lo plane u8
-        const uint32_t idesc_hi = umma_idesc_i8(1, 1, 128, 2 * TC_NRB);  // taps s8 x hi plane s8
+        const uint32_t idesc_lo = umma_idesc_i8(1, 0, 128, 2 * P.nrb);  // taps s8 x lo plane u8
+        const uint32_t idesc_hi = umma_idesc_i8(1, 1, 128, 2 * P.nrb);  // taps s8 x hi plane s8
+        const uint32_t hi_cols = P.p2 ? 2 * P.nrb : 0;  // p2: the hi plane has its own accumulator columns
         const uint32_t a_base = smem_u32(a_smem), s_base = smem_u32(stages);
         // descriptor = {high word: SBO 128 B, version 1} {low word: LBO >> 4 << 16 | address >> 4}
         const uint32_t desc_hi = (128u >> 4) | (1u << 14);
@@ -388,27 +393,29 @@ __device__ __forceinline__ void tc_mma_role(const TcParams &P, const TcRole &R)
         for (long long tile = first_tile; tile < R.tile_end; tile += tile_step) {
             mbar_wait_acc<DBG>(bar_tempty + 8 * acc, ((acc_phases >> acc) & 1) ^ 1, P.error_flag, m_tempty);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * (2 * TC_NRB);
+            const uint32_t d_tmem = tmem_base + acc * (2 * TC_NRB);  // (p2: 128 + 128 columns of the same 256)
             uint32_t accumulate = 0;
             for (int kc = 0; kc < KS; ++kc) {
                 mbar_wait_acc<DBG>(bar_full + 8 * stage, phase, P.error_flag, m_full);
                 tc_fence_after();
                 const uint32_t cnt = no_mma ? 0u : hdr.y;
                 const uint32_t bs = b_const + sb16;
+                // the hi plane accumulates into the same columns (weight slot + 1 of the master) or, in p2 mode, into
+                // its own columns, where its first MMA of the tile must not accumulate either
+                const uint32_t acc_hi0 = P.p2 ? accumulate : 1u;
                 if (elect_one()) {
                     if (cnt > 0) {
                         umma_i8(d_tmem, desc(a_const + e0.x), desc(bs + e0.z), idesc_lo, accumulate);
-                        // hi byte plane: weight slot + 1  ==  master moved back by one slot
-                        if (!no_hi) umma_i8(d_tmem, desc(a_const + e0.y), desc(bs + e0.w), idesc_hi, 1);
+                        if (!no_hi) umma_i8(d_tmem + hi_cols, desc(a_const + e0.y), desc(bs + e0.w), idesc_hi, acc_hi0);
                     }
                     if (cnt > 1) {
                         umma_i8(d_tmem, desc(a_const + e1.x), desc(bs + e1.z), idesc_lo, 1);
-                        if (!no_hi) umma_i8(d_tmem, desc(a_const + e1.y), desc(bs + e1.w), idesc_hi, 1);
+                        if (!no_hi) umma_i8(d_tmem + hi_cols, desc(a_const + e1.y), desc(bs + e1.w), idesc_hi, 1);
                     }
                     for (uint32_t i = 2; i < cnt; ++i) {
                         const uint4 e = plan_ent[hdr.x + i];
                         umma_i8(d_tmem, desc(a_const + e.x), desc(bs + e.z), idesc_lo, 1);
-                        if (!no_hi) umma_i8(d_tmem, desc(a_const + e.y), desc(bs + e.w), idesc_hi, 1);
+                        if (!no_hi) umma_i8(d_tmem + hi_cols, desc(a_const + e.y), desc(bs + e.w), idesc_hi, 1);
                     }
                     tc_commit(bar_empty + 8 * stage);  // frees the stage when these MMAs have read it
                     if (kc == KS - 1) tc_commit(bar_tfull + 8 * acc);
@@ -463,7 +470,45 @@ __device__ __forceinline__ void tc_epilogue_role(const TcParams &P, const TcRole
         mbar_wait_acc<DBG>(bar_tfull + 8 * acc, (acc_phases >> acc) & 1, P.error_flag, e_wait);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + ((uint32_t)(32 * warp) << 16) + acc * (2 * TC_NRB);
-        if (P.grouped) {
+        if (P.p2) {
+            // p2 mode: lane = 16*(b>>3) + 8*p + (b&7) for output b (64 per row-block) and digit slot p; columns 0..127
+            // hold the lo byte plane's sums, 128..255 the hi plane's.  A 16x256b load of lanes 16h..16h+15 hands one
+            // thread both digit slots of output b = 16*warp + 8*h + lane/4 for the (re, im) pairs of 4 row-blocks.
+            for (int h = 0; h < 2; ++h) {
+                const int b2 = 16 * warp + 8 * h + (lane >> 2);
+                const long long idx_lane = (tt * P.nrb + (lane & 3)) * 64 + b2;
+                uint32_t *o_lane = o + idx_lane;
+                const bool full_tile = (tt + 1) * (long long)(TC_NRB * TC_BOUT) <= P.n_out;
+#pragma unroll 1
+                for (int c0 = 0; c0 < ((P.debug & 4) ? 0 : 2 * P.nrb); c0 += 32) {
+                    uint32_t a[16], hh[16];
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+                        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                        : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]),
+                          "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]),
+                          "=r"(a[15])
+                        : "r"(t_addr + ((uint32_t)(16 * h) << 16) + c0));
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+                        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                        : "=r"(hh[0]), "=r"(hh[1]), "=r"(hh[2]), "=r"(hh[3]), "=r"(hh[4]), "=r"(hh[5]), "=r"(hh[6]), "=r"(hh[7]),
+                          "=r"(hh[8]), "=r"(hh[9]), "=r"(hh[10]), "=r"(hh[11]), "=r"(hh[12]), "=r"(hh[13]), "=r"(hh[14]),
+                          "=r"(hh[15])
+                        : "r"(t_addr + ((uint32_t)(16 * h) << 16) + 2 * P.nrb + c0));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    uint32_t *op = o_lane + c0 * 32;  // row-block c0 / 2, 64 outputs each
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        // lo*d0 + 256 * (lo*d1 + hi*d0) + 65536 * hi*d1 (mod 2^32, exactly the reference's int32 wrap)
+                        const uint32_t re = a[4 * k] + ((a[4 * k + 2] + hh[4 * k]) << 8) + (hh[4 * k + 2] << 16);
+                        const uint32_t im = a[4 * k + 1] + ((a[4 * k + 3] + hh[4 * k + 1]) << 8) + (hh[4 * k + 3] << 16);
+                        const uint32_t word = scale_pack_sym_sat((int)re, (int)im, P.shift);
+                        if (full_tile || idx_lane + (c0 / 2 + 4 * k) * 64 < P.n_out) op[4 * k * 64] = word;
+                    }
+                }
+            }
+        } else if (P.grouped) {
             // weight slots of output b sit 8 TMEM lanes apart: a 16x256b load hands one thread the
             // slots {0,1} (lanes 0-15 of the warp's quadrant) or {2,3} (lanes 16-31) of output
             // b = 8*warp + lane/4 for the column pairs (re, im) of 4 row-blocks -> no shuffles
@@ -602,7 +647,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dec_tc_kernel(const __grid_cons
     // previous tile's last rows, still in L2; the fused mixer's per-channel state changes rarely)
     const long long first_tile = P.total_tiles * blockIdx.x / gridDim.x, tile_end = P.total_tiles * (blockIdx.x + 1) / gridDim.x;
     const long long tile_step = 1;
-    const int KS = P.M;  // K-steps per tile
+    const int KS = P.ksteps;  // K-steps per tile
     const TcRole role{a_smem, stages, stage_bytes, NS, J, KS, warp, lane, bar_full, bar_empty, bar_tfull, bar_tempty, tmem_base,
                       first_tile, tile_step, tile_end, P.pf_dist > 0 ? smem_u32(&progress_s) : 0u};
 

@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(MIX ? 32 * (TMA_CONV_WARP0 + TMA_MAX_CONV_MIX)
     // previous tile's last rows, still in L2; the fused mixer's per-channel sequence changes rarely)
     const long long first_tile = P.total_tiles * blockIdx.x / gridDim.x, tile_end = P.total_tiles * (blockIdx.x + 1) / gridDim.x;
     const long long tile_step = 1;
-    const int KS = P.M;
+    const int KS = P.ksteps;
     const TcRole role{a_smem, stages, stage_bytes, NS, J, KS, warp, lane, bar_full, bar_empty, bar_tfull, bar_tempty, tmem_base,
                       first_tile, tile_step, tile_end, 0u};
 
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(MIX ? 32 * (TMA_CONV_WARP0 + TMA_MAX_CONV_MIX)
         const int g = cw / W, wi = cw - g * W;
         const int piece = lane & 7, grp = lane >> 3;
         const int chunk = P.rbp * 16;
-        const int halo_rows4 = X.raw_rows - TC_NRB;   // 4 * ceil((J-1)/4)
+        const int halo_rows4 = X.raw_rows - P.nrb;    // 4 * ceil((J-1)/4)
         const int HQ = halo_rows4 / 4;                // row groups in front of the tile (halo + padding rows)
         const int NQ = X.raw_rows / 4;                // row groups per stage
         // raw row i (0 .. raw_rows) holds row-block rb = i - halo_rows4; its byte-plane rows are
@@ -254,6 +254,7 @@ __global__ void __launch_bounds__(MIX ? 32 * (TMA_CONV_WARP0 + TMA_MAX_CONV_MIX)
         const uint32_t dst_main = smem_u32(stages) + (HQ + wi) * 128 + dst_lane;
         const uint32_t tab_u32 = smem_u32(tab_smem);
         const unsigned mask4 = P.mix_mask << 2;
+        const bool two_batches = P.nrb / (4 * W) == 8;  // 8 main row groups per warp (W = 4, 128 row-blocks); else 4
         int rs = g % NR, ss = g % NS;
         uint32_t rpar = 0, spar = 1;  // first wait on a fresh "empty" barrier passes
         int halo_turn = 0;
@@ -276,9 +277,9 @@ __global__ void __launch_bounds__(MIX ? 32 * (TMA_CONV_WARP0 + TMA_MAX_CONV_MIX)
                 tt = tl - ch * (unsigned)P.tiles_per_ch;
                 x = P.in + (size_t)ch * P.in_stride;
                 hist = P.hist_in + (size_t)ch * P.H;
-                tile0 = (long long)tt * TC_NRB * (long long)P.G;  // sample of (row-block 0, K-step 0)
+                tile0 = (long long)tt * P.nrb * (long long)P.G;  // sample of (row-block 0, K-step 0)
                 // rows the TMA tensor does not hold: history in front of the block, everything from the ragged row-block on
-                edge = (tt == 0 && J > 1) || ((long long)(tt + 1) * TC_NRB > X.rows_full);
+                edge = (tt == 0 && J > 1) || ((long long)(tt + 1) * P.nrb > X.rows_full);
                 if (MIX) {
                     if ((int)ch != cur_ch) {
                         // new channel: all converter warps rebuild the oscillator sequence lo[n] = T[(phi0 + n * freq) mod N]
@@ -320,10 +321,10 @@ __global__ void __launch_bounds__(MIX ? 32 * (TMA_CONV_WARP0 + TMA_MAX_CONV_MIX)
                     m.re = lds128<0>(tab_u32 + idx4);
                     m.im = lds128<0>(tab_u32 + mask4 + 4 + idx4);
                     tma_convert4_same<W>(src, dst, dst + hi_off, m);
-                    if (W == 4) tma_convert4_same<W>(src + 16 * 512, dst + 16 * 128, dst + 16 * 128 + hi_off, m);
+                    if (two_batches) tma_convert4_same<W>(src + 16 * 512, dst + 16 * 128, dst + 16 * 128 + hi_off, m);
                 } else {
                     tma_convert4<MIX, W>(src, dst, dst + hi_off, tab_u32, idx4, didx4, mask4);
-                    if (W == 4)
+                    if (two_batches)
                         tma_convert4<MIX, W>(src + 16 * 512, dst + 16 * 128, dst + 16 * 128 + hi_off, tab_u32, (idx4 + 4 * didx4) & mask4,
                                              didx4, mask4);
                 }
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(MIX ? 32 * (TMA_CONV_WARP0 + TMA_MAX_CONV_MIX)
                     uint4 v;
                     if (rb < -(J - 1)) {
                         v = make_uint4(0, 0, 0, 0);  // padding rows in front of the halo: never read by an MMA
-                    } else if (n < 0 || (long long)(tt * TC_NRB) + rb >= X.rows_full) {
+                    } else if (n < 0 || (long long)(tt * P.nrb) + rb >= X.rows_full) {
                         // carried history (already mixed) / ragged end: straight from global memory
                         if (MIX) {
                             v.x = tc_sample_mix(P, x, hist, n, ph0, fr);
@@ -437,7 +438,7 @@ __global__ void __launch_bounds__(MIX ? 32 * (TMA_CONV_WARP0 + TMA_MAX_CONV_MIX)
                 const unsigned tl = (unsigned)tile;
                 const unsigned ch = tl / (unsigned)P.tiles_per_ch;
                 const unsigned tt = tl - ch * (unsigned)P.tiles_per_ch;
-                const int row0 = (int)tt * TC_NRB - (J - 1);  // negative / beyond the end: zero-filled by the TMA unit
+                const int row0 = (int)tt * P.nrb - (J - 1);  // negative / beyond the end: zero-filled by the TMA unit
                 for (int kc = 0; kc < KS; ++kc) {
                     mbar_wait(bar_rempty + 8 * rs, rpar, P.error_flag);
                     if (!(DBG & 2)) {

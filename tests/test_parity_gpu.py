@@ -412,6 +412,72 @@ def test_tma_strided_channel_rows_and_output_views(S, corc, mix):
     assert (oh[:, :8] == 12345).all() and (oh[:, 8 + n // M:] == 12345).all()
 
 
+@pytest.mark.parametrize("M,nt,amp", [(4, 1023, 300), (16, 255, 400), (8, 63, 2000), (2, 9, 100), (1, 33, 8000), (3, 31, 500),
+                                      (6, 40, 500), (10, 90, 30000), (12, 255, 32767), (32, 64, 127), (16, 17, 1), (2, 700, 32767)])
+@pytest.mark.parametrize("mix", [False, True])
+def test_tma_p2_geometry(S, corc, monkeypatch, M, nt, amp, mix):
+    """The "p2" tile geometry of the TMA-fed kernel (taps of at most 2 signed byte digits: 64 outputs x 2 digit slots per
+    row-block, the two byte planes in separate accumulator columns), forced for every ratio / length it accepts -- it is
+    chosen automatically only for long filters (4+ lags, cfg 5).  Streaming blocks, ragged ends, several channels."""
+    monkeypatch.setenv("SRCDSP_TMA_P2", "1")
+    rng = np.random.default_rng(M * 104729 + nt)
+    taps = rng.integers(-amp, amp + 1, nt).astype(np.int32)
+    taps[0] = amp
+    C = 3
+    d = S.FilterDnsamplingFir(M, taps, channels=C, obsolete=True)
+    d.set_kernel(2)
+    chain, fs = d, None
+    if mix:
+        m = S.Mixer(channels=C)
+        fs = np.array([-0.3217, 0.5, 0.0371], np.float32)
+        m.setFrequency(fs)
+        chain = S.Ddc(m, d)
+    st = [(0, None)] * C
+    # (with the fused mixer only blocks the TMA-fed kernel takes: the register-staged fallback has no room for the
+    # sine table next to every master layout of this sweep)
+    for blk, n_out in enumerate([4096 * 2 + 76, 4096, 1300, 4096 * 3, 64, 100] if mix else [4096 * 2 + 77, 5, 4096, 1300, 4096 * 3, 64, 100]):
+        x = rng.integers(-32768, 32768, (C, n_out * M, 2)).astype(np.int16)
+        got = host(chain.step(dev(x))) if blk % 2 == 0 else chain.step(x)
+        # a whole row-block is 64 outputs here
+        assert d.last_kernel.startswith("dec_tma" if n_out >= 64 and (n_out * M) % 4 == 0 else "dec_tc"), (d.last_kernel, n_out)
+        for c in range(C):
+            phi, h = st[c]
+            y = x[c]
+            if mix:
+                y, phi = corc.mixer_step(y, phi, corc.mixer_set_frequency(float(fs[c])))
+            y, h = corc.dec_step(taps, M, y, h)
+            st[c] = (phi, h)
+            assert np.array_equal(got[c], y), (M, nt, blk, c)
+
+
+@pytest.mark.parametrize("M,nt,C,n,mix", [(4, 1023, 8, 1 << 22, False), (4, 1023, 8, 1 << 22, True), (16, 255, 32, 1 << 21, False),
+                                          (8, 512, 16, 1 << 22, True)])
+@pytest.mark.parametrize("p2", ["0", "1"])
+def test_tma_long_filter_many_tiles_match_imad(S, monkeypatch, M, nt, C, n, mix, p2):
+    """Long filters (many lags per K-step) with every CTA walking many tiles, in both tile geometries: the rings wrap,
+    both accumulator buffers alternate, the result is the IMAD kernel's."""
+    import torch
+    monkeypatch.setenv("SRCDSP_TMA_P2", p2)
+    taps = O.design_lowpass_taps(nt, M)
+    x = torch.empty((C, n, 2), dtype=torch.int16, device="cuda")
+    S.synth_fill(x, 0x5EED00AB)
+    outs = []
+    for kind in (1, 2):
+        d = S.FilterDnsamplingFir(M, taps, channels=C, obsolete=True)
+        d.set_kernel(kind)
+        chain = d
+        if mix:
+            m = S.Mixer(channels=C)
+            m.setFrequency((-1 + 2 * (np.arange(C) + 0.5) / C).astype(np.float32))
+            chain = S.Ddc(m, d)
+        for rep in range(2):  # carried history + repeated launches
+            y = chain.step(x)
+        torch.cuda.synchronize()
+        outs.append(y)
+        assert d.last_kernel.startswith("dec_tma" if kind == 2 else "dec_fir")
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_tc_rejects_what_it_cannot_do(S):
     d = S.FilterDnsamplingFir(8, [2 ** 24] * 16, obsolete=True)  # needs 4 signed byte digits
     d.set_kernel(2)
