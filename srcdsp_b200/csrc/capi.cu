@@ -1225,13 +1225,36 @@ struct UpBank : Bank {
         P.taps_poly = d_taps_poly;
         P.hist_in = d_hist[cur];
         P.vec_in = aligned16(in, in_stride);
-        const int span = G * UP_R * UP_NI;
+        // register-blocked kernel (4 phases x 4 inputs per thread, 16-byte stores) for the usual ratios; the
+        // generic one for any other L or unaligned output rows
+        const bool blocked = (L == 4 || L == 8 || L == 16) && aligned16(out, out_stride) && !getenv("SRCDSP_UP_GENERIC");
+        const int span = blocked ? up4_span(L) : G * UP_R * UP_NI;
+        const size_t smem = blocked ? ((size_t)L * (Hp + 4) + (size_t)span + Hp + 8) * 4 : smem_bytes;
         P.tiles_per_ch = (int)((n_tot + span - 1) / span);
         const long long grid = (long long)P.tiles_per_ch * C;
         if (grid > 0x7fffffffll) return fail(SRCDSP_E_SIZE, "step too large: %lld tiles", grid);
-        if (smem_bytes > 48 * 1024)
-            SRCDSP_CUDA(cudaFuncSetAttribute(up_fir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        up_fir_kernel<<<(int)grid, UP_NT, smem_bytes, stream>>>(P);
+        if (smem > 227 * 1024) return fail(SRCDSP_E_SIZE, "L=%d with %d taps needs %zu bytes of shared memory per CTA", L, ntaps, smem);
+#define SRCDSP_UP4(LL, SG)                                                                                                   \
+    do {                                                                                                                     \
+        if (smem > 48 * 1024)                                                                                                \
+            SRCDSP_CUDA(cudaFuncSetAttribute(up_fir4_kernel<LL, SG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+        up_fir4_kernel<LL, SG><<<(int)grid, UP_NT, smem, stream>>>(P);                                                        \
+    } while (0)
+        if (blocked) {
+            const bool single = Hp == UP_HC;
+            if (L == 4) {
+                if (single) SRCDSP_UP4(4, true); else SRCDSP_UP4(4, false);
+            } else if (L == 8) {
+                if (single) SRCDSP_UP4(8, true); else SRCDSP_UP4(8, false);
+            } else {
+                if (single) SRCDSP_UP4(16, true); else SRCDSP_UP4(16, false);
+            }
+        } else {
+            if (smem > 48 * 1024)
+                SRCDSP_CUDA(cudaFuncSetAttribute(up_fir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            up_fir_kernel<<<(int)grid, UP_NT, smem, stream>>>(P);
+        }
+#undef SRCDSP_UP4
         SRCDSP_LAUNCH_CHECK();
         dim3 hgrid((unsigned)std::max(1, std::min((H + 255) / 256, 64)), (unsigned)C);
         up_history_kernel<<<hgrid, 256, 0, stream>>>(in, in_stride, (long long)n_in, (long long)n_tot, d_hist[cur],

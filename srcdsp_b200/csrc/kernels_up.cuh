@@ -140,6 +140,136 @@ __global__ void __launch_bounds__(UP_NT) up_fir_kernel(const UpParams P)
     }
 }
 
+// Register-blocked variant for L in {4, 8, 16} and 16-byte aligned output rows: one thread owns 4 ADJACENT phases
+// x 4 consecutive inputs.  The sliding window (11 samples per 8 taps) is unpacked once for 16 outputs instead of
+// 15 samples for 8, the 4 x 8 taps stay in registers for the whole CTA when the filter has at most 8 taps per
+// phase (SINGLE), the 4 phases of an input leave as one STG.128 with an immediate offset, and all index math is
+// 32-bit: ~21 issued instructions per output (16 of them the IMADs) instead of ~36, so the multiply pipe -- the
+// roofline of this path, 16 IMAD per output at 64 lanes/clk/SM -- is what binds, not the issue slots.
+constexpr int UP4_R = 4;    // consecutive inputs per thread per iteration
+constexpr int UP4_PH = 4;   // adjacent phases per thread
+constexpr int UP4_NI = 8;   // iterations per CTA
+constexpr int up4_span(int L) { return (UP_NT / (L / UP4_PH)) * UP4_R * UP4_NI; }
+
+template <int L, bool SINGLE>
+__global__ void __launch_bounds__(UP_NT) up_fir4_kernel(const UpParams P)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    constexpr int PG = L / UP4_PH;        // phase groups per input
+    constexpr int G = UP_NT / PG;         // j-groups per CTA
+    constexpr int SPAN_IT = G * UP4_R;    // inputs per CTA iteration
+    constexpr int span = SPAN_IT * UP4_NI;
+    const int Hp = SINGLE ? UP_HC : P.Hp, HP = Hp + 4;
+    int32_t *tp = reinterpret_cast<int32_t *>(smem);  // [L][HP]
+    uint32_t *xs = smem + L * HP;                      // [span + Hp + 8]
+
+    const int tid = threadIdx.x;
+    const int ch = blockIdx.x / P.tiles_per_ch;
+    const int tile = blockIdx.x - ch * P.tiles_per_ch;
+    const long long J0 = (long long)tile * span;
+    const uint32_t *x = P.in + (size_t)ch * P.in_stride;
+    const uint32_t *hist = P.hist_in + (size_t)ch * P.H;
+
+    for (int i = tid; i < L * HP; i += UP_NT) tp[i] = P.taps_poly[i];
+
+    // xs[col] = xx[J0 - Hp + col], col in [0, span + Hp)
+    const int n_cols = span + Hp;
+    const long long n_lo = J0 - Hp;  // multiple of 8: 16-byte aligned when vec_in
+    const bool interior = P.vec_in && n_lo >= 0 && n_lo + n_cols <= P.n_in;
+    if (interior) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(x + n_lo);
+        for (int g = tid; g < (n_cols >> 2); g += UP_NT) reinterpret_cast<uint4 *>(xs)[g] = __ldg(src + g);
+    } else {
+        for (int g = tid; g < (n_cols >> 2); g += UP_NT) {
+            const long long n0 = n_lo + 4ll * g;
+            uint4 q;
+            if (P.vec_in && n0 >= 0 && n0 + 4 <= P.n_in) {
+                q = __ldg(reinterpret_cast<const uint4 *>(x + n0));
+            } else {
+                uint32_t v[4];
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const long long n = n0 + s;
+                    uint32_t w = 0;
+                    if (n >= 0) {
+                        if (n < P.n_in) w = __ldg(x + n);
+                    } else if (n >= -(long long)P.H) {
+                        w = __ldg(hist + (P.H + n));
+                    }
+                    v[s] = w;
+                }
+                q = make_uint4(v[0], v[1], v[2], v[3]);
+            }
+            reinterpret_cast<uint4 *>(xs)[g] = q;
+        }
+    }
+    __syncthreads();
+
+    const int phg = tid % PG, jg = tid / PG;
+    const int32_t *tpr = tp + (UP4_PH * phg) * HP;
+    const long long left = P.n_tot - J0;
+    const int rem = left < (long long)span ? (int)left : span;  // inputs of this CTA that exist
+    uint32_t *o = P.out + (size_t)ch * P.out_stride + (size_t)J0 * L + UP4_PH * phg;
+    const unsigned shift = P.shift;
+
+    int c[UP4_PH][UP_HC];
+    auto load_taps = [&](int i0) {
+#pragma unroll
+        for (int ph = 0; ph < UP4_PH; ++ph) {
+            const int4 c0 = *reinterpret_cast<const int4 *>(tpr + ph * HP + i0);
+            const int4 c1 = *reinterpret_cast<const int4 *>(tpr + ph * HP + i0 + 4);
+            c[ph][0] = c0.x, c[ph][1] = c0.y, c[ph][2] = c0.z, c[ph][3] = c0.w;
+            c[ph][4] = c1.x, c[ph][5] = c1.y, c[ph][6] = c1.z, c[ph][7] = c1.w;
+        }
+    };
+    if (SINGLE) load_taps(0);
+
+#pragma unroll 1
+    for (int it = 0; it < UP4_NI; ++it) {
+        const int jr = it * SPAN_IT + jg * UP4_R;  // first input (relative to J0) of this thread
+        if (jr >= rem) break;
+        int ar[UP4_PH][UP4_R], ai[UP4_PH][UP4_R];
+#pragma unroll
+        for (int ph = 0; ph < UP4_PH; ++ph)
+#pragma unroll
+            for (int r = 0; r < UP4_R; ++r) ar[ph][r] = ai[ph][r] = 0;
+#pragma unroll 1
+        for (int i0 = 0; i0 < Hp; i0 += UP_HC) {
+            // sample for (r, u): xx[J0 + jr + r - i0 - u] = xs[jr - i0 - 8 + Hp + (8 + r - u)], 8 + r - u in [1, 11]
+            const uint4 *wp = reinterpret_cast<const uint4 *>(xs + (jr - i0 - 8 + Hp));
+            const uint4 q0 = wp[0], q1 = wp[1], q2 = wp[2];
+            if (!SINGLE) load_taps(i0);
+            const uint32_t w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+            int re[12], im[12];
+#pragma unroll
+            for (int e = 1; e < 12; ++e) {
+                re[e] = sx_lo(w[e]);
+                im[e] = sx_hi(w[e]);
+            }
+#pragma unroll
+            for (int u = 0; u < UP_HC; ++u) {
+#pragma unroll
+                for (int r = 0; r < UP4_R; ++r) {
+#pragma unroll
+                    for (int ph = 0; ph < UP4_PH; ++ph) {
+                        ar[ph][r] += c[ph][u] * re[8 + r - u];
+                        ai[ph][r] += c[ph][u] * im[8 + r - u];
+                    }
+                }
+            }
+            if (SINGLE) break;
+        }
+        // the 4 phases of input jr + r are 4 consecutive output samples: one 16-byte store each
+        uint4 *op = reinterpret_cast<uint4 *>(o + (size_t)jr * L);
+#pragma unroll
+        for (int r = 0; r < UP4_R; ++r) {
+            if (jr + r < rem)
+                op[r * (L / 4)] = make_uint4(scale_pack_asym_sat(ar[0][r], ai[0][r], shift), scale_pack_asym_sat(ar[1][r], ai[1][r], shift),
+                                             scale_pack_asym_sat(ar[2][r], ai[2][r], shift), scale_pack_asym_sat(ar[3][r], ai[3][r], shift));
+        }
+    }
+}
+
 // New age-ordered history a'[k] = xx[n_tot - H + k], k < H  (xx includes the flush zeros).
 __global__ void up_history_kernel(const uint32_t *__restrict__ in, size_t in_stride, long long n_in,
                                   long long n_tot, const uint32_t *__restrict__ hist_in,

@@ -150,7 +150,8 @@ def test_decimator_reset_state_and_errors(S, corc):
     assert np.array_equal(d2.step(x), e)
 
 
-@pytest.mark.parametrize("L,nt", [(1, 5), (2, 8), (3, 30), (4, 32), (5, 35), (8, 64), (8, 128), (16, 64), (10, 200), (64, 512)])
+@pytest.mark.parametrize("L,nt", [(1, 5), (2, 8), (3, 30), (4, 32), (5, 35), (8, 64), (8, 128), (16, 64), (10, 200), (64, 512),
+                                  (4, 100), (16, 256), (8, 8), (16, 16)])
 def test_upsampler_sweep(S, corc, L, nt):
     rng = np.random.default_rng(L * 977 + nt)
     taps = rng.integers(-6000, 6000, nt).astype(np.int32)
@@ -167,6 +168,31 @@ def test_upsampler_sweep(S, corc, L, nt):
                 u.step(x, flush=fl, iterator_overload=sm == 1)
             assert np.array_equal(got, exp), (L, nt, sm, blk)
         assert np.array_equal(u.history(), h)
+
+
+@pytest.mark.parametrize("L,nt", [(8, 64), (8, 128), (4, 32), (16, 64), (16, 400)])
+def test_upsampler_blocked_kernel_many_tiles(S, corc, monkeypatch, L, nt):
+    """The register-blocked kernel (4 phases x 4 inputs per thread, L in {4, 8, 16}) over several CTAs per channel,
+    streaming blocks with ragged lengths and a flush; unaligned output rows take the generic kernel: same result."""
+    import torch
+    rng = np.random.default_rng(L * 131 + nt)
+    taps = O.design_interp_taps(nt, L)
+    C = 3
+    u = S.FilterUpsamplingFir(L, taps, channels=C)
+    g = S.FilterUpsamplingFir(L, taps, channels=C)
+    hs = [None] * C
+    for blk, n in enumerate([10000 + 3, 4096, 2049, 9000]):
+        fl = blk == 3
+        x = rng.integers(-32768, 32768, (C, n, 2)).astype(np.int16)
+        got = host(u.step(dev(x), flush=fl))
+        n_out = got.shape[1]
+        # the same through an output view at a 4-byte offset (not 16-byte aligned): generic kernel
+        big = torch.zeros((C, n_out + 8, 2), dtype=torch.int16, device="cuda")
+        g.step(dev(x), flush=fl, out=big[:, 1: 1 + n_out])
+        assert np.array_equal(host(big[:, 1: 1 + n_out]), got)
+        for c in range(C):
+            e, hs[c] = corc.up_step(taps, L, x[c], hs[c], fl, 0)
+            assert np.array_equal(got[c], e), (L, nt, blk, c)
 
 
 def test_upsampler_bank_and_errors(S, corc):
