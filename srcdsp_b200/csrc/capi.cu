@@ -957,6 +957,9 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
         T.n_stages = tc_stages;
         T.rb_stride = T.G;
         T.kc_stride = 32;
+        T.epi_sleep_ns = 400;
+        if (const char *e = getenv("SRCDSP_EPI_SLEEP")) T.epi_sleep_ns = (unsigned)std::max(0, atoi(e));
+        if (const char *e = getenv("SRCDSP_CONV_SLEEP")) T.conv_sleep_ns = (unsigned)std::max(0, atoi(e));
         if (mixer) {
             T.cs_table = mixer->d_cs;
             T.phi = P.phi;

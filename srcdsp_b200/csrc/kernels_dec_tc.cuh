@@ -68,6 +68,8 @@ struct TcParams {
                       // accumulate into separate halves of the accumulator (128 columns each) and meet in the epilogue
     int ksteps;       // K-steps per tile: M, or 2 * M in p2 mode (row-blocks of 64 * M samples)
     int M;            // decimation ratio
+    unsigned epi_sleep_ns;  // epilogue back-off between polls of the accumulator barrier
+    unsigned conv_sleep_ns; // TMA variant: converter back-off between polls of the raw-stage barrier (0: plain try_wait loop)
     int G;            // 32 * M samples per row-block
     int J;            // lags: 1 + ceil((Nt-1)/G)
     int tiles_per_ch;
@@ -139,6 +141,42 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int *er
         : "memory");
     if (!ok) {
         // error_flag points into mapped host memory: the record survives the trap that kills the context
+        if (error_flag && atomicExch(error_flag, 1) == 0) {
+            error_flag[1] = (int)bar;
+            error_flag[2] = (int)parity;
+            error_flag[3] = (int)blockIdx.x;
+            error_flag[4] = (int)threadIdx.x;
+            __threadfence_system();
+        }
+        __trap();
+    }
+}
+// Same for a role that waits long and is not on the critical path (the epilogue warps wait most of a tile for the
+// accumulator): try_wait's own suspend ends at every mbarrier event of the CTA (~40 ns apart here), so a failed
+// attempt is followed by a plain sleep -- ~10x fewer polling instructions taken from the working warps' issue slots.
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, int *error_flag, uint32_t sleep_ns)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .u32 n;\n\t"
+        "mov.u32 n, 0;\n\t"
+        "mov.u32 %0, 1;\n"
+        "MBAR_WAITB_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "@p bra MBAR_WAITB_DONE;\n\t"
+        "nanosleep.u32 %4;\n\t"
+        "add.u32 n, n, 1;\n\t"
+        "setp.lt.u32 p, n, 0x400000;\n\t"
+        "@p bra MBAR_WAITB_LOOP;\n\t"
+        "mov.u32 %0, 0;\n"
+        "MBAR_WAITB_DONE:\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(1000u), "r"(sleep_ns)
+        : "memory");
+    if (!ok) {
         if (error_flag && atomicExch(error_flag, 1) == 0) {
             error_flag[1] = (int)bar;
             error_flag[2] = (int)parity;
@@ -467,7 +505,11 @@ __device__ __forceinline__ void tc_epilogue_role(const TcParams &P, const TcRole
         const unsigned ch = (unsigned)tile / (unsigned)P.tiles_per_ch;  // total_tiles < 2^31 (host check)
         const long long tt = (long long)((unsigned)tile - ch * (unsigned)P.tiles_per_ch);
         uint32_t *o = P.out + (size_t)ch * P.out_stride;
-        mbar_wait_acc<DBG>(bar_tfull + 8 * acc, (acc_phases >> acc) & 1, P.error_flag, e_wait);
+        if ((DBG & 16) || P.epi_sleep_ns == 0) {
+            mbar_wait_acc<DBG>(bar_tfull + 8 * acc, (acc_phases >> acc) & 1, P.error_flag, e_wait);
+        } else {
+            mbar_wait_backoff(bar_tfull + 8 * acc, (acc_phases >> acc) & 1, P.error_flag, P.epi_sleep_ns);
+        }
         tc_fence_after();
         const uint32_t t_addr = tmem_base + ((uint32_t)(32 * warp) << 16) + acc * (2 * TC_NRB);
         if (P.p2) {
@@ -545,6 +587,7 @@ __device__ __forceinline__ void tc_epilogue_role(const TcParams &P, const TcRole
                 }
             }
         } else {
+        const bool full_tile = (tt + 1) * (long long)(TC_NRB * TC_BOUT) <= P.n_out;
 #pragma unroll 1
         for (int c0 = 0; c0 < ((P.debug & 4) ? 0 : 2 * TC_NRB); c0 += 32) {
             uint32_t v[32];
@@ -559,25 +602,33 @@ __device__ __forceinline__ void tc_epilogue_role(const TcParams &P, const TcRole
                   "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                 : "r"(t_addr + c0));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            // sum_w 256^w * D_w over the 4 lanes of the quad (mod 2^32, exactly the int32 wrap)
+            // sum_w 256^w * D_w over the 4 lanes of the quad (mod 2^32, exactly the int32 wrap), as a transposing
+            // reduction: every lane shifts its slot's sums into place, then two exchange rounds halve the columns a
+            // lane keeps, so that lane w ends with the complete sums of the row-blocks m = c0/2 + 4*i + w -- 24
+            // shuffles per 32 columns instead of 64, and no register selection afterwards
+            const int sh8 = 8 * w;
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                uint32_t s = v[c] << (8 * w);
-                s += __shfl_xor_sync(0xffffffffu, s, 1);
-                s += __shfl_xor_sync(0xffffffffu, s, 2);
-                v[c] = s;
-            }
-            // lane w finalises the row-blocks m = c0/2 + 4*i + w of this chunk
+            for (int c = 0; c < 32; ++c) v[c] <<= sh8;
+            const bool hi2 = (w & 2) != 0, hi1 = (w & 1) != 0;
+            uint32_t k1[16];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                // select v[2*(4*i + w)], v[2*(4*i + w) + 1] without dynamic register indexing
-                uint32_t re = v[8 * i], im = v[8 * i + 1];
-                if (w == 1) re = v[8 * i + 2], im = v[8 * i + 3];
-                if (w == 2) re = v[8 * i + 4], im = v[8 * i + 5];
-                if (w == 3) re = v[8 * i + 6], im = v[8 * i + 7];
-                const int m = (c0 >> 1) + 4 * i + w;
-                const long long idx = (tt * TC_NRB + m) * TC_BOUT + b;
-                if (idx < P.n_out) o[idx] = scale_pack<true>((int)re, (int)im, P.shift);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {  // lanes with w & 2 keep the row-blocks 4*i + 2, 4*i + 3 (columns 8*i + 4 ..)
+                    const uint32_t keep = hi2 ? v[8 * i + 4 + c] : v[8 * i + c];
+                    const uint32_t send = hi2 ? v[8 * i + c] : v[8 * i + 4 + c];
+                    k1[4 * i + c] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                }
+            }
+            const long long idx0 = (tt * TC_NRB + (c0 >> 1) + w) * TC_BOUT + b;  // row-block c0/2 + w, output b
+            uint32_t *op = o + idx0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {  // lanes with w & 1 keep the odd row-block of the pair
+                const uint32_t kr = hi1 ? k1[4 * i + 2] : k1[4 * i], sr = hi1 ? k1[4 * i] : k1[4 * i + 2];
+                const uint32_t ki = hi1 ? k1[4 * i + 3] : k1[4 * i + 1], si = hi1 ? k1[4 * i + 1] : k1[4 * i + 3];
+                const uint32_t re = kr + __shfl_xor_sync(0xffffffffu, sr, 1);
+                const uint32_t im = ki + __shfl_xor_sync(0xffffffffu, si, 1);
+                if (full_tile || idx0 + 4 * i * TC_BOUT < P.n_out) op[4 * i * TC_BOUT] = scale_pack_sym_sat((int)re, (int)im, P.shift);
             }
         }
         }

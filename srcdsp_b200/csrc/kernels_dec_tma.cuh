@@ -308,7 +308,10 @@ __global__ void __launch_bounds__(MIX ? 32 * (TMA_CONV_WARP0 + TMA_MAX_CONV_MIX)
             // parity wait below would then pass a whole phase early.  Waiting first until that use has been
             // released (the phase before ours of the "empty" barrier; passes at once on a fresh barrier) closes it.
             if (X.shared_raw) mbar_wait_acc<DBG>(bar_rempty + 8 * rs, rpar ^ 1, P.error_flag, w_wait_raw);
-            mbar_wait_acc<DBG>(bar_rfull + 8 * rs, rpar, P.error_flag, w_wait_raw);
+            if (!(DBG & 16) && P.conv_sleep_ns)
+                mbar_wait_backoff(bar_rfull + 8 * rs, rpar, P.error_flag, P.conv_sleep_ns);
+            else
+                mbar_wait_acc<DBG>(bar_rfull + 8 * rs, rpar, P.error_flag, w_wait_raw);
             mbar_wait_acc<DBG>(bar_empty + 8 * ss, spar, P.error_flag, w_wait_split);
             if (P.debug & 8) {
                 // timing experiment: barriers only
