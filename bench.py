@@ -250,7 +250,7 @@ def corr_bench(args, w, base, S, torch, device):
     alg = 4.0 * C * n
     line = dict(base, metric="input Msamples/s", value=C * n / (ms * 1e-3) / 1e6, ms_per_step=ms,
                 roofline={"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                          "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "corr_scan_kernel",
+                          "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "corr_scan_blocked_kernel",
                           "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "kernel_ms": ms,
                           "note": "step() is synchronous (it returns found / corrIndex): ms includes the 1 KB D2H of the result; "
                                   "2*N = 64 complex multiply-adds + 64 energy terms per sample put the scan on the IMAD pipe"},
@@ -389,7 +389,7 @@ def main():
         traffic = json.load(open(tp)).get(args.workload)
     roof = {"bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
             "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / peak, "traffic": traffic,
-            "kernel": dec.last_kernel if dec is not None else ("mixer_kernel" if w["kind"] == "mix" else "up_fir_kernel"), "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+            "kernel": dec.last_kernel if dec is not None else ("mixer_kernel" if w["kind"] == "mix" else "up_fir4_kernel<8,true>" if w["kind"] == "up" else "up_fir_kernel"), "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
             "kernel_ms": k_ms,
             "imad_note": "imad_frac = the same work counted as 2*taps INT32 multiply-adds per output against "
                          "148 SM x 64 IMAD/clk x sm_max_mhz: the ceiling of any CUDA-core kernel (SURVEY.md 8(d)); "

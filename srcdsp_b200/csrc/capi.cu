@@ -1324,6 +1324,7 @@ struct CorrBank : Bank {
         SRCDSP_CUDA(cudaMalloc(&d_cnt, (size_t)C * 8));
         h_found.resize(C);
         SRCDSP_CUDA(cudaFuncSetAttribute(corr_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        SRCDSP_CUDA(cudaFuncSetAttribute(corr_scan_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         return reset();
     }
 
@@ -1403,8 +1404,18 @@ struct CorrBank : Bank {
         SRCDSP_CUDA(cudaMemsetAsync(d_found, 0x7f, (size_t)C * sizeof(int), stream));  // 0x7f7f7f7f > any index
         const int halo = (N - 1) * S + 2;
         const size_t smem = (3 * ((size_t)halo + CORR_THREADS) + 2 * N + 2 * (CORR_THREADS + 2)) * 4;
-        dim3 grid((unsigned)((n + CORR_THREADS - 1) / CORR_THREADS), (unsigned)C);
-        corr_scan_kernel<<<grid, CORR_THREADS, smem, stream>>>(P);
+        // register-blocked scan (8 outputs S apart per thread) for power-of-two strides; the one-output-per-thread
+        // kernel for any other stride
+        const bool blocked = (S & (S - 1)) == 0 && S <= CORR_THREADS && !getenv("SRCDSP_CORR_GENERIC") &&
+                             corr_blocked_smem(N, S) <= 200 * 1024;
+        if (blocked) {
+            const int TT = CORR_THREADS * CORR_R;
+            dim3 grid((unsigned)((n + TT - 1) / TT), (unsigned)C);
+            corr_scan_blocked_kernel<<<grid, CORR_THREADS, corr_blocked_smem(N, S), stream>>>(P, aligned16(d_in, stride) ? 1 : 0);
+        } else {
+            dim3 grid((unsigned)((n + CORR_THREADS - 1) / CORR_THREADS), (unsigned)C);
+            corr_scan_kernel<<<grid, CORR_THREADS, smem, stream>>>(P);
+        }
         SRCDSP_LAUNCH_CHECK();
         corr_finish_kernel<<<C, CORR_THREADS, 0, stream>>>(P);
         SRCDSP_LAUNCH_CHECK();

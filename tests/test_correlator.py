@@ -76,8 +76,15 @@ def S_(built_lib):
     return srcdsp_b200
 
 
+# (the blocked scan kernel covers power-of-two strides: tiles of 2048 outputs, tap blocks of 8 with zero padding; other
+# strides take the one-output-per-thread kernel)
+GPU_CASES = CASES + [(5, 32, 4, 300000, [100000, 100000, 100000]), (6, 20, 16, 9000, [2048, 2049, 4903]),
+                     (7, 5, 3, 5000, [5000]), (8, 100, 2, 20000, [7000, 13000]), (9, 33, 1, 10000, [2047, 2, 7951]),
+                     (10, 64, 32, 30000, [30000]), (11, 7, 64, 9000, [4500, 4500])]
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("seed,N,S,n,blocks", CASES + [(5, 32, 4, 300000, [100000, 100000, 100000])])
+@pytest.mark.parametrize("seed,N,S,n,blocks", GPU_CASES)
 def test_gpu_correlator_matches_oracle(S_, seed, N, S, n, blocks):
     pat, x, _ = make_case(seed, N, S, n, n_bursts=4)
     a = O.OrcCorrelator(O.corc(), N, S)
