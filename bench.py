@@ -143,17 +143,17 @@ def cpu_reference_run(w, steps: int, warmup: int, cores: int, target_cpu_seconds
     block = 1 << 16
     c = O.corc()
     lo = (-1 + 2 * (np.arange(ch) + 0.5) / ch).astype(np.float32) if w["mix"] else None
-    kind = {"dec": 0, "ddc": 1, "ddc2": 2, "up": 3}[w["kind"]]
+    wk = {"dec": 0, "ddc": 1, "ddc2": 2, "up": 3}[w["kind"]]  # harness selector (not the cpu_baseline "kind")
     # pilot run on one 64Ki block per channel sizes the sample for ~target_cpu_seconds of CPU work
     xp = np.stack([c.synth(SEED, k, 0, block, 2) for k in range(ch)])
-    tp, _ = r.bench_bank(kind, xp, block, cores, M, taps, w.get("M2", 1), taps2, lo_freq=lo)
+    tp, _ = r.bench_bank(wk, xp, block, cores, M, taps, w.get("M2", 1), taps2, lo_freq=lo)
     wall = target_cpu_seconds / cores
     n = int(block * max(1.0, wall / max(tp, 1e-6))) // block * block
     n = max(block, min(n, w["n"], (2 << 30) // (4 * ch) // block * block))
     x = np.stack([c.synth(SEED, k, 0, n, 2) for k in range(ch)])
     times = []
     for i in range(warmup + steps):
-        secs, _ = r.bench_bank(kind, x, block, cores, M, taps, w.get("M2", 1), taps2, lo_freq=lo)
+        secs, _ = r.bench_bank(wk, x, block, cores, M, taps, w.get("M2", 1), taps2, lo_freq=lo)
         if i >= warmup:
             times.append(secs)
     n_out = int(ch * n * out_per_in(w))
@@ -248,9 +248,11 @@ def corr_bench(args, w, base, S, torch, device):
     clocks = sampler.stop()
     peak, peak_src = peaks()
     alg = 4.0 * C * n
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    traffic = json.load(open(tp)).get("corr") if os.path.exists(tp) else None
     line = dict(base, metric="input Msamples/s", value=C * n / (ms * 1e-3) / 1e6, ms_per_step=ms,
                 roofline={"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                          "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "corr_scan_blocked_kernel",
+                          "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": traffic, "kernel": "corr_scan_blocked_kernel",
                           "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "kernel_ms": ms,
                           "note": "step() is synchronous (it returns found / corrIndex): ms includes the 1 KB D2H of the result; "
                                   "2*N = 64 complex multiply-adds + 64 energy terms per sample put the scan on the IMAD pipe"},
