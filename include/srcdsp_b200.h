@@ -157,6 +157,11 @@ int srcdsp_up_step(srcdsp_up_t h, const int16_t *in_iq, size_t in_stride, size_t
 int srcdsp_up_get_length(srcdsp_up_t h, int *length);
 int srcdsp_up_get_imp_length(srcdsp_up_t h, int *imp_length);
 int srcdsp_up_get_ratio(srcdsp_up_t h, int *ratio);
+/* which FIR kernel the last step launched: 0 none yet, 1 up_fir_kernel (any L), 2 up_fir4_kernel (register
+ * blocked, L in {4, 8, 16}), 3 up_tc_kernel (tcgen05 int8: one MMA per 4096 outputs; applicable when 32 % L == 0, the
+ * filter has at most 16 - 32 / L taps per phase, |taps| < 2^23 and the channel rows are 16-byte aligned; chosen when
+ * the filter has more than 8 taps per phase and the batch fills the machine) */
+int srcdsp_up_get_last_kernel(srcdsp_up_t h, int *kind);
 /* history of one channel in age order, oldest first, ntaps/L - 1 complex samples */
 int srcdsp_up_get_state(srcdsp_up_t h, int ch, int16_t *history_iq, size_t *n_samples);
 int srcdsp_up_set_state(srcdsp_up_t h, int ch, const int16_t *history_iq, size_t n_samples);

@@ -315,6 +315,12 @@ class FilterUpsamplingFir(_Handle):
                                    1 if iterator_overload else 0))
         return out
 
+    @property
+    def last_kernel(self) -> str:
+        v = C.c_int()
+        check(lib().srcdsp_up_get_last_kernel(self._h, C.byref(v)))
+        return {0: "none", 1: "up_fir_kernel", 2: "up_fir4_kernel", 3: "up_tc_kernel (tcgen05 int8)"}[v.value]
+
     def sync(self):
         check(lib().srcdsp_up_sync(self._h))
 

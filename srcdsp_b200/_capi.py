@@ -74,6 +74,7 @@ PROTOTYPES = {
     "srcdsp_up_get_length": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "srcdsp_up_get_imp_length": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "srcdsp_up_get_ratio": (C.c_int, [_vp, C.POINTER(C.c_int)]),
+    "srcdsp_up_get_last_kernel": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "srcdsp_up_get_state": (C.c_int, [_vp, C.c_int, _i16p, C.POINTER(_sz)]),
     "srcdsp_up_set_state": (C.c_int, [_vp, C.c_int, _i16p, _sz]),
     "srcdsp_up_set_stream": (C.c_int, [_vp, _vp]),

@@ -19,6 +19,7 @@
 #include "kernels_dec_tc.cuh"
 #include "kernels_dec_tma.cuh"
 #include "kernels_up.cuh"
+#include "kernels_up_tc.cuh"
 #include "kernels_corr.cuh"
 
 namespace srcdsp {
@@ -1129,6 +1130,73 @@ struct UpBank : Bank {
     uint32_t *d_hist[2] = {nullptr, nullptr};  // [C][H] age order, [H-1] newest, [0] stale slot
     int cur = 0;
     size_t smem_bytes = 0;
+    // tcgen05 form (kernels_up_tc.cuh): one MMA per 4096 outputs; applicable when 32 % L == 0, the group window
+    // 32 / L + H - 1 fits 15 samples and the taps fit 3 signed byte digits
+    uint8_t *d_a_image = nullptr;
+    bool tc_ok = false;
+    int tc_digits3 = 0, tc_KW = 0;
+    int *h_diag = nullptr, *d_diag = nullptr;
+    int sm_count = 148;
+    int last_kernel = 0;  // 1 = up_fir_kernel, 2 = up_fir4_kernel, 3 = up_tc_kernel
+
+    int prepare_tc(const int32_t *t, int n)
+    {
+        tc_ok = false;
+        if (d_a_image) {
+            cudaFree(d_a_image);
+            d_a_image = nullptr;
+        }
+        const int Hh = n / L;
+        if (L > 32 || 32 % L != 0) return SRCDSP_OK;
+        const int JJ = 32 / L, KW = JJ + Hh - 1;
+        if (KW > 15) return SRCDSP_OK;
+        auto digits = [](long long v, int nd, int *d) {  // signed base-256 digits, returns the remainder
+            for (int w = 0; w < nd; ++w) {
+                const int dg = (int)(((v + 128) & 255) - 128);
+                d[w] = dg;
+                v = (v - dg) >> 8;
+            }
+            return v;
+        };
+        std::vector<uint8_t> img(UPT_A_BYTES, 0);
+        int d3 = 0;
+        for (int g = 0; g < 32; ++g) {
+            const int jj = g / L, p = g % L;
+            long long sum = 0;
+            for (int i = 0; i < Hh; ++i) sum += t[p + i * L];
+            int bd[4];
+            digits((long long)(int32_t)(uint32_t)(128ull * (unsigned long long)sum), 4, bd);  // mod 2^32
+            if (bd[3] != 0) d3 = 1;  // the bias alone can reach the fourth slot
+            for (int w = 0; w < 4; ++w) {
+                const int row = 32 * (g >> 3) + 8 * w + (g & 7);
+                for (int m = 0; m < KW; ++m) {
+                    const int i = jj - m + Hh - 1;
+                    if (i < 0 || i >= Hh) continue;
+                    int d[3];
+                    if (digits(t[p + i * L], 3, d) != 0) return SRCDSP_OK;  // |c| >= 2^23: CUDA-core kernels only
+                    if (d[2] != 0) d3 = 1;
+                    if (w < 3) img[(size_t)row * 16 + m] = (uint8_t)d[w];                  // low plane, k = m
+                    if (w >= 1) img[(size_t)2048 + (size_t)row * 16 + m] = (uint8_t)d[w - 1];  // high plane, k = 16 + m
+                }
+                img[(size_t)row * 16 + 15] = (uint8_t)bd[w];  // bias column (the sample operand holds a 1 there)
+            }
+        }
+        DeviceGuard g(device);
+        SRCDSP_CUDA(cudaMalloc(&d_a_image, UPT_A_BYTES));
+        SRCDSP_CUDA(cudaMemcpy(d_a_image, img.data(), UPT_A_BYTES, cudaMemcpyHostToDevice));
+        if (!h_diag) {
+            SRCDSP_CUDA(cudaHostAlloc(&h_diag, 64, cudaHostAllocMapped));
+            memset(h_diag, 0, 64);
+            SRCDSP_CUDA(cudaHostGetDevicePointer(&d_diag, h_diag, 0));
+            cudaDeviceProp prop;
+            SRCDSP_CUDA(cudaGetDeviceProperties(&prop, device));
+            sm_count = prop.multiProcessorCount;
+        }
+        tc_digits3 = d3;
+        tc_KW = KW;
+        tc_ok = true;
+        return SRCDSP_OK;
+    }
 
     int set_coefficients(const int32_t *t, int n)
     {
@@ -1192,7 +1260,7 @@ struct UpBank : Bank {
         smem_bytes = ((size_t)L * HP + (size_t)span + Hp + 8) * 4;
         if (smem_bytes > 227 * 1024)
             return fail(SRCDSP_E_SIZE, "L=%d with %d taps needs %zu bytes of shared memory per CTA", L, n, smem_bytes);
-        return SRCDSP_OK;
+        return prepare_tc(t, n);
     }
 
     int reset()
@@ -1230,7 +1298,65 @@ struct UpBank : Bank {
         P.vec_in = aligned16(in, in_stride);
         // register-blocked kernel (4 phases x 4 inputs per thread, 16-byte stores) for the usual ratios; the
         // generic one for any other L or unaligned output rows
+        if (h_diag && h_diag[0])
+            return fail(SRCDSP_E_CUDA, "the tcgen05 upsampler timed out waiting on mbarrier 0x%x (parity %d, CTA %d, thread %d) and trapped",
+                        h_diag[1], h_diag[2], h_diag[3], h_diag[4]);
+        // tcgen05 kernel: when applicable, faster and the batch fills the machine (SRCDSP_UP_TC = 1 forces it, 0 disables it)
+        {
+            const int JJ = 32 / std::max(1, std::min(L, 32));
+            const long long tiles = tc_ok ? (long long)C * (((long long)n_tot + UPT_GROUPS * JJ - 1) / (UPT_GROUPS * JJ)) : 0;
+            const bool tc_able = tc_ok && aligned16(in, in_stride) && tiles > 0 && tiles < 0x7fffffffll;  // cp.async 16-byte chunks
+            // Its rate does not depend on the filter length (one MMA per 4096 outputs; the 32 bytes of accumulator per
+            // output that the epilogue reads from TMEM bound it at ~0.85-0.9 T out/s), the CUDA-core kernels pay 2 IMADs
+            // per tap: they win up to 8 taps per phase (one tap block, ~1.0 T out/s) and lose beyond (0.5 T out/s).
+            bool use_tc = tc_able && tiles >= sm_count / 2 && H > UP_HC;
+            if (const char *e = getenv("SRCDSP_UP_TC")) use_tc = tc_able && atoi(e) != 0;
+            if (use_tc) {
+                UpTcParams T{};
+                T.in = in, T.out = out, T.in_stride = in_stride, T.out_stride = out_stride;
+                T.n_in = (long long)n_in, T.n_tot = (long long)n_tot;
+                T.L = L, T.JJ = JJ, T.H = H, T.KW = tc_KW;
+                T.halo = (H - 1 + 3) & ~3;
+                T.raw_words = upt_raw_words(JJ, H);
+                T.a_image = d_a_image;
+                T.hist_in = d_hist[cur];
+                T.shift = P.shift;
+                T.tiles_per_ch = (int)(tiles / C);
+                T.total_tiles = tiles;
+                T.error_flag = d_diag;
+                if (const char *e = getenv("SRCDSP_UPT_DEBUG")) T.debug = atoi(e);
+                const int tgrid = (int)std::min<long long>(tiles, sm_count);
+                const size_t tsmem = upt_smem_bytes(JJ, H);
+                static unsigned long long *d_cnt = nullptr;
+                if (T.debug & 8) {
+                    if (!d_cnt) cudaMalloc(&d_cnt, 64);
+                    unsigned long long c[8];
+                    cudaMemcpy(c, d_cnt, 64, cudaMemcpyDeviceToHost);
+                    fprintf(stderr, "up_tc counters (cycles summed over warps): conv total %llu wait_empty %llu wait_data %llu | mma total %llu wait_full %llu wait_tempty %llu | epi total %llu wait_tfull %llu\n", c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7]);
+                    cudaMemset(d_cnt, 0, 64);
+                    T.counters = d_cnt;
+                }
+                if (tc_digits3) {
+                    SRCDSP_CUDA(cudaFuncSetAttribute(up_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                    up_tc_kernel<true><<<tgrid, UPT_THREADS, tsmem, stream>>>(T);
+                } else {
+                    SRCDSP_CUDA(cudaFuncSetAttribute(up_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                    up_tc_kernel<false><<<tgrid, UPT_THREADS, tsmem, stream>>>(T);
+                }
+                SRCDSP_LAUNCH_CHECK();
+                last_kernel = 3;
+                dim3 hgrid((unsigned)std::max(1, std::min((H + 255) / 256, 64)), (unsigned)C);
+                up_history_kernel<<<hgrid, 256, 0, stream>>>(in, in_stride, (long long)n_in, (long long)n_tot, d_hist[cur],
+                                                             d_hist[cur ^ 1], H);
+                SRCDSP_LAUNCH_CHECK();
+                count_launch(2);
+                cur ^= 1;
+                top += n_tot;
+                return SRCDSP_OK;
+            }
+        }
         const bool blocked = (L == 4 || L == 8 || L == 16) && aligned16(out, out_stride) && !getenv("SRCDSP_UP_GENERIC");
+        last_kernel = blocked ? 2 : 1;
         const int span = blocked ? up4_span(L) : G * UP_R * UP_NI;
         const size_t smem = blocked ? ((size_t)L * (Hp + 4) + (size_t)span + Hp + 8) * 4 : smem_bytes;
         P.tiles_per_ch = (int)((n_tot + span - 1) / span);
@@ -1276,6 +1402,8 @@ struct UpBank : Bank {
         if (d_taps_poly) cudaFree(d_taps_poly);
         if (d_hist[0]) cudaFree(d_hist[0]);
         if (d_hist[1]) cudaFree(d_hist[1]);
+        if (d_a_image) cudaFree(d_a_image);
+        if (h_diag) cudaFreeHost(h_diag);
     }
 };
 
@@ -1924,6 +2052,13 @@ int srcdsp_up_get_ratio(srcdsp_up_t h, int *v)
     CHECK_HANDLE(h);
     if (!v) return fail(SRCDSP_E_INVALID, "null pointer");
     *v = h->L;
+    return SRCDSP_OK;
+}
+int srcdsp_up_get_last_kernel(srcdsp_up_t h, int *v)
+{
+    CHECK_HANDLE(h);
+    if (!v) return fail(SRCDSP_E_INVALID, "null pointer");
+    *v = h->last_kernel;
     return SRCDSP_OK;
 }
 // the public state is the H-1 samples the next outputs depend on, oldest first

@@ -195,6 +195,64 @@ def test_upsampler_blocked_kernel_many_tiles(S, corc, monkeypatch, L, nt):
             assert np.array_equal(got[c], e), (L, nt, blk, c)
 
 
+@pytest.mark.parametrize("L,nt,amp", [(8, 64, 6000), (8, 96, 30000), (8, 8, 100), (4, 32, 6000), (4, 20, 2 ** 22), (16, 64, 6000),
+                                      (16, 224, 127), (32, 480, 6000), (32, 32, 40000), (8, 64, 2 ** 22)])
+@pytest.mark.parametrize("sm", [0, 1])
+def test_upsampler_tcgen05_kernel(S, corc, monkeypatch, L, nt, amp, sm):
+    """The tcgen05 form of the interpolator (one int8 MMA per 4096 outputs, bias column, low byte plane biased to
+    signed), forced for every ratio / length / tap magnitude it accepts: streaming blocks with ragged lengths, history,
+    flush, both overloads, several channels, full-scale input (saturation of the asymmetric clamp)."""
+    monkeypatch.setenv("SRCDSP_UP_TC", "1")
+    rng = np.random.default_rng(L * 7919 + nt + sm)
+    taps = rng.integers(-amp, amp + 1, nt).astype(np.int32)
+    taps[-2:] = 0
+    taps[0] = amp
+    C = 3
+    u = S.FilterUpsamplingFir(L, taps, channels=C)
+    hs = [None] * C
+    for blk, n in enumerate([4, 4096 + 76, 8, 1111, 3 * 512 * 4, 64, 5]):
+        x = rng.integers(-32768, 32768, (C, n, 2)).astype(np.int16)
+        fl = blk == 5
+        got = host(u.step(dev(x), flush=fl, iterator_overload=sm == 1)) if blk % 2 else u.step(x, flush=fl, iterator_overload=sm == 1)
+        if blk % 2:  # device rows: the cp.async feed needs them 16-byte aligned (n % 4 == 0), else a CUDA-core kernel runs
+            assert u.last_kernel.startswith("up_tc" if n % 4 == 0 else "up_fir"), (u.last_kernel, n)
+        for c in range(C):
+            e, hs[c] = corc.up_step(taps, L, x[c], hs[c], fl, sm)
+            assert np.array_equal(got[c], e), (L, nt, sm, blk, c)
+
+
+def test_upsampler_kernel_selection(S, monkeypatch):
+    """Automatic choice on a batch that fills the machine: up to 8 taps per phase the register-blocked CUDA-core kernel,
+    beyond that the tcgen05 kernel (whose rate does not depend on the filter length)."""
+    import torch
+    monkeypatch.delenv("SRCDSP_UP_TC", raising=False)
+    C, L, n = 128, 8, 1 << 14
+    x = torch.zeros((C, n, 2), dtype=torch.int16, device="cuda")
+    for nt, want in ((64, "up_fir4"), (96, "up_tc"), (128, "up_fir4")):  # 128 taps: 16 per phase do not fit one MMA
+        u = S.FilterUpsamplingFir(L, O.design_interp_taps(nt, L), channels=C)
+        u.step(x)
+        assert u.last_kernel.startswith(want), (nt, u.last_kernel)
+
+
+def test_upsampler_tcgen05_many_tiles_match_cuda_core_kernel(S, monkeypatch):
+    """cfg-4 shape in miniature with every CTA walking several tiles: the stage ring and both accumulators wrap."""
+    import torch
+    C, L, nt, n = 64, 8, 64, 1 << 16
+    taps = O.design_interp_taps(nt, L)
+    x = torch.empty((C, n, 2), dtype=torch.int16, device="cuda")
+    S.synth_fill(x, 0x5EED00C4)
+    outs = []
+    for tc in ("0", "1"):
+        monkeypatch.setenv("SRCDSP_UP_TC", tc)
+        u = S.FilterUpsamplingFir(L, taps, channels=C)
+        for rep in range(3):  # carried history + repeated launches
+            y = u.step(x)
+        torch.cuda.synchronize()
+        assert u.last_kernel.startswith("up_tc" if tc == "1" else "up_fir4")
+        outs.append(y)
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_upsampler_bank_and_errors(S, corc):
     rng = np.random.default_rng(2)
     C, L, nt = 4, 8, 64
