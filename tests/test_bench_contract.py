@@ -1,0 +1,33 @@
+"""bench.py's JSON contract on the CPU box: the reference arm (`--impl reference`) runs here (it times the compiled
+reference / the oracle on the host cores) and must print one line with the agreed keys and types."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.timeout(600)
+def test_reference_arm_line():
+    if O.ref() is None:
+        pytest.skip("no compiled reference here")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, cwd=ROOT, timeout=580)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference"
+    assert line["metric"] == "output Msamples/s" and line["unit"] == "Msamples/s" and line["higher_is_better"] is True
+    assert line["n_gpus"] == 1 and line["steps"] == 1 and line["warmup"] == 0
+    assert isinstance(line["value"], float) and line["value"] > 0
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and isinstance(cb["cores"], int) and cb["cores"] >= 1
+    assert cb["value"] == line["value"] and isinstance(cb["sample"], str) and cb["sample"]
+    e = line["e2e"]
+    assert e == {"value": line["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["config"]["workload"].startswith("cfg2")
+    assert line["vs_baseline"] is None and line["data"] == "synthetic"
