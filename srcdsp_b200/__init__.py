@@ -319,7 +319,8 @@ class FilterUpsamplingFir(_Handle):
     def last_kernel(self) -> str:
         v = C.c_int()
         check(lib().srcdsp_up_get_last_kernel(self._h, C.byref(v)))
-        return {0: "none", 1: "up_fir_kernel", 2: "up_fir4_kernel", 3: "up_tc_kernel (tcgen05 int8)"}[v.value]
+        return {0: "none", 1: "up_fir_kernel", 2: "up_fir4_kernel", 3: "up_tc_kernel (tcgen05 int8)",
+                4: "up_tc2_kernel (tcgen05 int8, taps on the N side)"}[v.value]
 
     def sync(self):
         check(lib().srcdsp_up_sync(self._h))

@@ -1137,7 +1137,8 @@ struct UpBank : Bank {
     int tc_digits3 = 0, tc_KW = 0;
     int *h_diag = nullptr, *d_diag = nullptr;
     int sm_count = 148;
-    int last_kernel = 0;  // 1 = up_fir_kernel, 2 = up_fir4_kernel, 3 = up_tc_kernel
+    int last_kernel = 0;  // 1 = up_fir_kernel, 2 = up_fir4_kernel, 3 = up_tc_kernel, 4 = up_tc2_kernel
+    bool last_kernel_form2 = false;
 
     int prepare_tc(const int32_t *t, int n)
     {
@@ -1158,7 +1159,8 @@ struct UpBank : Bank {
             }
             return v;
         };
-        std::vector<uint8_t> img(UPT_A_BYTES, 0);
+        // digit tables [g][w][k]: low-plane columns k = m (and the bias column 15), high-plane columns k = 16 + m
+        std::vector<int8_t> lo(32 * 4 * 16, 0), hi(32 * 4 * 16, 0);
         int d3 = 0;
         for (int g = 0; g < 32; ++g) {
             const int jj = g / L, p = g % L;
@@ -1168,22 +1170,35 @@ struct UpBank : Bank {
             digits((long long)(int32_t)(uint32_t)(128ull * (unsigned long long)sum), 4, bd);  // mod 2^32
             if (bd[3] != 0) d3 = 1;  // the bias alone can reach the fourth slot
             for (int w = 0; w < 4; ++w) {
-                const int row = 32 * (g >> 3) + 8 * w + (g & 7);
                 for (int m = 0; m < KW; ++m) {
                     const int i = jj - m + Hh - 1;
                     if (i < 0 || i >= Hh) continue;
                     int d[3];
                     if (digits(t[p + i * L], 3, d) != 0) return SRCDSP_OK;  // |c| >= 2^23: CUDA-core kernels only
                     if (d[2] != 0) d3 = 1;
-                    if (w < 3) img[(size_t)row * 16 + m] = (uint8_t)d[w];                  // low plane, k = m
-                    if (w >= 1) img[(size_t)2048 + (size_t)row * 16 + m] = (uint8_t)d[w - 1];  // high plane, k = 16 + m
+                    if (w < 3) lo[(g * 4 + w) * 16 + m] = (int8_t)d[w];
+                    if (w >= 1) hi[(g * 4 + w) * 16 + m] = (int8_t)d[w - 1];
                 }
-                img[(size_t)row * 16 + 15] = (uint8_t)bd[w];  // bias column (the sample operand holds a 1 there)
+                lo[(g * 4 + w) * 16 + 15] = (int8_t)bd[w];  // bias column (the sample operand holds a 1 there)
             }
         }
+        // two images of the same digits: up_tc_kernel's M-side operand [2][128][16] (row 32 * (g / 8) + 8 * w + g % 8) and
+        // up_tc2_kernel's N-side operand [2][32 * S][16] (row 32 * w + g; S = 3 slots unless the fourth is in use)
+        std::vector<uint8_t> img(2 * UPT_A_BYTES, 0);
+        const int S2 = d3 ? 4 : 3, N2 = 32 * S2;
+        for (int g = 0; g < 32; ++g)
+            for (int w = 0; w < 4; ++w) {
+                const int row = 32 * (g >> 3) + 8 * w + (g & 7), row2 = 32 * w + g;
+                memcpy(&img[(size_t)row * 16], &lo[(g * 4 + w) * 16], 16);
+                memcpy(&img[(size_t)2048 + (size_t)row * 16], &hi[(g * 4 + w) * 16], 16);
+                if (w < S2) {
+                    memcpy(&img[(size_t)UPT_A_BYTES + (size_t)row2 * 16], &lo[(g * 4 + w) * 16], 16);
+                    memcpy(&img[(size_t)UPT_A_BYTES + (size_t)(N2 + row2) * 16], &hi[(g * 4 + w) * 16], 16);
+                }
+            }
         DeviceGuard g(device);
-        SRCDSP_CUDA(cudaMalloc(&d_a_image, UPT_A_BYTES));
-        SRCDSP_CUDA(cudaMemcpy(d_a_image, img.data(), UPT_A_BYTES, cudaMemcpyHostToDevice));
+        SRCDSP_CUDA(cudaMalloc(&d_a_image, 2 * UPT_A_BYTES));
+        SRCDSP_CUDA(cudaMemcpy(d_a_image, img.data(), 2 * UPT_A_BYTES, cudaMemcpyHostToDevice));
         if (!h_diag) {
             SRCDSP_CUDA(cudaHostAlloc(&h_diag, 64, cudaHostAllocMapped));
             memset(h_diag, 0, 64);
@@ -1336,15 +1351,29 @@ struct UpBank : Bank {
                     cudaMemset(d_cnt, 0, 64);
                     T.counters = d_cnt;
                 }
-                if (tc_digits3) {
+                // form 2 (operand roles swapped: S accumulator slots per output instead of 4, no cross-lane reduction,
+                // 16-byte stores) is bit-identical but measured 3-12 % SLOWER than form 1 on B200 (x8/96 taps 2.93 vs
+                // 2.61 ms: its 32x32b TMEM loads deliver ~60 B/clk/SM, form 1's 16x256b loads ~90), so it only runs
+                // on request: SRCDSP_UP_TC_FORM = 2
+                bool form2 = false;
+                if (const char *e = getenv("SRCDSP_UP_TC_FORM")) form2 = atoi(e) == 2 && aligned16(out, out_stride);
+                T.n_image = d_a_image + UPT_A_BYTES;
+                if (form2 && tc_digits3) {
+                    SRCDSP_CUDA(cudaFuncSetAttribute(up_tc2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                    up_tc2_kernel<4><<<tgrid, UPT_THREADS, tsmem, stream>>>(T);
+                } else if (form2) {
+                    SRCDSP_CUDA(cudaFuncSetAttribute(up_tc2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                    up_tc2_kernel<3><<<tgrid, UPT_THREADS, tsmem, stream>>>(T);
+                } else if (tc_digits3) {
                     SRCDSP_CUDA(cudaFuncSetAttribute(up_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
                     up_tc_kernel<true><<<tgrid, UPT_THREADS, tsmem, stream>>>(T);
                 } else {
                     SRCDSP_CUDA(cudaFuncSetAttribute(up_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
                     up_tc_kernel<false><<<tgrid, UPT_THREADS, tsmem, stream>>>(T);
                 }
+                last_kernel_form2 = form2;
                 SRCDSP_LAUNCH_CHECK();
-                last_kernel = 3;
+                last_kernel = last_kernel_form2 ? 4 : 3;
                 dim3 hgrid((unsigned)std::max(1, std::min((H + 255) / 256, 64)), (unsigned)C);
                 up_history_kernel<<<hgrid, 256, 0, stream>>>(in, in_stride, (long long)n_in, (long long)n_tot, d_hist[cur],
                                                              d_hist[cur ^ 1], H);

@@ -198,11 +198,14 @@ def test_upsampler_blocked_kernel_many_tiles(S, corc, monkeypatch, L, nt):
 @pytest.mark.parametrize("L,nt,amp", [(8, 64, 6000), (8, 96, 30000), (8, 8, 100), (4, 32, 6000), (4, 20, 2 ** 22), (16, 64, 6000),
                                       (16, 224, 127), (32, 480, 6000), (32, 32, 40000), (8, 64, 2 ** 22)])
 @pytest.mark.parametrize("sm", [0, 1])
-def test_upsampler_tcgen05_kernel(S, corc, monkeypatch, L, nt, amp, sm):
-    """The tcgen05 form of the interpolator (one int8 MMA per 4096 outputs, bias column, low byte plane biased to
-    signed), forced for every ratio / length / tap magnitude it accepts: streaming blocks with ragged lengths, history,
-    flush, both overloads, several channels, full-scale input (saturation of the asymmetric clamp)."""
+@pytest.mark.parametrize("form", [1, 2])
+def test_upsampler_tcgen05_kernel(S, corc, monkeypatch, L, nt, amp, sm, form):
+    """The tcgen05 forms of the interpolator (int8 MMAs over 4096 outputs, bias column, low byte plane biased to
+    signed; form 1 = taps on the M side, form 2 = taps on the N side, 3 or 4 accumulator slots per output), forced
+    for every ratio / length / tap magnitude they accept: streaming blocks with ragged lengths, history, flush, both
+    overloads, several channels, full-scale input (saturation of the asymmetric clamp)."""
     monkeypatch.setenv("SRCDSP_UP_TC", "1")
+    monkeypatch.setenv("SRCDSP_UP_TC_FORM", str(form))
     rng = np.random.default_rng(L * 7919 + nt + sm)
     taps = rng.integers(-amp, amp + 1, nt).astype(np.int32)
     taps[-2:] = 0
@@ -215,10 +218,10 @@ def test_upsampler_tcgen05_kernel(S, corc, monkeypatch, L, nt, amp, sm):
         fl = blk == 5
         got = host(u.step(dev(x), flush=fl, iterator_overload=sm == 1)) if blk % 2 else u.step(x, flush=fl, iterator_overload=sm == 1)
         if blk % 2:  # device rows: the cp.async feed needs them 16-byte aligned (n % 4 == 0), else a CUDA-core kernel runs
-            assert u.last_kernel.startswith("up_tc" if n % 4 == 0 else "up_fir"), (u.last_kernel, n)
+            assert u.last_kernel.startswith(("up_tc2" if form == 2 else "up_tc_") if n % 4 == 0 else "up_fir"), (u.last_kernel, n)
         for c in range(C):
             e, hs[c] = corc.up_step(taps, L, x[c], hs[c], fl, sm)
-            assert np.array_equal(got[c], e), (L, nt, sm, blk, c)
+            assert np.array_equal(got[c], e), (L, nt, sm, form, blk, c)
 
 
 def test_upsampler_kernel_selection(S, monkeypatch):
@@ -242,15 +245,16 @@ def test_upsampler_tcgen05_many_tiles_match_cuda_core_kernel(S, monkeypatch):
     x = torch.empty((C, n, 2), dtype=torch.int16, device="cuda")
     S.synth_fill(x, 0x5EED00C4)
     outs = []
-    for tc in ("0", "1"):
+    for tc, form in (("0", "1"), ("1", "1"), ("1", "2")):
         monkeypatch.setenv("SRCDSP_UP_TC", tc)
+        monkeypatch.setenv("SRCDSP_UP_TC_FORM", form)
         u = S.FilterUpsamplingFir(L, taps, channels=C)
         for rep in range(3):  # carried history + repeated launches
             y = u.step(x)
         torch.cuda.synchronize()
-        assert u.last_kernel.startswith("up_tc" if tc == "1" else "up_fir4")
+        assert u.last_kernel.startswith(("up_tc2" if form == "2" else "up_tc_") if tc == "1" else "up_fir4")
         outs.append(y)
-    assert torch.equal(outs[0], outs[1])
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
 
 
 def test_upsampler_bank_and_errors(S, corc):

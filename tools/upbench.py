@@ -1,5 +1,5 @@
 """Times FilterUpsamplingFir.step (device resident) for one shape with the CUDA-core kernels and with the tcgen05 kernel
-(SRCDSP_UP_TC = 0 / 1):  python tools/upbench.py L ntaps [channels] [n_in]"""
+(SRCDSP_UP_TC = 0 / 1, SRCDSP_UP_TC_FORM = 1 / 2):  python tools/upbench.py L ntaps [channels] [n_in]"""
 import os
 import sys
 
@@ -15,8 +15,9 @@ n = int(sys.argv[4]) if len(sys.argv) > 4 else 1 << 20
 x = torch.empty((C, n, 2), dtype=torch.int16, device="cuda")
 S.synth_fill(x, 0x5EED0004)
 y = torch.empty((C, n * L, 2), dtype=torch.int16, device="cuda")
-for tc in ("0", "1"):
+for tc, form in (("0", "1"), ("1", "1"), ("1", "2")):
     os.environ["SRCDSP_UP_TC"] = tc
+    os.environ["SRCDSP_UP_TC_FORM"] = form
     u = S.FilterUpsamplingFir(L, O.design_interp_taps(nt, L), channels=C)
     for _ in range(3):
         u.step(x, out=y)
