@@ -45,6 +45,7 @@ typedef struct srcdsp_up_s *srcdsp_up_t;
 typedef struct srcdsp_ddc_s *srcdsp_ddc_t;
 typedef struct srcdsp_fifo_s *srcdsp_fifo_t;
 typedef struct srcdsp_corr_s *srcdsp_corr_t;
+typedef struct srcdsp_decf_s *srcdsp_decf_t;
 
 /* ------------------------------------------------------------------------------------------ */
 /* library                                                                                    */
@@ -124,6 +125,35 @@ int srcdsp_dec_set_kernel(srcdsp_dec_t h, int kind);
 /* which FIR kernel the last step launched: 0 none yet, 1 IMAD (dec_fir_kernel), 2 tcgen05 with
  * register-staged loads (dec_tc_kernel), 3 tcgen05 fed by TMA (dec_tma_kernel) */
 int srcdsp_dec_get_last_kernel(srcdsp_dec_t h, int *kind);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Float decimator bank -- dsptl::FilterDnsamplingFir<complex<float>, complex<float>,          */
+/* complex<float>, float, M>, the only float instantiation of the hot path the reference can   */
+/* build (Mixer has no float specialisation, the upsampler static_asserts integers).           */
+/* Bit-exact with the compiled reference: the sum runs in tap order with one rounded multiply  */
+/* and one rounded add per component (dsptl_dnsampling_filters.h:195-210), is truncated to      */
+/* int32, shifted by coeffScaling - leftShift, clamped to +-32767 (limitScale16,               */
+/* dsp_complex.cpp:63-73) and converted back to float (:214).  Samples: interleaved float I/Q  */
+/* (std::vector<std::complex<float>>::data()), strides and sizes in complex samples; host or   */
+/* device pointers.  Samples must be finite and |sum| < 2^31 (undefined in the reference).     */
+int srcdsp_decf_create(srcdsp_decf_t *h, int device, int channels, int M);
+int srcdsp_decf_destroy(srcdsp_decf_t h);
+/* setCoeffs (:114-134).  coeffScaling follows the reference literally: its unqualified abs()  */
+/* on a float tap is ::abs(int), so coeffScaling = floor(log2(sum |int(c_k)|)); when that sum  */
+/* is 0 (all |c_k| < 1) the reference's value is undefined and, as built by g++ for x86-64,    */
+/* results in a shift of (0x80000000 - leftShift) & 31 -- reproduced here.                      */
+int srcdsp_decf_set_coeffs(srcdsp_decf_t h, const float *taps, int ntaps, int require_multiple_of_m);
+int srcdsp_decf_set_left_shift(srcdsp_decf_t h, int left_shift);
+int srcdsp_decf_reset(srcdsp_decf_t h);
+/* step (:172-220): n_in_per_ch % M must be 0 (E_SIZE); writes n_in_per_ch / M samples per channel */
+int srcdsp_decf_step(srcdsp_decf_t h, const float *in_iq, size_t in_stride, size_t n_in_per_ch, float *out_iq,
+                     size_t out_stride);
+int srcdsp_decf_get_coeff_scaling(srcdsp_decf_t h, unsigned *coeff_scaling);
+/* history of one channel, oldest first, ntaps-1 complex samples (host pointers) */
+int srcdsp_decf_get_state(srcdsp_decf_t h, int ch, float *history_iq, size_t *n_samples);
+int srcdsp_decf_set_state(srcdsp_decf_t h, int ch, const float *history_iq, size_t n_samples);
+int srcdsp_decf_set_stream(srcdsp_decf_t h, void *cuda_stream);
+int srcdsp_decf_sync(srcdsp_decf_t h);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Fused DDC chain: mixer -> dec1 [-> dec2].  One call == the separate steps, bit for bit:     */

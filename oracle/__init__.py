@@ -42,6 +42,11 @@ def _p32(a: np.ndarray):
     return a.ctypes.data_as(_i32p)
 
 
+def _pf(a: np.ndarray):
+    assert a.dtype == np.float32 and a.flags.c_contiguous
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
 def as_taps(taps) -> np.ndarray:
     return np.ascontiguousarray(np.asarray(taps, dtype=np.int32))
 
@@ -65,6 +70,10 @@ class _COracle:
         L.orc_dec_coeff_scaling.argtypes = [_i32p, C.c_int]
         L.orc_dec_step.argtypes = [_i32p, C.c_int, C.c_int, C.c_uint, _i16p, _i16p, C.c_size_t, _i16p]
         L.orc_fir_step.argtypes = [_i32p, C.c_int, C.c_uint, _i16p, _i16p, C.c_size_t, _i16p]
+        fp = C.POINTER(C.c_float)
+        L.orc_decf_coeff_scaling.restype = C.c_uint
+        L.orc_decf_coeff_scaling.argtypes = [fp, C.c_int]
+        L.orc_decf_step.argtypes = [fp, C.c_int, C.c_int, C.c_uint, fp, fp, C.c_size_t, fp]
         L.orc_up_left_shift_factor.restype = C.c_int
         L.orc_up_left_shift_factor.argtypes = [C.c_int]
         L.orc_up_length.restype = C.c_int
@@ -111,6 +120,21 @@ class _COracle:
         out = np.empty((x.shape[0] // M, 2), np.int16)
         shift = self.dec_coeff_scaling(t) - left_shift
         self.lib.orc_dec_step(_p32(t), t.size, M, shift, _p16(h), _p16(x), x.shape[0], _p16(out))
+        return out, h
+
+    # -- float decimator (the reference's complex<float> instantiation) -----------------------------
+    def decf_coeff_scaling(self, taps) -> int:
+        t = np.ascontiguousarray(taps, np.float32)
+        return self.lib.orc_decf_coeff_scaling(_pf(t), t.size)
+
+    def decf_step(self, taps, M: int, x: np.ndarray, history: np.ndarray | None = None, left_shift: int = 0):
+        t = np.ascontiguousarray(taps, np.float32)
+        x = np.ascontiguousarray(x, np.float32).reshape(-1, 2)
+        h = np.zeros((t.size - 1, 2), np.float32) if history is None else np.array(history, np.float32).reshape(-1, 2)
+        assert h.shape[0] == t.size - 1 and x.shape[0] % M == 0
+        out = np.empty((x.shape[0] // M, 2), np.float32)
+        shift = (self.decf_coeff_scaling(t) - left_shift) & 0xFFFFFFFF
+        self.lib.orc_decf_step(_pf(t), t.size, M, shift, _pf(h), _pf(x), x.shape[0], _pf(out))
         return out, h
 
     def fir_step(self, taps, x: np.ndarray, history: np.ndarray | None = None):
@@ -259,6 +283,13 @@ class _RefLib:
         L.ref_dec_reset.argtypes = [vp]
         L.ref_dec_set_left_shift.argtypes = [vp, C.c_int]
         L.ref_dec_step.argtypes = [vp, _i16p, C.c_size_t, C.c_int, _i16p]
+        fp = C.POINTER(C.c_float)
+        L.ref_decf_create.restype = vp
+        L.ref_decf_create.argtypes = [C.c_int, C.c_int, fp, C.c_int]
+        L.ref_decf_destroy.argtypes = [vp]
+        L.ref_decf_reset.argtypes = [vp]
+        L.ref_decf_set_left_shift.argtypes = [vp, C.c_int]
+        L.ref_decf_step.argtypes = [vp, fp, C.c_size_t, C.c_int, fp]
         L.ref_fir_create.restype = vp
         L.ref_fir_create.argtypes = [_i32p, C.c_int]
         L.ref_fir_destroy.argtypes = [vp]
@@ -385,6 +416,36 @@ class RefDecimator:
         assert x.shape[0] % self.M == 0
         out = np.empty((x.shape[0] // self.M, 2), np.int16)
         self._l.ref_dec_step(self._h, _p16(x), x.shape[0], self.M, _p16(out))
+        return out
+
+
+class RefDecF:
+    """The reference's FilterDnsamplingFir<complex<float>, complex<float>, complex<float>, float, M>, compiled."""
+
+    def __init__(self, lib: _RefLib, M: int, taps, obsolete: bool = False):
+        self._l = lib.lib
+        self.M = M
+        t = np.ascontiguousarray(taps, np.float32)
+        self._h = self._l.ref_decf_create(0 if obsolete else 1, M, _pf(t), t.size)
+        if not self._h:
+            raise ValueError("reference would assert / unsupported M")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._l.ref_decf_destroy(self._h)
+            self._h = None
+
+    def reset(self):
+        self._l.ref_decf_reset(self._h)
+
+    def setLeftShiftBy2(self, s):
+        self._l.ref_decf_set_left_shift(self._h, s)
+
+    def step(self, x):
+        x = np.ascontiguousarray(x, np.float32).reshape(-1, 2)
+        assert x.shape[0] % self.M == 0
+        out = np.empty((x.shape[0] // self.M, 2), np.float32)
+        self._l.ref_decf_step(self._h, _pf(x), x.shape[0], self.M, _pf(out))
         return out
 
 
@@ -658,6 +719,31 @@ def np_dec_step(taps, M: int, x: np.ndarray, history: np.ndarray | None = None, 
     sh = np_dec_coeff_scaling(taps) - left_shift
     out = _cl16s(acc >> sh)
     return out, xx[xx.shape[0] - (Nt - 1):].astype(np.int16)
+
+
+def np_decf_coeff_scaling(taps) -> int:
+    """dsptl_dnsampling_filters.h:128-132 with float taps: abs() is ::abs(int) there."""
+    s = float(np.sum(np.abs(np.trunc(np.asarray(taps, np.float32)).astype(np.int64))))
+    return int(np.floor(np.log2(s))) & 0xFFFFFFFF if s >= 1 else 0x80000000
+
+
+def np_decf_step(taps, M: int, x: np.ndarray, history: np.ndarray | None = None, left_shift: int = 0):
+    """Float instantiation of the decimator (dsptl_dnsampling_filters.h:188-219): float32 multiply and add per tap,
+    in tap order, vectorised over the outputs (each numpy float32 operation is one IEEE rounding)."""
+    t = np.asarray(taps, np.float32)
+    x = np.asarray(x, np.float32).reshape(-1, 2)
+    Nt = t.size
+    h = np.zeros((Nt - 1, 2), np.float32) if history is None else np.asarray(history, np.float32).reshape(-1, 2)
+    xx = np.concatenate([h, x])
+    n_out = x.shape[0] // M
+    base = (Nt - 1) + np.arange(n_out) * M
+    acc = np.zeros((n_out, 2), np.float32)
+    for k in range(Nt):
+        acc = acc + t[k] * xx[base - k]
+    sh = ((np_decf_coeff_scaling(taps) - left_shift) & 0xFFFFFFFF) & 31
+    v = np.trunc(acc).astype(np.int64) >> sh
+    out = np.clip(v, -32767, 32767).astype(np.float32)
+    return out, xx[xx.shape[0] - (Nt - 1):].copy()
 
 
 def np_up_step(taps, L: int, x: np.ndarray, history: np.ndarray | None = None,

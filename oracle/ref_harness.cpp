@@ -160,6 +160,35 @@ inline std::vector<cs16> to_vec(const int16_t *iq, size_t n)
 
 }  // namespace
 
+// float decimator: the reference's own template with float types
+typedef std::complex<float> cf32;
+struct DecfBase {
+    virtual ~DecfBase() {}
+    virtual void step(const std::vector<cf32> &in, std::vector<cf32> &out) = 0;
+    virtual void reset() = 0;
+    virtual void setLeftShiftBy2(int) = 0;
+};
+template <class F>
+struct DecfT : DecfBase {
+    F f;
+    explicit DecfT(const std::vector<float> &taps) : f(taps) {}
+    void step(const std::vector<cf32> &in, std::vector<cf32> &out) { f.step(in, out); }
+    void reset() { f.reset(); }
+    void setLeftShiftBy2(int s) { f.setLeftShiftBy2(s); }
+};
+static DecfBase *make_decf(int variant, int M, const std::vector<float> &taps)
+{
+    switch (M) {
+#define X(m)                                                                                                   \
+    case m:                                                                                                    \
+        if (variant == 0) return new DecfT<ref_obsolete::dsptl::FilterDnsamplingFir<cf32, cf32, cf32, float, m> >(taps); \
+        return new DecfT<dsptl::FilterDnsamplingFir<cf32, cf32, cf32, float, m> >(taps);
+        RATIOS(X)
+#undef X
+    }
+    return nullptr;
+}
+
 extern "C" {
 
 // --- mixer -----------------------------------------------------------------------------------
@@ -197,6 +226,24 @@ void ref_dec_step(void *h, const int16_t *in_iq, size_t n_in, int M, int16_t *ou
     std::vector<cs16> in = to_vec(in_iq, n_in), out(n_in / M);
     static_cast<DecBase *>(h)->step(in, out);
     if (!out.empty()) std::memcpy(out_iq, out.data(), out.size() * sizeof(cs16));
+}
+
+// --- float decimator: dsptl::FilterDnsamplingFir<complex<float>, complex<float>, complex<float>, float, M> ------
+void *ref_decf_create(int variant, int M, const float *taps, int ntaps)
+{
+    if (ntaps < 1) return nullptr;
+    if (variant != 0 && ntaps % M != 0) return nullptr;  // dsptl_dnsampling_filters.h:122 would assert
+    return make_decf(variant, M, std::vector<float>(taps, taps + ntaps));
+}
+void ref_decf_destroy(void *h) { delete static_cast<DecfBase *>(h); }
+void ref_decf_reset(void *h) { static_cast<DecfBase *>(h)->reset(); }
+void ref_decf_set_left_shift(void *h, int s) { static_cast<DecfBase *>(h)->setLeftShiftBy2(s); }
+void ref_decf_step(void *h, const float *in_iq, size_t n_in, int M, float *out_iq)
+{
+    std::vector<cf32> in(n_in), out(n_in / M);
+    if (n_in) std::memcpy(in.data(), in_iq, n_in * sizeof(cf32));
+    static_cast<DecfBase *>(h)->step(in, out);
+    if (!out.empty()) std::memcpy(out_iq, out.data(), out.size() * sizeof(cf32));
 }
 
 // --- plain FIR (filters.h) ----------------------------------------------------------------------

@@ -149,6 +149,45 @@ void orc_dec_step(const int32_t *taps, int ntaps, int M, unsigned shift, int16_t
     fir_core(taps, ntaps, M, shift, history_iq, in_iq, n_in, out_iq);
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* The float instantiation FilterDnsamplingFir<complex<float>, complex<float>, complex<float>, float, M>.
+ * dsptl_dnsampling_filters.h:128-132: `abs(coeff[index])` inside namespace dsptl is ::abs(int) -- the float tap is
+ * truncated to int first -- and coeffScaling is an unsigned that receives int(floor(log2(sum))).  A sum of 0 makes the
+ * reference's value undefined; as compiled by g++ for x86-64 it is INT_MIN, returned here as 0x80000000. */
+unsigned orc_decf_coeff_scaling(const float *taps, int ntaps)
+{
+    double sum = 0;
+    for (int k = 0; k < ntaps; ++k) sum += abs((int)taps[k]);
+    return sum >= 1 ? (unsigned)(int)floor(log2(sum)) : 0x80000000u;
+}
+
+/* dsptl_dnsampling_filters.h:188-219 with float types: y += coeff[k] * xx[i*M - k] is one rounded float multiply and
+ * one rounded float add per component, in tap order (:195-210; no FMA contraction: see the pragma / build flags);
+ * :214 converts y to complex<int32_t> (truncation), applies limitScale16 (dsp_complex.cpp:63-73) with the shift
+ * count taken mod 32 (x86 sar) and converts the int16 pair back to float. */
+#pragma STDC FP_CONTRACT OFF
+void orc_decf_step(const float *taps, int ntaps, int M, unsigned shift, float *history_iq, const float *in_iq, size_t n_in,
+                   float *out_iq)
+{
+    const size_t H = (size_t)(ntaps - 1);
+    float *xx = (float *)malloc((H + n_in + 1) * 2 * sizeof(float));
+    memcpy(xx, history_iq, H * 2 * sizeof(float));
+    memcpy(xx + 2 * H, in_iq, n_in * 2 * sizeof(float));
+    for (size_t j = 0; j < n_in; j += (size_t)M) {
+        volatile float ar = 0.f, ai = 0.f; /* volatile: every partial sum is rounded to float */
+        const float *x = xx + 2 * (H + j);
+        for (int k = 0; k < ntaps; ++k) {
+            volatile float pr = taps[k] * x[-2 * k], pi = taps[k] * x[-2 * k + 1];
+            ar = ar + pr;
+            ai = ai + pi;
+        }
+        out_iq[2 * (j / M)] = (float)orc_limit_scale16((int32_t)ar, shift & 31u);
+        out_iq[2 * (j / M) + 1] = (float)orc_limit_scale16((int32_t)ai, shift & 31u);
+    }
+    memmove(history_iq, xx + 2 * n_in, H * 2 * sizeof(float));
+    free(xx);
+}
+
 /* filters.h:130-169 -- circular-buffer FIR; in age order it is the M = 1 decimator */
 void orc_fir_step(const int32_t *taps, int ntaps, unsigned shift, int16_t *history_iq,
                   const int16_t *in_iq, size_t n_in, int16_t *out_iq)

@@ -42,6 +42,9 @@ void orc_mixer_step(const int16_t *table, unsigned n_table, int *phi, int freq,
  *      == dnsampling_filters.h:83-97, :128-172 ---- */
 int orc_dec_coeff_scaling(const int32_t *taps, int ntaps);
 /* history: (ntaps-1) complex samples, oldest first; updated in place.  n_in % M == 0. */
+unsigned orc_decf_coeff_scaling(const float *taps, int ntaps);
+void orc_decf_step(const float *taps, int ntaps, int M, unsigned shift, float *history_iq, const float *in_iq, size_t n_in,
+                   float *out_iq);
 void orc_dec_step(const int32_t *taps, int ntaps, int M, unsigned shift, int16_t *history_iq,
                   const int16_t *in_iq, size_t n_in, int16_t *out_iq);
 

@@ -25,7 +25,7 @@ import numpy as np
 from . import _capi
 from ._capi import SrcDspError, check, lib
 
-__all__ = ["Mixer", "FilterDnsamplingFir", "FilterFir", "FilterUpsamplingFir", "Ddc", "SrcDspError",
+__all__ = ["Mixer", "FilterDnsamplingFir", "FilterDnsamplingFirFloat", "FilterFir", "FilterUpsamplingFir", "Ddc", "SrcDspError",
            "synth_fill", "launch_count", "device_count", "PinnedBuffer", "FifoWithTimeTrack", "saveBinarySamples",
            "readBinarySamples", "FixedPatternCorrelator"]
 
@@ -324,6 +324,97 @@ class FilterUpsamplingFir(_Handle):
 
     def sync(self):
         check(lib().srcdsp_up_sync(self._h))
+
+
+# ----------------------------------------------------------------------------------------------
+class _BufF32:
+    """A [C, n, 2] float32 view (interleaved I/Q == complex64) of a numpy array or a torch CUDA tensor."""
+
+    __slots__ = ("obj", "ptr", "C", "n", "stride", "device", "squeeze")
+
+    def __init__(self, x, channels: int):
+        self.obj = x
+        shape = tuple(x.shape)
+        self.squeeze = len(shape) == 2 and channels == 1
+        if self.squeeze:
+            shape = (1,) + shape
+        if len(shape) != 3 or shape[2] != 2 or shape[0] != channels:
+            raise ValueError(f"expected float32 [{channels}, n, 2] (or [n, 2] for one channel), got {tuple(x.shape)}")
+        self.C, self.n = shape[0], shape[1]
+        if _is_torch(x):
+            import torch
+            if x.dtype != torch.float32 or not x.is_cuda:
+                raise TypeError("torch buffers must be CUDA float32 tensors")
+            st = x.stride()
+            if st[-1] != 1 or st[-2] != 2:
+                raise ValueError("samples must be contiguous interleaved I/Q")
+            self.stride = (st[0] // 2) if not self.squeeze else self.n
+            self.ptr, self.device = x.data_ptr(), True
+        else:
+            if not isinstance(x, np.ndarray) or x.dtype != np.float32:
+                raise TypeError("host buffers must be numpy float32 arrays")
+            st = x.strides
+            if st[-1] != 4 or st[-2] != 8:
+                raise ValueError("samples must be contiguous interleaved I/Q")
+            self.stride = (st[0] // 8) if not self.squeeze else self.n
+            self.ptr, self.device = x.ctypes.data, False
+
+
+class FilterDnsamplingFirFloat(_Handle):
+    """dsptl::FilterDnsamplingFir<complex<float>, complex<float>, complex<float>, float, M>
+    (dsptl_dnsampling_filters.h:43-220), the float instantiation of the decimator: bit-exact with the compiled
+    reference, including its int32 truncation / limitScale16 of the float sum (:214) and its integer abs() in
+    coeffScaling (:128-132).  Buffers: float32 [C, n, 2] / [n, 2] numpy arrays or torch CUDA tensors."""
+
+    _destroy = "srcdsp_decf_destroy"
+
+    def __init__(self, M: int, firCoeff=None, channels: int = 1, device: int = 0, obsolete: bool = False):
+        super().__init__()
+        self.M, self.channels, self.device, self.obsolete = M, channels, device, obsolete
+        check(lib().srcdsp_decf_create(C.byref(self._h), device, channels, M))
+        if firCoeff is not None:
+            self.setCoeffs(firCoeff)
+
+    def setCoeffs(self, firCoeff):
+        t = np.ascontiguousarray(np.asarray(firCoeff, dtype=np.float32).reshape(-1))
+        check(lib().srcdsp_decf_set_coeffs(self._h, t.ctypes.data_as(C.POINTER(C.c_float)), t.size,
+                                           0 if self.obsolete else 1))
+        self.ntaps = t.size
+
+    def setLeftShiftBy2(self, leftShiftBy2: int):
+        check(lib().srcdsp_decf_set_left_shift(self._h, int(leftShiftBy2)))
+
+    def reset(self):
+        check(lib().srcdsp_decf_reset(self._h))
+
+    @property
+    def coeffScaling(self) -> int:
+        v = C.c_uint()
+        check(lib().srcdsp_decf_get_coeff_scaling(self._h, C.byref(v)))
+        return v.value
+
+    def step(self, x, out=None):
+        """dsptl_dnsampling_filters.h:172-220: out.size() * M == in.size()."""
+        bi = _BufF32(x, self.channels)
+        if bi.n % self.M:
+            raise SrcDspError(_capi.E_SIZE, "filteredSignal.size() * M != input.size() [dsptl_dnsampling_filters.h:181]")
+        n_out = bi.n // self.M
+        if out is None:
+            shape = (n_out, 2) if bi.squeeze else (self.channels, n_out, 2)
+            if _is_torch(x):
+                import torch
+                out = torch.empty(shape, dtype=torch.float32, device=x.device)
+            else:
+                out = np.empty(shape, np.float32)
+        bo = _BufF32(out, self.channels)
+        if bo.n != n_out:
+            raise SrcDspError(_capi.E_SIZE, "filteredSignal.size() * M != input.size() [dsptl_dnsampling_filters.h:181]")
+        self._bind_stream(bi, "srcdsp_decf_set_stream")
+        check(lib().srcdsp_decf_step(self._h, bi.ptr, bi.stride, bi.n, bo.ptr, bo.stride))
+        return out
+
+    def sync(self):
+        check(lib().srcdsp_decf_sync(self._h))
 
 
 # ----------------------------------------------------------------------------------------------

@@ -59,6 +59,18 @@ PROTOTYPES = {
     "srcdsp_dec_sync": (C.c_int, [_vp]),
     "srcdsp_dec_set_kernel": (C.c_int, [_vp, C.c_int]),
     "srcdsp_dec_get_last_kernel": (C.c_int, [_vp, C.POINTER(C.c_int)]),
+    # float decimator (the reference's complex<float> instantiation)
+    "srcdsp_decf_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int]),
+    "srcdsp_decf_destroy": (C.c_int, [_vp]),
+    "srcdsp_decf_set_coeffs": (C.c_int, [_vp, C.POINTER(C.c_float), C.c_int, C.c_int]),
+    "srcdsp_decf_set_left_shift": (C.c_int, [_vp, C.c_int]),
+    "srcdsp_decf_reset": (C.c_int, [_vp]),
+    "srcdsp_decf_step": (C.c_int, [_vp, _vp, _sz, _sz, _vp, _sz]),
+    "srcdsp_decf_get_coeff_scaling": (C.c_int, [_vp, C.POINTER(C.c_uint)]),
+    "srcdsp_decf_get_state": (C.c_int, [_vp, C.c_int, _vp, C.POINTER(_sz)]),
+    "srcdsp_decf_set_state": (C.c_int, [_vp, C.c_int, _vp, _sz]),
+    "srcdsp_decf_set_stream": (C.c_int, [_vp, _vp]),
+    "srcdsp_decf_sync": (C.c_int, [_vp]),
     # fused chain
     "srcdsp_ddc_create": (C.c_int, [C.POINTER(_vp), _vp, _vp, _vp]),
     "srcdsp_ddc_destroy": (C.c_int, [_vp]),

@@ -2203,3 +2203,5 @@ int srcdsp_corr_set_stream(srcdsp_corr_t h, void *cuda_stream)
 }
 
 }  // extern "C"
+
+#include "capi_decf.inc"

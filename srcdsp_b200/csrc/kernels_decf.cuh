@@ -1,0 +1,148 @@
+// kernels_decf.cuh -- the float instantiation of the decimating FIR,
+//   dsptl::FilterDnsamplingFir<complex<float>, complex<float>, complex<float>, float, M>::step
+//   (dsptl_dnsampling_filters.h:172-220), bit-exact on the FP32 pipe.
+//
+// What the reference computes for that instantiation (probed on the compiled reference, oracle/ref_harness.cpp):
+//
+//   y = complex<float>(0, 0)
+//   for k = 0 .. N-1 (ascending):  y.re += c[k] * xx[i*M - k].re ;  y.im += c[k] * xx[i*M - k].im      (:195-210)
+//   out[i] = complex<float>( limitScale16( complex<int32_t>(y), coeffScaling - leftShift ) )             (:214)
+//
+// i.e. one rounded multiply and one rounded add per component and tap (g++ for x86-64 does not contract them),
+// summed in tap order; the sum is truncated toward zero to int32, shifted, clamped to +-32767 and converted back.
+// The result depends on the order of the additions, so this kernel keeps it: every output is ONE sequential chain
+// of __fmul_rn / __fadd_rn per component (never an FMA, never a tree), and parallelism comes from the outputs.
+//
+// Shape.  4 FP32 instructions per tap and output make the FP32 pipe (128 lanes/clk/SM) the roofline; 8 bytes of
+// sample per 4 lane-instructions are twice what shared memory delivers (128 B/clk/SM), so samples are reused in
+// registers: a thread owns the output PAIR (2q, 2q+1) and walks the samples downwards from xx[(2q+1)*M]; sample
+// (2q+1)*M - e is tap k = e of the upper output and tap k = e - M of the lower one.  Per 4 samples: 2 LDS.128
+// (samples) + 2 LDS.128 (broadcast: 4 taps of each output, from two pre-shifted zero-padded copies of the taps) feed
+// 32 FP32 instructions; a thread carries two such pairs (8 independent add chains).  The lane stride is 2*M samples
+// = M 16-byte units; for even M every block of 2*M samples is followed by one unit of padding so that the stride is
+// odd and the LDS.128 are conflict free.  Zero taps in front of / behind a filter add +-0 to its chain, which leaves
+// every finite sum unchanged (samples must be finite -- the reference's int conversion of NaN/Inf is undefined).
+#pragma once
+
+#include "common.cuh"
+
+namespace srcdsp {
+
+constexpr int DECF_PAIRS = 2;  // output pairs per thread
+
+struct DecfParams {
+    const float2 *in;
+    float2 *out;
+    size_t in_stride, out_stride;  // complex samples per channel row
+    long long n_in, n_out;         // per channel
+    const float2 *hist;            // [C][N - 1] age order: hist[N - 2] = xx[-1]
+    const float *taps2;            // [2][E]: [1][e] = c[e], [0][e] = c[e - M], zero outside the filter
+    int M, N, E;                   // ratio, taps, padded walk length (multiple of 4, >= N + M)
+    int lead;                      // local sample index of stream sample tile_out * M * tile
+    int blk, padw;                 // samples per block (2 * M) and padding samples behind each (2 if M is even)
+    unsigned blk_magic;            // floor(2^32 / blk) + 1: idx / blk = umulhi(idx, magic) for the staged range
+    int blk_chunks;                // 4-sample chunks per block (M / 2), or INT_MAX without padding
+    int n_local;                   // staged samples per tile
+    int tile_out;                  // outputs per tile = 2 * DECF_PAIRS * blockDim.x
+    int tiles_per_ch;
+    unsigned shift;                // (coeffScaling - leftShift) & 31, as x86 `sar` applies it
+};
+
+__device__ __forceinline__ float decf_limit(float y, unsigned shift)
+{
+    int v = __float2int_rz(y) >> shift;  // complex<int32_t>(y): truncation; limitScale16 (dsp_complex.cpp:63-73)
+    v = max(-32767, min(32767, v));
+    return (float)v;
+}
+
+__global__ void __launch_bounds__(128) decf_fir_kernel(const __grid_constant__ DecfParams P)
+{
+    extern __shared__ __align__(16) uint8_t decf_smem[];
+    float *ts = reinterpret_cast<float *>(decf_smem);              // [2][E]
+    float2 *xs = reinterpret_cast<float2 *>(ts + 2 * P.E);         // padded samples (2 * E * 4 bytes is a multiple of 16)
+    const int tid = threadIdx.x, T = blockDim.x;
+    const unsigned ch = blockIdx.x / (unsigned)P.tiles_per_ch;
+    const int tile = (int)(blockIdx.x - ch * (unsigned)P.tiles_per_ch);
+
+    for (int i = tid; i < 2 * P.E; i += T) ts[i] = __ldg(P.taps2 + i);
+    // stage: local index idx <-> stream sample s = tile * tile_out * M + idx - lead
+    const float2 *x = P.in + (size_t)ch * P.in_stride;
+    const float2 *hist = P.hist + (size_t)ch * (P.N - 1);
+    const long long s0 = (long long)tile * P.tile_out * P.M - P.lead;
+    for (int idx = tid; idx < P.n_local; idx += T) {
+        const long long s = s0 + idx;
+        float2 v = make_float2(0.f, 0.f);
+        if (s >= 0) {
+            if (s < P.n_in) v = __ldg(x + s);
+        } else if (s >= -(long long)(P.N - 1)) {
+            v = __ldg(hist + (P.N - 1 + s));
+        }
+        xs[idx + P.padw * (int)__umulhi((unsigned)idx, P.blk_magic)] = v;
+    }
+    __syncthreads();
+
+    // pair q = tid + j * T: upper output 2q + 1 sits at local index (2q + 1) * M + lead = the LAST sample of block
+    // q + j0 (even M) -- chunks of 4 never straddle a block
+    float2 acc[DECF_PAIRS][2];
+    int pos[DECF_PAIRS];
+#pragma unroll
+    for (int j = 0; j < DECF_PAIRS; ++j) {
+        acc[j][0] = acc[j][1] = make_float2(0.f, 0.f);
+        const int top = (2 * (tid + j * T) + 1) * P.M + P.lead;
+        pos[j] = top + P.padw * (int)__umulhi((unsigned)top, P.blk_magic);
+    }
+    int in_blk = 0;
+    const float4 *t0 = reinterpret_cast<const float4 *>(ts), *t1 = reinterpret_cast<const float4 *>(ts + P.E);
+#pragma unroll 2
+    for (int c = 0; c < P.E / 4; ++c) {
+        const float4 k0 = t0[c], k1 = t1[c];  // taps e .. e + 3 of the lower / upper output (broadcast)
+#pragma unroll
+        for (int j = 0; j < DECF_PAIRS; ++j) {
+            // samples pos-3 .. pos (ascending address); e ascends as the address descends
+            const float4 hi = *reinterpret_cast<const float4 *>(xs + pos[j] - 1);  // {x[pos-1], x[pos]}
+            const float4 lo = *reinterpret_cast<const float4 *>(xs + pos[j] - 3);  // {x[pos-3], x[pos-2]}
+            float2 &a0 = acc[j][0], &a1 = acc[j][1];
+            a1.x = __fadd_rn(a1.x, __fmul_rn(k1.x, hi.z)), a1.y = __fadd_rn(a1.y, __fmul_rn(k1.x, hi.w));
+            a0.x = __fadd_rn(a0.x, __fmul_rn(k0.x, hi.z)), a0.y = __fadd_rn(a0.y, __fmul_rn(k0.x, hi.w));
+            a1.x = __fadd_rn(a1.x, __fmul_rn(k1.y, hi.x)), a1.y = __fadd_rn(a1.y, __fmul_rn(k1.y, hi.y));
+            a0.x = __fadd_rn(a0.x, __fmul_rn(k0.y, hi.x)), a0.y = __fadd_rn(a0.y, __fmul_rn(k0.y, hi.y));
+            a1.x = __fadd_rn(a1.x, __fmul_rn(k1.z, lo.z)), a1.y = __fadd_rn(a1.y, __fmul_rn(k1.z, lo.w));
+            a0.x = __fadd_rn(a0.x, __fmul_rn(k0.z, lo.z)), a0.y = __fadd_rn(a0.y, __fmul_rn(k0.z, lo.w));
+            a1.x = __fadd_rn(a1.x, __fmul_rn(k1.w, lo.x)), a1.y = __fadd_rn(a1.y, __fmul_rn(k1.w, lo.y));
+            a0.x = __fadd_rn(a0.x, __fmul_rn(k0.w, lo.x)), a0.y = __fadd_rn(a0.y, __fmul_rn(k0.w, lo.y));
+            pos[j] -= 4;
+        }
+        if (++in_blk == P.blk_chunks) {  // uniform: step over the padding in front of the block just finished
+            in_blk = 0;
+#pragma unroll
+            for (int j = 0; j < DECF_PAIRS; ++j) pos[j] -= P.padw;
+        }
+    }
+    float2 *o = P.out + (size_t)ch * P.out_stride;
+    const long long o0 = (long long)tile * P.tile_out;
+#pragma unroll
+    for (int j = 0; j < DECF_PAIRS; ++j) {
+        const long long i = o0 + 2 * (tid + j * T);
+        const float2 y0 = make_float2(decf_limit(acc[j][0].x, P.shift), decf_limit(acc[j][0].y, P.shift));
+        const float2 y1 = make_float2(decf_limit(acc[j][1].x, P.shift), decf_limit(acc[j][1].y, P.shift));
+        if (i + 1 < P.n_out && ((reinterpret_cast<uintptr_t>(o + i) & 15) == 0)) {
+            *reinterpret_cast<float4 *>(o + i) = make_float4(y0.x, y0.y, y1.x, y1.y);
+        } else {
+            if (i < P.n_out) o[i] = y0;
+            if (i + 1 < P.n_out) o[i + 1] = y1;
+        }
+    }
+}
+
+// history <- the last N - 1 samples of (history ++ input)   (dsptl_dnsampling_filters.h:218-219; shorter blocks than
+// N - 1 behave like one long call, as in the integer bank)
+__global__ void decf_history_kernel(const float2 *in, size_t in_stride, long long n_in, const float2 *hist_in, float2 *hist_out, int H)
+{
+    const unsigned ch = blockIdx.y;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < H; j += gridDim.x * blockDim.x) {
+        const long long s = n_in - H + j;
+        hist_out[(size_t)ch * H + j] = s >= 0 ? __ldg(in + (size_t)ch * in_stride + s) : __ldg(hist_in + (size_t)ch * H + (H + s));
+    }
+}
+
+}  // namespace srcdsp

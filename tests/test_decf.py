@@ -1,0 +1,194 @@
+"""The float instantiation of the decimator, dsptl::FilterDnsamplingFir<complex<float>, complex<float>,
+complex<float>, float, M> (dsptl_dnsampling_filters.h:43-220; the only float instantiation of the hot path that the
+reference can build).  north_star's tolerance for float samples is 1e-5 relative RMS; the bar here is stricter:
+BIT-EXACT (the kernel keeps the reference's tap-order sum of rounded products), asserted with array_equal -- a
+relative RMS error of exactly 0.
+
+CPU tests: the C / numpy restatements against the compiled reference and against the golden fixtures generated from
+it (tests/golden/make_golden_float.py).  GPU tests: the CUDA path through the C ABI against oracle and fixtures."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import oracle as O
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import make_golden_float as MGF  # noqa: E402
+
+FCASES = MGF.FCASES
+FGOLD = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "decf.npz")))
+REL_RMS_TOL = 1e-5  # north_star; every comparison below is in fact exact
+
+
+def rel_rms(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.sqrt(np.sum((a - b) ** 2) / max(np.sum(b ** 2), 1e-300)))
+
+
+def ftaps(rng, nt, kind):
+    if kind == "unity":
+        h = np.hamming(nt) * np.sinc((np.arange(nt) - (nt - 1) / 2.0) / 4.0)
+        return (h / h.sum()).astype(np.float32)
+    if kind == "int":
+        return np.round(rng.normal(0, 300, nt)).astype(np.float32)
+    return rng.normal(0, 3.0, nt).astype(np.float32)
+
+
+def run_blocks(step, case):
+    x, outs, pos = MGF.finput_for(case), [], 0
+    for n in case["blocks"]:
+        outs.append(step(x[pos:pos + n]))
+        pos += n
+    return np.concatenate(outs)
+
+
+# ---- oracle pinning (CPU) ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,nt", [(8, 63), (16, 255), (4, 1023), (1, 17), (3, 30), (5, 11), (2, 4), (64, 128)])
+@pytest.mark.parametrize("kind", ["unity", "int", "frac"])
+def test_float_oracle_vs_reference(corc, reflib, M, nt, kind):
+    rng = np.random.default_rng(M * 131 + nt)
+    t = ftaps(rng, nt, kind)
+    ls = 1 if kind == "int" else 0
+    ref = O.RefDecF(reflib, M, t, obsolete=True)
+    ref.setLeftShiftBy2(ls)
+    hc = hn = None
+    q = -(-(nt - 1) // M) * M  # the reference needs blocks of at least ntaps - 1 samples (:218-219)
+    for blk, n in enumerate([q + M * 40, q + M * 300, q + M * 7]):
+        x = rng.uniform(-20000, 20000, (n, 2)).astype(np.float32)
+        if blk == 1:
+            x = np.round(x)
+        e = ref.step(x)
+        g, hc = corc.decf_step(t, M, x, hc, ls)
+        g2, hn = O.np_decf_step(t, M, x, hn, ls)
+        assert np.array_equal(e, g) and np.array_equal(e, g2), (M, nt, kind, blk)
+    assert corc.decf_coeff_scaling(t) == O.np_decf_coeff_scaling(t)
+
+
+def test_float_coeff_scaling_is_integer_abs(corc):
+    """dsptl_dnsampling_filters.h:128-132: abs() on a float tap is ::abs(int) there."""
+    assert corc.decf_coeff_scaling(np.full(8, 0.9, np.float32)) == 0x80000000   # sum of int(0.9) = 0: undefined -> INT_MIN
+    assert corc.decf_coeff_scaling(np.full(8, 1.9, np.float32)) == 3            # 8 x 1
+    assert corc.decf_coeff_scaling(np.full(8, -300.7, np.float32)) == 11        # 8 x 300 = 2400
+
+
+@pytest.mark.parametrize("case", FCASES, ids=[c["name"] for c in FCASES])
+def test_float_oracle_matches_golden(corc, case):
+    t, h = MGF.ftaps_for(case), [None]
+
+    def step(x):
+        y, h[0] = corc.decf_step(t, case["M"], x, h[0], case["left_shift"])
+        return y
+    got = run_blocks(step, case)
+    assert np.array_equal(got, FGOLD[case["name"]]) and rel_rms(got, FGOLD[case["name"]]) <= REL_RMS_TOL
+
+
+@pytest.mark.parametrize("case", FCASES, ids=[c["name"] for c in FCASES])
+def test_float_golden_is_current_reference_output(reflib, case):
+    assert np.array_equal(MGF.run_reference_float(case), FGOLD[case["name"]])
+
+
+# ---- the CUDA path (GPU) -------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def S(built_lib):
+    import srcdsp_b200
+    return srcdsp_b200
+
+
+def dev(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.cpu().numpy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", FCASES, ids=[c["name"] for c in FCASES])
+@pytest.mark.parametrize("where", ["host", "device"])
+def test_float_golden_gpu(S, case, where):
+    d = S.FilterDnsamplingFirFloat(case["M"], MGF.ftaps_for(case), obsolete=True)
+    d.setLeftShiftBy2(case["left_shift"])
+    got = run_blocks((lambda x: d.step(x)) if where == "host" else (lambda x: host(d.step(dev(x)))), case)
+    assert np.array_equal(got, FGOLD[case["name"]]), rel_rms(got, FGOLD[case["name"]])
+    assert rel_rms(got, FGOLD[case["name"]]) <= REL_RMS_TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,nt", [(1, 17), (2, 9), (3, 31), (4, 1023), (5, 7), (6, 40), (7, 100), (8, 63), (10, 90),
+                                  (12, 255), (16, 255), (16, 256), (32, 64), (64, 300), (8, 1), (1, 1), (24, 48)])
+@pytest.mark.parametrize("kind", ["unity", "int", "frac"])
+def test_float_decimator_sweep(S, corc, M, nt, kind):
+    """Ragged streaming blocks (also shorter than ntaps - 1), host and device buffers, left shift, every tap family."""
+    rng = np.random.default_rng(M * 10007 + nt)
+    t = ftaps(rng, nt, kind)
+    ls = 1 if kind == "int" and nt > 4 else 0
+    d = S.FilterDnsamplingFirFloat(M, t, obsolete=True)
+    d.setLeftShiftBy2(ls)
+    assert d.coeffScaling == corc.decf_coeff_scaling(t)
+    h = None
+    for blk, nb in enumerate([nt + 37, 2600, 3, 1, 700]):
+        n = M * (nb // M + 1)
+        x = rng.uniform(-30000, 30000, (n, 2)).astype(np.float32)
+        exp, h = corc.decf_step(t, M, x, h, ls)
+        got = host(d.step(dev(x))) if blk % 2 else d.step(x)
+        assert np.array_equal(got, exp), (M, nt, kind, blk, rel_rms(got, exp))
+
+
+@pytest.mark.gpu
+def test_float_bank_channels_strides_and_errors(S, corc):
+    import torch
+    rng = np.random.default_rng(5)
+    C, M, nt = 5, 8, 64
+    t = ftaps(rng, nt, "frac")
+    d = S.FilterDnsamplingFirFloat(M, t, channels=C)
+    hs = [None] * C
+    for n in (M * 300, M * 129):
+        x = rng.uniform(-20000, 20000, (C, n, 2)).astype(np.float32)
+        big = torch.zeros((C, n + 24, 2), dtype=torch.float32, device="cuda")
+        big[:, 3:3 + n] = dev(x)                                  # strided rows, 8-byte (not 16-byte) aligned
+        out = torch.zeros((C, n // M + 5, 2), dtype=torch.float32, device="cuda")
+        d.step(big[:, 3:3 + n], out=out[:, 1:1 + n // M])
+        got = host(out[:, 1:1 + n // M])
+        for c in range(C):
+            e, hs[c] = corc.decf_step(t, M, x[c], hs[c])
+            assert np.array_equal(got[c], e), (n, c)
+        assert float(out[:, 0].abs().max()) == 0 and float(out[:, 1 + n // M:].abs().max()) == 0
+    d.reset()
+    x = rng.uniform(-1000, 1000, (C, M * 64, 2)).astype(np.float32)
+    got = d.step(x)
+    for c in range(C):
+        assert np.array_equal(got[c], corc.decf_step(t, M, x[c])[0])
+    with pytest.raises(S.SrcDspError):
+        d.step(x[:, :M * 64 - 1])                                  # size not a multiple of M (:181)
+    with pytest.raises(S.SrcDspError):
+        S.FilterDnsamplingFirFloat(M, t[:nt - 1])                  # taps % M != 0 with the new header (:122)
+    with pytest.raises(S.SrcDspError):
+        S.FilterDnsamplingFirFloat(M).step(x[0])                   # no coefficients yet
+    d.setCoeffs(ftaps(rng, 2 * nt, "unity"))                      # reload on a live object: history resized
+    assert d.coeffScaling == 0x80000000
+
+
+@pytest.mark.gpu
+def test_float_many_tiles_split_invariance_and_spot_check(S, corc):
+    """A batch that fills the machine (cfg2's filter, 64 channels x 1 Mi samples): one call == two half calls
+    (carried history across the block boundary), and random outputs recomputed by the oracle from their windows."""
+    import torch
+    C, M, nt, n = 64, 16, 255, 1 << 20
+    t = MGF.ftaps_for(dict(ntaps=nt, M=M, taps="unity"))
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = (torch.rand((C, n, 2), device="cuda", generator=g) - 0.5) * 40000
+    a = S.FilterDnsamplingFirFloat(M, t, channels=C, obsolete=True)
+    b = S.FilterDnsamplingFirFloat(M, t, channels=C, obsolete=True)
+    y = a.step(x)
+    y2 = torch.cat([b.step(x[:, :n // 2]), b.step(x[:, n // 2:])], dim=1)
+    assert torch.equal(y, y2)
+    rng = np.random.default_rng(3)
+    for _ in range(24):
+        c, i = int(rng.integers(C)), int(rng.integers(nt // M + 1, n // M))
+        # oracle with history = the nt - 1 samples in front of x[i * M] and one block of M samples starting there
+        hist = host(x[c, i * M - (nt - 1): i * M])
+        e, _ = corc.decf_step(t, M, host(x[c, i * M: i * M + M]), hist)
+        assert np.array_equal(host(y[c, i]), e[0]), (c, i)

@@ -1,0 +1,44 @@
+"""Times FilterDnsamplingFirFloat.step (device resident):  python tools/decfbench.py M ntaps [channels] [n_in]
+Prints output rate, the FP32-pipe fraction (4 * ntaps rounded FP32 operations per output -- the reference's separate
+multiply and add per component, which this kernel must keep -- against 148 SM x 128 lanes x SM clock) and the HBM
+fraction (8 * M + 8 bytes per output against MEASURED_PEAKS.json)."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import srcdsp_b200 as S
+
+M, nt = int(sys.argv[1]), int(sys.argv[2])
+C = int(sys.argv[3]) if len(sys.argv) > 3 else 256
+n = int(sys.argv[4]) if len(sys.argv) > 4 else 1 << 20
+h = np.hamming(nt) * np.sinc((np.arange(nt) - (nt - 1) / 2.0) / M)
+taps = (h / h.sum()).astype(np.float32)
+x = (torch.rand((C, n, 2), device="cuda") - 0.5) * 30000
+y = torch.empty((C, n // M, 2), dtype=torch.float32, device="cuda")
+d = S.FilterDnsamplingFirFloat(M, taps, channels=C, obsolete=True)
+for _ in range(3):
+    d.step(x, out=y)
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+torch.cuda.synchronize()
+ev[0].record()
+K = 10
+for _ in range(K):
+    d.step(x, out=y)
+ev[1].record()
+torch.cuda.synchronize()
+ms = ev[0].elapsed_time(ev[1]) / K
+outs = C * (n // M)
+try:
+    hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    hbm = 6549.8
+clk = torch.cuda.clock_rate() if hasattr(torch.cuda, "clock_rate") else 1965
+fp32_peak = 148 * 128 * 1.965e9
+print(f"M={M} ntaps={nt} C={C} n={n}: {ms:.3f} ms = {outs / ms / 1e6:.2f} G out/s; "
+      f"FP32 pipe {outs * 4 * nt / (ms * 1e-3) / fp32_peak:.3f} of 148x128x1.965 GHz; "
+      f"HBM {outs * (8 * M + 8) / (ms * 1e-3) / 1e9 / hbm:.3f} of {hbm} GB/s")
