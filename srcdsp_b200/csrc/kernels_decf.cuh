@@ -69,15 +69,28 @@ __global__ void __launch_bounds__(128) decf_fir_kernel(const __grid_constant__ D
     const float2 *x = P.in + (size_t)ch * P.in_stride;
     const float2 *hist = P.hist + (size_t)ch * (P.N - 1);
     const long long s0 = (long long)tile * P.tile_out * P.M - P.lead;
-    for (int idx = tid; idx < P.n_local; idx += T) {
-        const long long s = s0 + idx;
-        float2 v = make_float2(0.f, 0.f);
-        if (s >= 0) {
-            if (s < P.n_in) v = __ldg(x + s);
-        } else if (s >= -(long long)(P.N - 1)) {
-            v = __ldg(hist + (P.N - 1 + s));
+    if (s0 >= 0 && s0 + P.n_local <= P.n_in) {
+        // interior tile: every sample comes from the input row -- 8-byte cp.async (rows are only 8-byte aligned against
+        // the block grid), all of a thread's copies in flight at once, no registers
+        const uint32_t xs_u32 = (uint32_t)__cvta_generic_to_shared(xs);
+        const float2 *src = x + s0;
+        for (int idx = tid; idx < P.n_local; idx += T) {
+            const uint32_t dst = xs_u32 + 8u * (uint32_t)(idx + P.padw * (int)__umulhi((unsigned)idx, P.blk_magic));
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src + idx) : "memory");
         }
-        xs[idx + P.padw * (int)__umulhi((unsigned)idx, P.blk_magic)] = v;
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    } else {
+        // edge tile: carried history in front of the block, zeros behind it
+        for (int idx = tid; idx < P.n_local; idx += T) {
+            const long long s = s0 + idx;
+            float2 v = make_float2(0.f, 0.f);
+            if (s >= 0) {
+                if (s < P.n_in) v = __ldg(x + s);
+            } else if (s >= -(long long)(P.N - 1)) {
+                v = __ldg(hist + (P.N - 1 + s));
+            }
+            xs[idx + P.padw * (int)__umulhi((unsigned)idx, P.blk_magic)] = v;
+        }
     }
     __syncthreads();
 

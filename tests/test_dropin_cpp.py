@@ -96,3 +96,33 @@ def test_corr_program_dropin_build_prints_the_reference_output(built_lib):
     _compile_dropin(exe, SRC_CORR)
     out = subprocess.run([exe], check=True, capture_output=True, text=True, timeout=300).stdout
     assert out == open(GOLDEN_CORR).read()
+
+
+SRC_FLOAT = os.path.join(ROOT, "tests", "cpp", "user_float.cpp")   # the float instantiation of the decimator
+GOLDEN_FLOAT = os.path.join(ROOT, "tests", "golden", "user_float.txt")
+
+
+def test_float_program_compiles_against_dropin_headers(built_lib):
+    _compile_dropin(os.path.join(BUILD, "user_float_gpu"), SRC_FLOAT)
+
+
+def test_float_program_reference_build_matches_committed_golden():
+    """Pins tests/golden/user_float.txt (checksums over raw float bits) to the unmodified reference."""
+    if not os.path.exists(os.path.join(REF, "dnsampling_filters.h")):
+        pytest.skip("no /root/reference here")
+    os.makedirs(BUILD, exist_ok=True)
+    exe = os.path.join(BUILD, "user_float_ref")
+    subprocess.run(["g++", "-std=gnu++11", "-O2", "-w", "-I" + REF, SRC_FLOAT, os.path.join(REF, "dsp_complex.cpp"), "-o", exe],
+                   check=True, capture_output=True, text=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    if os.environ.get("SRCDSP_REGEN_GOLDEN"):
+        open(GOLDEN_FLOAT, "w").write(out)
+    assert out == open(GOLDEN_FLOAT).read()
+
+
+@pytest.mark.gpu
+def test_float_program_dropin_build_prints_the_reference_output(built_lib):
+    exe = os.path.join(BUILD, "user_float_gpu")
+    _compile_dropin(exe, SRC_FLOAT)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True, timeout=300).stdout
+    assert out == open(GOLDEN_FLOAT).read()
