@@ -57,6 +57,11 @@ WORKLOADS = {
                  desc="corr: FixedPatternCorrelator<int16,int32,32,4> bank, 256 ch x 4Mi samples of noise (no peak: full scan)"),
     "fifo": dict(kind="fifo", channels=1, n=1 << 22, M=16, ntaps=255, mix=False, blocks=24,
                  desc="fifo: one stream through FifoWithTimeTrack (pinned ring, 16Mi samples) -> decimate-by-16 255-tap FIR, 4Mi-sample blocks"),
+    "cfg2f": dict(kind="decf", channels=256, n=1 << 22, M=16, ntaps=255, mix=False,
+                  desc="cfg2f: the reference's FLOAT instantiation of cfg2's filter (complex<float> samples, float taps), "
+                       "decimate-by-16 255-tap FIR, 256 ch x 4Mi samples (8 GiB in) per GPU"),
+    "cfg1f": dict(kind="decf", channels=256, n=1 << 22, M=8, ntaps=63, mix=False,
+                  desc="cfg1f: float decimate-by-8 63-tap FIR (BASELINE configs[0]'s filter), 256 ch x 4Mi samples per GPU"),
     "smoke": dict(kind="dec", channels=8, n=1 << 18, M=16, ntaps=255, mix=False, desc="smoke: 8 ch x 256Ki"),
 }
 
@@ -317,6 +322,85 @@ def corr_bench(args, w, base, S, torch, device):
     return 0
 
 
+def decf_bench(args, w, base, S, O, torch, device):
+    """The float instantiation FilterDnsamplingFir<complex<float>, ..., float, M> (bit-exact with the reference's
+    tap-order float sum).  Algorithmic bytes per output: 8*M + 8; arithmetic: 4*ntaps rounded FP32 operations per
+    output (a separate multiply and add per component and tap -- fusing them would change the result), which makes the
+    FP32 pipe, not HBM, the binding roofline for cfg2's filter."""
+    C, n, M, nt = w["channels"], w["n"], w["M"], w["ntaps"]
+    h = np.hamming(nt) * np.sinc((np.arange(nt) - (nt - 1) / 2.0) / M)
+    taps = (h / h.sum()).astype(np.float32)
+    x = (torch.rand((C, n, 2), device="cuda", generator=torch.Generator(device="cuda").manual_seed(SEED)) - 0.5) * 16384
+    y = torch.empty((C, n // M, 2), dtype=torch.float32, device="cuda")
+    d = S.FilterDnsamplingFirFloat(M, taps, channels=C, device=device, obsolete=True)
+    for _ in range(args.warmup):
+        d.step(x, out=y)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(device)
+    sampler.start()
+    l0 = S.launch_count()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    evs[0].record()
+    for _ in range(args.steps):
+        d.step(x, out=y)
+    evs[1].record()
+    torch.cuda.synchronize()
+    ms = evs[0].elapsed_time(evs[1]) / args.steps
+    clocks = sampler.stop()
+    launches = int(S.launch_count() - l0)
+    peak, peak_src = peaks()
+    n_out = C * (n // M)
+    alg = (8.0 * M + 8.0) * n_out
+    roof = {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak,
+            "traffic": None, "kernel": "decf_fir_kernel (FP32 pipe, tap-order FMUL + FADD chains)", "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": alg, "kernel_ms": ms}
+    if clocks and clocks.get("sm_max_mhz"):
+        roof["fp32_frac"] = 4.0 * nt * n_out / (ms * 1e-3) / (148 * 128 * clocks["sm_max_mhz"] * 1e6)
+        roof["fp32_note"] = ("4*ntaps rounded FP32 operations per output against 148 SM x 128 lanes x sm_max_mhz; the reference's "
+                             "float sum is a multiply and an add per tap and component (no FMA), kept for bit-exactness")
+    cpu = None
+    if not args.no_cpu:
+        r = O.ref()
+        if r is not None:  # the unmodified reference's float instantiation, one thread, a bounded sample of the workload
+            import time
+            ns = 1 << 20
+            xs = x[0, :ns].cpu().numpy()
+            f = O.RefDecF(r, M, taps, obsolete=True)
+            f.step(xs[: 1 << 16])
+            t0 = time.perf_counter()
+            reps = 0
+            while time.perf_counter() - t0 < 10.0:
+                f.step(xs)
+                reps += 1
+            dt = time.perf_counter() - t0
+            cpu = {"value": reps * (ns // M) / dt / 1e6, "unit": "Msamples/s", "cores": 1, "kind": "reference",
+                   "sample": f"{reps} x 1 channel x {ns} input samples of {args.workload}, SrcDsp reference headers (float instantiation), "
+                             "unmodified, g++ optimised, 1 thread"}
+    # end to end: host float buffers through the C ABI (pinned), H2D + kernel + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        import time
+        Ce = min(C, 64)
+        hx, hy = S.PinnedBuffer(Ce, 2 * n), S.PinnedBuffer(Ce, 2 * (n // M))  # 8 bytes per complex float sample
+        xin = hx.array.view(np.float32).reshape(Ce, n, 2)
+        yout = hy.array.view(np.float32).reshape(Ce, n // M, 2)
+        xin[...] = x[:Ce].cpu().numpy()
+        de = S.FilterDnsamplingFirFloat(M, taps, channels=Ce, device=device, obsolete=True)
+        de.step(xin, out=yout)
+        t0 = time.perf_counter()
+        for _ in range(2):
+            de.step(xin, out=yout)
+        dt = (time.perf_counter() - t0) / 2
+        e2e = {"value": Ce * (n // M) / dt / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": int(xin.nbytes),
+               "d2h_bytes_per_step": int(yout.nbytes), "steps": 2, "ms_per_step": dt * 1e3,
+               "api": f"FilterDnsamplingFirFloat.step(host numpy float32, {Ce} channels) -> C ABI srcdsp_decf_step",
+               "pinned": True}
+    line = dict(base, dtype="f32", value=n_out / (ms * 1e-3) / 1e6, ms_per_step=ms, roofline=roof, cpu_baseline=cpu, e2e=e2e,
+                clocks=clocks, gpu_launches=launches, impl="ours")
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -377,6 +461,8 @@ def main():
         return fifo_stream_bench(args, w, base, S, O, torch, local_rank)
     if w["kind"] == "corr":
         return corr_bench(args, w, base, S, torch, local_rank)
+    if w["kind"] == "decf":
+        return decf_bench(args, w, base, S, O, torch, local_rank)
     from srcdsp_b200.sharding import channel_shard
     my_ch = channel_shard(C * world, world, rank)  # weak scaling: 256 channels per GPU
     n_out = int(n * out_per_in(w))

@@ -18,17 +18,19 @@
 // registers: a thread owns the output PAIR (2q, 2q+1) and walks the samples downwards from xx[(2q+1)*M]; sample
 // (2q+1)*M - e is tap k = e of the upper output and tap k = e - M of the lower one.  Per 4 samples: 2 LDS.128
 // (samples) + 2 LDS.128 (broadcast: 4 taps of each output, from two pre-shifted zero-padded copies of the taps) feed
-// 32 FP32 instructions; a thread carries two such pairs (8 independent add chains).  The lane stride is 2*M samples
+// 32 FP32 instructions; a thread carries PAIRS such pairs (1 with 256 threads per CTA by default: more warps hide the
+// LDS latency and overlap another CTA's staging better than more chains per thread do).  The lane stride is 2*M samples
 // = M 16-byte units; for even M every block of 2*M samples is followed by one unit of padding so that the stride is
 // odd and the LDS.128 are conflict free.  Zero taps in front of / behind a filter add +-0 to its chain, which leaves
 // every finite sum unchanged (samples must be finite -- the reference's int conversion of NaN/Inf is undefined).
 #pragma once
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace srcdsp {
 
-constexpr int DECF_PAIRS = 2;  // output pairs per thread
 
 struct DecfParams {
     const float2 *in;
@@ -43,7 +45,7 @@ struct DecfParams {
     unsigned blk_magic;            // floor(2^32 / blk) + 1: idx / blk = umulhi(idx, magic) for the staged range
     int blk_chunks;                // 4-sample chunks per block (M / 2), or INT_MAX without padding
     int n_local;                   // staged samples per tile
-    int tile_out;                  // outputs per tile = 2 * DECF_PAIRS * blockDim.x
+    int tile_out;                  // outputs per tile = 2 * PAIRS * blockDim.x
     int tiles_per_ch;
     unsigned shift;                // (coeffScaling - leftShift) & 31, as x86 `sar` applies it
 };
@@ -55,7 +57,8 @@ __device__ __forceinline__ float decf_limit(float y, unsigned shift)
     return (float)v;
 }
 
-__global__ void __launch_bounds__(128) decf_fir_kernel(const __grid_constant__ DecfParams P)
+template <int PAIRS>
+__global__ void __launch_bounds__(256) decf_fir_kernel(const __grid_constant__ DecfParams P)
 {
     extern __shared__ __align__(16) uint8_t decf_smem[];
     float *ts = reinterpret_cast<float *>(decf_smem);              // [2][E]
@@ -96,45 +99,56 @@ __global__ void __launch_bounds__(128) decf_fir_kernel(const __grid_constant__ D
 
     // pair q = tid + j * T: upper output 2q + 1 sits at local index (2q + 1) * M + lead = the LAST sample of block
     // q + j0 (even M) -- chunks of 4 never straddle a block
-    float2 acc[DECF_PAIRS][2];
-    int pos[DECF_PAIRS];
+    float2 acc[PAIRS][2];
+    int pos[PAIRS];
 #pragma unroll
-    for (int j = 0; j < DECF_PAIRS; ++j) {
+    for (int j = 0; j < PAIRS; ++j) {
         acc[j][0] = acc[j][1] = make_float2(0.f, 0.f);
         const int top = (2 * (tid + j * T) + 1) * P.M + P.lead;
         pos[j] = top + P.padw * (int)__umulhi((unsigned)top, P.blk_magic);
     }
     int in_blk = 0;
     const float4 *t0 = reinterpret_cast<const float4 *>(ts), *t1 = reinterpret_cast<const float4 *>(ts + P.E);
-#pragma unroll 2
-    for (int c = 0; c < P.E / 4; ++c) {
-        const float4 k0 = t0[c], k1 = t1[c];  // taps e .. e + 3 of the lower / upper output (broadcast)
+    // one chunk = 4 samples (e .. e + 3) for the upper (UP) and / or lower (LO) output of every pair
+    auto chunk = [&](int c, auto up_tag, auto lo_tag) {
+        constexpr bool UP = decltype(up_tag)::value, LO = decltype(lo_tag)::value;
+        float4 k0 = make_float4(0.f, 0.f, 0.f, 0.f), k1 = k0;  // taps e .. e + 3 of the lower / upper output (broadcast)
+        if (LO) k0 = t0[c];
+        if (UP) k1 = t1[c];
 #pragma unroll
-        for (int j = 0; j < DECF_PAIRS; ++j) {
+        for (int j = 0; j < PAIRS; ++j) {
             // samples pos-3 .. pos (ascending address); e ascends as the address descends
             const float4 hi = *reinterpret_cast<const float4 *>(xs + pos[j] - 1);  // {x[pos-1], x[pos]}
             const float4 lo = *reinterpret_cast<const float4 *>(xs + pos[j] - 3);  // {x[pos-3], x[pos-2]}
             float2 &a0 = acc[j][0], &a1 = acc[j][1];
-            a1.x = __fadd_rn(a1.x, __fmul_rn(k1.x, hi.z)), a1.y = __fadd_rn(a1.y, __fmul_rn(k1.x, hi.w));
-            a0.x = __fadd_rn(a0.x, __fmul_rn(k0.x, hi.z)), a0.y = __fadd_rn(a0.y, __fmul_rn(k0.x, hi.w));
-            a1.x = __fadd_rn(a1.x, __fmul_rn(k1.y, hi.x)), a1.y = __fadd_rn(a1.y, __fmul_rn(k1.y, hi.y));
-            a0.x = __fadd_rn(a0.x, __fmul_rn(k0.y, hi.x)), a0.y = __fadd_rn(a0.y, __fmul_rn(k0.y, hi.y));
-            a1.x = __fadd_rn(a1.x, __fmul_rn(k1.z, lo.z)), a1.y = __fadd_rn(a1.y, __fmul_rn(k1.z, lo.w));
-            a0.x = __fadd_rn(a0.x, __fmul_rn(k0.z, lo.z)), a0.y = __fadd_rn(a0.y, __fmul_rn(k0.z, lo.w));
-            a1.x = __fadd_rn(a1.x, __fmul_rn(k1.w, lo.x)), a1.y = __fadd_rn(a1.y, __fmul_rn(k1.w, lo.y));
-            a0.x = __fadd_rn(a0.x, __fmul_rn(k0.w, lo.x)), a0.y = __fadd_rn(a0.y, __fmul_rn(k0.w, lo.y));
+            if (UP) a1.x = __fadd_rn(a1.x, __fmul_rn(k1.x, hi.z)), a1.y = __fadd_rn(a1.y, __fmul_rn(k1.x, hi.w));
+            if (LO) a0.x = __fadd_rn(a0.x, __fmul_rn(k0.x, hi.z)), a0.y = __fadd_rn(a0.y, __fmul_rn(k0.x, hi.w));
+            if (UP) a1.x = __fadd_rn(a1.x, __fmul_rn(k1.y, hi.x)), a1.y = __fadd_rn(a1.y, __fmul_rn(k1.y, hi.y));
+            if (LO) a0.x = __fadd_rn(a0.x, __fmul_rn(k0.y, hi.x)), a0.y = __fadd_rn(a0.y, __fmul_rn(k0.y, hi.y));
+            if (UP) a1.x = __fadd_rn(a1.x, __fmul_rn(k1.z, lo.z)), a1.y = __fadd_rn(a1.y, __fmul_rn(k1.z, lo.w));
+            if (LO) a0.x = __fadd_rn(a0.x, __fmul_rn(k0.z, lo.z)), a0.y = __fadd_rn(a0.y, __fmul_rn(k0.z, lo.w));
+            if (UP) a1.x = __fadd_rn(a1.x, __fmul_rn(k1.w, lo.x)), a1.y = __fadd_rn(a1.y, __fmul_rn(k1.w, lo.y));
+            if (LO) a0.x = __fadd_rn(a0.x, __fmul_rn(k0.w, lo.x)), a0.y = __fadd_rn(a0.y, __fmul_rn(k0.w, lo.y));
             pos[j] -= 4;
         }
         if (++in_blk == P.blk_chunks) {  // uniform: step over the padding in front of the block just finished
             in_blk = 0;
 #pragma unroll
-            for (int j = 0; j < DECF_PAIRS; ++j) pos[j] -= P.padw;
+            for (int j = 0; j < PAIRS; ++j) pos[j] -= P.padw;
         }
-    }
+    };
+    // chunks below M / 4 hold only zero taps of the lower output (its tap index e - M is negative), chunks from
+    // ceil(N / 4) on only zero taps of the upper one: skipping a zero tap leaves its chain unchanged
+    const int c1 = min(P.M / 4, (P.N + 3) / 4), c2 = (P.N + 3) / 4, c3 = P.E / 4;
+    int c = 0;
+    for (; c < c1; ++c) chunk(c, std::true_type{}, std::false_type{});
+#pragma unroll 2
+    for (; c < c2; ++c) chunk(c, std::true_type{}, std::true_type{});
+    for (; c < c3; ++c) chunk(c, std::false_type{}, std::true_type{});
     float2 *o = P.out + (size_t)ch * P.out_stride;
     const long long o0 = (long long)tile * P.tile_out;
 #pragma unroll
-    for (int j = 0; j < DECF_PAIRS; ++j) {
+    for (int j = 0; j < PAIRS; ++j) {
         const long long i = o0 + 2 * (tid + j * T);
         const float2 y0 = make_float2(decf_limit(acc[j][0].x, P.shift), decf_limit(acc[j][0].y, P.shift));
         const float2 y1 = make_float2(decf_limit(acc[j][1].x, P.shift), decf_limit(acc[j][1].y, P.shift));

@@ -120,8 +120,11 @@ def test_float_golden_gpu(S, case, where):
 @pytest.mark.parametrize("M,nt", [(1, 17), (2, 9), (3, 31), (4, 1023), (5, 7), (6, 40), (7, 100), (8, 63), (10, 90),
                                   (12, 255), (16, 255), (16, 256), (32, 64), (64, 300), (8, 1), (1, 1), (24, 48)])
 @pytest.mark.parametrize("kind", ["unity", "int", "frac"])
-def test_float_decimator_sweep(S, corc, M, nt, kind):
-    """Ragged streaming blocks (also shorter than ntaps - 1), host and device buffers, left shift, every tap family."""
+@pytest.mark.parametrize("pairs", [1, 2])
+def test_float_decimator_sweep(S, corc, monkeypatch, M, nt, kind, pairs):
+    """Ragged streaming blocks (also shorter than ntaps - 1), host and device buffers, left shift, every tap family,
+    both thread shapes of the kernel (1 or 2 output pairs per thread)."""
+    monkeypatch.setenv("SRCDSP_DECF_PAIRS", str(pairs))
     rng = np.random.default_rng(M * 10007 + nt)
     t = ftaps(rng, nt, kind)
     ls = 1 if kind == "int" and nt > 4 else 0

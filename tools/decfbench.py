@@ -20,18 +20,25 @@ h = np.hamming(nt) * np.sinc((np.arange(nt) - (nt - 1) / 2.0) / M)
 taps = (h / h.sum()).astype(np.float32)
 x = (torch.rand((C, n, 2), device="cuda") - 0.5) * 30000
 y = torch.empty((C, n // M, 2), dtype=torch.float32, device="cuda")
-d = S.FilterDnsamplingFirFloat(M, taps, channels=C, obsolete=True)
-for _ in range(3):
-    d.step(x, out=y)
-ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-torch.cuda.synchronize()
-ev[0].record()
-K = 10
-for _ in range(K):
-    d.step(x, out=y)
-ev[1].record()
-torch.cuda.synchronize()
-ms = ev[0].elapsed_time(ev[1]) / K
+def run():
+    d = S.FilterDnsamplingFirFloat(M, taps, channels=C, obsolete=True)
+    for _ in range(3):
+        d.step(x, out=y)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    torch.cuda.synchronize()
+    ev[0].record()
+    K = 10
+    for _ in range(K):
+        d.step(x, out=y)
+    ev[1].record()
+    torch.cuda.synchronize()
+    return ev[0].elapsed_time(ev[1]) / K
+
+
+for pairs in ("2", "1"):
+    os.environ["SRCDSP_DECF_PAIRS"] = pairs
+    ms = run()
+    print(f"pairs per thread {pairs}: {ms:.3f} ms")
 outs = C * (n // M)
 try:
     hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
