@@ -47,6 +47,7 @@ struct DecfParams {
     int n_local;                   // staged samples per tile
     int tile_out;                  // outputs per tile = 2 * PAIRS * blockDim.x
     int tiles_per_ch;
+    int prefetch_dist;             // CTAs resident on the device at once (0: no L2 prefetch)
     unsigned shift;                // (coeffScaling - leftShift) & 31, as x86 `sar` applies it
 };
 
@@ -67,6 +68,18 @@ __global__ void __launch_bounds__(256) decf_fir_kernel(const __grid_constant__ D
     const unsigned ch = blockIdx.x / (unsigned)P.tiles_per_ch;
     const int tile = (int)(blockIdx.x - ch * (unsigned)P.tiles_per_ch);
 
+    // L2 prefetch of the tile that the CTA taking this one's place will stage (prefetch_dist = resident CTAs of the
+    // grid): one bulk prefetch by one thread, so that the staging below waits for L2, not for HBM
+    if (tid == 0 && P.prefetch_dist > 0 && blockIdx.x + (unsigned)P.prefetch_dist < gridDim.x) {
+        const unsigned nb = blockIdx.x + (unsigned)P.prefetch_dist, nch = nb / (unsigned)P.tiles_per_ch;
+        const long long a = max((long long)(nb - nch * (unsigned)P.tiles_per_ch) * P.tile_out * P.M - P.lead, 0ll);
+        const long long b = min(a + P.n_local, P.n_in);
+        if (b > a) {
+            const uintptr_t p0 = reinterpret_cast<uintptr_t>(P.in + (size_t)nch * P.in_stride + a);
+            const uintptr_t lo = (p0 + 15) & ~(uintptr_t)15, hi = (p0 + (uintptr_t)(b - a) * 8) & ~(uintptr_t)15;
+            if (hi > lo) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo), "r"((uint32_t)(hi - lo)) : "memory");
+        }
+    }
     for (int i = tid; i < 2 * P.E; i += T) ts[i] = __ldg(P.taps2 + i);
     // stage: local index idx <-> stream sample s = tile * tile_out * M + idx - lead
     const float2 *x = P.in + (size_t)ch * P.in_stride;
