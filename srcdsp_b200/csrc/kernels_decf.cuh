@@ -58,7 +58,7 @@ __device__ __forceinline__ float decf_limit(float y, unsigned shift)
     return (float)v;
 }
 
-template <int PAIRS>
+template <int PAIRS, int BC>
 __global__ void __launch_bounds__(256) decf_fir_kernel(const __grid_constant__ DecfParams P)
 {
     extern __shared__ __align__(16) uint8_t decf_smem[];
@@ -154,6 +154,42 @@ __global__ void __launch_bounds__(256) decf_fir_kernel(const __grid_constant__ D
     // ceil(N / 4) on only zero taps of the upper one: skipping a zero tap leaves its chain unchanged
     const int c1 = min(P.M / 4, (P.N + 3) / 4), c2 = (P.N + 3) / 4, c3 = P.E / 4;
     int c = 0;
+    if (BC > 0) {
+        // M = 2 * BC (a power of two up to 32) and N >= 2 * M: whole blocks of BC chunks with compile-time offsets --
+        // no per-chunk position / padding bookkeeping, every LDS address an immediate off one register per pair.
+        // The first block is upper-only below chunk BC / 2 (= M / 4), all later whole blocks feed both outputs.
+        auto block = [&](int cb, auto first_tag) {
+            constexpr bool FIRST = decltype(first_tag)::value;
+#pragma unroll
+            for (int i = 0; i < BC; ++i) {
+                const bool lo_on = !FIRST || i >= BC / 2;
+                float4 k0 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (lo_on) k0 = t0[cb + i];
+                const float4 k1 = t1[cb + i];
+#pragma unroll
+                for (int j = 0; j < PAIRS; ++j) {
+                    const float4 hi = *reinterpret_cast<const float4 *>(xs + pos[j] - 4 * i - 1);
+                    const float4 lo = *reinterpret_cast<const float4 *>(xs + pos[j] - 4 * i - 3);
+                    float2 &a0 = acc[j][0], &a1 = acc[j][1];
+                    a1.x = __fadd_rn(a1.x, __fmul_rn(k1.x, hi.z)), a1.y = __fadd_rn(a1.y, __fmul_rn(k1.x, hi.w));
+                    if (lo_on) a0.x = __fadd_rn(a0.x, __fmul_rn(k0.x, hi.z)), a0.y = __fadd_rn(a0.y, __fmul_rn(k0.x, hi.w));
+                    a1.x = __fadd_rn(a1.x, __fmul_rn(k1.y, hi.x)), a1.y = __fadd_rn(a1.y, __fmul_rn(k1.y, hi.y));
+                    if (lo_on) a0.x = __fadd_rn(a0.x, __fmul_rn(k0.y, hi.x)), a0.y = __fadd_rn(a0.y, __fmul_rn(k0.y, hi.y));
+                    a1.x = __fadd_rn(a1.x, __fmul_rn(k1.z, lo.z)), a1.y = __fadd_rn(a1.y, __fmul_rn(k1.z, lo.w));
+                    if (lo_on) a0.x = __fadd_rn(a0.x, __fmul_rn(k0.z, lo.z)), a0.y = __fadd_rn(a0.y, __fmul_rn(k0.z, lo.w));
+                    a1.x = __fadd_rn(a1.x, __fmul_rn(k1.w, lo.x)), a1.y = __fadd_rn(a1.y, __fmul_rn(k1.w, lo.y));
+                    if (lo_on) a0.x = __fadd_rn(a0.x, __fmul_rn(k0.w, lo.x)), a0.y = __fadd_rn(a0.y, __fmul_rn(k0.w, lo.y));
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < PAIRS; ++j) pos[j] -= 4 * BC + 2;  // the block and the padding in front of it
+        };
+        block(0, std::true_type{});
+        c = BC;
+#pragma unroll 1
+        for (; c + BC <= c2; c += BC) block(c, std::false_type{});
+        // in_blk is 0 here: the per-chunk code below finishes the last (partial) block and the lower-only tail
+    }
     for (; c < c1; ++c) chunk(c, std::true_type{}, std::false_type{});
 #pragma unroll 2
     for (; c < c2; ++c) chunk(c, std::true_type{}, std::true_type{});

@@ -125,6 +125,8 @@ def test_float_decimator_sweep(S, corc, monkeypatch, M, nt, kind, pairs):
     """Ragged streaming blocks (also shorter than ntaps - 1), host and device buffers, left shift, every tap family,
     both thread shapes of the kernel (1 or 2 output pairs per thread)."""
     monkeypatch.setenv("SRCDSP_DECF_PAIRS", str(pairs))
+    if pairs == 2 and kind == "frac":
+        monkeypatch.setenv("SRCDSP_DECF_BLOCKS", "0")  # the per-chunk code alone (power-of-two ratios default to whole blocks)
     rng = np.random.default_rng(M * 10007 + nt)
     t = ftaps(rng, nt, kind)
     ls = 1 if kind == "int" and nt > 4 else 0

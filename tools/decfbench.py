@@ -35,13 +35,15 @@ def run():
     return ev[0].elapsed_time(ev[1]) / K
 
 
-for pairs, pf in (("2", "1"), ("1", "1"), ("", "0"), ("", "1")):  # forced shapes, then the automatic choice without / with L2 prefetch
+# forced thread shapes, then the automatic choice without L2 prefetch / without the whole-block fast path / as shipped
+for pairs, pf, blocks in (("2", "1", "1"), ("1", "1", "1"), ("", "0", "1"), ("", "1", "0"), ("", "1", "1")):
     os.environ.pop("SRCDSP_DECF_PAIRS", None)
     if pairs:
         os.environ["SRCDSP_DECF_PAIRS"] = pairs
     os.environ["SRCDSP_DECF_PREFETCH"] = pf
+    os.environ["SRCDSP_DECF_BLOCKS"] = blocks
     ms = run()
-    print(f"pairs per thread {pairs or 'auto'}, L2 prefetch {pf}: {ms:.3f} ms")
+    print(f"pairs per thread {pairs or 'auto'}, L2 prefetch {pf}, whole blocks {blocks}: {ms:.3f} ms")
 outs = C * (n // M)
 try:
     hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
