@@ -290,6 +290,11 @@ class _RefLib:
         L.ref_decf_reset.argtypes = [vp]
         L.ref_decf_set_left_shift.argtypes = [vp, C.c_int]
         L.ref_decf_step.argtypes = [vp, fp, C.c_size_t, C.c_int, fp]
+        L.ref_firf_create.restype = vp
+        L.ref_firf_create.argtypes = [fp, C.c_int]
+        L.ref_firf_destroy.argtypes = [vp]
+        L.ref_firf_reset.argtypes = [vp]
+        L.ref_firf_step.argtypes = [vp, fp, C.c_size_t, fp]
         L.ref_fir_create.restype = vp
         L.ref_fir_create.argtypes = [_i32p, C.c_int]
         L.ref_fir_destroy.argtypes = [vp]
@@ -446,6 +451,29 @@ class RefDecF:
         assert x.shape[0] % self.M == 0
         out = np.empty((x.shape[0] // self.M, 2), np.float32)
         self._l.ref_decf_step(self._h, _pf(x), x.shape[0], self.M, _pf(out))
+        return out
+
+
+class RefFirF:
+    """The reference's FilterFir<complex<float>, complex<float>, complex<float>, float>, compiled."""
+
+    def __init__(self, lib: _RefLib, taps):
+        self._l = lib.lib
+        t = np.ascontiguousarray(taps, np.float32)
+        self._h = self._l.ref_firf_create(_pf(t), t.size)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._l.ref_firf_destroy(self._h)
+            self._h = None
+
+    def reset(self):
+        self._l.ref_firf_reset(self._h)
+
+    def step(self, x):
+        x = np.ascontiguousarray(x, np.float32).reshape(-1, 2)
+        out = np.empty_like(x)
+        self._l.ref_firf_step(self._h, _pf(x), x.shape[0], _pf(out))
         return out
 
 

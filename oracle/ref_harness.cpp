@@ -246,6 +246,21 @@ void ref_decf_step(void *h, const float *in_iq, size_t n_in, int M, float *out_i
     if (!out.empty()) std::memcpy(out_iq, out.data(), out.size() * sizeof(cf32));
 }
 
+// --- float plain FIR: FilterFir<complex<float>, complex<float>, complex<float>, float> (filters.h) ------------------
+void *ref_firf_create(const float *taps, int ntaps)
+{
+    return new FilterFir<cf32, cf32, cf32, float>(std::vector<float>(taps, taps + ntaps));
+}
+void ref_firf_destroy(void *h) { delete static_cast<FilterFir<cf32, cf32, cf32, float> *>(h); }
+void ref_firf_reset(void *h) { static_cast<FilterFir<cf32, cf32, cf32, float> *>(h)->reset(); }
+void ref_firf_step(void *h, const float *in_iq, size_t n, float *out_iq)
+{
+    std::vector<cf32> in(n), out(n);
+    if (n) std::memcpy(in.data(), in_iq, n * sizeof(cf32));
+    static_cast<FilterFir<cf32, cf32, cf32, float> *>(h)->step(in, out);
+    if (n) std::memcpy(out_iq, out.data(), n * sizeof(cf32));
+}
+
 // --- plain FIR (filters.h) ----------------------------------------------------------------------
 void *ref_fir_create(const int32_t *taps, int ntaps)
 {

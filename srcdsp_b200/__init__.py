@@ -25,7 +25,7 @@ import numpy as np
 from . import _capi
 from ._capi import SrcDspError, check, lib
 
-__all__ = ["Mixer", "FilterDnsamplingFir", "FilterDnsamplingFirFloat", "FilterFir", "FilterUpsamplingFir", "Ddc", "SrcDspError",
+__all__ = ["Mixer", "FilterDnsamplingFir", "FilterDnsamplingFirFloat", "FilterFirFloat", "FilterFir", "FilterUpsamplingFir", "Ddc", "SrcDspError",
            "synth_fill", "launch_count", "device_count", "PinnedBuffer", "FifoWithTimeTrack", "saveBinarySamples",
            "readBinarySamples", "FixedPatternCorrelator"]
 
@@ -415,6 +415,20 @@ class FilterDnsamplingFirFloat(_Handle):
 
     def sync(self):
         check(lib().srcdsp_decf_sync(self._h))
+
+
+class FilterFirFloat(FilterDnsamplingFirFloat):
+    """FilterFir<complex<float>, complex<float>, complex<float>, float> (reference filters.h:42-169 with float types):
+    in age order the M = 1 float decimator; setCoeffs clears the history (filters.h:96)."""
+
+    def __init__(self, firCoeff=None, channels: int = 1, device: int = 0):
+        super().__init__(1, None, channels, device, obsolete=True)
+        if firCoeff is not None:
+            self.setCoeffs(firCoeff)
+
+    def setCoeffs(self, firCoeff):
+        super().setCoeffs(firCoeff)
+        self.reset()
 
 
 # ----------------------------------------------------------------------------------------------

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "dnsampling_filters.h"   // obsolete twin: accepts 63 taps
+#include "filters.h"              // FilterFir (global namespace)
 
 typedef std::complex<float> cf32;
 
@@ -77,8 +78,33 @@ static void run(const char *name, int ntaps, double gain, int left_shift, float 
     std::printf("%s after reset, DC: out[last]=(%.1f,%.1f)\n", name, out.back().real(), out.back().imag());
 }
 
+// FilterFir<complex<float>, ...> (filters.h): the non-decimating FIR with float types, streaming blocks + copy
+static void run_fir()
+{
+    FilterFir<cf32, cf32, cf32, float> f(lowpass(33, 4, 311.7));
+    uint64_t n0 = 0;
+    const size_t blocks[3] = {1000, 3096, 17};
+    for (int b = 0; b < 3; ++b) {
+        std::vector<cf32> in(blocks[b]), out(blocks[b]);
+        for (size_t i = 0; i < in.size(); ++i) {
+            const uint32_t h = hash32(0x5EED0F11u, 1, n0 + i);
+            in[i] = cf32(0.25f * (float)(int16_t)(h & 0xFFFF), 0.25f * (float)(int16_t)(h >> 16));
+        }
+        n0 += in.size();
+        f.step(in, out);
+        std::printf("FilterFir float block %d: %zu  out[0]=(%.1f,%.1f) out[last]=(%.1f,%.1f) checksum %016llx\n", b, out.size(),
+                    out[0].real(), out[0].imag(), out.back().real(), out.back().imag(), (unsigned long long)checksum(out));
+    }
+    FilterFir<cf32, cf32, cf32, float> g(f);  // copies taps and history
+    std::vector<cf32> in(64, cf32(100.5f, -7.25f)), o1(64), o2(64);
+    f.step(in, o1);
+    g.step(in, o2);
+    std::printf("FilterFir float copy: %016llx %016llx\n", (unsigned long long)checksum(o1), (unsigned long long)checksum(o2));
+}
+
 int main()
 {
+    run_fir();
     run<8>("unity /8 63 taps", 63, 1.0, 0, 0.37f);        // all |c| < 1: the reference applies no shift
     run<16>("gain-40000 /16 255 taps", 255, 40000.0, 0, 0.5f);  // integer parts: coeffScaling = 15
     run<4>("gain-97.3 /4 1023 taps ls1", 1023, 97.3, 1, 1.0f);

@@ -66,6 +66,23 @@ def test_float_oracle_vs_reference(corc, reflib, M, nt, kind):
     assert corc.decf_coeff_scaling(t) == O.np_decf_coeff_scaling(t)
 
 
+@pytest.mark.parametrize("kind", ["unity", "int", "frac"])
+def test_float_fir_oracle_vs_reference(corc, reflib, kind):
+    """FilterFir<complex<float>, ...> (filters.h:130-169) in age order is the M = 1 float decimator, for any block
+    length (its circular buffer has no minimum block size), including after reset()."""
+    rng = np.random.default_rng(11)
+    t = ftaps(rng, 33, kind)
+    ref, h = O.RefFirF(reflib, t), None
+    for n in (1000, 5, 1, 777):
+        x = rng.uniform(-20000, 20000, (n, 2)).astype(np.float32)
+        e = ref.step(x)
+        g, h = corc.decf_step(t, 1, x, h)
+        assert np.array_equal(e, g), (kind, n)
+    ref.reset()
+    x = rng.uniform(-20000, 20000, (100, 2)).astype(np.float32)
+    assert np.array_equal(ref.step(x), corc.decf_step(t, 1, x)[0])
+
+
 def test_float_coeff_scaling_is_integer_abs(corc):
     """dsptl_dnsampling_filters.h:128-132: abs() on a float tap is ::abs(int) there."""
     assert corc.decf_coeff_scaling(np.full(8, 0.9, np.float32)) == 0x80000000   # sum of int(0.9) = 0: undefined -> INT_MIN
@@ -140,6 +157,22 @@ def test_float_decimator_sweep(S, corc, monkeypatch, M, nt, kind, pairs):
         exp, h = corc.decf_step(t, M, x, h, ls)
         got = host(d.step(dev(x))) if blk % 2 else d.step(x)
         assert np.array_equal(got, exp), (M, nt, kind, blk, rel_rms(got, exp))
+
+
+@pytest.mark.gpu
+def test_float_filter_fir(S, corc):
+    rng = np.random.default_rng(12)
+    t = ftaps(rng, 33, "frac")
+    f, h = S.FilterFirFloat(t, channels=2), [None, None]
+    for blk, n in enumerate((1000, 5, 1, 4096)):
+        x = rng.uniform(-20000, 20000, (2, n, 2)).astype(np.float32)
+        got = host(f.step(dev(x))) if blk % 2 else f.step(x)
+        for c in range(2):
+            e, h[c] = corc.decf_step(t, 1, x[c], h[c])
+            assert np.array_equal(got[c], e), (blk, c)
+    f.setCoeffs(t)  # clears the history (filters.h:96)
+    x = rng.uniform(-20000, 20000, (2, 64, 2)).astype(np.float32)
+    assert np.array_equal(f.step(x)[0], corc.decf_step(t, 1, x[0])[0])
 
 
 @pytest.mark.gpu
