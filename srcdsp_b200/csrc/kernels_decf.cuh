@@ -48,6 +48,7 @@ struct DecfParams {
     int tile_out;                  // outputs per tile = 2 * PAIRS * blockDim.x
     int tiles_per_ch;
     int prefetch_dist;             // CTAs resident on the device at once (0: no L2 prefetch)
+    unsigned stage_step;           // bytes the padded staging position advances per round of blockDim.x samples (0: blockDim.x % blk != 0)
     unsigned shift;                // (coeffScaling - leftShift) & 31, as x86 `sar` applies it
 };
 
@@ -90,9 +91,18 @@ __global__ void __launch_bounds__(256) decf_fir_kernel(const __grid_constant__ D
         // the block grid), all of a thread's copies in flight at once, no registers
         const uint32_t xs_u32 = (uint32_t)__cvta_generic_to_shared(xs);
         const float2 *src = x + s0;
-        for (int idx = tid; idx < P.n_local; idx += T) {
-            const uint32_t dst = xs_u32 + 8u * (uint32_t)(idx + P.padw * (int)__umulhi((unsigned)idx, P.blk_magic));
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src + idx) : "memory");
+        if (P.stage_step) {
+            // the CTA is a whole number of blocks wide: the padded position advances by a constant per round
+            uint32_t dst = xs_u32 + 8u * (uint32_t)(tid + P.padw * (int)__umulhi((unsigned)tid, P.blk_magic));
+            const float2 *sp = src + tid;
+#pragma unroll 4
+            for (int idx = tid; idx < P.n_local; idx += T, dst += P.stage_step, sp += T)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(sp) : "memory");
+        } else {
+            for (int idx = tid; idx < P.n_local; idx += T) {
+                const uint32_t dst = xs_u32 + 8u * (uint32_t)(idx + P.padw * (int)__umulhi((unsigned)idx, P.blk_magic));
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src + idx) : "memory");
+            }
         }
         asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
     } else {
