@@ -83,6 +83,27 @@ def test_float_fir_oracle_vs_reference(corc, reflib, kind):
     assert np.array_equal(ref.step(x), corc.decf_step(t, 1, x)[0])
 
 
+def test_float_time_sliced_stream_equals_sequential(corc):
+    """one long float stream cut into time slices with a warm-up halo (srcdsp_b200.sharding) gives the
+    sequential result bit for bit -- every output's float chain only ever sees its own ntaps-sample window."""
+    from srcdsp_b200.sharding import time_slices
+    rng = np.random.default_rng(21)
+    M, nt, n = 4, 1023, 4 * 3000
+    t = ftaps(rng, nt, "unity")
+    x = rng.uniform(-20000, 20000, (n, 2)).astype(np.float32)
+    whole, _ = corc.decf_step(t, M, x)
+    for W in (2, 3, 8):
+        outs = []
+        for sl in time_slices(n, W, [nt], [M]):
+            h = None
+            if sl.warmup:
+                _, h = corc.decf_step(t, M, x[sl.start - sl.warmup:sl.start], h)
+            y, _ = corc.decf_step(t, M, x[sl.start:sl.start + sl.length], h)
+            assert y.shape[0] == sl.out_length
+            outs.append(y)
+        assert np.array_equal(np.concatenate(outs), whole), W
+
+
 def test_float_coeff_scaling_is_integer_abs(corc):
     """dsptl_dnsampling_filters.h:128-132: abs() on a float tap is ::abs(int) there."""
     assert corc.decf_coeff_scaling(np.full(8, 0.9, np.float32)) == 0x80000000   # sum of int(0.9) = 0: undefined -> INT_MIN
