@@ -52,6 +52,12 @@ struct DecfParams {
     unsigned shift;                // (coeffScaling - leftShift) & 31, as x86 `sar` applies it
 };
 
+// taps of short filters travel in the kernel's parameter space (constant bank): 2 * E floats <= 3584 bytes
+constexpr int DECF_CT_MAX4 = 224;
+struct DecfTaps {
+    float4 t[DECF_CT_MAX4];  // [0, E/4): lower output (c[e - M]), [E/4, E/2): upper output (c[e])
+};
+
 __device__ __forceinline__ float decf_limit(float y, unsigned shift)
 {
     int v = __float2int_rz(y) >> shift;  // complex<int32_t>(y): truncation; limitScale16 (dsp_complex.cpp:63-73)
@@ -59,8 +65,9 @@ __device__ __forceinline__ float decf_limit(float y, unsigned shift)
     return (float)v;
 }
 
-template <int PAIRS, int BC>
-__global__ void __launch_bounds__(256) decf_fir_kernel(const __grid_constant__ DecfParams P)
+// CT: the taps are read from the parameter space (uniform constant loads: no LDS, no shared-memory wavefronts for them)
+template <int PAIRS, int BC, bool CT>
+__global__ void __launch_bounds__(256) decf_fir_kernel(const __grid_constant__ DecfParams P, const __grid_constant__ DecfTaps K)
 {
     extern __shared__ __align__(16) uint8_t decf_smem[];
     float *ts = reinterpret_cast<float *>(decf_smem);              // [2][E]
@@ -81,7 +88,8 @@ __global__ void __launch_bounds__(256) decf_fir_kernel(const __grid_constant__ D
             if (hi > lo) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo), "r"((uint32_t)(hi - lo)) : "memory");
         }
     }
-    for (int i = tid; i < 2 * P.E; i += T) ts[i] = __ldg(P.taps2 + i);
+    if (!CT)
+        for (int i = tid; i < 2 * P.E; i += T) ts[i] = __ldg(P.taps2 + i);
     // stage: local index idx <-> stream sample s = tile * tile_out * M + idx - lead
     const float2 *x = P.in + (size_t)ch * P.in_stride;
     const float2 *hist = P.hist + (size_t)ch * (P.N - 1);
@@ -132,12 +140,15 @@ __global__ void __launch_bounds__(256) decf_fir_kernel(const __grid_constant__ D
     }
     int in_blk = 0;
     const float4 *t0 = reinterpret_cast<const float4 *>(ts), *t1 = reinterpret_cast<const float4 *>(ts + P.E);
+    const int e4 = P.E / 4;
+    auto tap0 = [&](int c) { return CT ? K.t[c] : t0[c]; };
+    auto tap1 = [&](int c) { return CT ? K.t[e4 + c] : t1[c]; };
     // one chunk = 4 samples (e .. e + 3) for the upper (UP) and / or lower (LO) output of every pair
     auto chunk = [&](int c, auto up_tag, auto lo_tag) {
         constexpr bool UP = decltype(up_tag)::value, LO = decltype(lo_tag)::value;
         float4 k0 = make_float4(0.f, 0.f, 0.f, 0.f), k1 = k0;  // taps e .. e + 3 of the lower / upper output (broadcast)
-        if (LO) k0 = t0[c];
-        if (UP) k1 = t1[c];
+        if (LO) k0 = tap0(c);
+        if (UP) k1 = tap1(c);
 #pragma unroll
         for (int j = 0; j < PAIRS; ++j) {
             // samples pos-3 .. pos (ascending address); e ascends as the address descends
@@ -174,8 +185,8 @@ __global__ void __launch_bounds__(256) decf_fir_kernel(const __grid_constant__ D
             for (int i = 0; i < BC; ++i) {
                 const bool lo_on = !FIRST || i >= BC / 2;
                 float4 k0 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (lo_on) k0 = t0[cb + i];
-                const float4 k1 = t1[cb + i];
+                if (lo_on) k0 = tap0(cb + i);
+                const float4 k1 = tap1(cb + i);
 #pragma unroll
                 for (int j = 0; j < PAIRS; ++j) {
                     const float4 hi = *reinterpret_cast<const float4 *>(xs + pos[j] - 4 * i - 1);
