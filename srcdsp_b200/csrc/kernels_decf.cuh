@@ -23,6 +23,11 @@
 // = M 16-byte units; for even M every block of 2*M samples is followed by one unit of padding so that the stride is
 // odd and the LDS.128 are conflict free.  Zero taps in front of / behind a filter add +-0 to its chain, which leaves
 // every finite sum unchanged (samples must be finite -- the reference's int conversion of NaN/Inf is undefined).
+//
+// Measured steps (256 channels, /16 x 255 taps, 1 Mi samples per channel; tools/decfbench.py):
+//   plain staging loads 3.03 ms -> 8-byte cp.async (all copies of a thread in flight) 1.14 -> bulk L2 prefetch of the
+//   successor tile 1.00 -> whole blocks with compile-time offsets (BC > 0) 0.92 -> taps through the parameter space
+//   (CT: uniform constant loads, no tap LDS) 0.79 ms = 21.3 G out/s = 0.58 of the FP32 pipe.
 #pragma once
 
 #include <type_traits>
