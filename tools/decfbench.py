@@ -49,7 +49,6 @@ try:
     hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
 except Exception:
     hbm = 6549.8
-clk = torch.cuda.clock_rate() if hasattr(torch.cuda, "clock_rate") else 1965
 fp32_peak = 148 * 128 * 1.965e9
 print(f"M={M} ntaps={nt} C={C} n={n}: {ms:.3f} ms = {outs / ms / 1e6:.2f} G out/s; "
       f"FP32 pipe {outs * 4 * nt / (ms * 1e-3) / fp32_peak:.3f} of 148x128x1.965 GHz; "
