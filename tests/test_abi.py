@@ -26,7 +26,10 @@ def test_header_declares_the_reference_api():
               "srcdsp_dec_set_left_shift",
               "srcdsp_up_create", "srcdsp_up_set_coefficients", "srcdsp_up_step", "srcdsp_up_reset",
               "srcdsp_up_get_length", "srcdsp_up_get_imp_length", "srcdsp_up_get_ratio",
-              "srcdsp_ddc_create", "srcdsp_ddc_step"]:
+              "srcdsp_ddc_create", "srcdsp_ddc_step",
+              # the float instantiation of the decimator (and of FilterFir = its M = 1 case)
+              "srcdsp_decf_create", "srcdsp_decf_set_coeffs", "srcdsp_decf_step", "srcdsp_decf_reset",
+              "srcdsp_decf_set_left_shift"]:
         assert n in names
 
 
