@@ -189,6 +189,30 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
+def cpu_cfg1_variants(w):
+    """SURVEY.md 8(d) CPU baselines (A) and (B) on BASELINE configs[0] EXACTLY (one channel, NCO mix + decimate-by-8
+    63-tap FIR over 1 Mi samples, one step() call per stage): the unmodified reference built with its makefile's flags
+    (-std=gnu++11, no -O; makefile:18) and with -O2, one host thread each.  Reported, never a target."""
+    import oracle as O
+    c = O.corc()
+    n, M, nt = w["n"], w["M"], w["ntaps"]
+    x = c.synth(SEED, 0, 0, n, 2)[None]
+    taps = O.design_lowpass_taps(nt, M)
+    lo = np.array([-0.3217], np.float32)
+    out = {}
+    for name, opt, flags in (("makefile_build", "O0", "-std=gnu++11 (reference makefile:18, no -O)"), ("O2", "O2", "-std=gnu++11 -O2")):
+        r = O.ref(opt)
+        if r is None:
+            out[name] = {"value": None, "error": f"oracle/_ref ({opt}) is not built"}
+            continue
+        r.bench_bank(1, x, n, 1, M, taps, lo_freq=lo)  # warm-up
+        secs = [r.bench_bank(1, x, n, 1, M, taps, lo_freq=lo)[0] for _ in range(3)]
+        t = float(np.median(secs))
+        out[name] = {"value": (n // M) / t / 1e6, "unit": "Msamples/s", "cores": 1, "kind": "reference", "seconds": t,
+                     "sample": f"cfg1 exactly: 1 channel x {n} samples, mixer.step + decimator.step, g++ {flags}, median of 3"}
+    return out
+
+
 def cpu_reference_run(w, steps: int, warmup: int, cores: int, target_cpu_seconds: float = 20.0):
     """Times the unmodified reference (oracle/_ref) on a bounded sample of the workload."""
     import oracle as O
@@ -630,6 +654,11 @@ def main():
                     clocks=clocks, gpu_launches=int(launches), impl="ours")
         if ddc_extra is not None:
             line["ddc16"] = ddc_extra
+        if args.workload == "cfg1" and world == 1 and not args.no_cpu:
+            try:
+                line["cpu_baseline_variants"] = cpu_cfg1_variants(w)
+            except Exception as ex:
+                line["cpu_baseline_variants"] = {"error": str(ex)[:200]}
         print(json.dumps(line))
     if dist:
         dist.destroy_process_group()

@@ -31,3 +31,16 @@ def test_reference_arm_line():
     assert e == {"value": line["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["config"]["workload"].startswith("cfg2")
     assert line["vs_baseline"] is None and line["data"] == "synthetic"
+
+
+def test_cfg1_cpu_baseline_variants():
+    """SURVEY.md 8(d) CPU baselines (A) reference makefile flags and (B) -O2, one thread, on BASELINE configs[0] exactly."""
+    if O.ref() is None or O.ref("O0") is None:
+        pytest.skip("no compiled reference here")
+    sys.path.insert(0, ROOT)
+    import bench
+    v = bench.cpu_cfg1_variants(bench.WORKLOADS["cfg1"])
+    assert set(v) == {"makefile_build", "O2"}
+    for k in v.values():
+        assert k["cores"] == 1 and k["kind"] == "reference" and k["value"] > 0 and "cfg1 exactly" in k["sample"]
+    assert v["O2"]["value"] > v["makefile_build"]["value"]  # the optimised build is the faster one
