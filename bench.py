@@ -562,6 +562,9 @@ def main():
             "imad_note": "imad_frac = the same work counted as 2*taps INT32 multiply-adds per output against "
                          "148 SM x 64 IMAD/clk x sm_max_mhz: the ceiling of any CUDA-core kernel (SURVEY.md 8(d)); "
                          "the tcgen05 int8 kernel is not bound by it"}
+    # north_star quotes the roofline "against B200's ~8 TB/s": the same achieved rate against the nominal figure as well
+    roof["spec_peak"] = 8000.0
+    roof["frac_of_spec"] = roof["achieved"] / 8000.0
     if clocks and clocks.get("sm_max_mhz"):
         imad_peak = 148 * 64 * clocks["sm_max_mhz"] * 1e6
         macs = {"dec": 2 * nt, "ddc": 2 * nt + 4 * M, "up": 2 * nt / M, "mix": 4,
