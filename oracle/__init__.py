@@ -282,6 +282,8 @@ class _RefLib:
         L.ref_dec_destroy.argtypes = [vp]
         L.ref_dec_reset.argtypes = [vp]
         L.ref_dec_set_left_shift.argtypes = [vp, C.c_int]
+        if hasattr(L, "ref_dec_set_coeffs"):
+            L.ref_dec_set_coeffs.argtypes = [vp, C.c_int, _i32p, C.c_int]
         L.ref_dec_step.argtypes = [vp, _i16p, C.c_size_t, C.c_int, _i16p]
         fp = C.POINTER(C.c_float)
         L.ref_decf_create.restype = vp
@@ -415,6 +417,12 @@ class RefDecimator:
 
     def setLeftShiftBy2(self, s):
         self._l.ref_dec_set_left_shift(self._h, s)
+
+    def setCoeffs(self, taps):
+        """setCoeffs() on the live object (dsptl_dnsampling_filters.h:114-134; variant 1 only)."""
+        t = as_taps(taps)
+        if self._l.ref_dec_set_coeffs(self._h, self.M, _p32(t), t.size) != 0:
+            raise ValueError("reference would assert, or the obsolete header (no setCoeffs)")
 
     def step(self, x):
         x = np.ascontiguousarray(x, np.int16).reshape(-1, 2)
@@ -799,6 +807,85 @@ def np_up_step(taps, L: int, x: np.ndarray, history: np.ndarray | None = None,
 # ----------------------------------------------------------------------------------------------
 # tap design used by tests and bench: Hamming-windowed sinc, cutoff 1/ratio
 # ----------------------------------------------------------------------------------------------
+# ----------------------------------------------------------------------------------------------
+# live objects: setCoeffs() / setCoefficients() on an object that has already filtered samples
+# ----------------------------------------------------------------------------------------------
+class NpDecimatorLive:
+    """FilterDnsamplingFir as an object (dsptl_dnsampling_filters.h): `history` is the reference's member vector
+    (oldest sample first, :218-219); setCoeffs() RESIZES it -- the first min(old, new) entries stay where they are,
+    new entries are zero (:127) -- and resets leftShift (:133)."""
+
+    def __init__(self, M: int, taps):
+        self.M = M
+        self.history = np.zeros((0, 2), np.int16)
+        self.setCoeffs(taps)
+
+    def setCoeffs(self, taps):
+        t = as_taps(taps)
+        assert t.size % self.M == 0, "dsptl_dnsampling_filters.h:122"
+        h = np.zeros((t.size - 1, 2), np.int16)
+        keep = min(h.shape[0], self.history.shape[0])
+        h[:keep] = self.history[:keep]
+        self.taps, self.history, self.left_shift = t, h, 0
+
+    def reset(self):
+        self.history[:] = 0
+
+    def setLeftShiftBy2(self, s):
+        self.left_shift = s
+
+    def step(self, x):
+        out, self.history = np_dec_step(self.taps, self.M, x, self.history, self.left_shift)
+        return out
+
+
+class NpUpsamplerLive:
+    """FilterUpsamplingFir as an object (upsampling_filters.h): `buffer` is the reference's circular member vector,
+    `top` its insertion index (:163-194).  setCoefficients() resizes the RAW buffer and leaves `top` alone (:118), so
+    what the next step() sees as its history depends on where `top` stood."""
+
+    def __init__(self, L: int, taps):
+        self.L = L
+        self.buffer = np.zeros((0, 2), np.int16)
+        self.top = 0
+        self.setCoefficients(taps)
+
+    def setCoefficients(self, taps):
+        t = as_taps(taps)
+        assert t.size and t.size % self.L == 0, "upsampling_filters.h:110,113"
+        H = t.size // self.L
+        assert self.top < H, "the reference would write buffer[top] out of bounds"
+        b = np.zeros((H, 2), np.int16)
+        keep = min(H, self.buffer.shape[0])
+        b[:keep] = self.buffer[:keep]
+        self.taps, self.buffer = t, b
+        self.length = t.size
+        while self.length > 0 and t[self.length - 1] == 0:
+            self.length -= 1
+
+    def reset(self):
+        self.buffer[:] = 0
+        self.top = 0
+
+    def getLength(self):
+        return self.length
+
+    def getImpLength(self):
+        return self.taps.size
+
+    def step(self, x, flush=False, shift_mode=0):
+        x = np.asarray(x, np.int16).reshape(-1, 2)
+        H = self.buffer.shape[0]
+        # age order, oldest first, of the H - 1 samples in front of the next insertion: top+1 .. H-1, 0 .. top-1
+        order = [(self.top + 1 + k) % H for k in range(H - 1)]
+        out, _ = np_up_step(self.taps, self.L, x, self.buffer[order], flush, shift_mode)
+        fed = np.concatenate([x, np.zeros((self.length // self.L if flush else 0, 2), np.int16)])
+        for j in range(max(0, fed.shape[0] - H), fed.shape[0]):  # the last H insertions decide the buffer
+            self.buffer[(self.top + j) % H] = fed[j]
+        self.top = (self.top + fed.shape[0]) % H
+        return out
+
+
 def design_lowpass_taps(ntaps: int, ratio: int, target_sum: int = 49152, pad_to: int | None = None) -> np.ndarray:
     """int32 taps with 32768 <= sum|c| <= 65535 (coeffScaling = 15, no int32 overflow for any
     int16 input).  pad_to appends zero taps (output-identical, SURVEY.md section 0 trap (i))."""

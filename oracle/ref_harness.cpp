@@ -79,6 +79,7 @@ struct DecBase {
     virtual void step(const std::vector<cs16> &in, std::vector<cs16> &out) = 0;
     virtual void reset() = 0;
     virtual void setLeftShiftBy2(int) = 0;
+    virtual int setCoeffs(const std::vector<int32_t> &) { return -1; }  // the obsolete header has no setCoeffs()
 };
 template <class F>
 struct DecT : DecBase {
@@ -87,6 +88,16 @@ struct DecT : DecBase {
     void step(const std::vector<cs16> &in, std::vector<cs16> &out) { f.step(in, out); }
     void reset() { f.reset(); }
     void setLeftShiftBy2(int s) { f.setLeftShiftBy2(s); }
+};
+// dsptl_dnsampling_filters.h only: setCoeffs() on a live object (history.resize, :114-134)
+template <class F>
+struct DecTNew : DecT<F> {
+    explicit DecTNew(const std::vector<int32_t> &taps) : DecT<F>(taps) {}
+    int setCoeffs(const std::vector<int32_t> &t)
+    {
+        this->f.setCoeffs(t);
+        return 0;
+    }
 };
 
 struct UpBase {
@@ -121,7 +132,7 @@ DecBase *make_dec(int variant, int M, const std::vector<int32_t> &taps)
     case m:                                                                                      \
         if (variant == 0)                                                                        \
             return new DecT<ref_obsolete::dsptl::FilterDnsamplingFir<cs16, cs16, cs32, int32_t, m> >(taps); \
-        return new DecT<dsptl::FilterDnsamplingFir<cs16, cs16, cs32, int32_t, m> >(taps);
+        return new DecTNew<dsptl::FilterDnsamplingFir<cs16, cs16, cs32, int32_t, m> >(taps);
         RATIOS(X)
 #undef X
     }
@@ -221,6 +232,12 @@ void *ref_dec_create(int variant, int M, const int32_t *taps, int ntaps)
 void ref_dec_destroy(void *h) { delete static_cast<DecBase *>(h); }
 void ref_dec_reset(void *h) { static_cast<DecBase *>(h)->reset(); }
 void ref_dec_set_left_shift(void *h, int s) { static_cast<DecBase *>(h)->setLeftShiftBy2(s); }
+// setCoeffs() on a live object; -1: the object is the obsolete header's (no such member) or the call would assert
+int ref_dec_set_coeffs(void *h, int M, const int32_t *taps, int ntaps)
+{
+    if (ntaps < 1 || ntaps % M != 0) return -1;  // dsptl_dnsampling_filters.h:122 would assert
+    return static_cast<DecBase *>(h)->setCoeffs(std::vector<int32_t>(taps, taps + ntaps));
+}
 void ref_dec_step(void *h, const int16_t *in_iq, size_t n_in, int M, int16_t *out_iq)
 {
     std::vector<cs16> in = to_vec(in_iq, n_in), out(n_in / M);

@@ -47,6 +47,74 @@ int fail(int code, const char *fmt, ...)
 static std::atomic<uint64_t> g_launches{0};
 static inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
+// ---------------------------------------------------------------------------------------------
+// tuning knobs
+// ---------------------------------------------------------------------------------------------
+// Development sweeps override the measured defaults through SRCDSP_* environment variables.  A bank reads
+// them ONCE, when it is created (Bank::init) -- never on the step path -- and none of them changes a result:
+// the timing-experiment kernel instantiations that do (SRCDSP_TC_DEBUG, SRCDSP_UPT_DEBUG) exist only in
+// builds with -DSRCDSP_TIMING_EXPERIMENTS; the shipped library ignores both variables.
+struct Tuning {
+    int tma_stages = 0;    // SRCDSP_TMA_STAGES   byte-plane stages of dec_tma_kernel (0: groups + 1)
+    int tma_p2 = -1;       // SRCDSP_TMA_P2       force the 2-digit tile geometry on (1) / off (0)
+    int tma_grouped = -1;  // SRCDSP_TMA_GROUPED  force the grouped (1) / interleaved (0) master layout
+    int tma_w = 0;         // SRCDSP_TMA_W        converter warps per group (4 / 8)
+    int tma_groups = 0;    // SRCDSP_TMA_GROUPS   converter groups
+    int tma_raw = 0;       // SRCDSP_TMA_RAW      cap on the raw ring
+    int no_tma = 0;        // SRCDSP_NO_TMA       register-staged dec_tc_kernel instead of dec_tma_kernel
+    int epi_sleep = -1;    // SRCDSP_EPI_SLEEP    ns between epilogue polls
+    int conv_sleep = -1;   // SRCDSP_CONV_SLEEP   ns between converter polls of the raw ring
+    int mma_sleep = -1;    // SRCDSP_MMA_SLEEP    ns between MMA-warp polls of the byte-plane ring
+    int pf_dist = -1;      // SRCDSP_PF_DIST      dec_tc_kernel's L2 prefetch distance
+    int verbose = 0;       // SRCDSP_TMA_VERBOSE  print the chosen shared-memory plan
+    int seq_period = -1;   // SRCDSP_SEQ_PERIOD   0: always the full-table oscillator sequence
+    int up_tc = -1;        // SRCDSP_UP_TC        tcgen05 interpolator on (1) / off (0)
+    int up_tc_form = 0;    // SRCDSP_UP_TC_FORM   2: operand-swapped form
+    int up_generic = 0;    // SRCDSP_UP_GENERIC
+    int corr_generic = 0;  // SRCDSP_CORR_GENERIC
+    int decf_pairs = 0;    // SRCDSP_DECF_PAIRS   1 / 2
+    int decf_tile = 0;     // SRCDSP_DECF_TILE
+    int decf_ct = -1;      // SRCDSP_DECF_CT
+    int decf_blocks = -1;  // SRCDSP_DECF_BLOCKS
+    int decf_prefetch = -1;  // SRCDSP_DECF_PREFETCH
+    int tc_debug = 0;      // SRCDSP_TC_DEBUG / SRCDSP_UPT_DEBUG: timing experiments, -DSRCDSP_TIMING_EXPERIMENTS builds only
+    int upt_debug = 0;
+};
+static Tuning tuning_from_env()
+{
+    Tuning v;
+    auto get = [](const char *name, int &dst) {
+        if (const char *e = getenv(name)) dst = atoi(e);
+    };
+    get("SRCDSP_TMA_STAGES", v.tma_stages);
+    get("SRCDSP_TMA_P2", v.tma_p2);
+    get("SRCDSP_TMA_GROUPED", v.tma_grouped);
+    get("SRCDSP_TMA_W", v.tma_w);
+    get("SRCDSP_TMA_GROUPS", v.tma_groups);
+    get("SRCDSP_TMA_RAW", v.tma_raw);
+    v.no_tma = getenv("SRCDSP_NO_TMA") != nullptr;
+    get("SRCDSP_EPI_SLEEP", v.epi_sleep);
+    get("SRCDSP_CONV_SLEEP", v.conv_sleep);
+    get("SRCDSP_MMA_SLEEP", v.mma_sleep);
+    get("SRCDSP_PF_DIST", v.pf_dist);
+    v.verbose = getenv("SRCDSP_TMA_VERBOSE") != nullptr;
+    get("SRCDSP_SEQ_PERIOD", v.seq_period);
+    get("SRCDSP_UP_TC", v.up_tc);
+    get("SRCDSP_UP_TC_FORM", v.up_tc_form);
+    v.up_generic = getenv("SRCDSP_UP_GENERIC") != nullptr;
+    v.corr_generic = getenv("SRCDSP_CORR_GENERIC") != nullptr;
+    get("SRCDSP_DECF_PAIRS", v.decf_pairs);
+    get("SRCDSP_DECF_TILE", v.decf_tile);
+    get("SRCDSP_DECF_CT", v.decf_ct);
+    get("SRCDSP_DECF_BLOCKS", v.decf_blocks);
+    get("SRCDSP_DECF_PREFETCH", v.decf_prefetch);
+#ifdef SRCDSP_TIMING_EXPERIMENTS
+    get("SRCDSP_TC_DEBUG", v.tc_debug);
+    get("SRCDSP_UPT_DEBUG", v.upt_debug);
+#endif
+    return v;
+}
+
 #define SRCDSP_LAUNCH_CHECK()                                                                     \
     do {                                                                                          \
         cudaError_t _e = cudaGetLastError();                                                      \
@@ -108,6 +176,7 @@ constexpr size_t STAGE_TARGET_BYTES = 48u << 20;  // per chunk, larger of in/out
 struct Bank {
     int device = 0;
     int C = 0;
+    Tuning tune;  // environment overrides, captured at creation
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     // host staging
@@ -122,6 +191,7 @@ struct Bank {
         if (channels < 1) return fail(SRCDSP_E_INVALID, "channels must be >= 1 (got %d)", channels);
         device = dev;
         C = channels;
+        tune = tuning_from_env();
         DeviceGuard g(device);
         SRCDSP_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         own_stream = true;
@@ -303,6 +373,7 @@ struct MixerBank : Bank {
     bool dirty = true;
     std::vector<int> h_phi, h_freq;
     std::vector<float> h_nominal;
+    unsigned seq_period = 0;  // common period of the channels' oscillator sequences (power-of-two tables), see upload_if_dirty
 
     PhaseMod pm() const
     {
@@ -354,6 +425,19 @@ struct MixerBank : Bank {
     int upload_if_dirty()
     {
         if (!dirty) return SRCDSP_OK;
+        // The oscillator of a channel, T[(phi0 + n * freq) mod N] in time order, has period N / gcd(freq, N).  For a
+        // power-of-two table every such period is a power of two, so the largest one is a period of all channels: the
+        // fused mixer keeps that many sequence entries in shared memory instead of N (e.g. 512 for frequencies on a
+        // grid of 8 table steps) and gives the rest to the sample rings.
+        seq_period = n_table;
+        if ((n_table & (n_table - 1)) == 0) {
+            unsigned g = n_table;  // gcd of all frequencies and N
+            for (int c = 0; c < C; ++c) {
+                const unsigned f = (unsigned)h_freq[c] & (n_table - 1);
+                if (f) g = std::min(g, f & (~f + 1u));  // lowest set bit = gcd(f, 2^k)
+            }
+            seq_period = std::max(16u, n_table / g);  // 128 bytes at least: the sample rings behind it stay 128-byte aligned
+        }
         // pageable sources: the driver stages them before returning, so the vectors may change
         SRCDSP_CUDA(cudaMemcpyAsync(d_phi[cur], h_phi.data(), C * sizeof(int), cudaMemcpyHostToDevice, stream));
         SRCDSP_CUDA(cudaMemcpyAsync(d_freq, h_freq.data(), C * sizeof(int), cudaMemcpyHostToDevice, stream));
@@ -434,6 +518,11 @@ struct DecBank : Bank {
     // register-staged variant / TMA variant / TMA variant with the fused mixer (each with its own master layout)
     TcParams tc{}, tc_tma{}, tc_tma_mix{};
     bool tma_ok = false, tma_mix_ok = false;
+    std::vector<std::vector<int8_t>> tc_dig;  // signed base-256 digits of the taps
+    int tc_P = 1;                             // digits per tap
+    bool tc_want_p2 = false;
+    int tc_mix_table = 32768;                 // shared-memory bytes of the oscillator sequence the mixer variant was planned for
+    int build_variant(int variant, bool p2, int mix_table);
     uint8_t *d_master = nullptr, *d_master_tma = nullptr, *d_master_tma_mix = nullptr;
     size_t tc_fixed_tma = 0, tc_fixed_tma_mix = 0;
     int *d_error = nullptr;  // wait-cycle counters of the timing variants (device)
@@ -467,8 +556,7 @@ struct DecBank : Bank {
         // byte-plane stages: one per converter group being filled + 1 for the MMAs; the rest of the
         // shared memory is the raw ring = the bytes in flight from HBM (at least 4 stages wanted)
         int ns = groups + 1;
-        if (const char *e = getenv("SRCDSP_TMA_STAGES"))
-            if (atoi(e) > 0) ns = std::max(2, std::min(atoi(e), TC_MAX_STAGES));
+        if (tune.tma_stages > 0) ns = std::max(2, std::min(tune.tma_stages, TC_MAX_STAGES));
         while (ns > 2 && fixed + (size_t)table_bytes + ns * split + 4 * rawb > avail) --ns;
         int nr = (int)((avail - fixed - (size_t)table_bytes - ns * split) / rawb);
         if (nr > 8) nr = 8;  // more bytes in flight than ~128 KB per SM lowers the HBM rate (tools/tmabench.cu)
@@ -585,6 +673,170 @@ struct DecBank : Bank {
     }
 };
 
+// One layout variant of the tensor-core decimator (see prepare_tc): 0 = dec_tc_kernel, 1 = dec_tma_kernel,
+// 2 = dec_tma_kernel with the fused mixer, whose shared-memory plan depends on the oscillator sequence's size.
+int DecBank::build_variant(int variant, bool p2, int mix_table)
+{
+    const std::vector<std::vector<int8_t>> &dig = tc_dig;
+    const int P = tc_P;
+    uint8_t **pimg = variant == 2 ? &d_master_tma_mix : variant ? &d_master_tma : &d_master;
+    if (*pimg) {
+        DeviceGuard g0(device);
+        cudaFree(*pimg);
+        *pimg = nullptr;
+    }
+    if (variant == 2) tc_mix_table = mix_table;
+    TcParams &T = variant == 2 ? tc_tma_mix : variant ? tc_tma : tc;
+    uint8_t *&d_img = variant == 2 ? d_master_tma_mix : variant ? d_master_tma : d_master;
+    size_t &fixed = variant == 2 ? tc_fixed_tma_mix : variant ? tc_fixed_tma : tc_fixed;
+    bool &ok = variant == 2 ? tma_mix_ok : variant ? tma_ok : tc_ok;
+    ok = false;
+    const int nrb = p2 ? 64 : TC_NRB, bout = p2 ? 64 : TC_BOUT, S = p2 ? 2 : 4;
+    const int G = bout * M, ksteps = G / 32;
+    const int J = 1 + (ntaps - 1 + G - 1) / G;
+    const int OFF = bout;  // a = (32 * kc) / M < bout
+    const int front_pad = 2 * (4 * ((J - 1 + 3) / 4) - (J - 1));
+    const int rbp = (front_pad + 2 * (nrb + J - 1)) | 1;  // odd: conflict-free byte-plane stores
+    T = TcParams{};
+    T.rbp = rbp, T.J = J, T.nrb = nrb;  // the layout planners need these
+    std::vector<int> copy_of_kc(ksteps);
+    std::vector<std::pair<int, int>> copies;  // (s, r)
+    int grouped = 1, a_rows = 0;
+    size_t master_bytes = 0, image_bytes = 0;
+    for (; grouped >= (p2 ? 1 : 0); --grouped) {
+        copies.clear();
+        for (int kc = 0; kc < ksteps; ++kc) {
+            const int a = (32 * kc) / M, r = (32 * kc) % M;
+            const std::pair<int, int> key(grouped ? a % 8 : 0, r);
+            int idx = -1;
+            for (size_t i = 0; i < copies.size(); ++i)
+                if (copies[i] == key) idx = (int)i;
+            if (idx < 0) {
+                idx = (int)copies.size();
+                copies.push_back(key);
+            }
+            copy_of_kc[kc] = idx;
+        }
+        // rows: guard + S * OFF (shift range) + 128 per lag + slack
+        a_rows = grouped ? 128 * J + 8 * S + S * OFF + 64 : 128 * J + 136;
+        image_bytes = copies.size() * (size_t)a_rows * 32;
+        // the MMA plan behind the image: one 8-byte header per K-step, then one 16-byte entry per (K-step, lag) + 1 pad
+        master_bytes = image_bytes + (((size_t)ksteps * 8 + 15) & ~(size_t)15) + ((size_t)ksteps * J + 1) * 16;
+        fixed = ((master_bytes + 127) & ~(size_t)127) + 512;  // + mbarriers (at most 416 B)
+        if (variant) {
+            // grouped (shuffle-free epilogue, but several master copies) when enough raw stages remain: 4 for the
+            // plain decimator; 5 next to the fused mixer's oscillator sequence (32 KB for N = 4096), whose
+            // converters are slower and need the deeper ring more than the cheaper epilogue (sweeps on ddc16 / ddc8:
+            // /16 is faster interleaved with 6 raw stages, /8 grouped with 5).  Otherwise the interleaved layout,
+            // when it fits at all.
+            int nr = 0;
+            const int table = variant == 2 ? mix_table : 0, want = variant == 2 ? 5 : 4;
+            if (tune.tma_grouped >= 0) {  // tuning override
+                if (((tune.tma_grouped != 0) || p2) == (grouped != 0) && tma_layout(T, fixed, table, 1, nullptr, nullptr, nullptr) == SRCDSP_OK) break;
+                continue;
+            }
+            if (tma_layout(T, fixed, table, variant == 2 ? 3 : 2, &nr, nullptr, nullptr) == SRCDSP_OK && (nr >= want || p2)) break;
+            if (!grouped && tma_layout(T, fixed, table, 1, nullptr, nullptr, nullptr) == SRCDSP_OK) break;
+        } else {
+            tc.rbp = rbp;  // tc_layout reads it
+            if (tc_layout(16384, nullptr, nullptr) == SRCDSP_OK) break;  // leave room for a 4096-entry sine table
+            if (!grouped && tc_layout(0, nullptr, nullptr) == SRCDSP_OK) break;
+        }
+    }
+    if (grouped < (p2 ? 1 : 0)) {
+        if (!variant) tc_why = "Toeplitz master + stages exceed the shared memory of one SM";
+        return SRCDSP_OK;
+    }
+    std::vector<uint8_t> img(master_bytes, 0);
+    const int guard = grouped ? 8 * S : 4;
+    for (size_t ci = 0; ci < copies.size(); ++ci) {
+        uint8_t *base = img.data() + ci * (size_t)a_rows * 32;
+        const int s8 = copies[ci].first, r = copies[ci].second;
+        for (int row = guard; row < a_rows; ++row) {
+            int v, w;
+            if (grouped) {
+                const int q = row - guard;
+                v = 8 * (q / (8 * S)) + (q % 8);
+                w = (q % (8 * S)) / 8;
+            } else {
+                v = (row - guard) / 4;
+                w = (row - guard) % 4;
+            }
+            if (w >= P) continue;
+            const int u = v - s8 - OFF;
+            for (int t = 0; t < 32; ++t) {
+                const long long k = (long long)M * u - t - r;
+                if (k < 0 || k >= ntaps) continue;
+                // SWIZZLE_NONE K-major image: [kc = t / 16][row][t % 16]
+                base[(size_t)(t / 16) * a_rows * 16 + (size_t)row * 16 + (t % 16)] = (uint8_t)dig[w][k];
+            }
+        }
+    }
+    // per K-step: master row of (b = 0, slot 0, lag 0), v0 = OFF - a + s (a multiple of 8 when grouped), and the lags
+    // whose taps reach this K-step's samples
+    auto a_row_of = [&](int a) { return grouped ? S * (OFF - 8 * (a / 8)) + guard : 4 * (OFF - a) + 4; };
+    auto lag_active = [&](int a, int r, int j) {
+        const long long kmax = (long long)M * (bout - 1 + bout * j - a) - r;
+        const long long kmin = (long long)M * (bout * j - a) - r - 31;
+        return kmax >= 0 && kmin <= ntaps - 1;
+    };
+    // MMA plan (tc_mma_role): operand addresses >> 4, A relative to the master, B relative to the stage
+    const int plan_hdr_off = (int)image_bytes;
+    const int plan_ent_off = plan_hdr_off + (int)((((size_t)ksteps * 8 + 15) & ~(size_t)15));
+    {
+        uint32_t *hdr = reinterpret_cast<uint32_t *>(img.data() + plan_hdr_off);
+        uint32_t *ent = reinterpret_cast<uint32_t *>(img.data() + plan_ent_off);
+        // hi byte plane: one weight slot up = 8 rows (grouped) / 1 row (interleaved) back; p2: same rows, own columns
+        const int hi_shift = p2 ? 0 : grouped ? 128 : 16;
+        uint32_t n_ent = 0;
+        for (int kc = 0; kc < ksteps; ++kc) {
+            const int a = (32 * kc) / M, r = (32 * kc) % M;
+            const int res_off = copy_of_kc[kc] * a_rows * 32;
+            hdr[2 * kc] = n_ent;
+            uint32_t cnt = 0;
+            for (int j = 0; j < J; ++j) {
+                if (!lag_active(a, r, j)) continue;
+                const int a_addr = res_off + (a_row_of(a) + 128 * j) * 16;
+                const int b_addr = (front_pad + 2 * (J - 1 - j)) * 16;
+                ent[4 * n_ent + 0] = (uint32_t)a_addr >> 4;
+                ent[4 * n_ent + 1] = (uint32_t)(a_addr - hi_shift) >> 4;
+                ent[4 * n_ent + 2] = (uint32_t)b_addr >> 4;
+                ent[4 * n_ent + 3] = (uint32_t)(b_addr + 2 * rbp * 16) >> 4;
+                ++n_ent;
+                ++cnt;
+            }
+            hdr[2 * kc + 1] = cnt;
+        }
+    }
+    DeviceGuard g(device);
+    SRCDSP_CUDA(cudaMalloc(&d_img, master_bytes));
+    SRCDSP_CUDA(cudaMemcpy(d_img, img.data(), master_bytes, cudaMemcpyHostToDevice));
+    T.M = M;
+    T.G = G;
+    T.p2 = p2;
+    T.ksteps = ksteps;
+    T.master = d_img;
+    T.master_bytes = (int)master_bytes;
+    T.plan_hdr_off = plan_hdr_off;
+    T.plan_ent_off = plan_ent_off;
+    T.a_rows = a_rows;
+    T.front_pad = front_pad;
+    T.grouped = grouped;
+    T.error_flag = d_diag;
+    T.counters = d_error;
+    for (int kc = 0; kc < ksteps && kc < TC_MAX_KSTEPS; ++kc) {
+        const int a = (32 * kc) / M, r = (32 * kc) % M;
+        TcKstep &ks = T.ks[kc];
+        ks.a_row = a_row_of(a);
+        ks.res_off = copy_of_kc[kc] * a_rows * 32;
+        ks.jmask = 0;
+        for (int j = 0; j < J; ++j)
+            if (lag_active(a, r, j)) ks.jmask |= 1u << j;
+    }
+    ok = true;
+    return SRCDSP_OK;
+}
+
 // Builds the resident Toeplitz "master" operand and the per-K-step table of the tensor-core
 // kernel (see kernels_dec_tc.cuh for the layout).  Sets tc_ok = false (with a reason) when the
 // taps / ratio do not fit it; the IMAD kernel then handles every case.
@@ -600,7 +852,8 @@ int DecBank::prepare_tc()
     if (M > TC_MAX_KSTEPS) { tc_why = "M > 64"; return SRCDSP_OK; }
     // signed base-256 digits of every tap: c = sum_pl 256^pl * d_pl, d_pl in [-128, 127]
     int P = 1;
-    std::vector<std::vector<int8_t>> dig(4, std::vector<int8_t>(ntaps, 0));
+    std::vector<std::vector<int8_t>> &dig = tc_dig;
+    dig.assign(4, std::vector<int8_t>(ntaps, 0));
     for (int k = 0; k < ntaps; ++k) {
         long long c = taps[k];
         for (int pl = 0; pl < 4; ++pl) {
@@ -628,7 +881,9 @@ int DecBank::prepare_tc()
     // there: /4 with 1023 taps).  Short filters lose more to the doubled K-step count than they gain, so it is
     // used from 4 lags on (SRCDSP_TMA_P2 = 0 / 1 overrides).
     bool want_p2 = P <= 2 && 2 * M <= TC_MAX_KSTEPS && 1 + (ntaps - 1 + 32 * M - 1) / (32 * M) >= 4;
-    if (const char *e = getenv("SRCDSP_TMA_P2")) want_p2 = atoi(e) != 0 && P <= 2 && 2 * M <= TC_MAX_KSTEPS;
+    if (tune.tma_p2 >= 0) want_p2 = tune.tma_p2 != 0 && P <= 2 && 2 * M <= TC_MAX_KSTEPS;
+    tc_P = P;
+    tc_want_p2 = want_p2;
 
     // One resident "master" Toeplitz image per distinct tap alignment.  S = weight slots per output (4, or the 2
     // digit slots in p2 mode).  Preferred layout ("grouped"): row = 8*S*(v>>3) + 8*w + (v&7) (+ 8*S guard rows), the
@@ -638,162 +893,13 @@ int DecBank::prepare_tc()
     // The kernels have different shared-memory budgets (the TMA variant needs few byte-plane stages, the
     // register-staged one at least TC_OWNERS + 1), so each gets the best master layout that fits ITS budget:
     // variant 0 = dec_tc_kernel (tc), 1 = dec_tma_kernel (tc_tma), 2 = dec_tma_kernel with the fused mixer (tc_tma_mix).
-    auto build_variant = [&](int variant, bool p2) -> int {
-        TcParams &T = variant == 2 ? tc_tma_mix : variant ? tc_tma : tc;
-        uint8_t *&d_img = variant == 2 ? d_master_tma_mix : variant ? d_master_tma : d_master;
-        size_t &fixed = variant == 2 ? tc_fixed_tma_mix : variant ? tc_fixed_tma : tc_fixed;
-        bool &ok = variant == 2 ? tma_mix_ok : variant ? tma_ok : tc_ok;
-        ok = false;
-        const int nrb = p2 ? 64 : TC_NRB, bout = p2 ? 64 : TC_BOUT, S = p2 ? 2 : 4;
-        const int G = bout * M, ksteps = G / 32;
-        const int J = 1 + (ntaps - 1 + G - 1) / G;
-        const int OFF = bout;  // a = (32 * kc) / M < bout
-        const int front_pad = 2 * (4 * ((J - 1 + 3) / 4) - (J - 1));
-        const int rbp = (front_pad + 2 * (nrb + J - 1)) | 1;  // odd: conflict-free byte-plane stores
-        T = TcParams{};
-        T.rbp = rbp, T.J = J, T.nrb = nrb;  // the layout planners need these
-        std::vector<int> copy_of_kc(ksteps);
-        std::vector<std::pair<int, int>> copies;  // (s, r)
-        int grouped = 1, a_rows = 0;
-        size_t master_bytes = 0, image_bytes = 0;
-        for (; grouped >= (p2 ? 1 : 0); --grouped) {
-            copies.clear();
-            for (int kc = 0; kc < ksteps; ++kc) {
-                const int a = (32 * kc) / M, r = (32 * kc) % M;
-                const std::pair<int, int> key(grouped ? a % 8 : 0, r);
-                int idx = -1;
-                for (size_t i = 0; i < copies.size(); ++i)
-                    if (copies[i] == key) idx = (int)i;
-                if (idx < 0) {
-                    idx = (int)copies.size();
-                    copies.push_back(key);
-                }
-                copy_of_kc[kc] = idx;
-            }
-            // rows: guard + S * OFF (shift range) + 128 per lag + slack
-            a_rows = grouped ? 128 * J + 8 * S + S * OFF + 64 : 128 * J + 136;
-            image_bytes = copies.size() * (size_t)a_rows * 32;
-            // the MMA plan behind the image: one 8-byte header per K-step, then one 16-byte entry per (K-step, lag) + 1 pad
-            master_bytes = image_bytes + (((size_t)ksteps * 8 + 15) & ~(size_t)15) + ((size_t)ksteps * J + 1) * 16;
-            fixed = ((master_bytes + 127) & ~(size_t)127) + 512;  // + mbarriers (at most 416 B)
-            if (variant) {
-                // grouped (shuffle-free epilogue, but several master copies) when enough raw stages remain: 4 for the
-                // plain decimator; 5 next to the fused mixer's oscillator sequence (32 KB for N = 4096), whose
-                // converters are slower and need the deeper ring more than the cheaper epilogue (sweeps on ddc16 / ddc8:
-                // /16 is faster interleaved with 6 raw stages, /8 grouped with 5).  Otherwise the interleaved layout,
-                // when it fits at all.
-                int nr = 0;
-                const int table = variant == 2 ? 32768 : 0, want = variant == 2 ? 5 : 4;
-                if (const char *e = getenv("SRCDSP_TMA_GROUPED")) {  // tuning override
-                    if (((atoi(e) != 0) || p2) == (grouped != 0) && tma_layout(T, fixed, table, 1, nullptr, nullptr, nullptr) == SRCDSP_OK) break;
-                    continue;
-                }
-                if (tma_layout(T, fixed, table, variant == 2 ? 3 : 2, &nr, nullptr, nullptr) == SRCDSP_OK && (nr >= want || p2)) break;
-                if (!grouped && tma_layout(T, fixed, table, 1, nullptr, nullptr, nullptr) == SRCDSP_OK) break;
-            } else {
-                tc.rbp = rbp;  // tc_layout reads it
-                if (tc_layout(16384, nullptr, nullptr) == SRCDSP_OK) break;  // leave room for a 4096-entry sine table
-                if (!grouped && tc_layout(0, nullptr, nullptr) == SRCDSP_OK) break;
-            }
-        }
-        if (grouped < (p2 ? 1 : 0)) {
-            if (!variant) tc_why = "Toeplitz master + stages exceed the shared memory of one SM";
-            return SRCDSP_OK;
-        }
-        std::vector<uint8_t> img(master_bytes, 0);
-        const int guard = grouped ? 8 * S : 4;
-        for (size_t ci = 0; ci < copies.size(); ++ci) {
-            uint8_t *base = img.data() + ci * (size_t)a_rows * 32;
-            const int s8 = copies[ci].first, r = copies[ci].second;
-            for (int row = guard; row < a_rows; ++row) {
-                int v, w;
-                if (grouped) {
-                    const int q = row - guard;
-                    v = 8 * (q / (8 * S)) + (q % 8);
-                    w = (q % (8 * S)) / 8;
-                } else {
-                    v = (row - guard) / 4;
-                    w = (row - guard) % 4;
-                }
-                if (w >= P) continue;
-                const int u = v - s8 - OFF;
-                for (int t = 0; t < 32; ++t) {
-                    const long long k = (long long)M * u - t - r;
-                    if (k < 0 || k >= ntaps) continue;
-                    // SWIZZLE_NONE K-major image: [kc = t / 16][row][t % 16]
-                    base[(size_t)(t / 16) * a_rows * 16 + (size_t)row * 16 + (t % 16)] = (uint8_t)dig[w][k];
-                }
-            }
-        }
-        // per K-step: master row of (b = 0, slot 0, lag 0), v0 = OFF - a + s (a multiple of 8 when grouped), and the lags
-        // whose taps reach this K-step's samples
-        auto a_row_of = [&](int a) { return grouped ? S * (OFF - 8 * (a / 8)) + guard : 4 * (OFF - a) + 4; };
-        auto lag_active = [&](int a, int r, int j) {
-            const long long kmax = (long long)M * (bout - 1 + bout * j - a) - r;
-            const long long kmin = (long long)M * (bout * j - a) - r - 31;
-            return kmax >= 0 && kmin <= ntaps - 1;
-        };
-        // MMA plan (tc_mma_role): operand addresses >> 4, A relative to the master, B relative to the stage
-        const int plan_hdr_off = (int)image_bytes;
-        const int plan_ent_off = plan_hdr_off + (int)((((size_t)ksteps * 8 + 15) & ~(size_t)15));
-        {
-            uint32_t *hdr = reinterpret_cast<uint32_t *>(img.data() + plan_hdr_off);
-            uint32_t *ent = reinterpret_cast<uint32_t *>(img.data() + plan_ent_off);
-            // hi byte plane: one weight slot up = 8 rows (grouped) / 1 row (interleaved) back; p2: same rows, own columns
-            const int hi_shift = p2 ? 0 : grouped ? 128 : 16;
-            uint32_t n_ent = 0;
-            for (int kc = 0; kc < ksteps; ++kc) {
-                const int a = (32 * kc) / M, r = (32 * kc) % M;
-                const int res_off = copy_of_kc[kc] * a_rows * 32;
-                hdr[2 * kc] = n_ent;
-                uint32_t cnt = 0;
-                for (int j = 0; j < J; ++j) {
-                    if (!lag_active(a, r, j)) continue;
-                    const int a_addr = res_off + (a_row_of(a) + 128 * j) * 16;
-                    const int b_addr = (front_pad + 2 * (J - 1 - j)) * 16;
-                    ent[4 * n_ent + 0] = (uint32_t)a_addr >> 4;
-                    ent[4 * n_ent + 1] = (uint32_t)(a_addr - hi_shift) >> 4;
-                    ent[4 * n_ent + 2] = (uint32_t)b_addr >> 4;
-                    ent[4 * n_ent + 3] = (uint32_t)(b_addr + 2 * rbp * 16) >> 4;
-                    ++n_ent;
-                    ++cnt;
-                }
-                hdr[2 * kc + 1] = cnt;
-            }
-        }
-        DeviceGuard g(device);
-        SRCDSP_CUDA(cudaMalloc(&d_img, master_bytes));
-        SRCDSP_CUDA(cudaMemcpy(d_img, img.data(), master_bytes, cudaMemcpyHostToDevice));
-        T.M = M;
-        T.G = G;
-        T.p2 = p2;
-        T.ksteps = ksteps;
-        T.master = d_img;
-        T.master_bytes = (int)master_bytes;
-        T.plan_hdr_off = plan_hdr_off;
-        T.plan_ent_off = plan_ent_off;
-        T.a_rows = a_rows;
-        T.front_pad = front_pad;
-        T.grouped = grouped;
-        T.error_flag = d_diag;
-        T.counters = d_error;
-        for (int kc = 0; kc < ksteps && kc < TC_MAX_KSTEPS; ++kc) {
-            const int a = (32 * kc) / M, r = (32 * kc) % M;
-            TcKstep &ks = T.ks[kc];
-            ks.a_row = a_row_of(a);
-            ks.res_off = copy_of_kc[kc] * a_rows * 32;
-            ks.jmask = 0;
-            for (int j = 0; j < J; ++j)
-                if (lag_active(a, r, j)) ks.jmask |= 1u << j;
-        }
-        ok = true;
-        return SRCDSP_OK;
-    };
-    SRCDSP_TRY(build_variant(0, false));
+    SRCDSP_TRY(build_variant(0, false, 0));
     for (int variant = 1; variant <= 2; ++variant) {
-        // p2 first where it pays; the 4-slot geometry when its master does not fit next to the rings
-        if (want_p2) SRCDSP_TRY(build_variant(variant, true));
-        if (!(variant == 2 ? tma_mix_ok : tma_ok)) SRCDSP_TRY(build_variant(variant, false));
+        // p2 first where it pays; the 4-slot geometry when its master does not fit next to the rings.  The mixer
+        // variant is planned for a full 4096-entry oscillator sequence here and re-planned by step_device() when the
+        // mixer's frequencies allow a shorter one.
+        if (want_p2) SRCDSP_TRY(build_variant(variant, true, 32768));
+        if (!(variant == 2 ? tma_mix_ok : tma_ok)) SRCDSP_TRY(build_variant(variant, false, 32768));
     }
     if (!tc_ok) return SRCDSP_OK;
     cudaDeviceProp prop;
@@ -802,18 +908,22 @@ int DecBank::prepare_tc()
     const int max_smem = 226 * 1024;  // 227 KB minus the kernel's static shared memory
     SRCDSP_CUDA(cudaFuncSetAttribute(dec_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     SRCDSP_CUDA(cudaFuncSetAttribute(dec_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+#ifdef SRCDSP_TIMING_EXPERIMENTS
     SRCDSP_CUDA(cudaFuncSetAttribute(dec_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     SRCDSP_CUDA(cudaFuncSetAttribute(dec_tc_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     SRCDSP_CUDA(cudaFuncSetAttribute(dec_tc_kernel<10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     SRCDSP_CUDA(cudaFuncSetAttribute(dec_tc_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+#endif
 #define SRCDSP_TMA_ATTR(D, MX)                                                                                             \
     SRCDSP_CUDA(cudaFuncSetAttribute(dec_tma_kernel<D, MX, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));    \
     SRCDSP_CUDA(cudaFuncSetAttribute(dec_tma_kernel<D, MX, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))
     SRCDSP_TMA_ATTR(0, false);
     SRCDSP_TMA_ATTR(0, true);
+#ifdef SRCDSP_TIMING_EXPERIMENTS
     SRCDSP_TMA_ATTR(2, false);
     SRCDSP_TMA_ATTR(16, false);
     SRCDSP_TMA_ATTR(16, true);
+#endif
 #undef SRCDSP_TMA_ATTR
     tc_why = "";
     return SRCDSP_OK;
@@ -899,34 +1009,6 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
         const PhaseMod pm = mixer->pm();
         if (!pm.mask) use_tc = false, why = "fused mixer needs a power-of-two sine table";
     }
-    // TMA-fed variant: needs 16-byte aligned rows and at least one whole row-block in the tensor (row-blocks of
-    // G samples: 32 * M, or 64 * M in p2 mode -- the variants have their own tile geometry)
-    const int tbl_bytes = mixer ? (int)mixer->n_table * 4 : 0;      // LDG variant: copy of the packed (cos, sin) table
-    const int tma_tbl_bytes = mixer ? (int)mixer->n_table * 8 : 0;  // TMA variant: oscillator sequence, two digit words per sample
-    const TcParams &Ttma = mixer ? tc_tma_mix : tc_tma;
-    const bool tma_built = mixer ? tma_mix_ok : tma_ok;
-    const long long rows_tma = tma_built ? (long long)(n_in / (size_t)Ttma.G) : 0;
-    int tma_raw = 0, tma_stages = 0;
-    size_t tma_smem = 0;
-    const bool can_map = use_tc && P.vec_in && tensor_map_encoder() != nullptr;
-    // converter warps: groups of W warps, one K-step per group at a time
-    // defaults from sweeps on cfg2 / ddc16 (256 ch x 16 Mi, /16, 255 taps): W = 4; plain decimator 2 groups + 3 byte-plane
-    // stages (the raw ring gets the rest), fused mixer 3 groups + 4 stages (more ALU work per K-step)
-    int tma_w = 4, tma_groups = mixer ? 3 : 2;
-    if (const char *e = getenv("SRCDSP_TMA_W")) tma_w = atoi(e) == 8 ? 8 : 4;
-    if (tma_built && Ttma.p2) tma_w = 4;  // 16 main row groups per K-step: 4 per warp
-    if (const char *e = getenv("SRCDSP_TMA_GROUPS")) tma_groups = std::max(1, atoi(e));
-    tma_groups = std::min(tma_groups, (mixer ? TMA_MAX_CONV_MIX : TMA_MAX_CONV) / tma_w);
-    bool use_tma = can_map && tma_built && rows_tma >= 1 && rows_tma < 0x7fffffffll && kernel_kind != 3 && !getenv("SRCDSP_NO_TMA") &&
-                   tma_layout(Ttma, mixer ? tc_fixed_tma_mix : tc_fixed_tma, tma_tbl_bytes, tma_groups, &tma_raw, &tma_stages,
-                              &tma_smem) == SRCDSP_OK;
-    const long long rows_full = use_tma ? rows_tma : (long long)(n_in / (size_t)(32 * M));
-    const bool have_map = can_map && rows_full >= 1 && rows_full < 0x7fffffffll;
-    if (use_tc && !use_tma && tc_layout(tbl_bytes, &tc_stages, &tc_smem) != SRCDSP_OK)
-        use_tc = false, why = "sine table + Toeplitz master + stages exceed 227 KB of shared memory";
-    if (kernel_kind >= 2 && !use_tc)
-        return fail(SRCDSP_E_STATE, "tcgen05 kernel forced but not applicable: %s", tc_ok ? why : tc_why);
-
     if (mixer) {
         if (mixer->C != C || mixer->device != device)
             return fail(SRCDSP_E_INVALID, "mixer and decimator banks must have the same channels and device");
@@ -941,6 +1023,44 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
         P.freq = mixer->d_freq;
         P.pm = mixer->pm();
     }
+    // TMA-fed variant: needs 16-byte aligned rows and at least one whole row-block in the tensor (row-blocks of
+    // G samples: 32 * M, or 64 * M in p2 mode -- the variants have their own tile geometry)
+    const int tbl_bytes = mixer ? (int)mixer->n_table * 4 : 0;      // LDG variant: copy of the packed (cos, sin) table
+    // TMA variant: oscillator sequence in time order, two digit words per sample, one common period of all channels
+    // (SRCDSP_SEQ_PERIOD=0: always the whole table).  The mixer variant's shared-memory plan (master layout, ring
+    // depths) depends on its size, so it is re-planned when that changes -- a frequency change, not a per-step event.
+    const unsigned seq_len = mixer ? (tune.seq_period == 0 || !mixer->seq_period ? mixer->n_table : mixer->seq_period) : 0;
+    const int tma_tbl_bytes = (int)seq_len * 8;
+    if (use_tc && mixer && tma_tbl_bytes != tc_mix_table) {
+        SRCDSP_CUDA(cudaStreamSynchronize(stream));
+        tma_mix_ok = false;
+        if (tc_want_p2) SRCDSP_TRY(build_variant(2, true, tma_tbl_bytes));
+        if (!tma_mix_ok) SRCDSP_TRY(build_variant(2, false, tma_tbl_bytes));
+    }
+    const TcParams &Ttma = mixer ? tc_tma_mix : tc_tma;
+    const bool tma_built = mixer ? tma_mix_ok : tma_ok;
+    const long long rows_tma = tma_built ? (long long)(n_in / (size_t)Ttma.G) : 0;
+    int tma_raw = 0, tma_stages = 0;
+    size_t tma_smem = 0;
+    const bool can_map = use_tc && P.vec_in && tensor_map_encoder() != nullptr;
+    // converter warps: groups of W warps, one K-step per group at a time
+    // defaults from sweeps on cfg2 / ddc16 (256 ch x 16 Mi, /16, 255 taps): W = 4; plain decimator 2 groups + 3 byte-plane
+    // stages (the raw ring gets the rest), fused mixer 3 groups + 4 stages (more ALU work per K-step)
+    int tma_w = 4, tma_groups = mixer ? 3 : 2;
+    if (tune.tma_w) tma_w = tune.tma_w == 8 ? 8 : 4;
+    if (tma_built && Ttma.p2) tma_w = 4;  // 16 main row groups per K-step: 4 per warp
+    if (tune.tma_groups > 0) tma_groups = tune.tma_groups;
+    tma_groups = std::min(tma_groups, (mixer ? TMA_MAX_CONV_MIX : TMA_MAX_CONV) / tma_w);
+    bool use_tma = can_map && tma_built && rows_tma >= 1 && rows_tma < 0x7fffffffll && kernel_kind != 3 && !tune.no_tma &&
+                   tma_layout(Ttma, mixer ? tc_fixed_tma_mix : tc_fixed_tma, tma_tbl_bytes, tma_groups, &tma_raw, &tma_stages,
+                              &tma_smem) == SRCDSP_OK;
+    const long long rows_full = use_tma ? rows_tma : (long long)(n_in / (size_t)(32 * M));
+    const bool have_map = can_map && rows_full >= 1 && rows_full < 0x7fffffffll;
+    if (use_tc && !use_tma && tc_layout(tbl_bytes, &tc_stages, &tc_smem) != SRCDSP_OK)
+        use_tc = false, why = "sine table + Toeplitz master + stages exceed 227 KB of shared memory";
+    if (kernel_kind >= 2 && !use_tc)
+        return fail(SRCDSP_E_STATE, "tcgen05 kernel forced but not applicable: %s", tc_ok ? why : tc_why);
+
     if (use_tc) {
         TcParams T = use_tma ? (mixer ? tc_tma_mix : tc_tma) : tc;
         T.in = in;
@@ -959,24 +1079,28 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
         T.rb_stride = T.G;
         T.kc_stride = 32;
         T.epi_sleep_ns = 400;
-        if (const char *e = getenv("SRCDSP_EPI_SLEEP")) T.epi_sleep_ns = (unsigned)std::max(0, atoi(e));
-        if (const char *e = getenv("SRCDSP_CONV_SLEEP")) T.conv_sleep_ns = (unsigned)std::max(0, atoi(e));
+        if (tune.epi_sleep >= 0) T.epi_sleep_ns = (unsigned)tune.epi_sleep;
+        if (tune.conv_sleep >= 0) T.conv_sleep_ns = (unsigned)tune.conv_sleep;
+        T.mma_sleep_ns = mixer ? 100 : 0;
+        if (tune.mma_sleep >= 0) T.mma_sleep_ns = (unsigned)tune.mma_sleep;
         if (mixer) {
             T.cs_table = mixer->d_cs;
             T.phi = P.phi;
             T.freq = P.freq;
             T.mix_mask = P.pm.mask;
+            T.seq_mask = seq_len - 1;
             T.table_bytes = (int)mixer->n_table * 4;
         }
         const int tgrid = (int)std::min<long long>(tc_tiles, sm_count);
-        const char *dbg = getenv("SRCDSP_TC_DEBUG");  // timing experiments only (wrong results)
-        if (dbg && (!mixer || use_tma)) {
-            T.debug = atoi(dbg);
+#ifdef SRCDSP_TIMING_EXPERIMENTS
+        if (tune.tc_debug && (!mixer || use_tma)) {  // timing experiments only (wrong results)
+            T.debug = tune.tc_debug;
             if ((T.debug & 16) && !use_tma) {  // contiguous 128-byte lines per K-step instead of a 4*G-byte stride
                 T.rb_stride = 32;
                 T.kc_stride = 32 * TC_NRB;
             }
         }
+#endif
         // the input as a tensor [C][rows_full][G] of 32-bit words (one complex int16 sample each); a box is one
         // K-step of one tile: 32 samples x (J-1 halo + nrb) row-blocks x 1 channel
         CUtensorMap map;
@@ -993,14 +1117,13 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
             if (cr != CUDA_SUCCESS) return fail(SRCDSP_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
             if (!use_tma) {  // register-staged producers + TMA prefetch into L2
                 T.pf_dist = T.n_stages + 12;
-                if (const char *e = getenv("SRCDSP_PF_DIST")) T.pf_dist = std::max(0, atoi(e));
+                if (tune.pf_dist >= 0) T.pf_dist = tune.pf_dist;
             }
         }
         if (use_tma) {
             TmaExtra X{};
             X.n_raw = tma_raw;
-            if (const char *e = getenv("SRCDSP_TMA_RAW"))
-                if (atoi(e) > 0) X.n_raw = std::max(2, std::min(atoi(e), tma_raw));
+            if (tune.tma_raw > 0) X.n_raw = std::max(2, std::min(tune.tma_raw, tma_raw));
             tma_groups = std::max(1, std::min(tma_groups, std::min(X.n_raw, tma_stages - 1)));
             tma_groups = std::min(tma_groups, T.ksteps);  // every group must see every tile (per-channel rebuild barrier of the fused mixer)
             // a raw stage that different groups convert in turn needs an extra wait (see the converters)
@@ -1012,14 +1135,9 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
             T.n_stages = tma_stages;
             T.table_bytes = tma_tbl_bytes;
             const int threads = 32 * (TMA_CONV_WARP0 + X.n_conv);
-            if (getenv("SRCDSP_TMA_VERBOSE"))
+            if (tune.verbose)
                 fprintf(stderr, "dec_tma_kernel: M=%d p2=%d J=%d grouped=%d master=%d B table=%d B raw=%d split=%d W=%d groups=%d shared_raw=%d smem=%zu\n",
                         T.M, T.p2, T.J, T.grouped, T.master_bytes, T.table_bytes, X.n_raw, T.n_stages, tma_w, tma_groups, X.shared_raw, tma_smem);
-            if (T.debug & 32) {  // wait-cycle accounting variant; counters printed at the next launch
-                unsigned long long c[10];
-                cudaMemcpy(c, d_error, sizeof c, cudaMemcpyDeviceToHost);
-                fprintf(stderr, "tma counters (cycles summed over CTAs): conv total %llu wait_split_empty %llu wait_raw_full %llu fence %llu arrive %llu | mma total %llu wait_full %llu wait_tempty %llu | epi total %llu wait_tfull %llu\n", c[0], c[1], c[2], c[8], c[9], c[3], c[4], c[5], c[6], c[7]);
-                cudaMemset(d_error, 0, sizeof c);
 #define SRCDSP_TMA_LAUNCH(D, MX)                                                         \
     do {                                                                                 \
         if (tma_w == 8)                                                                  \
@@ -1027,33 +1145,44 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
         else                                                                             \
             dec_tma_kernel<D, MX, 4><<<tgrid, threads, tma_smem, stream>>>(T, X, map);   \
     } while (0)
+#ifdef SRCDSP_TIMING_EXPERIMENTS
+            if (T.debug & 32) {  // wait-cycle accounting variant; counters printed at the next launch
+                unsigned long long c[10];
+                cudaMemcpy(c, d_error, sizeof c, cudaMemcpyDeviceToHost);
+                fprintf(stderr, "tma counters (cycles summed over CTAs): conv total %llu wait_split_empty %llu wait_raw_full %llu fence %llu arrive %llu | mma total %llu wait_full %llu wait_tempty %llu | epi total %llu wait_tfull %llu\n", c[0], c[1], c[2], c[8], c[9], c[3], c[4], c[5], c[6], c[7]);
+                cudaMemset(d_error, 0, sizeof c);
                 if (mixer)
                     SRCDSP_TMA_LAUNCH(16, true);
                 else
                     SRCDSP_TMA_LAUNCH(16, false);
-            } else if (mixer) {
-                SRCDSP_TMA_LAUNCH(0, true);
-            } else if (T.debug & 2) {
+            } else if (!mixer && (T.debug & 2)) {
                 SRCDSP_TMA_LAUNCH(2, false);
+            } else
+#endif
+            if (mixer) {
+                SRCDSP_TMA_LAUNCH(0, true);
             } else {
                 SRCDSP_TMA_LAUNCH(0, false);
             }
 #undef SRCDSP_TMA_LAUNCH
         } else if (mixer) {
             dec_tc_kernel<0, true><<<tgrid, TC_THREADS, tc_smem, stream>>>(T, map);
+#ifdef SRCDSP_TIMING_EXPERIMENTS
         } else if (T.debug & 32) {  // wait-cycle accounting variant; counters printed at the next launch
             unsigned long long c[8];
             cudaMemcpy(c, d_error, sizeof c, cudaMemcpyDeviceToHost);
             fprintf(stderr, "tc counters (cycles summed over CTAs): prod total %llu wait_empty %llu fence %llu | mma total %llu wait_full %llu wait_tempty %llu | epi total %llu wait_tfull %llu\n", c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7]);
             cudaMemset(d_error, 0, sizeof c);
             dec_tc_kernel<16, false><<<tgrid, TC_THREADS, tc_smem, stream>>>(T, map);
-        } else {
-            switch (T.debug & 10) {  // 2 / 8: timing-experiment instantiations (wrong results)
+        } else if (T.debug & 10) {  // 2 / 8: timing-experiment instantiations (wrong results)
+            switch (T.debug & 10) {
             case 2: dec_tc_kernel<2, false><<<tgrid, TC_THREADS, tc_smem, stream>>>(T, map); break;
             case 8: dec_tc_kernel<8, false><<<tgrid, TC_THREADS, tc_smem, stream>>>(T, map); break;
-            case 10: dec_tc_kernel<10, false><<<tgrid, TC_THREADS, tc_smem, stream>>>(T, map); break;
-            default: dec_tc_kernel<0, false><<<tgrid, TC_THREADS, tc_smem, stream>>>(T, map); break;
+            default: dec_tc_kernel<10, false><<<tgrid, TC_THREADS, tc_smem, stream>>>(T, map); break;
             }
+#endif
+        } else {
+            dec_tc_kernel<0, false><<<tgrid, TC_THREADS, tc_smem, stream>>>(T, map);
         }
         SRCDSP_LAUNCH_CHECK();
         count_launch();
@@ -1222,6 +1351,10 @@ struct UpBank : Bank {
         const int newH = n / L;
         const int newHp = (newH + UP_HC - 1) / UP_HC * UP_HC;
         const int HP = newHp + 4;
+        // every check that can fail comes before any state is replaced: a refused call leaves the bank as it was
+        const size_t new_smem = ((size_t)L * HP + (size_t)(UP_NT / L) * UP_R * UP_NI + newHp + 8) * 4;
+        if (new_smem > 227 * 1024)
+            return fail(SRCDSP_E_SIZE, "L=%d with %d taps needs %zu bytes of shared memory per CTA", L, n, new_smem);
         std::vector<int32_t> poly((size_t)L * HP, 0);
         for (int k = 0; k < n; ++k) poly[(size_t)(k % L) * HP + k / L] = t[k];
         int len = n;
@@ -1271,10 +1404,7 @@ struct UpBank : Bank {
         length = len;
         imp_length = n;
         left_shift_factor = static_cast<int>(round(log2((double)L)));  // upsampling_filters.h:120
-        const int span = G * UP_R * UP_NI;
-        smem_bytes = ((size_t)L * HP + (size_t)span + Hp + 8) * 4;
-        if (smem_bytes > 227 * 1024)
-            return fail(SRCDSP_E_SIZE, "L=%d with %d taps needs %zu bytes of shared memory per CTA", L, n, smem_bytes);
+        smem_bytes = new_smem;
         return prepare_tc(t, n);
     }
 
@@ -1325,7 +1455,7 @@ struct UpBank : Bank {
             // output that the epilogue reads from TMEM bound it at ~0.85-0.9 T out/s), the CUDA-core kernels pay 2 IMADs
             // per tap: they win up to 8 taps per phase (one tap block, ~1.0 T out/s) and lose beyond (0.5 T out/s).
             bool use_tc = tc_able && tiles >= sm_count / 2 && H > UP_HC;
-            if (const char *e = getenv("SRCDSP_UP_TC")) use_tc = tc_able && atoi(e) != 0;
+            if (tune.up_tc >= 0) use_tc = tc_able && tune.up_tc != 0;
             if (use_tc) {
                 UpTcParams T{};
                 T.in = in, T.out = out, T.in_stride = in_stride, T.out_stride = out_stride;
@@ -1339,9 +1469,10 @@ struct UpBank : Bank {
                 T.tiles_per_ch = (int)(tiles / C);
                 T.total_tiles = tiles;
                 T.error_flag = d_diag;
-                if (const char *e = getenv("SRCDSP_UPT_DEBUG")) T.debug = atoi(e);
+                T.debug = tune.upt_debug;  // 0 unless built with -DSRCDSP_TIMING_EXPERIMENTS
                 const int tgrid = (int)std::min<long long>(tiles, sm_count);
                 const size_t tsmem = upt_smem_bytes(JJ, H);
+#ifdef SRCDSP_TIMING_EXPERIMENTS
                 static unsigned long long *d_cnt = nullptr;
                 if (T.debug & 8) {
                     if (!d_cnt) cudaMalloc(&d_cnt, 64);
@@ -1351,12 +1482,13 @@ struct UpBank : Bank {
                     cudaMemset(d_cnt, 0, 64);
                     T.counters = d_cnt;
                 }
+#endif
                 // form 2 (operand roles swapped: S accumulator slots per output instead of 4, no cross-lane reduction,
                 // 16-byte stores) is bit-identical but measured 3-12 % SLOWER than form 1 on B200 (x8/96 taps 2.93 vs
                 // 2.61 ms: its 32x32b TMEM loads deliver ~60 B/clk/SM, form 1's 16x256b loads ~90), so it only runs
                 // on request: SRCDSP_UP_TC_FORM = 2
                 bool form2 = false;
-                if (const char *e = getenv("SRCDSP_UP_TC_FORM")) form2 = atoi(e) == 2 && aligned16(out, out_stride);
+                if (tune.up_tc_form == 2) form2 = aligned16(out, out_stride);
                 T.n_image = d_a_image + UPT_A_BYTES;
                 if (form2 && tc_digits3) {
                     SRCDSP_CUDA(cudaFuncSetAttribute(up_tc2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -1384,7 +1516,7 @@ struct UpBank : Bank {
                 return SRCDSP_OK;
             }
         }
-        const bool blocked = (L == 4 || L == 8 || L == 16) && aligned16(out, out_stride) && !getenv("SRCDSP_UP_GENERIC");
+        const bool blocked = (L == 4 || L == 8 || L == 16) && aligned16(out, out_stride) && !tune.up_generic;
         last_kernel = blocked ? 2 : 1;
         const int span = blocked ? up4_span(L) : G * UP_R * UP_NI;
         const size_t smem = blocked ? ((size_t)L * (Hp + 4) + (size_t)span + Hp + 8) * 4 : smem_bytes;
@@ -1563,7 +1695,7 @@ struct CorrBank : Bank {
         const size_t smem = (3 * ((size_t)halo + CORR_THREADS) + 2 * N + 2 * (CORR_THREADS + 2)) * 4;
         // register-blocked scan (8 outputs S apart per thread) for power-of-two strides; the one-output-per-thread
         // kernel for any other stride
-        const bool blocked = (S & (S - 1)) == 0 && S <= CORR_THREADS && !getenv("SRCDSP_CORR_GENERIC") &&
+        const bool blocked = (S & (S - 1)) == 0 && S <= CORR_THREADS && !tune.corr_generic &&
                              corr_blocked_smem(N, S) <= 200 * 1024;
         if (blocked) {
             const int TT = CORR_THREADS * CORR_R;

@@ -12,6 +12,14 @@
 
 #include "../../include/srcdsp_b200.h"
 
+// Timing-experiment switches (kernel variants that skip work and therefore give WRONG results) exist only in
+// builds with -DSRCDSP_TIMING_EXPERIMENTS; in the shipped library the tests below are compile-time false.
+#ifdef SRCDSP_TIMING_EXPERIMENTS
+#define SRCDSP_EXP(params, bits) (((params).debug & (bits)) != 0)
+#else
+#define SRCDSP_EXP(params, bits) false
+#endif
+
 namespace srcdsp {
 
 // ---------------------------------------------------------------------------------------------
@@ -135,6 +143,32 @@ __device__ __forceinline__ uint32_t mix_sample_dp2a(uint32_t x, uint32_t bre, ui
     uint32_t p;
     asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(p) : "r"(i), "r"(r));  // {hi = sat(i), lo = sat(r)}
     return __vmaxs2(p, 0x80018001u);  // limitScale16's symmetric clamp (dsp_complex.cpp:63-73)
+}
+// The same mix for the 4 samples of a 16-byte piece, delivered as the 4 byte-plane words of the tcgen05 sample
+// operand (byte k of a word = sample k): the saturating pack is given the SAME component of two samples, so the
+// re / im de-interleave costs nothing and each plane is one PRMT of two packed pairs -- 4 PRMT per piece
+// instead of the 8 that splitting 4 packed (re, im) words takes.
+__device__ __forceinline__ int mix_component_dp2a(uint32_t x, uint32_t digits)
+{
+    return __dp2a_lo((int)x, (int)digits, __dp2a_hi((int)x, (int)digits, 0) * 256) >> 14;
+}
+__device__ __forceinline__ uint32_t pack2_sym_sat(int lo, int hi)
+{
+    uint32_t p;
+    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(p) : "r"(hi), "r"(lo));
+    return __vmaxs2(p, 0x80018001u);  // limitScale16's symmetric clamp (dsp_complex.cpp:63-73)
+}
+__device__ __forceinline__ void mix4_planes_dp2a(const uint4 q, const uint4 bre, const uint4 bim, uint32_t &re_lo, uint32_t &re_hi,
+                                                 uint32_t &im_lo, uint32_t &im_hi)
+{
+    const uint32_t r01 = pack2_sym_sat(mix_component_dp2a(q.x, bre.x), mix_component_dp2a(q.y, bre.y));
+    const uint32_t r23 = pack2_sym_sat(mix_component_dp2a(q.z, bre.z), mix_component_dp2a(q.w, bre.w));
+    const uint32_t i01 = pack2_sym_sat(mix_component_dp2a(q.x, bim.x), mix_component_dp2a(q.y, bim.y));
+    const uint32_t i23 = pack2_sym_sat(mix_component_dp2a(q.z, bim.z), mix_component_dp2a(q.w, bim.w));
+    asm("prmt.b32 %0, %1, %2, 0x6420;" : "=r"(re_lo) : "r"(r01), "r"(r23));
+    asm("prmt.b32 %0, %1, %2, 0x7531;" : "=r"(re_hi) : "r"(r01), "r"(r23));
+    asm("prmt.b32 %0, %1, %2, 0x6420;" : "=r"(im_lo) : "r"(i01), "r"(i23));
+    asm("prmt.b32 %0, %1, %2, 0x7531;" : "=r"(im_hi) : "r"(i01), "r"(i23));
 }
 // digits of one table entry cs = packed (cos, sin)
 __device__ __forceinline__ void mix_digits(uint32_t cs, uint32_t &bre, uint32_t &bim)

@@ -70,6 +70,8 @@ struct TcParams {
     int M;            // decimation ratio
     unsigned epi_sleep_ns;  // epilogue back-off between polls of the accumulator barrier
     unsigned conv_sleep_ns; // TMA variant: converter back-off between polls of the raw-stage barrier (0: plain try_wait loop)
+    unsigned mma_sleep_ns;  // MMA warp's back-off between polls of the byte-plane ring (0: plain try_wait loop).  The warp
+                            // shares a scheduler with converter warps; its polling takes their issue slots
     int G;            // 32 * M samples per row-block
     int J;            // lags: 1 + ceil((Nt-1)/G)
     int tiles_per_ch;
@@ -94,6 +96,7 @@ struct TcParams {
     const uint32_t *cs_table;
     const int *phi, *freq;   // [C] phase at sample 0 of this step, frequency
     unsigned mix_mask;
+    unsigned seq_mask;       // dec_tma_kernel: length - 1 of the oscillator sequence kept in shared memory (a period of every channel's oscillator)
     int table_bytes;         // bytes of the shared-memory copy of the table (0 without MIX)
     int rb_stride, kc_stride;  // samples between row-blocks / K-steps (G and 32; timing experiments permute them)
     int pf_dist;  // dec_tc_kernel: K-steps the L2 prefetcher runs ahead of the MMAs (0: no prefetch, no tensor map)
@@ -415,7 +418,7 @@ __device__ __forceinline__ void tc_mma_role(const TcParams &P, const TcRole &R)
         const uint32_t stage16 = (uint32_t)stage_bytes >> 4;
         const uint2 *plan_hdr = reinterpret_cast<const uint2 *>(a_smem + P.plan_hdr_off);
         const uint4 *plan_ent = reinterpret_cast<const uint4 *>(a_smem + P.plan_ent_off);
-        const bool no_mma = P.debug & 1, no_hi = P.debug & 64;
+        const bool no_mma = SRCDSP_EXP(P, 1), no_hi = SRCDSP_EXP(P, 64);
         auto desc = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | lo; };
         int stage = 0;
         uint32_t sb16 = 0;  // (stage * stage_bytes) >> 4
@@ -434,7 +437,10 @@ __device__ __forceinline__ void tc_mma_role(const TcParams &P, const TcRole &R)
             const uint32_t d_tmem = tmem_base + acc * (2 * TC_NRB);  // (p2: 128 + 128 columns of the same 256)
             uint32_t accumulate = 0;
             for (int kc = 0; kc < KS; ++kc) {
-                mbar_wait_acc<DBG>(bar_full + 8 * stage, phase, P.error_flag, m_full);
+                if (!(DBG & 16) && P.mma_sleep_ns)
+                    mbar_wait_backoff(bar_full + 8 * stage, phase, P.error_flag, P.mma_sleep_ns);
+                else
+                    mbar_wait_acc<DBG>(bar_full + 8 * stage, phase, P.error_flag, m_full);
                 tc_fence_after();
                 const uint32_t cnt = no_mma ? 0u : hdr.y;
                 const uint32_t bs = b_const + sb16;
@@ -522,7 +528,7 @@ __device__ __forceinline__ void tc_epilogue_role(const TcParams &P, const TcRole
                 uint32_t *o_lane = o + idx_lane;
                 const bool full_tile = (tt + 1) * (long long)(TC_NRB * TC_BOUT) <= P.n_out;
 #pragma unroll 1
-                for (int c0 = 0; c0 < ((P.debug & 4) ? 0 : 2 * P.nrb); c0 += 32) {
+                for (int c0 = 0; c0 < (SRCDSP_EXP(P, 4) ? 0 : 2 * P.nrb); c0 += 32) {
                     uint32_t a[16], hh[16];
                     asm volatile(
                         "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
@@ -558,7 +564,7 @@ __device__ __forceinline__ void tc_epilogue_role(const TcParams &P, const TcRole
             uint32_t *o_lane = o + idx_lane;
             const bool full_tile = (tt + 1) * (long long)(TC_NRB * TC_BOUT) <= P.n_out;
 #pragma unroll 1
-            for (int c0 = 0; c0 < ((P.debug & 4) ? 0 : 2 * TC_NRB); c0 += 32) {
+            for (int c0 = 0; c0 < (SRCDSP_EXP(P, 4) ? 0 : 2 * TC_NRB); c0 += 32) {
                 uint32_t a[16], h[16];
                 asm volatile(
                     "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
@@ -589,7 +595,7 @@ __device__ __forceinline__ void tc_epilogue_role(const TcParams &P, const TcRole
         } else {
         const bool full_tile = (tt + 1) * (long long)(TC_NRB * TC_BOUT) <= P.n_out;
 #pragma unroll 1
-        for (int c0 = 0; c0 < ((P.debug & 4) ? 0 : 2 * TC_NRB); c0 += 32) {
+        for (int c0 = 0; c0 < (SRCDSP_EXP(P, 4) ? 0 : 2 * TC_NRB); c0 += 32) {
             uint32_t v[32];
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 "

@@ -74,35 +74,45 @@ __device__ __forceinline__ uint32_t lds32(uint32_t a)
     return v;
 }
 
-// (mix_sample_dp2a / mix_digits: common.cuh)
-// The 4 samples of a piece.  lo = shared address of the channel's oscillator sequence in TIME order: two
-// arrays of N words, Bre[n] and Bim[n] for phase (phi0 + n * freq) mod N, n < N (the sequence has period N).
-// A piece takes two conflict-free LDS.128 instead of 4 gathers from the sine table, whose stride (the channel
-// frequency) makes the lanes collide on a few banks.  idx4 = (n mod N) * 4 of the piece's first sample.
-__device__ __forceinline__ void tma_mix4_with(uint4 &q, const uint4 &a, const uint4 &b)
-{
-    q.x = mix_sample_dp2a(q.x, a.x, b.x);
-    q.y = mix_sample_dp2a(q.y, a.y, b.y);
-    q.z = mix_sample_dp2a(q.z, a.z, b.z);
-    q.w = mix_sample_dp2a(q.w, a.w, b.w);
-}
-__device__ __forceinline__ void tma_mix4(uint4 &q, uint32_t lo, unsigned idx4, unsigned im_off)
-{
-    const uint4 a = lds128<0>(lo + idx4);
-    const uint4 b = lds128<0>(lo + im_off + idx4);
-    tma_mix4_with(q, a, b);
-}
-
+// (mix4_planes_dp2a / mix_digits: common.cuh)
 // one group of 4 rows: this lane's 16-byte piece -> its 4 byte-plane words
+template <int DST_OFF>
+__device__ __forceinline__ void tma_store_planes(uint32_t re_lo, uint32_t re_hi, uint32_t im_lo, uint32_t im_hi, uint32_t dst_lo,
+                                                 uint32_t dst_hi)
+{
+    sts32<DST_OFF>(dst_lo, re_lo);
+    sts32<DST_OFF + 16>(dst_lo, im_lo);
+    sts32<DST_OFF>(dst_hi, re_hi);
+    sts32<DST_OFF + 16>(dst_hi, im_hi);
+}
 template <int DST_OFF>
 __device__ __forceinline__ void tma_split_store(const uint4 q, uint32_t dst_lo, uint32_t dst_hi)
 {
     uint32_t re_lo, re_hi, im_lo, im_hi;
     split4(q, re_lo, re_hi, im_lo, im_hi);
-    sts32<DST_OFF>(dst_lo, re_lo);
-    sts32<DST_OFF + 16>(dst_lo, im_lo);
-    sts32<DST_OFF>(dst_hi, re_hi);
-    sts32<DST_OFF + 16>(dst_hi, im_hi);
+    tma_store_planes<DST_OFF>(re_lo, re_hi, im_lo, im_hi, dst_lo, dst_hi);
+}
+// The oscillator values of the 4 samples of a piece: Bre / Bim digit words (mix_digits).  They come from the
+// channel's oscillator sequence in TIME order in shared memory (two arrays Bre[n], Bim[n] for phase
+// (phi0 + n * freq) mod N; the sequence has period N): a piece takes two conflict-free LDS.128 instead of 4
+// gathers from the sine table, whose stride (the channel frequency) makes the lanes collide on a few banks.
+struct MixPiece {
+    uint4 re, im;
+};
+// lo = shared address of the sequence, idx4 = (n mod N) * 4 of the piece's first sample, im_off = bytes from Bre to Bim
+__device__ __forceinline__ MixPiece tma_mix_piece(uint32_t lo, unsigned idx4, unsigned im_off)
+{
+    MixPiece m;
+    m.re = lds128<0>(lo + idx4);
+    m.im = lds128<0>(lo + im_off + idx4);
+    return m;
+}
+template <int DST_OFF>
+__device__ __forceinline__ void tma_mix_store(const uint4 q, const MixPiece &m, uint32_t dst_lo, uint32_t dst_hi)
+{
+    uint32_t re_lo, re_hi, im_lo, im_hi;
+    mix4_planes_dp2a(q, m.re, m.im, re_lo, re_hi, im_lo, im_hi);
+    tma_store_planes<DST_OFF>(re_lo, re_hi, im_lo, im_hi, dst_lo, dst_hi);
 }
 
 // 4 row groups W apart (this warp's share of 4 * W groups): all loads first, then mix / split / store
@@ -110,39 +120,32 @@ template <bool MIX, int W>
 __device__ __forceinline__ void tma_convert4(uint32_t src, uint32_t dst_lo, uint32_t dst_hi, uint32_t lo, unsigned idx4, unsigned didx4,
                                              unsigned mask4)
 {
-    uint4 v0 = lds128<0>(src), v1 = lds128<W * 512>(src), v2 = lds128<2 * W * 512>(src), v3 = lds128<3 * W * 512>(src);
+    const uint4 v0 = lds128<0>(src), v1 = lds128<W * 512>(src), v2 = lds128<2 * W * 512>(src), v3 = lds128<3 * W * 512>(src);
     if (MIX) {
-        tma_mix4(v0, lo, idx4, mask4 + 4);
-        tma_mix4(v1, lo, (idx4 + didx4) & mask4, mask4 + 4);
-        tma_mix4(v2, lo, (idx4 + 2 * didx4) & mask4, mask4 + 4);
-        tma_mix4(v3, lo, (idx4 + 3 * didx4) & mask4, mask4 + 4);
+        tma_mix_store<0>(v0, tma_mix_piece(lo, idx4, mask4 + 4), dst_lo, dst_hi);
+        tma_mix_store<W * 128>(v1, tma_mix_piece(lo, (idx4 + didx4) & mask4, mask4 + 4), dst_lo, dst_hi);
+        tma_mix_store<2 * W * 128>(v2, tma_mix_piece(lo, (idx4 + 2 * didx4) & mask4, mask4 + 4), dst_lo, dst_hi);
+        tma_mix_store<3 * W * 128>(v3, tma_mix_piece(lo, (idx4 + 3 * didx4) & mask4, mask4 + 4), dst_lo, dst_hi);
+    } else {
+        tma_split_store<0>(v0, dst_lo, dst_hi);
+        tma_split_store<W * 128>(v1, dst_lo, dst_hi);
+        tma_split_store<2 * W * 128>(v2, dst_lo, dst_hi);
+        tma_split_store<3 * W * 128>(v3, dst_lo, dst_hi);
     }
-    tma_split_store<0>(v0, dst_lo, dst_hi);
-    tma_split_store<W * 128>(v1, dst_lo, dst_hi);
-    tma_split_store<2 * W * 128>(v2, dst_lo, dst_hi);
-    tma_split_store<3 * W * 128>(v3, dst_lo, dst_hi);
 }
 
 // Same with ONE oscillator piece for all 4 row groups: when the distance between a warp's row groups
-// (4 * W * G samples) is a multiple of the table size N -- the usual case, e.g. N = 4096 with W * M a
-// multiple of 32 -- the groups see the same oscillator values, which are then fetched and unpacked once
-// per K-step instead of once per piece.
-struct MixPiece {
-    uint4 re, im;  // Bre / Bim digit words of the 4 samples of the piece
-};
-__device__ __forceinline__ void tma_mix4_same(uint4 &q, const MixPiece &m) { tma_mix4_with(q, m.re, m.im); }
+// (4 * W * G samples) is a multiple of the sequence's period -- the usual case, e.g. N = 4096 with W * M a
+// multiple of 32 -- the groups see the same oscillator values, which are then fetched once per K-step
+// instead of once per piece.
 template <int W>
 __device__ __forceinline__ void tma_convert4_same(uint32_t src, uint32_t dst_lo, uint32_t dst_hi, const MixPiece &m)
 {
-    uint4 v0 = lds128<0>(src), v1 = lds128<W * 512>(src), v2 = lds128<2 * W * 512>(src), v3 = lds128<3 * W * 512>(src);
-    tma_mix4_same(v0, m);
-    tma_mix4_same(v1, m);
-    tma_mix4_same(v2, m);
-    tma_mix4_same(v3, m);
-    tma_split_store<0>(v0, dst_lo, dst_hi);
-    tma_split_store<W * 128>(v1, dst_lo, dst_hi);
-    tma_split_store<2 * W * 128>(v2, dst_lo, dst_hi);
-    tma_split_store<3 * W * 128>(v3, dst_lo, dst_hi);
+    const uint4 v0 = lds128<0>(src), v1 = lds128<W * 512>(src), v2 = lds128<2 * W * 512>(src), v3 = lds128<3 * W * 512>(src);
+    tma_mix_store<0>(v0, m, dst_lo, dst_hi);
+    tma_mix_store<W * 128>(v1, m, dst_lo, dst_hi);
+    tma_mix_store<2 * W * 128>(v2, m, dst_lo, dst_hi);
+    tma_mix_store<3 * W * 128>(v3, m, dst_lo, dst_hi);
 }
 
 // generic-pointer variant for the edge path (tab = the oscillator sequence Bre[N] ++ Bim[N], p0 = n mod N)
@@ -253,7 +256,7 @@ __global__ void __launch_bounds__(MIX ? 32 * (TMA_CONV_WARP0 + TMA_MAX_CONV_MIX)
         const uint32_t src_main = smem_u32(raw) + (HQ + wi) * 512 + src_lane;
         const uint32_t dst_main = smem_u32(stages) + (HQ + wi) * 128 + dst_lane;
         const uint32_t tab_u32 = smem_u32(tab_smem);
-        const unsigned mask4 = P.mix_mask << 2;
+        const unsigned mask4 = P.seq_mask << 2;
         const bool two_batches = P.nrb / (4 * W) == 8;  // 8 main row groups per warp (W = 4, 128 row-blocks); else 4
         int rs = g % NR, ss = g % NS;
         uint32_t rpar = 0, spar = 1;  // first wait on a fresh "empty" barrier passes
@@ -288,18 +291,18 @@ __global__ void __launch_bounds__(MIX ? 32 * (TMA_CONV_WARP0 + TMA_MAX_CONV_MIX)
                         ph0 = (unsigned)P.phi[ch];
                         fr = (unsigned)P.freq[ch];
                         asm volatile("bar.sync 1, %0;" ::"r"(NCW * 32) : "memory");
-                        for (unsigned i = cw * 32 + lane; i <= P.mix_mask; i += NCW * 32) {
+                        for (unsigned i = cw * 32 + lane; i <= P.seq_mask; i += NCW * 32) {
                             uint32_t bre, bim;
                             mix_digits(__ldg(P.cs_table + ((ph0 + i * fr) & P.mix_mask)), bre, bim);
                             tab_smem[i] = bre;
-                            tab_smem[P.mix_mask + 1 + i] = bim;
+                            tab_smem[P.seq_mask + 1 + i] = bim;
                         }
                         asm volatile("bar.sync 1, %0;" ::"r"(NCW * 32) : "memory");
                         cur_ch = (int)ch;
                     }
-                    didx4 = ((unsigned)(4 * W * P.G) & P.mix_mask) << 2;  // between a warp's row groups
+                    didx4 = ((unsigned)(4 * W * P.G) & P.seq_mask) << 2;  // between a warp's row groups
                     // sample index mod N of (row-block 4 * wi + grp, K-step 0, this lane's piece)
-                    n_lane = (unsigned)(tile0 + (long long)(4 * wi + grp) * P.G + 4 * piece) & P.mix_mask;
+                    n_lane = (unsigned)(tile0 + (long long)(4 * wi + grp) * P.G + 4 * piece) & P.seq_mask;
                 }
                 cur_tile = tile;
             }
@@ -313,16 +316,14 @@ __global__ void __launch_bounds__(MIX ? 32 * (TMA_CONV_WARP0 + TMA_MAX_CONV_MIX)
             else
                 mbar_wait_acc<DBG>(bar_rfull + 8 * rs, rpar, P.error_flag, w_wait_raw);
             mbar_wait_acc<DBG>(bar_empty + 8 * ss, spar, P.error_flag, w_wait_split);
-            if (P.debug & 8) {
+            if (SRCDSP_EXP(P, 8)) {
                 // timing experiment: barriers only
             } else if (!edge) {
                 const uint32_t src = src_main + rs * raw_bytes;
                 const uint32_t dst = dst_main + ss * stage_bytes;
-                const unsigned idx4 = MIX ? ((n_lane + 32 * kc) & P.mix_mask) << 2 : 0u;
+                const unsigned idx4 = MIX ? ((n_lane + 32 * kc) & P.seq_mask) << 2 : 0u;
                 if (MIX && didx4 == 0) {
-                    MixPiece m;
-                    m.re = lds128<0>(tab_u32 + idx4);
-                    m.im = lds128<0>(tab_u32 + mask4 + 4 + idx4);
+                    const MixPiece m = tma_mix_piece(tab_u32, idx4, mask4 + 4);
                     tma_convert4_same<W>(src, dst, dst + hi_off, m);
                     if (two_batches) tma_convert4_same<W>(src + 16 * 512, dst + 16 * 128, dst + 16 * 128 + hi_off, m);
                 } else {
@@ -338,12 +339,14 @@ __global__ void __launch_bounds__(MIX ? 32 * (TMA_CONV_WARP0 + TMA_MAX_CONV_MIX)
                     // (n mod N) * 4 of (raw row grp, this lane's piece): halo_rows4 row-blocks before row-block grp
                     unsigned hidx4 = 0;
                     if (MIX)
-                        hidx4 = ((unsigned)(tile0 + (long long)(grp - halo_rows4) * P.G + 32 * kc + 4 * piece) & P.mix_mask) << 2;
-                    const unsigned hstep4 = ((unsigned)(4 * P.G) & P.mix_mask) << 2;
+                        hidx4 = ((unsigned)(tile0 + (long long)(grp - halo_rows4) * P.G + 32 * kc + 4 * piece) & P.seq_mask) << 2;
+                    const unsigned hstep4 = ((unsigned)(4 * P.G) & P.seq_mask) << 2;
                     for (int q = 0; q < HQ; ++q) {
-                        uint4 v = lds128<0>(hsrc);
-                        if (MIX) tma_mix4(v, tab_u32, hidx4, mask4 + 4);
-                        tma_split_store<0>(v, hdst, hdst + hi_off);
+                        const uint4 v = lds128<0>(hsrc);
+                        if (MIX)
+                            tma_mix_store<0>(v, tma_mix_piece(tab_u32, hidx4, mask4 + 4), hdst, hdst + hi_off);
+                        else
+                            tma_split_store<0>(v, hdst, hdst + hi_off);
                         hsrc += 512;
                         hdst += 128;
                         hidx4 = (hidx4 + hstep4) & mask4;
@@ -378,14 +381,14 @@ __global__ void __launch_bounds__(MIX ? 32 * (TMA_CONV_WARP0 + TMA_MAX_CONV_MIX)
                     } else {
                         v = *reinterpret_cast<const uint4 *>(src + q * 512);
                     }
-                    tma_convert_store<MIX>(v, dst + q * 128, hi_off, tab_smem, (unsigned)n & P.mix_mask, P.mix_mask);
+                    tma_convert_store<MIX>(v, dst + q * 128, hi_off, tab_smem, (unsigned)n & P.seq_mask, P.seq_mask);
                 }
             }
             // the MMA reads shared memory through the async proxy: fence this warp's stores, then
             // one arrival per warp on both rings
             if (DBG & 16) {
                 const long long f0 = clock64();
-                if (!(P.debug & 128)) fence_async_smem();
+                if (!SRCDSP_EXP(P, 128)) fence_async_smem();
                 const long long f1 = clock64();
                 __syncwarp();
                 if (lane == 0) {
@@ -395,7 +398,7 @@ __global__ void __launch_bounds__(MIX ? 32 * (TMA_CONV_WARP0 + TMA_MAX_CONV_MIX)
                 w_fence += f1 - f0;
                 w_arrive += clock64() - f1;
             } else {
-                if (!(P.debug & 128)) fence_async_smem();
+                if (!SRCDSP_EXP(P, 128)) fence_async_smem();
                 __syncwarp();
                 if (lane == 0) {
                     mbar_arrive(bar_full + 8 * ss);

@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(UPT_THREADS, 1) up_tc_kernel(const __grid_cons
     const int n_tiles = (int)(tile_end - first_tile);
     const unsigned ch0 = (unsigned)(first_tile / P.tiles_per_ch);
     const int tt0 = (int)(first_tile - (long long)ch0 * P.tiles_per_ch);
-    const bool acct = (P.debug & 8) != 0;
+    const bool acct = SRCDSP_EXP(P, 8);
 
     if (warp >= UPT_CONV_WARP0) {
         upt_converter_role(P, stages, raw, bar_full, bar_empty, tid, lane, n_tiles, ch0, tt0, acct);
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(UPT_THREADS, 1) up_tc_kernel(const __grid_cons
                         }
                         const int off = (grp + 4 * k) * 32;
                         const uint32_t word = scale_pack_asym_sat((int)re, (int)im, P.shift);
-                        if ((P.debug & 1) ? word == 0x12345678u : (full_tile || lane_off + off < left)) ot[off] = word;
+                        if (SRCDSP_EXP(P, 1) ? word == 0x12345678u : (full_tile || lane_off + off < left)) ot[off] = word;
                     }
                 };
                 finish(a0, h0, 32 * pass);
@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(UPT_THREADS, 1) up_tc2_kernel(const __grid_con
     const int n_tiles = (int)(tile_end - first_tile);
     const unsigned ch0 = (unsigned)(first_tile / P.tiles_per_ch);
     const int tt0 = (int)(first_tile - (long long)ch0 * P.tiles_per_ch);
-    const bool acct = (P.debug & 8) != 0;
+    const bool acct = SRCDSP_EXP(P, 8);
 
     if (warp >= UPT_CONV_WARP0) {
         upt_converter_role(P, stages, raw, bar_full, bar_empty, tid, lane, n_tiles, ch0, tt0, acct);

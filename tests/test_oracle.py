@@ -178,3 +178,62 @@ def test_oracle_matches_golden(corc, case):
 def test_golden_is_current_reference_output(reflib, case):
     import make_golden as MG
     assert np.array_equal(MG.run_reference(case), GOLD[case["name"]])
+
+
+# ---- live objects: setCoeffs / setCoefficients after samples have been filtered --------------------------------
+def _live_script(rng, sizes, unit, n_ops=14):
+    """(kind, payload) operations: steps of random length (multiples of `unit`) interleaved with coefficient
+    changes that grow, shrink and keep the tap count."""
+    ops = []
+    for i in range(n_ops):
+        if i % 3 == 2:
+            ops.append(("coeffs", rng.integers(-3000, 3000, int(rng.choice(sizes))).astype(np.int32)))
+        else:
+            ops.append(("step", rng.integers(-32768, 32768, (unit * int(rng.integers(1, 40)), 2)).astype(np.int16)))
+    return ops
+
+
+@pytest.mark.parametrize("M,sizes", [(4, (8, 16, 32, 64)), (8, (8, 64, 24)), (1, (5, 33, 2)), (16, (256, 16, 64))])
+def test_live_setcoeffs_decimator_vs_reference(reflib, M, sizes):
+    """history.resize() on a live object (dsptl_dnsampling_filters.h:127): the numpy object model used by the GPU
+    tests equals the compiled reference, whatever the order of growing / shrinking / same-size changes."""
+    rng = np.random.default_rng(100 + M)
+    ops = _live_script(rng, sizes, M * 8)  # blocks of at least ntaps - 1 are not needed: same-size rule only for the reference
+    t0 = rng.integers(-3000, 3000, sizes[0]).astype(np.int32)
+    r, m = O.RefDecimator(reflib, M, t0, variant=1), O.NpDecimatorLive(M, t0)
+    for i, (kind, v) in enumerate(ops):
+        if kind == "coeffs":
+            r.setCoeffs(v)
+            m.setCoeffs(v)
+            if i % 2:
+                r.setLeftShiftBy2(1)
+                m.setLeftShiftBy2(1)
+        else:
+            # the reference reads out of bounds for blocks shorter than ntaps - 1 (:218-219): feed at least that
+            need = m.taps.size - 1
+            if v.shape[0] < need:
+                v = np.concatenate([v] * (need // v.shape[0] + 1))
+                v = v[: (v.shape[0] // M) * M]
+            assert np.array_equal(r.step(v), m.step(v)), (M, i)
+
+
+@pytest.mark.parametrize("L,sizes", [(8, (64, 128, 8, 32)), (4, (32, 4, 64)), (2, (16, 6, 2)), (16, (64, 256, 16))])
+def test_live_setcoefficients_upsampler_vs_reference(reflib, L, sizes):
+    """buffer.resize() with `top` left alone (upsampling_filters.h:118): model == compiled reference.  A change that
+    would leave `top` outside the new buffer (the reference then writes out of bounds) is skipped by reset()."""
+    rng = np.random.default_rng(200 + L)
+    ops = _live_script(rng, sizes, 1, n_ops=20)
+    t0 = rng.integers(-3000, 3000, sizes[0]).astype(np.int32)
+    t0[-1] = 0
+    r, m = O.RefUpsampler(reflib, L, t0), O.NpUpsamplerLive(L, t0)
+    for i, (kind, v) in enumerate(ops):
+        if kind == "coeffs":
+            if m.top >= v.size // L:
+                r.reset()
+                m.reset()
+            r.setCoefficients(v)
+            m.setCoefficients(v)
+            assert (r.getLength(), r.getImpLength()) == (m.getLength(), m.getImpLength())
+        else:
+            fl = i % 4 == 1
+            assert np.array_equal(r.step(v, flush=fl, shift_mode=i % 2), m.step(v, flush=fl, shift_mode=i % 2)), (L, i)
