@@ -133,8 +133,12 @@ class ClockSampler:
         n = self.nvml
         while not self.stop_flag:
             try:
+                try:
+                    pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                except Exception:
+                    pw = None
                 self.samples.append((float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)),
-                                     int(self._reasons(self.handle))))
+                                     int(self._reasons(self.handle)), pw))
             except Exception:
                 pass
             time.sleep(0.003)
@@ -163,8 +167,11 @@ class ClockSampler:
             for s in self.samples:
                 mask |= s[1]
             reasons = sorted(nm for bit, nm in self.REASONS.items() if mask & bit)
-            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
-                    "samples": len(sm), "source": "nvml, sampled inside the timed region"}
+            pw = [s[2] for s in self.samples if s[2] is not None]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": float(min(sm)) if sm else None,
+                    "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm),
+                    "power_w": float(np.median(pw)) if pw else None, "power_w_max": float(max(pw)) if pw else None,
+                    "source": "nvml, sampled inside the timed region"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -437,6 +444,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ddc", action="store_true", help="skip the fused mixer + decimator side measurement")
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 IMAD kernel, 2 tcgen05 kernel")
+    ap.add_argument("--taps", default="design", choices=["design", "impulse", "random"],
+                    help="power experiments only: an impulse (all other taps zero) or dense random 2-digit taps instead of the designed low-pass")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -502,7 +511,13 @@ def main():
         chain = S.FilterUpsamplingFir(M, O.design_interp_taps(nt, M), channels=C, device=local_rank)
         stateful = [chain]
     else:
-        dec = S.FilterDnsamplingFir(M, O.design_lowpass_taps(nt, M), channels=C, device=local_rank, obsolete=True)
+        taps = O.design_lowpass_taps(nt, M)
+        if args.taps == "impulse":
+            taps = np.zeros(nt, np.int32)
+            taps[nt // 2] = 32767
+        elif args.taps == "random":
+            taps = np.random.default_rng(1).integers(-32767, 32768, nt).astype(np.int32)
+        dec = S.FilterDnsamplingFir(M, taps, channels=C, device=local_rank, obsolete=True)
         dec.set_kernel(args.kernel)
         chain, stateful = dec, [dec]
         if w["mix"]:

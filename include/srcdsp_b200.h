@@ -135,7 +135,9 @@ int srcdsp_dec_get_last_kernel(srcdsp_dec_t h, int *kind);
 /* int32, shifted by coeffScaling - leftShift, clamped to +-32767 (limitScale16,               */
 /* dsp_complex.cpp:63-73) and converted back to float (:214).  Samples: interleaved float I/Q  */
 /* (std::vector<std::complex<float>>::data()), strides and sizes in complex samples; host or   */
-/* device pointers.  Samples must be finite and |sum| < 2^31 (undefined in the reference).     */
+/* device pointers.  A sum with |sum| >= 2^31 converts as the reference's x86-64 build does    */
+/* (cvttss2si: 0x80000000 for either sign -- tested); samples must be FINITE: the kernel       */
+/* multiplies zero padding taps, so an infinity or NaN reaches outputs the reference keeps clean. */
 int srcdsp_decf_create(srcdsp_decf_t *h, int device, int channels, int M);
 int srcdsp_decf_destroy(srcdsp_decf_t h);
 /* setCoeffs (:114-134).  coeffScaling follows the reference literally: its unqualified abs()  */
@@ -161,6 +163,12 @@ int srcdsp_decf_sync(srcdsp_decf_t h);
 /* (mixers.h:168-188 feeding dsptl_dnsampling_filters.h:172-220 twice).  The NCO mix is fused  */
 /* into the first decimator's load stage.  mixer may be NULL (dec1 -> dec2 only); dec2 may be  */
 /* NULL.  The handles stay owned by the caller and keep their streaming state.                */
+/* Streams: while the chain exists its members run on dec1's stream (srcdsp_dec_set_stream on   */
+/* dec1 and srcdsp_ddc_set_stream reach them); srcdsp_ddc_destroy -- or destroying dec1 --      */
+/* hands the mixer and dec2 private streams again.  Destroy the chain BEFORE dec1.             */
+/* Aliasing (all filter step functions): DEVICE input and output ranges must not overlap       */
+/* (SRCDSP_E_INVALID); HOST buffers are staged and may alias where the reference allows it      */
+/* (FilterFir::step in place, filters.h:130-169); srcdsp_mixer_step works in place either way. */
 int srcdsp_ddc_create(srcdsp_ddc_t *h, srcdsp_mixer_t mixer, srcdsp_dec_t dec1, srcdsp_dec_t dec2);
 int srcdsp_ddc_destroy(srcdsp_ddc_t h);
 int srcdsp_ddc_step(srcdsp_ddc_t h, const int16_t *in_iq, size_t in_stride, size_t n_in_per_ch,

@@ -777,7 +777,9 @@ def np_decf_step(taps, M: int, x: np.ndarray, history: np.ndarray | None = None,
     for k in range(Nt):
         acc = acc + t[k] * xx[base - k]
     sh = ((np_decf_coeff_scaling(taps) - left_shift) & 0xFFFFFFFF) & 31
-    v = np.trunc(acc).astype(np.int64) >> sh
+    with np.errstate(invalid="ignore"):  # cvttss2si: 0x80000000 for NaN and every |y| >= 2^31 (x86-64 build of the reference)
+        inr = np.abs(acc) < np.float32(2147483648.0)
+        v = np.where(inr, np.trunc(np.where(inr, acc, 0)).astype(np.int64), -(1 << 31)) >> sh
     out = np.clip(v, -32767, 32767).astype(np.float32)
     return out, xx[xx.shape[0] - (Nt - 1):].copy()
 

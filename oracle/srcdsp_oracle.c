@@ -154,6 +154,14 @@ void orc_dec_step(const int32_t *taps, int ntaps, int M, unsigned shift, int16_t
  * dsptl_dnsampling_filters.h:128-132: `abs(coeff[index])` inside namespace dsptl is ::abs(int) -- the float tap is
  * truncated to int first -- and coeffScaling is an unsigned that receives int(floor(log2(sum))).  A sum of 0 makes the
  * reference's value undefined; as compiled by g++ for x86-64 it is INT_MIN, returned here as 0x80000000. */
+/* complex<int32_t>(y) of a float sum as the reference's x86-64 build does it (cvttss2si): truncation, and the
+   "integer indefinite" value 0x80000000 for NaN and for every |y| >= 2^31 -- positive overflow included, which then
+   clamps to -32767.  (A C cast is undefined there; written out so that the restatement does not depend on it.) */
+static int32_t orc_cvttss2si(float y)
+{
+    return (fabsf(y) < 2147483648.0f) ? (int32_t)y : INT32_MIN;
+}
+
 unsigned orc_decf_coeff_scaling(const float *taps, int ntaps)
 {
     double sum = 0;
@@ -181,8 +189,8 @@ void orc_decf_step(const float *taps, int ntaps, int M, unsigned shift, float *h
             ar = ar + pr;
             ai = ai + pi;
         }
-        out_iq[2 * (j / M)] = (float)orc_limit_scale16((int32_t)ar, shift & 31u);
-        out_iq[2 * (j / M) + 1] = (float)orc_limit_scale16((int32_t)ai, shift & 31u);
+        out_iq[2 * (j / M)] = (float)orc_limit_scale16(orc_cvttss2si(ar), shift & 31u);
+        out_iq[2 * (j / M) + 1] = (float)orc_limit_scale16(orc_cvttss2si(ai), shift & 31u);
     }
     memmove(history_iq, xx + 2 * n_in, H * 2 * sizeof(float));
     free(xx);

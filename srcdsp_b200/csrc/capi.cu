@@ -179,6 +179,11 @@ struct Bank {
     Tuning tune;  // environment overrides, captured at creation
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    // A DDC chain runs all of its members on the leader's (first decimator's) stream, so that phase / history
+    // ping-pong stays ordered.  The borrow is tracked: the leader's set_stream() reaches its followers, and a
+    // leader that goes away -- or a chain that is destroyed -- hands every follower a private stream again.
+    Bank *leader = nullptr;
+    std::vector<Bank *> followers;
     // host staging
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_h2d[NBUF] = {}, ev_comp[NBUF] = {}, ev_d2h[NBUF] = {};
@@ -201,8 +206,7 @@ struct Bank {
     int set_stream(void *s)
     {
         DeviceGuard g(device);
-        // a borrowed stream may already be gone (e.g. the chain's leader replaced it): only an
-        // owned stream is drained and destroyed here
+        // only an owned stream is drained and destroyed here; a borrowed one belongs to the caller or the leader
         if (own_stream) {
             SRCDSP_CUDA(cudaStreamSynchronize(stream));
             cudaStreamDestroy(stream);
@@ -214,7 +218,45 @@ struct Bank {
         } else {
             stream = static_cast<cudaStream_t>(s);
         }
+        for (Bank *f : followers) {  // chain members keep running on the leader's stream, whatever it is now
+            if (f->own_stream) {
+                cudaStreamSynchronize(f->stream);
+                cudaStreamDestroy(f->stream);
+                f->own_stream = false;
+            }
+            f->stream = stream;
+        }
         return SRCDSP_OK;
+    }
+
+    // chain membership (srcdsp_ddc_create / _destroy)
+    void follow(Bank *l)
+    {
+        unfollow();
+        if (own_stream) {
+            DeviceGuard g(device);
+            cudaStreamSynchronize(stream);
+            cudaStreamDestroy(stream);
+            own_stream = false;
+        }
+        leader = l;
+        stream = l->stream;
+        l->followers.push_back(this);
+    }
+    void unfollow()
+    {
+        if (!leader) return;
+        auto &v = leader->followers;
+        for (size_t i = 0; i < v.size(); ++i)
+            if (v[i] == this) {
+                v.erase(v.begin() + i);
+                break;
+            }
+        leader = nullptr;
+        DeviceGuard g(device);
+        cudaStreamSynchronize(stream);  // the leader's stream is still alive here
+        own_stream = false;
+        if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) == cudaSuccess) own_stream = true;
     }
 
     int sync()
@@ -257,6 +299,19 @@ struct Bank {
     void release()
     {
         DeviceGuard g(device);
+        // leave the chains this bank takes part in BEFORE its stream goes away
+        while (!followers.empty()) followers.back()->unfollow();
+        if (leader) {
+            auto &v = leader->followers;
+            for (size_t i = 0; i < v.size(); ++i)
+                if (v[i] == this) {
+                    v.erase(v.begin() + i);
+                    break;
+                }
+            leader = nullptr;
+            stream = nullptr;  // borrowed: nothing to destroy
+            own_stream = false;
+        }
         // a borrowed stream may already have been destroyed by its owner; cudaFree below
         // synchronises the device before releasing memory, so no work can still touch it
         if (own_stream && stream) cudaStreamSynchronize(stream);
@@ -334,6 +389,18 @@ static int classify(const void *in, const void *out, bool *on_device)
         return fail(SRCDSP_E_INVALID, "input and output must both be device or both be host pointers");
     *on_device = di;
     return SRCDSP_OK;
+}
+
+// Device buffers of a filter step must not overlap: a CTA reads halo samples that a neighbouring CTA may already have
+// overwritten, and the history kernel reads the input after the main kernel has written the output.  (The reference
+// documents FilterFir::step as usable in place; through this ABI that holds for HOST buffers, which are staged, and
+// for the mixer, which is element-wise.)  Ranges are [p, p + ((C - 1) * stride + n) * bytes).
+static bool device_ranges_overlap(const void *a, size_t a_stride, size_t a_n, const void *b, size_t b_stride, size_t b_n, int C,
+                                  size_t bytes_per_sample)
+{
+    const uintptr_t a0 = (uintptr_t)a, a1 = a0 + ((size_t)(C - 1) * a_stride + a_n) * bytes_per_sample;
+    const uintptr_t b0 = (uintptr_t)b, b1 = b0 + ((size_t)(C - 1) * b_stride + b_n) * bytes_per_sample;
+    return a0 < b1 && b0 < a1;
 }
 
 static inline bool aligned16(const void *p, size_t stride_words)
@@ -1657,7 +1724,8 @@ struct CorrBank : Bank {
     {
         if (!has_pattern) return fail(SRCDSP_E_STATE, "correlator has no pattern (call srcdsp_corr_set_pattern)");
         if (!found || !corr_index) return fail(SRCDSP_E_INVALID, "found / corr_index are null");
-        if (n > 0x7ffffff0u) return fail(SRCDSP_E_SIZE, "correlator block too long (int indices, correlators.h:211)");
+        if (n >= 0x7f7f7f7fu)  // the "not found" sentinel written by cudaMemsetAsync(0x7f) must stay above every index
+            return fail(SRCDSP_E_SIZE, "correlator block too long (int indices, correlators.h:211; at most 0x7f7f7f7e samples per call)");
         for (int c = 0; c < C; ++c) found[c] = 0;
         if (n == 0) return SRCDSP_OK;
         DeviceGuard g(device);
@@ -2018,9 +2086,12 @@ int srcdsp_dec_step(srcdsp_dec_t h, const int16_t *in, size_t in_stride, size_t 
     if (h->C > 1 && (in_stride < n_in || out_stride < n_in / h->M)) return fail(SRCDSP_E_SIZE, "stride smaller than block");
     bool dev;
     SRCDSP_TRY(classify(in, out, &dev));
-    if (dev)
+    if (dev) {
+        if (device_ranges_overlap(in, in_stride, n_in, out, out_stride, n_in / h->M, h->C, 4))
+            return fail(SRCDSP_E_INVALID, "device input and output buffers overlap (in-place filtering needs host buffers)");
         return h->step_device(reinterpret_cast<const uint32_t *>(in), in_stride, n_in,
                               reinterpret_cast<uint32_t *>(out), out_stride, nullptr);
+    }
     return staged_run(*h, in, in_stride, n_in, out, out_stride, (size_t)h->M, 1, (size_t)h->M, 0,
                       [&](const uint32_t *di, size_t dis, size_t len, uint32_t *dout, size_t dos, bool) {
                           return h->step_device(di, dis, len, dout, dos, nullptr);
@@ -2083,9 +2154,10 @@ int srcdsp_ddc_create(srcdsp_ddc_t *h, srcdsp_mixer_t mixer, srcdsp_dec_t dec1, 
     d->mixer = mixer;
     d->d1 = dec1;
     d->d2 = dec2;
-    // one stream for the whole chain so that phase / history ping-pong stays ordered
-    if (mixer) mixer->set_stream(dec1->stream);
-    if (dec2) dec2->set_stream(dec1->stream);
+    // one stream for the whole chain so that phase / history ping-pong stays ordered: the members follow dec1
+    // (tracked borrow, see Bank::follow) until the chain -- or dec1 -- is destroyed
+    if (mixer) mixer->follow(dec1);
+    if (dec2) dec2->follow(dec1);
     *h = d;
     return SRCDSP_OK;
 }
@@ -2097,6 +2169,9 @@ int srcdsp_ddc_destroy(srcdsp_ddc_t h)
         cudaStreamSynchronize(h->d1->stream);
         cudaFree(h->d_mid);
     }
+    // the members get private streams back (no-ops for members that were destroyed first or re-chained since)
+    if (h->mixer && h->mixer->leader == h->d1) h->mixer->unfollow();
+    if (h->d2 && h->d2->leader == h->d1) h->d2->unfollow();
     delete h;
     return SRCDSP_OK;
 }
@@ -2112,9 +2187,12 @@ int srcdsp_ddc_step(srcdsp_ddc_t h, const int16_t *in, size_t in_stride, size_t 
     if (h->d1->C > 1 && (in_stride < n_in || out_stride < n_in / Mt)) return fail(SRCDSP_E_SIZE, "stride smaller than block");
     bool dev;
     SRCDSP_TRY(classify(in, out, &dev));
-    if (dev)
+    if (dev) {
+        if (device_ranges_overlap(in, in_stride, n_in, out, out_stride, n_in / Mt, h->d1->C, 4))
+            return fail(SRCDSP_E_INVALID, "device input and output buffers overlap (in-place filtering needs host buffers)");
         return h->step_device(reinterpret_cast<const uint32_t *>(in), in_stride, n_in,
                               reinterpret_cast<uint32_t *>(out), out_stride);
+    }
     return staged_run(*h->d1, in, in_stride, n_in, out, out_stride, Mt, 1, Mt, 0,
                       [&](const uint32_t *di, size_t dis, size_t len, uint32_t *dout, size_t dos, bool) {
                           return h->step_device(di, dis, len, dout, dos);
@@ -2123,10 +2201,7 @@ int srcdsp_ddc_step(srcdsp_ddc_t h, const int16_t *in, size_t in_stride, size_t 
 int srcdsp_ddc_set_stream(srcdsp_ddc_t h, void *s)
 {
     CHECK_HANDLE(h);
-    SRCDSP_TRY(h->d1->set_stream(s));
-    if (h->mixer) SRCDSP_TRY(h->mixer->set_stream(h->d1->stream));
-    if (h->d2) SRCDSP_TRY(h->d2->set_stream(h->d1->stream));
-    return SRCDSP_OK;
+    return h->d1->set_stream(s);  // reaches the members: they follow dec1 (Bank::follow)
 }
 int srcdsp_ddc_sync(srcdsp_ddc_t h)
 {
@@ -2186,9 +2261,12 @@ int srcdsp_up_step(srcdsp_up_t h, const int16_t *in, size_t in_stride, size_t n_
     } else {
         dev = is_device_ptr(out);
     }
-    if (dev)
+    if (dev) {
+        if (n_in && device_ranges_overlap(in, in_stride, n_in, out, out_stride, n_tot * L, h->C, 4))
+            return fail(SRCDSP_E_INVALID, "device input and output buffers overlap");
         return h->step_device(reinterpret_cast<const uint32_t *>(in), in_stride, n_in, n_flush,
                               reinterpret_cast<uint32_t *>(out), out_stride, shift_mode);
+    }
     return staged_run(*h, in, in_stride, n_in, out, out_stride, 1, L, 1, n_flush * L,
                       [&](const uint32_t *di, size_t dis, size_t len, uint32_t *dout, size_t dos, bool last) {
                           return h->step_device(di, dis, len, last ? n_flush : 0, dout, dos, shift_mode);

@@ -117,41 +117,61 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Bounded wait: a protocol bug must surface as an error, never as a hung GPU.  The loop is two
-// instructions while the phase is incomplete (try_wait suspends the thread for up to the hint, so
-// waiting warps leave the issue slots to the working ones); 2^24 failed attempts (>= 0.3 s even if
-// every attempt returned at once) raise the error flag and trap.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int *error_flag)
+// Bounded wait: a protocol bug must surface as an error, never as a hung GPU.  The bound is WALL-CLOCK time
+// (%globaltimer, checked every 1024 failed attempts): a legitimate stall -- time-slicing under MPS, compute
+// preemption, a debugger or sanitizer, throttled clocks under a persistent CTA -- is far shorter than
+// TC_WAIT_TIMEOUT_NS, a lost arrival is not.  On a timeout the waiter records which barrier in mapped host memory
+// (the record survives) and traps: the trap ends the kernel but poisons the CUDA context, so the next call on the
+// handle reports SRCDSP_E_CUDA and the process has to tear the context down.  It is a bug tripwire, not a
+// recoverable condition.
+constexpr unsigned long long TC_WAIT_TIMEOUT_NS = 20ull * 1000 * 1000 * 1000;
+
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t ok;
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        ".reg .u32 n;\n\t"
-        "mov.u32 n, 0;\n\t"
-        "mov.u32 %0, 1;\n"
-        "MBAR_WAIT_LOOP:\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "@p bra MBAR_WAIT_DONE;\n\t"
-        "add.u32 n, n, 1;\n\t"
-        "setp.lt.u32 p, n, 0x1000000;\n\t"
-        "@p bra MBAR_WAIT_LOOP;\n\t"
-        "mov.u32 %0, 0;\n"
-        "MBAR_WAIT_DONE:\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
         "}\n"
         : "=r"(ok)
         : "r"(bar), "r"(parity), "r"(1000u)  // suspend-time hint (ns)
         : "memory");
-    if (!ok) {
-        // error_flag points into mapped host memory: the record survives the trap that kills the context
-        if (error_flag && atomicExch(error_flag, 1) == 0) {
-            error_flag[1] = (int)bar;
-            error_flag[2] = (int)parity;
-            error_flag[3] = (int)blockIdx.x;
-            error_flag[4] = (int)threadIdx.x;
-            __threadfence_system();
+    return ok != 0;
+}
+__device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity, int *error_flag)
+{
+    if (error_flag && atomicExch(error_flag, 1) == 0) {
+        error_flag[1] = (int)bar;
+        error_flag[2] = (int)parity;
+        error_flag[3] = (int)blockIdx.x;
+        error_flag[4] = (int)threadIdx.x;
+        __threadfence_system();
+    }
+    __trap();
+}
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// The loop is a handful of instructions while the phase is incomplete (try_wait suspends the thread for up to the
+// hint, so waiting warps leave the issue slots to the working ones).
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int *error_flag)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    unsigned long long t0 = 0;
+    for (uint32_t n = 1;; ++n) {
+        if (mbar_try_wait(bar, parity)) return;
+        if ((n & 1023u) == 0) {
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0)
+                t0 = now;
+            else if (now - t0 > TC_WAIT_TIMEOUT_NS)
+                mbar_timeout(bar, parity, error_flag);
         }
-        __trap();
     }
 }
 // Same for a role that waits long and is not on the critical path (the epilogue warps wait most of a tile for the
@@ -159,35 +179,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int *er
 // attempt is followed by a plain sleep -- ~10x fewer polling instructions taken from the working warps' issue slots.
 __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, int *error_flag, uint32_t sleep_ns)
 {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        ".reg .u32 n;\n\t"
-        "mov.u32 n, 0;\n\t"
-        "mov.u32 %0, 1;\n"
-        "MBAR_WAITB_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "@p bra MBAR_WAITB_DONE;\n\t"
-        "nanosleep.u32 %4;\n\t"
-        "add.u32 n, n, 1;\n\t"
-        "setp.lt.u32 p, n, 0x400000;\n\t"
-        "@p bra MBAR_WAITB_LOOP;\n\t"
-        "mov.u32 %0, 0;\n"
-        "MBAR_WAITB_DONE:\n\t"
-        "}\n"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity), "r"(1000u), "r"(sleep_ns)
-        : "memory");
-    if (!ok) {
-        if (error_flag && atomicExch(error_flag, 1) == 0) {
-            error_flag[1] = (int)bar;
-            error_flag[2] = (int)parity;
-            error_flag[3] = (int)blockIdx.x;
-            error_flag[4] = (int)threadIdx.x;
-            __threadfence_system();
+    if (mbar_try_wait(bar, parity)) return;
+    unsigned long long t0 = 0;
+    for (uint32_t n = 1;; ++n) {
+        __nanosleep(sleep_ns);
+        if (mbar_try_wait(bar, parity)) return;
+        if ((n & 1023u) == 0) {
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0)
+                t0 = now;
+            else if (now - t0 > TC_WAIT_TIMEOUT_NS)
+                mbar_timeout(bar, parity, error_flag);
         }
-        __trap();
     }
 }
 // DBG & 16: per-role wait-cycle accounting into P.error_flag[1..] (timing experiments)
@@ -447,6 +450,25 @@ __device__ __forceinline__ void tc_mma_role(const TcParams &P, const TcRole &R)
                 // the hi plane accumulates into the same columns (weight slot + 1 of the master) or, in p2 mode, into
                 // its own columns, where its first MMA of the tile must not accumulate either
                 const uint32_t acc_hi0 = P.p2 ? accumulate : 1u;
+#ifdef SRCDSP_TIMING_EXPERIMENTS
+                if (SRCDSP_EXP(P, 256)) {
+                    // timing experiment (wrong results): the MMA cost structure of the operand-swapped form -- samples on the
+                    // M side (two halves of 128 rows), a band of N = (debug >> 12) tap rows on the N side, per lag and plane
+                    const int nn = (P.debug >> 12) ? (P.debug >> 12) : 56;
+                    const uint32_t it_lo = umma_idesc_i8(0, 1, 128, nn), it_hi = umma_idesc_i8(1, 1, 128, nn);
+                    if (elect_one()) {
+                        for (uint32_t i = 0; i < cnt; ++i) {
+                            const uint4 e = plan_ent[hdr.x + i];
+                            for (uint32_t half = 0; half < 2; ++half) {
+                                umma_i8(d_tmem + half * 128 + 8 * i, desc(bs + e.z + half * 128), desc(a_const + e.x), it_lo, 1);
+                                umma_i8(d_tmem + half * 128 + 8 * i, desc(bs + e.w + half * 128), desc(a_const + e.y), it_hi, 1);
+                            }
+                        }
+                        tc_commit(bar_empty + 8 * stage);
+                        if (kc == KS - 1) tc_commit(bar_tfull + 8 * acc);
+                    }
+                } else
+#endif
                 if (elect_one()) {
                     if (cnt > 0) {
                         umma_i8(d_tmem, desc(a_const + e0.x), desc(bs + e0.z), idesc_lo, accumulate);

@@ -65,7 +65,9 @@ struct DecfTaps {
 
 __device__ __forceinline__ float decf_limit(float y, unsigned shift)
 {
-    int v = __float2int_rz(y) >> shift;  // complex<int32_t>(y): truncation; limitScale16 (dsp_complex.cpp:63-73)
+    // complex<int32_t>(y): truncation as the reference's x86-64 build does it (cvttss2si) -- 0x80000000 for NaN and for every
+    // |y| >= 2^31, positive overflow included (cvt.rzi would saturate to INT_MAX there); then limitScale16 (dsp_complex.cpp:63-73)
+    int v = (fabsf(y) < 2147483648.0f ? __float2int_rz(y) : (int)0x80000000) >> shift;
     v = max(-32767, min(32767, v));
     return (float)v;
 }

@@ -66,6 +66,36 @@ def test_float_oracle_vs_reference(corc, reflib, M, nt, kind):
     assert corc.decf_coeff_scaling(t) == O.np_decf_coeff_scaling(t)
 
 
+def _overflow_case(rng, M, nt):
+    """Large-gain taps and unscaled samples: sums beyond +-2^31, where the reference's x86-64 build yields the
+    "integer indefinite" 0x80000000 (cvttss2si) for BOTH signs -- positive overflow comes out as -32767."""
+    t = rng.uniform(-3e4, 3e4, nt).astype(np.float32)
+    x = rng.uniform(-3e4, 3e4, (M * 400, 2)).astype(np.float32)
+    x[::7] *= np.float32(40.0)
+    return t, x  # finite samples only: see the note on non-finite input in include/srcdsp_b200.h
+
+
+@pytest.mark.parametrize("M,nt", [(8, 63), (4, 32), (1, 9)])
+def test_float_out_of_range_sums_oracle_vs_reference(corc, reflib, M, nt):
+    rng = np.random.default_rng(77 + M)
+    t, x = _overflow_case(rng, M, nt)
+    e = O.RefDecF(reflib, M, t, obsolete=True).step(x)
+    g, _ = corc.decf_step(t, M, x)
+    g2, _ = O.np_decf_step(t, M, x)
+    assert np.array_equal(e, g) and np.array_equal(e, g2)
+    indefinite = max(-32767, -((1 << 31) >> (corc.decf_coeff_scaling(t) & 31)))  # 0x80000000 >> shift, clamped
+    assert (e == indefinite).sum() > 10  # the case does reach the out-of-range conversion
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,nt", [(8, 63), (4, 32), (1, 9), (16, 255)])
+def test_float_out_of_range_sums_gpu(S, corc, M, nt):
+    rng = np.random.default_rng(77 + M)
+    t, x = _overflow_case(rng, M, nt)
+    exp, _ = corc.decf_step(t, M, x)
+    assert np.array_equal(S.FilterDnsamplingFirFloat(M, t, obsolete=True).step(x), exp)
+
+
 @pytest.mark.parametrize("kind", ["unity", "int", "frac"])
 def test_float_fir_oracle_vs_reference(corc, reflib, kind):
     """FilterFir<complex<float>, ...> (filters.h:130-169) in age order is the M = 1 float decimator, for any block

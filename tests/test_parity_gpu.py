@@ -677,3 +677,71 @@ def test_time_sliced_stream_equals_sequential(S, corc, kernel):
         outs.append(host(chain.step(dev(x[s.start: s.start + s.length]))))
         assert outs[-1].shape[0] == s.out_length
     assert np.array_equal(np.concatenate(outs), whole)
+
+
+def test_device_buffers_must_not_overlap(S):
+    """In-place filtering through DEVICE pointers is refused (a CTA would read halo samples a neighbour has already
+    overwritten); host buffers are staged and may alias, as the reference documents for FilterFir::step."""
+    import torch
+    taps = O.design_lowpass_taps(33, 4)
+    x = torch.zeros((8192, 2), dtype=torch.int16, device="cuda")
+    S.synth_fill(x.view(1, 8192, 2), 0x5EED0F00)
+    f = S.FilterFir(taps)
+    with pytest.raises(S.SrcDspError) as ei:
+        f.step(x, out=x)
+    assert ei.value.code == -1
+    d = S.FilterDnsamplingFir(4, taps, obsolete=True)
+    with pytest.raises(S.SrcDspError) as ei:
+        d.step(x, out=x[:2048])
+    assert ei.value.code == -1
+    u = S.FilterUpsamplingFir(4, O.design_interp_taps(32, 4))
+    with pytest.raises(S.SrcDspError) as ei:
+        u.step(x[:1024], out=x[512:512 + 4096])
+    assert ei.value.code == -1
+    # host buffers, in place (M = 1): same result as out of place
+    xh = x.cpu().numpy()
+    ref = S.FilterFir(taps).step(xh.copy())
+    buf = xh.copy()
+    S.FilterFir(taps).step(buf, out=buf)
+    assert np.array_equal(buf, ref)
+    # the mixer is element-wise: in place is fine on the device
+    m = S.Mixer()
+    m.setFrequency(0.3)
+    y = m.step(x.clone())
+    m.reset(0.3)
+    z = x.clone()
+    m.step(z, out=z)
+    assert torch.equal(y, z)
+
+
+def test_chain_members_survive_the_chain_and_its_leader(S, corc):
+    """srcdsp_ddc_create lends dec1's stream to the mixer and dec2; destroying the chain, re-binding dec1's stream
+    or destroying dec1 must not leave them with a dangling stream."""
+    import torch
+    rng = np.random.default_rng(9)
+    t1, t2 = O.design_lowpass_taps(63, 8), O.design_lowpass_taps(63, 4)
+    x = rng.integers(-32768, 32768, (4096, 2)).astype(np.int16)
+    m, d1, d2 = S.Mixer(), S.FilterDnsamplingFir(8, t1, obsolete=True), S.FilterDnsamplingFir(4, t2, obsolete=True)
+    m.setFrequency(-0.25)
+    fr = corc.mixer_set_frequency(-0.25)
+    chain = S.Ddc(m, d1, d2)
+    e, phi = corc.mixer_step(x, 0, fr)
+    e, h1 = corc.dec_step(t1, 8, e)
+    e, h2 = corc.dec_step(t2, 4, e)
+    assert np.array_equal(chain.step(x), e)
+    with torch.cuda.stream(torch.cuda.Stream()):  # a device-buffer step re-binds dec1 (and with it the members)
+        y = chain.step(torch.from_numpy(x).cuda())
+        torch.cuda.current_stream().synchronize()
+    e1, phi = corc.mixer_step(x, phi, fr)
+    e1, h1 = corc.dec_step(t1, 8, e1, h1)
+    e1, h2 = corc.dec_step(t2, 4, e1, h2)
+    assert np.array_equal(y.cpu().numpy(), e1)
+    del chain, d1  # the leader goes first; the mixer and dec2 run on private streams again
+    import gc
+    gc.collect()
+    e2, phi = corc.mixer_step(x, phi, fr)
+    assert np.array_equal(m.step(x), e2)
+    e3, h2 = corc.dec_step(t2, 4, x, h2)
+    assert np.array_equal(d2.step(x), e3)
+    d2.setCoeffs(t2)  # cudaStreamSynchronize on its own stream
+    m.sync()

@@ -28,16 +28,17 @@ def main():
     variants = []
     for a in args:
         name, lib, env, wl = a.split(":")
-        variants.append((name, lib, dict(e.split("=") for e in env.split(",") if e), wl))
+        wl, _, extra = wl.partition("+")  # workload+--flag=value+... : extra bench.py arguments
+        variants.append((name, lib, dict(e.split("=") for e in env.split(",") if e), wl, [x for x in extra.split("+") if x]))
     res = {v[0]: [] for v in variants}
     for rep in range(reps):
-        for name, lib, env, wl in variants:
+        for name, lib, env, wl, extra in variants:
             if lib != "-":
                 shutil.copyfile(os.path.join(ROOT, "build", "ab", lib), LIB)
             e = dict(os.environ)
             e.update(env)
             p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", wl, "--steps", str(steps), "--warmup", "3",
-                                "--no-ddc", "--no-cpu", "--no-e2e"], capture_output=True, text=True, env=e, timeout=600)
+                                "--no-ddc", "--no-cpu", "--no-e2e"] + extra, capture_output=True, text=True, env=e, timeout=600)
             line = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
             if p.returncode != 0 or not line:
                 print(f"{name} rep{rep}: FAILED rc={p.returncode} {p.stderr[-300:]}", flush=True)
@@ -47,8 +48,8 @@ def main():
                     print("   | " + ln[:600], flush=True)
             d = json.loads(line[-1])
             res[name].append(d["ms_per_step"])
-            print(f"{name} {wl} rep{rep}: {d['ms_per_step']:.3f} ms frac={d['roofline']['frac']:.3f} clk={d['clocks']['sm_mhz']} "
-                  f"{d['clocks']['reasons']}", flush=True)
+            print(f"{name} {wl} rep{rep}: {d['ms_per_step']:.3f} ms frac={d['roofline']['frac']:.3f} clk={d['clocks']['sm_mhz']}/{d['clocks'].get('sm_min_mhz')} "
+                  f"P={d['clocks'].get('power_w')}/{d['clocks'].get('power_w_max')}W {d['clocks']['reasons']}", flush=True)
     print("---- summary (min / median ms) ----")
     for name, v in res.items():
         if v:

@@ -40,7 +40,7 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 // step s -> (tile = s / ksteps, kc = s % ksteps): rows tile*ROWS.., byte column kc*BOXW
 template <int MODE>
 __global__ void __launch_bounds__(1024, 1) tmastream(const __grid_constant__ CUtensorMap map, long long n_steps, int ksteps,
-                                                     int rows, int boxw, int ns, int cw, uint32_t *sink)
+                                                     int rows, int boxw, int ns, int cw, uint32_t *sink, int sub)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -66,7 +66,11 @@ __global__ void __launch_bounds__(1024, 1) tmastream(const __grid_constant__ CUt
                 mbar_expect_tx(bar_full + 8 * stage, stage_bytes);
                 const long long tile = s / ksteps;
                 const int kc = (int)(s - tile * ksteps);
-                tma_load_2d(smem_u32(raw + stage * stage_bytes), &map, kc * (boxw / 4), (int)(tile * rows), bar_full + 8 * stage);
+                // sub > 1: the stage is filled by `sub` boxes of boxw / sub bytes per row (the map's box is that narrow),
+                // each into its own dense region -- the in-place byte-plane layout needs 32-byte rows
+                for (int q = 0; q < sub; ++q)
+                    tma_load_2d(smem_u32(raw + stage * stage_bytes + q * (stage_bytes / sub)), &map, kc * (boxw / 4) + q * (boxw / sub / 4),
+                                (int)(tile * rows), bar_full + 8 * stage);
                 if (++stage == ns) {
                     stage = 0;
                     parity ^= 1;
@@ -135,22 +139,26 @@ int main()
     EncodeFn encode = (EncodeFn)fn;
     CK(cudaFuncSetAttribute(tmastream<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(tmastream<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    struct Cfg { int mode, pitch, boxw, rows, ns, cw, l2promo; };
+    struct Cfg { int mode, pitch, boxw, rows, ns, cw, l2promo, sub, swz; };
     const Cfg cfgs[] = {
         {0, 2048, 128, 128, 8, 8, 2},  {0, 2048, 128, 128, 12, 8, 2}, {0, 2048, 128, 128, 8, 16, 2}, {0, 2048, 256, 128, 6, 8, 2},
         {0, 2048, 128, 128, 8, 8, 0},  {0, 2048, 128, 128, 8, 8, 3},  {0, 2048, 128, 64, 16, 8, 2},  {0, 2048, 1024, 16, 8, 8, 2},
         {0, 512, 128, 128, 8, 8, 2},   {0, 8192, 128, 128, 8, 8, 2},
         {1, 2048, 128, 128, 8, 8, 2},  {1, 2048, 128, 128, 8, 12, 2}, {1, 2048, 128, 128, 8, 16, 2}, {1, 2048, 128, 128, 6, 24, 2},
         {1, 2048, 256, 128, 4, 16, 2}, {1, 512, 128, 128, 8, 16, 2},
+        // a K-step as 2 boxes of 64-byte rows / 4 boxes of 32-byte rows (plain and with the 32-byte swizzle)
+        {0, 2048, 128, 128, 8, 8, 2, 2, 0}, {0, 2048, 128, 128, 8, 8, 2, 4, 0}, {0, 2048, 128, 128, 8, 8, 2, 4, 1},
+        {0, 2048, 128, 128, 12, 8, 2, 4, 1}, {0, 2048, 128, 128, 8, 8, 1, 4, 1}, {0, 2048, 128, 128, 8, 8, 3, 4, 1},
     };
     for (const Cfg &c : cfgs) {
         CUtensorMap map;
         const cuuint64_t gdim[2] = {(cuuint64_t)c.pitch / 4, (cuuint64_t)(bytes / c.pitch)};
         const cuuint64_t gstr[1] = {(cuuint64_t)c.pitch};
-        const cuuint32_t box[2] = {(cuuint32_t)c.boxw / 4, (cuuint32_t)c.rows};
+        const int sub = c.sub ? c.sub : 1;
+        const cuuint32_t box[2] = {(cuuint32_t)c.boxw / 4 / sub, (cuuint32_t)c.rows};
         const cuuint32_t estr[2] = {1, 1};
         CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, d, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            CU_TENSOR_MAP_SWIZZLE_NONE, (CUtensorMapL2promotion)c.l2promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                            c.swz ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE, (CUtensorMapL2promotion)c.l2promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             printf("encode failed %d\n", (int)r);
             continue;
@@ -164,9 +172,9 @@ int main()
         CK(cudaEventCreate(&e1));
         auto launch = [&]() {
             if (c.mode == 0)
-                tmastream<0><<<148, threads, smem>>>(map, n_steps, ksteps, c.rows, c.boxw, c.ns, c.cw, sink);
+                tmastream<0><<<148, threads, smem>>>(map, n_steps, ksteps, c.rows, c.boxw, c.ns, c.cw, sink, sub);
             else
-                tmastream<1><<<148, threads, smem>>>(map, n_steps, ksteps, c.rows, c.boxw, c.ns, c.cw, sink);
+                tmastream<1><<<148, threads, smem>>>(map, n_steps, ksteps, c.rows, c.boxw, c.ns, c.cw, sink, sub);
         };
         launch();
         CK(cudaDeviceSynchronize());
@@ -176,8 +184,8 @@ int main()
         CK(cudaDeviceSynchronize());
         float ms;
         CK(cudaEventElapsedTime(&ms, e0, e1));
-        printf("mode=%d pitch=%5d boxw=%4d rows=%3d stages=%2d (%3d KB in flight) consumers=%2d l2promo=%d : %.0f GB/s\n", c.mode, c.pitch,
-               c.boxw, c.rows, c.ns, c.ns * c.rows * c.boxw / 1024, c.cw, c.l2promo, (double)bytes * 4 / (ms * 1e-3) / 1e9);
+        printf("mode=%d pitch=%5d boxw=%4d rows=%3d stages=%2d (%3d KB in flight) consumers=%2d l2promo=%d sub=%d swz=%d : %.0f GB/s\n", c.mode, c.pitch,
+               c.boxw, c.rows, c.ns, c.ns * c.rows * c.boxw / 1024, c.cw, c.l2promo, sub, c.swz, (double)bytes * 4 / (ms * 1e-3) / 1e9);
     }
     return 0;
 }

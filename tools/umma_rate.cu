@@ -81,7 +81,10 @@ int main()
     CK(cudaFuncSetAttribute(rate<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     struct C { int kind, m, n, distinct, grid, layout, alt; } cs[] = {
         {0, 128, 256, 1, 148, 0, 0}, {0, 128, 256, 1, 148, 0, 1}, {0, 128, 256, 1, 148, 2, 0}, {0, 128, 256, 4, 148, 2, 1}, {0, 128, 64, 1, 148, 2, 0},
-        {0, 128, 128, 1, 148, 2, 0}, {1, 128, 256, 1, 148, 2, 0}, {1, 128, 64, 1, 148, 2, 0},  {0, 128, 256, 1, 148, 6, 0}, {0, 128, 64, 1, 148, 6, 0}};
+        {0, 128, 128, 1, 148, 2, 0}, {1, 128, 256, 1, 148, 2, 0}, {1, 128, 64, 1, 148, 2, 0},  {0, 128, 256, 1, 148, 6, 0}, {0, 128, 64, 1, 148, 6, 0},
+        // narrow N with the SWIZZLE_NONE layout (samples on the M side, a band of the taps on the N side)
+        {0, 128, 16, 1, 148, 0, 0},  {0, 128, 24, 1, 148, 0, 0},  {0, 128, 32, 1, 148, 0, 0},  {0, 128, 48, 1, 148, 0, 0},  {0, 128, 64, 1, 148, 0, 0},
+        {0, 128, 96, 1, 148, 0, 0},  {0, 128, 128, 1, 148, 0, 0}, {0, 128, 48, 1, 148, 0, 1},  {0, 64, 48, 1, 148, 0, 0},   {0, 64, 256, 1, 148, 0, 0}};
     const int reps = 4000;
     for (auto c : cs) {
         for (int it = 0; it < 2; ++it) {
