@@ -74,8 +74,22 @@ def bytes_per_out(w):
     if w["kind"] == "mix":
         return 8.0
     if w["kind"] == "ddc2":
-        return 4.0 * w["M"] * w["M2"] + 4.0 + 8.0 * w["M2"]
+        return 4.0 * w["M"] * w["M2"] + 4.0  # 132 B; the stage-1 round trip is traffic, not algorithm
     return 4.0 * w["M"] + 4.0
+
+
+def traffic_model_bytes_per_out(w):
+    """What the kernels really move per output: the two-stage chain writes and re-reads the stage-1 stream."""
+    return bytes_per_out(w) + (8.0 * w["M2"] if w["kind"] == "ddc2" else 0.0)
+
+
+BINDING = {  # which resource bounds the dominant kernel of a workload (DESIGN.md 4); the roofline fraction is always vs HBM
+    "cfg2": "hbm (shared-memory bandwidth and, sustained, the 1 kW power cap before it)",
+    "ddc16": "sm issue / integer pipes of the fused mixer, then hbm",
+    "ddc8": "hbm", "cfg3": "hbm (+ the stage-1 round trip)", "cfg4": "int32 multiply pipe (16 IMAD per output), hbm writes next",
+    "cfg5": "tensor pipe + shared-memory operand reads (2046 MACs per output)", "cfg1": "launch latency (131072 outputs)",
+    "mix": "hbm", "mid": "hbm",
+}
 
 
 def out_per_in(w):
@@ -432,6 +446,130 @@ def decf_bench(args, w, base, S, O, torch, device):
     return 0
 
 
+def h2d_ceiling(torch, S, device, dist, barrier, all_max, chunk_bytes=48 << 20, total_bytes=4 << 30):
+    """The box's ceiling for the end-to-end number: every rank copies pinned host memory to its GPU with one bare
+    cudaMemcpyAsync per 48 MB chunk (nothing batched, no kernels), all ranks at once; D2H the same way afterwards."""
+    src = torch.empty(chunk_bytes * 4, dtype=torch.uint8, pin_memory=True)
+    dst = torch.empty(chunk_bytes * 4, dtype=torch.uint8, device="cuda")
+    out = {}
+    for name, (a, b) in (("h2d", (dst, src)), ("d2h", (src, dst))):
+        n_chunks = total_bytes // chunk_bytes
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(n_chunks):
+            o = (i % 4) * chunk_bytes
+            a[o:o + chunk_bytes].copy_(b[o:o + chunk_bytes], non_blocking=True)
+        torch.cuda.synchronize()
+        dt_own = time.perf_counter() - t0
+        barrier()
+        dt = all_max(dt_own)
+        out[name + "_gbs_per_gpu_slowest"] = n_chunks * chunk_bytes / dt / 1e9
+        out[name + "_gbs_this_rank"] = n_chunks * chunk_bytes / dt_own / 1e9
+    out["chunk_bytes"] = chunk_bytes
+    out["note"] = "bare cudaMemcpyAsync from / to pinned memory, one call per chunk, all ranks concurrently; per-GPU rate of the slowest rank"
+    return out
+
+
+STREAM_SAMPLES = 1 << 32   # BASELINE configs[4]: "single very long stream (4G complex samples)"
+STREAM_CALL = 1 << 29      # samples per step() call (the reference indexes with int: < 2^31 per call)
+
+
+def stream_bench(args, w, base, S, O, torch, dist, rank, world, local_rank, timed, roofline_of, time_slices):
+    """BASELINE configs[4] as a fixed job (strong scaling): ONE stream of 2^32 complex samples, decimate-by-4 1023-tap FIR,
+    cut into `world` time slices at multiples of the decimation.  Rank g holds samples [start - warm, start + length) of
+    the stream in HBM; a step = reset, warm-up run over the halo in front of the slice (outputs discarded; rank 0 has
+    none: the stream starts from a reset filter), then the slice in calls of 2^29 samples with carried history.  Rank g's
+    outputs are the stream's outputs [start / 4, (start + length) / 4): no collective, no exchange."""
+    M, nt = w["M"], w["ntaps"]
+    sl = time_slices(STREAM_SAMPLES, world, [nt], [M])[rank]
+    x = torch.empty((1, sl.warmup + sl.length, 2), dtype=torch.int16, device="cuda")
+    y = torch.empty((1, sl.length // M, 2), dtype=torch.int16, device="cuda")
+    scratch = torch.empty((1, max(1, sl.warmup // M), 2), dtype=torch.int16, device="cuda")
+    S.synth_fill(x, 0x5EED0005, ch0=0, n0=sl.start - sl.warmup, amp_shift=2)
+    dec = S.FilterDnsamplingFir(M, O.design_lowpass_taps(nt, M), channels=1, device=local_rank, obsolete=True)
+    dec.set_kernel(args.kernel)
+    calls = [(o, min(STREAM_CALL, sl.length - o)) for o in range(0, sl.length, STREAM_CALL)]
+
+    def step():
+        dec.reset()
+        if sl.warmup:
+            dec.step(x[:, :sl.warmup], out=scratch)
+        for o, ln in calls:
+            dec.step(x[:, sl.warmup + o: sl.warmup + o + ln], out=y[:, o // M:(o + ln) // M])
+
+    m = timed(step, args.steps, args.warmup)
+    n_out_total = STREAM_SAMPLES // M
+    roof = roofline_of("cfg5", w, dec, sl.length // M, m["k_ms"], m["clocks"])
+    roof["launches_per_step"] = len(calls) + (1 if sl.warmup else 0)
+    line = dict(base, scaling="strong", value=n_out_total * args.steps / (m["total_ms"] * 1e-3) / 1e6,
+                ms_per_step=m["total_ms"] / args.steps, roofline=roof, cpu_baseline=None, e2e=None, clocks=m["clocks"],
+                gpu_launches=m["launches"], impl="ours")
+    line["config"] = {"workload": "cfg5: ONE stream of 2^32 complex samples, decimate-by-4 1023-tap FIR, time-sliced with halo",
+                      "stream_samples": STREAM_SAMPLES, "slices": world, "slice_samples": sl.length, "halo_warmup_samples": sl.warmup,
+                      "samples_per_call": STREAM_CALL, "ratio": M, "taps": nt, "nco_mix": False,
+                      "sharding": "time slices at multiples of the decimation, warm-up halo, no collective (strong scaling)",
+                      "l2": "2 GiB per call >> 126 MB L2 (no flush needed)"}
+    if rank == 0:
+        print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
+def group_bench(args, w, base, S, O, torch):
+    """cfg3 / cfg5 through the single-process multi-device driver (srcdsp_group_*): pinned host buffers in and out, one
+    host thread + three streams per device, outputs written to their final place -- north_star's "results are gathered to
+    the host with async copies from pinned memory".  End to end by construction (value == e2e)."""
+    if int(os.environ.get("WORLD_SIZE", "1")) != 1:
+        raise SystemExit("--group drives all devices from ONE process: run it without torchrun")
+    G = args.gpus
+    if args.workload == "cfg5":
+        C, n, M1, M2, nt, mode = 1, STREAM_SAMPLES, w["M"], 0, w["ntaps"], "slices"
+        grp = S.DdcGroup(mode, list(range(G)), C, M1, O.design_lowpass_taps(nt, M1))
+    elif args.workload == "cfg3":
+        C, n, M1, M2, nt, mode = w["channels"], w["n"], w["M"], w["M2"], w["ntaps"], "channels"
+        grp = S.DdcGroup(mode, list(range(G)), C, M1, O.design_lowpass_taps(nt, M1), M2, O.design_lowpass_taps(w["ntaps2"], M2), n_table=4096)
+        grp.setFrequency((-1 + 2 * (np.arange(C) + 0.5) / C).astype(np.float32))
+    else:
+        raise SystemExit("--group is for the workloads that shard one job: cfg3 (channel batches), cfg5 (time slices)")
+    Mt = M1 * (M2 or 1)
+    hin, hout = S.PinnedBuffer(C, n), S.PinnedBuffer(C, n // Mt)
+    # synthetic input, generated on device 0 and copied to the pinned buffer piece by piece
+    piece = 1 << 28
+    tmp = torch.empty((1, min(piece, n), 2), dtype=torch.int16, device="cuda:0")
+    with torch.cuda.device(0):
+        for c in range(C):
+            for o in range(0, n, piece):
+                ln = min(piece, n - o)
+                S.synth_fill(tmp[:, :ln], SEED, ch0=c, n0=o, amp_shift=2)
+                torch.cuda.synchronize()
+                S._capi.check(S.lib().srcdsp_memcpy(0, hin.array[c, o:o + ln].ctypes.data, tmp.data_ptr(), ln * 4))
+    del tmp
+    grp.step(hin.array, out=hout.array)  # allocates the staging buffers
+    grp.reset()
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = S.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        grp.step(hin.array, out=hout.array)
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    lay, used = grp.layout()
+    n_out = C * (n // Mt)
+    value = n_out * args.e2e_steps / dt / 1e6
+    line = dict(base, scaling="strong", value=value, ms_per_step=dt / args.e2e_steps * 1e3, steps=args.e2e_steps, roofline=None,
+                cpu_baseline=None, clocks=clocks, gpu_launches=int(S.launch_count() - l0), impl="ours",
+                e2e={"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": C * n * 4, "d2h_bytes_per_step": n_out * 4,
+                     "h2d_gbs_total": C * n * 4 * args.e2e_steps / dt / 1e9,
+                     "api": f"DdcGroup('{mode}').step(pinned host in, pinned host out) -> srcdsp_group_step"})
+    line["config"] = {"workload": w["desc"].split(":")[0] + f" through one process driving {G} device(s)", "mode": mode, "channels": C,
+                      "samples_per_channel": n, "ratio": Mt, "members": [{"device": d, "ch0": c0, "channels": nc} for d, c0, nc in lay],
+                      "members_used": used, "sharding": "single process, one host thread + 3 streams per device, no collective"}
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -444,6 +582,11 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ddc", action="store_true", help="skip the fused mixer + decimator side measurement")
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 IMAD kernel, 2 tcgen05 kernel")
+    ap.add_argument("--group", action="store_true",
+                    help="cfg3 / cfg5 through ONE process driving --gpus devices (srcdsp_group_*: per-device host threads and "
+                         "streams, pinned host buffers in and out); not under torchrun")
+    ap.add_argument("--h2d-ceiling", action="store_true",
+                    help="with e2e: also time bare per-GPU cudaMemcpyAsync copies from pinned memory (all ranks at once), the box's ceiling for e2e")
     ap.add_argument("--taps", default="design", choices=["design", "impulse", "random"],
                     help="power experiments only: an impulse (all other taps zero) or dense random 2-digit taps instead of the designed low-pass")
     args = ap.parse_args()
@@ -470,7 +613,7 @@ def main():
         line = dict(base, impl="reference", value=res["value"], ms_per_step=t * 1e3, cpu_baseline=res,
                     e2e={"value": res["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                     gpu_launches=0)
-        line["config"]["note"] = "CPU reference arm: each step is the bounded sample described in cpu_baseline.sample"
+        line["note"] = "CPU reference arm: each step is the bounded sample described in cpu_baseline.sample"
         print(json.dumps(line))
         return 0
 
@@ -496,39 +639,9 @@ def main():
         return corr_bench(args, w, base, S, torch, local_rank)
     if w["kind"] == "decf":
         return decf_bench(args, w, base, S, O, torch, local_rank)
-    from srcdsp_b200.sharding import channel_shard
-    my_ch = channel_shard(C * world, world, rank)  # weak scaling: 256 channels per GPU
-    n_out = int(n * out_per_in(w))
-    x = torch.empty((C, n, 2), dtype=torch.int16, device="cuda")
-    y = torch.empty((C, n_out, 2), dtype=torch.int16, device="cuda")
-    S.synth_fill(x, SEED, ch0=my_ch.start, amp_shift=2)
-    dec = None
-    if w["kind"] == "mix":
-        chain = S.Mixer(channels=C, device=local_rank)
-        chain.setFrequency((-1 + 2 * (np.arange(my_ch.start, my_ch.stop) + 0.5) / (C * world)).astype(np.float32))
-        stateful = [chain]
-    elif w["kind"] == "up":
-        chain = S.FilterUpsamplingFir(M, O.design_interp_taps(nt, M), channels=C, device=local_rank)
-        stateful = [chain]
-    else:
-        taps = O.design_lowpass_taps(nt, M)
-        if args.taps == "impulse":
-            taps = np.zeros(nt, np.int32)
-            taps[nt // 2] = 32767
-        elif args.taps == "random":
-            taps = np.random.default_rng(1).integers(-32767, 32768, nt).astype(np.int32)
-        dec = S.FilterDnsamplingFir(M, taps, channels=C, device=local_rank, obsolete=True)
-        dec.set_kernel(args.kernel)
-        chain, stateful = dec, [dec]
-        if w["mix"]:
-            mix = S.Mixer(channels=C, device=local_rank)
-            mix.setFrequency((-1 + 2 * (np.arange(my_ch.start, my_ch.stop) + 0.5) / (C * world)).astype(np.float32))
-            dec2 = None
-            if w["kind"] == "ddc2":
-                dec2 = S.FilterDnsamplingFir(w["M2"], O.design_lowpass_taps(w["ntaps2"], w["M2"]), channels=C,
-                                             device=local_rank, obsolete=True)
-                stateful.append(dec2)
-            chain = S.Ddc(mix, dec, dec2)
+    if args.group:
+        return group_bench(args, w, base, S, O, torch)
+    from srcdsp_b200.sharding import channel_shard, time_slices
 
     def barrier():
         torch.cuda.synchronize()
@@ -536,87 +649,183 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        chain.step(x, out=y)
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    l0 = S.launch_count()
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    evs[0].record()
-    for i in range(args.steps):
-        chain.step(x, out=y)
-        evs[i + 1].record()
-    barrier()
-    launches = S.launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
-    total_ms = evs[0].elapsed_time(evs[-1])
-    step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    if dist:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    n_out_total = C * n_out * world
-    value = n_out_total * args.steps / (total_ms * 1e-3) / 1e6
+    def all_max(v):
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        if dist:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    # roofline of the dominant kernel (the decimating-FIR kernel: one launch per step; the history
-    # kernel that shares the step is ~2 us).  Algorithmic bytes per launch = (4*M + 4) B/output x
-    # outputs per launch (68 B/output for cfg2).
+    def timed(step_fn, steps, warmup, settle_s=0.0):
+        """W untimed + K timed calls of step_fn, CUDA events on the launching stream, barrier + synchronize on both
+        sides, clocks / throttle reasons / power sampled during the timed region (rank 0), max over ranks.
+        settle_s: idle time in front, so that a side measurement starts from the same power state as the headline
+        does after its set-up (the boxes run into the 1 kW software power cap within ~100 ms of these kernels)."""
+        if settle_s:
+            barrier()
+            time.sleep(settle_s)
+        for _ in range(warmup):
+            step_fn()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        l0 = S.launch_count()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        evs[0].record()
+        for i in range(steps):
+            step_fn()
+            evs[i + 1].record()
+        barrier()
+        launches = S.launch_count() - l0
+        clocks = sampler.stop() if rank == 0 else None
+        total_ms = all_max(evs[0].elapsed_time(evs[-1]))
+        step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
+        return {"total_ms": total_ms, "ms": total_ms / steps, "k_ms": float(np.mean(step_ms)), "clocks": clocks, "launches": int(launches)}
+
+    def lo_freqs(ch: range, total: int):
+        return (-1 + 2 * (np.arange(ch.start, ch.stop) + 0.5) / total).astype(np.float32)
+
+    def build_chain(wk, ch: range, total_ch: int):
+        """The banks of workload wk for the channels `ch` of `total_ch` on this rank's device."""
+        Cc = len(ch)
+        Mw, ntw = wk["M"], wk["ntaps"]
+        if wk["kind"] == "mix":
+            chain = S.Mixer(channels=Cc, device=local_rank)
+            chain.setFrequency(lo_freqs(ch, total_ch))
+            return chain, None, [chain]
+        if wk["kind"] == "up":
+            chain = S.FilterUpsamplingFir(Mw, O.design_interp_taps(ntw, Mw), channels=Cc, device=local_rank)
+            return chain, None, [chain]
+        taps = O.design_lowpass_taps(ntw, Mw)
+        if args.taps == "impulse":
+            taps = np.zeros(ntw, np.int32)
+            taps[ntw // 2] = 32767
+        elif args.taps == "random":
+            taps = np.random.default_rng(1).integers(-32767, 32768, ntw).astype(np.int32)
+        d = S.FilterDnsamplingFir(Mw, taps, channels=Cc, device=local_rank, obsolete=True)
+        d.set_kernel(args.kernel)
+        chain, stateful = d, [d]
+        if wk["mix"]:
+            mix = S.Mixer(channels=Cc, device=local_rank)
+            mix.setFrequency(lo_freqs(ch, total_ch))
+            d2 = None
+            if wk["kind"] == "ddc2":
+                d2 = S.FilterDnsamplingFir(wk["M2"], O.design_lowpass_taps(wk["ntaps2"], wk["M2"]), channels=Cc,
+                                           device=local_rank, obsolete=True)
+                stateful.append(d2)
+            chain = S.Ddc(mix, d, d2)
+        return chain, d, stateful
+
+    def kernel_name(wk, d):
+        if d is not None:
+            return d.last_kernel
+        return "mixer_seq_kernel" if wk["kind"] == "mix" else "up_fir4_kernel<8,true>" if wk["kind"] == "up" else "up_fir_kernel"
+
     peak, peak_src = peaks()
-    k_ms = float(np.mean(step_ms))
-    alg_bytes = bytes_per_out(w) * C * n_out
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(args.workload)
-    roof = {"bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-            "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / peak, "traffic": traffic,
-            "kernel": dec.last_kernel if dec is not None else ("mixer_kernel" if w["kind"] == "mix" else "up_fir4_kernel<8,true>" if w["kind"] == "up" else "up_fir_kernel"), "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-            "kernel_ms": k_ms,
-            "imad_note": "imad_frac = the same work counted as 2*taps INT32 multiply-adds per output against "
-                         "148 SM x 64 IMAD/clk x sm_max_mhz: the ceiling of any CUDA-core kernel (SURVEY.md 8(d)); "
-                         "the tcgen05 int8 kernel is not bound by it"}
-    # north_star quotes the roofline "against B200's ~8 TB/s": the same achieved rate against the nominal figure as well
-    roof["spec_peak"] = 8000.0
-    roof["frac_of_spec"] = roof["achieved"] / 8000.0
-    if clocks and clocks.get("sm_max_mhz"):
-        imad_peak = 148 * 64 * clocks["sm_max_mhz"] * 1e6
-        macs = {"dec": 2 * nt, "ddc": 2 * nt + 4 * M, "up": 2 * nt / M, "mix": 4,
-                "ddc2": w.get("M2", 1) * (2 * nt + 4 * M) + 2 * w.get("ntaps2", 0)}[w["kind"]]
-        roof["imad_frac"] = macs * C * n_out / (k_ms * 1e-3) / imad_peak
 
-    # ---- the same batch through the fused NCO mixer + decimator (north_star's "256-channel mix + decimate-by-16
-    #      DDC"): kernel-only, reported beside the headline as an extra object ----
-    ddc_extra = None
+    def roofline_of(name, wk, d, n_out_rank, k_ms, clocks):
+        alg_bytes = bytes_per_out(wk) * n_out_rank
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(name)
+        roof = {"bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / peak, "traffic": traffic, "kernel": kernel_name(wk, d),
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms,
+                "binding": BINDING.get(name),
+                "imad_note": "imad_frac = the same work counted as 2*taps INT32 multiply-adds per output against "
+                             "148 SM x 64 IMAD/clk x sm_max_mhz: the ceiling of any CUDA-core kernel (SURVEY.md 8(d)); "
+                             "the tcgen05 int8 kernel is not bound by it"}
+        if wk["kind"] == "ddc2":
+            roof["traffic_model_bytes_per_launch"] = traffic_model_bytes_per_out(wk) * n_out_rank
+            roof["note"] = ("algorithmic bytes follow SURVEY.md 8(d) (132 B per output); the chain also writes and re-reads the "
+                            "stage-1 stream (8 * M2 = 32 B per output more, traffic_model_bytes_per_launch)")
+        # north_star quotes the roofline "against B200's ~8 TB/s": the same achieved rate against the nominal figure as well
+        roof["spec_peak"] = 8000.0
+        roof["frac_of_spec"] = roof["achieved"] / 8000.0
+        if clocks and clocks.get("sm_max_mhz"):
+            imad_peak = 148 * 64 * clocks["sm_max_mhz"] * 1e6
+            ntw, Mw = wk["ntaps"], wk["M"]
+            macs = {"dec": 2 * ntw, "ddc": 2 * ntw + 4 * Mw, "up": 2 * ntw / Mw, "mix": 4,
+                    "ddc2": wk.get("M2", 1) * (2 * ntw + 4 * Mw) + 2 * wk.get("ntaps2", 0)}[wk["kind"]]
+            roof["imad_frac"] = macs * n_out_rank / (k_ms * 1e-3) / imad_peak
+        return roof
+
+    # ------------------------------------------------------------------------------------------
+    # multi-GPU workloads that SHARD a fixed job (strong scaling): cfg3 = 1024 channels dealt to the ranks in
+    # contiguous batches; cfg5 = ONE 2^32-sample stream cut into time slices with a warm-up halo
+    # ------------------------------------------------------------------------------------------
+    if args.workload == "cfg5":
+        return stream_bench(args, w, base, S, O, torch, dist, rank, world, local_rank, timed, roofline_of, time_slices)
+    strong = args.workload == "cfg3"
+    total_ch = C if strong else C * world
+    my_ch = channel_shard(total_ch, world, rank)
+    Cr = len(my_ch)
+    n_out = int(n * out_per_in(w))
+    x = torch.empty((Cr, n, 2), dtype=torch.int16, device="cuda")
+    y = torch.empty((Cr, n_out, 2), dtype=torch.int16, device="cuda")
+    S.synth_fill(x, SEED, ch0=my_ch.start, amp_shift=2)
+    chain, dec, stateful = build_chain(w, my_ch, total_ch)
+    m = timed(lambda: chain.step(x, out=y), args.steps, args.warmup)
+    n_out_total = total_ch * n_out
+    value = n_out_total * args.steps / (m["total_ms"] * 1e-3) / 1e6
+    roof = roofline_of(args.workload, w, dec, Cr * n_out, m["k_ms"], m["clocks"])
+    base["scaling"] = "strong" if strong else "weak"
+    if strong:
+        base["config"]["channels_total"] = total_ch
+        base["config"]["channels_per_gpu"] = Cr
+        base["config"]["sharding"] = "1024 channels in contiguous batches per rank (strong scaling), no collective"
+
+    # ---- side measurements on the same device-resident batch (kernel-only, each with its own clocks record):
+    #      ddc16 = north_star's "256-channel mix + decimate-by-16 DDC"; cfg3 / cfg4 / cfg5 = the other BASELINE configs
+    #      at their single-GPU shapes; "sustained" = the headline and ddc16 over a run long enough for the power cap ----
+    side, ddc_extra = {}, None
     if args.workload == "cfg2" and not args.no_ddc:
-        try:
-            mix2 = S.Mixer(channels=C, device=local_rank)
-            mix2.setFrequency((-1 + 2 * (np.arange(my_ch.start, my_ch.stop) + 0.5) / (C * world)).astype(np.float32))
-            dec2 = S.FilterDnsamplingFir(M, O.design_lowpass_taps(nt, M), channels=C, device=local_rank, obsolete=True)
-            dec2.set_kernel(args.kernel)
-            ddc = S.Ddc(mix2, dec2)
-            for _ in range(args.warmup):
-                ddc.step(x, out=y)
-            barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(args.steps):
-                ddc.step(x, out=y)
-            e1.record()
-            barrier()
-            tm = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-            if dist:
-                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-            ms = float(tm.item()) / args.steps
-            ddc_extra = {"workload": WORKLOADS["ddc16"]["desc"], "value": n_out_total / (ms * 1e-3) / 1e6, "unit": "Msamples/s",
-                         "ms_per_step": ms, "kernel": dec2.last_kernel,
-                         "roofline_frac": alg_bytes / (ms * 1e-3) / 1e9 / peak,
-                         "note": "same input batch and algorithmic bytes as the headline; the mixer adds 4 int32 multiply-adds, "
-                                 "a shift and a saturating pack per input sample in the kernel's load stage"}
-            del ddc, dec2, mix2
-        except Exception as ex:  # report, never fake
-            ddc_extra = {"value": None, "error": str(ex)[:200]}
+        def side_run(name, views, steps=None, warmup=None, settle=1.0):
+            wk = WORKLOADS[name]
+            ch = channel_shard(wk["channels"] * world, world, rank)
+            try:
+                xs, ys = views(wk)
+                c2, d2, _ = build_chain(wk, ch, wk["channels"] * world)
+                mm = timed(lambda: c2.step(xs, out=ys), steps or args.steps, warmup or args.warmup, settle)
+                nout = wk["channels"] * int(wk["n"] * out_per_in(wk))
+                rf = roofline_of(name, wk, d2, nout, mm["k_ms"], mm["clocks"])
+                return {"workload": wk["desc"], "value": nout * world / (mm["ms"] * 1e-3) / 1e6, "unit": "Msamples/s",
+                        "ms_per_step": mm["ms"], "steps": steps or args.steps, "kernel": rf["kernel"], "roofline_frac": rf["frac"],
+                        "frac_of_spec": rf["frac_of_spec"], "binding": rf["binding"], "clocks": mm["clocks"],
+                        "algorithmic_bytes_per_launch": rf["algorithmic_bytes_per_launch"],
+                        "settle_s": settle}
+            except Exception as ex:  # report, never fake
+                return {"value": None, "error": str(ex)[:200]}
+
+        flat = x.view(-1)  # the 16 GiB batch, re-viewed for the other shapes (fresh synthetic data where the shape differs)
+
+        def in_view(wk):
+            return flat[: wk["channels"] * wk["n"] * 2].view(wk["channels"], wk["n"], 2)
+
+        def dec_views(wk):
+            xs = in_view(wk)
+            if (wk["channels"], wk["n"]) != (C, n):
+                S.synth_fill(xs, SEED, ch0=0, amp_shift=2)
+            return xs, y.view(-1)[: wk["channels"] * int(wk["n"] * out_per_in(wk)) * 2].view(wk["channels"], -1, 2)
+
+        def up_views(wk):
+            xs = in_view(wk)
+            return xs, torch.empty((wk["channels"], wk["n"] * wk["M"], 2), dtype=torch.int16, device="cuda")
+
+        ddc_extra = side_run("ddc16", dec_views)
+        ddc_extra["note"] = ("same input batch and algorithmic bytes as the headline; the mixer adds 4 int32 multiply-adds, a shift "
+                             "and a saturating pack per input sample in the kernel's load stage")
+        side["cfg3"] = side_run("cfg3", dec_views)
+        side["cfg5_slice"] = side_run("cfg5", dec_views)
+        side["cfg4"] = side_run("cfg4", up_views)
+        S.synth_fill(x, SEED, ch0=my_ch.start, amp_shift=2)  # the headline's batch again (for e2e)
+        sus = max(100, 4 * args.steps)
+        side["sustained"] = {
+            "note": f"{sus} steps back to back (~0.4 s): long enough for the boxes' 1 kW software power cap to lower the SM clock; "
+                    "the numbers above are the first tens of milliseconds after an idle second",
+            "cfg2": side_run("cfg2", dec_views, steps=sus, settle=0.0),
+            "ddc16": side_run("ddc16", dec_views, steps=sus, settle=0.0)}
 
     # ---- e2e: public API with pinned HOST buffers, H2D + kernels + D2H inside the timed region ----
     e2e = None
@@ -625,15 +834,15 @@ def main():
             # every rank pins its whole batch (17 GiB for cfg2); with many ranks on one host check that it fits
             try:
                 import psutil
-                need = world * (C * n + C * n_out) * 4
+                need = world * (Cr * n + Cr * n_out) * 4
                 if psutil.virtual_memory().available < 1.3 * need:
                     raise MemoryError(f"host has {psutil.virtual_memory().available >> 30} GiB available, "
                                       f"{need >> 30} GiB of pinned staging needed for {world} ranks")
             except ImportError:
                 pass
-            hin = S.PinnedBuffer(C, n)
-            hout = S.PinnedBuffer(C, n_out)
-            S._capi.check(S.lib().srcdsp_memcpy(local_rank, hin.array.ctypes.data, x.data_ptr(), C * n * 4))
+            hin = S.PinnedBuffer(Cr, n)
+            hout = S.PinnedBuffer(Cr, n_out)
+            S._capi.check(S.lib().srcdsp_memcpy(local_rank, hin.array.ctypes.data, x.data_ptr(), Cr * n * 4))
             del x
             torch.cuda.empty_cache()
             chain.step(hin.array, out=hout.array)  # warm the staging buffers
@@ -644,17 +853,16 @@ def main():
             for _ in range(args.e2e_steps):
                 chain.step(hin.array, out=hout.array)  # returns when the output is in host memory
             barrier()
-            dt = time.perf_counter() - t0
-            tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-            if dist:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt.item())
+            dt = all_max(time.perf_counter() - t0)
             e2e = {"value": n_out_total * args.e2e_steps / dt / 1e6, "unit": "Msamples/s",
-                   "h2d_bytes_per_step": C * n * 4, "d2h_bytes_per_step": C * n_out * 4,
+                   "h2d_bytes_per_step": Cr * n * 4, "d2h_bytes_per_step": Cr * n_out * 4,
                    "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
+                   "h2d_gbs_per_gpu": Cr * n * 4 * args.e2e_steps / dt / 1e9,
                    "api": type(chain).__name__ + ".step(host numpy view of pinned memory) -> C ABI step"}
             if numa:
                 e2e["numa_binding_rank0"] = numa
+            if args.h2d_ceiling:
+                e2e["h2d_ceiling"] = h2d_ceiling(torch, S, local_rank, dist, barrier, all_max)
             hin.free()
             hout.free()
         except Exception as ex:  # report, never fake
@@ -668,10 +876,11 @@ def main():
             cpu = {"value": None, "error": str(ex)[:200]}
 
     if rank == 0:
-        line = dict(base, value=value, ms_per_step=total_ms / args.steps, roofline=roof, cpu_baseline=cpu, e2e=e2e,
-                    clocks=clocks, gpu_launches=int(launches), impl="ours")
+        line = dict(base, value=value, ms_per_step=m["total_ms"] / args.steps, roofline=roof, cpu_baseline=cpu, e2e=e2e,
+                    clocks=m["clocks"], gpu_launches=m["launches"], impl="ours")
         if ddc_extra is not None:
             line["ddc16"] = ddc_extra
+            line["side"] = side
         if args.workload == "cfg1" and world == 1 and not args.no_cpu:
             try:
                 line["cpu_baseline_variants"] = cpu_cfg1_variants(w)

@@ -46,6 +46,7 @@ typedef struct srcdsp_ddc_s *srcdsp_ddc_t;
 typedef struct srcdsp_fifo_s *srcdsp_fifo_t;
 typedef struct srcdsp_corr_s *srcdsp_corr_t;
 typedef struct srcdsp_decf_s *srcdsp_decf_t;
+typedef struct srcdsp_group_s *srcdsp_group_t;
 
 /* ------------------------------------------------------------------------------------------ */
 /* library                                                                                    */
@@ -175,6 +176,41 @@ int srcdsp_ddc_step(srcdsp_ddc_t h, const int16_t *in_iq, size_t in_stride, size
                     int16_t *out_iq, size_t out_stride);
 int srcdsp_ddc_set_stream(srcdsp_ddc_t h, void *cuda_stream);
 int srcdsp_ddc_sync(srcdsp_ddc_t h);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Device group: ONE chain (mixer -> dec1 [-> dec2]) spread over several GPUs of one box and    */
+/* driven from one process -- the reference has no such object; a user of it runs one           */
+/* Mixer / FilterDnsamplingFir set per stream on one thread.  No collective   */
+/* and no peer traffic: every device gets its own banks and, during a step, its own host       */
+/* thread that stages ITS part of the caller's HOST buffers (pinned for speed:                 */
+/* srcdsp_host_alloc) and writes its outputs to their final place in the caller's output.      */
+/*   SRCDSP_GROUP_CHANNELS  independent channels: member g owns the contiguous channel batch   */
+/*       [C*g/G, C*(g+1)/G) (balanced) together with its streaming state.                      */
+/*   SRCDSP_GROUP_SLICES    one (or a few) very long stream(s): every member holds all         */
+/*       channels; a block is cut into G time slices at multiples of the total decimation;     */
+/*       slice g > 0 is preceded by a warm-up run over the (N1-1) + (N2-1)*M1 samples in front */
+/*       of it (rounded up to the total decimation, outputs discarded) starting from zero      */
+/*       history and the closed-form NCO phase, so that outputs, history and phase equal the   */
+/*       reference's sequential run bit for bit (dsptl_dnsampling_filters.h:198-205,218-219;   */
+/*       mixers.h:177).  Blocks too short for that use fewer members.  Between calls the        */
+/*       stream's state lives in member 0's banks.                                             */
+/* devices[] may name a device more than once (several members on one GPU).  n_table == 0:      */
+/* no mixer; M2 == 0: a single decimator.  Calls mirror the chain's: set_coeffs(stage 1 | 2),  */
+/* set_frequencies([channels]), reset, step (n_in_per_ch % (M1*M2) == 0, returns when every     */
+/* output is in host memory).                                                                  */
+#define SRCDSP_GROUP_CHANNELS 0
+#define SRCDSP_GROUP_SLICES 1
+int srcdsp_group_create(srcdsp_group_t *h, int mode, const int *devices, int n_devices, int channels, unsigned n_table,
+                        int M1, int M2);
+int srcdsp_group_destroy(srcdsp_group_t h);
+int srcdsp_group_set_coeffs(srcdsp_group_t h, int stage, const int32_t *taps, int ntaps, int require_multiple_of_m);
+int srcdsp_group_set_frequencies(srcdsp_group_t h, const float *lo_freq);
+int srcdsp_group_reset(srcdsp_group_t h);
+int srcdsp_group_step(srcdsp_group_t h, const int16_t *in_iq, size_t in_stride, size_t n_in_per_ch, int16_t *out_iq,
+                      size_t out_stride);
+/* member `index`: its device and channel batch; number of members and how many the last step used */
+int srcdsp_group_get_layout(srcdsp_group_t h, int index, int *device, int *ch0, int *n_channels);
+int srcdsp_group_size(srcdsp_group_t h, int *n_members, int *used_in_last_step);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Upsampler bank -- dsptl::FilterUpsamplingFir<cs16, cs16, cs32, int32_t, L>                 */

@@ -25,7 +25,7 @@ import numpy as np
 from . import _capi
 from ._capi import SrcDspError, check, lib
 
-__all__ = ["Mixer", "FilterDnsamplingFir", "FilterDnsamplingFirFloat", "FilterFirFloat", "FilterFir", "FilterUpsamplingFir", "Ddc", "SrcDspError",
+__all__ = ["DdcGroup", "Mixer", "FilterDnsamplingFir", "FilterDnsamplingFirFloat", "FilterFirFloat", "FilterFir", "FilterUpsamplingFir", "Ddc", "SrcDspError",
            "synth_fill", "launch_count", "device_count", "PinnedBuffer", "FifoWithTimeTrack", "saveBinarySamples",
            "readBinarySamples", "FixedPatternCorrelator"]
 
@@ -461,6 +461,59 @@ class Ddc(_Handle):
 
     def sync(self):
         check(lib().srcdsp_ddc_sync(self._h))
+
+
+class DdcGroup(_Handle):
+    """One chain (mixer -> dec1 [-> dec2]) over several GPUs of one box, driven from this process (srcdsp_group_*):
+    mode "channels" = contiguous channel batches per device, mode "slices" = time slices of one long stream with a
+    warm-up halo.  Buffers are HOST numpy arrays (views of PinnedBuffer for speed); every device copies its own part
+    and writes its outputs to their final place in `out`."""
+
+    _destroy = "srcdsp_group_destroy"
+
+    def __init__(self, mode: str, devices: Sequence[int], channels: int, M1: int, taps1, M2: int = 0, taps2=None,
+                 n_table: int = 0, obsolete: bool = True):
+        super().__init__()
+        dv = (C.c_int * len(devices))(*devices)
+        self.mode, self.channels, self.M = mode, channels, M1 * (M2 if M2 else 1)
+        check(lib().srcdsp_group_create(C.byref(self._h), {"channels": 0, "slices": 1}[mode], dv, len(devices), channels,
+                                        n_table, M1, M2))
+        t = _taps(taps1)
+        check(lib().srcdsp_group_set_coeffs(self._h, 1, t.ctypes.data_as(C.POINTER(C.c_int32)), t.size, 0 if obsolete else 1))
+        if M2:
+            t = _taps(taps2)
+            check(lib().srcdsp_group_set_coeffs(self._h, 2, t.ctypes.data_as(C.POINTER(C.c_int32)), t.size, 0 if obsolete else 1))
+
+    def setFrequency(self, loFreq):
+        f = np.ascontiguousarray(np.broadcast_to(np.asarray(loFreq, np.float32), (self.channels,)))
+        check(lib().srcdsp_group_set_frequencies(self._h, f.ctypes.data_as(C.POINTER(C.c_float))))
+
+    def reset(self):
+        check(lib().srcdsp_group_reset(self._h))
+
+    def layout(self):
+        n, used = C.c_int(), C.c_int()
+        check(lib().srcdsp_group_size(self._h, C.byref(n), C.byref(used)))
+        out = []
+        for i in range(n.value):
+            d, c0, nc = C.c_int(), C.c_int(), C.c_int()
+            check(lib().srcdsp_group_get_layout(self._h, i, C.byref(d), C.byref(c0), C.byref(nc)))
+            out.append((d.value, c0.value, nc.value))
+        return out, used.value
+
+    def step(self, x, out=None):
+        bi = _Buf(x, self.channels)
+        if bi.device:
+            raise TypeError("a DdcGroup takes host buffers")
+        if bi.n % self.M:
+            raise SrcDspError(_capi.E_SIZE, f"n_in ({bi.n}) must be a multiple of {self.M}")
+        if out is None:
+            out = _alloc_like(x, self.channels, bi.n // self.M, bi.squeeze)
+        bo = _Buf(out, self.channels)
+        if bo.n * self.M != bi.n:
+            raise SrcDspError(_capi.E_SIZE, "out.size() * M_total != in.size()")
+        check(lib().srcdsp_group_step(self._h, bi.ptr, bi.stride, bi.n, bo.ptr, bo.stride))
+        return out
 
 
 # ----------------------------------------------------------------------------------------------

@@ -77,6 +77,15 @@ PROTOTYPES = {
     "srcdsp_ddc_step": (C.c_int, [_vp, _i16p, _sz, _sz, _i16p, _sz]),
     "srcdsp_ddc_set_stream": (C.c_int, [_vp, _vp]),
     "srcdsp_ddc_sync": (C.c_int, [_vp]),
+    # device group (one chain over several GPUs, one process)
+    "srcdsp_group_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_uint, C.c_int, C.c_int]),
+    "srcdsp_group_destroy": (C.c_int, [_vp]),
+    "srcdsp_group_set_coeffs": (C.c_int, [_vp, C.c_int, _i32p, C.c_int, C.c_int]),
+    "srcdsp_group_set_frequencies": (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    "srcdsp_group_reset": (C.c_int, [_vp]),
+    "srcdsp_group_step": (C.c_int, [_vp, _i16p, _sz, _sz, _i16p, _sz]),
+    "srcdsp_group_get_layout": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "srcdsp_group_size": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     # upsampler
     "srcdsp_up_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int]),
     "srcdsp_up_destroy": (C.c_int, [_vp]),

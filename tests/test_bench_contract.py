@@ -30,6 +30,9 @@ def test_reference_arm_line():
     e = line["e2e"]
     assert e == {"value": line["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["config"]["workload"].startswith("cfg2")
+    # the config object is exactly the GPU arm's (the driver compares them); remarks about the arm live beside it
+    assert set(line["config"]) == {"workload", "channels_per_gpu", "samples_per_channel", "ratio", "taps", "nco_mix", "sharding", "l2"}
+    assert "bounded sample" in line["note"]
     assert line["vs_baseline"] is None and line["data"] == "synthetic"
 
 
