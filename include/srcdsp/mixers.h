@@ -13,28 +13,25 @@
 
 namespace dsptl {
 
+/* dsptl::_Mixer (mixers.h:26-41): the base that carries frequency and phase.  Same template parameters and public
+ * members; the protected data members of the reference (phi, freq, nominalFreq, ptable) live in the GPU bank here,
+ * so a class derived from _Mixer reaches them through state() / set_state() instead of by name.  PhaseType must be
+ * able to hold N (reference :23-25); the table has N entries of amplitude 16383 (mixers.h:149-160). */
 template <class InType, class OutType, class PhaseType, unsigned N = 4096>
-class Mixer;  // like the reference, the primary template is only declared (mixers.h:120-121)
-
-template <unsigned N>
-class Mixer<std::complex<int16_t>, std::complex<int16_t>, int16_t, N> {
+class _Mixer {
 public:
-    /* mixers.h:149-160: builds the N-entry sine table; phase and frequency start at zero */
-    Mixer() : h_(nullptr)
+    _Mixer() : h_(nullptr) { srcdsp_dropin::check(srcdsp_mixer_create(&h_, srcdsp_dropin::default_device(), 1, N), "_Mixer()"); }
+    _Mixer(const _Mixer &o) : h_(nullptr)
     {
-        srcdsp_dropin::check(srcdsp_mixer_create(&h_, srcdsp_dropin::default_device(), 1, N), "Mixer()");
-    }
-    Mixer(const Mixer &o) : h_(nullptr)
-    {
-        srcdsp_dropin::check(srcdsp_mixer_create(&h_, srcdsp_dropin::default_device(), 1, N), "Mixer(copy)");
+        srcdsp_dropin::check(srcdsp_mixer_create(&h_, srcdsp_dropin::default_device(), 1, N), "_Mixer(copy)");
         copy_state(o);
     }
-    Mixer &operator=(const Mixer &o)
+    _Mixer &operator=(const _Mixer &o)
     {
         if (this != &o) copy_state(o);
         return *this;
     }
-    ~Mixer() { srcdsp_mixer_destroy(h_); }
+    ~_Mixer() { srcdsp_mixer_destroy(h_); }
 
     /* mixers.h:51-67 */
     void setFrequency(float loFreq) { srcdsp_dropin::check(srcdsp_mixer_set_frequency(h_, 0, loFreq), "Mixer::setFrequency"); }
@@ -45,21 +42,23 @@ public:
     {
         srcdsp_dropin::check(srcdsp_mixer_adjust_frequency(h_, 0, loFreq), "Mixer::adjustFrequency");
     }
-    /* mixers.h:168-188: out must hold at least in.size() samples; out may be in */
-    void step(std::vector<std::complex<int16_t>> &in, std::vector<std::complex<int16_t>> &out)
-    {
-        if (in.empty()) return;
-        srcdsp_dropin::check(out.size() >= in.size() ? SRCDSP_OK : SRCDSP_E_SIZE, "Mixer::step (out too small)");
-        srcdsp_dropin::check(srcdsp_mixer_step(h_, srcdsp_dropin::iq(in), in.size(), srcdsp_dropin::iq(out),
-                                               out.size(), in.size()),
-                             "Mixer::step");
-    }
 
     /* extension: the C-ABI handle, e.g. to build a fused srcdsp_ddc chain */
     srcdsp_mixer_t handle() const { return h_; }
 
-private:
-    void copy_state(const Mixer &o)
+protected:
+    /* the reference's protected phi / freq / nominalFreq */
+    void state(PhaseType &phi, PhaseType &freq, float &nominalFreq) const
+    {
+        int p, f;
+        srcdsp_dropin::check(srcdsp_mixer_get_state(h_, 0, &p, &f, &nominalFreq), "_Mixer::state");
+        phi = static_cast<PhaseType>(p), freq = static_cast<PhaseType>(f);
+    }
+    void set_state(PhaseType phi, PhaseType freq, float nominalFreq)
+    {
+        srcdsp_dropin::check(srcdsp_mixer_set_state(h_, 0, (int)phi, (int)freq, nominalFreq), "_Mixer::set_state");
+    }
+    void copy_state(const _Mixer &o)
     {
         int phi, freq;
         float nominal;
@@ -67,6 +66,30 @@ private:
         srcdsp_dropin::check(srcdsp_mixer_set_state(h_, 0, phi, freq, nominal), "Mixer copy");
     }
     srcdsp_mixer_t h_;
+};
+
+template <class InType, class OutType, class PhaseType, unsigned N>
+class Mixer;  // like the reference, the primary template is only declared (mixers.h:120-121)
+
+/* mixers.h:130-137: the one specialisation the reference defines, derived from _Mixer like there */
+template <unsigned N>
+class Mixer<std::complex<int16_t>, std::complex<int16_t>, int16_t, N>
+    : public dsptl::_Mixer<std::complex<int16_t>, std::complex<int16_t>, int16_t, N> {
+    typedef dsptl::_Mixer<std::complex<int16_t>, std::complex<int16_t>, int16_t, N> Base;
+
+public:
+    /* mixers.h:149-160: builds the N-entry sine table; phase and frequency start at zero */
+    Mixer() : Base() {}
+
+    /* mixers.h:168-188: out must hold at least in.size() samples; out may be in */
+    void step(std::vector<std::complex<int16_t>> &in, std::vector<std::complex<int16_t>> &out)
+    {
+        if (in.empty()) return;
+        srcdsp_dropin::check(out.size() >= in.size() ? SRCDSP_OK : SRCDSP_E_SIZE, "Mixer::step (out too small)");
+        srcdsp_dropin::check(srcdsp_mixer_step(this->h_, srcdsp_dropin::iq(in), in.size(), srcdsp_dropin::iq(out),
+                                               out.size(), in.size()),
+                             "Mixer::step");
+    }
 };
 
 }  // namespace dsptl

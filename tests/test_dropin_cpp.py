@@ -126,3 +126,20 @@ def test_float_program_dropin_build_prints_the_reference_output(built_lib):
     _compile_dropin(exe, SRC_FLOAT)
     out = subprocess.run([exe], check=True, capture_output=True, text=True, timeout=300).stdout
     assert out == open(GOLDEN_FLOAT).read()
+
+
+def test_mixer_base_class_is_exported(built_lib):
+    """dsptl::_Mixer (reference mixers.h:26-41) exists with the same template parameters and public members: a class
+    derived from it compiles against both header trees."""
+    os.makedirs(BUILD, exist_ok=True)
+    src = os.path.join(BUILD, "user_mixer_base.cpp")
+    open(src, "w").write(
+        "#include <cassert>\n#include <cmath>\n#include <complex>\n#include <cstdint>\n#include <vector>\n#include \"mixers.h\"\n"
+        "typedef std::complex<int16_t> cs16;\n"
+        "struct Lo : dsptl::_Mixer<cs16, cs16, int16_t, 1024> {};\n"
+        "int main() { Lo m; m.setFrequency(0.25f); m.adjustFrequency(-0.1f); m.reset(); m.reset(0.5f);\n"
+        "  dsptl::Mixer<cs16, cs16, int16_t, 1024> x; dsptl::_Mixer<cs16, cs16, int16_t, 1024> &b = x; b.setFrequency(-0.5f); return 0; }\n")
+    _compile_dropin(os.path.join(BUILD, "user_mixer_base_gpu"), src)
+    if os.path.exists(os.path.join(REF, "mixers.h")):
+        subprocess.run(["g++", "-std=gnu++11", "-O1", "-w", "-I" + REF, src, os.path.join(REF, "dsp_complex.cpp"), "-o",
+                        os.path.join(BUILD, "user_mixer_base_ref")], check=True, capture_output=True, text=True)
