@@ -121,10 +121,12 @@ int srcdsp_dec_set_stream(srcdsp_dec_t h, void *cuda_stream);
 int srcdsp_dec_sync(srcdsp_dec_t h);
 /* kernel selection: 0 = automatic, 1 = force the INT32-FMA (IMAD) kernel, 2 = force the
  * tcgen05 int8 Toeplitz kernel (E_STATE at step if the taps do not fit it; TMA-fed when the input
- * rows are 16-byte aligned, register-staged loads otherwise), 3 = force its register-staged variant. */
+ * rows are 16-byte aligned -- in the band form where that applies --, register-staged loads otherwise),
+ * 3 = force its register-staged variant, 4 = force the band form (dec_band_kernel: even M,
+ * ntaps <= 32 M + 1), 5 = force the TMA-fed kernel in its original form (dec_tma_kernel). */
 int srcdsp_dec_set_kernel(srcdsp_dec_t h, int kind);
 /* which FIR kernel the last step launched: 0 none yet, 1 IMAD (dec_fir_kernel), 2 tcgen05 with
- * register-staged loads (dec_tc_kernel), 3 tcgen05 fed by TMA (dec_tma_kernel) */
+ * register-staged loads (dec_tc_kernel), 3 tcgen05 fed by TMA (dec_tma_kernel), 4 its band form (dec_band_kernel) */
 int srcdsp_dec_get_last_kernel(srcdsp_dec_t h, int *kind);
 
 /* ------------------------------------------------------------------------------------------ */

@@ -201,7 +201,8 @@ class FilterDnsamplingFir(_Handle):
         v = C.c_int()
         check(lib().srcdsp_dec_get_last_kernel(self._h, C.byref(v)))
         return {0: "none", 1: "dec_fir_kernel (IMAD)", 2: "dec_tc_kernel (tcgen05 int8, LDG producers)",
-                3: "dec_tma_kernel (tcgen05 int8, TMA-fed)"}[v.value]
+                3: "dec_tma_kernel (tcgen05 int8, TMA-fed)",
+                4: "dec_band_kernel (tcgen05 int8, TMA-fed, band form)"}[v.value]
 
     @property
     def coeffScaling(self) -> int:

@@ -18,6 +18,7 @@
 #include "kernels_dec.cuh"
 #include "kernels_dec_tc.cuh"
 #include "kernels_dec_tma.cuh"
+#include "kernels_dec_band.cuh"
 #include "kernels_up.cuh"
 #include "kernels_up_tc.cuh"
 #include "kernels_corr.cuh"
@@ -68,6 +69,7 @@ struct Tuning {
     int pf_dist = -1;      // SRCDSP_PF_DIST      dec_tc_kernel's L2 prefetch distance
     int verbose = 0;       // SRCDSP_TMA_VERBOSE  print the chosen shared-memory plan
     int seq_period = -1;   // SRCDSP_SEQ_PERIOD   0: always the full-table oscillator sequence
+    int band = -1;         // SRCDSP_BAND         0: never the band form (dec_band_kernel), 1: whenever applicable
     int up_tc = -1;        // SRCDSP_UP_TC        tcgen05 interpolator on (1) / off (0)
     int up_tc_form = 0;    // SRCDSP_UP_TC_FORM   2: operand-swapped form
     int up_generic = 0;    // SRCDSP_UP_GENERIC
@@ -99,6 +101,7 @@ static Tuning tuning_from_env()
     get("SRCDSP_PF_DIST", v.pf_dist);
     v.verbose = getenv("SRCDSP_TMA_VERBOSE") != nullptr;
     get("SRCDSP_SEQ_PERIOD", v.seq_period);
+    get("SRCDSP_BAND", v.band);
     get("SRCDSP_UP_TC", v.up_tc);
     get("SRCDSP_UP_TC_FORM", v.up_tc_form);
     v.up_generic = getenv("SRCDSP_UP_GENERIC") != nullptr;
@@ -590,6 +593,28 @@ struct DecBank : Bank {
     bool tc_want_p2 = false;
     int tc_mix_table = 32768;                 // shared-memory bytes of the oscillator sequence the mixer variant was planned for
     int build_variant(int variant, bool p2, int mix_table);
+    // band form (kernels_dec_band.cuh): samples on the M side, a band of the taps on the N side, lags merged
+    TcParams tc_band{};
+    BandExtra band{};
+    bool band_ok = false;
+    uint8_t *d_master_band = nullptr;
+    size_t band_fixed = 0;
+    int build_band();
+    int band_layout(int table_bytes, int groups, int *n_raw, int *n_stages, size_t *smem) const
+    {
+        const size_t avail = (size_t)226 * 1024;
+        if (band_fixed + (size_t)table_bytes + 2 * (size_t)BAND_STAGE_BYTES + 2 * (size_t)BAND_RAW_BYTES > avail) return SRCDSP_E_SIZE;
+        int ns = groups + 1;
+        if (tune.tma_stages > 0) ns = std::max(2, std::min(tune.tma_stages, TC_MAX_STAGES));
+        while (ns > 2 && band_fixed + (size_t)table_bytes + (size_t)ns * BAND_STAGE_BYTES + 4 * (size_t)BAND_RAW_BYTES > avail) --ns;
+        int nr = (int)((avail - band_fixed - (size_t)table_bytes - (size_t)ns * BAND_STAGE_BYTES) / BAND_RAW_BYTES);
+        if (nr > 8) nr = 8;
+        if (nr < 2) return SRCDSP_E_SIZE;
+        if (n_raw) *n_raw = nr;
+        if (n_stages) *n_stages = ns;
+        if (smem) *smem = band_fixed + (size_t)table_bytes + (size_t)ns * BAND_STAGE_BYTES + (size_t)nr * BAND_RAW_BYTES;
+        return SRCDSP_OK;
+    }
     uint8_t *d_master = nullptr, *d_master_tma = nullptr, *d_master_tma_mix = nullptr;
     size_t tc_fixed_tma = 0, tc_fixed_tma_mix = 0;
     int *d_error = nullptr;  // wait-cycle counters of the timing variants (device)
@@ -735,6 +760,7 @@ struct DecBank : Bank {
         if (d_master) cudaFree(d_master);
         if (d_master_tma) cudaFree(d_master_tma);
         if (d_master_tma_mix) cudaFree(d_master_tma_mix);
+        if (d_master_band) cudaFree(d_master_band);
         if (d_error) cudaFree(d_error);
         if (h_diag) cudaFreeHost(h_diag);
     }
@@ -904,6 +930,93 @@ int DecBank::build_variant(int variant, bool p2, int mix_table)
     return SRCDSP_OK;
 }
 
+// The band form's tap operand and MMA plan (kernels_dec_band.cuh).  One master copy per residue r = (32 kc) mod M:
+// row 4 (u + UOFF) + w holds, for the 32 samples t of a K-step, the digit d_w[M u - t - r] of the tap that output
+// (a + u) of the row-block applies to sample t (a = (32 kc) / M); rows outside the filter's support are zero.  The plan
+// gives, per K-step, the window of outputs the K-step meets: the first master row (lo plane; the hi plane reads one row
+// earlier = one weight slot up), the MMA's N and its first accumulator column.
+int DecBank::build_band()
+{
+    band_ok = false;
+    if (d_master_band) {
+        DeviceGuard g0(device);
+        cudaFree(d_master_band);
+        d_master_band = nullptr;
+    }
+    const int P = tc_P;
+    if (M < 2 || (M & 1) || M > TC_MAX_KSTEPS || P > 3) return SRCDSP_OK;
+    const int E = ntaps >= 2 ? (ntaps - 2) / M + 1 : 0;
+    if (E > 32) return SRCDSP_OK;  // the filter reaches more than one row-block back
+    const int G = 32 * M;
+    std::vector<int> residues, copy_of_kc(M);
+    for (int kc = 0; kc < M; ++kc) {
+        const int r = (32 * kc) % M;
+        int idx = -1;
+        for (size_t i = 0; i < residues.size(); ++i)
+            if (residues[i] == r) idx = (int)i;
+        if (idx < 0) {
+            idx = (int)residues.size();
+            residues.push_back(r);
+        }
+        copy_of_kc[kc] = idx;
+    }
+    const int a_rows = 4 * (64 + 2 * BAND_UOFF);
+    const size_t copy_bytes = (size_t)a_rows * 32;
+    const size_t image_bytes = residues.size() * copy_bytes;
+    const size_t master_bytes = image_bytes + (size_t)M * 16;
+    band_fixed = ((master_bytes + 127) & ~(size_t)127) + 2048 + 512;  // + boundary hand-over + mbarriers
+    if (band_fixed + 2 * (size_t)BAND_STAGE_BYTES + 2 * (size_t)BAND_RAW_BYTES > (size_t)226 * 1024) return SRCDSP_OK;
+    std::vector<uint8_t> img(master_bytes, 0);
+    for (size_t ci = 0; ci < residues.size(); ++ci) {
+        uint8_t *base = img.data() + ci * copy_bytes;
+        const int r = residues[ci];
+        for (int row = 0; row < a_rows; ++row) {
+            const int u = row / 4 - BAND_UOFF, w = row % 4;
+            if (w >= P) continue;
+            for (int t = 0; t < 32; ++t) {
+                const long long k = (long long)M * u - t - r;
+                if (k < 0 || k >= ntaps) continue;
+                base[(size_t)(t / 16) * a_rows * 16 + (size_t)row * 16 + (t % 16)] = (uint8_t)tc_dig[w][k];
+            }
+        }
+    }
+    uint32_t *plan = reinterpret_cast<uint32_t *>(img.data() + image_bytes);
+    for (int kc = 0; kc < M; ++kc) {
+        const int a = (32 * kc) / M, r = (32 * kc) % M;
+        int b0, nb;
+        if (kc == 0) {  // first MMA of a tile: all columns, accumulate = 0
+            b0 = 0;
+            nb = (32 + E + 3) & ~3;
+        } else {
+            const int b_lo = a + (r > 0 ? 1 : 0);
+            const int b_hi = std::min(32 + E - 1, (32 * kc + 31 + ntaps - 1) / M);
+            b0 = b_lo & ~1;
+            nb = std::max(4, (b_hi - b0 + 1 + 3) & ~3);
+        }
+        if (b0 + nb > 64) b0 = 64 - nb;
+        const int u0 = b0 - a;
+        if (u0 < -BAND_UOFF + 1 || u0 + nb > 64 + BAND_UOFF || 4 * nb > 256 || b0 < 0) return SRCDSP_OK;  // (cannot happen for E <= 32)
+        const uint32_t addr = (uint32_t)(copy_of_kc[kc] * copy_bytes) + (uint32_t)(4 * (u0 + BAND_UOFF)) * 16;
+        plan[4 * kc + 0] = addr >> 4;
+        plan[4 * kc + 1] = (addr - 16) >> 4;
+        plan[4 * kc + 2] = (uint32_t)(4 * nb);
+        plan[4 * kc + 3] = (uint32_t)(4 * b0);
+    }
+    DeviceGuard g(device);
+    SRCDSP_CUDA(cudaMalloc(&d_master_band, master_bytes));
+    SRCDSP_CUDA(cudaMemcpy(d_master_band, img.data(), master_bytes, cudaMemcpyHostToDevice));
+    TcParams &T = tc_band;
+    T = TcParams{};
+    T.M = M, T.G = G, T.ksteps = M, T.nrb = BAND_NEW, T.J = 2;
+    T.master = d_master_band, T.master_bytes = (int)master_bytes;
+    T.a_rows = a_rows, T.rbp = BAND_RBP;
+    T.error_flag = d_diag, T.counters = d_error;
+    band = BandExtra{};
+    band.E = E, band.a_rows = a_rows, band.ks2 = M / 2, band.plan_off = (int)image_bytes;
+    band_ok = true;
+    return SRCDSP_OK;
+}
+
 // Builds the resident Toeplitz "master" operand and the per-K-step table of the tensor-core
 // kernel (see kernels_dec_tc.cuh for the layout).  Sets tc_ok = false (with a reason) when the
 // taps / ratio do not fit it; the IMAD kernel then handles every case.
@@ -992,6 +1105,9 @@ int DecBank::prepare_tc()
     SRCDSP_TMA_ATTR(16, true);
 #endif
 #undef SRCDSP_TMA_ATTR
+    SRCDSP_CUDA(cudaFuncSetAttribute(dec_band_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    SRCDSP_CUDA(cudaFuncSetAttribute(dec_band_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    SRCDSP_TRY(build_band());
     tc_why = "";
     return SRCDSP_OK;
 }
@@ -1070,7 +1186,7 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
     const long long tc_tiles = (long long)C * ((P.n_out + TC_NRB * TC_BOUT - 1) / (TC_NRB * TC_BOUT));
     int tc_stages = 0;
     size_t tc_smem = 0;
-    bool use_tc = tc_ok && tc_tiles < 0x7fffffffll && (kernel_kind >= 2 || (kernel_kind == 0 && tc_tiles >= sm_count / 2));
+    bool use_tc = tc_ok && tc_tiles < 0x7fffffffll && (kernel_kind >= 2 || (kernel_kind == 0 && tc_tiles >= sm_count / 2));  // (4 / 5: forms of 2)
     const char *why = tc_why;
     if (use_tc && mixer) {
         const PhaseMod pm = mixer->pm();
@@ -1128,7 +1244,76 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
     if (kernel_kind >= 2 && !use_tc)
         return fail(SRCDSP_E_STATE, "tcgen05 kernel forced but not applicable: %s", tc_ok ? why : tc_why);
 
-    if (use_tc) {
+    // band form (kernels_dec_band.cuh): 2x fewer tensor-pipe cycles and ~4x fewer MACs per output than dec_tma_kernel, but
+    // an epilogue of ~28 instead of ~12 instructions per output (32x32b loads, row hand-over, re / im exchange): it wins
+    // where outputs are sparse (same-box sweep, 256 ch x 8 Mi: /16 0.89-0.90x the time of the original form, with and
+    // without the mixer; /8 1.03-1.15x; /4 1.3-1.9x), so it is chosen from /12 on.  kernel_kind 4 forces it, 5 forces
+    // dec_tma_kernel's form, SRCDSP_BAND = 0 / 1 overrides.
+    const long long band_rbs = (P.n_out + 31) / 32;
+    const long long band_tiles = (long long)C * ((band_rbs + BAND_NEW - 1) / BAND_NEW);
+    const long long band_rows_full = (long long)(n_in / (size_t)(32 * M));
+    int band_raw = 0, band_stages = 0;
+    size_t band_smem = 0;
+    const int band_groups = std::max(1, std::min(tune.tma_groups > 0 ? tune.tma_groups : (mixer ? 3 : 2),
+                                                 (mixer ? TMA_MAX_CONV_MIX : TMA_MAX_CONV) / 4));
+    const bool use_band = band_ok && tc_ok && P.vec_in && tensor_map_encoder() != nullptr && tune.band != 0 &&
+                          (kernel_kind == 0 || kernel_kind == 2 || kernel_kind == 4) && band_rows_full >= 1 &&
+                          band_rows_full < 0x7fffffffll && band_tiles < 0x7fffffffll &&
+                          (kernel_kind == 4 || tune.band == 1 || M >= 12) &&
+                          (kernel_kind != 0 || tune.band == 1 || band_tiles >= sm_count / 2) && (!mixer || mixer->pm().mask) &&
+                          band_layout(tma_tbl_bytes, band_groups, &band_raw, &band_stages, &band_smem) == SRCDSP_OK;
+    if (kernel_kind == 4 && !use_band)
+        return fail(SRCDSP_E_STATE, "band-form tcgen05 kernel forced but not applicable (needs even M, ntaps <= 32 M + 1, taps < 2^23, 16-byte aligned rows)");
+    if (use_band) {
+        TcParams T = tc_band;
+        T.in = in, T.out = out, T.in_stride = in_stride, T.out_stride = out_stride;
+        T.n_in = P.n_in, T.n_out = P.n_out;
+        T.tiles_per_ch = (int)(band_tiles / C);
+        T.total_tiles = band_tiles;
+        T.hist_in = d_hist[cur];
+        T.H = H;
+        T.shift = P.shift;
+        T.vec_in = P.vec_in, T.vec_out = P.vec_out;
+        T.epi_sleep_ns = tune.epi_sleep >= 0 ? (unsigned)tune.epi_sleep : 400;
+        T.mma_sleep_ns = tune.mma_sleep >= 0 ? (unsigned)tune.mma_sleep : (mixer ? 100 : 0);
+        T.table_bytes = tma_tbl_bytes;
+        if (mixer) {
+            T.cs_table = mixer->d_cs;
+            T.phi = P.phi;
+            T.freq = P.freq;
+            T.mix_mask = P.pm.mask;
+            T.seq_mask = seq_len - 1;
+        }
+        BandExtra X = band;
+        X.n_raw = tune.tma_raw > 0 ? std::max(2, std::min(tune.tma_raw, band_raw)) : band_raw;
+        const int groups = std::max(1, std::min(band_groups, std::min(std::min(X.n_raw, band_stages - 1), X.ks2)));
+        X.shared_raw = (X.n_raw % groups) != 0;
+        X.n_conv = 4 * groups;
+        X.rows_full = band_rows_full;
+        T.n_stages = band_stages;
+        CUtensorMap map;
+        memset(&map, 0, sizeof map);
+        const cuuint64_t gdim[3] = {(cuuint64_t)T.G, (cuuint64_t)band_rows_full, (cuuint64_t)C};
+        const cuuint64_t gstr[2] = {(cuuint64_t)T.G * 4, C > 1 ? (cuuint64_t)in_stride * 4 : (cuuint64_t)band_rows_full * T.G * 4};
+        const cuuint32_t box[3] = {64, (cuuint32_t)BAND_ROWS, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const CUresult cr = tensor_map_encoder()(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)in, gdim, gstr, box, estr,
+                                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) return fail(SRCDSP_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
+        const int tgrid = (int)std::min<long long>(band_tiles, sm_count);
+        const int threads = 32 * (TMA_CONV_WARP0 + X.n_conv);
+        if (tune.verbose)
+            fprintf(stderr, "dec_band_kernel: M=%d E=%d master=%d B table=%d B raw=%d split=%d groups=%d shared_raw=%d smem=%zu tiles=%lld\n",
+                    T.M, X.E, T.master_bytes, T.table_bytes, X.n_raw, T.n_stages, groups, X.shared_raw, band_smem, band_tiles);
+        if (mixer)
+            dec_band_kernel<true, 4><<<tgrid, threads, band_smem, stream>>>(T, X, map);
+        else
+            dec_band_kernel<false, 4><<<tgrid, threads, band_smem, stream>>>(T, X, map);
+        SRCDSP_LAUNCH_CHECK();
+        count_launch();
+        last_kernel = 4;
+    } else if (use_tc) {
         TcParams T = use_tma ? (mixer ? tc_tma_mix : tc_tma) : tc;
         T.in = in;
         T.out = out;
@@ -2063,7 +2248,7 @@ int srcdsp_dec_get_coeff_scaling(srcdsp_dec_t h, int *cs)
 int srcdsp_dec_set_kernel(srcdsp_dec_t h, int kind)
 {
     CHECK_HANDLE(h);
-    if (kind < 0 || kind > 3) return fail(SRCDSP_E_INVALID, "kernel kind must be 0, 1, 2 or 3");
+    if (kind < 0 || kind > 5) return fail(SRCDSP_E_INVALID, "kernel kind must be in [0, 5]");
     h->kernel_kind = kind;
     return SRCDSP_OK;
 }

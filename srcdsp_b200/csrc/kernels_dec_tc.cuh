@@ -90,6 +90,7 @@ struct TcParams {
     int H;
     unsigned shift;
     int vec_in;
+    int vec_out;             // dec_band_kernel: output rows are 16-byte aligned (STG.128)
     int *error_flag;         // mapped host memory: [0] set by a timed-out barrier wait, [1..4] which one
     int *counters;           // device memory: wait-cycle counters of the timing variants
     // fused NCO mix (MIX instantiation): packed (cos, sin) table of n_table = mix_mask + 1 entries (power of two)
@@ -457,7 +458,8 @@ __device__ __forceinline__ void tc_mma_role(const TcParams &P, const TcRole &R)
                     const int nn = (P.debug >> 12) ? (P.debug >> 12) : 56;
                     const uint32_t it_lo = umma_idesc_i8(0, 1, 128, nn), it_hi = umma_idesc_i8(1, 1, 128, nn);
                     if (elect_one()) {
-                        for (uint32_t i = 0; i < cnt; ++i) {
+                        const uint32_t cnt_t = SRCDSP_EXP(P, 512) ? (cnt ? 1u : 0u) : cnt;  // 512: lags merged into one band
+                        for (uint32_t i = 0; i < cnt_t; ++i) {
                             const uint4 e = plan_ent[hdr.x + i];
                             for (uint32_t half = 0; half < 2; ++half) {
                                 umma_i8(d_tmem + half * 128 + 8 * i, desc(bs + e.z + half * 128), desc(a_const + e.x), it_lo, 1);

@@ -116,11 +116,12 @@ __device__ __forceinline__ void tma_mix_store(const uint4 q, const MixPiece &m, 
 }
 
 // 4 row groups W apart (this warp's share of 4 * W groups): all loads first, then mix / split / store
-template <bool MIX, int W>
+// SRC_GS: bytes between consecutive groups of 4 raw rows (512 for rows of 32 samples, 1024 for dec_band_kernel's rows of 64)
+template <bool MIX, int W, int SRC_GS = 512>
 __device__ __forceinline__ void tma_convert4(uint32_t src, uint32_t dst_lo, uint32_t dst_hi, uint32_t lo, unsigned idx4, unsigned didx4,
                                              unsigned mask4)
 {
-    const uint4 v0 = lds128<0>(src), v1 = lds128<W * 512>(src), v2 = lds128<2 * W * 512>(src), v3 = lds128<3 * W * 512>(src);
+    const uint4 v0 = lds128<0>(src), v1 = lds128<W * SRC_GS>(src), v2 = lds128<2 * W * SRC_GS>(src), v3 = lds128<3 * W * SRC_GS>(src);
     if (MIX) {
         tma_mix_store<0>(v0, tma_mix_piece(lo, idx4, mask4 + 4), dst_lo, dst_hi);
         tma_mix_store<W * 128>(v1, tma_mix_piece(lo, (idx4 + didx4) & mask4, mask4 + 4), dst_lo, dst_hi);
@@ -138,10 +139,10 @@ __device__ __forceinline__ void tma_convert4(uint32_t src, uint32_t dst_lo, uint
 // (4 * W * G samples) is a multiple of the sequence's period -- the usual case, e.g. N = 4096 with W * M a
 // multiple of 32 -- the groups see the same oscillator values, which are then fetched once per K-step
 // instead of once per piece.
-template <int W>
+template <int W, int SRC_GS = 512>
 __device__ __forceinline__ void tma_convert4_same(uint32_t src, uint32_t dst_lo, uint32_t dst_hi, const MixPiece &m)
 {
-    const uint4 v0 = lds128<0>(src), v1 = lds128<W * 512>(src), v2 = lds128<2 * W * 512>(src), v3 = lds128<3 * W * 512>(src);
+    const uint4 v0 = lds128<0>(src), v1 = lds128<W * SRC_GS>(src), v2 = lds128<2 * W * SRC_GS>(src), v3 = lds128<3 * W * SRC_GS>(src);
     tma_mix_store<0>(v0, m, dst_lo, dst_hi);
     tma_mix_store<W * 128>(v1, m, dst_lo, dst_hi);
     tma_mix_store<2 * W * 128>(v2, m, dst_lo, dst_hi);

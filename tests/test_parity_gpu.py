@@ -387,11 +387,11 @@ def test_cfg2_full_size_spot_and_split_invariance(S, corc):
     assert np.array_equal(yh[1][: (1 << 18) // M], e)
 
 
-# ---- tcgen05 int8 Toeplitz kernel (forced with set_kernel(2)) ----------------------------------------
+# ---- tcgen05 int8 Toeplitz kernel (forced with set_kernel(5)) ----------------------------------------
 @pytest.mark.parametrize("M,nt,amp", [(16, 255, 400), (16, 256, 30000), (8, 63, 2000), (4, 1023, 300), (2, 9, 100),
                                       (1, 33, 8000), (3, 31, 500), (5, 50, 500), (10, 90, 100000), (12, 255, 2 ** 22),
                                       (32, 64, 127), (64, 300, 500), (16, 17, 1)])
-@pytest.mark.parametrize("kind", [2, 3])
+@pytest.mark.parametrize("kind", [5, 3])
 def test_tc_decimator_sweep(S, corc, M, nt, amp, kind):
     """The tensor-core path is exact for every ratio / length / tap magnitude it accepts, across
     streaming blocks (history), ragged tile ends and several channels (persistent tile loop)."""
@@ -408,7 +408,7 @@ def test_tc_decimator_sweep(S, corc, M, nt, amp, kind):
         got = host(d.step(dev(x))) if blk % 2 == 0 else d.step(x)
         # kind 2 is fed by TMA whenever a whole row-block (32 outputs) exists and the channel rows are
         # 16-byte aligned, kind 3 never
-        assert d.last_kernel.startswith("dec_tma" if kind == 2 and n_out >= 32 and n % 4 == 0 else "dec_tc"), d.last_kernel
+        assert d.last_kernel.startswith("dec_tma" if kind == 5 and n_out >= 32 and n % 4 == 0 else "dec_tc"), d.last_kernel
         for c in range(C):
             exp, hs[c] = corc.dec_step(taps, M, x[c], hs[c])
             assert np.array_equal(got[c], exp), (M, nt, blk, c)
@@ -445,8 +445,8 @@ def test_tma_pipeline_shapes_match_imad(S, monkeypatch, w, groups, stages, raw, 
     x = torch.empty((C, n, 2), dtype=torch.int16, device="cuda")
     S.synth_fill(x, 0x5EED00AA)
     outs = []
-    for kind in (1, 2):
-        if kind == 2:
+    for kind in (1, 5):
+        if kind == 5:
             monkeypatch.setenv("SRCDSP_TMA_W", str(w))
             monkeypatch.setenv("SRCDSP_TMA_GROUPS", str(groups))
             if stages:
@@ -464,7 +464,7 @@ def test_tma_pipeline_shapes_match_imad(S, monkeypatch, w, groups, stages, raw, 
             y = chain.step(x)
         torch.cuda.synchronize()
         outs.append(y)
-        assert d.last_kernel.startswith("dec_tma" if kind == 2 else "dec_fir")
+        assert d.last_kernel.startswith("dec_tma" if kind == 5 else "dec_fir")
     assert torch.equal(outs[0], outs[1])
 
 
@@ -481,7 +481,7 @@ def test_tma_strided_channel_rows_and_output_views(S, corc, mix):
     obig = torch.full((C, n // M + 40, 2), 12345, dtype=torch.int16, device="cuda")
     y = obig[:, 8: 8 + n // M]
     d = S.FilterDnsamplingFir(M, taps, channels=C, obsolete=True)
-    d.set_kernel(2)
+    d.set_kernel(5)
     chain, fs = d, None
     if mix:
         m = S.Mixer(channels=C)
@@ -513,7 +513,7 @@ def test_tma_p2_geometry(S, corc, monkeypatch, M, nt, amp, mix):
     taps[0] = amp
     C = 3
     d = S.FilterDnsamplingFir(M, taps, channels=C, obsolete=True)
-    d.set_kernel(2)
+    d.set_kernel(5)
     chain, fs = d, None
     if mix:
         m = S.Mixer(channels=C)
@@ -550,7 +550,7 @@ def test_tma_long_filter_many_tiles_match_imad(S, monkeypatch, M, nt, C, n, mix,
     x = torch.empty((C, n, 2), dtype=torch.int16, device="cuda")
     S.synth_fill(x, 0x5EED00AB)
     outs = []
-    for kind in (1, 2):
+    for kind in (1, 5):
         d = S.FilterDnsamplingFir(M, taps, channels=C, obsolete=True)
         d.set_kernel(kind)
         chain = d
@@ -562,13 +562,13 @@ def test_tma_long_filter_many_tiles_match_imad(S, monkeypatch, M, nt, C, n, mix,
             y = chain.step(x)
         torch.cuda.synchronize()
         outs.append(y)
-        assert d.last_kernel.startswith("dec_tma" if kind == 2 else "dec_fir")
+        assert d.last_kernel.startswith("dec_tma" if kind == 5 else "dec_fir")
     assert torch.equal(outs[0], outs[1])
 
 
 def test_tc_rejects_what_it_cannot_do(S):
     d = S.FilterDnsamplingFir(8, [2 ** 24] * 16, obsolete=True)  # needs 4 signed byte digits
-    d.set_kernel(2)
+    d.set_kernel(5)
     with pytest.raises(S.SrcDspError) as ei:
         d.step(np.zeros((64, 2), np.int16))
     assert ei.value.code == -5
@@ -577,7 +577,7 @@ def test_tc_rejects_what_it_cannot_do(S):
 
 
 @pytest.mark.parametrize("M,nt,n_table", [(16, 255, 4096), (8, 63, 4096), (4, 200, 1024), (2, 50, 4096), (3, 31, 256)])
-@pytest.mark.parametrize("kind", [2, 3])
+@pytest.mark.parametrize("kind", [5, 3])
 def test_tc_fused_mixer(S, corc, M, nt, n_table, kind):
     """NCO mix fused into the tensor-core kernel's load stage == Mixer::step then decimator::step."""
     rng = np.random.default_rng(M * 31 + nt)
@@ -596,7 +596,7 @@ def test_tc_fused_mixer(S, corc, M, nt, n_table, kind):
             m.adjustFrequency(0.0101, ch=1)
             fs[1] = corc.mixer_adjust_nominal(float(fs[1]), 0.0101)
         got = host(chain.step(dev(x))) if blk % 2 == 0 else chain.step(x)
-        assert d.last_kernel.startswith("dec_tma" if kind == 2 and n_out >= 32 and (n_out * M) % 4 == 0 else "dec_tc")
+        assert d.last_kernel.startswith("dec_tma" if kind == 5 and n_out >= 32 and (n_out * M) % 4 == 0 else "dec_tc")
         for c in range(C):
             phi, h = st[c]
             y, phi = corc.mixer_step(x[c], phi, corc.mixer_set_frequency(float(fs[c]), n_table), n_table)
@@ -616,8 +616,8 @@ def test_tc_two_stage_chain(S, corc):
     m.setFrequency(fs)
     d1 = S.FilterDnsamplingFir(8, t1, channels=C, obsolete=True)
     d2 = S.FilterDnsamplingFir(4, t2, channels=C, obsolete=True)
-    d1.set_kernel(2)
-    d2.set_kernel(2)
+    d1.set_kernel(5)
+    d2.set_kernel(5)
     chain = S.Ddc(m, d1, d2)
     st = [(0, None, None)] * C
     for blk in range(2):
