@@ -986,7 +986,7 @@ int DecBank::build_band()
         int b0, nb;
         if (kc == 0) {  // first MMA of a tile: all columns, accumulate = 0
             b0 = 0;
-            nb = (32 + E + 3) & ~3;
+            nb = (32 + E + 7) & ~7;  // whole chunks of 8 outputs: the epilogue adds extended chunks without per-output checks
         } else {
             const int b_lo = a + (r > 0 ? 1 : 0);
             const int b_hi = std::min(32 + E - 1, (32 * kc + 31 + ntaps - 1) / M);
@@ -1246,20 +1246,21 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
 
     // band form (kernels_dec_band.cuh): 2x fewer tensor-pipe cycles and ~4x fewer MACs per output than dec_tma_kernel, but
     // an epilogue of ~28 instead of ~12 instructions per output (32x32b loads, row hand-over, re / im exchange): it wins
-    // where outputs are sparse (same-box sweep, 256 ch x 8 Mi: /16 0.89-0.90x the time of the original form, with and
-    // without the mixer; /8 1.03-1.15x; /4 1.3-1.9x), so it is chosen from /12 on.  kernel_kind 4 forces it, 5 forces
-    // dec_tma_kernel's form, SRCDSP_BAND = 0 / 1 overrides.
+    // where outputs are sparse (tools/bandbench.py, 256 ch x 8 Mi, with and without the mixer: /10 .. /64 0.65-0.91x the
+    // time of the original form, /8 0.91x with 63 taps and 1.01x with 255, /6 1.02-1.05x, /4 1.07-1.5x, /2 1.6-1.8x --
+    // profiles/r2_bandbench.txt), so it is chosen from /10 on and for /8 with short filters (at most 16 extended outputs).
+    // kernel_kind 4 forces it, 5 forces dec_tma_kernel's form, SRCDSP_BAND = 0 / 1 overrides.
     const long long band_rbs = (P.n_out + 31) / 32;
     const long long band_tiles = (long long)C * ((band_rbs + BAND_NEW - 1) / BAND_NEW);
     const long long band_rows_full = (long long)(n_in / (size_t)(32 * M));
     int band_raw = 0, band_stages = 0;
     size_t band_smem = 0;
     const int band_groups = std::max(1, std::min(tune.tma_groups > 0 ? tune.tma_groups : (mixer ? 3 : 2),
-                                                 (mixer ? TMA_MAX_CONV_MIX : TMA_MAX_CONV) / 4));
+                                                 TMA_MAX_CONV_MIX / 4));
     const bool use_band = band_ok && tc_ok && P.vec_in && tensor_map_encoder() != nullptr && tune.band != 0 &&
                           (kernel_kind == 0 || kernel_kind == 2 || kernel_kind == 4) && band_rows_full >= 1 &&
                           band_rows_full < 0x7fffffffll && band_tiles < 0x7fffffffll &&
-                          (kernel_kind == 4 || tune.band == 1 || M >= 12) &&
+                          (kernel_kind == 4 || tune.band == 1 || M >= 10 || (M >= 8 && band.E <= 16)) &&
                           (kernel_kind != 0 || tune.band == 1 || band_tiles >= sm_count / 2) && (!mixer || mixer->pm().mask) &&
                           band_layout(tma_tbl_bytes, band_groups, &band_raw, &band_stages, &band_smem) == SRCDSP_OK;
     if (kernel_kind == 4 && !use_band)

@@ -51,7 +51,7 @@ struct BandExtra {
 };
 
 template <bool MIX, int W>
-__global__ void __launch_bounds__(MIX ? 32 * (TMA_CONV_WARP0 + TMA_MAX_CONV_MIX) : TMA_MAX_THREADS, 1)
+__global__ void __launch_bounds__(32 * (TMA_CONV_WARP0 + TMA_MAX_CONV_MIX), 1)  // at most 3 converter groups of 4 warps: 113 registers
     dec_band_kernel(const __grid_constant__ TcParams P, const __grid_constant__ BandExtra X, const __grid_constant__ CUtensorMap in_map)
 {
     extern __shared__ __align__(128) uint8_t tc_smem_raw[];
@@ -308,6 +308,7 @@ __global__ void __launch_bounds__(MIX ? 32 * (TMA_CONV_WARP0 + TMA_MAX_CONV_MIX)
         const int comp = lane & 1;
         const int row = 16 * warp + (lane >> 1);
         const int E = X.E;
+        const uint32_t swap_sel = comp ? 0x1032u : 0x3210u;  // the im lane of a pair holds (other, mine) = (re, im) swapped
         uint32_t acc_phases = 0;
         int acc = 0;
         unsigned par = 0;
@@ -337,33 +338,42 @@ __global__ void __launch_bounds__(MIX ? 32 * (TMA_CONV_WARP0 + TMA_MAX_CONV_MIX)
 #pragma unroll
                 for (int k = 0; k < 8; ++k) val[k] = v[4 * k] + (v[4 * k + 1] << 8) + (v[4 * k + 2] << 16) + (v[4 * k + 3] << 24);
             };
-            // phase 1: the extended outputs of this warp's LAST row (lanes 30, 31) belong to the next warp's first row
+            // phase 1: the extended outputs of this warp's LAST row (lanes 30, 31) belong to the next warp's first row.
+            // (Every extended chunk is whole: the tile's first MMA writes the accumulator up to a multiple of 8 outputs.)
             int *xo = ext_x + ((par * 4 + warp) * 2 + comp) * 32;
             for (int j = 0; 8 * j < E; ++j) {
                 uint32_t e8[8];
                 load8(128 + 32 * j, e8);
                 if (lane >= 30) {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) xo[8 * j + k] = (int)e8[k];
+                    *reinterpret_cast<uint4 *>(xo + 8 * j) = make_uint4(e8[0], e8[1], e8[2], e8[3]);
+                    *reinterpret_cast<uint4 *>(xo + 8 * j + 4) = make_uint4(e8[4], e8[5], e8[6], e8[7]);
                 }
             }
             asm volatile("bar.sync %0, 128;" ::"n"(BAND_EPI_BAR) : "memory");
             // phase 2: own outputs + the previous row's extended outputs, scale, pack (re, im), store
             const int *xi = ext_x + ((par * 4 + (warp > 0 ? warp - 1 : 0)) * 2 + comp) * 32;
             const long long n_rb = tt * BAND_NEW + row - 1;  // output row-block of this row (row 0: none)
-            const long long idx0 = n_rb * 32;
-#pragma unroll 1
+            const long long idx0 = n_rb * 32 + 4 * comp;
+            uint32_t *op = o + idx0;
+            // whole row inside the block and 16-byte aligned rows: no per-store checks
+            const bool fast = row > 0 && P.vec_out && (n_rb + 1) * 32 <= P.n_out;
+#pragma unroll
             for (int j = 0; j < 4; ++j) {
                 uint32_t v8[8];
                 load8(32 * j, v8);
                 if (8 * j < E) {
                     uint32_t e8[8];
                     load8(128 + 32 * j, e8);
+                    uint4 x0 = make_uint4(0, 0, 0, 0), x1 = x0;
+                    if (lane < 2) {
+                        x0 = *reinterpret_cast<const uint4 *>(xi + 8 * j);
+                        x1 = *reinterpret_cast<const uint4 *>(xi + 8 * j + 4);
+                    }
+                    const uint32_t xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        uint32_t up = __shfl_up_sync(0xffffffffu, e8[k], 2);
-                        if (lane < 2) up = (uint32_t)xi[8 * j + k];
-                        if (8 * j + k < E) v8[k] += up;
+                        const uint32_t up = __shfl_up_sync(0xffffffffu, e8[k], 2);
+                        v8[k] += lane < 2 ? xs[k] : up;
                     }
                 }
                 // the pair (re lane, im lane) shares the 8 outputs: the re lane packs and stores outputs 0..3 of the chunk,
@@ -374,17 +384,15 @@ __global__ void __launch_bounds__(MIX ? 32 * (TMA_CONV_WARP0 + TMA_MAX_CONV_MIX)
                     const uint32_t mine = comp ? v8[4 + k] : v8[k];
                     const uint32_t send = comp ? v8[k] : v8[4 + k];
                     const uint32_t other = __shfl_xor_sync(0xffffffffu, send, 1);
-                    w4[k] = comp ? scale_pack_sym_sat((int)other, (int)mine, P.shift) : scale_pack_sym_sat((int)mine, (int)other, P.shift);
+                    // limitScale16 (dsp_complex.cpp:63-73) of both components at once, then (re, im) into place
+                    w4[k] = prmt(scale_pack_sym_sat((int)mine, (int)other, P.shift), 0u, swap_sel);
                 }
-                const long long idx = idx0 + 8 * j + 4 * comp;
-                if (row > 0 && idx < P.n_out) {
-                    if (idx + 4 <= P.n_out && P.vec_out) {
-                        *reinterpret_cast<uint4 *>(o + idx) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-                    } else {
+                if (fast) {
+                    *reinterpret_cast<uint4 *>(op + 8 * j) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                } else if (row > 0) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            if (idx + k < P.n_out) o[idx + k] = w4[k];
-                    }
+                    for (int k = 0; k < 4; ++k)
+                        if (idx0 + 8 * j + k < P.n_out) op[8 * j + k] = w4[k];
                 }
             }
             tc_fence_before();
