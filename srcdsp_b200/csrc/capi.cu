@@ -1264,7 +1264,7 @@ int DecBank::step_device(const uint32_t *in, size_t in_stride, size_t n_in, uint
                           (kernel_kind != 0 || tune.band == 1 || band_tiles >= sm_count / 2) && (!mixer || mixer->pm().mask) &&
                           band_layout(tma_tbl_bytes, band_groups, &band_raw, &band_stages, &band_smem) == SRCDSP_OK;
     if (kernel_kind == 4 && !use_band)
-        return fail(SRCDSP_E_STATE, "band-form tcgen05 kernel forced but not applicable (needs even M, ntaps <= 32 M + 1, taps < 2^23, 16-byte aligned rows)");
+        return fail(SRCDSP_E_STATE, "band-form tcgen05 kernel forced but not applicable (needs even M, ntaps <= 32 M + 1, taps < 2^23, 16-byte aligned rows, at least 32 M samples per call)");
     if (use_band) {
         TcParams T = tc_band;
         T.in = in, T.out = out, T.in_stride = in_stride, T.out_stride = out_stride;

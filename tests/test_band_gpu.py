@@ -110,3 +110,54 @@ def test_band_rejects_what_it_cannot_do(S):
         with pytest.raises(S.SrcDspError) as ei:
             d.step(dev(x[: (len(x) // M) * M]))
         assert ei.value.code == -5
+
+
+@pytest.mark.parametrize("mix", [False, True])
+@pytest.mark.parametrize("out_off", [8, 6])  # 6: output rows not 16-byte aligned -> the scalar store path of the epilogue
+def test_band_strided_channel_rows_and_output_views(S, corc, mix, out_off):
+    """Channel rows that are views into wider buffers (in_stride > n, out_stride > n_out): the TMA tensor map carries the
+    stride, neighbouring memory is not touched, unaligned output rows take the scalar stores."""
+    import torch
+    rng = np.random.default_rng(31 + out_off)
+    C, M, nt, n, pad = 3, 16, 255, 16 * 2016 * 3 + 16 * 40, 64
+    taps = O.design_lowpass_taps(nt, M)
+    big = torch.from_numpy(rng.integers(-32768, 32768, (C, n + pad, 2)).astype(np.int16)).cuda()
+    x = big[:, 32: 32 + n]
+    obig = torch.full((C, n // M + 41, 2), 12345, dtype=torch.int16, device="cuda")
+    y = obig[:, out_off: out_off + n // M]
+    d = S.FilterDnsamplingFir(M, taps, channels=C, obsolete=True)
+    d.set_kernel(4)
+    chain, fs = d, None
+    if mix:
+        m = S.Mixer(channels=C)
+        fs = np.array([-0.25, 0.125, 0.7], np.float32)
+        m.setFrequency(fs)
+        chain = S.Ddc(m, d)
+    chain.step(x, out=y)
+    assert d.last_kernel.startswith("dec_band")
+    yh, xh, oh = host(y), host(x), host(obig)
+    for c in range(C):
+        e = xh[c]
+        if mix:
+            e, _ = corc.mixer_step(e, 0, corc.mixer_set_frequency(float(fs[c])))
+        e, _ = corc.dec_step(taps, M, e)
+        assert np.array_equal(yh[c], e)
+    assert (oh[:, :out_off] == 12345).all() and (oh[:, out_off + n // M:] == 12345).all()
+
+
+def test_band_time_sliced_stream_equals_sequential(S, corc):
+    """Time slices with a warm-up halo on the band form (what bench.py --workload cfg5-style sharding does for /16)."""
+    from srcdsp_b200.sharding import time_slices
+    rng = np.random.default_rng(77)
+    M, nt, n = 16, 255, 16 * 2016 * 8
+    taps = O.design_lowpass_taps(nt, M)
+    x = rng.integers(-32768, 32768, (n, 2)).astype(np.int16)
+    exp, _ = corc.dec_step(taps, M, x)
+    out = np.zeros_like(exp)
+    for sl in time_slices(n, 4, [nt], [M]):
+        d = S.FilterDnsamplingFir(M, taps, obsolete=True)
+        if sl.warmup:  # 256 samples: less than one row-block, the automatic choice takes the IMAD kernel
+            d.step(dev(x[sl.start - sl.warmup: sl.start]))
+        d.set_kernel(4)
+        out[sl.out_start: sl.out_start + sl.out_length] = host(d.step(dev(x[sl.start: sl.start + sl.length])))
+    assert np.array_equal(out, exp)

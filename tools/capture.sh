@@ -22,11 +22,11 @@ cap() {  # cap <name> <kernel regex> <skip> <command...>
   fi
 }
 B="python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --no-ddc"
-cap ${R}_dec_tma_cfg2 dec_tma_kernel 3 $B --workload cfg2
-cap ${R}_dec_tma_mix_ddc16 dec_tma_kernel 3 $B --workload ddc16
+cap ${R}_dec_band_cfg2 dec_band_kernel 3 $B --workload cfg2
+cap ${R}_dec_band_mix_ddc16 dec_band_kernel 3 $B --workload ddc16
 cap ${R}_dec_tma_p2_cfg5 dec_tma_kernel 1 $B --workload cfg5
-cap ${R}_dec_tma_cfg3_stage1 dec_tma_kernel 6 $B --workload cfg3
-cap ${R}_dec_tma_cfg3_stage2 dec_tma_kernel 7 $B --workload cfg3
+cap ${R}_dec_band_cfg3_stage1 dec_band_kernel 3 $B --workload cfg3
+cap ${R}_dec_tma_cfg3_stage2 dec_tma_kernel 3 $B --workload cfg3
 cap ${R}_up_fir4_cfg4 up_fir4_kernel 3 $B --workload cfg4
 CMD="python tools/decfbench.py 16 255"
 $CMD > $O/plain_${R}_decf.log 2>&1 && timeout 300 ncu --set full --clock-control none --import-source on -k regex:decf_fir_kernel -s 62 -c 1 -f -o $O/prof_${R}_decf $CMD > $O/ncu_${R}_decf.log 2>&1
