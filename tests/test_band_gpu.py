@@ -29,7 +29,8 @@ def host(t):
 
 
 SHAPES = [(16, 255, 400), (16, 256, 30000), (8, 63, 2000), (2, 9, 100), (4, 129, 300), (4, 31, 5000), (10, 90, 100000),
-          (12, 255, 2 ** 22), (32, 64, 127), (64, 300, 500), (16, 17, 1), (6, 193, 900), (16, 513, 200), (2, 65, 40)]
+          (12, 255, 2 ** 22), (32, 64, 127), (64, 300, 500), (16, 17, 1), (6, 193, 900), (16, 513, 200), (2, 65, 40),
+          (16, 1, 3), (2, 2, 50), (8, 9, 1000), (64, 2049, 60)]  # no / one extended output; the longest reach (E = 32) at /64
 
 
 @pytest.mark.parametrize("M,nt,amp", SHAPES)
@@ -37,7 +38,7 @@ def test_band_decimator_sweep(S, corc, M, nt, amp):
     rng = np.random.default_rng(M * 1009 + nt)
     taps = rng.integers(-amp, amp + 1, nt).astype(np.int32)
     taps[nt // 2] = amp
-    C = 3
+    C = 1 if nt > 2000 else 3  # (keeps the oracle's share of the test short)
     d = S.FilterDnsamplingFir(M, taps, channels=C, obsolete=True)
     d.set_kernel(4)
     hs = [None] * C
