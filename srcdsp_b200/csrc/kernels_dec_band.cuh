@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(32 * (TMA_CONV_WARP0 + TMA_MAX_CONV_MIX), 1)  
         const int dst_lane = (piece >> 2) * chunk + grp * 32 + (piece & 3) * 4;
         // row groups of this warp: wi + W * i, i < 16 / W (both halves of the stage)
         const uint32_t src_main = smem_u32(raw) + wi * 1024 + src_lane;
-        const uint32_t dst_main = smem_u32(stages) + wi * 128 + dst_lane;
+        const uint32_t dst_main = smem_u32(stages) + wi * 128 + tma_stm_lane(lane, chunk);  // stmatrix row address of this lane
         const uint32_t tab_u32 = smem_u32(tab_smem);
         const unsigned mask4 = P.seq_mask << 2;
         int rs = g % NR, ss = g % NS;
@@ -171,10 +171,9 @@ __global__ void __launch_bounds__(32 * (TMA_CONV_WARP0 + TMA_MAX_CONV_MIX), 1)  
                     const unsigned idx4 = MIX ? ((n_lane + 64 * kk + 32 * h) & P.seq_mask) << 2 : 0u;
                     if (MIX && didx4 == 0) {
                         const MixPiece m = tma_mix_piece(tab_u32, idx4, mask4 + 4);
-                        tma_convert4_same<W, 1024>(src + h * 128, dst + h * BAND_HALF_BYTES, dst + h * BAND_HALF_BYTES + hi_off, m);
+                        tma_convert4_same<W, 1024>(src + h * 128, dst + h * BAND_HALF_BYTES, m);
                     } else {
-                        tma_convert4<MIX, W, 1024>(src + h * 128, dst + h * BAND_HALF_BYTES, dst + h * BAND_HALF_BYTES + hi_off, tab_u32, idx4,
-                                                   didx4, mask4);
+                        tma_convert4<MIX, W, 1024>(src + h * 128, dst + h * BAND_HALF_BYTES, tab_u32, idx4, didx4, mask4);
                     }
                 }
             } else {

@@ -75,22 +75,30 @@ __device__ __forceinline__ uint32_t lds32(uint32_t a)
 }
 
 // (mix4_planes_dp2a / mix_digits: common.cuh)
-// one group of 4 rows: this lane's 16-byte piece -> its 4 byte-plane words
-template <int DST_OFF>
-__device__ __forceinline__ void tma_store_planes(uint32_t re_lo, uint32_t re_hi, uint32_t im_lo, uint32_t im_hi, uint32_t dst_lo,
-                                                 uint32_t dst_hi)
+// One group of 4 rows: the warp's 32 lanes hold, per byte plane, 8 rows x 16 bytes of the sample operand -- lane
+// (grp, piece) has word (piece & 3) of row (grp, piece >> 2).  That is exactly the fragment layout of an 8 x 8 b16 matrix
+// (thread t: row t / 4, columns 2 (t % 4) and 2 (t % 4) + 1), so the four plane words of a piece leave as ONE
+// stmatrix.x4 instead of four STS.32: matrix 0 = re lo, 1 = im lo, 2 = re hi, 3 = im hi, and lane L supplies the
+// shared address of row L % 8 of matrix L / 8 (tma_stm_lane).  Same bytes, same 4 conflict-free wavefronts, a
+// quarter of the store instructions.
+__device__ __forceinline__ int tma_stm_lane(int lane, int chunk)
 {
-    sts32<DST_OFF>(dst_lo, re_lo);
-    sts32<DST_OFF + 16>(dst_lo, im_lo);
-    sts32<DST_OFF>(dst_hi, re_hi);
-    sts32<DST_OFF + 16>(dst_hi, im_hi);
+    const int m = lane >> 3, j = lane & 7;  // matrix, row: (grp, kc chunk) = (j >> 1, j & 1)
+    return (m >> 1) * 2 * chunk + (m & 1) * 16 + (j & 1) * chunk + (j >> 1) * 32;
 }
 template <int DST_OFF>
-__device__ __forceinline__ void tma_split_store(const uint4 q, uint32_t dst_lo, uint32_t dst_hi)
+__device__ __forceinline__ void tma_store_planes(uint32_t re_lo, uint32_t re_hi, uint32_t im_lo, uint32_t im_hi, uint32_t dst)
+{
+    asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0+%5], {%1, %2, %3, %4};" ::"r"(dst), "r"(re_lo), "r"(im_lo), "r"(re_hi),
+                 "r"(im_hi), "n"(DST_OFF)
+                 : "memory");
+}
+template <int DST_OFF>
+__device__ __forceinline__ void tma_split_store(const uint4 q, uint32_t dst)
 {
     uint32_t re_lo, re_hi, im_lo, im_hi;
     split4(q, re_lo, re_hi, im_lo, im_hi);
-    tma_store_planes<DST_OFF>(re_lo, re_hi, im_lo, im_hi, dst_lo, dst_hi);
+    tma_store_planes<DST_OFF>(re_lo, re_hi, im_lo, im_hi, dst);
 }
 // The oscillator values of the 4 samples of a piece: Bre / Bim digit words (mix_digits).  They come from the
 // channel's oscillator sequence in TIME order in shared memory (two arrays Bre[n], Bim[n] for phase
@@ -108,30 +116,29 @@ __device__ __forceinline__ MixPiece tma_mix_piece(uint32_t lo, unsigned idx4, un
     return m;
 }
 template <int DST_OFF>
-__device__ __forceinline__ void tma_mix_store(const uint4 q, const MixPiece &m, uint32_t dst_lo, uint32_t dst_hi)
+__device__ __forceinline__ void tma_mix_store(const uint4 q, const MixPiece &m, uint32_t dst)
 {
     uint32_t re_lo, re_hi, im_lo, im_hi;
     mix4_planes_dp2a(q, m.re, m.im, re_lo, re_hi, im_lo, im_hi);
-    tma_store_planes<DST_OFF>(re_lo, re_hi, im_lo, im_hi, dst_lo, dst_hi);
+    tma_store_planes<DST_OFF>(re_lo, re_hi, im_lo, im_hi, dst);
 }
 
 // 4 row groups W apart (this warp's share of 4 * W groups): all loads first, then mix / split / store
 // SRC_GS: bytes between consecutive groups of 4 raw rows (512 for rows of 32 samples, 1024 for dec_band_kernel's rows of 64)
 template <bool MIX, int W, int SRC_GS = 512>
-__device__ __forceinline__ void tma_convert4(uint32_t src, uint32_t dst_lo, uint32_t dst_hi, uint32_t lo, unsigned idx4, unsigned didx4,
-                                             unsigned mask4)
+__device__ __forceinline__ void tma_convert4(uint32_t src, uint32_t dst, uint32_t lo, unsigned idx4, unsigned didx4, unsigned mask4)
 {
     const uint4 v0 = lds128<0>(src), v1 = lds128<W * SRC_GS>(src), v2 = lds128<2 * W * SRC_GS>(src), v3 = lds128<3 * W * SRC_GS>(src);
     if (MIX) {
-        tma_mix_store<0>(v0, tma_mix_piece(lo, idx4, mask4 + 4), dst_lo, dst_hi);
-        tma_mix_store<W * 128>(v1, tma_mix_piece(lo, (idx4 + didx4) & mask4, mask4 + 4), dst_lo, dst_hi);
-        tma_mix_store<2 * W * 128>(v2, tma_mix_piece(lo, (idx4 + 2 * didx4) & mask4, mask4 + 4), dst_lo, dst_hi);
-        tma_mix_store<3 * W * 128>(v3, tma_mix_piece(lo, (idx4 + 3 * didx4) & mask4, mask4 + 4), dst_lo, dst_hi);
+        tma_mix_store<0>(v0, tma_mix_piece(lo, idx4, mask4 + 4), dst);
+        tma_mix_store<W * 128>(v1, tma_mix_piece(lo, (idx4 + didx4) & mask4, mask4 + 4), dst);
+        tma_mix_store<2 * W * 128>(v2, tma_mix_piece(lo, (idx4 + 2 * didx4) & mask4, mask4 + 4), dst);
+        tma_mix_store<3 * W * 128>(v3, tma_mix_piece(lo, (idx4 + 3 * didx4) & mask4, mask4 + 4), dst);
     } else {
-        tma_split_store<0>(v0, dst_lo, dst_hi);
-        tma_split_store<W * 128>(v1, dst_lo, dst_hi);
-        tma_split_store<2 * W * 128>(v2, dst_lo, dst_hi);
-        tma_split_store<3 * W * 128>(v3, dst_lo, dst_hi);
+        tma_split_store<0>(v0, dst);
+        tma_split_store<W * 128>(v1, dst);
+        tma_split_store<2 * W * 128>(v2, dst);
+        tma_split_store<3 * W * 128>(v3, dst);
     }
 }
 
@@ -140,13 +147,13 @@ __device__ __forceinline__ void tma_convert4(uint32_t src, uint32_t dst_lo, uint
 // multiple of 32 -- the groups see the same oscillator values, which are then fetched once per K-step
 // instead of once per piece.
 template <int W, int SRC_GS = 512>
-__device__ __forceinline__ void tma_convert4_same(uint32_t src, uint32_t dst_lo, uint32_t dst_hi, const MixPiece &m)
+__device__ __forceinline__ void tma_convert4_same(uint32_t src, uint32_t dst, const MixPiece &m)
 {
     const uint4 v0 = lds128<0>(src), v1 = lds128<W * SRC_GS>(src), v2 = lds128<2 * W * SRC_GS>(src), v3 = lds128<3 * W * SRC_GS>(src);
-    tma_mix_store<0>(v0, m, dst_lo, dst_hi);
-    tma_mix_store<W * 128>(v1, m, dst_lo, dst_hi);
-    tma_mix_store<2 * W * 128>(v2, m, dst_lo, dst_hi);
-    tma_mix_store<3 * W * 128>(v3, m, dst_lo, dst_hi);
+    tma_mix_store<0>(v0, m, dst);
+    tma_mix_store<W * 128>(v1, m, dst);
+    tma_mix_store<2 * W * 128>(v2, m, dst);
+    tma_mix_store<3 * W * 128>(v3, m, dst);
 }
 
 // generic-pointer variant for the edge path (tab = the oscillator sequence Bre[N] ++ Bim[N], p0 = n mod N)
@@ -255,7 +262,7 @@ __global__ void __launch_bounds__(MIX ? 32 * (TMA_CONV_WARP0 + TMA_MAX_CONV_MIX)
         // main row groups of this warp: HQ + wi + W * i, i < 32 / W; the HQ groups in front go to one warp
         // of the group in turn
         const uint32_t src_main = smem_u32(raw) + (HQ + wi) * 512 + src_lane;
-        const uint32_t dst_main = smem_u32(stages) + (HQ + wi) * 128 + dst_lane;
+        const uint32_t dst_main = smem_u32(stages) + (HQ + wi) * 128 + tma_stm_lane(lane, chunk);  // stmatrix row address of this lane
         const uint32_t tab_u32 = smem_u32(tab_smem);
         const unsigned mask4 = P.seq_mask << 2;
         const bool two_batches = P.nrb / (4 * W) == 8;  // 8 main row groups per warp (W = 4, 128 row-blocks); else 4
@@ -325,13 +332,11 @@ __global__ void __launch_bounds__(MIX ? 32 * (TMA_CONV_WARP0 + TMA_MAX_CONV_MIX)
                 const unsigned idx4 = MIX ? ((n_lane + 32 * kc) & P.seq_mask) << 2 : 0u;
                 if (MIX && didx4 == 0) {
                     const MixPiece m = tma_mix_piece(tab_u32, idx4, mask4 + 4);
-                    tma_convert4_same<W>(src, dst, dst + hi_off, m);
-                    if (two_batches) tma_convert4_same<W>(src + 16 * 512, dst + 16 * 128, dst + 16 * 128 + hi_off, m);
+                    tma_convert4_same<W>(src, dst, m);
+                    if (two_batches) tma_convert4_same<W>(src + 16 * 512, dst + 16 * 128, m);
                 } else {
-                    tma_convert4<MIX, W>(src, dst, dst + hi_off, tab_u32, idx4, didx4, mask4);
-                    if (two_batches)
-                        tma_convert4<MIX, W>(src + 16 * 512, dst + 16 * 128, dst + 16 * 128 + hi_off, tab_u32, (idx4 + 4 * didx4) & mask4,
-                                             didx4, mask4);
+                    tma_convert4<MIX, W>(src, dst, tab_u32, idx4, didx4, mask4);
+                    if (two_batches) tma_convert4<MIX, W>(src + 16 * 512, dst + 16 * 128, tab_u32, (idx4 + 4 * didx4) & mask4, didx4, mask4);
                 }
                 if (HQ > 0 && wi == halo_turn) {
                     // the row groups in front of the tile (the previous tile's last row-blocks): same shared-space
@@ -345,9 +350,9 @@ __global__ void __launch_bounds__(MIX ? 32 * (TMA_CONV_WARP0 + TMA_MAX_CONV_MIX)
                     for (int q = 0; q < HQ; ++q) {
                         const uint4 v = lds128<0>(hsrc);
                         if (MIX)
-                            tma_mix_store<0>(v, tma_mix_piece(tab_u32, hidx4, mask4 + 4), hdst, hdst + hi_off);
+                            tma_mix_store<0>(v, tma_mix_piece(tab_u32, hidx4, mask4 + 4), hdst);
                         else
-                            tma_split_store<0>(v, hdst, hdst + hi_off);
+                            tma_split_store<0>(v, hdst);
                         hsrc += 512;
                         hdst += 128;
                         hidx4 = (hidx4 + hstep4) & mask4;

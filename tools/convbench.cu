@@ -34,10 +34,8 @@ __global__ void __launch_bounds__(MAXT, MINB) conv_kernel(int iters, unsigned se
     const int wi = warp & 3, g = warp >> 2;
     const int piece = lane & 7, grp = lane >> 3;
     const int src_lane = grp * 128 + piece * 16;
-    const int dst_lane = (piece >> 2) * chunk + grp * 32 + (piece & 3) * 4;
-    const int hi_off = 2 * chunk;
     const uint32_t src_main = smem_u32(raw) + (1 + wi) * 512 + src_lane + (g & 1) * raw_bytes;
-    const uint32_t dst_main = smem_u32(stages) + (1 + wi) * 128 + dst_lane + (g & 1) * stage_bytes;
+    const uint32_t dst_main = smem_u32(stages) + (1 + wi) * 128 + tma_stm_lane(lane, chunk) + (g & 1) * stage_bytes;
     const uint32_t tab_u32 = smem_u32(tab);
     const unsigned mask4 = seq_mask << 2;
     unsigned n_lane = ((4 * wi + grp) * 512 + 4 * piece) & seq_mask;
@@ -46,11 +44,11 @@ __global__ void __launch_bounds__(MAXT, MINB) conv_kernel(int iters, unsigned se
         const unsigned idx4 = ((n_lane + 32 * (it & 15)) & seq_mask) << 2;
         if (MIX) {
             const MixPiece m = tma_mix_piece(tab_u32, idx4, mask4 + 4);
-            tma_convert4_same<4>(src_main, dst_main, dst_main + hi_off, m);
-            tma_convert4_same<4>(src_main + 16 * 512, dst_main + 16 * 128, dst_main + 16 * 128 + hi_off, m);
+            tma_convert4_same<4>(src_main, dst_main, m);
+            tma_convert4_same<4>(src_main + 16 * 512, dst_main + 16 * 128, m);
         } else {
-            tma_convert4<false, 4>(src_main, dst_main, dst_main + hi_off, tab_u32, 0, 0, 0);
-            tma_convert4<false, 4>(src_main + 16 * 512, dst_main + 16 * 128, dst_main + 16 * 128 + hi_off, tab_u32, 0, 0, 0);
+            tma_convert4<false, 4>(src_main, dst_main, tab_u32, 0, 0, 0);
+            tma_convert4<false, 4>(src_main + 16 * 512, dst_main + 16 * 128, tab_u32, 0, 0, 0);
         }
         fence_async_smem();
         __syncwarp();
