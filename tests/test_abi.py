@@ -67,6 +67,12 @@ def test_no_cpu_fallback_without_gpu(built_lib):
     import srcdsp_b200 as S
     with pytest.raises(S.SrcDspError):
         S.Mixer()
+    # the multi-device driver refuses as well (and cleans up after the member that failed)
+    g, devs = C.c_void_p(), (C.c_int * 2)(0, 1)
+    st = built_lib.srcdsp_group_create(C.byref(g), 1, devs, 2, 1, 4096, 8, 4)
+    assert st == _capi.E_NOGPU and not g
+    with pytest.raises(S.SrcDspError):
+        S.DdcGroup("channels", [0], 4, 8, [1] * 8)
 
 
 def test_product_never_imports_the_oracle():
