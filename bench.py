@@ -241,6 +241,8 @@ def cpu_reference_run(w, steps: int, warmup: int, cores: int, target_cpu_seconds
     kind = "reference"
     if r is None:
         raise RuntimeError("oracle/_ref is not built (run `make -C oracle` where /root/reference exists)")
+    if w["kind"] not in ("dec", "ddc", "ddc2", "up"):
+        raise RuntimeError(f"the reference harness has no bank benchmark for workload kind '{w['kind']}'")
     M, nt = w["M"], w["ntaps"]
     up = w["kind"] == "up"
     taps = O.design_interp_taps(nt, M) if up else O.design_lowpass_taps(nt, M)
