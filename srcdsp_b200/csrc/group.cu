@@ -63,6 +63,18 @@ using srcdsp::fail;
         }                                                  \
     } while (0)
 
+// Starting a host thread can fail (std::system_error): nothing may be thrown across the C ABI, so the member's part runs
+// on the calling thread instead.
+template <class F>
+static void start_member(std::vector<std::thread> &threads, F &&fn)
+{
+    try {
+        threads.emplace_back(fn);
+    } catch (...) {
+        fn();
+    }
+}
+
 static int collect(srcdsp_group_s *g, int used)
 {
     for (int i = 0; i < used; ++i)
@@ -188,12 +200,13 @@ int srcdsp_group_step(srcdsp_group_t h, const int16_t *in, size_t in_stride, siz
     cudaGetLastError();
     const int G = (int)h->members.size();
     std::vector<std::thread> threads;
+    threads.reserve(G);
 
     if (h->mode == SRCDSP_GROUP_CHANNELS) {
         for (int i = 0; i < G; ++i) {
             Member *m = &h->members[i];
             m->status = SRCDSP_OK;
-            threads.emplace_back([=] {
+            start_member(threads, [=] {
                 GROUP_TRY_MEMBER(*m, srcdsp_ddc_step(m->chain, in + 2 * (size_t)m->ch0 * in_stride, in_stride, n_in,
                                                      out + 2 * (size_t)m->ch0 * out_stride, out_stride));
             });
@@ -222,7 +235,7 @@ int srcdsp_group_step(srcdsp_group_t h, const int16_t *in, size_t in_stride, siz
         m->status = SRCDSP_OK;
         const size_t o0 = n_out * i / used, o1 = n_out * (i + 1) / used;
         const size_t start = o0 * Mt, len = (o1 - o0) * Mt;
-        threads.emplace_back([=, &phi0, &freq, &nominal] {
+        start_member(threads, [=, &phi0, &freq, &nominal] {
             if (i > 0) {
                 for (int c = 0; c < C; ++c) {
                     if (m->mixer) {
