@@ -399,12 +399,13 @@ def decf_bench(args, w, base, S, O, torch, device):
     n_out = C * (n // M)
     alg = (8.0 * M + 8.0) * n_out
     roof = {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak,
-            "traffic": None, "kernel": "decf_fir_kernel (FP32 pipe, tap-order FMUL + FADD chains)", "peak_source": peak_src,
+            "traffic": None, "kernel": d.last_kernel, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": alg, "kernel_ms": ms}
     if clocks and clocks.get("sm_max_mhz"):
         roof["fp32_frac"] = 4.0 * nt * n_out / (ms * 1e-3) / (148 * 128 * clocks["sm_max_mhz"] * 1e6)
         roof["fp32_note"] = ("4*ntaps rounded FP32 operations per output against 148 SM x 128 lanes x sm_max_mhz; the reference's "
-                             "float sum is a multiply and an add per tap and component (no FMA), kept for bit-exactness")
+                             "float sum is a multiply and an add per tap and component (no FMA), kept for bit-exactness; the kernel issues them "
+                             "as packed FFMA2(x, k, -0.0) + FADD2 on (re, im): the same two roundings per component")
     cpu = None
     if not args.no_cpu:
         r = O.ref()

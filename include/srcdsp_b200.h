@@ -154,6 +154,9 @@ int srcdsp_decf_reset(srcdsp_decf_t h);
 int srcdsp_decf_step(srcdsp_decf_t h, const float *in_iq, size_t in_stride, size_t n_in_per_ch, float *out_iq,
                      size_t out_stride);
 int srcdsp_decf_get_coeff_scaling(srcdsp_decf_t h, unsigned *coeff_scaling);
+/* which kernel the current coefficients select: 1 = decf_fir_kernel (an output pair per thread), */
+/* 2 = decf_quad_kernel (four outputs per thread: M in {4, 8, 16, 32} and ntaps > 2 M)          */
+int srcdsp_decf_get_last_kernel(srcdsp_decf_t h, int *kind);
 /* history of one channel, oldest first, ntaps-1 complex samples (host pointers) */
 int srcdsp_decf_get_state(srcdsp_decf_t h, int ch, float *history_iq, size_t *n_samples);
 int srcdsp_decf_set_state(srcdsp_decf_t h, int ch, const float *history_iq, size_t n_samples);

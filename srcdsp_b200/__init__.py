@@ -394,6 +394,13 @@ class FilterDnsamplingFirFloat(_Handle):
         check(lib().srcdsp_decf_get_coeff_scaling(self._h, C.byref(v)))
         return v.value
 
+    @property
+    def last_kernel(self) -> str:
+        v = C.c_int()
+        check(lib().srcdsp_decf_get_last_kernel(self._h, C.byref(v)))
+        return {1: "decf_fir_kernel (FP32 pipe, packed FFMA2 + FADD2 chains, output pair per thread)",
+                2: "decf_quad_kernel (FP32 pipe, packed FFMA2 + FADD2 chains, four outputs per thread)"}.get(v.value, "none")
+
     def step(self, x, out=None):
         """dsptl_dnsampling_filters.h:172-220: out.size() * M == in.size()."""
         bi = _BufF32(x, self.channels)

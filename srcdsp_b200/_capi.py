@@ -67,6 +67,7 @@ PROTOTYPES = {
     "srcdsp_decf_reset": (C.c_int, [_vp]),
     "srcdsp_decf_step": (C.c_int, [_vp, _vp, _sz, _sz, _vp, _sz]),
     "srcdsp_decf_get_coeff_scaling": (C.c_int, [_vp, C.POINTER(C.c_uint)]),
+    "srcdsp_decf_get_last_kernel": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "srcdsp_decf_get_state": (C.c_int, [_vp, C.c_int, _vp, C.POINTER(_sz)]),
     "srcdsp_decf_set_state": (C.c_int, [_vp, C.c_int, _vp, _sz]),
     "srcdsp_decf_set_stream": (C.c_int, [_vp, _vp]),

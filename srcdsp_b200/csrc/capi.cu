@@ -79,6 +79,7 @@ struct Tuning {
     int decf_ct = -1;      // SRCDSP_DECF_CT
     int decf_blocks = -1;  // SRCDSP_DECF_BLOCKS
     int decf_prefetch = -1;  // SRCDSP_DECF_PREFETCH
+    int decf_quad = -1;    // SRCDSP_DECF_QUAD    0: pairs of outputs per thread only
     int tc_debug = 0;      // SRCDSP_TC_DEBUG / SRCDSP_UPT_DEBUG: timing experiments, -DSRCDSP_TIMING_EXPERIMENTS builds only
     int upt_debug = 0;
 };
@@ -111,6 +112,7 @@ static Tuning tuning_from_env()
     get("SRCDSP_DECF_CT", v.decf_ct);
     get("SRCDSP_DECF_BLOCKS", v.decf_blocks);
     get("SRCDSP_DECF_PREFETCH", v.decf_prefetch);
+    get("SRCDSP_DECF_QUAD", v.decf_quad);
 #ifdef SRCDSP_TIMING_EXPERIMENTS
     get("SRCDSP_TC_DEBUG", v.tc_debug);
     get("SRCDSP_UPT_DEBUG", v.upt_debug);

@@ -43,7 +43,9 @@ struct DecfParams {
     size_t in_stride, out_stride;  // complex samples per channel row
     long long n_in, n_out;         // per channel
     const float2 *hist;            // [C][N - 1] age order: hist[N - 2] = xx[-1]
-    const float *taps2;            // [2][E]: [1][e] = c[e], [0][e] = c[e - M], zero outside the filter
+    const float *taps2;            // pair kernel [2][E]: [1][e] = c[e], [0][e] = c[e - M], zero outside the filter; quad kernel: c[0 .. 4 * rows * MC)
+    int tap_floats;                // floats of taps2 (shared memory in front of the samples; 2 * E or 4 * rows * M / 4)
+    int rows;                      // quad kernel: rows of M samples per output (ceil(N / M), >= 3)
     int M, N, E;                   // ratio, taps, padded walk length (multiple of 4, >= N + M)
     int lead;                      // local sample index of stream sample tile_out * M * tile
     int blk, padw;                 // samples per block (2 * M) and padding samples behind each (2 if M is even)
@@ -55,6 +57,8 @@ struct DecfParams {
     int prefetch_dist;             // CTAs resident on the device at once (0: no L2 prefetch)
     unsigned stage_step;           // bytes the padded staging position advances per round of blockDim.x samples (0: blockDim.x % blk != 0)
     unsigned shift;                // (coeffScaling - leftShift) & 31, as x86 `sar` applies it
+    unsigned nz_bits, nz_mask;     // 0x80000000 and 0: -0.0f = nz_bits | (tid & nz_mask), a value the compiler can neither see nor
+                                   // prove uniform (decf_mac: the uniform operand slot of the FFMA2 belongs to the tap)
 };
 
 // taps of short filters travel in the kernel's parameter space (constant bank): 2 * E floats <= 3584 bytes
@@ -72,17 +76,39 @@ __device__ __forceinline__ float decf_limit(float y, unsigned shift)
     return (float)v;
 }
 
-// CT: the taps are read from the parameter space (uniform constant loads: no LDS, no shared-memory wavefronts for them)
-template <int PAIRS, int BC, bool CT>
-__global__ void __launch_bounds__(256) decf_fir_kernel(const __grid_constant__ DecfParams P, const __grid_constant__ DecfTaps K)
+// Packed FP32 (sm_100: FFMA2 / FADD2, two lanes of one 64-bit register pair per instruction): (re, im) of a sample are such
+// a pair, so a tap costs one multiply and one add INSTRUCTION per output instead of two each -- the same FP32 pipe time
+// (a packed instruction occupies the pipe for two issue cycles) at half the issue slots, which is what bound this kernel.
+// Each lane rounds exactly like the scalar instruction.  ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (a single
+// rounding: not the reference's result), explicit .rn or -fmad=false notwithstanding, so the multiply is written as
+// fma(x, k, -0.0) with a -0.0 the compiler cannot see (DecfParams::nz_bits): x * k + (-0) is the rounded product with its own sign
+// (+0 + -0 = +0, -0 + -0 = -0), and an fma followed by an add has no fused form.  cuobjdump -sass: FFMA2 = FADD2 count.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t f32x2_bcast(float v)
 {
-    extern __shared__ __align__(16) uint8_t decf_smem[];
-    float *ts = reinterpret_cast<float *>(decf_smem);              // [2][E]
-    float2 *xs = reinterpret_cast<float2 *>(ts + 2 * P.E);         // padded samples (2 * E * 4 bytes is a multiple of 16)
-    const int tid = threadIdx.x, T = blockDim.x;
-    const unsigned ch = blockIdx.x / (unsigned)P.tiles_per_ch;
-    const int tile = (int)(blockIdx.x - ch * (unsigned)P.tiles_per_ch);
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float2 f32x2_unpack(f32x2_t v)
+{
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+// acc.re += k * x.re ; acc.im += k * x.im   (dsptl_dnsampling_filters.h:209-210 with float types: two roundings per component)
+__device__ __forceinline__ void decf_mac(f32x2_t &acc, float k, f32x2_t x, f32x2_t nz)
+{
+    f32x2_t p;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(p) : "l"(x), "l"(f32x2_bcast(k)), "l"(nz));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(acc) : "l"(acc), "l"(p));
+}
 
+// Head of both kernels: L2 prefetch for the successor CTA, taps into shared memory (unless they travel in the parameter
+// space), the tile's samples into the padded staging area.  Ends with __syncthreads().
+__device__ __forceinline__ void decf_stage_tile(const DecfParams &P, float *ts, float2 *xs, unsigned ch, int tile, bool taps_to_smem)
+{
+    const int tid = threadIdx.x, T = blockDim.x;
     // L2 prefetch of the tile that the CTA taking this one's place will stage (prefetch_dist = resident CTAs of the
     // grid): one bulk prefetch by one thread, so that the staging below waits for L2, not for HBM
     if (tid == 0 && P.prefetch_dist > 0 && blockIdx.x + (unsigned)P.prefetch_dist < gridDim.x) {
@@ -95,8 +121,8 @@ __global__ void __launch_bounds__(256) decf_fir_kernel(const __grid_constant__ D
             if (hi > lo) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo), "r"((uint32_t)(hi - lo)) : "memory");
         }
     }
-    if (!CT)
-        for (int i = tid; i < 2 * P.E; i += T) ts[i] = __ldg(P.taps2 + i);
+    if (taps_to_smem)
+        for (int i = tid; i < P.tap_floats; i += T) ts[i] = __ldg(P.taps2 + i);
     // stage: local index idx <-> stream sample s = tile * tile_out * M + idx - lead
     const float2 *x = P.in + (size_t)ch * P.in_stride;
     const float2 *hist = P.hist + (size_t)ch * (P.N - 1);
@@ -134,14 +160,28 @@ __global__ void __launch_bounds__(256) decf_fir_kernel(const __grid_constant__ D
         }
     }
     __syncthreads();
+}
+
+// CT: the taps are read from the parameter space (uniform constant loads: no LDS, no shared-memory wavefronts for them)
+template <int PAIRS, int BC, bool CT>
+__global__ void __launch_bounds__(256) decf_fir_kernel(const __grid_constant__ DecfParams P, const __grid_constant__ DecfTaps K)
+{
+    extern __shared__ __align__(16) uint8_t decf_smem[];
+    float *ts = reinterpret_cast<float *>(decf_smem);              // [2][E]
+    float2 *xs = reinterpret_cast<float2 *>(ts + P.tap_floats);    // padded samples (tap_floats * 4 bytes is a multiple of 16)
+    const int tid = threadIdx.x, T = blockDim.x;
+    const unsigned ch = blockIdx.x / (unsigned)P.tiles_per_ch;
+    const int tile = (int)(blockIdx.x - ch * (unsigned)P.tiles_per_ch);
+    decf_stage_tile(P, ts, xs, ch, tile, !CT);
 
     // pair q = tid + j * T: upper output 2q + 1 sits at local index (2q + 1) * M + lead = the LAST sample of block
     // q + j0 (even M) -- chunks of 4 never straddle a block
-    float2 acc[PAIRS][2];
+    f32x2_t acc[PAIRS][2];  // (re, im) of the lower / upper output, packed
+    const f32x2_t nz = f32x2_bcast(__uint_as_float(P.nz_bits | (threadIdx.x & P.nz_mask)));
     int pos[PAIRS];
 #pragma unroll
     for (int j = 0; j < PAIRS; ++j) {
-        acc[j][0] = acc[j][1] = make_float2(0.f, 0.f);
+        acc[j][0] = acc[j][1] = 0ull;
         const int top = (2 * (tid + j * T) + 1) * P.M + P.lead;
         pos[j] = top + P.padw * (int)__umulhi((unsigned)top, P.blk_magic);
     }
@@ -159,17 +199,17 @@ __global__ void __launch_bounds__(256) decf_fir_kernel(const __grid_constant__ D
 #pragma unroll
         for (int j = 0; j < PAIRS; ++j) {
             // samples pos-3 .. pos (ascending address); e ascends as the address descends
-            const float4 hi = *reinterpret_cast<const float4 *>(xs + pos[j] - 1);  // {x[pos-1], x[pos]}
-            const float4 lo = *reinterpret_cast<const float4 *>(xs + pos[j] - 3);  // {x[pos-3], x[pos-2]}
-            float2 &a0 = acc[j][0], &a1 = acc[j][1];
-            if (UP) a1.x = __fadd_rn(a1.x, __fmul_rn(k1.x, hi.z)), a1.y = __fadd_rn(a1.y, __fmul_rn(k1.x, hi.w));
-            if (LO) a0.x = __fadd_rn(a0.x, __fmul_rn(k0.x, hi.z)), a0.y = __fadd_rn(a0.y, __fmul_rn(k0.x, hi.w));
-            if (UP) a1.x = __fadd_rn(a1.x, __fmul_rn(k1.y, hi.x)), a1.y = __fadd_rn(a1.y, __fmul_rn(k1.y, hi.y));
-            if (LO) a0.x = __fadd_rn(a0.x, __fmul_rn(k0.y, hi.x)), a0.y = __fadd_rn(a0.y, __fmul_rn(k0.y, hi.y));
-            if (UP) a1.x = __fadd_rn(a1.x, __fmul_rn(k1.z, lo.z)), a1.y = __fadd_rn(a1.y, __fmul_rn(k1.z, lo.w));
-            if (LO) a0.x = __fadd_rn(a0.x, __fmul_rn(k0.z, lo.z)), a0.y = __fadd_rn(a0.y, __fmul_rn(k0.z, lo.w));
-            if (UP) a1.x = __fadd_rn(a1.x, __fmul_rn(k1.w, lo.x)), a1.y = __fadd_rn(a1.y, __fmul_rn(k1.w, lo.y));
-            if (LO) a0.x = __fadd_rn(a0.x, __fmul_rn(k0.w, lo.x)), a0.y = __fadd_rn(a0.y, __fmul_rn(k0.w, lo.y));
+            const ulonglong2 hi = *reinterpret_cast<const ulonglong2 *>(xs + pos[j] - 1);  // {x[pos-1], x[pos]}
+            const ulonglong2 lo = *reinterpret_cast<const ulonglong2 *>(xs + pos[j] - 3);  // {x[pos-3], x[pos-2]}
+            f32x2_t &a0 = acc[j][0], &a1 = acc[j][1];
+            if (UP) decf_mac(a1, k1.x, hi.y, nz);
+            if (LO) decf_mac(a0, k0.x, hi.y, nz);
+            if (UP) decf_mac(a1, k1.y, hi.x, nz);
+            if (LO) decf_mac(a0, k0.y, hi.x, nz);
+            if (UP) decf_mac(a1, k1.z, lo.y, nz);
+            if (LO) decf_mac(a0, k0.z, lo.y, nz);
+            if (UP) decf_mac(a1, k1.w, lo.x, nz);
+            if (LO) decf_mac(a0, k0.w, lo.x, nz);
             pos[j] -= 4;
         }
         if (++in_blk == P.blk_chunks) {  // uniform: step over the padding in front of the block just finished
@@ -196,17 +236,17 @@ __global__ void __launch_bounds__(256) decf_fir_kernel(const __grid_constant__ D
                 const float4 k1 = tap1(cb + i);
 #pragma unroll
                 for (int j = 0; j < PAIRS; ++j) {
-                    const float4 hi = *reinterpret_cast<const float4 *>(xs + pos[j] - 4 * i - 1);
-                    const float4 lo = *reinterpret_cast<const float4 *>(xs + pos[j] - 4 * i - 3);
-                    float2 &a0 = acc[j][0], &a1 = acc[j][1];
-                    a1.x = __fadd_rn(a1.x, __fmul_rn(k1.x, hi.z)), a1.y = __fadd_rn(a1.y, __fmul_rn(k1.x, hi.w));
-                    if (lo_on) a0.x = __fadd_rn(a0.x, __fmul_rn(k0.x, hi.z)), a0.y = __fadd_rn(a0.y, __fmul_rn(k0.x, hi.w));
-                    a1.x = __fadd_rn(a1.x, __fmul_rn(k1.y, hi.x)), a1.y = __fadd_rn(a1.y, __fmul_rn(k1.y, hi.y));
-                    if (lo_on) a0.x = __fadd_rn(a0.x, __fmul_rn(k0.y, hi.x)), a0.y = __fadd_rn(a0.y, __fmul_rn(k0.y, hi.y));
-                    a1.x = __fadd_rn(a1.x, __fmul_rn(k1.z, lo.z)), a1.y = __fadd_rn(a1.y, __fmul_rn(k1.z, lo.w));
-                    if (lo_on) a0.x = __fadd_rn(a0.x, __fmul_rn(k0.z, lo.z)), a0.y = __fadd_rn(a0.y, __fmul_rn(k0.z, lo.w));
-                    a1.x = __fadd_rn(a1.x, __fmul_rn(k1.w, lo.x)), a1.y = __fadd_rn(a1.y, __fmul_rn(k1.w, lo.y));
-                    if (lo_on) a0.x = __fadd_rn(a0.x, __fmul_rn(k0.w, lo.x)), a0.y = __fadd_rn(a0.y, __fmul_rn(k0.w, lo.y));
+                    const ulonglong2 hi = *reinterpret_cast<const ulonglong2 *>(xs + pos[j] - 4 * i - 1);
+                    const ulonglong2 lo = *reinterpret_cast<const ulonglong2 *>(xs + pos[j] - 4 * i - 3);
+                    f32x2_t &a0 = acc[j][0], &a1 = acc[j][1];
+                    decf_mac(a1, k1.x, hi.y, nz);
+                    if (lo_on) decf_mac(a0, k0.x, hi.y, nz);
+                    decf_mac(a1, k1.y, hi.x, nz);
+                    if (lo_on) decf_mac(a0, k0.y, hi.x, nz);
+                    decf_mac(a1, k1.z, lo.y, nz);
+                    if (lo_on) decf_mac(a0, k0.z, lo.y, nz);
+                    decf_mac(a1, k1.w, lo.x, nz);
+                    if (lo_on) decf_mac(a0, k0.w, lo.x, nz);
                 }
             }
 #pragma unroll
@@ -227,14 +267,94 @@ __global__ void __launch_bounds__(256) decf_fir_kernel(const __grid_constant__ D
 #pragma unroll
     for (int j = 0; j < PAIRS; ++j) {
         const long long i = o0 + 2 * (tid + j * T);
-        const float2 y0 = make_float2(decf_limit(acc[j][0].x, P.shift), decf_limit(acc[j][0].y, P.shift));
-        const float2 y1 = make_float2(decf_limit(acc[j][1].x, P.shift), decf_limit(acc[j][1].y, P.shift));
+        const float2 sum0 = f32x2_unpack(acc[j][0]), sum1 = f32x2_unpack(acc[j][1]);
+        const float2 y0 = make_float2(decf_limit(sum0.x, P.shift), decf_limit(sum0.y, P.shift));
+        const float2 y1 = make_float2(decf_limit(sum1.x, P.shift), decf_limit(sum1.y, P.shift));
         if (i + 1 < P.n_out && ((reinterpret_cast<uintptr_t>(o + i) & 15) == 0)) {
             *reinterpret_cast<float4 *>(o + i) = make_float4(y0.x, y0.y, y1.x, y1.y);
         } else {
             if (i < P.n_out) o[i] = y0;
             if (i + 1 < P.n_out) o[i + 1] = y1;
         }
+    }
+}
+
+// The same computation with FOUR consecutive outputs per thread (M = 4 * MC in {4, 8, 16, 32}, filters of at least 3 M taps).
+// With the packed MAC the pair kernel above is bound by shared memory, not by issue slots: 2 LDS.128 (8 wavefronts) feed
+// 16 packed instructions = 8 SM-clocks of the FP32 pipe (ncu: shared memory 88 % busy at 0.65 of the pipe).  A quad of
+// outputs reuses every sample four times from registers -- half the wavefronts per MAC.  Thread t owns outputs
+// 4t .. 4t + 3 (acc[j] = output 4t + 3 - j) and walks the samples down from xx[(4t + 3) M]; sample (4t + 3) M - e is tap
+// e - j M of output j.  The walk is cut into ROWS of M samples = MC chunks: output j is active in rows [j, j + rows), so
+// the active set is a compile-time range per row (ramp up {0}, {0,1}, {0,1,2}; all four; ramp down {1,2,3}, {2,3}, {3}),
+// every output uses the SAME tap array shifted by whole rows (chunk (r - j) MC + i: one copy of the taps, zero padded
+// to whole rows -- a zero tap adds +-0), and all LDS offsets inside a row are immediates.  The lane stride is 4 M samples +
+// one 16-byte unit of padding (odd in units of 16 bytes: conflict-free LDS.128); a block of 4 rows ends at a thread's top
+// sample, so rows never straddle the padding.  Each output is still ONE chain in tap order (k ascends with e).
+template <int MC, bool CT>
+__global__ void __launch_bounds__(256) decf_quad_kernel(const __grid_constant__ DecfParams P, const __grid_constant__ DecfTaps K)
+{
+    extern __shared__ __align__(16) uint8_t decf_smem[];
+    float *ts = reinterpret_cast<float *>(decf_smem);
+    float2 *xs = reinterpret_cast<float2 *>(ts + P.tap_floats);
+    const int tid = threadIdx.x;
+    const unsigned ch = blockIdx.x / (unsigned)P.tiles_per_ch;
+    const int tile = (int)(blockIdx.x - ch * (unsigned)P.tiles_per_ch);
+    decf_stage_tile(P, ts, xs, ch, tile, !CT);
+
+    f32x2_t acc[4] = {0ull, 0ull, 0ull, 0ull};
+    const f32x2_t nz = f32x2_bcast(__uint_as_float(P.nz_bits | (threadIdx.x & P.nz_mask)));
+    const int top = (4 * tid + 3) * P.M + P.lead;  // the last sample of a block
+    int pos = top + P.padw * (int)__umulhi((unsigned)top, P.blk_magic);
+    const float4 *tsm = reinterpret_cast<const float4 *>(ts);
+    auto row = [&](int r, auto jlo_tag, auto jhi_tag) {
+        constexpr int JLO = decltype(jlo_tag)::value, JHI = decltype(jhi_tag)::value;
+#pragma unroll
+        for (int i = 0; i < MC; ++i) {
+            const ulonglong2 hi = *reinterpret_cast<const ulonglong2 *>(xs + pos - 4 * i - 1);  // {x[pos-1], x[pos]}
+            const ulonglong2 lo = *reinterpret_cast<const ulonglong2 *>(xs + pos - 4 * i - 3);  // {x[pos-3], x[pos-2]}
+            float4 k[4];
+#pragma unroll
+            for (int j = JLO; j <= JHI; ++j) k[j] = CT ? K.t[(r - j) * MC + i] : tsm[(r - j) * MC + i];
+#pragma unroll
+            for (int j = JLO; j <= JHI; ++j) decf_mac(acc[j], k[j].x, hi.y, nz);
+#pragma unroll
+            for (int j = JLO; j <= JHI; ++j) decf_mac(acc[j], k[j].y, hi.x, nz);
+#pragma unroll
+            for (int j = JLO; j <= JHI; ++j) decf_mac(acc[j], k[j].z, lo.y, nz);
+#pragma unroll
+            for (int j = JLO; j <= JHI; ++j) decf_mac(acc[j], k[j].w, lo.x, nz);
+        }
+        pos -= 4 * MC + ((r & 3) == 3 ? P.padw : 0);  // the row, and the padding in front of the block after its fourth row
+    };
+    typedef std::integral_constant<int, 0> I0;
+    typedef std::integral_constant<int, 1> I1;
+    typedef std::integral_constant<int, 2> I2;
+    typedef std::integral_constant<int, 3> I3;
+    const int R = P.rows;
+    row(0, I0{}, I0{});
+    row(1, I0{}, I1{});
+    row(2, I0{}, I2{});
+#pragma unroll 1
+    for (int r = 3; r < R; ++r) row(r, I0{}, I3{});
+    row(R, I1{}, I3{});
+    row(R + 1, I2{}, I3{});
+    row(R + 2, I3{}, I3{});
+
+    float2 *o = P.out + (size_t)ch * P.out_stride;
+    const long long i0 = (long long)tile * P.tile_out + 4 * tid;
+    float2 y[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 sum = f32x2_unpack(acc[3 - j]);
+        y[j] = make_float2(decf_limit(sum.x, P.shift), decf_limit(sum.y, P.shift));
+    }
+    if (i0 + 3 < P.n_out && ((reinterpret_cast<uintptr_t>(o + i0) & 15) == 0)) {
+        *reinterpret_cast<float4 *>(o + i0) = make_float4(y[0].x, y[0].y, y[1].x, y[1].y);
+        *reinterpret_cast<float4 *>(o + i0 + 2) = make_float4(y[2].x, y[2].y, y[3].x, y[3].y);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (i0 + j < P.n_out) o[i0 + j] = y[j];
     }
 }
 

@@ -184,23 +184,38 @@ def test_float_golden_gpu(S, case, where):
     assert rel_rms(got, FGOLD[case["name"]]) <= REL_RMS_TOL
 
 
+def quad_applies(M, nt):
+    return M in (4, 8, 16, 32) and -(-nt // M) >= 3
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("M,nt", [(1, 17), (2, 9), (3, 31), (4, 1023), (5, 7), (6, 40), (7, 100), (8, 63), (10, 90),
-                                  (12, 255), (16, 255), (16, 256), (32, 64), (64, 300), (8, 1), (1, 1), (24, 48)])
+                                  (12, 255), (16, 255), (16, 256), (32, 64), (64, 300), (8, 1), (1, 1), (24, 48),
+                                  (4, 9), (4, 12), (4, 13), (8, 17), (8, 1000), (16, 33), (16, 2047), (32, 65), (32, 512)])
 @pytest.mark.parametrize("kind", ["unity", "int", "frac"])
-@pytest.mark.parametrize("pairs", [1, 2])
-def test_float_decimator_sweep(S, corc, monkeypatch, M, nt, kind, pairs):
+@pytest.mark.parametrize("shape", ["pairs1", "pairs2", "quad"])
+def test_float_decimator_sweep(S, corc, monkeypatch, M, nt, kind, shape):
     """Ragged streaming blocks (also shorter than ntaps - 1), host and device buffers, left shift, every tap family,
-    both thread shapes of the kernel (1 or 2 output pairs per thread)."""
-    monkeypatch.setenv("SRCDSP_DECF_PAIRS", str(pairs))
-    if pairs == 2 and kind == "frac":
-        monkeypatch.setenv("SRCDSP_DECF_BLOCKS", "0")  # the per-chunk code alone (power-of-two ratios default to whole blocks)
+    every thread shape of the kernels (1 or 2 output pairs per thread; four outputs per thread where that applies:
+    3 rows of taps -- the shortest -- up to taps that no longer fit the parameter space)."""
+    if shape == "quad":
+        if not quad_applies(M, nt):
+            pytest.skip("four outputs per thread need M in {4, 8, 16, 32} and more than 2 M taps")
+        if kind == "frac":
+            monkeypatch.setenv("SRCDSP_DECF_CT", "0")  # taps through shared memory instead of the parameter space
+    else:
+        pairs = 1 if shape == "pairs1" else 2
+        monkeypatch.setenv("SRCDSP_DECF_QUAD", "0")
+        monkeypatch.setenv("SRCDSP_DECF_PAIRS", str(pairs))
+        if pairs == 2 and kind == "frac":
+            monkeypatch.setenv("SRCDSP_DECF_BLOCKS", "0")  # the per-chunk code alone (power-of-two ratios default to whole blocks)
     rng = np.random.default_rng(M * 10007 + nt)
     t = ftaps(rng, nt, kind)
     ls = 1 if kind == "int" and nt > 4 else 0
     d = S.FilterDnsamplingFirFloat(M, t, obsolete=True)
     d.setLeftShiftBy2(ls)
     assert d.coeffScaling == corc.decf_coeff_scaling(t)
+    assert d.last_kernel.startswith("decf_quad" if shape == "quad" else "decf_fir")
     h = None
     for blk, nb in enumerate([nt + 37, 2600, 3, 1, 700]):
         n = M * (nb // M + 1)
@@ -281,3 +296,27 @@ def test_float_many_tiles_split_invariance_and_spot_check(S, corc):
         hist = host(x[c, i * M - (nt - 1): i * M])
         e, _ = corc.decf_step(t, M, host(x[c, i * M: i * M + M]), hist)
         assert np.array_equal(host(y[c, i]), e[0]), (c, i)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,nt", [(4, 63), (8, 64), (16, 255), (32, 97), (16, 1500)])
+def test_float_quad_kernel_interior_tiles(S, corc, monkeypatch, M, nt):
+    """Many interior tiles (cp.async staging, padded lane stride) of the four-outputs-per-thread kernel on rows that are
+    only 8-byte aligned: == the pair kernel on every channel, == the oracle on one, with carried history."""
+    import torch
+    rng = np.random.default_rng(M + nt)
+    C, n = 3, M * 6000
+    t = ftaps(rng, nt, "frac")
+    big = (torch.rand((C, 2 * n + 7, 2), device="cuda") - 0.5) * 30000
+    x = big[:, 3: 3 + 2 * n]
+    q = S.FilterDnsamplingFirFloat(M, t, channels=C, obsolete=True)
+    assert q.last_kernel.startswith("decf_quad")
+    monkeypatch.setenv("SRCDSP_DECF_QUAD", "0")
+    p = S.FilterDnsamplingFirFloat(M, t, channels=C, obsolete=True)
+    assert p.last_kernel.startswith("decf_fir")
+    h = None
+    for a, b in ((0, n + M * 5), (n + M * 5, 2 * n)):
+        yq, yp = q.step(x[:, a:b]), p.step(x[:, a:b])
+        assert torch.equal(yq, yp)
+        e, h = corc.decf_step(t, M, host(x[1, a:b]), h)
+        assert np.array_equal(host(yq[1]), e)
