@@ -10,24 +10,28 @@
 //
 // i.e. one rounded multiply and one rounded add per component and tap (g++ for x86-64 does not contract them),
 // summed in tap order; the sum is truncated toward zero to int32, shifted, clamped to +-32767 and converted back.
-// The result depends on the order of the additions, so this kernel keeps it: every output is ONE sequential chain
-// of __fmul_rn / __fadd_rn per component (never an FMA, never a tree), and parallelism comes from the outputs.
+// The result depends on the order of the additions, so the kernels keep it: every output is ONE sequential chain of a
+// rounded multiply and a rounded add per component (never a fused multiply-add, never a tree), and parallelism comes
+// from the outputs.  The two components of a sample share a packed instruction (decf_mac below: FFMA2 with a -0.0
+// addend + FADD2), which halves the issue slots without changing a single rounding.
 //
-// Shape.  4 FP32 instructions per tap and output make the FP32 pipe (128 lanes/clk/SM) the roofline; 8 bytes of
-// sample per 4 lane-instructions are twice what shared memory delivers (128 B/clk/SM), so samples are reused in
-// registers: a thread owns the output PAIR (2q, 2q+1) and walks the samples downwards from xx[(2q+1)*M]; sample
-// (2q+1)*M - e is tap k = e of the upper output and tap k = e - M of the lower one.  Per 4 samples: 2 LDS.128
-// (samples) + 2 LDS.128 (broadcast: 4 taps of each output, from two pre-shifted zero-padded copies of the taps) feed
-// 32 FP32 instructions; a thread carries PAIRS such pairs (1 with 256 threads per CTA by default: more warps hide the
-// LDS latency and overlap another CTA's staging better than more chains per thread do).  The lane stride is 2*M samples
-// = M 16-byte units; for even M every block of 2*M samples is followed by one unit of padding so that the stride is
-// odd and the LDS.128 are conflict free.  Zero taps in front of / behind a filter add +-0 to its chain, which leaves
-// every finite sum unchanged (samples must be finite -- the reference's int conversion of NaN/Inf is undefined).
+// Shape.  4 FP32 lane-operations per tap and output make the FP32 pipe (128 lanes/clk/SM) the roofline; 8 bytes of
+// sample per 4 lane-operations are twice what shared memory delivers (128 B/clk/SM), so samples are reused in
+// registers.  decf_fir_kernel: a thread owns the output PAIR (2q, 2q+1) and walks the samples downwards from
+// xx[(2q+1)*M]; sample (2q+1)*M - e is tap k = e of the upper output and tap k = e - M of the lower one.  Per 4
+// samples: 2 LDS.128 (samples) + the taps (uniform constant loads from the parameter space for short filters, 2
+// broadcast LDS.128 from two pre-shifted zero-padded copies otherwise) feed 16 packed instructions; a thread carries
+// PAIRS such pairs.  The lane stride is 2*M samples = M 16-byte units; for even M every block of 2*M samples is followed
+// by one unit of padding so that the stride is odd and the LDS.128 are conflict free.  Zero taps in front of / behind a
+// filter add +-0 to its chain, which leaves every finite sum unchanged (samples must be finite -- the reference's int
+// conversion of NaN/Inf is undefined).  decf_quad_kernel (further down): FOUR outputs per thread, half the
+// shared-memory reads per MAC; the default from /16 on and for long filters at /8.
 //
 // Measured steps (256 channels, /16 x 255 taps, 1 Mi samples per channel; tools/decfbench.py):
 //   plain staging loads 3.03 ms -> 8-byte cp.async (all copies of a thread in flight) 1.14 -> bulk L2 prefetch of the
 //   successor tile 1.00 -> whole blocks with compile-time offsets (BC > 0) 0.92 -> taps through the parameter space
-//   (CT: uniform constant loads, no tap LDS) 0.79 ms = 21.3 G out/s = 0.58 of the FP32 pipe.
+//   (CT: uniform constant loads, no tap LDS) 0.79 -> packed FFMA2 + FADD2 0.71 -> four outputs per thread 0.67 ms =
+//   25.1 G out/s = 0.69 of the FP32 pipe (0.72 on bench.py's 4 Mi-sample cfg2f; profiles/r2_decf_packed_quad_ab.txt).
 #pragma once
 
 #include <type_traits>

@@ -201,6 +201,7 @@ def test_float_decimator_sweep(S, corc, monkeypatch, M, nt, kind, shape):
     if shape == "quad":
         if not quad_applies(M, nt):
             pytest.skip("four outputs per thread need M in {4, 8, 16, 32} and more than 2 M taps")
+        monkeypatch.setenv("SRCDSP_DECF_QUAD", "1")  # wherever it applies (the default keeps small ratios on the pair kernel)
         if kind == "frac":
             monkeypatch.setenv("SRCDSP_DECF_CT", "0")  # taps through shared memory instead of the parameter space
     else:
@@ -299,23 +300,26 @@ def test_float_many_tiles_split_invariance_and_spot_check(S, corc):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("M,nt", [(4, 63), (8, 64), (16, 255), (32, 97), (16, 1500)])
-def test_float_quad_kernel_interior_tiles(S, corc, monkeypatch, M, nt):
-    """Many interior tiles (cp.async staging, padded lane stride) of the four-outputs-per-thread kernel on rows that are
-    only 8-byte aligned: == the pair kernel on every channel, == the oracle on one, with carried history."""
+@pytest.mark.parametrize("M,nt", [(4, 63), (8, 64), (16, 255), (32, 97), (16, 1500), (16, 256), (8, 23)])
+@pytest.mark.parametrize("off", [2, 3])
+def test_float_quad_kernel_interior_tiles(S, corc, monkeypatch, M, nt, off):
+    """Many interior tiles (cp.async staging, padded lane stride) of the four-outputs-per-thread kernel, forced for every
+    ratio it supports, on rows that are 16-byte (off = 2) or only 8-byte aligned (off = 3): == the pair kernel on every
+    channel, == the oracle on one, with carried history."""
     import torch
     rng = np.random.default_rng(M + nt)
     C, n = 3, M * 6000
     t = ftaps(rng, nt, "frac")
-    big = (torch.rand((C, 2 * n + 7, 2), device="cuda") - 0.5) * 30000
-    x = big[:, 3: 3 + 2 * n]
+    big = (torch.rand((C, 2 * n + 8, 2), device="cuda") - 0.5) * 30000
+    x = big[:, off: off + 2 * n]
+    monkeypatch.setenv("SRCDSP_DECF_QUAD", "1")
     q = S.FilterDnsamplingFirFloat(M, t, channels=C, obsolete=True)
     assert q.last_kernel.startswith("decf_quad")
     monkeypatch.setenv("SRCDSP_DECF_QUAD", "0")
     p = S.FilterDnsamplingFirFloat(M, t, channels=C, obsolete=True)
     assert p.last_kernel.startswith("decf_fir")
     h = None
-    for a, b in ((0, n + M * 5), (n + M * 5, 2 * n)):
+    for a, b in ((0, n + M * 6), (n + M * 6, 2 * n)):
         yq, yp = q.step(x[:, a:b]), p.step(x[:, a:b])
         assert torch.equal(yq, yp)
         e, h = corc.decf_step(t, M, host(x[1, a:b]), h)

@@ -35,15 +35,19 @@ def run():
     return ev[0].elapsed_time(ev[1]) / K
 
 
-# forced thread shapes, then the automatic choice without L2 prefetch / without the whole-block fast path / as shipped
-for pairs, pf, blocks in (("2", "1", "1"), ("1", "1", "1"), ("", "0", "1"), ("", "1", "0"), ("", "1", "1")):
-    os.environ.pop("SRCDSP_DECF_PAIRS", None)
+# the pair kernel in its forced thread shapes, then the automatic choice (four outputs per thread where that applies)
+# without L2 prefetch, the pair kernel without its whole-block fast path, and the library as shipped
+for pairs, pf, blocks, quad in (("2", "1", "1", "0"), ("1", "1", "1", "0"), ("", "0", "1", ""), ("", "1", "0", "0"), ("", "1", "1", "")):
+    for k in ("SRCDSP_DECF_PAIRS", "SRCDSP_DECF_QUAD"):
+        os.environ.pop(k, None)
     if pairs:
         os.environ["SRCDSP_DECF_PAIRS"] = pairs
+    if quad:
+        os.environ["SRCDSP_DECF_QUAD"] = quad
     os.environ["SRCDSP_DECF_PREFETCH"] = pf
     os.environ["SRCDSP_DECF_BLOCKS"] = blocks
     ms = run()
-    print(f"pairs per thread {pairs or 'auto'}, L2 prefetch {pf}, whole blocks {blocks}: {ms:.3f} ms")
+    print(f"pairs per thread {pairs or 'auto'}, quad {quad or 'auto'}, L2 prefetch {pf}, whole blocks {blocks}: {ms:.3f} ms")
 outs = C * (n // M)
 try:
     hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
