@@ -31,7 +31,7 @@
 //   plain staging loads 3.03 ms -> 8-byte cp.async (all copies of a thread in flight) 1.14 -> bulk L2 prefetch of the
 //   successor tile 1.00 -> whole blocks with compile-time offsets (BC > 0) 0.92 -> taps through the parameter space
 //   (CT: uniform constant loads, no tap LDS) 0.79 -> packed FFMA2 + FADD2 0.71 -> four outputs per thread 0.67 ms =
-//   25.1 G out/s = 0.69 of the FP32 pipe (0.72 on bench.py's 4 Mi-sample cfg2f; profiles/r2_decf_packed_quad_ab.txt).
+//   25.1 G out/s = 0.69 of the FP32 pipe (0.73 on bench.py's 4 Mi-sample cfg2f; profiles/r2_decf_packed_quad_ab.txt).
 #pragma once
 
 #include <type_traits>
