@@ -20,11 +20,8 @@ sys.path.insert(0, ROOT)
 import oracle as O  # noqa: E402
 import srcdsp_b200 as S  # noqa: E402
 
-budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
-seed = int(sys.argv[2]) if len(sys.argv) > 2 else 12345
-rng = np.random.default_rng(seed)
-O.build()
-corc = O.corc()
+rng = None
+corc = None
 fails, cases = [], {"dec": 0, "ddc": 0, "up": 0, "decf": 0}
 kernels = {}  # which kernels the passed cases ran (last step of the case)
 
@@ -160,19 +157,48 @@ def fuzz_decf():
     kernels[k] = kernels.get(k, 0) + 1
 
 
-t0 = time.time()
-while time.time() - t0 < budget and len(fails) < 10:
-    r = rng.integers(10)
-    if r < 4:
-        fuzz_dec(False)
-    elif r < 7:
-        fuzz_dec(True)
-    elif r < 8:
-        fuzz_up()
-    else:
-        fuzz_decf()
-for f in fails:
-    print("FAIL", f)
-print(f"fuzz_parity: seed {seed}, {time.time() - t0:.0f} s, passed cases {cases}, failures {len(fails)}")
-print("kernels of the passed cases:", dict(sorted(kernels.items())))
-sys.exit(1 if fails else 0)
+def run(budget: float, seed: int, max_cases: int = 0):
+    """Runs random cases for `budget` seconds (or until `max_cases` have been drawn: a deterministic set for a seed);
+    returns (cases, failures, kernels)."""
+    global rng, corc
+    rng = np.random.default_rng(seed)
+    O.build()
+    corc = O.corc()
+    fails.clear()
+    kernels.clear()
+    for k in cases:
+        cases[k] = 0
+    saved = {k: os.environ.get(k) for k in ("SRCDSP_DECF_QUAD", "SRCDSP_DECF_CT")}
+    t0 = time.time()
+    try:
+        drawn = 0
+        while time.time() - t0 < budget and len(fails) < 10 and (max_cases <= 0 or drawn < max_cases):
+            drawn += 1
+            r = rng.integers(10)
+            if r < 4:
+                fuzz_dec(False)
+            elif r < 7:
+                fuzz_dec(True)
+            elif r < 8:
+                fuzz_up()
+            else:
+                fuzz_decf()
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    return dict(cases), list(fails), dict(kernels)
+
+
+if __name__ == "__main__":
+    budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
+    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 12345
+    t0 = time.time()
+    c, f, k = run(budget, seed)
+    for x in f:
+        print("FAIL", x)
+    print(f"fuzz_parity: seed {seed}, {time.time() - t0:.0f} s, passed cases {c}, failures {len(f)}")
+    print("kernels of the passed cases:", dict(sorted(k.items())))
+    sys.exit(1 if f else 0)
