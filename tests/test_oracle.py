@@ -237,3 +237,91 @@ def test_live_setcoefficients_upsampler_vs_reference(reflib, L, sizes):
         else:
             fl = i % 4 == 1
             assert np.array_equal(r.step(v, flush=fl, shift_mode=i % 2), m.step(v, flush=fl, shift_mode=i % 2)), (L, i)
+
+
+# ---- randomised: C oracle == numpy restatement == compiled reference over random shapes ------------------------------
+RATIOS = (1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 16, 20, 24, 32, 64)  # the instantiations oracle/ref_harness.cpp holds
+
+
+def _rand_int_taps(rng, nt):
+    """Random taps whose full-scale worst case stays inside int32 (sum |c| <= 65535: signed overflow is undefined in the
+    reference), with 1-, 2- and 3-byte magnitudes and sparse patterns."""
+    amp = int(rng.choice([3, 100, 4000, 60000]))
+    t = rng.integers(-amp, amp + 1, nt).astype(np.int64)
+    if rng.integers(3) == 0:
+        t[rng.random(nt) < 0.6] = 0
+    if not t.any():
+        t[int(rng.integers(nt))] = amp
+    s = int(np.abs(t).sum())
+    if s > 65535:
+        t = (t * 65535) // s
+        if not t.any():
+            t[nt // 2] = 1
+    return t.astype(np.int32)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_shapes_oracle_vs_reference(corc, reflib, seed):
+    """40 random scripts per seed: decimator (both headers where the tap count allows, left shift, 1-3 ragged streaming
+    blocks with carried history), upsampler (both overloads, flush, trailing zero taps), mixer (random frequencies with
+    adjustFrequency in mid-stream), float decimator -- C oracle == numpy restatement == the unmodified reference."""
+    rng = np.random.default_rng(1000 + seed)
+    for case in range(40):
+        kind = int(rng.integers(4))
+        if kind == 0:
+            M = int(rng.choice(RATIOS))
+            nt = int(rng.integers(1, 400))
+            if rng.integers(3) == 0:
+                nt = M * max(1, nt // M)  # a multiple of M: the new header accepts it
+            taps = _rand_int_taps(rng, nt)
+            ls = int(rng.integers(0, 3)) if corc.dec_coeff_scaling(taps) >= 2 else 0
+            variant = 1 if nt % M == 0 and rng.integers(2) else 0
+            d = O.RefDecimator(reflib, M, taps, variant=variant)
+            d.setLeftShiftBy2(ls)
+            h = hn = None
+            for _ in range(int(rng.integers(1, 4))):
+                n = M * ((nt + int(rng.integers(0, 900))) // M + 1)  # >= ntaps - 1 (shorter blocks read out of bounds in the reference)
+                x = rng.integers(-32768, 32768, (n, 2)).astype(np.int16)
+                y, h = corc.dec_step(taps, M, x, h, ls)
+                yn, hn = O.np_dec_step(taps, M, x, hn, ls)
+                assert np.array_equal(d.step(x), y) and np.array_equal(yn, y), ("dec", seed, case, M, nt, ls, variant)
+        elif kind == 1:
+            L = int(rng.choice(RATIOS))
+            H = int(rng.integers(1, 17))
+            taps = _rand_int_taps(rng, L * H)
+            if rng.integers(2):
+                taps[-int(rng.integers(1, L * H)):] = 0 if L * H > 1 else taps[-1:]
+                if not taps.any():
+                    taps[0] = 1
+            u = O.RefUpsampler(reflib, L, taps)
+            assert u.getLength() == corc.up_length(taps)
+            h = None
+            nblk = int(rng.integers(1, 4))
+            for blk in range(nblk):
+                x = rng.integers(-32768, 32768, (int(rng.integers(1, 400)), 2)).astype(np.int16)
+                flush, sm = (blk == nblk - 1 and bool(rng.integers(2))), int(rng.integers(2))
+                y, h = corc.up_step(taps, L, x, h, flush, sm)
+                assert np.array_equal(u.step(x, flush, sm), y), ("up", seed, case, L, H, blk, flush, sm)
+        elif kind == 2:
+            n_table = int(rng.choice([256, 1024, 4096, 8192]))
+            m = O.RefMixer(reflib, n_table)
+            f = float(np.float32(rng.uniform(-1, 1)))
+            m.setFrequency(f)
+            fr, phi = corc.mixer_set_frequency(f, n_table), 0
+            assert fr == m.freq
+            for blk in range(3):
+                x = rng.integers(-32768, 32768, (int(rng.integers(1, 3000)), 2)).astype(np.int16)
+                y, phi = corc.mixer_step(x, phi, fr, n_table)
+                assert np.array_equal(m.step(x), y) and phi == m.phi, ("mixer", seed, case, f, n_table, blk)
+        else:
+            M = int(rng.choice(RATIOS))
+            nt = int(rng.integers(1, 300))
+            tk = int(rng.integers(3))
+            t = (rng.normal(0, 1, nt) / nt if tk == 0 else rng.integers(-200, 201, nt) if tk == 1 else rng.uniform(-3, 3, nt)).astype(np.float32)
+            d = O.RefDecF(reflib, M, t, obsolete=True)
+            h = None
+            for _ in range(int(rng.integers(1, 3))):
+                n = M * ((nt + int(rng.integers(0, 600))) // M + 1)
+                x = rng.uniform(-30000, 30000, (n, 2)).astype(np.float32)
+                y, h = corc.decf_step(t, M, x, h)
+                assert np.array_equal(d.step(x), y), ("decf", seed, case, M, nt, tk)
