@@ -300,7 +300,7 @@ def test_float_many_tiles_split_invariance_and_spot_check(S, corc):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("M,nt", [(4, 63), (8, 64), (16, 255), (32, 97), (16, 1500), (16, 256), (8, 23)])
+@pytest.mark.parametrize("M,nt", [(4, 63), (8, 64), (16, 255), (32, 97), (16, 1500), (16, 256), (8, 23), (32, 14000)])
 @pytest.mark.parametrize("off", [2, 3])
 def test_float_quad_kernel_interior_tiles(S, corc, monkeypatch, M, nt, off):
     """Many interior tiles (cp.async staging, padded lane stride) of the four-outputs-per-thread kernel, forced for every
@@ -316,11 +316,35 @@ def test_float_quad_kernel_interior_tiles(S, corc, monkeypatch, M, nt, off):
     q = S.FilterDnsamplingFirFloat(M, t, channels=C, obsolete=True)
     assert q.last_kernel.startswith("decf_quad")
     monkeypatch.setenv("SRCDSP_DECF_QUAD", "0")
-    p = S.FilterDnsamplingFirFloat(M, t, channels=C, obsolete=True)
-    assert p.last_kernel.startswith("decf_fir")
+    try:
+        p = S.FilterDnsamplingFirFloat(M, t, channels=C, obsolete=True)
+        assert p.last_kernel.startswith("decf_fir")
+    except S.SrcDspError as e:  # the pair kernel keeps two shifted tap copies in shared memory: the longest filters only fit the quad kernel
+        assert e.code == -2 and nt > 10000
+        p = None
     h = None
     for a, b in ((0, n + M * 6), (n + M * 6, 2 * n)):
-        yq, yp = q.step(x[:, a:b]), p.step(x[:, a:b])
-        assert torch.equal(yq, yp)
+        yq = q.step(x[:, a:b])
+        if p is not None:
+            assert torch.equal(yq, p.step(x[:, a:b]))
         e, h = corc.decf_step(t, M, host(x[1, a:b]), h)
         assert np.array_equal(host(yq[1]), e)
+
+
+@pytest.mark.gpu
+def test_float_longest_filters_fall_back_to_the_kernel_that_fits(S, corc):
+    """/4 keeps the pair kernel by default, but its two shifted tap copies stop fitting shared memory before the quad
+    kernel's single copy does: 16000 taps run on the quad kernel instead of failing.  Beyond both, E_SIZE."""
+    rng = np.random.default_rng(99)
+    M, nt = 4, 16000
+    t = ftaps(rng, nt, "frac")
+    d = S.FilterDnsamplingFirFloat(M, t, obsolete=True)
+    assert d.last_kernel.startswith("decf_quad")
+    h = None
+    for n in (M * 2500, M * 700):
+        x = rng.uniform(-30000, 30000, (n, 2)).astype(np.float32)
+        e, h = corc.decf_step(t, M, x, h)
+        assert np.array_equal(d.step(x), e)
+    with pytest.raises(S.SrcDspError) as ei:
+        S.FilterDnsamplingFirFloat(M, ftaps(rng, 40000, "frac"), obsolete=True)
+    assert ei.value.code == -2
