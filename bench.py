@@ -272,15 +272,18 @@ def cpu_reference_run(w, steps: int, warmup: int, cores: int, target_cpu_seconds
                 seconds=t), t
 
 
-def fifo_stream_bench(args, w, base, S, O, torch, device):
+def fifo_stream_bench(args, w, base, S, torch, device):
     """a producer thread writes time-stamped blocks into the pinned FifoWithTimeTrack, the
     consumer takes zero-copy segments of the ring and runs the decimator on them (H2D DMA straight from the ring,
     D2H of the outputs).  End-to-end by construction: value == e2e."""
     n, M, nt, blocks = w["n"], w["M"], w["ntaps"], w["blocks"]
     fifo = S.FifoWithTimeTrack(4 * n, 1e8)
-    dec = S.FilterDnsamplingFir(M, O.design_lowpass_taps(nt, M), channels=1, device=device, obsolete=True)
+    dec = S.FilterDnsamplingFir(M, S.design_lowpass_taps(nt, M), channels=1, device=device, obsolete=True)
     src = S.PinnedBuffer(1, n)
-    src.array[0] = O.corc().synth(SEED, 0, 0, n, 2)
+    blk = torch.empty((1, n, 2), dtype=torch.int16, device="cuda")
+    S.synth_fill(blk, SEED, ch0=0, n0=0, amp_shift=2)
+    src.array[0] = blk[0].cpu().numpy()
+    del blk
     out = S.PinnedBuffer(1, n // M)
     total = args.warmup + args.steps * blocks
     state = {"written": 0, "stop": False}
@@ -369,7 +372,7 @@ def corr_bench(args, w, base, S, torch, device):
     return 0
 
 
-def decf_bench(args, w, base, S, O, torch, device):
+def decf_bench(args, w, base, S, torch, device):
     """The float instantiation FilterDnsamplingFir<complex<float>, ..., float, M> (bit-exact with the reference's
     tap-order float sum).  Algorithmic bytes per output: 8*M + 8; arithmetic: 4*ntaps rounded FP32 operations per
     output (a separate multiply and add per component and tap -- fusing them would change the result), which makes the
@@ -408,6 +411,7 @@ def decf_bench(args, w, base, S, O, torch, device):
                              "as packed FFMA2(x, k, -0.0) + FADD2 on (re, im): the same two roundings per component")
     cpu = None
     if not args.no_cpu:
+        import oracle as O  # cpu_baseline leg: the compiled reference
         r = O.ref()
         if r is not None:  # the unmodified reference's float instantiation, one thread, a bounded sample of the workload
             import time
@@ -477,7 +481,7 @@ STREAM_SAMPLES = 1 << 32   # BASELINE configs[4]: "single very long stream (4G c
 STREAM_CALL = 1 << 29      # samples per step() call (the reference indexes with int: < 2^31 per call)
 
 
-def stream_bench(args, w, base, S, O, torch, dist, rank, world, local_rank, timed, roofline_of, time_slices):
+def stream_bench(args, w, base, S, torch, dist, rank, world, local_rank, timed, roofline_of, time_slices):
     """BASELINE configs[4] as a fixed job (strong scaling): ONE stream of 2^32 complex samples, decimate-by-4 1023-tap FIR,
     cut into `world` time slices at multiples of the decimation.  Rank g holds samples [start - warm, start + length) of
     the stream in HBM; a step = reset, warm-up run over the halo in front of the slice (outputs discarded; rank 0 has
@@ -489,7 +493,7 @@ def stream_bench(args, w, base, S, O, torch, dist, rank, world, local_rank, time
     y = torch.empty((1, sl.length // M, 2), dtype=torch.int16, device="cuda")
     scratch = torch.empty((1, max(1, sl.warmup // M), 2), dtype=torch.int16, device="cuda")
     S.synth_fill(x, 0x5EED0005, ch0=0, n0=sl.start - sl.warmup, amp_shift=2)
-    dec = S.FilterDnsamplingFir(M, O.design_lowpass_taps(nt, M), channels=1, device=local_rank, obsolete=True)
+    dec = S.FilterDnsamplingFir(M, S.design_lowpass_taps(nt, M), channels=1, device=local_rank, obsolete=True)
     dec.set_kernel(args.kernel)
     calls = [(o, min(STREAM_CALL, sl.length - o)) for o in range(0, sl.length, STREAM_CALL)]
 
@@ -519,7 +523,7 @@ def stream_bench(args, w, base, S, O, torch, dist, rank, world, local_rank, time
     return 0
 
 
-def group_bench(args, w, base, S, O, torch):
+def group_bench(args, w, base, S, torch):
     """cfg3 / cfg5 through the single-process multi-device driver (srcdsp_group_*): pinned host buffers in and out, one
     host thread + three streams per device, outputs written to their final place -- north_star's "results are gathered to
     the host with async copies from pinned memory".  End to end by construction (value == e2e)."""
@@ -528,10 +532,10 @@ def group_bench(args, w, base, S, O, torch):
     G = args.gpus
     if args.workload == "cfg5":
         C, n, M1, M2, nt, mode = 1, STREAM_SAMPLES, w["M"], 0, w["ntaps"], "slices"
-        grp = S.DdcGroup(mode, list(range(G)), C, M1, O.design_lowpass_taps(nt, M1))
+        grp = S.DdcGroup(mode, list(range(G)), C, M1, S.design_lowpass_taps(nt, M1))
     elif args.workload == "cfg3":
         C, n, M1, M2, nt, mode = w["channels"], w["n"], w["M"], w["M2"], w["ntaps"], "channels"
-        grp = S.DdcGroup(mode, list(range(G)), C, M1, O.design_lowpass_taps(nt, M1), M2, O.design_lowpass_taps(w["ntaps2"], M2), n_table=4096)
+        grp = S.DdcGroup(mode, list(range(G)), C, M1, S.design_lowpass_taps(nt, M1), M2, S.design_lowpass_taps(w["ntaps2"], M2), n_table=4096)
         grp.setFrequency((-1 + 2 * (np.arange(C) + 0.5) / C).astype(np.float32))
     else:
         raise SystemExit("--group is for the workloads that shard one job: cfg3 (channel batches), cfg5 (time slices)")
@@ -622,7 +626,6 @@ def main():
 
     # ------------------------------------------------------------------------------------------
     import torch
-    import oracle as O          # tap design + cpu_baseline leg only
     import srcdsp_b200 as S
 
     if not torch.cuda.is_available():
@@ -637,13 +640,13 @@ def main():
 
     C, n, M, nt = w["channels"], w["n"], w["M"], w["ntaps"]
     if w["kind"] == "fifo":
-        return fifo_stream_bench(args, w, base, S, O, torch, local_rank)
+        return fifo_stream_bench(args, w, base, S, torch, local_rank)
     if w["kind"] == "corr":
         return corr_bench(args, w, base, S, torch, local_rank)
     if w["kind"] == "decf":
-        return decf_bench(args, w, base, S, O, torch, local_rank)
+        return decf_bench(args, w, base, S, torch, local_rank)
     if args.group:
-        return group_bench(args, w, base, S, O, torch)
+        return group_bench(args, w, base, S, torch)
     from srcdsp_b200.sharding import channel_shard, time_slices
 
     def barrier():
@@ -697,9 +700,9 @@ def main():
             chain.setFrequency(lo_freqs(ch, total_ch))
             return chain, None, [chain]
         if wk["kind"] == "up":
-            chain = S.FilterUpsamplingFir(Mw, O.design_interp_taps(ntw, Mw), channels=Cc, device=local_rank)
+            chain = S.FilterUpsamplingFir(Mw, S.design_interp_taps(ntw, Mw), channels=Cc, device=local_rank)
             return chain, None, [chain]
-        taps = O.design_lowpass_taps(ntw, Mw)
+        taps = S.design_lowpass_taps(ntw, Mw)
         if args.taps == "impulse":
             taps = np.zeros(ntw, np.int32)
             taps[ntw // 2] = 32767
@@ -713,7 +716,7 @@ def main():
             mix.setFrequency(lo_freqs(ch, total_ch))
             d2 = None
             if wk["kind"] == "ddc2":
-                d2 = S.FilterDnsamplingFir(wk["M2"], O.design_lowpass_taps(wk["ntaps2"], wk["M2"]), channels=Cc,
+                d2 = S.FilterDnsamplingFir(wk["M2"], S.design_lowpass_taps(wk["ntaps2"], wk["M2"]), channels=Cc,
                                            device=local_rank, obsolete=True)
                 stateful.append(d2)
             chain = S.Ddc(mix, d, d2)
@@ -762,7 +765,7 @@ def main():
     # contiguous batches; cfg5 = ONE 2^32-sample stream cut into time slices with a warm-up halo
     # ------------------------------------------------------------------------------------------
     if args.workload == "cfg5":
-        return stream_bench(args, w, base, S, O, torch, dist, rank, world, local_rank, timed, roofline_of, time_slices)
+        return stream_bench(args, w, base, S, torch, dist, rank, world, local_rank, timed, roofline_of, time_slices)
     strong = args.workload == "cfg3"
     total_ch = C if strong else C * world
     my_ch = channel_shard(total_ch, world, rank)

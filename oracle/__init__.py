@@ -807,7 +807,8 @@ def np_up_step(taps, L: int, x: np.ndarray, history: np.ndarray | None = None,
 
 
 # ----------------------------------------------------------------------------------------------
-# tap design used by tests and bench: Hamming-windowed sinc, cutoff 1/ratio
+# tap design used by the tests: Hamming-windowed sinc, cutoff 1/ratio; bench.py's device arm uses
+# the product's own srcdsp_b200/design.py, which tests/test_design.py keeps equal to these
 # ----------------------------------------------------------------------------------------------
 # ----------------------------------------------------------------------------------------------
 # live objects: setCoeffs() / setCoefficients() on an object that has already filtered samples

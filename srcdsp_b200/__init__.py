@@ -24,10 +24,11 @@ import numpy as np
 
 from . import _capi
 from ._capi import SrcDspError, check, lib
+from .design import design_interp_taps, design_lowpass_taps
 
 __all__ = ["DdcGroup", "Mixer", "FilterDnsamplingFir", "FilterDnsamplingFirFloat", "FilterFirFloat", "FilterFir", "FilterUpsamplingFir", "Ddc", "SrcDspError",
            "synth_fill", "launch_count", "device_count", "PinnedBuffer", "FifoWithTimeTrack", "saveBinarySamples",
-           "readBinarySamples", "FixedPatternCorrelator"]
+           "readBinarySamples", "FixedPatternCorrelator", "design_lowpass_taps", "design_interp_taps"]
 
 
 # ----------------------------------------------------------------------------------------------

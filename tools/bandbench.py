@@ -5,7 +5,6 @@ import sys, os, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-import oracle as O
 import srcdsp_b200 as S
 
 
@@ -14,7 +13,7 @@ def run(M, nt, C, n, kind, mix):
     x = torch.empty((C, n, 2), dtype=torch.int16, device="cuda")
     S.synth_fill(x, 1, amp_shift=2)
     y = torch.empty((C, n // M, 2), dtype=torch.int16, device="cuda")
-    d = S.FilterDnsamplingFir(M, O.design_lowpass_taps(nt, M), channels=C, obsolete=True)
+    d = S.FilterDnsamplingFir(M, S.design_lowpass_taps(nt, M), channels=C, obsolete=True)
     d.set_kernel(kind)
     ch = d
     if mix:

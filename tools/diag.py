@@ -2,13 +2,12 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-import oracle as O
 import srcdsp_b200 as S
 C, n, M, nt = 64, 1 << 22, 16, 255
 x = torch.empty((C, n, 2), dtype=torch.int16, device="cuda")
 y = torch.empty((C, n // M, 2), dtype=torch.int16, device="cuda")
 S.synth_fill(x, 1)
-d = S.FilterDnsamplingFir(M, O.design_lowpass_taps(nt, M), channels=C, obsolete=True)
+d = S.FilterDnsamplingFir(M, S.design_lowpass_taps(nt, M), channels=C, obsolete=True)
 try:
     d.step(x, out=y)
     torch.cuda.synchronize()

@@ -3,7 +3,6 @@ import sys, os, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-import oracle as O
 import srcdsp_b200 as S
 mixer = sys.argv[1] == "ddc16"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 60
@@ -11,7 +10,7 @@ C, n, M, nt = 256, 1 << 24, 16, 255
 x = torch.empty((C, n, 2), dtype=torch.int16, device="cuda")
 y = torch.empty((C, n // M, 2), dtype=torch.int16, device="cuda")
 S.synth_fill(x, 0x5EED0002, amp_shift=2)
-d = S.FilterDnsamplingFir(M, O.design_lowpass_taps(nt, M), channels=C, obsolete=True)
+d = S.FilterDnsamplingFir(M, S.design_lowpass_taps(nt, M), channels=C, obsolete=True)
 chain = d
 if mixer:
     m = S.Mixer(channels=C)

@@ -6,7 +6,6 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import oracle as O  # tap design only
 import srcdsp_b200 as S
 
 L, nt = int(sys.argv[1]), int(sys.argv[2])
@@ -18,7 +17,7 @@ y = torch.empty((C, n * L, 2), dtype=torch.int16, device="cuda")
 for tc, form in (("0", "1"), ("1", "1"), ("1", "2")):
     os.environ["SRCDSP_UP_TC"] = tc
     os.environ["SRCDSP_UP_TC_FORM"] = form
-    u = S.FilterUpsamplingFir(L, O.design_interp_taps(nt, L), channels=C)
+    u = S.FilterUpsamplingFir(L, S.design_interp_taps(nt, L), channels=C)
     for _ in range(3):
         u.step(x, out=y)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
