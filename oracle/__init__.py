@@ -807,10 +807,6 @@ def np_up_step(taps, L: int, x: np.ndarray, history: np.ndarray | None = None,
 
 
 # ----------------------------------------------------------------------------------------------
-# tap design used by the tests (SURVEY.md 8(d)): Hamming-windowed sinc, cutoff 1/ratio; bench.py's device arm uses
-# the product's own srcdsp_b200/design.py, which tests/test_design.py keeps equal to these
-# ----------------------------------------------------------------------------------------------
-# ----------------------------------------------------------------------------------------------
 # live objects: setCoeffs() / setCoefficients() on an object that has already filtered samples
 # ----------------------------------------------------------------------------------------------
 class NpDecimatorLive:
@@ -889,6 +885,10 @@ class NpUpsamplerLive:
         return out
 
 
+# ----------------------------------------------------------------------------------------------
+# tap design used by the tests (SURVEY.md 8(d)): Hamming-windowed sinc, cutoff 1/ratio; bench.py's device arm uses
+# the product's own srcdsp_b200/design.py, which tests/test_design.py keeps equal to these
+# ----------------------------------------------------------------------------------------------
 def design_lowpass_taps(ntaps: int, ratio: int, target_sum: int = 49152, pad_to: int | None = None) -> np.ndarray:
     """int32 taps with 32768 <= sum|c| <= 65535 (coeffScaling = 15, no int32 overflow for any
     int16 input).  pad_to appends zero taps (output-identical, SURVEY.md section 0 trap (i))."""

@@ -121,3 +121,51 @@ def test_world_size_2_gloo_channel_sharding(corc):
         y, _ = corc.dec_step(taps, M, corc.synth(0x5EED0003, ch, 0, n, 0))
         ref += int(y.astype(np.int64).sum()) + 31 * ch
     assert tmax == 2.0 and units == C * (n // M) and chk == ref
+
+
+def _slice_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    import oracle as OO
+    from srcdsp_b200.sharding import time_slices as ts
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n, M, nt = 4 * 5000, 4, 1023
+    taps = OO.design_lowpass_taps(nt, M)
+    c = OO.corc()
+    sl = ts(n, world, [nt], [M])[rank]
+    # what bench.py --workload cfg5 does per rank: the rank holds [start - warmup, start + length) of the ONE stream
+    # (counter-based synthesis: no rank needs another rank's samples), warm-up with outputs discarded, then its slice
+    x = c.synth(0x5EED0005, 0, sl.start - sl.warmup, sl.warmup + sl.length, 0)
+    h = None
+    if sl.warmup:
+        _, h = c.dec_step(taps, M, x[:sl.warmup], h)
+    y, _ = c.dec_step(taps, M, x[sl.warmup:], h)
+    assert y.shape[0] == sl.out_length
+    # outputs land at [out_start, out_start + out_length) of the stream's output; summing the disjoint pieces is
+    # the test's stand-in for "one pinned host buffer at per-device offsets" (no data-path collective in the product)
+    full = torch.zeros((n // M, 2), dtype=torch.int32)
+    full[sl.out_start:sl.out_start + sl.out_length] = torch.from_numpy(y.astype(np.int32))
+    dist.all_reduce(full, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        q.put(full.numpy().astype(np.int16))
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_time_slices(corc):
+    """cfg5's partition on two ranks: slice + warm-up halo per rank == the sequential run of the whole stream."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_slice_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    got = q.get(timeout=120)
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n, M, nt = 4 * 5000, 4, 1023
+    whole, _ = corc.dec_step(O.design_lowpass_taps(nt, M), M, corc.synth(0x5EED0005, 0, 0, n, 0))
+    assert np.array_equal(got, whole)
