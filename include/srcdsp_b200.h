@@ -8,7 +8,8 @@
  *
  * Conventions
  *   - every function returns an int status: 0 = SRCDSP_OK, negative = SRCDSP_E_*;
- *     srcdsp_last_error() returns a thread-local message for the last failure.  Nothing throws.
+ *     srcdsp_last_error() returns a thread-local message for the last failure.  Nothing throws:
+ *     every entry point catches C++ exceptions at the boundary (std::bad_alloc -> SRCDSP_E_NOMEM).
  *   - a handle is a BANK of `channels` independent streams that share taps (the reference
  *     models a channel as one object; a bank with channels == 1 is exactly one object).
  *   - samples are interleaved I/Q int16 (byte-identical to std::vector<std::complex<int16_t>>

@@ -45,6 +45,27 @@ int fail(int code, const char *fmt, ...)
     return code;
 }
 
+int abi_exception() noexcept
+{
+    try {
+        throw;  // re-throw the exception the entry point's handler caught
+    } catch (const std::bad_alloc &) {
+        try {
+            return fail(SRCDSP_E_NOMEM, "out of host memory");
+        } catch (...) {
+            return SRCDSP_E_NOMEM;
+        }
+    } catch (const std::exception &e) {
+        try {
+            return fail(SRCDSP_E_INVALID, "unexpected C++ exception: %s", e.what());
+        } catch (...) {
+            return SRCDSP_E_INVALID;
+        }
+    } catch (...) {
+        return SRCDSP_E_INVALID;
+    }
+}
+
 static std::atomic<uint64_t> g_launches{0};
 static inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
@@ -141,6 +162,24 @@ struct DeviceGuard {
     ~DeviceGuard()
     {
         if (changed) cudaSetDevice(prev);
+    }
+};
+
+// device allocation that is freed unless its owner takes it over (error paths of the set-up code)
+struct DeviceBuffer {
+    void *p = nullptr;
+    DeviceBuffer() = default;
+    DeviceBuffer(const DeviceBuffer &) = delete;
+    DeviceBuffer &operator=(const DeviceBuffer &) = delete;
+    ~DeviceBuffer()
+    {
+        if (p) cudaFree(p);
+    }
+    void *release()
+    {
+        void *q = p;
+        p = nullptr;
+        return q;
     }
 };
 
@@ -696,28 +735,29 @@ struct DecBank : Bank {
             return fail(SRCDSP_E_SIZE, "M=%d with %d taps does not fit the 227 KB shared-memory tile", M, n);
         std::vector<int32_t> poly((size_t)M * newQp, 0);
         for (int k = 0; k < n; ++k) poly[(size_t)(k % M) * newQp + k / M] = t[k];
-        int32_t *nd = nullptr;
-        SRCDSP_CUDA(cudaMalloc(&nd, poly.size() * 4));
-        SRCDSP_CUDA(cudaMemcpy(nd, poly.data(), poly.size() * 4, cudaMemcpyHostToDevice));
+        // the new buffers are owned locally until everything that can fail has succeeded: a failed call leaves the
+        // bank as it was and leaks nothing
+        DeviceBuffer nd, nh[2];
+        SRCDSP_CUDA(cudaMalloc(&nd.p, poly.size() * 4));
+        SRCDSP_CUDA(cudaMemcpy(nd.p, poly.data(), poly.size() * 4, cudaMemcpyHostToDevice));
         // history.resize(n-1) (dsptl_dnsampling_filters.h:127): keeps the first min(old,new)
         // entries, value-initialises the rest
-        uint32_t *nh[2] = {nullptr, nullptr};
         const size_t hw = (size_t)C * (newH > 0 ? newH : 1);
         for (int k = 0; k < 2; ++k) {
-            SRCDSP_CUDA(cudaMalloc(&nh[k], hw * 4));
-            SRCDSP_CUDA(cudaMemset(nh[k], 0, hw * 4));
+            SRCDSP_CUDA(cudaMalloc(&nh[k].p, hw * 4));
+            SRCDSP_CUDA(cudaMemset(nh[k].p, 0, hw * 4));
         }
         if (d_hist[cur] && H > 0 && newH > 0) {
             const int keep = H < newH ? H : newH;
-            SRCDSP_CUDA(cudaMemcpy2D(nh[0], (size_t)newH * 4, d_hist[cur], (size_t)H * 4, (size_t)keep * 4, C,
+            SRCDSP_CUDA(cudaMemcpy2D(nh[0].p, (size_t)newH * 4, d_hist[cur], (size_t)H * 4, (size_t)keep * 4, C,
                                      cudaMemcpyDeviceToDevice));
         }
         if (d_taps_poly) cudaFree(d_taps_poly);
         if (d_hist[0]) cudaFree(d_hist[0]);
         if (d_hist[1]) cudaFree(d_hist[1]);
-        d_taps_poly = nd;
-        d_hist[0] = nh[0];
-        d_hist[1] = nh[1];
+        d_taps_poly = static_cast<int32_t *>(nd.release());
+        d_hist[0] = static_cast<uint32_t *>(nh[0].release());
+        d_hist[1] = static_cast<uint32_t *>(nh[1].release());
         cur = 0;
         taps.assign(t, t + n);
         ntaps = n;
@@ -1615,43 +1655,43 @@ struct UpBank : Bank {
         int len = n;
         while (len > 0 && t[len - 1] == 0) --len;  // upsampling_filters.h:122-123
         if (len == 0) return fail(SRCDSP_E_SIZE, "all taps are zero (the reference reads coeff[-1] here)");
-        int32_t *nd = nullptr;
-        SRCDSP_CUDA(cudaMalloc(&nd, poly.size() * 4));
-        SRCDSP_CUDA(cudaMemcpy(nd, poly.data(), poly.size() * 4, cudaMemcpyHostToDevice));
+        DeviceBuffer nd;  // freed on every early return below
+        SRCDSP_CUDA(cudaMalloc(&nd.p, poly.size() * 4));
+        SRCDSP_CUDA(cudaMemcpy(nd.p, poly.data(), poly.size() * 4, cudaMemcpyHostToDevice));
         if (newH != H) {
             // buffer.resize(newH) on the RAW circular buffer with `top` unchanged
             // (upsampling_filters.h:118): rebuild the raw buffer from age order, resize, re-age.
             std::vector<uint32_t> nh((size_t)C * newH, 0);
+            unsigned long long new_top = top;
             if (H > 0 && d_hist[cur]) {
                 std::vector<uint32_t> oh((size_t)C * H);
                 SRCDSP_CUDA(cudaMemcpy(oh.data(), d_hist[cur], oh.size() * 4, cudaMemcpyDeviceToHost));
                 const int tp = (int)(top % (unsigned long long)H);
-                if (tp >= newH) {
-                    cudaFree(nd);
+                if (tp >= newH)
                     return fail(SRCDSP_E_STATE,
                                 "setCoefficients shrinks the buffer below the insertion index (top=%d, new size %d): "
                                 "the reference writes out of bounds here; call reset() first", tp, newH);
-                }
                 std::vector<uint32_t> raw(std::max(H, newH));
                 for (int c = 0; c < C; ++c) {
                     std::fill(raw.begin(), raw.end(), 0u);
                     for (int k = 0; k < H; ++k) raw[(tp + k) % H] = oh[(size_t)c * H + k];
                     for (int k = 0; k < newH; ++k) nh[(size_t)c * newH + k] = raw[(tp + k) % newH];
                 }
-                top = (unsigned long long)tp;
+                new_top = (unsigned long long)tp;
             }
-            uint32_t *b0 = nullptr, *b1 = nullptr;
-            SRCDSP_CUDA(cudaMalloc(&b0, nh.size() * 4));
-            SRCDSP_CUDA(cudaMalloc(&b1, nh.size() * 4));
-            SRCDSP_CUDA(cudaMemcpy(b0, nh.data(), nh.size() * 4, cudaMemcpyHostToDevice));
+            DeviceBuffer b0, b1;
+            SRCDSP_CUDA(cudaMalloc(&b0.p, nh.size() * 4));
+            SRCDSP_CUDA(cudaMalloc(&b1.p, nh.size() * 4));
+            SRCDSP_CUDA(cudaMemcpy(b0.p, nh.data(), nh.size() * 4, cudaMemcpyHostToDevice));
             if (d_hist[0]) cudaFree(d_hist[0]);
             if (d_hist[1]) cudaFree(d_hist[1]);
-            d_hist[0] = b0;
-            d_hist[1] = b1;
+            d_hist[0] = static_cast<uint32_t *>(b0.release());
+            d_hist[1] = static_cast<uint32_t *>(b1.release());
             cur = 0;
+            top = new_top;
         }
         if (d_taps_poly) cudaFree(d_taps_poly);
-        d_taps_poly = nd;
+        d_taps_poly = static_cast<int32_t *>(nd.release());
         ntaps = n;
         H = newH;
         Hp = newHp;
@@ -2009,7 +2049,7 @@ int srcdsp_version(void) { return 100; }
 uint64_t srcdsp_launch_count(void) { return g_launches.load(); }
 
 int srcdsp_device_count(int *count)
-{
+try {
     if (!count) return fail(SRCDSP_E_INVALID, "count is null");
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -2021,42 +2061,48 @@ int srcdsp_device_count(int *count)
     *count = n;
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 
 int srcdsp_host_alloc(void **ptr, size_t bytes)
-{
+try {
     if (!ptr) return fail(SRCDSP_E_INVALID, "ptr is null");
     SRCDSP_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable));
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 int srcdsp_host_free(void *ptr)
-{
+try {
     SRCDSP_CUDA(cudaFreeHost(ptr));
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 int srcdsp_device_alloc(int device, void **ptr, size_t bytes)
-{
+try {
     if (!ptr) return fail(SRCDSP_E_INVALID, "ptr is null");
     SRCDSP_TRY(check_device(device));
     DeviceGuard g(device);
     SRCDSP_CUDA(cudaMalloc(ptr, bytes ? bytes : 1));
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 int srcdsp_device_free(int device, void *ptr)
-{
+try {
     DeviceGuard g(device);
     SRCDSP_CUDA(cudaFree(ptr));
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 int srcdsp_memcpy(int device, void *dst, const void *src, size_t bytes)
-{
+try {
     DeviceGuard g(device);
     SRCDSP_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDefault));
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 
 int srcdsp_synth_fill(int device, void *stream, int16_t *d_iq, size_t stride, int channels, size_t n_per_ch,
                       uint32_t seed, uint32_t ch0, uint64_t n0, int amp_shift)
-{
+try {
     SRCDSP_TRY(check_device(device));
     if (!d_iq || channels < 1 || amp_shift < 0 || amp_shift > 15) return fail(SRCDSP_E_INVALID, "bad synth arguments");
     if (!is_device_ptr(d_iq)) return fail(SRCDSP_E_INVALID, "srcdsp_synth_fill needs a device pointer");
@@ -2069,10 +2115,11 @@ int srcdsp_synth_fill(int device, void *stream, int16_t *d_iq, size_t stride, in
     count_launch();
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 
 // ---- mixer ------------------------------------------------------------------------------------
 int srcdsp_mixer_create(srcdsp_mixer_t *h, int device, int channels, unsigned n_table)
-{
+try {
     if (!h) return fail(SRCDSP_E_INVALID, "handle pointer is null");
     *h = nullptr;
     srcdsp_mixer_s *m = new (std::nothrow) srcdsp_mixer_s();
@@ -2086,13 +2133,15 @@ int srcdsp_mixer_create(srcdsp_mixer_t *h, int device, int channels, unsigned n_
     *h = m;
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 int srcdsp_mixer_destroy(srcdsp_mixer_t h)
-{
+try {
     if (!h) return SRCDSP_OK;
     h->destroy();
     delete h;
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 static int mixer_for_channels(srcdsp_mixer_t h, int ch, int *c0, int *c1)
 {
     CHECK_HANDLE(h);
@@ -2102,7 +2151,7 @@ static int mixer_for_channels(srcdsp_mixer_t h, int ch, int *c0, int *c1)
     return SRCDSP_OK;
 }
 int srcdsp_mixer_set_frequency(srcdsp_mixer_t h, int ch, float lo)
-{
+try {
     int c0, c1;
     SRCDSP_TRY(mixer_for_channels(h, ch, &c0, &c1));
     if (!(lo <= 1 && lo >= -1)) return fail(SRCDSP_E_SIZE, "loFreq %g outside [-1, 1] [mixers.h:54]", (double)lo);
@@ -2114,8 +2163,9 @@ int srcdsp_mixer_set_frequency(srcdsp_mixer_t h, int ch, float lo)
     h->dirty = true;
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 int srcdsp_mixer_set_frequencies(srcdsp_mixer_t h, const float *lo)
-{
+try {
     CHECK_HANDLE(h);
     if (!lo) return fail(SRCDSP_E_INVALID, "lo_freq is null");
     for (int c = 0; c < h->C; ++c)
@@ -2127,16 +2177,18 @@ int srcdsp_mixer_set_frequencies(srcdsp_mixer_t h, const float *lo)
     h->dirty = true;
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 int srcdsp_mixer_reset(srcdsp_mixer_t h, int ch, float lo)
-{
+try {
     int c0, c1;
     SRCDSP_TRY(mixer_for_channels(h, ch, &c0, &c1));
     if (!(lo <= 1 && lo >= -1)) return fail(SRCDSP_E_SIZE, "loFreq %g outside [-1, 1] [mixers.h:54]", (double)lo);
     for (int c = c0; c < c1; ++c) h->h_phi[c] = 0;
     return srcdsp_mixer_set_frequency(h, ch, lo);
 }
+SRCDSP_ABI_CATCH
 int srcdsp_mixer_adjust_frequency(srcdsp_mixer_t h, int ch, float adjust)
-{
+try {
     int c0, c1;
     SRCDSP_TRY(mixer_for_channels(h, ch, &c0, &c1));
     for (int c = c0; c < c1; ++c) {
@@ -2151,8 +2203,9 @@ int srcdsp_mixer_adjust_frequency(srcdsp_mixer_t h, int ch, float adjust)
     h->dirty = true;
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 int srcdsp_mixer_get_state(srcdsp_mixer_t h, int ch, int *phi, int *freq, float *nominal)
-{
+try {
     CHECK_HANDLE(h);
     if (ch < 0 || ch >= h->C) return fail(SRCDSP_E_INVALID, "channel %d out of range", ch);
     if (phi) *phi = h->h_phi[ch];
@@ -2160,8 +2213,9 @@ int srcdsp_mixer_get_state(srcdsp_mixer_t h, int ch, int *phi, int *freq, float 
     if (nominal) *nominal = h->h_nominal[ch];
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 int srcdsp_mixer_set_state(srcdsp_mixer_t h, int ch, int phi, int freq, float nominal)
-{
+try {
     CHECK_HANDLE(h);
     if (ch < 0 || ch >= h->C) return fail(SRCDSP_E_INVALID, "channel %d out of range", ch);
     if (phi < 0 || phi >= (int)h->n_table || freq < 0 || freq >= (int)h->n_table)
@@ -2172,9 +2226,10 @@ int srcdsp_mixer_set_state(srcdsp_mixer_t h, int ch, int phi, int freq, float no
     h->dirty = true;
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 int srcdsp_mixer_step(srcdsp_mixer_t h, const int16_t *in, size_t in_stride, int16_t *out, size_t out_stride,
                       size_t n)
-{
+try {
     CHECK_HANDLE(h);
     if (n == 0) return SRCDSP_OK;
     if (!in || !out) return fail(SRCDSP_E_INVALID, "null buffer");
@@ -2189,20 +2244,23 @@ int srcdsp_mixer_step(srcdsp_mixer_t h, const int16_t *in, size_t in_stride, int
                           return len ? h->step_device(di, dis, dout, dos, len) : SRCDSP_OK;
                       });
 }
+SRCDSP_ABI_CATCH
 int srcdsp_mixer_set_stream(srcdsp_mixer_t h, void *s)
-{
+try {
     CHECK_HANDLE(h);
     return h->set_stream(s);
 }
+SRCDSP_ABI_CATCH
 int srcdsp_mixer_sync(srcdsp_mixer_t h)
-{
+try {
     CHECK_HANDLE(h);
     return h->sync();
 }
+SRCDSP_ABI_CATCH
 
 // ---- decimator --------------------------------------------------------------------------------
 int srcdsp_dec_create(srcdsp_dec_t *h, int device, int channels, int M)
-{
+try {
     if (!h) return fail(SRCDSP_E_INVALID, "handle pointer is null");
     *h = nullptr;
     if (M < 1 || M > 1024) return fail(SRCDSP_E_INVALID, "M must be in [1, 1024] (got %d)", M);
@@ -2217,54 +2275,62 @@ int srcdsp_dec_create(srcdsp_dec_t *h, int device, int channels, int M)
     *h = d;
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 int srcdsp_dec_destroy(srcdsp_dec_t h)
-{
+try {
     if (!h) return SRCDSP_OK;
     h->destroy();
     delete h;
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 int srcdsp_dec_set_coeffs(srcdsp_dec_t h, const int32_t *taps, int ntaps, int require_multiple_of_m)
-{
+try {
     CHECK_HANDLE(h);
     return h->set_coeffs(taps, ntaps, require_multiple_of_m);
 }
+SRCDSP_ABI_CATCH
 int srcdsp_dec_set_left_shift(srcdsp_dec_t h, int s)
-{
+try {
     CHECK_HANDLE(h);
     h->left_shift = s;
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 int srcdsp_dec_reset(srcdsp_dec_t h)
-{
+try {
     CHECK_HANDLE(h);
     return h->reset();
 }
+SRCDSP_ABI_CATCH
 int srcdsp_dec_get_coeff_scaling(srcdsp_dec_t h, int *cs)
-{
+try {
     CHECK_HANDLE(h);
     if (!cs) return fail(SRCDSP_E_INVALID, "null pointer");
     if (h->ntaps == 0) return fail(SRCDSP_E_STATE, "no coefficients");
     *cs = h->coeff_scaling;
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 int srcdsp_dec_set_kernel(srcdsp_dec_t h, int kind)
-{
+try {
     CHECK_HANDLE(h);
     if (kind < 0 || kind > 5) return fail(SRCDSP_E_INVALID, "kernel kind must be in [0, 5]");
     h->kernel_kind = kind;
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 int srcdsp_dec_get_last_kernel(srcdsp_dec_t h, int *kind)
-{
+try {
     CHECK_HANDLE(h);
     if (!kind) return fail(SRCDSP_E_INVALID, "null pointer");
     *kind = h->last_kernel;
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 int srcdsp_dec_step(srcdsp_dec_t h, const int16_t *in, size_t in_stride, size_t n_in, int16_t *out,
                     size_t out_stride)
-{
+try {
     CHECK_HANDLE(h);
     if (h->ntaps == 0) return fail(SRCDSP_E_STATE, "decimator has no coefficients (call srcdsp_dec_set_coeffs)");
     if (n_in % (size_t)h->M != 0)
@@ -2285,6 +2351,7 @@ int srcdsp_dec_step(srcdsp_dec_t h, const int16_t *in, size_t in_stride, size_t 
                           return h->step_device(di, dis, len, dout, dos, nullptr);
                       });
 }
+SRCDSP_ABI_CATCH
 static int hist_io(Bank &b, uint32_t *d_hist, int H, int ch, int16_t *get, const int16_t *set, size_t *n)
 {
     if (ch < 0 || ch >= b.C) return fail(SRCDSP_E_INVALID, "channel %d out of range", ch);
@@ -2300,7 +2367,7 @@ static int hist_io(Bank &b, uint32_t *d_hist, int H, int ch, int16_t *get, const
     return SRCDSP_OK;
 }
 int srcdsp_dec_get_state(srcdsp_dec_t h, int ch, int16_t *hist, size_t *n)
-{
+try {
     CHECK_HANDLE(h);
     if (h->ntaps == 0) return fail(SRCDSP_E_STATE, "no coefficients");
     if (!hist) {
@@ -2309,27 +2376,31 @@ int srcdsp_dec_get_state(srcdsp_dec_t h, int ch, int16_t *hist, size_t *n)
     }
     return hist_io(*h, h->d_hist[h->cur], h->H, ch, hist, nullptr, n);
 }
+SRCDSP_ABI_CATCH
 int srcdsp_dec_set_state(srcdsp_dec_t h, int ch, const int16_t *hist, size_t n)
-{
+try {
     CHECK_HANDLE(h);
     if (h->ntaps == 0) return fail(SRCDSP_E_STATE, "no coefficients");
     if (!hist && h->H > 0) return fail(SRCDSP_E_INVALID, "null state");
     return hist_io(*h, h->d_hist[h->cur], h->H, ch, nullptr, hist, &n);
 }
+SRCDSP_ABI_CATCH
 int srcdsp_dec_set_stream(srcdsp_dec_t h, void *s)
-{
+try {
     CHECK_HANDLE(h);
     return h->set_stream(s);
 }
+SRCDSP_ABI_CATCH
 int srcdsp_dec_sync(srcdsp_dec_t h)
-{
+try {
     CHECK_HANDLE(h);
     return h->sync();
 }
+SRCDSP_ABI_CATCH
 
 // ---- fused DDC chain ----------------------------------------------------------------------------
 int srcdsp_ddc_create(srcdsp_ddc_t *h, srcdsp_mixer_t mixer, srcdsp_dec_t dec1, srcdsp_dec_t dec2)
-{
+try {
     if (!h) return fail(SRCDSP_E_INVALID, "handle pointer is null");
     *h = nullptr;
     if (!dec1) return fail(SRCDSP_E_INVALID, "dec1 is required");
@@ -2349,8 +2420,9 @@ int srcdsp_ddc_create(srcdsp_ddc_t *h, srcdsp_mixer_t mixer, srcdsp_dec_t dec1, 
     *h = d;
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 int srcdsp_ddc_destroy(srcdsp_ddc_t h)
-{
+try {
     if (!h) return SRCDSP_OK;
     if (h->d_mid) {
         DeviceGuard g(h->d1->device);
@@ -2363,9 +2435,10 @@ int srcdsp_ddc_destroy(srcdsp_ddc_t h)
     delete h;
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 int srcdsp_ddc_step(srcdsp_ddc_t h, const int16_t *in, size_t in_stride, size_t n_in, int16_t *out,
                     size_t out_stride)
-{
+try {
     CHECK_HANDLE(h);
     const size_t Mt = (size_t)h->d1->M * (h->d2 ? (size_t)h->d2->M : 1);
     if (h->d1->ntaps == 0 || (h->d2 && h->d2->ntaps == 0)) return fail(SRCDSP_E_STATE, "a decimator has no coefficients");
@@ -2386,20 +2459,23 @@ int srcdsp_ddc_step(srcdsp_ddc_t h, const int16_t *in, size_t in_stride, size_t 
                           return h->step_device(di, dis, len, dout, dos);
                       });
 }
+SRCDSP_ABI_CATCH
 int srcdsp_ddc_set_stream(srcdsp_ddc_t h, void *s)
-{
+try {
     CHECK_HANDLE(h);
     return h->d1->set_stream(s);  // reaches the members: they follow dec1 (Bank::follow)
 }
+SRCDSP_ABI_CATCH
 int srcdsp_ddc_sync(srcdsp_ddc_t h)
-{
+try {
     CHECK_HANDLE(h);
     return h->d1->sync();
 }
+SRCDSP_ABI_CATCH
 
 // ---- upsampler ----------------------------------------------------------------------------------
 int srcdsp_up_create(srcdsp_up_t *h, int device, int channels, int L)
-{
+try {
     if (!h) return fail(SRCDSP_E_INVALID, "handle pointer is null");
     *h = nullptr;
     if (L < 1 || L > UP_NT) return fail(SRCDSP_E_INVALID, "L must be in [1, %d] (got %d)", UP_NT, L);
@@ -2414,26 +2490,30 @@ int srcdsp_up_create(srcdsp_up_t *h, int device, int channels, int L)
     *h = u;
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 int srcdsp_up_destroy(srcdsp_up_t h)
-{
+try {
     if (!h) return SRCDSP_OK;
     h->destroy();
     delete h;
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 int srcdsp_up_set_coefficients(srcdsp_up_t h, const int32_t *taps, int ntaps)
-{
+try {
     CHECK_HANDLE(h);
     return h->set_coefficients(taps, ntaps);
 }
+SRCDSP_ABI_CATCH
 int srcdsp_up_reset(srcdsp_up_t h)
-{
+try {
     CHECK_HANDLE(h);
     return h->reset();
 }
+SRCDSP_ABI_CATCH
 int srcdsp_up_step(srcdsp_up_t h, const int16_t *in, size_t in_stride, size_t n_in, int16_t *out,
                    size_t out_stride, int flush, int shift_mode)
-{
+try {
     CHECK_HANDLE(h);
     if (h->ntaps == 0) return fail(SRCDSP_E_STATE, "upsampler has no coefficients [upsampling_filters.h:155]");
     if (shift_mode != 0 && shift_mode != 1) return fail(SRCDSP_E_INVALID, "shift_mode must be 0 or 1");
@@ -2460,37 +2540,42 @@ int srcdsp_up_step(srcdsp_up_t h, const int16_t *in, size_t in_stride, size_t n_
                           return h->step_device(di, dis, len, last ? n_flush : 0, dout, dos, shift_mode);
                       });
 }
+SRCDSP_ABI_CATCH
 int srcdsp_up_get_length(srcdsp_up_t h, int *v)
-{
+try {
     CHECK_HANDLE(h);
     if (!v) return fail(SRCDSP_E_INVALID, "null pointer");
     *v = h->length;
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 int srcdsp_up_get_imp_length(srcdsp_up_t h, int *v)
-{
+try {
     CHECK_HANDLE(h);
     if (!v) return fail(SRCDSP_E_INVALID, "null pointer");
     *v = h->imp_length;
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 int srcdsp_up_get_ratio(srcdsp_up_t h, int *v)
-{
+try {
     CHECK_HANDLE(h);
     if (!v) return fail(SRCDSP_E_INVALID, "null pointer");
     *v = h->L;
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 int srcdsp_up_get_last_kernel(srcdsp_up_t h, int *v)
-{
+try {
     CHECK_HANDLE(h);
     if (!v) return fail(SRCDSP_E_INVALID, "null pointer");
     *v = h->last_kernel;
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 // the public state is the H-1 samples the next outputs depend on, oldest first
 int srcdsp_up_get_state(srcdsp_up_t h, int ch, int16_t *hist, size_t *n)
-{
+try {
     CHECK_HANDLE(h);
     if (h->ntaps == 0) return fail(SRCDSP_E_STATE, "no coefficients");
     if (!hist) {
@@ -2506,8 +2591,9 @@ int srcdsp_up_get_state(srcdsp_up_t h, int ch, int16_t *hist, size_t *n)
                                cudaMemcpyDeviceToHost));
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 int srcdsp_up_set_state(srcdsp_up_t h, int ch, const int16_t *hist, size_t n)
-{
+try {
     CHECK_HANDLE(h);
     if (h->ntaps == 0) return fail(SRCDSP_E_STATE, "no coefficients");
     if (ch < 0 || ch >= h->C) return fail(SRCDSP_E_INVALID, "channel %d out of range", ch);
@@ -2519,21 +2605,24 @@ int srcdsp_up_set_state(srcdsp_up_t h, int ch, const int16_t *hist, size_t n)
                                cudaMemcpyHostToDevice));
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 int srcdsp_up_set_stream(srcdsp_up_t h, void *s)
-{
+try {
     CHECK_HANDLE(h);
     return h->set_stream(s);
 }
+SRCDSP_ABI_CATCH
 int srcdsp_up_sync(srcdsp_up_t h)
-{
+try {
     CHECK_HANDLE(h);
     return h->sync();
 }
+SRCDSP_ABI_CATCH
 
 
 // ---- correlator ---------------------------------------------------------------------------------
 int srcdsp_corr_create(srcdsp_corr_t *h, int device, int channels, int N, int S)
-{
+try {
     if (!h) return fail(SRCDSP_E_INVALID, "handle pointer is null");
     srcdsp_corr_s *b = new (std::nothrow) srcdsp_corr_s;
     if (!b) return fail(SRCDSP_E_NOMEM, "out of memory");
@@ -2545,30 +2634,35 @@ int srcdsp_corr_create(srcdsp_corr_t *h, int device, int channels, int N, int S)
     *h = b;
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 int srcdsp_corr_destroy(srcdsp_corr_t h)
-{
+try {
     if (!h) return SRCDSP_OK;
     h->destroy();
     delete h;
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 int srcdsp_corr_set_pattern(srcdsp_corr_t h, const int32_t *pattern_iq, double threshold_coeff)
-{
+try {
     CHECK_HANDLE(h);
     return h->set_pattern(pattern_iq, threshold_coeff);
 }
+SRCDSP_ABI_CATCH
 int srcdsp_corr_reset(srcdsp_corr_t h)
-{
+try {
     CHECK_HANDLE(h);
     return h->reset();
 }
+SRCDSP_ABI_CATCH
 int srcdsp_corr_step(srcdsp_corr_t h, const int16_t *in_iq, size_t in_stride, size_t n_per_ch, int *found, int *corr_index)
-{
+try {
     CHECK_HANDLE(h);
     return h->step(in_iq, in_stride, n_per_ch, found, corr_index);
 }
+SRCDSP_ABI_CATCH
 int srcdsp_corr_get_ref_bit_samples(srcdsp_corr_t h, int ch, int16_t *bits_iq)
-{
+try {
     CHECK_HANDLE(h);
     if (ch < 0 || ch >= h->C || !bits_iq) return fail(SRCDSP_E_INVALID, "bad channel or null pointer");
     DeviceGuard g(h->device);
@@ -2576,9 +2670,10 @@ int srcdsp_corr_get_ref_bit_samples(srcdsp_corr_t h, int ch, int16_t *bits_iq)
     SRCDSP_CUDA(cudaMemcpy(bits_iq, h->d_bits + (size_t)ch * h->N, (size_t)h->N * 4, cudaMemcpyDeviceToHost));
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 int srcdsp_corr_get_status(srcdsp_corr_t h, int ch, uint32_t *energy_value3, uint32_t *corr_value3, uint32_t *coeffs_energy,
                            int *coeff_scaling, double *threshold_factor)
-{
+try {
     CHECK_HANDLE(h);
     if (ch < 0 || ch >= h->C) return fail(SRCDSP_E_INVALID, "bad channel");
     DeviceGuard g(h->device);
@@ -2594,11 +2689,13 @@ int srcdsp_corr_get_status(srcdsp_corr_t h, int ch, uint32_t *energy_value3, uin
     if (threshold_factor) *threshold_factor = h->threshold_factor;
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 int srcdsp_corr_set_stream(srcdsp_corr_t h, void *cuda_stream)
-{
+try {
     CHECK_HANDLE(h);
     return h->set_stream(cuda_stream);
 }
+SRCDSP_ABI_CATCH
 
 }  // extern "C"
 

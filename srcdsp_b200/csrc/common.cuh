@@ -42,6 +42,13 @@ int fail(int code, const char *fmt, ...);
         if (_s != SRCDSP_OK) return _s;  \
     } while (0)
 
+// No C++ exception crosses the C ABI ("never throw across the ABI"): every extern "C" entry point that
+// does more than return a field is a function-try-block closed by SRCDSP_ABI_CATCH.  std::bad_alloc (a std::vector
+// growing under memory pressure) becomes SRCDSP_E_NOMEM, anything else SRCDSP_E_INVALID, with the message kept.
+int abi_exception() noexcept;
+#define SRCDSP_ABI_CATCH \
+    catch (...) { return ::srcdsp::abi_exception(); }
+
 // ---------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------

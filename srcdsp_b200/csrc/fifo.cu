@@ -38,7 +38,7 @@ using namespace srcdsp;
 extern "C" {
 
 int srcdsp_fifo_create(srcdsp_fifo_t *h, size_t elem_bytes, size_t capacity, double sampling_frequency)
-{
+try {
     if (!h || elem_bytes == 0 || capacity == 0) return fail(SRCDSP_E_INVALID, "fifo: element size and capacity must be > 0");
     srcdsp_fifo_s *f = new (std::nothrow) srcdsp_fifo_s;
     if (!f) return fail(SRCDSP_E_CUDA, "out of memory");
@@ -61,9 +61,10 @@ int srcdsp_fifo_create(srcdsp_fifo_t *h, size_t elem_bytes, size_t capacity, dou
     *h = f;
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 
 int srcdsp_fifo_destroy(srcdsp_fifo_t f)
-{
+try {
     if (!f) return SRCDSP_OK;
     if (f->pinned)
         cudaFreeHost(f->storage);
@@ -72,12 +73,13 @@ int srcdsp_fifo_destroy(srcdsp_fifo_t f)
     delete f;
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 
 int srcdsp_fifo_is_pinned(srcdsp_fifo_t f) { return f && f->pinned; }
 
 /* write: buffers.h:139-217.  n must be < capacity (the reference asserts, :144). */
 int srcdsp_fifo_write(srcdsp_fifo_t f, const void *in, size_t n, unsigned seconds, double frac_seconds)
-{
+try {
     if (!f || (!in && n)) return fail(SRCDSP_E_INVALID, "fifo: null argument");
     const size_t N = f->N;
     if (n >= N) return fail(SRCDSP_E_SIZE, "fifo write of %zu elements into a fifo of %zu: must be smaller [buffers.h:144]", n, N);
@@ -117,6 +119,7 @@ int srcdsp_fifo_write(srcdsp_fifo_t f, const void *in, size_t n, unsigned second
     }
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 
 /* the bookkeeping half of read (buffers.h:284-320): returns 1 in *error when the range is not available */
 static void fifo_locate(srcdsp_fifo_t f, size_t n, uint64_t *start, size_t *startPtr, int *error, int *adjusted)
@@ -137,7 +140,7 @@ static void fifo_locate(srcdsp_fifo_t f, size_t n, uint64_t *start, size_t *star
 
 /* read: buffers.h:284-352.  *error = the reference's return value (true = range not available). */
 int srcdsp_fifo_read(srcdsp_fifo_t f, void *out, size_t n, uint64_t *start, int *error)
-{
+try {
     if (!f || !out || !start || !error) return fail(SRCDSP_E_INVALID, "fifo: null argument");
     if (n == 0) return fail(SRCDSP_E_SIZE, "fifo read of 0 elements [buffers.h:288]");
     size_t sp = 0;
@@ -150,11 +153,12 @@ int srcdsp_fifo_read(srcdsp_fifo_t f, void *out, size_t n, uint64_t *start, int 
     if (first < n) memcpy(static_cast<uint8_t *>(out) + first * f->elem, f->storage, (n - first) * f->elem);
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 
 /* zero-copy read: the (at most two) contiguous pieces of the ring that hold [start, start + n) */
 int srcdsp_fifo_segments(srcdsp_fifo_t f, size_t n, uint64_t *start, const void **p0, size_t *n0, const void **p1,
                          size_t *n1, int *error)
-{
+try {
     if (!f || !start || !p0 || !n0 || !p1 || !n1 || !error) return fail(SRCDSP_E_INVALID, "fifo: null argument");
     if (n == 0) return fail(SRCDSP_E_SIZE, "fifo read of 0 elements [buffers.h:288]");
     size_t sp = 0;
@@ -172,10 +176,11 @@ int srcdsp_fifo_segments(srcdsp_fifo_t f, size_t n, uint64_t *start, const void 
     }
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 
 /* count: buffers.h:361-377 */
 int srcdsp_fifo_count(srcdsp_fifo_t f, size_t *count)
-{
+try {
     if (!f || !count) return fail(SRCDSP_E_INVALID, "fifo: null argument");
     std::lock_guard<std::mutex> lk(f->mx);
     if (!f->rolloverFlag)
@@ -184,10 +189,11 @@ int srcdsp_fifo_count(srcdsp_fifo_t f, size_t *count)
         *count = (size_t)((UINT64_MAX - f->timeStart) + f->timeEnd + 1);
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 
 /* reset: buffers.h:262-276 (the stored values are not cleared) */
 int srcdsp_fifo_reset(srcdsp_fifo_t f)
-{
+try {
     if (!f) return fail(SRCDSP_E_INVALID, "fifo: null handle");
     std::lock_guard<std::mutex> lk(f->mx);
     f->writePtr = 0;
@@ -196,11 +202,12 @@ int srcdsp_fifo_reset(srcdsp_fifo_t f)
     f->rolloverFlag = false;
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 
 /* getAbsoluteTime: buffers.h:396-459 */
 int srcdsp_fifo_get_absolute_time(srcdsp_fifo_t f, uint64_t time_point, double frac_time_point, unsigned *seconds,
                                   double *frac_seconds)
-{
+try {
     if (!f || !seconds || !frac_seconds) return fail(SRCDSP_E_INVALID, "fifo: null argument");
     std::lock_guard<std::mutex> lk(f->mx);
     const int64_t sampleDiff = (int64_t)(time_point - f->ref.timePoint);
@@ -216,10 +223,11 @@ int srcdsp_fifo_get_absolute_time(srcdsp_fifo_t f, uint64_t time_point, double f
     *frac_seconds = fr;
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 
 /* writePtr, timeStart, timeEnd, rolloverFlag (what dumpInfo prints, buffers.h:227-251) */
 int srcdsp_fifo_get_state(srcdsp_fifo_t f, size_t *write_ptr, uint64_t *time_start, uint64_t *time_end, int *rollover)
-{
+try {
     if (!f) return fail(SRCDSP_E_INVALID, "fifo: null handle");
     std::lock_guard<std::mutex> lk(f->mx);
     if (write_ptr) *write_ptr = f->writePtr;
@@ -228,17 +236,19 @@ int srcdsp_fifo_get_state(srcdsp_fifo_t f, size_t *write_ptr, uint64_t *time_sta
     if (rollover) *rollover = f->rolloverFlag;
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 
 /* test hook: place the time counters near the 64-bit rollover (the reference has no such entry point; its
  * rollover branches are otherwise unreachable in a test) */
 int srcdsp_fifo_set_time(srcdsp_fifo_t f, uint64_t time_start, uint64_t time_end)
-{
+try {
     if (!f) return fail(SRCDSP_E_INVALID, "fifo: null handle");
     std::lock_guard<std::mutex> lk(f->mx);
     f->timeStart = time_start;
     f->timeEnd = time_end;
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 
 const void *srcdsp_fifo_storage(srcdsp_fifo_t f) { return f ? f->storage : nullptr; }
 

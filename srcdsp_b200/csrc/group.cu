@@ -86,7 +86,7 @@ static int collect(srcdsp_group_s *g, int used)
 extern "C" {
 
 int srcdsp_group_create(srcdsp_group_t *h, int mode, const int *devices, int n_devices, int channels, unsigned n_table, int M1, int M2)
-{
+try {
     if (!h) return fail(SRCDSP_E_INVALID, "handle pointer is null");
     *h = nullptr;
     if (mode != SRCDSP_GROUP_CHANNELS && mode != SRCDSP_GROUP_SLICES) return fail(SRCDSP_E_INVALID, "mode must be SRCDSP_GROUP_CHANNELS or SRCDSP_GROUP_SLICES");
@@ -121,9 +121,10 @@ int srcdsp_group_create(srcdsp_group_t *h, int mode, const int *devices, int n_d
     *h = g.release();
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 
 int srcdsp_group_destroy(srcdsp_group_t h)
-{
+try {
     if (!h) return SRCDSP_OK;
     for (Member &m : h->members) {
         if (m.chain) srcdsp_ddc_destroy(m.chain);  // before its members
@@ -134,26 +135,29 @@ int srcdsp_group_destroy(srcdsp_group_t h)
     delete h;
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 
 int srcdsp_group_set_coeffs(srcdsp_group_t h, int stage, const int32_t *taps, int ntaps, int require_multiple_of_m)
-{
+try {
     if (!h) return fail(SRCDSP_E_INVALID, "null handle");
     if (stage != 1 && !(stage == 2 && h->M2 > 0)) return fail(SRCDSP_E_INVALID, "stage must be 1%s", h->M2 > 0 ? " or 2" : " (single-stage group)");
     for (Member &m : h->members) SRCDSP_TRY(srcdsp_dec_set_coeffs(stage == 1 ? m.d1 : m.d2, taps, ntaps, require_multiple_of_m));
     (stage == 1 ? h->ntaps1 : h->ntaps2) = ntaps;
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 
 int srcdsp_group_set_frequencies(srcdsp_group_t h, const float *lo_freq)
-{
+try {
     if (!h || !lo_freq) return fail(SRCDSP_E_INVALID, "null handle / pointer");
     if (!h->n_table) return fail(SRCDSP_E_STATE, "the group was created without a mixer (n_table == 0)");
     for (Member &m : h->members) SRCDSP_TRY(srcdsp_mixer_set_frequencies(m.mixer, lo_freq + m.ch0));
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 
 int srcdsp_group_reset(srcdsp_group_t h)
-{
+try {
     if (!h) return fail(SRCDSP_E_INVALID, "null handle");
     for (Member &m : h->members) {
         if (m.mixer)
@@ -168,26 +172,29 @@ int srcdsp_group_reset(srcdsp_group_t h)
     }
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 
 int srcdsp_group_get_layout(srcdsp_group_t h, int index, int *device, int *ch0, int *n_channels)
-{
+try {
     if (!h || index < 0 || index >= (int)h->members.size()) return fail(SRCDSP_E_INVALID, "bad handle / index");
     if (device) *device = h->members[index].device;
     if (ch0) *ch0 = h->members[index].ch0;
     if (n_channels) *n_channels = h->members[index].C;
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 
 int srcdsp_group_size(srcdsp_group_t h, int *n_members, int *used_in_last_step)
-{
+try {
     if (!h) return fail(SRCDSP_E_INVALID, "null handle");
     if (n_members) *n_members = (int)h->members.size();
     if (used_in_last_step) *used_in_last_step = h->last_used;
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 
 int srcdsp_group_step(srcdsp_group_t h, const int16_t *in, size_t in_stride, size_t n_in, int16_t *out, size_t out_stride)
-{
+try {
     if (!h) return fail(SRCDSP_E_INVALID, "null handle");
     if (!in || !out) return fail(SRCDSP_E_INVALID, "null buffer");
     const size_t Mt = (size_t)h->M1 * (size_t)(h->M2 > 0 ? h->M2 : 1);
@@ -278,5 +285,6 @@ int srcdsp_group_step(srcdsp_group_t h, const int16_t *in, size_t in_stride, siz
     }
     return SRCDSP_OK;
 }
+SRCDSP_ABI_CATCH
 
 }  // extern "C"

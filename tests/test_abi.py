@@ -88,3 +88,35 @@ def test_product_never_imports_the_oracle():
         p = os.path.join(ROOT, "include", f)
         if os.path.isfile(p):
             assert "oracle" not in open(p).read().replace("oracle/srcdsp_oracle.c:orc_synth_fill", "")
+
+
+def test_no_exception_crosses_the_abi():
+    """never throw across the ABI.  Every extern "C" entry point with a body of its own is a
+    function-try-block that ends in SRCDSP_ABI_CATCH (checked statically: provoking std::bad_alloc is not a unit test)."""
+    csrc = os.path.join(ROOT, "srcdsp_b200", "csrc")
+    guarded = 0
+    for f in ("capi.cu", "capi_decf.inc", "fifo.cu", "group.cu"):
+        lines = open(os.path.join(csrc, f)).read().split("\n")
+        lo = next(i for i, l in enumerate(lines) if l.startswith('extern "C" {'))
+        hi = next(i for i, l in enumerate(lines) if l.startswith('}  // extern "C"'))
+        i = lo
+        while i < hi:
+            l = lines[i]
+            if re.match(r"^\w[\w \*]*\bsrcdsp_\w+\(", l) and not l.startswith("static") and not l.rstrip().endswith(";"):
+                if l.rstrip().endswith("}"):  # one-line accessor: returns a field, allocates nothing
+                    assert "new " not in l and "std::" not in l, (f, l)
+                    i += 1
+                    continue
+                j = i
+                while lines[j].strip() not in ("{", "try {"):
+                    j += 1
+                assert lines[j] == "try {", f"{f}:{i + 1}: {l.strip()} is not a function-try-block"
+                k = j + 1
+                while lines[k] != "}":
+                    k += 1
+                assert lines[k + 1] == "SRCDSP_ABI_CATCH", f"{f}:{k + 2}"
+                guarded += 1
+                i = k + 1
+            else:
+                i += 1
+    assert guarded >= 80
