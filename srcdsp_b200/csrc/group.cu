@@ -63,15 +63,27 @@ using srcdsp::fail;
         }                                                  \
     } while (0)
 
-// Starting a host thread can fail (std::system_error): nothing may be thrown across the C ABI, so the member's part runs
-// on the calling thread instead.
+// Starting a host thread can fail (std::system_error) and a member's part can run out of host memory: nothing may be
+// thrown across the C ABI or out of a std::thread (that would be std::terminate), so a part that cannot get a thread
+// runs on the calling thread, and an exception inside a part becomes that member's status.
 template <class F>
-static void start_member(std::vector<std::thread> &threads, F &&fn)
+static void start_member(std::vector<std::thread> &threads, Member *m, F fn)
 {
+    auto guarded = [m, fn] {
+        try {
+            fn();
+        } catch (...) {
+            m->status = srcdsp::abi_exception();
+            try {
+                m->error = srcdsp_last_error();
+            } catch (...) {
+            }
+        }
+    };
     try {
-        threads.emplace_back(fn);
+        threads.emplace_back(guarded);
     } catch (...) {
-        fn();
+        guarded();
     }
 }
 
@@ -213,7 +225,7 @@ try {
         for (int i = 0; i < G; ++i) {
             Member *m = &h->members[i];
             m->status = SRCDSP_OK;
-            start_member(threads, [=] {
+            start_member(threads, m, [=] {
                 GROUP_TRY_MEMBER(*m, srcdsp_ddc_step(m->chain, in + 2 * (size_t)m->ch0 * in_stride, in_stride, n_in,
                                                      out + 2 * (size_t)m->ch0 * out_stride, out_stride));
             });
@@ -242,7 +254,7 @@ try {
         m->status = SRCDSP_OK;
         const size_t o0 = n_out * i / used, o1 = n_out * (i + 1) / used;
         const size_t start = o0 * Mt, len = (o1 - o0) * Mt;
-        start_member(threads, [=, &phi0, &freq, &nominal] {
+        start_member(threads, m, [=, &phi0, &freq, &nominal] {
             if (i > 0) {
                 for (int c = 0; c < C; ++c) {
                     if (m->mixer) {
