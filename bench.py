@@ -106,9 +106,9 @@ def peaks():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region: an NVML polling thread (one sample every
-    ~3 ms; the timed region of the default run is ~60 ms, too short for an `nvidia-smi -lms` child to report
-    anything but the idle GPU afterwards), `nvidia-smi` only as a fallback when NVML cannot be loaded."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polling threads (clock + reasons about
+    every 2 ms, board power on its own thread; the timed region of the default run is ~30-60 ms, too short for an
+    `nvidia-smi -lms` child to report anything but the idle GPU afterwards), `nvidia-smi` only as a fallback when NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
@@ -117,6 +117,7 @@ class ClockSampler:
     def __init__(self, index: int):
         self.index, self.proc, self.lines = index, None, []
         self.nvml, self.handle, self.samples, self.stop_flag, self.t = None, None, [], False, None
+        self.power, self.tp = [], None
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -144,24 +145,33 @@ class ClockSampler:
             self.nvml = None
 
     def _poll(self):
+        # clock + throttle reasons: two cheap queries per sample
         n = self.nvml
         while not self.stop_flag:
             try:
-                try:
-                    pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
-                except Exception:
-                    pw = None
-                self.samples.append((float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)),
-                                     int(self._reasons(self.handle)), pw))
+                self.samples.append((float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)), int(self._reasons(self.handle))))
             except Exception:
                 pass
-            time.sleep(0.003)
+            time.sleep(0.002)
+
+    def _poll_power(self):
+        # board power on its own thread: the query can take 10-20 ms, which left the headline's 30 ms region with a
+        # single clock sample when it shared the loop above
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                self.power.append(n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
         if self.nvml is not None:
-            self.samples, self.stop_flag = [], False
+            self.samples, self.power, self.stop_flag = [], [], False
             self.t = threading.Thread(target=self._poll, daemon=True)
+            self.tp = threading.Thread(target=self._poll_power, daemon=True)
             self.t.start()
+            self.tp.start()
             return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -174,14 +184,15 @@ class ClockSampler:
     def stop(self):
         if self.nvml is not None:
             self.stop_flag = True
-            if self.t:
-                self.t.join(timeout=2)
+            for th in (self.t, self.tp):
+                if th:
+                    th.join(timeout=2)
             sm = [s[0] for s in self.samples]
             mask = 0
             for s in self.samples:
                 mask |= s[1]
             reasons = sorted(nm for bit, nm in self.REASONS.items() if mask & bit)
-            pw = [s[2] for s in self.samples if s[2] is not None]
+            pw = list(self.power)
             return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": float(min(sm)) if sm else None,
                     "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm),
                     "power_w": float(np.median(pw)) if pw else None, "power_w_max": float(max(pw)) if pw else None,

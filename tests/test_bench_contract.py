@@ -47,3 +47,33 @@ def test_cfg1_cpu_baseline_variants():
     for k in v.values():
         assert k["cores"] == 1 and k["kind"] == "reference" and k["value"] > 0 and "cfg1 exactly" in k["sample"]
     assert v["O2"]["value"] > v["makefile_build"]["value"]  # the optimised build is the faster one
+
+
+def test_clock_sampler_samples_densely_even_when_the_power_query_is_slow(monkeypatch):
+    """bench.ClockSampler against a stand-in NVML whose power query takes 20 ms (as on the B200 boxes): the clock /
+    throttle-reason samples of a 60 ms region must not be held back by it."""
+    import time
+    import types
+    fake = types.ModuleType("pynvml")
+    fake.NVML_CLOCK_SM = 1
+    fake.nvmlInit = lambda: None
+    fake.nvmlDeviceGetHandleByUUID = lambda u: "h"
+    fake.nvmlDeviceGetHandleByIndex = lambda i: "h"
+    fake.nvmlDeviceGetMaxClockInfo = lambda h, k: 1965
+    fake.nvmlDeviceGetClockInfo = lambda h, k: 1900
+    fake.nvmlDeviceGetCurrentClocksEventReasons = lambda h: 0x4
+
+    def power(h):
+        time.sleep(0.02)
+        return 500000
+    fake.nvmlDeviceGetPowerUsage = power
+    monkeypatch.setitem(sys.modules, "pynvml", fake)
+    sys.path.insert(0, ROOT)
+    import bench
+    s = bench.ClockSampler(0)
+    assert s.nvml is fake
+    s.start()
+    time.sleep(0.06)
+    c = s.stop()
+    assert c["samples"] >= 10 and c["sm_mhz"] == 1900.0 and c["sm_max_mhz"] == 1965.0
+    assert c["reasons"] == ["sw_power_cap"] and c["power_w"] == 500.0 and c["source"].startswith("nvml")
