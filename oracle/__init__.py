@@ -325,6 +325,8 @@ class _RefLib:
         L.ref_fifo_count.argtypes = [vp]
         L.ref_fifo_reset.argtypes = [vp]
         L.ref_fifo_abs_time.argtypes = [vp, C.c_uint64, C.c_double, C.POINTER(C.c_uint), C.POINTER(C.c_double)]
+        L.ref_fifo_set_time.argtypes = [vp, C.c_uint64, C.c_uint64]
+        L.ref_fifo_state.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
         L.ref_save_binary.argtypes = [C.c_char_p, _i16p, C.c_size_t]
         L.ref_read_binary.restype = C.c_size_t
         L.ref_read_binary.argtypes = [C.c_char_p, _i16p, C.c_size_t, C.c_size_t]
@@ -582,6 +584,16 @@ class RefFifo:
         self._l.ref_fifo_abs_time(self._h, tp, frac, C.byref(s), C.byref(f))
         return s.value, f.value
 
+    def _set_time(self, time_start, time_end):
+        """Places the reference object's PRIVATE time counters (ref_harness.cpp reaches them through an explicit
+        template instantiation, the reference source is untouched): the only way to drive buffers.h:179-207."""
+        self._l.ref_fifo_set_time(self._h, time_start, time_end)
+
+    def state(self):
+        wp, a, b, r = C.c_size_t(), C.c_uint64(), C.c_uint64(), C.c_int()
+        self._l.ref_fifo_state(self._h, C.byref(wp), C.byref(a), C.byref(b), C.byref(r))
+        return wp.value, a.value, b.value, bool(r.value)
+
 
 class PyFifo:
     """Plain-Python restatement of FifoWithTimeTrack's bookkeeping (buffers.h:139-217, 262-276, 284-352,
@@ -609,8 +621,8 @@ class PyFifo:
         else:
             self.timeEnd = n - diff
             self.rollover = True
-        if not self.rollover:
-            self.timeStart = self.timeEnd - N + 1 if (self.timeEnd - self.timeStart + 1) > N else 1
+        if not self.rollover:  # uint64 arithmetic, as the reference: after a wrap timeEnd < timeStart and the differences wrap too
+            self.timeStart = (self.timeEnd - N + 1) & self.U64 if ((self.timeEnd - self.timeStart + 1) & self.U64) > N else 1
         else:
             d2 = self.U64 - self.timeStart
             self.timeStart = self.timeStart + n if d2 >= n else n - d2
@@ -621,7 +633,7 @@ class PyFifo:
             start = self.timeStart
         if ((start + n - 1) & self.U64) > self.timeEnd:
             return True, start, None
-        sp = (self.writePtr + self.N - (self.timeEnd - start) - 1) % self.N
+        sp = ((self.writePtr + self.N - (self.timeEnd - start) - 1) & self.U64) % self.N
         return False, start, self.storage[(sp + np.arange(n)) % self.N].copy()
 
     def count(self):  # buffers.h:361-377
@@ -632,6 +644,12 @@ class PyFifo:
     def reset(self):  # buffers.h:262-276
         self.writePtr = self.timeStart = self.timeEnd = 0
         self.rollover = False
+
+    def _set_time(self, time_start, time_end):  # test hook, see RefFifo._set_time
+        self.timeStart, self.timeEnd = time_start, time_end
+
+    def state(self):
+        return self.writePtr, self.timeStart, self.timeEnd, self.rollover
 
     def getAbsoluteTime(self, tp, frac=0.0):  # buffers.h:396-459
         import math

@@ -421,6 +421,40 @@ double ref_bench_bank(int kind, int C, size_t n_per_ch, size_t block_len, int n_
 // ---------------------------------------------------------------------------------------------
 // FifoWithTimeTrack<cs16, N> for the capacities the tests use (N is a template parameter)
 extern "C++" {
+// The reference keeps its time counters private and has no way to start them near 2^64, so its rollover branches
+// (buffers.h:179-207) could not be exercised through the public API.  The reference source stays untouched: an explicit
+// template instantiation may name private members ([temp.explicit]), and the friend function it defines hands the
+// member pointer to this file.
+template <class Tag, typename Tag::type Member>
+struct FifoMemberOf {
+    friend typename Tag::type fifo_member(Tag) { return Member; }
+};
+template <size_t N>
+struct FifoPeek;
+#define REF_FIFO_MEMBER(N, member, mtype)                                         \
+    struct FifoTag_##member##_##N {                                               \
+        typedef mtype dsptl::FifoWithTimeTrack<cs16, N>::*type;                   \
+        friend type fifo_member(FifoTag_##member##_##N);                          \
+    };                                                                            \
+    template struct FifoMemberOf<FifoTag_##member##_##N, &dsptl::FifoWithTimeTrack<cs16, N>::member>;
+#define REF_FIFO_PEEK(N)                                                                          \
+    REF_FIFO_MEMBER(N, writePtr, size_t)                                                          \
+    REF_FIFO_MEMBER(N, timeStart, uint64_t)                                                       \
+    REF_FIFO_MEMBER(N, timeEnd, uint64_t)                                                         \
+    REF_FIFO_MEMBER(N, rolloverFlag, bool)                                                        \
+    template <>                                                                                   \
+    struct FifoPeek<N> {                                                                          \
+        typedef dsptl::FifoWithTimeTrack<cs16, N> F;                                              \
+        static size_t &write_ptr(F &f) { return f.*fifo_member(FifoTag_writePtr_##N()); }         \
+        static uint64_t &time_start(F &f) { return f.*fifo_member(FifoTag_timeStart_##N()); }     \
+        static uint64_t &time_end(F &f) { return f.*fifo_member(FifoTag_timeEnd_##N()); }         \
+        static bool &rollover(F &f) { return f.*fifo_member(FifoTag_rolloverFlag_##N()); }        \
+    };
+REF_FIFO_PEEK(16)
+REF_FIFO_PEEK(100)
+REF_FIFO_PEEK(1024)
+REF_FIFO_PEEK(65536)
+
 struct FifoBase {
     virtual ~FifoBase() {}
     virtual void write(std::vector<cs16> &in, unsigned s, double f) = 0;
@@ -428,6 +462,8 @@ struct FifoBase {
     virtual size_t count() = 0;
     virtual void reset() = 0;
     virtual std::pair<unsigned, double> abs_time(uint64_t tp, double f) = 0;
+    virtual void set_time(uint64_t start, uint64_t end) = 0;
+    virtual void state(size_t *wp, uint64_t *start, uint64_t *end, int *rollover) = 0;
 };
 template <size_t N>
 struct FifoImpl : FifoBase {
@@ -438,6 +474,18 @@ struct FifoImpl : FifoBase {
     size_t count() override { return f.count(); }
     void reset() override { f.reset(); }
     std::pair<unsigned, double> abs_time(uint64_t tp, double fr) override { return f.getAbsoluteTime(tp, fr); }
+    void set_time(uint64_t start, uint64_t end) override
+    {
+        FifoPeek<N>::time_start(f) = start;
+        FifoPeek<N>::time_end(f) = end;
+    }
+    void state(size_t *wp, uint64_t *start, uint64_t *end, int *rollover) override
+    {
+        *wp = FifoPeek<N>::write_ptr(f);
+        *start = FifoPeek<N>::time_start(f);
+        *end = FifoPeek<N>::time_end(f);
+        *rollover = FifoPeek<N>::rollover(f) ? 1 : 0;
+    }
 };
 }  // extern "C++"
 
@@ -467,6 +515,11 @@ int ref_fifo_read(void *h, int16_t *iq, size_t n, uint64_t *start)
 }
 size_t ref_fifo_count(void *h) { return static_cast<FifoBase *>(h)->count(); }
 void ref_fifo_reset(void *h) { static_cast<FifoBase *>(h)->reset(); }
+void ref_fifo_set_time(void *h, uint64_t start, uint64_t end) { static_cast<FifoBase *>(h)->set_time(start, end); }
+void ref_fifo_state(void *h, size_t *wp, uint64_t *start, uint64_t *end, int *rollover)
+{
+    static_cast<FifoBase *>(h)->state(wp, start, end, rollover);
+}
 void ref_fifo_abs_time(void *h, uint64_t tp, double f, unsigned *s, double *fr)
 {
     auto r = static_cast<FifoBase *>(h)->abs_time(tp, f);
