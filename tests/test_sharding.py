@@ -169,3 +169,35 @@ def test_world_size_2_gloo_time_slices(corc):
     n, M, nt = 4 * 5000, 4, 1023
     whole, _ = corc.dec_step(O.design_lowpass_taps(nt, M), M, corc.synth(0x5EED0005, 0, 0, n, 0))
     assert np.array_equal(got, whole)
+
+
+def test_time_slices_properties_randomised():
+    """For random chains, stream lengths and world sizes: the slices tile the stream, start at multiples of the total
+    decimation, and each one's warm-up either reaches back over the whole delay-line reach or to the stream's start
+    (where the reset filter's zero history IS the sequential run's) -- the two cases in which slicing is exact."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.lists(st.tuples(st.integers(1, 300), st.integers(1, 16)), min_size=1, max_size=3),
+           st.integers(1, 4000), st.integers(1, 9))
+    def check(chain, blocks, world):
+        ntaps, ratios = [c[0] for c in chain], [c[1] for c in chain]
+        total = int(np.prod(ratios))
+        n = blocks * total
+        sl = time_slices(n, world, ntaps, ratios)
+        halo = chain_halo(ntaps, ratios)
+        assert len(sl) == world and sl[0].start == 0 and sl[0].warmup == 0
+        assert sum(s.length for s in sl) == n and sum(s.out_length for s in sl) == n // total
+        pos = 0
+        for s in sl:
+            assert s.start == pos and s.start % total == 0 and s.length % total == 0 and s.warmup % total == 0
+            assert s.out_start * total == s.start and s.out_length * total == s.length
+            assert 0 <= s.warmup <= s.start and (s.warmup >= halo or s.warmup == s.start)
+            assert s.nco_phase(5, 3437, 4096) == (5 + (s.start - s.warmup) * 3437) % 4096
+            pos += s.length
+        sizes = [s.out_length for s in sl]
+        assert max(sizes) - min(sizes) <= 1  # balanced to one output
+
+    check()
+    with pytest.raises(ValueError):
+        time_slices(33, 2, [63], [8])
