@@ -143,3 +143,20 @@ def test_mixer_base_class_is_exported(built_lib):
     if os.path.exists(os.path.join(REF, "mixers.h")):
         subprocess.run(["g++", "-std=gnu++11", "-O1", "-w", "-I" + REF, src, os.path.join(REF, "dsp_complex.cpp"), "-o",
                         os.path.join(BUILD, "user_mixer_base_ref")], check=True, capture_output=True, text=True)
+
+
+@pytest.mark.parametrize("obsolete", [False, True])
+def test_public_signatures_compile_against_both_trees(obsolete):
+    """SURVEY.md 8(b) "signatures to keep" as static_asserts (tests/cpp/signatures.cpp: members, default arguments,
+    return types, constness, what the obsolete header lacks): the same file must compile against the drop-in headers
+    and -- where the reference checkout is present -- against the reference's own."""
+    src = os.path.join(ROOT, "tests", "cpp", "signatures.cpp")
+    trees = [os.path.join(ROOT, "include", "srcdsp")]
+    if os.path.exists(os.path.join(REF, "mixers.h")):
+        trees.append(REF)
+    for inc in trees:
+        cmd = ["g++", "-std=gnu++11", "-fsyntax-only", "-w", "-I" + inc, src]
+        if obsolete:
+            cmd.insert(3, "-DSRCDSP_SIGNATURES_OBSOLETE_HEADER")
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, f"{inc}:\n{r.stderr[-3000:]}"
